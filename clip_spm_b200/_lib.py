@@ -1,0 +1,77 @@
+"""ctypes binding of include/clipspm_b200.h.  The library is required: nothing in this package falls back to
+PyTorch or CPU code when it is missing -- loading fails loudly instead."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libclipspm_b200.so")
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_ll = ctypes.c_longlong
+
+
+class SpmConfig(ctypes.Structure):
+    """Mirror of `spm_config` (include/clipspm_b200.h)."""
+    _fields_ = [
+        ("backbone", c_int),
+        ("seq_len", c_int),
+        ("n_text_classes", c_int),
+        ("mid_dim_text", c_float),
+        ("mid_dim_vision", c_float),
+        ("negative_slope", c_float),
+        ("alpha", c_float),
+        ("single_direct", c_int),
+        ("precision", c_int),
+        ("max_episodes", c_int),
+        ("max_support", c_int),
+        ("max_query", c_int),
+        ("max_way", c_int),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/clipspm_b200.h
+SIGNATURES = {
+    "spm_last_error": (ctypes.c_char_p, []),
+    "spm_abi_version": (c_int, []),
+    "spm_create": (c_int, [ctypes.POINTER(SpmConfig), ctypes.POINTER(c_void_p)]),
+    "spm_destroy": (c_int, [c_void_p]),
+    "spm_load_weights": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p),
+                                 ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_int64)]),
+    "spm_set_text_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
+    "spm_encode_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "spm_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 7),
+    "spm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 7),
+    "spm_eval": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),
+    "spm_eval_host": (c_int, [c_void_p, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),
+    "spm_otam_distance": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                  c_float, c_float, c_void_p]),
+    "spm_gemm": (c_int, [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_int,
+                         c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library (built by __graft_entry__.build()) and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "clip_spm_b200: %s is missing -- run `python __graft_entry__.py` (nvcc, sm_100a) first; "
+            "there is no CPU or PyTorch fallback for this path" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise RuntimeError("clipspm_b200: " + load().spm_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,45 @@
+// Host-side interface of the tcgen05 GEMM used by every dense contraction on the path
+// (frame-encoder linears, patch embedding, head linears, temporal convolutions as GEMMs).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spm {
+
+enum GemmKind { GEMM_BF16 = 0, GEMM_TF32 = 1 };
+enum GemmAct { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_GELU_ERF = 2, ACT_LEAKY = 3, ACT_SIGMOID = 4, ACT_RELU = 5 };
+
+// out[orow(m), n] = act(sum_k A[m,k] * B[n,k] + bias[n]) (+ residual[rrow(m), n])
+struct GemmEpilogue {
+  const float* bias = nullptr;      // [N] fp32 or null
+  const float* residual = nullptr;  // fp32, leading dim ldr, added AFTER the activation
+  int ldr = 0;
+  int res_row_mod = 0;    // 0: rrow = orow ; >0: rrow = (m % res_row_mod) + res_row_off  (positional table)
+  int res_row_off = 0;
+  int out_row_group = 0;  // 0: orow = m ; >0: orow = m + m / out_row_group + 1  (skip one class-token row per frame)
+  void* out = nullptr;    // fp32 or bf16, leading dim ldo (elements)
+  int ldo = 0;
+  int out_bf16 = 0;
+  int act = ACT_NONE;
+  float slope = 0.f;      // LeakyReLU negative slope
+};
+
+struct GemmOp {
+  CUtensorMap ta, tb;
+  GemmEpilogue ep;
+  int M = 0, N = 0, K = 0;
+  int bn = 256;
+  int kind = GEMM_BF16;
+  int grid = 0;
+};
+
+// A: [M, K] (row stride lda elements), B: [N, K] (row stride ldb) -- both K-contiguous ("K-major"),
+// bf16 (GEMM_BF16) or fp32 (GEMM_TF32).  Returns 0 on success, else sets an error string.
+int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+              const GemmEpilogue& ep, int num_sms, const char** err);
+int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err);
+// one-time: opt into large dynamic shared memory for every instantiation
+int gemm_init(const char** err);
+
+}  // namespace spm

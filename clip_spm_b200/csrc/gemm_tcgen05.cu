@@ -1,0 +1,324 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   out[orow(m), n] = act( sum_k A[m,k] * B[n,k] + bias[n] ) (+ residual[rrow(m), n])
+//
+// A [M,K] and B [N,K] are K-contiguous (a torch.nn.Linear weight [out,in] is already "B").
+// Roles inside one 256-thread CTA (one CTA per SM, grid = min(#tiles, #SMs), static round-robin tiles):
+//   warp 0 (1 lane)  TMA producer: 128B-swizzled [128 x 128B] A box + [BN x 128B] B box per stage
+//   warp 1 (1 lane)  MMA issuer  : 4 x tcgen05.mma (128 x BN x 32 bytes of K) per stage, fp32 accum in TMEM
+//   warp 2           TMEM allocator (2 accumulator buffers of BN columns -> epilogue overlaps the next tile)
+//   warps 4..7       epilogue    : tcgen05.ld (one accumulator row per thread) -> bias/act/residual -> global
+//
+// This replaces the cuBLASLt / cuDNN calls the reference makes through ATen for
+// models/clip_fsar.py:626-632,673,687 (ViT linears, patch-embed conv, projection) and
+// models/myRes.py:944-996 + models/model_clipspm.py:76-99,171-174 (head linears, gates, temporal convs).
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace spm {
+
+struct GemmArgs {
+  GemmEpilogue ep;
+  int M, N, K;
+};
+
+template <int BN, int KIND>
+struct GemmTile {
+  static constexpr int BM = 128;
+  static constexpr int ELEM = (KIND == GEMM_BF16) ? 2 : 4;
+  static constexpr int BK = 128 / ELEM;  // elements per 128-byte swizzled row
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+};
+
+__device__ __forceinline__ float apply_act(float x, int act, float slope) {
+  switch (act) {
+    case ACT_QUICKGELU: return x / (1.f + __expf(-1.702f * x));
+    case ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    case ACT_LEAKY: return x > 0.f ? x : slope * x;
+    case ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    case ACT_RELU: return fmaxf(x, 0.f);
+    default: return x;
+  }
+}
+
+template <int BN, int KIND>
+__global__ void __launch_bounds__(256, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmArgs args) {
+  using T = GemmTile<BN, KIND>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T::STAGES * T::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + T::STAGES;
+  uint64_t* tfull_bar = empty_bar + T::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int M = args.M, N = args.N, K = args.K;
+  const int num_m = (M + T::BM - 1) / T::BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + T::BK - 1) / T::BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < T::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, T::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * T::BM;
+        const int n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * T::STAGE_BYTES;
+          uint8_t* sb = sa + T::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], T::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * T::BK, m0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * T::BK, n0);
+          if (++stage == T::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = umma_idesc(KIND == GEMM_BF16 ? 1 : 2, T::BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_phase = (t >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * T::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + T::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // +32 bytes along K inside the 128B swizzle atom == +2 in the (addr >> 4) field
+            if (KIND == GEMM_BF16)
+              mma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+            else
+              mma_tf32_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == T::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const GemmEpilogue& ep = args.ep;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int acc = t & 1;
+      const uint32_t acc_phase = (t >> 1) & 1;
+      const int m = (tile / num_n) * T::BM + q * 32 + lane;
+      const int n0 = (tile % num_n) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const bool row_ok = m < M;
+      long long orow = m;
+      if (ep.out_row_group > 0) orow = (long long)m + m / ep.out_row_group + 1;
+      long long rrow = orow;
+      if (ep.res_row_mod > 0) rrow = (m % ep.res_row_mod) + ep.res_row_off;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(bp + j);
+              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (ep.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act, ep.slope);
+          }
+          if (ep.residual != nullptr) {
+            const float4* rp = reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = rp[j];
+              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (ep.out_bf16) {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow * ep.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&p0);
+              u.y = *reinterpret_cast<uint32_t*>(&p1);
+              u.z = *reinterpret_cast<uint32_t*>(&p2);
+              u.w = *reinterpret_cast<uint32_t*>(&p3);
+              op[j] = u;
+            }
+          } else {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow * ep.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+      }
+      // accumulator buffer drained -> hand it back to the MMA warp
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, T::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  return fn;
+}
+
+// 2-D K-contiguous operand [rows, K] with row stride ld (elements): box = [box_rows x 128 bytes], SWIZZLE_128B.
+static int make_operand_map(CUtensorMap* map, int kind, const void* ptr, long long ld, int rows, int K, int box_rows,
+                            const char** err) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) { *err = "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)"; return 1; }
+  const int elem = kind == GEMM_BF16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem) & 15)) {
+    *err = "GEMM operand must be 16-byte aligned with a 16-byte-multiple row stride";
+    return 1;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)(ld * elem)};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, kind == GEMM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed"; return 1; }
+  return 0;
+}
+
+int gemm_init(const char** err) {
+#define SPM_SET_SMEM(BN, KIND)                                                                               \
+  if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                           GemmTile<BN, KIND>::SMEM_BYTES) != cudaSuccess) {                                 \
+    *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the GEMM kernel";                    \
+    return 1;                                                                                                \
+  }
+  SPM_SET_SMEM(256, GEMM_BF16)
+  SPM_SET_SMEM(128, GEMM_BF16)
+  SPM_SET_SMEM(256, GEMM_TF32)
+  SPM_SET_SMEM(128, GEMM_TF32)
+#undef SPM_SET_SMEM
+  return 0;
+}
+
+int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+              const GemmEpilogue& ep, int num_sms, const char** err) {
+  if (M <= 0 || N <= 0 || K <= 0) { *err = "GEMM: empty problem"; return 1; }
+  if (N % 32 != 0) { *err = "GEMM: N must be a multiple of 32"; return 1; }
+  if (ep.out == nullptr) { *err = "GEMM: null output"; return 1; }
+  op->M = M; op->N = N; op->K = K; op->kind = kind; op->ep = ep;
+  // Tile width: 256 for the big encoder GEMMs; 128 when that yields more CTAs than SMs can use otherwise
+  const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
+  op->bn = (N % 256 == 0 && tiles256 >= num_sms) ? 256 : 128;
+  const long long tiles = (long long)((M + 127) / 128) * ((N + op->bn - 1) / op->bn);
+  op->grid = (int)(tiles < num_sms ? tiles : num_sms);
+  if (make_operand_map(&op->ta, kind, A, lda, M, K, 128, err)) return 1;
+  if (make_operand_map(&op->tb, kind, B, ldb, N, K, op->bn, err)) return 1;
+  return 0;
+}
+
+int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
+  GemmArgs a;
+  a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K;
+#define SPM_LAUNCH(BN, KIND)                                                                                 \
+  gemm_tcgen05_kernel<BN, KIND><<<op->grid, 256, GemmTile<BN, KIND>::SMEM_BYTES, stream>>>(op->ta, op->tb, a)
+  if (op->kind == GEMM_BF16) {
+    if (op->bn == 256) SPM_LAUNCH(256, GEMM_BF16); else SPM_LAUNCH(128, GEMM_BF16);
+  } else {
+    if (op->bn == 256) SPM_LAUNCH(256, GEMM_TF32); else SPM_LAUNCH(128, GEMM_TF32);
+  }
+#undef SPM_LAUNCH
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+}  // namespace spm

@@ -1,0 +1,46 @@
+"""Per-stage entry points of the C-ABI library on torch CUDA tensors (torch is used for device memory and
+streams only).  These are what the `-m gpu` parity tests call."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+ACT = {"none": 0, "quickgelu": 1, "gelu": 2, "leaky_relu": 3, "sigmoid": 4, "relu": 5}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("clip_spm_b200 ops take CUDA tensors (no CPU fallback exists)")
+
+
+def gemm(a, b, bias=None, act="none", slope=0.0, residual=None, res_row_mod=0, res_row_off=0, out_row_group=0,
+         out=None, out_dtype=torch.float32):
+    """out[orow(m), :] = act(a @ b.T + bias) (+ residual[rrow(m), :]).  a [M,K], b [N,K]: both bf16 (tensor-core
+    bf16 path) or both fp32 (tf32 path), last dim contiguous."""
+    lib = _lib.load()
+    _need_cuda(a, b, bias, residual, out)
+    assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float32)
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[0]
+    if out is None:
+        rows = M if out_row_group == 0 else M + M // out_row_group + 1
+        out = torch.empty(rows, N, device=a.device, dtype=out_dtype)
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(1) == 1
+    kind = 0 if a.dtype == torch.bfloat16 else 1
+    _lib.check(lib.spm_gemm(_stream(), kind, _ptr(a), a.stride(0), _ptr(b), b.stride(0), M, N, K, _ptr(bias),
+                            ACT[act], float(slope), _ptr(residual),
+                            0 if residual is None else residual.stride(0), res_row_mod, res_row_off, out_row_group,
+                            _ptr(out), out.stride(0), 1 if out.dtype == torch.bfloat16 else 0))
+    return out

@@ -1,0 +1,117 @@
+/*
+ * clipspm_b200 -- C ABI of the B200-native CLIP-SPM episode-evaluation hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes (no torch types), returns an int
+ * status (0 = ok) and records a message readable with spm_last_error().  All tensor arguments are
+ * DEVICE pointers unless the name says `host`; the caller owns every buffer; the library owns only
+ * the opaque handle (packed weights + workspace).  `stream` is a cudaStream_t passed as void*.
+ * A handle is not thread-safe: one handle per (process, device).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo root):
+ *   spm_create / spm_destroy      models/model_clipspm.py:15-101   CNN.__init__ (module construction)
+ *   spm_load_weights              torch.nn.Module.load_state_dict of that CNN (keys listed in SURVEY.md 8b)
+ *   spm_set_text_features         models/model_clipspm.py:60,70    text_features_{train,test} attributes
+ *   spm_forward                   models/model_clipspm.py:111-144  CNN.forward(inputs) -> logits, dists
+ *   spm_eval                      run/main_run.py:390-392 + utils/utils.py:174-186,259-264 (loss, accuracy)
+ *   spm_eval_host                 run/main_run.py:266-279 (prepare_task H2D + forward + loss/acc + .item())
+ *   spm_encode_frames             models/clip_fsar.py:672-689 VisionTransformer.forward / :593-608 ModifiedResNet
+ *   spm_head                      models/model_clipspm.py:125-143  (everything after get_feats)
+ *   spm_otam_distance             models/model_clipspm.py:348-362 + models/myRes.py:756-765,821-855
+ *   spm_gemm                      ATen linear / conv-as-GEMM calls (cuBLASLt) under all of the above
+ */
+#ifndef CLIPSPM_B200_H
+#define CLIPSPM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPM_ABI_VERSION 1
+
+typedef struct spm_handle spm_handle;
+
+enum { SPM_BACKBONE_VIT_B16 = 0, SPM_BACKBONE_RN50 = 1 };
+/* arithmetic of the dense contractions: bf16 tensor cores (the reference's autocast(bfloat16) mode) or the
+ * fp32-equivalent mode (split-precision tensor-core products, fp32 accumulate) */
+enum { SPM_PRECISION_BF16 = 0, SPM_PRECISION_FP32 = 1 };
+
+typedef struct spm_config {
+  int backbone;         /* cfg.MODEL.BACKBONE: SPM_BACKBONE_*                         model_clipspm.py:18,24 */
+  int seq_len;          /* cfg.DATA.SEQ_LEN (T frames per video)                      model_clipspm.py:154   */
+  int n_text_classes;   /* rows of the text-feature table                             model_clipspm.py:60,70 */
+  float mid_dim_text;   /* cfg.params['mid_dim_text']   (gate_text hidden = D * this) model_clipspm.py:89    */
+  float mid_dim_vision; /* cfg.params['mid_dim_vision']                               model_clipspm.py:95    */
+  float negative_slope; /* cfg.params['negative_slope'] (LeakyReLU)                   model_clipspm.py:90,96 */
+  float alpha;          /* cfg.params['alpha']                                        model_clipspm.py:304   */
+  int single_direct;    /* cfg.MODEL.SINGLE_DIRECT (0 = bidirectional OTAM)           model_clipspm.py:358   */
+  int precision;        /* SPM_PRECISION_*                                                                   */
+  int max_episodes;     /* episodes per spm_forward call the workspace is sized for                          */
+  int max_support;      /* S = way*shot support videos per episode (upper bound)                             */
+  int max_query;        /* Q query videos per episode (upper bound)                                          */
+  int max_way;          /* W distinct support labels per episode (upper bound)                               */
+} spm_config;
+
+const char* spm_last_error(void);
+int spm_abi_version(void);
+
+int spm_create(const spm_config* cfg, spm_handle** out);
+int spm_destroy(spm_handle* h);
+
+/* Weights: `n` fp32 contiguous device tensors keyed by the reference state_dict names
+ * (e.g. "backbone.transformer.resblocks.0.attn.in_proj_weight", "context2.layers.0.0.fn.to_q.weight").
+ * The library repacks them (bf16 copies, fused QKV, conv->GEMM layouts, folded BatchNorm) into its own storage;
+ * the caller's tensors are not referenced after the call returns (the call synchronises `stream`). */
+int spm_load_weights(spm_handle* h, void* stream, int n, const char* const* names, const void* const* dev_ptrs,
+                     const int64_t* numel);
+/* text feature table [n_cls, D] fp32 (the reference's text_features_test / _train) */
+int spm_set_text_features(spm_handle* h, void* stream, const float* table, int n_cls, int dim);
+
+/* Frame encoder: images [F,3,224,224] fp32 NCHW in [0,1] -> features [F, D] fp32 */
+int spm_encode_frames(spm_handle* h, void* stream, const float* images, int n_frames, float* feats_out);
+
+/* Metric head on precomputed frame features, n_episodes episodes at once.
+ *   su [E,S,T,D], qu [E,Q,T,D] fp32; support_labels [E,S], real_support [E,S], real_target [E,Q] fp32
+ *   (labels arrive as float tensors: video_reader.py:322-326).
+ *   logits_out [E,Q,W] (column w <-> w-th smallest distinct support label), dists_out [E]. */
+int spm_head(spm_handle* h, void* stream, int n_episodes, int S, int Q, const float* su, const float* qu,
+             const float* support_labels, const float* real_support, const float* real_target, float* logits_out,
+             float* dists_out);
+
+/* CNN.forward for n_episodes episodes: support_images [E,S*T,3,224,224], target_images [E,Q*T,3,224,224] */
+int spm_forward(spm_handle* h, void* stream, int n_episodes, int S, int Q, const float* support_images,
+                const float* target_images, const float* support_labels, const float* real_support,
+                const float* real_target, float* logits_out, float* dists_out);
+
+/* forward + loss/accuracy of run/main_run.py:390-392: per episode
+ *   loss_out[e] = sum_q CE(logits[e,q,:], target_labels[e,q]) / tasks_per_batch + 0.001 * dists[e]
+ *   acc_out[e]  = mean_q [argmax_w logits[e,q,w] == target_labels[e,q]];  pred_out [E,Q] int32 (may be null) */
+int spm_eval(spm_handle* h, void* stream, int n_episodes, int S, int Q, const float* support_images,
+             const float* target_images, const float* support_labels, const float* real_support,
+             const float* real_target, const int64_t* target_labels, float tasks_per_batch, float* logits_out,
+             float* dists_out, float* loss_out, float* acc_out, int32_t* pred_out);
+
+/* Same with HOST buffers (pinned or pageable): stages the host->device copies of every episode on a copy
+ * stream overlapped with compute, runs spm_eval, and copies logits/dists/loss/acc/pred back to host.
+ * Blocks until the results are in the host buffers. */
+int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, const float* support_images_host,
+                  const float* target_images_host, const float* support_labels_host, const float* real_support_host,
+                  const float* real_target_host, const int64_t* target_labels_host, float tasks_per_batch,
+                  float* logits_host, float* dists_host, float* loss_host, float* acc_host, int32_t* pred_host);
+
+/* cos_sim + (bi)directional OTAM soft-DTW of n_pairs independent problems:
+ *   support [P,W,T,D], target [P,Q,T,D] fp32 -> out [P,Q,W] (accumulated: out = beta*out + alpha*otam) */
+int spm_otam_distance(void* stream, int n_pairs, int W, int Q, int T, int D, const float* support,
+                      const float* target, int single_direct, float alpha, float beta, float* out);
+
+/* out[orow(m), n] = act(sum_k A[m,k] B[n,k] + bias[n]) (+ residual[rrow(m), n]); see csrc/gemm.cuh.
+ * kind: 0 = bf16 operands, 1 = tf32 (fp32 operands).  act: 0 none, 1 QuickGELU, 2 GELU(erf), 3 LeakyReLU, 4 sigmoid, 5 ReLU */
+int spm_gemm(void* stream, int kind, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+             const float* bias, int act, float slope, const float* residual, int ldr, int res_row_mod,
+             int res_row_off, int out_row_group, void* out, int ldo, int out_bf16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPSPM_B200_H */

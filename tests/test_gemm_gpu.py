@@ -1,0 +1,94 @@
+"""tcgen05 GEMM (csrc/gemm_tcgen05.cu) against torch.matmul in fp32 on the same (bf16-rounded) operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_act(x, act, slope):
+    if act == "quickgelu":
+        return x * torch.sigmoid(1.702 * x)
+    if act == "gelu":
+        return torch.nn.functional.gelu(x)
+    if act == "leaky_relu":
+        return torch.nn.functional.leaky_relu(x, slope)
+    if act == "sigmoid":
+        return torch.sigmoid(x)
+    if act == "relu":
+        return torch.relu(x)
+    return x
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 128, 128), (300, 768, 768), (197 * 8, 2304, 768),
+                                   (20000, 2304, 768), (4097, 768, 3072), (45, 512, 1536), (9, 6144, 512)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_plain(M, N, K, dtype):
+    from clip_spm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M * 31 + N * 7 + K)
+    a = torch.randn(M, K, generator=g).cuda().to(dtype)
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().to(dtype)
+    out = ops.gemm(a, b)
+    torch.cuda.synchronize()
+    if dtype == torch.float32:
+        # tf32 keeps 10 mantissa bits of each operand
+        ref = a.double() @ b.double().t()
+        tol = 2e-3
+    else:
+        ref = a.double() @ b.double().t()
+        tol = 1e-4  # operands are exactly bf16; only fp32 accumulation order differs
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < tol, (M, N, K, err)
+
+
+@pytest.mark.parametrize("act", ["none", "quickgelu", "gelu", "leaky_relu", "sigmoid", "relu"])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_epilogue(act, out_dtype):
+    from clip_spm_b200 import ops
+    M, N, K = 1000, 768, 512
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = torch.randn(M, K, generator=g).cuda().bfloat16()
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    out = ops.gemm(a, b, bias=bias, act=act, slope=0.0025, residual=res, out_dtype=out_dtype)
+    ref = _ref_act(a.float() @ b.float().t() + bias, act, 0.0025) + res
+    tol = 2e-2 if out_dtype == torch.bfloat16 else 2e-4
+    err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < tol, (act, out_dtype, err)
+
+
+def test_gemm_inplace_residual_and_row_maps():
+    from clip_spm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(9)
+    # in-place residual stream update: x += a @ b.T + bias
+    M, N, K = 197 * 5, 768, 3072
+    a = torch.randn(M, K, generator=g).cuda().bfloat16()
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    x = torch.randn(M, N, generator=g).cuda()
+    ref = x + a.float() @ b.float().t() + bias
+    ops.gemm(a, b, bias=bias, residual=x, out=x)
+    assert (x - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+    # patch-embedding layout: patch row m of frame f goes to token row f*197 + 1 + m%196, plus pos[1 + m%196]
+    F_, P, W = 3, 196, 768
+    a = torch.randn(F_ * P, W, generator=g).cuda().bfloat16()
+    b = (torch.randn(W, W, generator=g) / W ** 0.5).cuda().bfloat16()
+    pos = torch.randn(P + 1, W, generator=g).cuda()
+    out = torch.zeros(F_ * (P + 1), W, device="cuda")
+    ops.gemm(a, b, residual=pos, res_row_mod=P, res_row_off=1, out_row_group=P, out=out)
+    ref = (a.float() @ b.float().t()).view(F_, P, W) + pos[1:]
+    got = out.view(F_, P + 1, W)
+    assert (got[:, 1:] - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+    assert got[:, 0].abs().max().item() == 0.0
+
+
+def test_gemm_strided_rows():
+    """A operand taken as every 197th row (class-token rows) without a gather."""
+    from clip_spm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn(40 * 197, 768, generator=g).cuda().bfloat16()
+    w = (torch.randn(512, 768, generator=g) / 768 ** 0.5).cuda().bfloat16()
+    a = x.view(40, 197, 768)[:, 0, :]
+    out = ops.gemm(a, w)
+    ref = a.float() @ w.float().t()
+    assert (out - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
