@@ -1,0 +1,497 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  A CPU restatement (plain torch fp32/fp64 tensor ops, no nn.Module of the
+reference, no CUDA) of the algorithm on CLIP-SPM's episode-evaluation hot path.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import this module; the product path (clip_spm_b200/) never
+does and fails loudly when its CUDA library is missing.
+
+Parity status: PINNED.  The reference has no golden vectors or tests of its own, so this
+restatement is pinned against outputs of the reference itself: oracle/pin_against_reference.py imports the
+reference's own modules from /root/reference (CPU), feeds them the same seeded weights and episodes, asserts that
+every stage tensor agrees with this file and writes the stage tensors to tests/golden/*.npz.
+
+Every function cites the reference file:line it restates (paths relative to the reference repo root).
+"""
+import math
+import zlib
+
+import torch
+import torch.nn.functional as F
+
+VIT = dict(width=768, layers=12, heads=12, patch=16, res=224, out_dim=512)
+RN50 = dict(width=64, layers=(3, 4, 6, 3), heads=32, res=224, out_dim=1024)
+
+
+# =====================================================================================================
+# frame encoder: CLIP ViT-B/16 visual tower
+# =====================================================================================================
+def layer_norm(x, w, b, eps=1e-5):
+    """models/clip_fsar.py:610-616 (nn.LayerNorm computed in fp32, eps 1e-5)."""
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def quick_gelu(x):
+    """models/clip_fsar.py:618-620."""
+    return x * torch.sigmoid(1.702 * x)
+
+
+def vit_block(x, w, p, heads):
+    """models/clip_fsar.py:622-643 ResidualAttentionBlock on x [F, L, C] (batch-first restatement of
+    nn.MultiheadAttention(d_model, n_head) self-attention without mask)."""
+    Fn, L, C = x.shape
+    hd = C // heads
+    h = layer_norm(x, w[p + "ln_1.weight"], w[p + "ln_1.bias"])
+    qkv = h @ w[p + "attn.in_proj_weight"].t() + w[p + "attn.in_proj_bias"]
+    q, k, v = qkv.split(C, dim=-1)
+    q = q.view(Fn, L, heads, hd).transpose(1, 2)
+    k = k.view(Fn, L, heads, hd).transpose(1, 2)
+    v = v.view(Fn, L, heads, hd).transpose(1, 2)
+    att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+    o = (att @ v).transpose(1, 2).reshape(Fn, L, C)
+    x = x + o @ w[p + "attn.out_proj.weight"].t() + w[p + "attn.out_proj.bias"]
+    h = layer_norm(x, w[p + "ln_2.weight"], w[p + "ln_2.bias"])
+    h = quick_gelu(h @ w[p + "mlp.c_fc.weight"].t() + w[p + "mlp.c_fc.bias"])
+    x = x + h @ w[p + "mlp.c_proj.weight"].t() + w[p + "mlp.c_proj.bias"]
+    return x
+
+
+def vit_forward(w, images, prefix="backbone.", chunk=32):
+    """models/clip_fsar.py:672-689 VisionTransformer.forward: images [F,3,224,224] -> [F,512]."""
+    outs = []
+    for s in range(0, images.shape[0], chunk):
+        img = images[s:s + chunk].to(w[prefix + "conv1.weight"].dtype)
+        x = F.conv2d(img, w[prefix + "conv1.weight"], stride=VIT["patch"])          # :673
+        x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)                   # :674-675
+        cls = w[prefix + "class_embedding"].expand(x.shape[0], 1, -1)
+        x = torch.cat([cls, x], dim=1) + w[prefix + "positional_embedding"]          # :676-677
+        x = layer_norm(x, w[prefix + "ln_pre.weight"], w[prefix + "ln_pre.bias"])    # :678
+        for i in range(VIT["layers"]):                                               # :680-682
+            x = vit_block(x, w, prefix + "transformer.resblocks.%d." % i, VIT["heads"])
+        x = layer_norm(x[:, 0, :], w[prefix + "ln_post.weight"], w[prefix + "ln_post.bias"])  # :684
+        outs.append(x @ w[prefix + "proj"])                                          # :686-687
+    return torch.cat(outs, 0)
+
+
+# =====================================================================================================
+# frame encoder: CLIP ModifiedResNet-50 visual tower
+# =====================================================================================================
+def _bn(x, w, p, eps=1e-5):
+    """nn.BatchNorm2d in eval mode (running statistics)."""
+    scale = w[p + "weight"] / torch.sqrt(w[p + "running_var"] + eps)
+    shift = w[p + "bias"] - w[p + "running_mean"] * scale
+    return x * scale[None, :, None, None] + shift[None, :, None, None]
+
+
+def rn50_bottleneck(x, w, p, stride):
+    """models/clip_fsar.py:502-547 Bottleneck."""
+    out = torch.relu(_bn(F.conv2d(x, w[p + "conv1.weight"]), w, p + "bn1."))
+    out = torch.relu(_bn(F.conv2d(out, w[p + "conv2.weight"], padding=1), w, p + "bn2."))
+    if stride > 1:
+        out = F.avg_pool2d(out, stride)
+    out = _bn(F.conv2d(out, w[p + "conv3.weight"]), w, p + "bn3.")
+    if (p + "downsample.0.weight") in w:
+        idn = F.avg_pool2d(x, stride) if stride > 1 else x
+        idn = _bn(F.conv2d(idn, w[p + "downsample.0.weight"]), w, p + "downsample.1.")
+    else:
+        idn = x
+    return torch.relu(out + idn)
+
+
+def rn50_attnpool(x, w, p, heads):
+    """models/clip_fsar.py:407-410,481-500 AttentionPool2d: query = mean token only."""
+    Fn, C = x.shape[0], x.shape[1]
+    t = x.flatten(2).permute(0, 2, 1)                              # [F, HW, C]
+    t = torch.cat([t.mean(dim=1, keepdim=True), t], dim=1)         # [F, HW+1, C]
+    t = t + w[p + "positional_embedding"]
+    hd = C // heads
+    q = (t[:, :1] @ w[p + "q_proj.weight"].t() + w[p + "q_proj.bias"]).view(Fn, 1, heads, hd).transpose(1, 2)
+    k = (t @ w[p + "k_proj.weight"].t() + w[p + "k_proj.bias"]).view(Fn, -1, heads, hd).transpose(1, 2)
+    v = (t @ w[p + "v_proj.weight"].t() + w[p + "v_proj.bias"]).view(Fn, -1, heads, hd).transpose(1, 2)
+    att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+    o = (att @ v).transpose(1, 2).reshape(Fn, C)
+    return o @ w[p + "c_proj.weight"].t() + w[p + "c_proj.bias"]
+
+
+def rn50_forward(w, images, prefix="backbone.", chunk=16):
+    """models/clip_fsar.py:593-608 ModifiedResNet.forward: images [F,3,224,224] -> [F,1024]."""
+    outs = []
+    for s in range(0, images.shape[0], chunk):
+        x = images[s:s + chunk]
+        x = torch.relu(_bn(F.conv2d(x, w[prefix + "conv1.weight"], stride=2, padding=1), w, prefix + "bn1."))
+        x = torch.relu(_bn(F.conv2d(x, w[prefix + "conv2.weight"], padding=1), w, prefix + "bn2."))
+        x = torch.relu(_bn(F.conv2d(x, w[prefix + "conv3.weight"], padding=1), w, prefix + "bn3."))
+        x = F.avg_pool2d(x, 2)
+        for li, nb in enumerate(RN50["layers"]):
+            for bi in range(nb):
+                stride = 2 if (li > 0 and bi == 0) else 1
+                x = rn50_bottleneck(x, w, prefix + "layer%d.%d." % (li + 1, bi), stride)
+        outs.append(rn50_attnpool(x, w, prefix + "attnpool.", RN50["heads"]))
+    return torch.cat(outs, 0)
+
+
+# =====================================================================================================
+# metric head
+# =====================================================================================================
+def feed_forward(x, w, p):
+    """models/myRes.py:984-996 FeedForward: Linear -> exact (erf) GELU -> Linear (dropouts are identity in eval)."""
+    h = F.gelu(x @ w[p + "net.0.weight"].t() + w[p + "net.0.bias"])
+    return h @ w[p + "net.3.weight"].t() + w[p + "net.3.bias"]
+
+
+def transformer_v1(x, w, p, heads=8, dim_head=256):
+    """models/myRes.py:1066-1075 Transformer_v1.forward with q=k=v=x, depth 1:
+    PreNormattention_qkv (:1039-1040, the SAME LayerNorm on q,k,v, residual is the un-normalised q),
+    Attention_qkv.forward (:964-982), then x = ff(x) + x."""
+    B, n, _ = x.shape
+    h = layer_norm(x, w[p + "layers.0.0.norm.weight"], w[p + "layers.0.0.norm.bias"])
+    q = (h @ w[p + "layers.0.0.fn.to_q.weight"].t()).view(B, n, heads, dim_head).transpose(1, 2)
+    k = (h @ w[p + "layers.0.0.fn.to_k.weight"].t()).view(B, n, heads, dim_head).transpose(1, 2)
+    v = (h @ w[p + "layers.0.0.fn.to_v.weight"].t()).view(B, n, heads, dim_head).transpose(1, 2)
+    att = torch.softmax((q @ k.transpose(-1, -2)) * dim_head ** -0.5, dim=-1)
+    o = (att @ v).transpose(1, 2).reshape(B, n, heads * dim_head)
+    y = o @ w[p + "layers.0.0.fn.to_out.0.weight"].t() + w[p + "layers.0.0.fn.to_out.0.bias"] + x
+    return feed_forward(y, w, p + "layers.0.1.") + y
+
+
+def motion_feats(x, w):
+    """models/model_clipspm.py:169-191 get_motion_feats for one tensor x [N,T,D] -> [N,D]."""
+    xt = x.permute(0, 2, 1)
+    c = F.conv1d(xt, w["motion_conv1.weight"], w["motion_conv1.bias"], padding=1)
+    c = F.conv1d(c, w["motion_conv2.weight"], w["motion_conv2.bias"], padding=1)
+    f = c[:, :, 1:] - xt[:, :, :-1]
+    b = c[:, :, :-1] - xt[:, :, 1:]
+    return (0.5 * (f + b)).mean(-1)
+
+
+def gate(x, w, p, slope):
+    """models/model_clipspm.py:88-99 gate_text / gate_vision: Linear -> LeakyReLU -> Linear -> Sigmoid."""
+    h = F.leaky_relu(x @ w[p + "0.weight"].t() + w[p + "0.bias"], slope)
+    return torch.sigmoid(h @ w[p + "2.weight"].t() + w[p + "2.bias"])
+
+
+def se_te(x, tok, w, params):
+    """models/model_clipspm.py:296-314: x [N,T,D], tok [N,1,D] -> (frames [N,T,D], token [N,1,D])."""
+    gt = gate(tok, w, "gate_text.", params["negative_slope"])
+    gv = gate(x, w, "gate_vision.", params["negative_slope"])
+    q = tok * gt * params["alpha"] + x * gv
+    z = transformer_v1(torch.cat([tok, q], dim=1), w, "context2.")
+    return z[:, 1:, :], z[:, 0:1, :]
+
+
+def token_trans(token, x, w):
+    """models/model_clipspm.py:371-378: token [1,D], x [N,T,D] -> [N,1,D]."""
+    t = token.expand(x.size(0), -1, -1)
+    return feed_forward(t * x.mean(dim=[1, 2], keepdim=True), w, "token_tr.mlp.")
+
+
+def dis(x, y):
+    """models/model_clipspm.py:341-346 _dis."""
+    d = x - y
+    dims = [-2, -1] if d.dim() == 3 else [-1]
+    return (d ** 2).sum(dim=dims).mean()
+
+
+def class_means(x, labels):
+    """models/model_clipspm.py:133-137,231-239 + models/myRes.py:730-739: per sorted-unique label mean."""
+    return torch.stack([x[labels == c].mean(dim=0) for c in torch.unique(labels)])
+
+
+def cos_sim(x, y, epsilon=0.01):
+    """models/myRes.py:756-765."""
+    num = x @ y.transpose(-1, -2)
+    den = x.norm(dim=-1).unsqueeze(-1) @ y.norm(dim=-1).unsqueeze(-1).transpose(-1, -2) + epsilon
+    return num / den
+
+
+def otam_cum_dist_v2(d, lbda=0.5):
+    """models/myRes.py:821-855 OTAM_cum_dist_v2 on d [..., L, M] (cum_dists is always fp32 there, :829)."""
+    d = F.pad(d, (1, 1), "constant", 0.0)
+    L, M2 = d.shape[-2], d.shape[-1]
+    c = torch.zeros(d.shape, dtype=torch.float32 if d.dtype != torch.float64 else torch.float64)
+    for m in range(1, M2):
+        c[..., 0, m] = d[..., 0, m] + c[..., 0, m - 1]
+    for l in range(1, L):
+        c[..., l, 1] = d[..., l, 1] - lbda * torch.log(
+            torch.exp(-c[..., l - 1, 0] / lbda) + torch.exp(-c[..., l - 1, 1] / lbda) + torch.exp(-c[..., l, 0] / lbda))
+        for m in range(2, M2 - 1):
+            c[..., l, m] = d[..., l, m] - lbda * torch.log(
+                torch.exp(-c[..., l - 1, m - 1] / lbda) + torch.exp(-c[..., l, m - 1] / lbda))
+        c[..., l, -1] = d[..., l, -1] - lbda * torch.log(
+            torch.exp(-c[..., l - 1, -2] / lbda) + torch.exp(-c[..., l - 1, -1] / lbda)
+            + torch.exp(-c[..., l, -2] / lbda))
+    return c[..., -1, -1]
+
+
+def otam_distance(support, target, single_direct=False):
+    """models/model_clipspm.py:348-362: support [W,T,D], target [Q,T,D] -> [Q,W]."""
+    W, T, D = support.shape
+    Q = target.shape[0]
+    sim = cos_sim(target.reshape(Q * T, D), support.reshape(W * T, D))
+    d = (1 - sim).view(Q, T, W, T).permute(0, 2, 1, 3)  # tb sb ts ss
+    out = otam_cum_dist_v2(d)
+    if not single_direct:
+        out = out + otam_cum_dist_v2(d.transpose(-1, -2))
+    return out
+
+
+def head_forward(w, text_features, su, qu, support_labels, real_support, real_target, params, single_direct=False):
+    """models/model_clipspm.py:116-143 after get_feats (eval branch).  Returns every stage tensor."""
+    st = {}
+    ctx_s = text_features[real_support.long()].unsqueeze(1)   # :120
+    ctx_q = text_features[real_target.long()].unsqueeze(1)    # :121
+    # ---- mo (:193-206)
+    su_mo, qu_mo = motion_feats(su, w), motion_feats(qu, w)
+    qu_m, qu_mo2 = se_te(qu, qu_mo.unsqueeze(1), w, params)
+    su_m, su_mo2 = se_te(su, su_mo.unsqueeze(1), w, params)
+    new_sm, new_qm = motion_feats(su_m, w), motion_feats(qu_m, w)
+    mo_dist = dis(new_qm, qu_mo2.squeeze(1)) + dis(new_sm, su_mo2.squeeze(1))
+    st.update(su_mo=su_mo, qu_mo=qu_mo, mo_dist_pre=mo_dist)
+    # ---- sem / cpt_sem (:208-273); the two se_te calls whose outputs only feed discarded distances are skipped
+    token = torch.cat([ctx_q, ctx_s], dim=0).mean(dim=0)       # :213-214  [1,D]
+    target_token = token_trans(token, qu, w)                   # :216
+    qu_fake, token_q_fake = se_te(qu, target_token, w, params)     # :226
+    su_real, token_s_real = se_te(su, ctx_s, w, params)            # :229
+    su_pro = class_means(su_real, support_labels)                  # :231-239
+    class_dists_l = otam_distance(su_pro, qu_fake, single_direct)  # :269
+    st.update(target_token=target_token, qu_fake=qu_fake, su_real=su_real, token_q_fake=token_q_fake,
+              token_s_real=token_s_real, su_pro=su_pro, class_dists_l=class_dists_l)
+    dists = w["mo_alpha1"] * mo_dist                               # :129 (consist/text distances are 0, :258-259)
+    # ---- taskM (:275-294)
+    uniq = torch.unique(support_labels)
+    suu = torch.stack([su_real[support_labels == c] for c in uniq])          # [W,K,T,D]
+    cn = suu.size(0)
+    token_s = torch.cat([suu, qu_fake.unsqueeze(0).repeat(cn, 1, 1, 1)], dim=1).mean(dim=1)   # :283
+    token_q = token_s.mean(dim=0, keepdim=True)                                              # :284
+    su_t = torch.cat([token_s, su_real], dim=0).permute(1, 0, 2)
+    qu_t = torch.cat([token_q, qu_fake], dim=0).permute(1, 0, 2)
+    _su = transformer_v1(su_t, w, "context1.").permute(1, 0, 2)
+    _qu = transformer_v1(qu_t, w, "context1.").permute(1, 0, 2)
+    su_2, qu_2, su_t2, qu_t2 = _su[cn:], _qu[1:], _su[:cn], _qu[0:1]
+    su_pro2 = class_means(su_2, support_labels)                                 # :133-137
+    task_dist = otam_distance(su_pro2, qu_2, single_direct) + otam_distance(su_t2, qu_t2, single_direct)  # :138
+    logits = -(0.5 * class_dists_l + task_dist).unsqueeze(0)                    # :141
+    st.update(su_2=su_2, qu_2=qu_2, su_t2=su_t2, qu_t2=qu_t2, su_pro2=su_pro2, task_dist=task_dist,
+              logits=logits, dists=dists.reshape(()))
+    return st
+
+
+def forward(w, text_features, inputs, cfg):
+    """models/model_clipspm.py:111-144 CNN.forward (eval): inputs is the reference's episode dict."""
+    T = cfg["seq_len"]
+    enc = vit_forward if cfg["backbone"] == "ViT-B/16" else rn50_forward
+    su = enc(w, inputs["context_images"]).reshape(-1, T, cfg["mid_dim"])        # :158-163
+    qu = enc(w, inputs["target_images"]).reshape(-1, T, cfg["mid_dim"])
+    st = head_forward(w, text_features, su, qu, inputs["context_labels"], inputs["real_support_labels"],
+                      inputs["real_target_labels"], cfg["params"], cfg.get("single_direct", False))
+    st.update(su=su, qu=qu)
+    return st
+
+
+def loss_and_acc(logits, dists, target_labels, tasks_per_batch=16):
+    """utils/utils.py:174-186 loss (CE summed over queries for the single logit sample), :259-264
+    aggregate_accuracy, combined as run/main_run.py:390-392."""
+    lg = logits[0].double()
+    ce = -(lg.log_softmax(-1).gather(1, target_labels.long().view(-1, 1)).squeeze(1))
+    loss = ce.sum() / tasks_per_batch + 0.001 * dists.double()
+    pred = lg.argmax(-1)
+    acc = (pred == target_labels.long()).double().mean()
+    return loss.float(), acc.float(), pred
+
+
+# =====================================================================================================
+# synthetic protocol: seeded weights and episodes, shared by the oracle, the reference
+# pinning script and the CUDA path so that all three see bit-identical inputs
+# =====================================================================================================
+DEFAULT_PARAMS = dict(mid_dim_vision=0.5, mid_dim_text=1.5, negative_slope=0.0025, alpha=0.2, motion_alpha=1)
+
+
+def _gen(seed, name):
+    return torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63 - 1))
+
+
+def _normal(seed, name, shape, std):
+    return torch.randn(*shape, generator=_gen(seed, name)) * std
+
+
+def _uniform(seed, name, shape, lo, hi):
+    return torch.rand(*shape, generator=_gen(seed, name)) * (hi - lo) + lo
+
+
+def head_weight_shapes(D, params=DEFAULT_PARAMS):
+    ht, hv = int(D * params["mid_dim_text"]), int(D * params["mid_dim_vision"])
+    s = {"scale": (1,), "mo_alpha1": (),
+         "motion_conv1.weight": (D, D, 3), "motion_conv1.bias": (D,),
+         "motion_conv2.weight": (D, D, 3), "motion_conv2.bias": (D,),
+         "token_tr.mlp.net.0.weight": (2048, D), "token_tr.mlp.net.0.bias": (2048,),
+         "token_tr.mlp.net.3.weight": (D, 2048), "token_tr.mlp.net.3.bias": (D,),
+         "gate_text.0.weight": (ht, D), "gate_text.0.bias": (ht,), "gate_text.2.weight": (D, ht),
+         "gate_text.2.bias": (D,),
+         "gate_vision.0.weight": (hv, D), "gate_vision.0.bias": (hv,), "gate_vision.2.weight": (D, hv),
+         "gate_vision.2.bias": (D,)}
+    for c in ("context1.", "context2."):
+        s.update({c + "layers.0.0.norm.weight": (D,), c + "layers.0.0.norm.bias": (D,),
+                  c + "layers.0.0.fn.to_q.weight": (2048, D), c + "layers.0.0.fn.to_k.weight": (2048, D),
+                  c + "layers.0.0.fn.to_v.weight": (2048, D),
+                  c + "layers.0.0.fn.to_out.0.weight": (D, 2048), c + "layers.0.0.fn.to_out.0.bias": (D,),
+                  c + "layers.0.1.net.0.weight": (2048, D), c + "layers.0.1.net.0.bias": (2048,),
+                  c + "layers.0.1.net.3.weight": (D, 2048), c + "layers.0.1.net.3.bias": (D,)})
+    return s
+
+
+def vit_weight_shapes(prefix="backbone."):
+    C = VIT["width"]
+    s = {prefix + "conv1.weight": (C, 3, 16, 16), prefix + "class_embedding": (C,),
+         prefix + "positional_embedding": (197, C), prefix + "ln_pre.weight": (C,), prefix + "ln_pre.bias": (C,),
+         prefix + "ln_post.weight": (C,), prefix + "ln_post.bias": (C,), prefix + "proj": (C, VIT["out_dim"])}
+    for i in range(VIT["layers"]):
+        p = prefix + "transformer.resblocks.%d." % i
+        s.update({p + "attn.in_proj_weight": (3 * C, C), p + "attn.in_proj_bias": (3 * C,),
+                  p + "attn.out_proj.weight": (C, C), p + "attn.out_proj.bias": (C,),
+                  p + "ln_1.weight": (C,), p + "ln_1.bias": (C,), p + "ln_2.weight": (C,), p + "ln_2.bias": (C,),
+                  p + "mlp.c_fc.weight": (4 * C, C), p + "mlp.c_fc.bias": (4 * C,),
+                  p + "mlp.c_proj.weight": (C, 4 * C), p + "mlp.c_proj.bias": (C,)})
+    return s
+
+
+def rn50_weight_shapes(prefix="backbone."):
+    wd = RN50["width"]
+    s = {}
+
+    def bn(p, c):
+        s.update({p + "weight": (c,), p + "bias": (c,), p + "running_mean": (c,), p + "running_var": (c,),
+                  p + "num_batches_tracked": ()})
+    s[prefix + "conv1.weight"] = (wd // 2, 3, 3, 3); bn(prefix + "bn1.", wd // 2)
+    s[prefix + "conv2.weight"] = (wd // 2, wd // 2, 3, 3); bn(prefix + "bn2.", wd // 2)
+    s[prefix + "conv3.weight"] = (wd, wd // 2, 3, 3); bn(prefix + "bn3.", wd)
+    inpl = wd
+    for li, nb in enumerate(RN50["layers"]):
+        planes = wd * (2 ** li)
+        for bi in range(nb):
+            p = prefix + "layer%d.%d." % (li + 1, bi)
+            stride = 2 if (li > 0 and bi == 0) else 1
+            s[p + "conv1.weight"] = (planes, inpl, 1, 1); bn(p + "bn1.", planes)
+            s[p + "conv2.weight"] = (planes, planes, 3, 3); bn(p + "bn2.", planes)
+            s[p + "conv3.weight"] = (planes * 4, planes, 1, 1); bn(p + "bn3.", planes * 4)
+            if stride > 1 or inpl != planes * 4:
+                s[p + "downsample.0.weight"] = (planes * 4, inpl, 1, 1); bn(p + "downsample.1.", planes * 4)
+            inpl = planes * 4
+    E = wd * 32
+    p = prefix + "attnpool."
+    s[p + "positional_embedding"] = (50, E)
+    for n in ("q_proj", "k_proj", "v_proj"):
+        s[p + n + ".weight"] = (E, E); s[p + n + ".bias"] = (E,)
+    s[p + "c_proj.weight"] = (RN50["out_dim"], E); s[p + "c_proj.bias"] = (RN50["out_dim"],)
+    return s
+
+
+def make_weights(backbone, seed=0, protocol="P1", head_only=False, params=DEFAULT_PARAMS):
+    """Seeded synthetic state_dict keyed by the reference's names.  Not the reference's RNG stream:
+    each tensor has its own generator (seed, crc32(name)) so any subset regenerates identically anywhere.
+      P0: scales of CLIP/PyTorch default init (features of different frames nearly collinear -> near-tied logits)
+      P1: "separable": residual-branch weights N(0,1/fan_in), wide attention in-projections, non-trivial
+          LayerNorm/BatchNorm affine terms and biases -> logit rows with usable top-1/top-2 margins."""
+    D = 512 if backbone == "ViT-B/16" else 1024
+    w = {}
+    shapes = dict(head_weight_shapes(D, params))
+    if not head_only:
+        shapes.update(vit_weight_shapes() if backbone == "ViT-B/16" else rn50_weight_shapes())
+    for name, shp in shapes.items():
+        leaf = name.split(".")[-1]
+        if name == "scale":
+            w[name] = torch.ones(1)
+        elif name == "mo_alpha1":
+            w[name] = torch.tensor(1.0)
+        elif leaf == "num_batches_tracked":
+            w[name] = torch.tensor(0, dtype=torch.long)
+        elif leaf == "running_mean":
+            w[name] = _normal(seed, name, shp, 0.1)
+        elif leaf == "running_var":
+            w[name] = _uniform(seed, name, shp, 0.5, 1.5)
+        elif len(shp) == 1 and leaf == "weight":   # LayerNorm / BatchNorm scale
+            w[name] = (_uniform(seed, name, shp, 0.5, 1.5) if "bn" in name or "downsample" in name
+                       else 1.0 + _normal(seed, name, shp, 0.1))
+        elif leaf == "bias" or leaf == "in_proj_bias":
+            w[name] = _normal(seed, name, shp, 0.02)
+        elif leaf in ("class_embedding", "positional_embedding", "proj"):
+            w[name] = _normal(seed, name, shp, shp[-1 if leaf != "proj" else 0] ** -0.5)
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            if protocol == "P1" and leaf == "in_proj_weight":
+                std = 3.0 * fan_in ** -0.5
+            elif protocol == "P1" and (name.endswith("out_proj.weight") or name.endswith("c_proj.weight")):
+                std = fan_in ** -0.5
+            elif leaf == "in_proj_weight":
+                std = (2.0 / (fan_in + shp[0])) ** 0.5          # xavier_uniform of nn.MultiheadAttention
+            elif "backbone." in name and len(shp) == 4:
+                std = (2.0 / fan_in) ** 0.5 if backbone == "RN50" else (3.0 * fan_in) ** -0.5
+            else:
+                std = (3.0 * fan_in) ** -0.5                    # U(-1/sqrt(fan_in), 1/sqrt(fan_in)) of nn.Linear
+            w[name] = _normal(seed, name, shp, std)
+    return w
+
+
+def make_text_features(n_cls, D, seed=0):
+    return torch.randn(n_cls, D, generator=_gen(seed, "text_features"))
+
+
+def make_labels(way, shot, query_per_class, n_text_cls, seed):
+    """Episode labels as the sampler builds them (video_reader.py:312-326): float tensors, shuffled order."""
+    g = _gen(seed, "labels")
+    sl = torch.arange(way).repeat_interleave(shot)
+    sl = sl[torch.randperm(sl.numel(), generator=g)]
+    tl = torch.arange(way).repeat_interleave(query_per_class)
+    tl = tl[torch.randperm(tl.numel(), generator=g)]
+    cls_map = torch.randperm(n_text_cls, generator=g)[:way]
+    return dict(context_labels=sl.float(), target_labels=tl.long(), real_support_labels=cls_map[sl].float(),
+                real_target_labels=cls_map[tl].float(), batch_class_list=cls_map.float())
+
+
+def make_images(labels_support, labels_target, T, seed, protocol="P1", res=224):
+    """float32 NCHW frames in [0,1].  P0: iid U[0,1).  P1: class-structured (per-class 14x14x3 prototype
+    up-sampled x16, per-video offset +-0.075, per-frame class-specific drift 0.05*t, pixel noise +-0.025)."""
+    g = _gen(seed, "images")
+
+    def build(lbl):
+        n = lbl.numel()
+        if protocol == "P0":
+            return torch.rand(n * T, 3, res, res, generator=g)
+        out = torch.empty(n, T, 3, res, res)
+        for i in range(n):
+            c = int(lbl[i])
+            gc = _gen(seed, "proto%d" % c)
+            proto = torch.rand(3, res // 16, res // 16, generator=gc) * 0.6 + 0.2
+            drift = torch.rand(3, res // 16, res // 16, generator=gc) - 0.5
+            off = (torch.rand(3, 1, 1, generator=g) - 0.5) * 0.15
+            for t in range(T):
+                base = (proto + off + 0.05 * t * drift).repeat_interleave(16, 1).repeat_interleave(16, 2)
+                out[i, t] = (base + (torch.rand(3, res, res, generator=g) - 0.5) * 0.05).clamp_(0, 1)
+        return out.view(n * T, 3, res, res)
+
+    return build(labels_support), build(labels_target)
+
+
+def make_episode(seed, way=5, shot=1, query_per_class=1, T=8, n_text_cls=24, protocol="P1", images=True):
+    ep = make_labels(way, shot, query_per_class, n_text_cls, seed)
+    if images:
+        s, t = make_images(ep["context_labels"], ep["target_labels"].float(), T, seed, protocol)
+        ep["context_images"], ep["target_images"] = s, t
+    return ep
+
+
+def make_features(seed, n_support, n_query, T, D, labels_support=None, labels_target=None, sep=0.12):
+    """Synthetic frame features for head-only cases: class centre + per-video + per-frame noise."""
+    g = _gen(seed, "features")
+    W = int(max(labels_support.max(), labels_target.max())) + 1 if labels_support is not None else 1
+    centres = torch.randn(W, 1, D, generator=g)
+    drift = torch.randn(W, 1, D, generator=g)
+
+    def build(n, lbl):
+        x = torch.randn(n, T, D, generator=g) * 0.5 + torch.randn(n, 1, D, generator=g) * 0.3
+        if lbl is not None:
+            tt = torch.arange(T).float().view(1, T, 1) / T
+            x = x + sep * (centres[lbl.long()] + tt * drift[lbl.long()])
+        return x
+
+    return build(n_support, labels_support), build(n_query, labels_target)

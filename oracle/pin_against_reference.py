@@ -1,0 +1,172 @@
+"""Pins oracle/clipspm_oracle.py against the REAL reference and writes the golden fixtures.
+
+Runs only in the build container (needs /root/reference, CPU is enough):
+    python oracle/pin_against_reference.py            # all cases, rewrites tests/golden/*.npz
+It imports the reference's own modules through the import shim of SURVEY.md 8(c) (stub `ftfy`; `load` replaced by a
+random-init CLIP(...) because checkpoints cannot be downloaded; Tensor.cuda a no-op on this CPU box), loads the
+seeded synthetic state_dict of oracle.make_weights() key-for-key (strict), runs the reference's CNN.forward on the
+seeded episodes, records every stage tensor by wrapping the reference's methods, asserts the oracle restatement
+reproduces them, and stores them under tests/golden/ (small .npz files; weights and images are NOT stored -- they
+regenerate from the seeds).  Nothing here is imported by the product path."""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+from oracle import clipspm_oracle as O  # noqa: E402
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    ftfy = types.ModuleType("ftfy")
+    ftfy.fix_text = lambda s: s
+    sys.modules.setdefault("ftfy", ftfy)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    import models.clip_fsar as clip_fsar
+    import models.model_clipspm as m
+
+    def fake_load(name, device="cpu", cfg=None, jit=False):
+        if name == "ViT-B/16":
+            net = clip_fsar.CLIP(512, 224, 12, 768, 16, 77, 49408, 512, 8, 12)
+        else:
+            net = clip_fsar.CLIP(1024, 224, (3, 4, 6, 3), 64, None, 77, 49408, 512, 8, 12)
+        return net.float().eval(), None
+
+    m.load = fake_load
+    return m
+
+
+class NS(types.SimpleNamespace):
+    pass
+
+
+def build_reference(m, backbone, T, single_direct=False):
+    cfg = NS(MODEL=NS(BACKBONE=backbone), TRAIN=NS(CLASS_NAME=["run"]), TEST=NS(CLASS_NAME=["run"]),
+             DATA=NS(SEQ_LEN=T), DEVICE=NS(NUM_GPUS=1), params=dict(O.DEFAULT_PARAMS))
+    if single_direct:
+        cfg.MODEL.SINGLE_DIRECT = True
+    torch.manual_seed(0)
+    net = m.CNN(cfg).eval()
+    return net
+
+
+def record(net):
+    """Wrap the reference's own methods to capture stage tensors (no reference source is modified)."""
+    st = {}
+    orig = dict(get_feats=net.get_feats, mo=net.mo, sem=net.sem, taskM=net.taskM, token_tr=net.token_tr.forward,
+                get_motion_feats=net.get_motion_feats)
+
+    def get_feats(*a, **k):
+        r = orig["get_feats"](*a, **k)
+        st["su"], st["qu"] = r[0].clone(), r[1].clone()
+        return r
+
+    def gmf(*a, **k):
+        r = orig["get_motion_feats"](*a, **k)
+        if "su_mo" not in st:
+            st["su_mo"], st["qu_mo"] = r[0].clone(), r[1].clone()
+        return r
+
+    def mo(*a, **k):
+        r = orig["mo"](*a, **k)
+        st["mo_dist_pre"] = r.clone()
+        return r
+
+    def sem(*a, **k):
+        r = orig["sem"](*a, **k)
+        st["su_real"], st["qu_fake"], st["su_pro"] = r[0].clone(), r[1].clone(), r[2].clone()
+        st["target_token"] = r[6].clone()
+        st["token_q_fake"], st["token_s_real"] = r[8].clone().unsqueeze(1) if r[8].dim() == 2 else r[8].clone(), r[9].clone()
+        return r
+
+    def taskM(*a, **k):
+        r = orig["taskM"](*a, **k)
+        st["su_2"], st["qu_2"], st["su_t2"], st["qu_t2"] = [x.clone() for x in r]
+        return r
+
+    net.get_feats, net.get_motion_feats, net.mo, net.sem, net.taskM = get_feats, gmf, mo, sem, taskM
+    return st
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+CASES = {
+    # name: (backbone, way, shot, qpc, T, n_text_cls, protocol, head_only, single_direct, seed)
+    "vit_5w1s_t8_p1": ("ViT-B/16", 5, 1, 1, 8, 24, "P1", False, False, 1000),      # BASELINE config 1
+    "vit_2w1s_t2_p0": ("ViT-B/16", 2, 1, 1, 2, 24, "P0", False, False, 1001),      # tiny tower case, default-scale init
+    "head_5w5s_t8": ("ViT-B/16", 5, 5, 1, 8, 24, "P1", True, False, 1002),         # config 2/5 head shape
+    "head_5w1s_t16": ("ViT-B/16", 5, 1, 1, 16, 24, "P1", True, False, 1003),       # config 3 (OTAM 16x18 grid)
+    "head_5w3s_t8_d1024": ("RN50", 5, 3, 1, 8, 10, "P1", True, False, 1004),       # config 4 head shape
+    "head_5w2s_t8_q3_single": ("ViT-B/16", 5, 2, 3, 8, 24, "P1", True, True, 1005),  # SINGLE_DIRECT, 3 queries/class
+    "rn50_2w1s_t2_p1": ("RN50", 2, 1, 1, 2, 10, "P1", False, False, 1006),         # RN50 tower
+}
+
+
+def run_case(m, name):
+    backbone, way, shot, qpc, T, ncls, proto, head_only, single, seed = CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    net = build_reference(m, backbone, T, single)
+    w = O.make_weights(backbone, seed=0, protocol=proto, head_only=False)
+    missing, unexpected = net.load_state_dict(w, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    text = O.make_text_features(ncls, D, seed=0)
+    net.text_features_test = text
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, proto, images=not head_only)
+    cfg = dict(backbone=backbone, seq_len=T, mid_dim=D, params=O.DEFAULT_PARAMS, single_direct=single)
+    st_ref = record(net)
+    if head_only:
+        su, qu = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+        net.get_feats = lambda *a, **k: (su, qu, None)
+        ep["context_images"] = torch.zeros(1)
+        ep["target_images"] = torch.zeros(1)
+    with torch.no_grad():
+        out = net(ep)
+        if head_only:
+            st_ref["su"], st_ref["qu"] = su, qu
+            st = O.head_forward(w, text, su, qu, ep["context_labels"], ep["real_support_labels"],
+                                ep["real_target_labels"], O.DEFAULT_PARAMS, single)
+            st.update(su=su, qu=qu)
+        else:
+            st = O.forward(w, text, ep, cfg)
+    st_ref["logits"], st_ref["dists"] = out["logits"], out["dists"].reshape(())
+    # loss / accuracy through the reference's own utils (matplotlib stubbed: it is imported but unused there)
+    for mod in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    import utils.utils as U
+    loss_ref = U.loss(out["logits"], ep["target_labels"].long(), "cpu") / 16 + 0.001 * out["dists"]
+    acc_ref = U.aggregate_accuracy(out["logits"], ep["target_labels"])
+    loss, acc, pred = O.loss_and_acc(st["logits"], st["dists"], ep["target_labels"])
+    st_ref["loss"], st_ref["acc"] = loss_ref.reshape(()), acc_ref.reshape(())
+    st["loss"], st["acc"] = loss.reshape(()), acc.reshape(())
+    worst = 0.0
+    for k, v in st_ref.items():
+        r = rel(st[k].reshape(v.shape), v)
+        worst = max(worst, r)
+        assert r < 2e-4, "oracle disagrees with the reference on %s/%s: rel err %.3e" % (name, k, r)
+    lg = st_ref["logits"][0]
+    top2 = lg.topk(2, dim=-1).values
+    margin = (top2[:, 0] - top2[:, 1])
+    print("%-24s oracle==reference, worst stage rel err %.2e | logits row spread %.3f, min top1-top2 margin %.4f, "
+          "ref acc %.2f" % (name, worst, float((lg.max(-1).values - lg.min(-1).values).mean()), float(margin.min()),
+                            float(acc_ref)))
+    gold = {k: v.detach().float().numpy() for k, v in st_ref.items()}
+    gold["pred"] = lg.argmax(-1).numpy()
+    gold["margin"] = margin.numpy()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
+
+
+if __name__ == "__main__":
+    m = import_reference()
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        run_case(m, n)
