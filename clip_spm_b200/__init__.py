@@ -1,5 +1,6 @@
 """clip_spm_b200 -- B200-native (sm_100a) implementation of the CLIP-SPM episode-evaluation hot path
 (reference: models/model_clipspm.py::CNN.forward), behind a C-ABI shared library."""
 from . import _lib  # noqa: F401
+from .model import CNN  # noqa: F401
 
-__all__ = ["_lib"]
+__all__ = ["CNN", "_lib"]

@@ -41,14 +41,14 @@ SIGNATURES = {
                                  ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_int64)]),
     "spm_set_text_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "spm_encode_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    "spm_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 7),
-    "spm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 7),
-    "spm_eval": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),
-    "spm_eval_host": (c_int, [c_void_p, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),
+    "spm_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7),
+    "spm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7),
+    "spm_eval": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),
+    "spm_eval_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),
     "spm_otam_distance": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                   c_float, c_float, c_void_p]),
     "spm_gemm": (c_int, [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_int,
-                         c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int]),
+                         c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int]),
 }
 
 _lib = None

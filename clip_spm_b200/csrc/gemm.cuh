@@ -17,7 +17,11 @@ struct GemmEpilogue {
   int ldr = 0;
   int res_row_mod = 0;    // 0: rrow = orow ; >0: rrow = (m % res_row_mod) + res_row_off  (positional table)
   int res_row_off = 0;
-  int out_row_group = 0;  // 0: orow = m ; >0: orow = m + m / out_row_group + 1  (skip one class-token row per frame)
+  // 0: orow = m ; >0: orow = (m / out_row_group) * out_group_stride + (m % out_row_group) + out_row_off
+  // (patch rows skip one class-token row per frame: 196 / 197 / 1; query tokens land after the supports of their episode)
+  int out_row_group = 0;
+  int out_group_stride = 0;
+  int out_row_off = 0;
   void* out = nullptr;    // fp32 or bf16, leading dim ldo (elements)
   int ldo = 0;
   int out_bf16 = 0;

@@ -160,7 +160,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after_sync();
       const bool row_ok = m < M;
       long long orow = m;
-      if (ep.out_row_group > 0) orow = (long long)m + m / ep.out_row_group + 1;
+      if (ep.out_row_group > 0)
+        orow = (long long)(m / ep.out_row_group) * ep.out_group_stride + (m % ep.out_row_group) + ep.out_row_off;
       long long rrow = orow;
       if (ep.res_row_mod > 0) rrow = (m % ep.res_row_mod) + ep.res_row_off;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);

@@ -1,0 +1,35 @@
+// Launchers of the metric-head kernels (head_kernels.cu, otam.cu).  Return 0 on success, a cudaError_t value on a
+// launch failure, or a negative number for an unsupported shape.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spm {
+
+int k_temporal_im2col(cudaStream_t st, const float* x, long long vid_stride, int V, int T, int D, float* out);
+int k_motion_reduce(cudaStream_t st, const float* conv, const float* x, long long vid_stride, int V, int T, int D,
+                    float* out);
+int k_mo_dist(cudaStream_t st, const float* new_m, const float* z_tok, long long tok_stride, int E, int S, int Q, int D,
+              const float* mo_alpha1, float* dists);
+int k_token_prepare(cudaStream_t st, const float* text, const float* real_support, const float* real_target,
+                    const float* X, int E, int S, int Q, int T, int D, float* tok_b, float* tt_in);
+int k_seq_build(cudaStream_t st, const float* tok, const float* gt, const float* X, const float* gv, int n_calls,
+                int V, int T, int D, float alpha, float* seq);
+int k_seq_attention_init();
+int k_seq_attention(cudaStream_t st, const float* qkv, float* out, int n_batch, int rows_per_batch, int n_groups,
+                    int off0, int len0, int off1, int len1, int heads, int dh);
+int k_padm_build(cudaStream_t st, const float* z, const float* labels, int E, int S, int Q, int W, int T, int D,
+                 float* su_pro, float* seq1, int* err_flag);
+int k_class_mean_padm(cudaStream_t st, const float* z1, const float* labels, int E, int S, int Q, int W, int T, int D,
+                      float* su_pro2);
+int k_finalize(cudaStream_t st, const float* accd, const float* d3, int E, int Q, int W, const long long* target,
+               float tasks_per_batch, const float* dists, float* logits, float* loss, float* accuracy, int* pred,
+               const int* err_flag);
+int k_otam_init();
+// out[p,q,w] = beta*out + alpha * otam(support[p,w,:,:], target[p,q,:,:]); element (p,w,t,d) of the support set is at
+// sup + p*s_p + w*s_w + t*s_t + d (strides in floats), likewise for the target set.
+int k_otam(cudaStream_t st, const float* sup, long long s_p, long long s_w, long long s_t, const float* tgt,
+           long long t_p, long long t_q, long long t_t, int P, int W, int Q, int T, int D, int single_direct,
+           float alpha, float beta, float* out);
+
+}  // namespace spm

@@ -1,0 +1,801 @@
+// Handle, weight packing, workspace and the stream-ordered pipelines behind the C ABI:
+//   frame encoder (ViT-B/16)  models/clip_fsar.py:672-689
+//   metric head               models/model_clipspm.py:116-143 (mo / sem / taskM / otam_distance / logits)
+//   loss + accuracy           utils/utils.py:174-186,259-264 ; run/main_run.py:390-392
+// No allocation happens inside a forward call once the shapes have been seen (plans and workspace are cached),
+// and nothing synchronises with the host except spm_load_weights and spm_eval_host (whose contract is blocking).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/clipspm_b200.h"
+#include "api_common.cuh"
+#include "gemm.cuh"
+#include "head_kernels.cuh"
+#include "kernels.cuh"
+#include "rn50.cuh"
+
+namespace spm {
+
+int device_sm_count(int* out);
+
+namespace {
+constexpr int VIT_C = 768, VIT_L = 197, VIT_P = 196, VIT_LAYERS = 12, VIT_OUT = 512;
+constexpr int HEAD_INNER = 2048, HEAD_HEADS = 8, HEAD_DH = 256, HEAD_MLP = 2048;
+constexpr long long FRAME_ELEMS = 3LL * 224 * 224;
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+#define SPM_KERNEL(call)                                                                       \
+  do {                                                                                         \
+    int _r = (call);                                                                           \
+    if (_r != 0) {                                                                             \
+      set_error(std::string(#call) + (_r < 0 ? ": unsupported shape"                          \
+                                              : std::string(": ") + cudaGetErrorString((cudaError_t)_r))); \
+      return 1;                                                                                \
+    }                                                                                          \
+  } while (0)
+
+#define SPM_GEMM_RUN(op)                                 \
+  do {                                                   \
+    const char* _e = "";                                 \
+    if (gemm_run(&(op), st, &_e)) {                      \
+      set_error(std::string("gemm_run " #op ": ") + _e); \
+      return 1;                                          \
+    }                                                    \
+  } while (0)
+
+struct VitLayerW {
+  __nv_bfloat16 *qkv_w, *out_w, *fc_w, *proj_w;
+  float *qkv_b, *out_b, *fc_b, *proj_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+struct VitW {
+  __nv_bfloat16* conv1_w = nullptr;  // [768, 768]
+  float *cls_pos = nullptr, *pos = nullptr, *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr,
+        *ln_post_b = nullptr;
+  __nv_bfloat16* projT = nullptr;  // [512, 768]
+  VitLayerW layer[VIT_LAYERS];
+};
+struct CtxW {
+  float *ln_g, *ln_b, *qkv_w, *out_w, *out_b, *ff0_w, *ff0_b, *ff3_w, *ff3_b;
+};
+struct HeadW {
+  float *mc1_w, *mc1_b, *mc2_w, *mc2_b;
+  float *tt0_w, *tt0_b, *tt3_w, *tt3_b;
+  float *gt0_w, *gt0_b, *gt2_w, *gt2_b, *gv0_w, *gv0_b, *gv2_w, *gv2_b;
+  CtxW ctx[2];  // [0] = context1 (PADM), [1] = context2 (SPM se_te)
+  float* mo_alpha1;
+};
+
+struct VitPlan {
+  GemmOp patch, qkv[VIT_LAYERS], outp[VIT_LAYERS], fc[VIT_LAYERS], proj[VIT_LAYERS], fin;
+};
+struct CtxPlan {
+  GemmOp qkv, outp, ff0, ff3;
+};
+struct HeadPlan {
+  int E, S, Q, W;
+  GemmOp mc1, mc2, tt0, tt3, gt0, gt2, gv0, gv2;
+  CtxPlan c2, c1;
+};
+}  // namespace
+}  // namespace spm
+
+struct spm_handle {
+  spm_config cfg;
+  int D = 512, HT = 768, HV = 256;
+  int sms = 148;
+  int frame_chunk = 256;
+  bool weights_loaded = false, text_set = false;
+  std::vector<void*> allocs;
+  spm::VitW vit;
+  spm::Rn50* rn50 = nullptr;
+  spm::HeadW head;
+  float* text = nullptr;
+  int n_cls = 0;
+  // encoder workspace (sized for frame_chunk frames)
+  __nv_bfloat16 *patches = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr, *cls = nullptr;
+  float* x = nullptr;
+  float* feats = nullptr;  // [max frames per call, D]
+  long long feats_cap = 0;
+  std::map<int, std::unique_ptr<spm::VitPlan>> vit_plans;
+  // head workspace
+  long long head_cap_E = 0, head_cap_S = 0, head_cap_Q = 0, head_cap_W = 0;
+  float *X = nullptr, *XC = nullptr, *C1 = nullptr, *C2 = nullptr, *TOK = nullptr, *TTIN = nullptr, *TTH = nullptr,
+        *GTH = nullptr, *GT = nullptr, *GVH = nullptr, *GV = nullptr, *SEQ = nullptr, *HN = nullptr, *QKVH = nullptr,
+        *AO = nullptr, *Y = nullptr, *FFH = nullptr, *Z = nullptr, *Z1 = nullptr, *NEWM = nullptr, *SUPRO = nullptr,
+        *SUPRO2 = nullptr, *ACC = nullptr, *D3 = nullptr;
+  int* err_flag = nullptr;
+  std::vector<std::unique_ptr<spm::HeadPlan>> head_plans;
+  // forward workspace: logits/dists when the caller only wants loss/acc, host staging for spm_eval_host
+  float *tmp_logits = nullptr, *tmp_dists = nullptr;
+  struct Stage {
+    float *su = nullptr, *qu = nullptr, *lab = nullptr, *rs = nullptr, *rt = nullptr;
+    long long* tl = nullptr;
+    float *logits = nullptr, *dists = nullptr, *loss = nullptr, *acc = nullptr;
+    int* pred = nullptr;
+    cudaEvent_t copied = nullptr, done = nullptr;
+  } stage[2];
+  long long stage_cap_frames_s = 0, stage_cap_frames_q = 0;
+  cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+};
+
+namespace spm {
+namespace {
+
+int dalloc(spm_handle* h, void** p, size_t bytes) {
+  SPM_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  h->allocs.push_back(*p);
+  return 0;
+}
+template <class T>
+int dalloc_t(spm_handle* h, T** p, long long n) {
+  return dalloc(h, reinterpret_cast<void**>(p), (size_t)n * sizeof(T));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------------------
+struct WeightTable {
+  std::unordered_map<std::string, std::pair<const float*, long long>> m;
+  int get(const std::string& name, long long numel, const float** out) const {
+    auto it = m.find(name);
+    if (it == m.end()) { set_error("spm_load_weights: missing tensor '" + name + "'"); return 1; }
+    if (it->second.second != numel) {
+      set_error("spm_load_weights: tensor '" + name + "' has " + std::to_string(it->second.second) +
+                " elements, expected " + std::to_string(numel));
+      return 1;
+    }
+    *out = it->second.first;
+    return 0;
+  }
+};
+
+int copy_f32(spm_handle* h, cudaStream_t st, const WeightTable& wt, const std::string& name, long long n, float** dst) {
+  const float* src;
+  SPM_TRY(wt.get(name, n, &src));
+  SPM_TRY(dalloc_t(h, dst, n));
+  SPM_CUDA(cudaMemcpyAsync(*dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+int copy_bf16(spm_handle* h, cudaStream_t st, const WeightTable& wt, const std::string& name, long long n,
+              __nv_bfloat16** dst) {
+  const float* src;
+  SPM_TRY(wt.get(name, n, &src));
+  SPM_TRY(dalloc_t(h, dst, n));
+  SPM_KERNEL(k_cast_bf16(st, src, *dst, n));
+  return 0;
+}
+
+int load_vit(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
+  VitW& v = h->vit;
+  const std::string p = "backbone.";
+  const int C = VIT_C;
+  SPM_TRY(copy_bf16(h, st, wt, p + "conv1.weight", (long long)C * C, &v.conv1_w));
+  SPM_TRY(copy_f32(h, st, wt, p + "positional_embedding", (long long)VIT_L * C, &v.pos));
+  const float* ce;
+  SPM_TRY(wt.get(p + "class_embedding", C, &ce));
+  SPM_TRY(dalloc_t(h, &v.cls_pos, C));
+  SPM_KERNEL(k_add_vec(st, ce, v.pos, v.cls_pos, C));  // class token row = class_embedding + pos[0]
+  SPM_TRY(copy_f32(h, st, wt, p + "ln_pre.weight", C, &v.ln_pre_g));
+  SPM_TRY(copy_f32(h, st, wt, p + "ln_pre.bias", C, &v.ln_pre_b));
+  SPM_TRY(copy_f32(h, st, wt, p + "ln_post.weight", C, &v.ln_post_g));
+  SPM_TRY(copy_f32(h, st, wt, p + "ln_post.bias", C, &v.ln_post_b));
+  const float* proj;
+  SPM_TRY(wt.get(p + "proj", (long long)C * VIT_OUT, &proj));
+  SPM_TRY(dalloc_t(h, &v.projT, (long long)C * VIT_OUT));
+  SPM_KERNEL(k_transpose_cast_bf16(st, proj, v.projT, C, VIT_OUT));
+  for (int i = 0; i < VIT_LAYERS; ++i) {
+    const std::string b = p + "transformer.resblocks." + std::to_string(i) + ".";
+    VitLayerW& l = v.layer[i];
+    SPM_TRY(copy_bf16(h, st, wt, b + "attn.in_proj_weight", 3LL * C * C, &l.qkv_w));
+    SPM_TRY(copy_f32(h, st, wt, b + "attn.in_proj_bias", 3 * C, &l.qkv_b));
+    SPM_TRY(copy_bf16(h, st, wt, b + "attn.out_proj.weight", (long long)C * C, &l.out_w));
+    SPM_TRY(copy_f32(h, st, wt, b + "attn.out_proj.bias", C, &l.out_b));
+    SPM_TRY(copy_bf16(h, st, wt, b + "mlp.c_fc.weight", 4LL * C * C, &l.fc_w));
+    SPM_TRY(copy_f32(h, st, wt, b + "mlp.c_fc.bias", 4 * C, &l.fc_b));
+    SPM_TRY(copy_bf16(h, st, wt, b + "mlp.c_proj.weight", 4LL * C * C, &l.proj_w));
+    SPM_TRY(copy_f32(h, st, wt, b + "mlp.c_proj.bias", C, &l.proj_b));
+    SPM_TRY(copy_f32(h, st, wt, b + "ln_1.weight", C, &l.ln1_g));
+    SPM_TRY(copy_f32(h, st, wt, b + "ln_1.bias", C, &l.ln1_b));
+    SPM_TRY(copy_f32(h, st, wt, b + "ln_2.weight", C, &l.ln2_g));
+    SPM_TRY(copy_f32(h, st, wt, b + "ln_2.bias", C, &l.ln2_b));
+  }
+  return 0;
+}
+
+int load_head(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
+  HeadW& w = h->head;
+  const long long D = h->D, HT = h->HT, HV = h->HV;
+  const float* src;
+  SPM_TRY(wt.get("motion_conv1.weight", D * D * 3, &src));
+  SPM_TRY(dalloc_t(h, &w.mc1_w, D * D * 3));
+  SPM_KERNEL(k_repack_conv1d(st, src, w.mc1_w, (int)D, (int)D));
+  SPM_TRY(wt.get("motion_conv2.weight", D * D * 3, &src));
+  SPM_TRY(dalloc_t(h, &w.mc2_w, D * D * 3));
+  SPM_KERNEL(k_repack_conv1d(st, src, w.mc2_w, (int)D, (int)D));
+  SPM_TRY(copy_f32(h, st, wt, "motion_conv1.bias", D, &w.mc1_b));
+  SPM_TRY(copy_f32(h, st, wt, "motion_conv2.bias", D, &w.mc2_b));
+  SPM_TRY(copy_f32(h, st, wt, "token_tr.mlp.net.0.weight", HEAD_MLP * D, &w.tt0_w));
+  SPM_TRY(copy_f32(h, st, wt, "token_tr.mlp.net.0.bias", HEAD_MLP, &w.tt0_b));
+  SPM_TRY(copy_f32(h, st, wt, "token_tr.mlp.net.3.weight", D * HEAD_MLP, &w.tt3_w));
+  SPM_TRY(copy_f32(h, st, wt, "token_tr.mlp.net.3.bias", D, &w.tt3_b));
+  SPM_TRY(copy_f32(h, st, wt, "gate_text.0.weight", HT * D, &w.gt0_w));
+  SPM_TRY(copy_f32(h, st, wt, "gate_text.0.bias", HT, &w.gt0_b));
+  SPM_TRY(copy_f32(h, st, wt, "gate_text.2.weight", D * HT, &w.gt2_w));
+  SPM_TRY(copy_f32(h, st, wt, "gate_text.2.bias", D, &w.gt2_b));
+  SPM_TRY(copy_f32(h, st, wt, "gate_vision.0.weight", HV * D, &w.gv0_w));
+  SPM_TRY(copy_f32(h, st, wt, "gate_vision.0.bias", HV, &w.gv0_b));
+  SPM_TRY(copy_f32(h, st, wt, "gate_vision.2.weight", D * HV, &w.gv2_w));
+  SPM_TRY(copy_f32(h, st, wt, "gate_vision.2.bias", D, &w.gv2_b));
+  SPM_TRY(copy_f32(h, st, wt, "mo_alpha1", 1, &w.mo_alpha1));
+  for (int c = 0; c < 2; ++c) {
+    const std::string p = c == 0 ? "context1.layers.0." : "context2.layers.0.";
+    CtxW& x = w.ctx[c];
+    SPM_TRY(copy_f32(h, st, wt, p + "0.norm.weight", D, &x.ln_g));
+    SPM_TRY(copy_f32(h, st, wt, p + "0.norm.bias", D, &x.ln_b));
+    // fused [Wq; Wk; Wv] : one [3*2048, D] B operand (myRes.py:957-959)
+    SPM_TRY(dalloc_t(h, &x.qkv_w, 3LL * HEAD_INNER * D));
+    const char* names[3] = {"0.fn.to_q.weight", "0.fn.to_k.weight", "0.fn.to_v.weight"};
+    for (int i = 0; i < 3; ++i) {
+      SPM_TRY(wt.get(p + names[i], HEAD_INNER * D, &src));
+      SPM_CUDA(cudaMemcpyAsync(x.qkv_w + (long long)i * HEAD_INNER * D, src, (size_t)HEAD_INNER * D * 4,
+                               cudaMemcpyDeviceToDevice, st));
+    }
+    SPM_TRY(copy_f32(h, st, wt, p + "0.fn.to_out.0.weight", D * HEAD_INNER, &x.out_w));
+    SPM_TRY(copy_f32(h, st, wt, p + "0.fn.to_out.0.bias", D, &x.out_b));
+    SPM_TRY(copy_f32(h, st, wt, p + "1.net.0.weight", HEAD_MLP * D, &x.ff0_w));
+    SPM_TRY(copy_f32(h, st, wt, p + "1.net.0.bias", HEAD_MLP, &x.ff0_b));
+    SPM_TRY(copy_f32(h, st, wt, p + "1.net.3.weight", D * HEAD_MLP, &x.ff3_w));
+    SPM_TRY(copy_f32(h, st, wt, p + "1.net.3.bias", D, &x.ff3_b));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ViT-B/16 frame encoder
+// ---------------------------------------------------------------------------------------------------------
+int plan_gemm(GemmOp* op, int kind, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+              const GemmEpilogue& ep, int sms) {
+  const char* err = "";
+  if (gemm_plan(op, kind, A, lda, B, ldb, M, N, K, ep, sms, &err)) {
+    set_error(std::string("gemm_plan: ") + err);
+    return 1;
+  }
+  return 0;
+}
+
+int ensure_vit_workspace(spm_handle* h) {
+  if (h->x != nullptr) return 0;
+  const long long M = (long long)h->frame_chunk * VIT_L;
+  SPM_TRY(dalloc_t(h, &h->patches, (long long)h->frame_chunk * VIT_P * VIT_C));
+  SPM_TRY(dalloc_t(h, &h->x, M * VIT_C));
+  SPM_TRY(dalloc_t(h, &h->xn, M * VIT_C));
+  SPM_TRY(dalloc_t(h, &h->qkv, M * 3 * VIT_C));
+  SPM_TRY(dalloc_t(h, &h->attn, M * VIT_C));
+  SPM_TRY(dalloc_t(h, &h->hid, M * 4 * VIT_C));
+  SPM_TRY(dalloc_t(h, &h->cls, (long long)h->frame_chunk * VIT_C));
+  return 0;
+}
+
+int get_vit_plan(spm_handle* h, int F, VitPlan** out) {
+  auto it = h->vit_plans.find(F);
+  if (it != h->vit_plans.end()) { *out = it->second.get(); return 0; }
+  std::unique_ptr<VitPlan> pl(new VitPlan());
+  const int C = VIT_C, M = F * VIT_L;
+  const VitW& v = h->vit;
+  {
+    GemmEpilogue ep;  // x[f*197 + 1 + p] = patch . W + pos[1 + p]
+    ep.residual = v.pos; ep.ldr = C; ep.res_row_mod = VIT_P; ep.res_row_off = 1;
+    ep.out_row_group = VIT_P; ep.out_group_stride = VIT_L; ep.out_row_off = 1;
+    ep.out = h->x; ep.ldo = C;
+    SPM_TRY(plan_gemm(&pl->patch, GEMM_BF16, h->patches, C, v.conv1_w, C, F * VIT_P, C, C, ep, h->sms));
+  }
+  for (int i = 0; i < VIT_LAYERS; ++i) {
+    const VitLayerW& l = v.layer[i];
+    GemmEpilogue e1;
+    e1.bias = l.qkv_b; e1.out = h->qkv; e1.ldo = 3 * C; e1.out_bf16 = 1;
+    SPM_TRY(plan_gemm(&pl->qkv[i], GEMM_BF16, h->xn, C, l.qkv_w, C, M, 3 * C, C, e1, h->sms));
+    GemmEpilogue e2;
+    e2.bias = l.out_b; e2.residual = h->x; e2.ldr = C; e2.out = h->x; e2.ldo = C;
+    SPM_TRY(plan_gemm(&pl->outp[i], GEMM_BF16, h->attn, C, l.out_w, C, M, C, C, e2, h->sms));
+    GemmEpilogue e3;
+    e3.bias = l.fc_b; e3.act = ACT_QUICKGELU; e3.out = h->hid; e3.ldo = 4 * C; e3.out_bf16 = 1;
+    SPM_TRY(plan_gemm(&pl->fc[i], GEMM_BF16, h->xn, C, l.fc_w, C, M, 4 * C, C, e3, h->sms));
+    GemmEpilogue e4;
+    e4.bias = l.proj_b; e4.residual = h->x; e4.ldr = C; e4.out = h->x; e4.ldo = C;
+    SPM_TRY(plan_gemm(&pl->proj[i], GEMM_BF16, h->hid, 4 * C, l.proj_w, 4 * C, M, C, 4 * C, e4, h->sms));
+  }
+  {
+    GemmEpilogue ep;
+    ep.out = h->x;  // patched per call
+    ep.ldo = VIT_OUT;
+    SPM_TRY(plan_gemm(&pl->fin, GEMM_BF16, h->cls, C, v.projT, C, F, VIT_OUT, C, ep, h->sms));
+  }
+  *out = pl.get();
+  h->vit_plans[F] = std::move(pl);
+  return 0;
+}
+
+// `F` frames already im2col'ed into h->patches -> feats_out [F, 512]
+int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
+  VitPlan* pl;
+  SPM_TRY(get_vit_plan(h, F, &pl));
+  const VitW& v = h->vit;
+  const int C = VIT_C, M = F * VIT_L;
+  SPM_GEMM_RUN(pl->patch);
+  SPM_KERNEL(k_layernorm(st, h->x, C, M, C, v.ln_pre_g, v.ln_pre_b, v.cls_pos, VIT_L, h->x, nullptr, C));
+  for (int i = 0; i < VIT_LAYERS; ++i) {
+    const VitLayerW& l = v.layer[i];
+    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln1_g, l.ln1_b, nullptr, 0, nullptr, h->xn, C));
+    SPM_GEMM_RUN(pl->qkv[i]);
+    SPM_KERNEL(k_vit_attention(st, h->qkv, h->attn, F));
+    SPM_GEMM_RUN(pl->outp[i]);
+    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xn, C));
+    SPM_GEMM_RUN(pl->fc[i]);
+    SPM_GEMM_RUN(pl->proj[i]);
+  }
+  SPM_KERNEL(k_layernorm(st, h->x, (long long)VIT_L * C, F, C, v.ln_post_g, v.ln_post_b, nullptr, 0, nullptr, h->cls, C));
+  GemmOp fin = pl->fin;
+  fin.ep.out = feats_out;
+  SPM_GEMM_RUN(fin);
+  return 0;
+}
+
+struct Segment {
+  const float* images;
+  long long n_frames;
+};
+
+// Encode the concatenation of the segments; feature rows come out in segment order.
+int encode_segments(spm_handle* h, cudaStream_t st, const Segment* segs, int nseg, float* feats_out) {
+  SPM_CHECK(h->weights_loaded, "encode: weights not loaded (spm_load_weights)");
+  if (h->cfg.backbone == SPM_BACKBONE_RN50) {
+    long long done = 0;
+    for (int s = 0; s < nseg; ++s) {
+      SPM_TRY(rn50_encode(h->rn50, st, segs[s].images, (int)segs[s].n_frames, feats_out + done * h->D));
+      done += segs[s].n_frames;
+    }
+    return 0;
+  }
+  SPM_TRY(ensure_vit_workspace(h));
+  long long total = 0;
+  for (int s = 0; s < nseg; ++s) total += segs[s].n_frames;
+  for (long long f0 = 0; f0 < total; f0 += h->frame_chunk) {
+    const long long f1 = std::min(total, f0 + h->frame_chunk);
+    long long seg0 = 0;
+    for (int s = 0; s < nseg; ++s) {
+      const long long a = std::max(f0, seg0), b = std::min(f1, seg0 + segs[s].n_frames);
+      if (a < b)
+        SPM_KERNEL(k_patch_im2col(st, segs[s].images + (a - seg0) * FRAME_ELEMS,
+                                  h->patches + (a - f0) * VIT_P * VIT_C, (int)(b - a)));
+      seg0 += segs[s].n_frames;
+    }
+    SPM_TRY(vit_run(h, st, (int)(f1 - f0), feats_out + f0 * h->D));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// metric head
+// ---------------------------------------------------------------------------------------------------------
+int ensure_head_workspace(spm_handle* h, int E, int S, int Q, int W) {
+  if (E <= h->head_cap_E && S <= h->head_cap_S && Q <= h->head_cap_Q && W <= h->head_cap_W) return 0;
+  // grow-only: plans that point into the old buffers are dropped
+  h->head_plans.clear();
+  const long long cE = std::max<long long>(E, h->head_cap_E), cS = std::max<long long>(S, h->head_cap_S),
+                  cQ = std::max<long long>(Q, h->head_cap_Q), cW = std::max<long long>(W, h->head_cap_W);
+  const long long T = h->cfg.seq_len, D = h->D, N = cS + cQ, V = cE * N;
+  const long long R2 = 2 * V * (T + 1), R1 = cE * T * (cW + cS + 1 + cQ), R = std::max(R1, R2);
+  SPM_TRY(dalloc_t(h, &h->X, V * T * D));
+  SPM_TRY(dalloc_t(h, &h->XC, V * T * 3 * D));
+  SPM_TRY(dalloc_t(h, &h->C1, V * T * D));
+  SPM_TRY(dalloc_t(h, &h->C2, V * T * D));
+  SPM_TRY(dalloc_t(h, &h->TOK, 2 * V * D));
+  SPM_TRY(dalloc_t(h, &h->TTIN, cE * cQ * D));
+  SPM_TRY(dalloc_t(h, &h->TTH, cE * cQ * HEAD_MLP));
+  SPM_TRY(dalloc_t(h, &h->GTH, 2 * V * h->HT));
+  SPM_TRY(dalloc_t(h, &h->GT, 2 * V * D));
+  SPM_TRY(dalloc_t(h, &h->GVH, V * T * h->HV));
+  SPM_TRY(dalloc_t(h, &h->GV, V * T * D));
+  SPM_TRY(dalloc_t(h, &h->SEQ, R * D));
+  SPM_TRY(dalloc_t(h, &h->HN, R * D));
+  SPM_TRY(dalloc_t(h, &h->QKVH, R * 3 * HEAD_INNER));
+  SPM_TRY(dalloc_t(h, &h->AO, R * HEAD_INNER));
+  SPM_TRY(dalloc_t(h, &h->Y, R * D));
+  SPM_TRY(dalloc_t(h, &h->FFH, R * HEAD_MLP));
+  SPM_TRY(dalloc_t(h, &h->Z, R2 * D));
+  SPM_TRY(dalloc_t(h, &h->Z1, R1 * D));
+  SPM_TRY(dalloc_t(h, &h->NEWM, V * D));
+  SPM_TRY(dalloc_t(h, &h->SUPRO, cE * cW * T * D));
+  SPM_TRY(dalloc_t(h, &h->SUPRO2, cE * cW * T * D));
+  SPM_TRY(dalloc_t(h, &h->ACC, cE * cQ * cW));
+  SPM_TRY(dalloc_t(h, &h->D3, cE * cW));
+  SPM_TRY(dalloc_t(h, &h->tmp_logits, cE * cQ * cW));
+  SPM_TRY(dalloc_t(h, &h->tmp_dists, cE));
+  if (h->err_flag == nullptr) {
+    SPM_TRY(dalloc_t(h, &h->err_flag, 1));
+    SPM_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
+  }
+  h->head_cap_E = cE; h->head_cap_S = cS; h->head_cap_Q = cQ; h->head_cap_W = cW;
+  return 0;
+}
+
+int plan_ctx(spm_handle* h, CtxPlan* p, const CtxW& w, int R, float* seq, float* out) {
+  const int D = h->D;
+  GemmEpilogue e1;
+  e1.out = h->QKVH; e1.ldo = 3 * HEAD_INNER;
+  SPM_TRY(plan_gemm(&p->qkv, GEMM_TF32, h->HN, D, w.qkv_w, D, R, 3 * HEAD_INNER, D, e1, h->sms));
+  GemmEpilogue e2;  // to_out + bias + the un-normalised sequence (myRes.py:1040)
+  e2.bias = w.out_b; e2.residual = seq; e2.ldr = D; e2.out = h->Y; e2.ldo = D;
+  SPM_TRY(plan_gemm(&p->outp, GEMM_TF32, h->AO, HEAD_INNER, w.out_w, HEAD_INNER, R, D, HEAD_INNER, e2, h->sms));
+  GemmEpilogue e3;
+  e3.bias = w.ff0_b; e3.act = ACT_GELU_ERF; e3.out = h->FFH; e3.ldo = HEAD_MLP;
+  SPM_TRY(plan_gemm(&p->ff0, GEMM_TF32, h->Y, D, w.ff0_w, D, R, HEAD_MLP, D, e3, h->sms));
+  GemmEpilogue e4;  // x = ff(x) + x (myRes.py:1069)
+  e4.bias = w.ff3_b; e4.residual = h->Y; e4.ldr = D; e4.out = out; e4.ldo = D;
+  SPM_TRY(plan_gemm(&p->ff3, GEMM_TF32, h->FFH, HEAD_MLP, w.ff3_w, HEAD_MLP, R, D, HEAD_MLP, e4, h->sms));
+  return 0;
+}
+
+int get_head_plan(spm_handle* h, int E, int S, int Q, int W, HeadPlan** out) {
+  SPM_TRY(ensure_head_workspace(h, E, S, Q, W));
+  for (auto& p : h->head_plans)
+    if (p->E == E && p->S == S && p->Q == Q && p->W == W) { *out = p.get(); return 0; }
+  std::unique_ptr<HeadPlan> pl(new HeadPlan());
+  pl->E = E; pl->S = S; pl->Q = Q; pl->W = W;
+  const HeadW& w = h->head;
+  const int T = h->cfg.seq_len, D = h->D, N = S + Q, V = E * N;
+  {
+    GemmEpilogue e;
+    e.bias = w.mc1_b; e.out = h->C1; e.ldo = D;
+    SPM_TRY(plan_gemm(&pl->mc1, GEMM_TF32, h->XC, 3 * D, w.mc1_w, 3 * D, V * T, D, 3 * D, e, h->sms));
+    e.bias = w.mc2_b; e.out = h->C2;
+    SPM_TRY(plan_gemm(&pl->mc2, GEMM_TF32, h->XC, 3 * D, w.mc2_w, 3 * D, V * T, D, 3 * D, e, h->sms));
+  }
+  {
+    GemmEpilogue e;
+    e.bias = w.tt0_b; e.act = ACT_GELU_ERF; e.out = h->TTH; e.ldo = HEAD_MLP;
+    SPM_TRY(plan_gemm(&pl->tt0, GEMM_TF32, h->TTIN, D, w.tt0_w, D, E * Q, HEAD_MLP, D, e, h->sms));
+    GemmEpilogue e2;  // query tokens of the `sem` call land after the S support tokens of their episode
+    e2.bias = w.tt3_b; e2.out = h->TOK + (long long)V * D; e2.ldo = D;
+    e2.out_row_group = Q; e2.out_group_stride = N; e2.out_row_off = S;
+    SPM_TRY(plan_gemm(&pl->tt3, GEMM_TF32, h->TTH, HEAD_MLP, w.tt3_w, HEAD_MLP, E * Q, D, HEAD_MLP, e2, h->sms));
+  }
+  {
+    GemmEpilogue e;
+    e.bias = w.gt0_b; e.act = ACT_LEAKY; e.slope = h->cfg.negative_slope; e.out = h->GTH; e.ldo = h->HT;
+    SPM_TRY(plan_gemm(&pl->gt0, GEMM_TF32, h->TOK, D, w.gt0_w, D, 2 * V, h->HT, D, e, h->sms));
+    GemmEpilogue e2;
+    e2.bias = w.gt2_b; e2.act = ACT_SIGMOID; e2.out = h->GT; e2.ldo = D;
+    SPM_TRY(plan_gemm(&pl->gt2, GEMM_TF32, h->GTH, h->HT, w.gt2_w, h->HT, 2 * V, D, h->HT, e2, h->sms));
+    GemmEpilogue e3;
+    e3.bias = w.gv0_b; e3.act = ACT_LEAKY; e3.slope = h->cfg.negative_slope; e3.out = h->GVH; e3.ldo = h->HV;
+    SPM_TRY(plan_gemm(&pl->gv0, GEMM_TF32, h->X, D, w.gv0_w, D, V * T, h->HV, D, e3, h->sms));
+    GemmEpilogue e4;
+    e4.bias = w.gv2_b; e4.act = ACT_SIGMOID; e4.out = h->GV; e4.ldo = D;
+    SPM_TRY(plan_gemm(&pl->gv2, GEMM_TF32, h->GVH, h->HV, w.gv2_w, h->HV, V * T, D, h->HV, e4, h->sms));
+  }
+  SPM_TRY(plan_ctx(h, &pl->c2, w.ctx[1], 2 * V * (T + 1), h->SEQ, h->Z));
+  SPM_TRY(plan_ctx(h, &pl->c1, w.ctx[0], E * T * (W + S + 1 + Q), h->SEQ, h->Z1));
+  *out = pl.get();
+  h->head_plans.push_back(std::move(pl));
+  return 0;
+}
+
+int run_ctx(spm_handle* h, cudaStream_t st, const CtxPlan& p, const CtxW& w, int R, int n_batch, int rows_per_batch,
+            int n_groups, int off0, int len0, int off1, int len1) {
+  const int D = h->D;
+  SPM_KERNEL(k_layernorm(st, h->SEQ, D, R, D, w.ln_g, w.ln_b, nullptr, 0, h->HN, nullptr, D));
+  SPM_GEMM_RUN(p.qkv);
+  SPM_KERNEL(k_seq_attention(st, h->QKVH, h->AO, n_batch, rows_per_batch, n_groups, off0, len0, off1, len1,
+                             HEAD_HEADS, HEAD_DH));
+  SPM_GEMM_RUN(p.outp);
+  SPM_GEMM_RUN(p.ff0);
+  SPM_GEMM_RUN(p.ff3);
+  return 0;
+}
+
+// Frame features already in h->X as [E, N, T, D] (supports first).  Produces logits [E,Q,W], dists [E] and, when
+// target_labels is given, loss / accuracy / predictions.
+int head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const float* labels, const float* real_s,
+             const float* real_t, const long long* target_labels, float tasks_per_batch, float* logits, float* dists,
+             float* loss, float* acc, int* pred) {
+  SPM_CHECK(h->text_set, "head: text features not set (spm_set_text_features)");
+  HeadPlan* pl;
+  SPM_TRY(get_head_plan(h, E, S, Q, W, &pl));
+  const HeadW& w = h->head;
+  const int T = h->cfg.seq_len, D = h->D, N = S + Q, V = E * N, L1 = W + S + 1 + Q;
+  const long long TD = (long long)T * D, T1D = (long long)(T + 1) * D;
+  // ---- HSMR: motion features of the raw frames (model_clipspm.py:195)
+  SPM_KERNEL(k_temporal_im2col(st, h->X, TD, V, T, D, h->XC));
+  SPM_GEMM_RUN(pl->mc1);
+  SPM_KERNEL(k_temporal_im2col(st, h->C1, TD, V, T, D, h->XC));
+  SPM_GEMM_RUN(pl->mc2);
+  SPM_KERNEL(k_motion_reduce(st, h->C2, h->X, TD, V, T, D, h->TOK));  // tokens of the `mo` se_te call
+  // ---- SPM tokens (model_clipspm.py:120-121,213-216)
+  SPM_KERNEL(k_token_prepare(st, h->text, real_s, real_t, h->X, E, S, Q, T, D, h->TOK + (long long)V * D, h->TTIN));
+  SPM_GEMM_RUN(pl->tt0);
+  SPM_GEMM_RUN(pl->tt3);
+  // ---- gates + the two live se_te batches (mo: tokens = motion; sem: tokens = prompts), one context2 pass
+  SPM_GEMM_RUN(pl->gt0);
+  SPM_GEMM_RUN(pl->gt2);
+  SPM_GEMM_RUN(pl->gv0);
+  SPM_GEMM_RUN(pl->gv2);
+  SPM_KERNEL(k_seq_build(st, h->TOK, h->GT, h->X, h->GV, 2, V, T, D, h->cfg.alpha, h->SEQ));
+  SPM_TRY(run_ctx(h, st, pl->c2, w.ctx[1], 2 * V * (T + 1), 2 * V, T + 1, 1, 0, T + 1, 0, 0));
+  // ---- HSMR: motion of the refined frames vs the refined motion token (model_clipspm.py:200-205)
+  SPM_KERNEL(k_temporal_im2col(st, h->Z + D, T1D, V, T, D, h->XC));
+  SPM_GEMM_RUN(pl->mc1);
+  SPM_KERNEL(k_temporal_im2col(st, h->C1, TD, V, T, D, h->XC));
+  SPM_GEMM_RUN(pl->mc2);
+  SPM_KERNEL(k_motion_reduce(st, h->C2, h->Z + D, T1D, V, T, D, h->NEWM));
+  SPM_KERNEL(k_mo_dist(st, h->NEWM, h->Z, T1D, E, S, Q, D, w.mo_alpha1, dists));
+  // ---- prototypes, class_dists_l, PADM sequences (model_clipspm.py:231-239,269,275-287)
+  const float* Zb = h->Z + (long long)V * T1D;  // outputs of the `sem` call
+  SPM_KERNEL(k_padm_build(st, Zb, labels, E, S, Q, W, T, D, h->SUPRO, h->SEQ, h->err_flag));
+  SPM_KERNEL(k_otam(st, h->SUPRO, (long long)W * TD, TD, D, Zb + ((long long)S * (T + 1) + 1) * D, (long long)N * T1D,
+                    T1D, D, E, W, Q, T, D, h->cfg.single_direct, 0.5f, 0.f, h->ACC));
+  SPM_TRY(run_ctx(h, st, pl->c1, w.ctx[0], E * T * L1, E * T, L1, 2, 0, W + S, W + S, 1 + Q));
+  // ---- task distances on the PADM outputs (model_clipspm.py:133-138)
+  SPM_KERNEL(k_class_mean_padm(st, h->Z1, labels, E, S, Q, W, T, D, h->SUPRO2));
+  const long long L1D = (long long)L1 * D;
+  SPM_KERNEL(k_otam(st, h->SUPRO2, (long long)W * TD, TD, D, h->Z1 + (long long)(W + S + 1) * D, (long long)T * L1D, D,
+                    L1D, E, W, Q, T, D, h->cfg.single_direct, 1.f, 1.f, h->ACC));
+  SPM_KERNEL(k_otam(st, h->Z1, (long long)T * L1D, D, L1D, h->Z1 + (long long)(W + S) * D, (long long)T * L1D, 0, L1D,
+                    E, W, 1, T, D, h->cfg.single_direct, 1.f, 0.f, h->D3));
+  SPM_KERNEL(k_finalize(st, h->ACC, h->D3, E, Q, W, target_labels, tasks_per_batch, dists, logits, loss, acc, pred,
+                        h->err_flag));
+  return 0;
+}
+
+int check_shapes(spm_handle* h, int E, int S, int Q, int W) {
+  SPM_CHECK(h != nullptr, "null handle");
+  SPM_CHECK(E >= 1 && S >= 1 && Q >= 1 && W >= 1, "episode shape must be positive");
+  SPM_CHECK(W <= S, "way cannot exceed the number of support videos");
+  SPM_CHECK(W + S <= 64 && Q + 1 <= 64, "PADM sequences longer than 64 tokens are not supported");
+  SPM_CHECK(W <= 32 && Q <= 64, "at most 32 classes / 64 queries per episode");
+  SPM_CHECK(h->cfg.seq_len >= 2 && h->cfg.seq_len <= 30, "seq_len must be in [2, 30]");
+  return 0;
+}
+
+int forward_impl(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const float* su_img, const float* qu_img,
+                 const float* labels, const float* real_s, const float* real_t, const long long* target_labels,
+                 float tasks_per_batch, float* logits, float* dists, float* loss, float* acc, int* pred) {
+  SPM_TRY(check_shapes(h, E, S, Q, W));
+  SPM_TRY(ensure_head_workspace(h, E, S, Q, W));
+  const int T = h->cfg.seq_len, D = h->D, N = S + Q;
+  const long long nf = (long long)E * N * T;
+  if (nf > h->feats_cap) {
+    SPM_TRY(dalloc_t(h, &h->feats, nf * D));
+    h->feats_cap = nf;
+  }
+  Segment segs[2] = {{su_img, (long long)E * S * T}, {qu_img, (long long)E * Q * T}};
+  SPM_TRY(encode_segments(h, st, segs, 2, h->feats));
+  // feature rows [E*S*T | E*Q*T] -> X [E, N, T, D] (supports first inside each episode)
+  const size_t row = (size_t)T * D * 4;
+  SPM_CUDA(cudaMemcpy2DAsync(h->X, (size_t)N * row, h->feats, (size_t)S * row, (size_t)S * row, E,
+                             cudaMemcpyDeviceToDevice, st));
+  SPM_CUDA(cudaMemcpy2DAsync(h->X + (long long)S * T * D, (size_t)N * row, h->feats + (long long)E * S * T * D,
+                             (size_t)Q * row, (size_t)Q * row, E, cudaMemcpyDeviceToDevice, st));
+  if (logits == nullptr) logits = h->tmp_logits;
+  if (dists == nullptr) dists = h->tmp_dists;
+  return head_run(h, st, E, S, Q, W, labels, real_s, real_t, target_labels, tasks_per_batch, logits, dists, loss, acc,
+                  pred);
+}
+
+}  // namespace
+}  // namespace spm
+
+// =============================================================================================================
+// C ABI
+// =============================================================================================================
+using namespace spm;
+
+extern "C" {
+
+int spm_create(const spm_config* cfg, spm_handle** out) {
+  SPM_CHECK(cfg != nullptr && out != nullptr, "spm_create: null argument");
+  SPM_CHECK(cfg->backbone == SPM_BACKBONE_VIT_B16 || cfg->backbone == SPM_BACKBONE_RN50, "spm_create: unknown backbone");
+  SPM_CHECK(cfg->seq_len >= 2 && cfg->seq_len <= 30, "spm_create: seq_len must be in [2, 30]");
+  SPM_CHECK(cfg->precision == SPM_PRECISION_BF16, "spm_create: only SPM_PRECISION_BF16 is implemented");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("spm_create: no CUDA device -- this library has no CPU path");
+    return 1;
+  }
+  int dev = 0, major = 0;
+  SPM_CUDA(cudaGetDevice(&dev));
+  SPM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  SPM_CHECK(major == 10, "spm_create: the kernels are built for sm_100a (B200) only");
+  std::unique_ptr<spm_handle> h(new spm_handle());
+  h->cfg = *cfg;
+  h->D = cfg->backbone == SPM_BACKBONE_VIT_B16 ? 512 : 1024;
+  h->HT = (int)(h->D * cfg->mid_dim_text);
+  h->HV = (int)(h->D * cfg->mid_dim_vision);
+  SPM_CHECK(h->HT % 32 == 0 && h->HV % 32 == 0 && h->HT > 0 && h->HV > 0,
+            "spm_create: gate hidden sizes must be positive multiples of 32");
+  SPM_TRY(device_sm_count(&h->sms));
+  if (const char* e = getenv("SPM_FRAME_CHUNK")) h->frame_chunk = std::max(1, atoi(e));
+  const char* err = "";
+  if (gemm_init(&err)) { set_error(err); return 1; }
+  SPM_KERNEL(k_vit_attention_init());
+  SPM_KERNEL(k_seq_attention_init());
+  SPM_KERNEL(k_otam_init());
+  *out = h.release();
+  return 0;
+}
+
+int spm_destroy(spm_handle* h) {
+  if (h == nullptr) return 0;
+  cudaDeviceSynchronize();
+  if (h->rn50) rn50_destroy(h->rn50);
+  for (void* p : h->allocs) cudaFree(p);
+  for (auto& s : h->stage) {
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
+  delete h;
+  return 0;
+}
+
+int spm_load_weights(spm_handle* h, void* stream, int n, const char* const* names, const void* const* dev_ptrs,
+                     const int64_t* numel) {
+  SPM_CHECK(h != nullptr && names != nullptr && dev_ptrs != nullptr && numel != nullptr, "spm_load_weights: null argument");
+  SPM_CHECK(!h->weights_loaded, "spm_load_weights: weights already loaded for this handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  WeightTable wt;
+  for (int i = 0; i < n; ++i) wt.m[names[i]] = {static_cast<const float*>(dev_ptrs[i]), (long long)numel[i]};
+  if (h->cfg.backbone == SPM_BACKBONE_VIT_B16) {
+    SPM_TRY(load_vit(h, st, wt));
+  } else {
+    auto getter = [&](const std::string& name, long long ne, const float** out) { return wt.get(name, ne, out); };
+    SPM_TRY(rn50_create(&h->rn50, st, h->sms, getter));
+  }
+  SPM_TRY(load_head(h, st, wt));
+  SPM_CUDA(cudaStreamSynchronize(st));
+  h->weights_loaded = true;
+  return 0;
+}
+
+int spm_set_text_features(spm_handle* h, void* stream, const float* table, int n_cls, int dim) {
+  SPM_CHECK(h != nullptr && table != nullptr, "spm_set_text_features: null argument");
+  SPM_CHECK(dim == h->D, "spm_set_text_features: feature dim does not match the backbone's mid_dim");
+  SPM_CHECK(n_cls >= 1, "spm_set_text_features: empty table");
+  if (n_cls > h->n_cls) SPM_TRY(dalloc_t(h, &h->text, (long long)n_cls * dim));
+  SPM_CUDA(cudaMemcpyAsync(h->text, table, (size_t)n_cls * dim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  h->n_cls = n_cls;
+  h->text_set = true;
+  return 0;
+}
+
+int spm_encode_frames(spm_handle* h, void* stream, const float* images, int n_frames, float* feats_out) {
+  SPM_CHECK(h != nullptr && images != nullptr && feats_out != nullptr, "spm_encode_frames: null argument");
+  if (n_frames <= 0) return 0;
+  Segment seg{images, n_frames};
+  return encode_segments(h, (cudaStream_t)stream, &seg, 1, feats_out);
+}
+
+int spm_head(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, const float* su, const float* qu,
+             const float* support_labels, const float* real_support, const float* real_target, float* logits_out,
+             float* dists_out) {
+  SPM_TRY(check_shapes(h, n_episodes, S, Q, W));
+  SPM_CHECK(su && qu && support_labels && real_support && real_target && logits_out && dists_out, "spm_head: null argument");
+  SPM_CHECK(h->weights_loaded, "spm_head: weights not loaded");
+  cudaStream_t st = (cudaStream_t)stream;
+  SPM_TRY(ensure_head_workspace(h, n_episodes, S, Q, W));
+  const int T = h->cfg.seq_len, D = h->D, N = S + Q;
+  const size_t row = (size_t)T * D * 4;
+  SPM_CUDA(cudaMemcpy2DAsync(h->X, (size_t)N * row, su, (size_t)S * row, (size_t)S * row, n_episodes,
+                             cudaMemcpyDeviceToDevice, st));
+  SPM_CUDA(cudaMemcpy2DAsync(h->X + (long long)S * T * D, (size_t)N * row, qu, (size_t)Q * row, (size_t)Q * row,
+                             n_episodes, cudaMemcpyDeviceToDevice, st));
+  return head_run(h, st, n_episodes, S, Q, W, support_labels, real_support, real_target, nullptr, 1.f, logits_out,
+                  dists_out, nullptr, nullptr, nullptr);
+}
+
+int spm_forward(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, const float* support_images,
+                const float* target_images, const float* support_labels, const float* real_support,
+                const float* real_target, float* logits_out, float* dists_out) {
+  SPM_CHECK(support_images && target_images && support_labels && real_support && real_target && logits_out && dists_out,
+            "spm_forward: null argument");
+  return forward_impl(h, (cudaStream_t)stream, n_episodes, S, Q, W, support_images, target_images, support_labels,
+                      real_support, real_target, nullptr, 1.f, logits_out, dists_out, nullptr, nullptr, nullptr);
+}
+
+int spm_eval(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, const float* support_images,
+             const float* target_images, const float* support_labels, const float* real_support,
+             const float* real_target, const int64_t* target_labels, float tasks_per_batch, float* logits_out,
+             float* dists_out, float* loss_out, float* acc_out, int32_t* pred_out) {
+  SPM_CHECK(support_images && target_images && support_labels && real_support && real_target && target_labels,
+            "spm_eval: null argument");
+  return forward_impl(h, (cudaStream_t)stream, n_episodes, S, Q, W, support_images, target_images, support_labels,
+                      real_support, real_target, reinterpret_cast<const long long*>(target_labels), tasks_per_batch,
+                      logits_out, dists_out, loss_out, acc_out, pred_out);
+}
+
+int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const float* su_h, const float* qu_h,
+                  const float* lab_h, const float* rs_h, const float* rt_h, const int64_t* tl_h, float tasks_per_batch,
+                  float* logits_h, float* dists_h, float* loss_h, float* acc_h, int32_t* pred_h) {
+  SPM_CHECK(h && su_h && qu_h && lab_h && rs_h && rt_h && tl_h, "spm_eval_host: null argument");
+  SPM_TRY(check_shapes(h, 1, S, Q, W));
+  const int T = h->cfg.seq_len;
+  const int EC = std::max(1, h->cfg.max_episodes);  // episodes per chunk
+  const long long fs = (long long)EC * S * T, fq = (long long)EC * Q * T;
+  if (h->copy_stream == nullptr) {
+    SPM_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    SPM_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+    for (auto& s : h->stage) {
+      SPM_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+      SPM_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+  }
+  if (fs > h->stage_cap_frames_s || fq > h->stage_cap_frames_q) {
+    for (auto& s : h->stage) {
+      SPM_TRY(dalloc_t(h, &s.su, fs * FRAME_ELEMS));
+      SPM_TRY(dalloc_t(h, &s.qu, fq * FRAME_ELEMS));
+      SPM_TRY(dalloc_t(h, &s.lab, (long long)EC * S));
+      SPM_TRY(dalloc_t(h, &s.rs, (long long)EC * S));
+      SPM_TRY(dalloc_t(h, &s.rt, (long long)EC * Q));
+      SPM_TRY(dalloc_t(h, &s.tl, (long long)EC * Q));
+      SPM_TRY(dalloc_t(h, &s.logits, (long long)EC * Q * W));
+      SPM_TRY(dalloc_t(h, &s.dists, EC));
+      SPM_TRY(dalloc_t(h, &s.loss, EC));
+      SPM_TRY(dalloc_t(h, &s.acc, EC));
+      SPM_TRY(dalloc_t(h, &s.pred, (long long)EC * Q));
+    }
+    h->stage_cap_frames_s = fs; h->stage_cap_frames_q = fq;
+  }
+  cudaStream_t cs = h->copy_stream, ks = h->compute_stream;
+  int chunk = 0;
+  for (int e0 = 0; e0 < n_episodes; e0 += EC, ++chunk) {
+    const int E = std::min(EC, n_episodes - e0);
+    spm_handle::Stage& s = h->stage[chunk & 1];
+    if (chunk >= 2) SPM_CUDA(cudaStreamWaitEvent(cs, s.done, 0));  // buffer free once chunk-2 has been consumed
+    SPM_CUDA(cudaMemcpyAsync(s.su, su_h + (long long)e0 * S * T * FRAME_ELEMS, (size_t)E * S * T * FRAME_ELEMS * 4,
+                             cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.qu, qu_h + (long long)e0 * Q * T * FRAME_ELEMS, (size_t)E * Q * T * FRAME_ELEMS * 4,
+                             cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.lab, lab_h + (long long)e0 * S, (size_t)E * S * 4, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.rs, rs_h + (long long)e0 * S, (size_t)E * S * 4, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.rt, rt_h + (long long)e0 * Q, (size_t)E * Q * 4, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.tl, tl_h + (long long)e0 * Q, (size_t)E * Q * 8, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaEventRecord(s.copied, cs));
+    SPM_CUDA(cudaStreamWaitEvent(ks, s.copied, 0));
+    SPM_TRY(forward_impl(h, ks, E, S, Q, W, s.su, s.qu, s.lab, s.rs, s.rt, s.tl, tasks_per_batch, s.logits, s.dists,
+                         s.loss, s.acc, s.pred));
+    if (logits_h) SPM_CUDA(cudaMemcpyAsync(logits_h + (long long)e0 * Q * W, s.logits, (size_t)E * Q * W * 4, cudaMemcpyDeviceToHost, ks));
+    if (dists_h) SPM_CUDA(cudaMemcpyAsync(dists_h + e0, s.dists, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
+    if (loss_h) SPM_CUDA(cudaMemcpyAsync(loss_h + e0, s.loss, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
+    if (acc_h) SPM_CUDA(cudaMemcpyAsync(acc_h + e0, s.acc, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
+    if (pred_h) SPM_CUDA(cudaMemcpyAsync(pred_h + (long long)e0 * Q, s.pred, (size_t)E * Q * 4, cudaMemcpyDeviceToHost, ks));
+    SPM_CUDA(cudaEventRecord(s.done, ks));
+  }
+  SPM_CUDA(cudaStreamSynchronize(ks));
+  int flag = 0;
+  SPM_CUDA(cudaMemcpy(&flag, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  SPM_CHECK(flag == 0, "spm_eval_host: an episode's number of distinct support labels differs from `W`");
+  return 0;
+}
+
+int spm_otam_distance(void* stream, int n_pairs, int W, int Q, int T, int D, const float* support, const float* target,
+                      int single_direct, float alpha, float beta, float* out) {
+  SPM_CHECK(support && target && out, "spm_otam_distance: null argument");
+  static bool inited = false;
+  if (!inited) { SPM_KERNEL(k_otam_init()); inited = true; }
+  SPM_KERNEL(k_otam((cudaStream_t)stream, support, (long long)W * T * D, (long long)T * D, D, target,
+                    (long long)Q * T * D, (long long)T * D, D, n_pairs, W, Q, T, D, single_direct, alpha, beta, out));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,323 @@
+"""Host-side mirror of the reference's operator interface for the episode-evaluation path:
+
+    reference                                   here
+    models/model_clipspm.py:13  class CNN       class CNN(cfg, text_features_test=..., text_features_train=...)
+    :111  forward(inputs: dict) -> dict         forward(inputs) -> {"logits": [1,Q,W], "dists": 0-d}   (same keys)
+    models/model_clipfsar.py:49 forward(support_images, support_labels, target_images)  -> forward3(...)
+    run/main_run.py:390-392 loss / accuracy     evaluate(inputs) -> loss, accuracy   (device scalars, no host sync)
+
+`state_dict()` has exactly the reference's keys so `load_state_dict(reference_state_dict)` is the
+weight hand-off.  All arithmetic happens in the C-ABI library (include/clipspm_b200.h); torch only owns the memory.
+There is no CPU / eager fallback: without a CUDA device or without the built library this raises."""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_FRAME = 3 * 224 * 224
+
+
+def _p(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _param_shapes(backbone, D, params):
+    """Names and shapes of the reference CNN's parameters/buffers (models/model_clipspm.py:72-99 and the CLIP visual
+    tower of models/clip_fsar.py:549-689), written out here from the module definitions."""
+    ht, hv = int(D * params["mid_dim_text"]), int(D * params["mid_dim_vision"])
+    s = {"scale": (1,), "mo_alpha1": ()}
+    for n in ("motion_conv1", "motion_conv2"):
+        s[n + ".weight"] = (D, D, 3)
+        s[n + ".bias"] = (D,)
+    s.update({"token_tr.mlp.net.0.weight": (2048, D), "token_tr.mlp.net.0.bias": (2048,),
+              "token_tr.mlp.net.3.weight": (D, 2048), "token_tr.mlp.net.3.bias": (D,)})
+    for c in ("context1", "context2"):
+        p = c + ".layers.0."
+        s.update({p + "0.norm.weight": (D,), p + "0.norm.bias": (D,), p + "0.fn.to_q.weight": (2048, D),
+                  p + "0.fn.to_k.weight": (2048, D), p + "0.fn.to_v.weight": (2048, D),
+                  p + "0.fn.to_out.0.weight": (D, 2048), p + "0.fn.to_out.0.bias": (D,),
+                  p + "1.net.0.weight": (2048, D), p + "1.net.0.bias": (2048,),
+                  p + "1.net.3.weight": (D, 2048), p + "1.net.3.bias": (D,)})
+    s.update({"gate_text.0.weight": (ht, D), "gate_text.0.bias": (ht,), "gate_text.2.weight": (D, ht),
+              "gate_text.2.bias": (D,), "gate_vision.0.weight": (hv, D), "gate_vision.0.bias": (hv,),
+              "gate_vision.2.weight": (D, hv), "gate_vision.2.bias": (D,)})
+    b = "backbone."
+    if backbone == "ViT-B/16":
+        C = 768
+        s.update({b + "class_embedding": (C,), b + "positional_embedding": (197, C), b + "proj": (C, 512),
+                  b + "conv1.weight": (C, 3, 16, 16), b + "ln_pre.weight": (C,), b + "ln_pre.bias": (C,),
+                  b + "ln_post.weight": (C,), b + "ln_post.bias": (C,)})
+        for i in range(12):
+            p = b + "transformer.resblocks.%d." % i
+            s.update({p + "attn.in_proj_weight": (3 * C, C), p + "attn.in_proj_bias": (3 * C,),
+                      p + "attn.out_proj.weight": (C, C), p + "attn.out_proj.bias": (C,),
+                      p + "ln_1.weight": (C,), p + "ln_1.bias": (C,), p + "mlp.c_fc.weight": (4 * C, C),
+                      p + "mlp.c_fc.bias": (4 * C,), p + "mlp.c_proj.weight": (C, 4 * C), p + "mlp.c_proj.bias": (C,),
+                      p + "ln_2.weight": (C,), p + "ln_2.bias": (C,)})
+    else:
+        wd = 64
+
+        def bn(p, c):
+            s.update({p + "weight": (c,), p + "bias": (c,), p + "running_mean": (c,), p + "running_var": (c,),
+                      p + "num_batches_tracked": None})
+        s[b + "conv1.weight"] = (wd // 2, 3, 3, 3); bn(b + "bn1.", wd // 2)
+        s[b + "conv2.weight"] = (wd // 2, wd // 2, 3, 3); bn(b + "bn2.", wd // 2)
+        s[b + "conv3.weight"] = (wd, wd // 2, 3, 3); bn(b + "bn3.", wd)
+        inpl = wd
+        for li, nb in enumerate((3, 4, 6, 3)):
+            planes = wd * 2 ** li
+            for bi in range(nb):
+                p = b + "layer%d.%d." % (li + 1, bi)
+                stride = 2 if (li > 0 and bi == 0) else 1
+                s[p + "conv1.weight"] = (planes, inpl, 1, 1); bn(p + "bn1.", planes)
+                s[p + "conv2.weight"] = (planes, planes, 3, 3); bn(p + "bn2.", planes)
+                s[p + "conv3.weight"] = (planes * 4, planes, 1, 1); bn(p + "bn3.", planes * 4)
+                if stride > 1 or inpl != planes * 4:
+                    s[p + "downsample.0.weight"] = (planes * 4, inpl, 1, 1); bn(p + "downsample.1.", planes * 4)
+                inpl = planes * 4
+        E = wd * 32
+        p = b + "attnpool."
+        s[p + "positional_embedding"] = (50, E)
+        for n in ("k_proj", "q_proj", "v_proj"):
+            s[p + n + ".weight"] = (E, E); s[p + n + ".bias"] = (E,)
+        s[p + "c_proj.weight"] = (1024, E); s[p + "c_proj.bias"] = (1024,)
+    return s
+
+
+class _Node(nn.Module):
+    """Parameter container: gives the flat reference names their nested-module structure (no compute)."""
+
+
+def _register(root, name, tensor, buffer=False):
+    parts = name.split(".")
+    mod = root
+    for part in parts[:-1]:
+        if not hasattr(mod, part):
+            mod.add_module(part, _Node())
+        mod = getattr(mod, part)
+    if buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+def _cfg_get(obj, path, default=None):
+    for part in path.split("."):
+        if isinstance(obj, dict):
+            if part not in obj:
+                return default
+            obj = obj[part]
+        else:
+            if not hasattr(obj, part):
+                return default
+            obj = getattr(obj, part)
+    return obj
+
+
+class CNN(nn.Module):
+    """Drop-in for models/model_clipspm.py::CNN on the evaluation path.
+
+    cfg: the reference's config object (attribute tree or nested dict) -- reads MODEL.BACKBONE, DATA.SEQ_LEN,
+    params{mid_dim_text, mid_dim_vision, negative_slope, alpha, motion_alpha}, optional MODEL.SINGLE_DIRECT,
+    optional TRAIN.WAY (number of classes per episode; derived with torch.unique, a host sync, when absent).
+    The text tower is not run here: pass the [n_cls, D] prompt features the reference keeps
+    in `text_features_test` / `text_features_train`."""
+
+    def __init__(self, cfg, text_features_test=None, text_features_train=None, max_episodes=1, device="cuda"):
+        super().__init__()
+        self.args = cfg
+        self.backbone_name = _cfg_get(cfg, "MODEL.BACKBONE")
+        if self.backbone_name not in ("ViT-B/16", "RN50"):
+            raise RuntimeError("unsupported MODEL.BACKBONE %r" % (self.backbone_name,))
+        self.mid_dim = 512 if self.backbone_name == "ViT-B/16" else 1024
+        self.params = dict(_cfg_get(cfg, "params"))
+        self.seq_len = int(_cfg_get(cfg, "DATA.SEQ_LEN"))
+        self.single_direct = bool(_cfg_get(cfg, "MODEL.SINGLE_DIRECT", False))
+        self.way = _cfg_get(cfg, "TRAIN.WAY", None)
+        self.tasks_per_batch = float(_cfg_get(cfg, "TRAIN.TASKS_PER_BATCH", 16))
+        self.max_episodes = int(max_episodes)
+        self._dev = torch.device(device)
+        for name, shape in _param_shapes(self.backbone_name, self.mid_dim, self.params).items():
+            if shape is None:
+                _register(self, name, torch.zeros((), dtype=torch.long), buffer=True)
+            elif name.split(".")[-1] in ("running_mean", "running_var"):
+                _register(self, name, torch.zeros(shape) if name.endswith("mean") else torch.ones(shape), buffer=True)
+            else:
+                _register(self, name, torch.zeros(shape))
+        self.scale.data.fill_(1.0)
+        self.mo_alpha1.data.fill_(1.0)
+        self.text_features_test = text_features_test
+        self.text_features_train = text_features_train
+        self._h = None
+        self._packed_text = None
+        self.eval()
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def distribute_model(self):
+        """models/model_clipspm.py:103-109 (DataParallel over the backbone) has no equivalent here: episodes are
+        sharded across ranks instead (clip_spm_b200.sweep)."""
+        return None
+
+    def _handle(self):
+        if self._h is not None:
+            return self._h
+        if not torch.cuda.is_available():
+            raise RuntimeError("clip_spm_b200.CNN needs a CUDA device (sm_100a); there is no CPU fallback")
+        lib = _lib.load()
+        c = _lib.SpmConfig(
+            backbone=0 if self.backbone_name == "ViT-B/16" else 1, seq_len=self.seq_len,
+            n_text_classes=0 if self.text_features_test is None else int(self.text_features_test.shape[0]),
+            mid_dim_text=float(self.params["mid_dim_text"]), mid_dim_vision=float(self.params["mid_dim_vision"]),
+            negative_slope=float(self.params["negative_slope"]), alpha=float(self.params["alpha"]),
+            single_direct=int(self.single_direct), precision=0, max_episodes=self.max_episodes, max_support=0,
+            max_query=0, max_way=0)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self._dev):
+            _lib.check(lib.spm_create(ctypes.byref(c), ctypes.byref(h)))
+            sd = {k: v.detach().to(self._dev, torch.float32).contiguous() for k, v in self.state_dict().items()
+                  if v.dtype.is_floating_point}
+            names = list(sd.keys())
+            arr_n = (ctypes.c_char_p * len(names))(*[n.encode() for n in names])
+            arr_p = (ctypes.c_void_p * len(names))(*[sd[n].data_ptr() for n in names])
+            arr_e = (ctypes.c_int64 * len(names))(*[sd[n].numel() for n in names])
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            try:
+                _lib.check(lib.spm_load_weights(h, st, len(names), arr_n, arr_p, arr_e))
+            except Exception:
+                lib.spm_destroy(h)
+                raise
+        self._h = h
+        return h
+
+    def _text(self):
+        tf = self.text_features_train if self.training else self.text_features_test  # model_clipspm.py:116-121
+        if tf is None:
+            raise RuntimeError("text_features_%s is not set" % ("train" if self.training else "test"))
+        if self._packed_text is not tf:
+            h = self._handle()
+            t = tf.detach().to(self._dev, torch.float32).contiguous()
+            _lib.check(_lib.load().spm_set_text_features(
+                h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(t), t.shape[0], t.shape[1]))
+            torch.cuda.current_stream().synchronize()  # `t` may be a temporary
+            self._packed_text = tf
+        return tf
+
+    def load_state_dict(self, state_dict, strict=True):
+        if self._h is not None:
+            raise RuntimeError("load_state_dict must be called before the first forward (weights are packed once)")
+        return super().load_state_dict(state_dict, strict=strict)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None:
+                _lib.load().spm_destroy(self._h)
+        except Exception:
+            pass
+
+    def _way(self, labels):
+        if self.way is not None:
+            return int(self.way)
+        return int(torch.unique(labels).numel())  # host sync, like the reference's own torch.unique (:133)
+
+    def _f32(self, t):
+        return t.to(self._dev, torch.float32).contiguous()
+
+    # ------------------------------------------------------------------------------------------------- forward
+    def forward(self, inputs):
+        """models/model_clipspm.py:111-144: one episode dict -> {"logits": [1,Q,W], "dists": 0-d}."""
+        out = self.forward_episodes(inputs["context_images"], inputs["context_labels"], inputs["target_images"],
+                                    inputs["real_support_labels"], inputs["real_target_labels"], n_episodes=1)
+        return {"logits": out["logits"][0].unsqueeze(0), "dists": out["dists"][0]}
+
+    def forward3(self, support_images, support_labels, target_images, real_support_labels, real_target_labels):
+        """The 3-tensor form of models/model_clipfsar.py:49 plus the two label tensors CLIP-SPM really consumes."""
+        return self.forward(dict(context_images=support_images, context_labels=support_labels,
+                                 target_images=target_images, real_support_labels=real_support_labels,
+                                 real_target_labels=real_target_labels))
+
+    def forward_episodes(self, context_images, context_labels, target_images, real_support_labels,
+                         real_target_labels, n_episodes=1, target_labels=None):
+        """`n_episodes` episodes stacked along dim 0 of every tensor (images [E*S*T,3,224,224] etc.).
+        Returns logits [E,Q,W], dists [E] and, with target_labels, loss [E], acc [E], pred [E,Q]."""
+        if self.training:
+            raise RuntimeError("only the evaluation path is implemented (model.eval())")
+        h = self._handle()
+        self._text()
+        lib = _lib.load()
+        E, T = int(n_episodes), self.seq_len
+        lab = self._f32(context_labels).view(E, -1)
+        S = lab.shape[1]
+        rs, rt = self._f32(real_support_labels).view(E, -1), self._f32(real_target_labels).view(E, -1)
+        Q = rt.shape[1]
+        W = self._way(lab[0])
+        su, qu = self._f32(context_images), self._f32(target_images)
+        if su.numel() != E * S * T * _FRAME or qu.numel() != E * Q * T * _FRAME:
+            raise RuntimeError("image tensors do not match [E*S*T,3,224,224] / [E*Q*T,3,224,224]")
+        logits = torch.empty(E, Q, W, device=self._dev)
+        dists = torch.empty(E, device=self._dev)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        out = {"logits": logits, "dists": dists}
+        if target_labels is None:
+            _lib.check(lib.spm_forward(h, st, E, S, Q, W, _p(su), _p(qu), _p(lab), _p(rs), _p(rt), _p(logits),
+                                       _p(dists)))
+        else:
+            tl = target_labels.to(self._dev, torch.int64).contiguous()
+            loss, acc = torch.empty(E, device=self._dev), torch.empty(E, device=self._dev)
+            pred = torch.empty(E, Q, device=self._dev, dtype=torch.int32)
+            _lib.check(lib.spm_eval(h, st, E, S, Q, W, _p(su), _p(qu), _p(lab), _p(rs), _p(rt), _p(tl),
+                                    self.tasks_per_batch, _p(logits), _p(dists), _p(loss), _p(acc), _p(pred)))
+            out.update(loss=loss, acc=acc, pred=pred)
+        return out
+
+    def evaluate(self, inputs):
+        """forward + run/main_run.py:390-392: returns (loss, accuracy) as device scalars."""
+        out = self.forward_episodes(inputs["context_images"], inputs["context_labels"], inputs["target_images"],
+                                    inputs["real_support_labels"], inputs["real_target_labels"], 1,
+                                    inputs["target_labels"])
+        return out["loss"][0], out["acc"][0]
+
+    def evaluate_host(self, context_images, context_labels, target_images, real_support_labels, real_target_labels,
+                      target_labels, n_episodes, way):
+        """Episodes in HOST memory (pinned for overlap): chunked H2D on a copy stream overlapped with compute
+        (spm_eval_host); returns host tensors.  This is the call the end-to-end benchmark times."""
+        h = self._handle()
+        self._text()
+        lib = _lib.load()
+        E, T = int(n_episodes), self.seq_len
+        S, Q, W = context_labels.numel() // E, real_target_labels.numel() // E, int(way)
+        for t in (context_images, target_images, context_labels, real_support_labels, real_target_labels):
+            assert not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        assert target_labels.dtype == torch.int64 and not target_labels.is_cuda
+        logits, dists = torch.empty(E, Q, W), torch.empty(E)
+        loss, acc, pred = torch.empty(E), torch.empty(E), torch.empty(E, Q, dtype=torch.int32)
+        with torch.cuda.device(self._dev):
+            _lib.check(lib.spm_eval_host(h, E, S, Q, W, _p(context_images), _p(target_images), _p(context_labels),
+                                         _p(real_support_labels), _p(real_target_labels), _p(target_labels),
+                                         self.tasks_per_batch, _p(logits), _p(dists), _p(loss), _p(acc), _p(pred)))
+        return dict(logits=logits, dists=dists, loss=loss, acc=acc, pred=pred)
+
+    # --------------------------------------------------------------------------------------------- stage hooks
+    def encode_frames(self, images):
+        """models/clip_fsar.py:672-689 / :593-608: [F,3,224,224] -> [F, D] (stage entry point for the tests)."""
+        h = self._handle()
+        img = self._f32(images)
+        out = torch.empty(img.shape[0], self.mid_dim, device=self._dev)
+        _lib.check(_lib.load().spm_encode_frames(h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), _p(img),
+                                                 img.shape[0], _p(out)))
+        return out
+
+    def head(self, su, qu, context_labels, real_support_labels, real_target_labels, n_episodes=1):
+        """models/model_clipspm.py:125-143 on precomputed features su [E,S,T,D], qu [E,Q,T,D]."""
+        h = self._handle()
+        self._text()
+        E = int(n_episodes)
+        su, qu = self._f32(su), self._f32(qu)
+        lab = self._f32(context_labels).view(E, -1)
+        rs, rt = self._f32(real_support_labels).view(E, -1), self._f32(real_target_labels).view(E, -1)
+        S, Q, W = lab.shape[1], rt.shape[1], self._way(lab[0])
+        logits, dists = torch.empty(E, Q, W, device=self._dev), torch.empty(E, device=self._dev)
+        _lib.check(_lib.load().spm_head(h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), E, S, Q, W,
+                                        _p(su), _p(qu), _p(lab), _p(rs), _p(rt), _p(logits), _p(dists)))
+        return {"logits": logits, "dists": dists}

@@ -24,7 +24,7 @@ def _need_cuda(*ts):
 
 
 def gemm(a, b, bias=None, act="none", slope=0.0, residual=None, res_row_mod=0, res_row_off=0, out_row_group=0,
-         out=None, out_dtype=torch.float32):
+         out_group_stride=0, out_row_off=0, out=None, out_dtype=torch.float32):
     """out[orow(m), :] = act(a @ b.T + bias) (+ residual[rrow(m), :]).  a [M,K], b [N,K]: both bf16 (tensor-core
     bf16 path) or both fp32 (tf32 path), last dim contiguous."""
     lib = _lib.load()
@@ -34,7 +34,8 @@ def gemm(a, b, bias=None, act="none", slope=0.0, residual=None, res_row_mod=0, r
     M, K = a.shape
     N = b.shape[0]
     if out is None:
-        rows = M if out_row_group == 0 else M + M // out_row_group + 1
+        assert out_row_group == 0, "row-mapped output needs an explicit `out`"
+        rows = M
         out = torch.empty(rows, N, device=a.device, dtype=out_dtype)
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.stride(1) == 1
@@ -42,5 +43,20 @@ def gemm(a, b, bias=None, act="none", slope=0.0, residual=None, res_row_mod=0, r
     _lib.check(lib.spm_gemm(_stream(), kind, _ptr(a), a.stride(0), _ptr(b), b.stride(0), M, N, K, _ptr(bias),
                             ACT[act], float(slope), _ptr(residual),
                             0 if residual is None else residual.stride(0), res_row_mod, res_row_off, out_row_group,
-                            _ptr(out), out.stride(0), 1 if out.dtype == torch.bfloat16 else 0))
+                            out_group_stride, out_row_off, _ptr(out), out.stride(0), 1 if out.dtype == torch.bfloat16 else 0))
+    return out
+
+
+def otam_distance(support, target, single_direct=False, alpha=1.0, beta=0.0, out=None):
+    """cos_sim + (bi)directional OTAM (models/model_clipspm.py:348-362): support [P,W,T,D], target [P,Q,T,D] fp32
+    -> [P,Q,W]."""
+    lib = _lib.load()
+    _need_cuda(support, target, out)
+    support, target = support.contiguous().float(), target.contiguous().float()
+    P, W, T, D = support.shape
+    Q = target.shape[1]
+    if out is None:
+        out = torch.zeros(P, Q, W, device=support.device)
+    _lib.check(lib.spm_otam_distance(_stream(), P, W, Q, T, D, _ptr(support), _ptr(target), int(single_direct),
+                                     float(alpha), float(beta), _ptr(out)))
     return out

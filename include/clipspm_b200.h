@@ -74,20 +74,22 @@ int spm_encode_frames(spm_handle* h, void* stream, const float* images, int n_fr
 /* Metric head on precomputed frame features, n_episodes episodes at once.
  *   su [E,S,T,D], qu [E,Q,T,D] fp32; support_labels [E,S], real_support [E,S], real_target [E,Q] fp32
  *   (labels arrive as float tensors: video_reader.py:322-326).
+ *   W = number of distinct support labels of every episode (the reference derives it with torch.unique, a host
+ *   sync; here the caller states it and the kernels verify it: a mismatch yields NaN logits).
  *   logits_out [E,Q,W] (column w <-> w-th smallest distinct support label), dists_out [E]. */
-int spm_head(spm_handle* h, void* stream, int n_episodes, int S, int Q, const float* su, const float* qu,
+int spm_head(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, const float* su, const float* qu,
              const float* support_labels, const float* real_support, const float* real_target, float* logits_out,
              float* dists_out);
 
 /* CNN.forward for n_episodes episodes: support_images [E,S*T,3,224,224], target_images [E,Q*T,3,224,224] */
-int spm_forward(spm_handle* h, void* stream, int n_episodes, int S, int Q, const float* support_images,
+int spm_forward(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, const float* support_images,
                 const float* target_images, const float* support_labels, const float* real_support,
                 const float* real_target, float* logits_out, float* dists_out);
 
 /* forward + loss/accuracy of run/main_run.py:390-392: per episode
  *   loss_out[e] = sum_q CE(logits[e,q,:], target_labels[e,q]) / tasks_per_batch + 0.001 * dists[e]
  *   acc_out[e]  = mean_q [argmax_w logits[e,q,w] == target_labels[e,q]];  pred_out [E,Q] int32 (may be null) */
-int spm_eval(spm_handle* h, void* stream, int n_episodes, int S, int Q, const float* support_images,
+int spm_eval(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, const float* support_images,
              const float* target_images, const float* support_labels, const float* real_support,
              const float* real_target, const int64_t* target_labels, float tasks_per_batch, float* logits_out,
              float* dists_out, float* loss_out, float* acc_out, int32_t* pred_out);
@@ -95,7 +97,7 @@ int spm_eval(spm_handle* h, void* stream, int n_episodes, int S, int Q, const fl
 /* Same with HOST buffers (pinned or pageable): stages the host->device copies of every episode on a copy
  * stream overlapped with compute, runs spm_eval, and copies logits/dists/loss/acc/pred back to host.
  * Blocks until the results are in the host buffers. */
-int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, const float* support_images_host,
+int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const float* support_images_host,
                   const float* target_images_host, const float* support_labels_host, const float* real_support_host,
                   const float* real_target_host, const int64_t* target_labels_host, float tasks_per_batch,
                   float* logits_host, float* dists_host, float* loss_host, float* acc_host, int32_t* pred_host);
@@ -109,7 +111,8 @@ int spm_otam_distance(void* stream, int n_pairs, int W, int Q, int T, int D, con
  * kind: 0 = bf16 operands, 1 = tf32 (fp32 operands).  act: 0 none, 1 QuickGELU, 2 GELU(erf), 3 LeakyReLU, 4 sigmoid, 5 ReLU */
 int spm_gemm(void* stream, int kind, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
              const float* bias, int act, float slope, const float* residual, int ldr, int res_row_mod,
-             int res_row_off, int out_row_group, void* out, int ldo, int out_bf16);
+             int res_row_off, int out_row_group, int out_group_stride, int out_row_off, void* out, int ldo,
+             int out_bf16);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,66 @@
+"""Shared helpers of the parity tests: build the CUDA model and the oracle inputs from the same seeds."""
+import os
+import types
+
+import numpy as np
+import torch
+
+from oracle import clipspm_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# name: (backbone, way, shot, qpc, T, n_text_cls, protocol, head_only, single_direct, seed) -- must match
+# oracle/pin_against_reference.py::CASES (the golden files were written by that script from the real reference)
+CASES = {
+    "vit_5w1s_t8_p1": ("ViT-B/16", 5, 1, 1, 8, 24, "P1", False, False, 1000),
+    "vit_2w1s_t2_p0": ("ViT-B/16", 2, 1, 1, 2, 24, "P0", False, False, 1001),
+    "head_5w5s_t8": ("ViT-B/16", 5, 5, 1, 8, 24, "P1", True, False, 1002),
+    "head_5w1s_t16": ("ViT-B/16", 5, 1, 1, 16, 24, "P1", True, False, 1003),
+    "head_5w3s_t8_d1024": ("RN50", 5, 3, 1, 8, 10, "P1", True, False, 1004),
+    "head_5w2s_t8_q3_single": ("ViT-B/16", 5, 2, 3, 8, 24, "P1", True, True, 1005),
+    "rn50_2w1s_t2_p1": ("RN50", 2, 1, 1, 2, 10, "P1", False, False, 1006),
+}
+
+
+def golden(name):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in np.load(os.path.join(GOLDEN, name + ".npz")).items()}
+
+
+def make_cfg(backbone, T, single_direct=False, way=None):
+    cfg = types.SimpleNamespace(
+        MODEL=types.SimpleNamespace(BACKBONE=backbone), DATA=types.SimpleNamespace(SEQ_LEN=T),
+        TRAIN=types.SimpleNamespace(TASKS_PER_BATCH=16), params=dict(O.DEFAULT_PARAMS))
+    if single_direct:
+        cfg.MODEL.SINGLE_DIRECT = True
+    if way is not None:
+        cfg.TRAIN.WAY = way
+    return cfg
+
+
+def case_inputs(name):
+    backbone, way, shot, qpc, T, ncls, proto, head_only, single, seed = CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    w = O.make_weights(backbone, seed=0, protocol=proto, head_only=head_only)
+    text = O.make_text_features(ncls, D, seed=0)
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, proto, images=not head_only)
+    feats = None
+    if head_only:
+        feats = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+    return dict(backbone=backbone, way=way, shot=shot, qpc=qpc, T=T, D=D, weights=w, text=text, episode=ep,
+                feats=feats, single=single, head_only=head_only)
+
+
+def build_cuda_model(ci, max_episodes=1):
+    from clip_spm_b200 import CNN
+    net = CNN(make_cfg(ci["backbone"], ci["T"], ci["single"], ci["way"]), text_features_test=ci["text"],
+              max_episodes=max_episodes)
+    missing, unexpected = net.load_state_dict(ci["weights"], strict=False)
+    assert not unexpected, unexpected
+    if not ci["head_only"]:
+        assert not missing, missing
+    return net
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

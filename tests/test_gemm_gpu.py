@@ -75,7 +75,8 @@ def test_gemm_inplace_residual_and_row_maps():
     b = (torch.randn(W, W, generator=g) / W ** 0.5).cuda().bfloat16()
     pos = torch.randn(P + 1, W, generator=g).cuda()
     out = torch.zeros(F_ * (P + 1), W, device="cuda")
-    ops.gemm(a, b, residual=pos, res_row_mod=P, res_row_off=1, out_row_group=P, out=out)
+    ops.gemm(a, b, residual=pos, res_row_mod=P, res_row_off=1, out_row_group=P, out_group_stride=P + 1, out_row_off=1,
+             out=out)
     ref = (a.float() @ b.float().t()).view(F_, P, W) + pos[1:]
     got = out.view(F_, P + 1, W)
     assert (got[:, 1:] - ref).abs().max().item() < 2e-4 * ref.abs().max().item()

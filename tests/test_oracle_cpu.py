@@ -1,0 +1,126 @@
+"""CPU suite: the oracle restatement against the golden stage tensors written from the executed reference
+(oracle/pin_against_reference.py), the OTAM recurrence against hand-derivable cases, host-side logic, and the
+C-ABI library's symbol table.  No GPU needed."""
+import ctypes
+import math
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import clipspm_oracle as O
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", ["head_5w5s_t8", "head_5w1s_t16", "head_5w3s_t8_d1024", "head_5w2s_t8_q3_single"])
+def test_oracle_head_matches_reference_golden(name):
+    ci, g = H.case_inputs(name), H.golden(name)
+    ep = ci["episode"]
+    su, qu = ci["feats"]
+    with torch.no_grad():
+        st = O.head_forward(ci["weights"], ci["text"], su, qu, ep["context_labels"], ep["real_support_labels"],
+                            ep["real_target_labels"], O.DEFAULT_PARAMS, ci["single"])
+    for k in ("su_mo", "qu_mo", "mo_dist_pre", "target_token", "su_real", "qu_fake", "su_pro", "su_2", "qu_2",
+              "su_t2", "qu_t2", "logits", "dists"):
+        assert H.rel_err(st[k].reshape(g[k].shape), g[k]) < 1e-4, k
+    loss, acc, pred = O.loss_and_acc(st["logits"], st["dists"], ep["target_labels"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
+    assert float(acc) == float(g["acc"])
+    assert torch.equal(pred, g["pred"].long())
+
+
+def test_oracle_vit_tower_matches_reference_golden():
+    name = "vit_2w1s_t2_p0"
+    ci, g = H.case_inputs(name), H.golden(name)
+    with torch.no_grad():
+        su = O.vit_forward(ci["weights"], ci["episode"]["context_images"])
+    assert H.rel_err(su.reshape(g["su"].shape), g["su"]) < 1e-4
+
+
+def test_oracle_rn50_tower_matches_reference_golden():
+    name = "rn50_2w1s_t2_p1"
+    ci, g = H.case_inputs(name), H.golden(name)
+    with torch.no_grad():
+        su = O.rn50_forward(ci["weights"], ci["episode"]["context_images"])
+    assert H.rel_err(su.reshape(g["su"].shape), g["su"]) < 5e-4
+
+
+def test_otam_hand_cases():
+    """models/myRes.py:821-855 on cases derivable by hand."""
+    lb = 0.5
+    sm = lambda *a: -lb * math.log(sum(math.exp(-x / lb) for x in a))
+    # T=2: padded grid 2 x 4.  Row 0 prefix sums: [0, a, a+b, a+b]; row 1: see recurrence
+    a, b, c, d = 0.3, 0.7, 0.2, 0.9
+    dist = torch.tensor([[[[a, b], [c, d]]]])
+    c01, c02, c03 = a, a + b, a + b
+    c11 = c + sm(0.0, c01, 0.0)
+    c12 = d + sm(c01, c11)
+    c13 = 0.0 + sm(c02, c03, c12)
+    assert abs(float(O.otam_cum_dist_v2(dist)) - c13) < 1e-6
+    # all-zero distances: every soft-min only subtracts lambda*log(k)
+    z = O.otam_cum_dist_v2(torch.zeros(1, 1, 3, 3))
+    assert float(z) < 0
+    # identical videos -> both directions agree
+    x = torch.randn(1, 4, 16, generator=torch.Generator().manual_seed(0))
+    one = O.otam_distance(x, x, single_direct=True)
+    two = O.otam_distance(x, x, single_direct=False)
+    assert abs(float(two) - 2 * float(one)) < 1e-5
+
+
+def test_class_means_follow_sorted_unique_labels():
+    x = torch.arange(12.0).view(6, 1, 2)
+    lab = torch.tensor([7.0, 3.0, 7.0, 5.0, 3.0, 5.0])
+    pm = O.class_means(x, lab)
+    assert torch.allclose(pm[0], x[[1, 4]].mean(0)) and torch.allclose(pm[2], x[[0, 2]].mean(0))
+
+
+def test_synthetic_protocol_is_deterministic():
+    a = O.make_weights("ViT-B/16", seed=0, head_only=True)
+    b = O.make_weights("ViT-B/16", seed=0, head_only=True)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    e1, e2 = O.make_episode(7, images=False), O.make_episode(7, images=False)
+    assert all(torch.equal(e1[k], e2[k]) for k in e1)
+    assert e1["context_labels"].dtype == torch.float32 and e1["target_labels"].dtype == torch.int64
+
+
+def test_state_dict_keys_match_reference_names():
+    """The drop-in's state_dict must be loadable from the reference's: same keys, same shapes."""
+    from clip_spm_b200 import CNN
+    for backbone in ("ViT-B/16", "RN50"):
+        net = CNN(H.make_cfg(backbone, 8))
+        ref = O.make_weights(backbone, seed=0)
+        sd = net.state_dict()
+        assert set(sd.keys()) == set(ref.keys()), set(sd.keys()) ^ set(ref.keys())
+        for k in ref:
+            assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+        net.load_state_dict(ref, strict=True)
+
+
+def test_product_path_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from clip_spm_b200 import CNN
+    net = CNN(H.make_cfg("ViT-B/16", 8), text_features_test=torch.zeros(4, 512))
+    ep = O.make_episode(1, images=False)
+    ep["context_images"] = torch.zeros(40, 3, 224, 224)
+    ep["target_images"] = torch.zeros(40, 3, 224, 224)
+    with pytest.raises(RuntimeError):
+        net(ep)
+
+
+def test_library_exports_every_declared_symbol():
+    """include/clipspm_b200.h <-> built .so <-> ctypes table (no compute calls)."""
+    from clip_spm_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "clipspm_b200.h")).read()
+    declared = set(re.findall(r"\b(spm_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"spm_handle", "spm_config"}
+    assert declared == set(_lib.SIGNATURES.keys()), declared ^ set(_lib.SIGNATURES.keys())
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    loaded = _lib.load()
+    assert loaded.spm_abi_version() == 1
+    assert isinstance(loaded.spm_last_error(), bytes)

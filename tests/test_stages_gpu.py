@@ -1,0 +1,162 @@
+"""GPU parity tests proper: every stage of the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs AND against the golden tensors written from the executed reference.
+
+Tolerances (BASELINE.json north_star): 2e-2 relative (max-abs-error / max-abs-reference) for the bf16 tensor-core
+frame encoder; the head runs in fp32 with tf32 tensor-core products -> 5e-3; the OTAM tail is pure fp32 -> 1e-5.
+Predicted classes must be identical on every query whose reference top-1/top-2 margin exceeds 4x the measured
+logit error."""
+import pytest
+import torch
+
+from oracle import clipspm_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL_BF16 = 2e-2
+TOL_HEAD = 5e-3
+TOL_OTAM = 1e-5
+
+
+@pytest.mark.parametrize("P,W,Q,T,D,single", [(1, 5, 5, 8, 512, False), (3, 5, 5, 16, 512, False),
+                                              (2, 5, 1, 8, 1024, False), (4, 7, 3, 8, 512, True),
+                                              (1, 1, 1, 2, 512, False), (2, 32, 2, 30, 512, False)])
+def test_otam_distance_matches_oracle(P, W, Q, T, D, single):
+    from clip_spm_b200 import ops
+    g = torch.Generator().manual_seed(P * 100 + T)
+    sup = torch.randn(P, W, T, D, generator=g)
+    tgt = torch.randn(P, Q, T, D, generator=g) + 0.5 * sup[:, :1].expand(P, Q, T, D)
+    ref = torch.stack([O.otam_distance(sup[p], tgt[p], single) for p in range(P)])
+    out = ops.otam_distance(sup.cuda(), tgt.cuda(), single)
+    assert H.rel_err(out, ref) < TOL_OTAM
+    # accumulate form: out = beta*out + alpha*otam
+    acc = ops.otam_distance(sup.cuda(), tgt.cuda(), single, alpha=0.5, beta=2.0, out=out.clone())
+    assert H.rel_err(acc, 2.5 * ref) < 1e-5
+
+
+def test_otam_properties_full_size():
+    """size-independent properties at the 1000-episode batch size of BASELINE config 2"""
+    from clip_spm_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1000, 5, 8, 512, generator=g).cuda()
+    y = torch.randn(1000, 5, 8, 512, generator=g).cuda()
+    one = ops.otam_distance(x, y, True)
+    two = ops.otam_distance(x, y, False)
+    # bidirectional = dir(x,y) + dir(y,x)^T (the transposed DP is the single-direction DP of the swapped pair)
+    swapped = ops.otam_distance(y, x, True)
+    assert torch.allclose(two, one + swapped.transpose(1, 2), atol=1e-4)
+    # scale invariance of the cosine: positive rescaling of a video's frames changes distances only through eps=0.01
+    big = ops.otam_distance(x * 1e3, y * 1e3, False)
+    assert (big - two).abs().max() < 0.05
+    # a video against itself is closer than against an independent one
+    self_d = ops.otam_distance(x[:, :1], x[:, :1], False)
+    other_d = ops.otam_distance(x[:, :1], y[:, :1], False)
+    assert bool((self_d < other_d).all())
+
+
+@pytest.mark.parametrize("name", ["head_5w5s_t8", "head_5w1s_t16", "head_5w2s_t8_q3_single", "head_5w3s_t8_d1024"])
+def test_head_matches_reference_golden(name):
+    ci, g = H.case_inputs(name), H.golden(name)
+    net = H.build_cuda_model(ci)
+    ep = ci["episode"]
+    su, qu = ci["feats"]
+    out = net.head(su.cuda(), qu.cuda(), ep["context_labels"], ep["real_support_labels"], ep["real_target_labels"])
+    torch.cuda.synchronize()
+    err = H.rel_err(out["logits"].cpu().unsqueeze(0), g["logits"])
+    assert err < TOL_HEAD, err
+    assert H.rel_err(out["dists"][0].cpu(), g["dists"]) < TOL_HEAD
+    abs_err = float((out["logits"][0].cpu() - g["logits"][0]).abs().max())
+    pred = out["logits"][0].argmax(-1).cpu()
+    safe = g["margin"] > 4 * abs_err
+    assert bool(safe.any())
+    assert torch.equal(pred[safe], g["pred"].long()[safe])
+
+
+def test_head_batched_episodes_equal_single_episodes():
+    """E episodes in one call == E separate calls (episodes are independent units: SURVEY.md 8e)"""
+    ci = H.case_inputs("head_5w5s_t8")
+    net = H.build_cuda_model(ci)
+    eps, sus, qus = [], [], []
+    for e in range(3):
+        ep = O.make_episode(2000 + e, 5, 5, 1, 8, 24, images=False)
+        su, qu = O.make_features(2000 + e, 25, 5, 8, 512, ep["context_labels"], ep["target_labels"].float())
+        eps.append(ep); sus.append(su); qus.append(qu)
+    cat = lambda k: torch.stack([e[k] for e in eps])
+    out = net.head(torch.stack(sus).cuda(), torch.stack(qus).cuda(), cat("context_labels"),
+                   cat("real_support_labels"), cat("real_target_labels"), n_episodes=3)
+    for e in range(3):
+        one = net.head(sus[e].cuda(), qus[e].cuda(), eps[e]["context_labels"], eps[e]["real_support_labels"],
+                       eps[e]["real_target_labels"])
+        assert torch.allclose(out["logits"][e], one["logits"][0], atol=1e-4, rtol=1e-4)
+        assert torch.allclose(out["dists"][e], one["dists"][0], atol=1e-4, rtol=1e-4)
+        with torch.no_grad():
+            ref = O.head_forward(ci["weights"], ci["text"], sus[e], qus[e], eps[e]["context_labels"],
+                                 eps[e]["real_support_labels"], eps[e]["real_target_labels"], O.DEFAULT_PARAMS)
+        assert H.rel_err(out["logits"][e].cpu(), ref["logits"][0]) < TOL_HEAD
+
+
+def test_head_wrong_way_fails_loudly():
+    ci = H.case_inputs("head_5w5s_t8")
+    ci["way"] = 4  # episode really has 5 classes
+    net = H.build_cuda_model(ci)
+    ep = ci["episode"]
+    su, qu = ci["feats"]
+    out = net.head(su.cuda(), qu.cuda(), ep["context_labels"], ep["real_support_labels"], ep["real_target_labels"])
+    assert bool(torch.isnan(out["logits"]).all())
+
+
+@pytest.mark.parametrize("name", ["vit_2w1s_t2_p0", "vit_5w1s_t8_p1"])
+def test_vit_encoder_matches_reference_golden(name):
+    ci, g = H.case_inputs(name), H.golden(name)
+    net = H.build_cuda_model(ci)
+    ep = ci["episode"]
+    su = net.encode_frames(ep["context_images"].cuda())
+    qu = net.encode_frames(ep["target_images"].cuda())
+    torch.cuda.synchronize()
+    assert H.rel_err(su.cpu().view(g["su"].shape), g["su"]) < TOL_BF16
+    assert H.rel_err(qu.cpu().view(g["qu"].shape), g["qu"]) < TOL_BF16
+    # frames are independent: encoding a subset gives the same rows (chunking / tile-boundary independence)
+    part = net.encode_frames(ep["context_images"][1:3].cuda())
+    assert torch.allclose(part, su[1:3], atol=2e-3, rtol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["vit_2w1s_t2_p0", "vit_5w1s_t8_p1"])
+def test_forward_matches_reference_golden(name):
+    """CNN.forward / loss / accuracy end to end (BASELINE config 1 is vit_5w1s_t8_p1)"""
+    ci, g = H.case_inputs(name), H.golden(name)
+    net = H.build_cuda_model(ci)
+    ep = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in ci["episode"].items()}
+    out = net(ep)
+    assert out["logits"].shape == g["logits"].shape and out["dists"].dim() == 0
+    err = H.rel_err(out["logits"].cpu(), g["logits"])
+    assert err < TOL_BF16, err
+    assert H.rel_err(out["dists"].cpu(), g["dists"]) < 5e-2
+    abs_err = float((out["logits"].cpu() - g["logits"]).abs().max())
+    pred = out["logits"][0].argmax(-1).cpu()
+    safe = g["margin"] > 4 * abs_err
+    assert torch.equal(pred[safe], g["pred"].long()[safe])
+    print("\n%s: logits rel err %.2e abs err %.4f; %d/%d queries above the margin filter, all agree; raw agreement %d/%d"
+          % (name, err, abs_err, int(safe.sum()), safe.numel(), int((pred == g["pred"].long()).sum()), safe.numel()))
+    loss, acc = net.evaluate(ep)
+    if bool(safe.all()):
+        assert float(acc) == float(g["acc"])
+    assert abs(float(loss) - float(g["loss"])) < 5e-2 * max(1.0, abs(float(g["loss"])))
+    # forward3 convenience form == dict form
+    o3 = net.forward3(ep["context_images"], ep["context_labels"], ep["target_images"], ep["real_support_labels"],
+                      ep["real_target_labels"])
+    assert torch.equal(o3["logits"], out["logits"])
+
+
+def test_eval_host_matches_device_path():
+    ci = H.case_inputs("vit_2w1s_t2_p0")
+    net = H.build_cuda_model(ci)
+    eps = [O.make_episode(3000 + e, 2, 1, 1, 2, 24, "P0") for e in range(3)]
+    cat = lambda k: torch.cat([e[k] for e in eps]).contiguous()
+    host = net.evaluate_host(cat("context_images").pin_memory(), cat("context_labels"), cat("target_images").pin_memory(),
+                             cat("real_support_labels"), cat("real_target_labels"), cat("target_labels"), 3, 2)
+    for e in range(3):
+        ep = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in eps[e].items()}
+        out = net(ep)
+        assert torch.allclose(host["logits"][e], out["logits"][0].cpu(), atol=1e-5)
+        loss, acc = net.evaluate(ep)
+        assert abs(float(host["loss"][e]) - float(loss)) < 1e-5 and float(host["acc"][e]) == float(acc)
