@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Headline benchmark: 5-way 5-shot CLIP-SPM (ViT-B/16, 8 frames @224) episode evaluation, episodes/s and frames/s.
+
+    python bench.py --gpus 1 --steps K --warmup W                  # this repo's CUDA path
+    torchrun ... bench.py --gpus N ...                              # one rank per GPU, episodes sharded (weak scaling)
+    python bench.py --impl reference ...                            # the reference algorithm on the host CPU cores
+
+A "step" = one pass of the hot path (frame encoder + metric head + loss/accuracy) over a batch of
+`--episodes-per-step` synthetic episodes per GPU.  `value` is measured with the inputs already resident in HBM
+(CUDA events, barrier + synchronize on both sides, max over ranks); `e2e` is the same metric through the public
+host-buffer call (CNN.evaluate_host -> spm_eval_host) with pinned host inputs, H2D/D2H copies inside the timed
+region.  Inputs of one step (8 x 144.5 MB) are larger than the 126 MB L2, so no explicit L2 flush is needed."""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WAY, SHOT, QPC, T, N_TEXT = 5, 5, 1, 8, 24           # BASELINE.json configs[1]: Kinetics-shape 5-way 5-shot
+S, Q = WAY * SHOT, WAY * QPC
+FRAMES = (S + Q) * T                                  # 240 frames per episode
+VIT_GFLOP_PER_FRAME = 35.127
+WORKLOAD = "CLIP-SPM ViT-B/16 5-way 5-shot Kinetics-shape eval (S=25,Q=5,T=8: 240 frames@224 per episode), bf16"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16=d.get("bf16_tflops_sustained", d.get("bf16_tflops")), hbm=d.get("hbm_gbs"), which="measured")
+    return dict(bf16=1590.0, hbm=6650.0, which="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.p = index, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_leg(frames_sample, threads):
+    """The reference algorithm (oracle port, pinned against the executed reference: oracle/pin_against_reference.py)
+    on the host cores: `frames_sample` frames through the ViT tower + one full 5-way 5-shot head.  The tower is
+    99.5 % of the reference's time, so an episode costs tower_time * 240/frames + head_time."""
+    from oracle import clipspm_oracle as O
+    torch.set_num_threads(threads)
+    w = O.make_weights("ViT-B/16", seed=0, protocol="P0")
+    text = O.make_text_features(N_TEXT, 512, seed=0)
+    ep = O.make_episode(1000, WAY, SHOT, QPC, T, N_TEXT, images=False)
+    su, qu = O.make_features(1000, S, Q, T, 512, ep["context_labels"], ep["target_labels"].float())
+    imgs = torch.rand(frames_sample, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+
+    def step():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.vit_forward(w, imgs, chunk=frames_sample)
+            t1 = time.perf_counter()
+            st = O.head_forward(w, text, su, qu, ep["context_labels"], ep["real_support_labels"],
+                                ep["real_target_labels"], O.DEFAULT_PARAMS)
+            O.loss_and_acc(st["logits"], st["dists"], ep["target_labels"])
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    fs = args.ref_frames
+    step = cpu_reference_leg(fs, threads)
+    for _ in range(args.warmup):
+        step()
+    tt = th = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, b = step()
+        tt += a; th += b
+    wall = time.perf_counter() - t0
+    ep_s = 1.0 / ((tt / args.steps) * FRAMES / fs + th / args.steps)
+    line = {"impl": "reference", "metric": "episodes_per_sec", "value": ep_s, "unit": "episodes/s",
+            "frames_per_s": ep_s * FRAMES, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD.replace(", bf16", ", fp32 CPU"), "way": WAY, "shot": SHOT, "seq_len": T},
+            "cpu_baseline": {"value": ep_s, "unit": "episodes/s", "cores": threads, "kind": "port",
+                             "sample": "per step: %d of the 240 frames of one episode through the ViT-B/16 tower + "
+                                       "one full metric head; episode time = tower_time*240/%d + head_time" % (fs, fs)},
+            "e2e": {"value": ep_s, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- CUDA arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--episodes-per-step", type=int, default=8)
+    ap.add_argument("--episodes-per-call", type=int, default=1)
+    ap.add_argument("--ref-frames", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    import __graft_entry__
+    __graft_entry__.build()
+    from clip_spm_b200 import CNN, _lib, sweep
+    from tests.helpers import make_cfg  # plain namespace builder (no oracle use)
+    lib = _lib.load()
+    EPS, EPC = args.episodes_per_step, args.episodes_per_call
+    net = CNN(make_cfg("ViT-B/16", T, False, WAY), max_episodes=EPC, device=dev)
+    net.init_random_(seed=0)
+    net.text_features_test = torch.randn(N_TEXT, 512, generator=torch.Generator().manual_seed(0))
+
+    # this rank's episodes of one step (global ids: weak scaling, every rank has EPS of its own), resident in HBM
+    ids = [rank * EPS + i for i in range(EPS)]
+    dev_batch = sweep.synthetic_episode_batch(ids, WAY, SHOT, QPC, T, N_TEXT, dev)
+
+    def device_step():
+        accs, losses = [], []
+        for i in range(0, EPS, EPC):
+            n = min(EPC, EPS - i)
+            o = net.forward_episodes(dev_batch["context_images"][i * S * T:(i + n) * S * T],
+                                     dev_batch["context_labels"][i:i + n],
+                                     dev_batch["target_images"][i * Q * T:(i + n) * Q * T],
+                                     dev_batch["real_support_labels"][i:i + n],
+                                     dev_batch["real_target_labels"][i:i + n], n, dev_batch["target_labels"][i:i + n])
+            accs.append(o["acc"]); losses.append(o["loss"])
+        return torch.cat(accs), torch.cat(losses)
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.spm_launch_count()
+    _lib.check(lib.spm_profile_begin(args.steps * EPS * 120 + 64))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    acc_all, loss_all = [], []
+    for _ in range(args.steps):
+        a, l = device_step()
+        acc_all.append(a); loss_all.append(l)
+    stats = sweep.reduce_stats(sweep.make_stats(torch.cat(acc_all), torch.cat(loss_all)))  # the path's one collective
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    launches = lib.spm_launch_count() - launches0
+    flops4 = (ctypes.c_double * 4)(); ms4 = (ctypes.c_double * 4)(); cnt4 = (ctypes.c_int * 4)()
+    _lib.check(lib.spm_profile_end(flops4, ms4, cnt4))
+    clocks = sampler.stop()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    total_eps = world * EPS * args.steps
+    value = total_eps / (ms / 1e3)
+    summary = sweep.summarize(stats)
+
+    # ---- e2e: host buffers through the public host call, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hb = sweep.synthetic_episode_batch(ids, WAY, SHOT, QPC, T, N_TEXT, "cpu", pin=True)
+        call = lambda: net.evaluate_host(hb["context_images"], hb["context_labels"].contiguous(), hb["target_images"],
+                                         hb["real_support_labels"].contiguous(), hb["real_target_labels"].contiguous(),
+                                         hb["target_labels"].contiguous(), EPS, WAY)
+        call(); call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = call()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = EPS * (FRAMES * 3 * 224 * 224 * 4 + (2 * S + Q) * 4 + Q * 8)
+        d2h = EPS * (Q * WAY * 4 + 3 * 4 + Q * 4)
+        e2e = {"value": total_eps / float(dt), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    # dominant kernel = the 128x256 bf16 tcgen05 GEMM (tag 1); its algorithmic FLOPs / its summed launch time
+    dom = 1
+    achieved = (flops4[dom] / 1e12) / (ms4[dom] / 1e3) if ms4[dom] > 0 else None
+    gemm_ms_all = sum(ms4)
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256,bf16> (frame-encoder linears)",
+                "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                "frac": (achieved / peaks["bf16"]) if achieved else None, "peak_source": peaks["which"] +
+                " bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks["which"] == "measured" else "fallback 1590",
+                "traffic": None, "launches_timed": int(cnt4[dom]),
+                "gemm_share_of_step": gemm_ms_all / (ms if ms > 0 else 1.0),
+                "whole_step_tflops": value / world * FRAMES * VIT_GFLOP_PER_FRAME / 1e3}
+    line = {"metric": "episodes_per_sec", "value": value, "unit": "episodes/s", "frames_per_s": value * FRAMES,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "way": WAY, "shot": SHOT, "seq_len": T,
+                       "episodes_per_step_per_gpu": EPS, "episodes_per_call": EPC,
+                       "l2": "step inputs (%.0f MB) exceed the 126 MB L2; no explicit flush" % (EPS * FRAMES * 0.602112),
+                       "weights": "random-init (no checkpoints offline)"},
+            "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "clocks": clocks,
+            "sweep_stats": summary}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        step = cpu_reference_leg(args.ref_frames, threads)
+        step()
+        a, b = step()
+        ep_s = 1.0 / (a * FRAMES / args.ref_frames + b)
+        line["cpu_baseline"] = {"value": ep_s, "unit": "episodes/s", "cores": threads, "kind": "port",
+                                "sample": "%d of 240 frames of one episode through the oracle ViT-B/16 tower + one "
+                                          "full metric head, scaled to one episode" % args.ref_frames}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,10 @@ class SpmConfig(ctypes.Structure):
 SIGNATURES = {
     "spm_last_error": (ctypes.c_char_p, []),
     "spm_abi_version": (c_int, []),
+    "spm_launch_count": (c_ll, []),
+    "spm_profile_begin": (c_int, [c_int]),
+    "spm_profile_end": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                ctypes.POINTER(c_int)]),
     "spm_create": (c_int, [ctypes.POINTER(SpmConfig), ctypes.POINTER(c_void_p)]),
     "spm_destroy": (c_int, [c_void_p]),
     "spm_load_weights": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p),

@@ -2,12 +2,35 @@
 // tcgen05 kernel against torch.matmul before anything is stacked on top of it).
 #include "../../include/clipspm_b200.h"
 #include "api_common.cuh"
+#include <atomic>
+#include <vector>
+
 #include "gemm.cuh"
+#include "profile.cuh"
 
 namespace spm {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* get_error() { return g_err.c_str(); }
+
+// ---- instrumentation (profile.cuh)
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct GemmRecord { cudaEvent_t a, b; int tag; double flops; };
+static std::vector<GemmRecord> g_records;
+static int g_used = 0;
+static bool g_profiling = false;
+
+bool profile_gemm_begin(cudaStream_t st, int tag, double flops, int* slot) {
+  if (!g_profiling || g_used >= (int)g_records.size()) return false;
+  GemmRecord& r = g_records[g_used];
+  r.tag = tag; r.flops = flops;
+  if (cudaEventRecord(r.a, st) != cudaSuccess) return false;
+  *slot = g_used++;
+  return true;
+}
+void profile_gemm_end(cudaStream_t st, int slot) { cudaEventRecord(g_records[slot].b, st); }
 
 int device_sm_count(int* out) {
   int dev = 0;
@@ -22,6 +45,36 @@ extern "C" {
 const char* spm_last_error(void) { return spm::get_error(); }
 
 int spm_abi_version(void) { return SPM_ABI_VERSION; }
+
+long long spm_launch_count(void) { return spm::g_launches.load(); }
+
+int spm_profile_begin(int max_records) {
+  using namespace spm;
+  while ((int)g_records.size() < max_records) {
+    GemmRecord r;
+    SPM_CUDA(cudaEventCreate(&r.a));
+    SPM_CUDA(cudaEventCreate(&r.b));
+    g_records.push_back(r);
+  }
+  g_used = 0;
+  g_profiling = true;
+  return 0;
+}
+
+int spm_profile_end(double* flops4, double* ms4, int* count4) {
+  using namespace spm;
+  g_profiling = false;
+  for (int t = 0; t < 4; ++t) { flops4[t] = 0; ms4[t] = 0; count4[t] = 0; }
+  SPM_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < g_used; ++i) {
+    float ms = 0.f;
+    SPM_CUDA(cudaEventElapsedTime(&ms, g_records[i].a, g_records[i].b));
+    const int t = g_records[i].tag & 3;
+    flops4[t] += g_records[i].flops; ms4[t] += ms; count4[t] += 1;
+  }
+  g_used = 0;
+  return 0;
+}
 
 int spm_gemm(void* stream, int kind, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
              const float* bias, int act, float slope, const float* residual, int ldr, int res_row_mod,

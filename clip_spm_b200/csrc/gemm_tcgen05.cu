@@ -13,6 +13,7 @@
 // models/clip_fsar.py:626-632,673,687 (ViT linears, patch-embed conv, projection) and
 // models/myRes.py:944-996 + models/model_clipspm.py:76-99,171-174 (head linears, gates, temporal convs).
 #include "gemm.cuh"
+#include "profile.cuh"
 #include "ptx.cuh"
 
 namespace spm {
@@ -309,6 +310,9 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
 int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
   GemmArgs a;
   a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K;
+  int slot = -1;
+  const bool prof = profile_gemm_begin(stream, op->kind * 2 + (op->bn == 256 ? 1 : 0),
+                                       2.0 * (double)op->M * (double)op->N * (double)op->K, &slot);
 #define SPM_LAUNCH(BN, KIND)                                                                                 \
   gemm_tcgen05_kernel<BN, KIND><<<op->grid, 256, GemmTile<BN, KIND>::SMEM_BYTES, stream>>>(op->ta, op->tb, a)
   if (op->kind == GEMM_BF16) {
@@ -318,7 +322,9 @@ int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
   }
 #undef SPM_LAUNCH
   cudaError_t e = cudaGetLastError();
+  if (prof) profile_gemm_end(stream, slot);
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return 1; }
+  count_launch();
   return 0;
 }
 

@@ -3,6 +3,7 @@
 // on the device from the float labels (the reference does torch.unique + nonzero host syncs,
 // models/model_clipspm.py:133,231,277 + models/myRes.py:730-739).
 #include "head_kernels.cuh"
+#include "profile.cuh"
 
 namespace spm {
 
@@ -10,6 +11,7 @@ namespace spm {
   do {                                                       \
     cudaError_t _e = cudaGetLastError();                     \
     if (_e != cudaSuccess) return (int)_e;                   \
+    count_launch();                                          \
   } while (0)
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }

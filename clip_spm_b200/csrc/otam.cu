@@ -10,6 +10,7 @@
 // __shfl_up from lane m-1 (its last and second-to-last values) and from the lane's own last value:
 // 2T+1 dependent steps instead of the reference's T*(T+2) sequential host-launched cells.
 #include "head_kernels.cuh"
+#include "profile.cuh"
 
 namespace spm {
 
@@ -146,6 +147,7 @@ int k_otam(cudaStream_t st, const float* sup, long long s_p, long long s_w, long
   else
     otam_kernel<8><<<grid, 256, smem, st>>>(sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, W, Q, T, single_direct, alpha, beta, out);
   cudaError_t e = cudaGetLastError();
+  count_launch();
   return (int)e;
 }
 

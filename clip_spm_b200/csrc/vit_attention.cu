@@ -8,6 +8,7 @@
 // warp's own (dead) Q rows so the global store is 128-byte coalesced.
 // Tensor-core path: mma.sync.m16n8k16 bf16 (4 % of the encoder FLOPs; the GEMMs carry the tcgen05 path).
 #include "kernels.cuh"
+#include "profile.cuh"
 
 namespace spm {
 
@@ -169,6 +170,7 @@ int k_vit_attention(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* ou
   if (n_frames <= 0) return 0;
   vit_attention_kernel<<<n_frames * HEADS, 128, SMEM_BYTES, st>>>(qkv, out);
   cudaError_t e = cudaGetLastError();
+  count_launch();
   return (int)e;
 }
 

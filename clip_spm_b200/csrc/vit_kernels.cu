@@ -1,6 +1,7 @@
 // Bandwidth-bound kernels around the frame-encoder GEMMs: weight packing, patch im2col, LayerNorm.
 // All are coalesced, 128-bit vectorised, one pass over their input.
 #include "kernels.cuh"
+#include "profile.cuh"
 
 namespace spm {
 
@@ -8,6 +9,7 @@ namespace spm {
   do {                                                       \
     cudaError_t _e = cudaGetLastError();                     \
     if (_e != cudaSuccess) return (int)_e;                   \
+    count_launch();                                          \
   } while (0)
 
 // ------------------------------------------------------------------------------------------------------

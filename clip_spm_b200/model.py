@@ -160,6 +160,27 @@ class CNN(nn.Module):
         sharded across ranks instead (clip_spm_b200.sweep)."""
         return None
 
+    def init_random_(self, seed=0):
+        """Random-init weights of the architecture for benchmarking (checkpoints are unavailable offline): fan-in
+        scaled normals for matrices / conv kernels, LayerNorm-BatchNorm scales near 1, small biases."""
+        if self._h is not None:
+            raise RuntimeError("init_random_ must be called before the first forward")
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for name, p in list(self.named_parameters()) + list(self.named_buffers()):
+                leaf = name.split(".")[-1]
+                if not p.dtype.is_floating_point or name in ("scale", "mo_alpha1"):
+                    continue
+                if leaf == "running_var":
+                    p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+                elif p.dim() <= 1:
+                    is_scale = leaf == "weight"
+                    p.copy_(torch.randn(p.shape, generator=g) * (0.05 if is_scale else 0.02) + (1.0 if is_scale else 0.0))
+                else:
+                    fan_in = p[0].numel() if leaf != "proj" else p.shape[0]
+                    p.copy_(torch.randn(p.shape, generator=g) * fan_in ** -0.5)
+        return self
+
     def _handle(self):
         if self._h is not None:
             return self._h

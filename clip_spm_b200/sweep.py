@@ -1,0 +1,82 @@
+"""Episode sweep (the caller side of the path: run/main_run.py:256-293 `Learner.test`): episodes are independent
+units, so rank r of a world of n evaluates episodes r, r+n, r+2n, ... with a full weight replica and no
+intra-episode exchange; the only collective is one all-reduce (SUM) of four fp64 sufficient statistics
+[n, sum acc, sum acc^2, sum loss] at the end, from which accuracy, the 95 % confidence interval and the mean loss
+of run/main_run.py:286-289 follow."""
+import math
+
+import torch
+
+
+def shard_episodes(n_episodes, rank, world_size):
+    """Global episode indices owned by `rank` (round-robin: e -> e mod world_size)."""
+    return list(range(rank, n_episodes, world_size))
+
+
+def make_stats(acc, loss):
+    """Per-rank sufficient statistics from per-episode accuracy / loss tensors (any device)."""
+    acc, loss = acc.double().flatten(), loss.double().flatten()
+    return torch.stack([torch.tensor(float(acc.numel()), dtype=torch.float64, device=acc.device), acc.sum(),
+                        (acc * acc).sum(), loss.sum()])
+
+
+def reduce_stats(stats, group=None):
+    """The path's single collective: all-reduce(SUM) of 32 bytes (NCCL over NVLink on GPUs, gloo in CPU tests)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def summarize(stats):
+    """accuracy = mean*100, confidence = 196*std/sqrt(n) (population std, np.std), loss = mean
+    (run/main_run.py:286-289)."""
+    n, s1, s2, sl = [float(v) for v in stats.tolist()]
+    mean = s1 / n
+    var = max(s2 / n - mean * mean, 0.0)
+    return dict(n=int(n), accuracy=100.0 * mean, confidence=196.0 * math.sqrt(var) / math.sqrt(n), loss=sl / n)
+
+
+def synthetic_episode_batch(episode_ids, way, shot, query_per_class, T, n_text_cls, device, pin=False):
+    """Synthetic episodes of the benchmark shape, seeded by GLOBAL episode index so that any sharding evaluates the
+    same episodes.  Pixels are iid U[0,1) float32 (the sampler's format: video_reader.py:65,271); labels follow
+    video_reader.py:312-326 (shuffled float tensors).  Returns stacked tensors (dim 0 = episode-major)."""
+    S, Q = way * shot, way * query_per_class
+    E = len(episode_ids)
+    dev = torch.device(device)
+    su = torch.empty(E * S * T, 3, 224, 224, device=dev, pin_memory=pin and dev.type == "cpu")
+    qu = torch.empty(E * Q * T, 3, 224, 224, device=dev, pin_memory=pin and dev.type == "cpu")
+    lab, rs, rt, tl = [], [], [], []
+    for i, e in enumerate(episode_ids):
+        g = torch.Generator(device=dev).manual_seed(1000 + int(e))
+        su[i * S * T:(i + 1) * S * T].uniform_(0, 1, generator=g)
+        qu[i * Q * T:(i + 1) * Q * T].uniform_(0, 1, generator=g)
+        gc = torch.Generator().manual_seed(1000 + int(e))
+        sl = torch.arange(way).repeat_interleave(shot)
+        sl = sl[torch.randperm(sl.numel(), generator=gc)]
+        ql = torch.arange(way).repeat_interleave(query_per_class)
+        ql = ql[torch.randperm(ql.numel(), generator=gc)]
+        cmap = torch.randperm(n_text_cls, generator=gc)[:way]
+        lab.append(sl.float()); rs.append(cmap[sl].float()); rt.append(cmap[ql].float()); tl.append(ql.long())
+    mk = lambda xs: torch.stack(xs)
+    out = dict(context_images=su, target_images=qu, context_labels=mk(lab), real_support_labels=mk(rs),
+               real_target_labels=mk(rt), target_labels=mk(tl))
+    if dev.type != "cpu":
+        out = {k: v.to(dev) for k, v in out.items()}
+    return out
+
+
+def run_sweep(net, n_episodes, way, shot, query_per_class, n_text_cls, rank=0, world_size=1, episodes_per_call=1):
+    """Evaluate this rank's shard on the CUDA path and return the REDUCED statistics (identical on every rank)."""
+    mine = shard_episodes(n_episodes, rank, world_size)
+    accs, losses = [], []
+    for i in range(0, len(mine), episodes_per_call):
+        ids = mine[i:i + episodes_per_call]
+        b = synthetic_episode_batch(ids, way, shot, query_per_class, net.seq_len, n_text_cls, net._dev)
+        out = net.forward_episodes(b["context_images"], b["context_labels"], b["target_images"],
+                                   b["real_support_labels"], b["real_target_labels"], len(ids), b["target_labels"])
+        accs.append(out["acc"]); losses.append(out["loss"])
+    dev = net._dev
+    acc = torch.cat(accs) if accs else torch.zeros(0, device=dev)
+    loss = torch.cat(losses) if losses else torch.zeros(0, device=dev)
+    return summarize(reduce_stats(make_stats(acc, loss)))

@@ -56,6 +56,14 @@ typedef struct spm_config {
 const char* spm_last_error(void);
 int spm_abi_version(void);
 
+/* Instrumentation for bench.py: number of this library's kernel launches so far (process-wide), and CUDA-event
+ * timing of every GEMM launch between begin/end.  spm_profile_end synchronises the device and returns, per GEMM
+ * flavour t = kind*2 + (tile N == 256) [kind 0 = bf16, 1 = tf32], the summed algorithmic FLOPs (2MNK), the summed
+ * launch durations in ms and the launch count. */
+long long spm_launch_count(void);
+int spm_profile_begin(int max_records);
+int spm_profile_end(double* flops4, double* ms4, int* count4);
+
 int spm_create(const spm_config* cfg, spm_handle** out);
 int spm_destroy(spm_handle* h);
 
