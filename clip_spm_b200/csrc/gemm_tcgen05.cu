@@ -34,15 +34,29 @@ struct GemmTile {
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int STG_BYTES_PER_WARP = 32 * 128;  // epilogue staging tile of one warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 4 * STG_BYTES_PER_WARP + 1024;  // +1024: alignment slack
 };
+
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ float apply_act(float x, int act, float slope) {
   switch (act) {
-    case ACT_QUICKGELU: return x / (1.f + __expf(-1.702f * x));
+    case ACT_QUICKGELU: return __fdividef(x, 1.f + __expf(-1.702f * x));
     case ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
     case ACT_LEAKY: return x > 0.f ? x : slope * x;
-    case ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    case ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-x));
     case ACT_RELU: return fmaxf(x, 0.f);
     default: return x;
   }
@@ -151,73 +165,114 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== epilogue =====================
     const GemmEpilogue& ep = args.ep;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // warp-private staging tile: 32 rows x 128 B, 16-byte units XOR-swizzled by (row & 7) -> conflict-free both ways
+    const uint32_t stg_u = smem_u32(smem + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES + q * T::STG_BYTES_PER_WARP);
+    const int rr = lane >> 3, uu = lane & 7;  // read-back mapping: row i*4 + rr, 16-byte unit uu
+    const int halves = ep.out_bf16 ? 2 : 1;   // 32-column accumulator chunks per 128-byte output group
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
-      const int m = (tile / num_n) * T::BM + q * 32 + lane;
+      const int m_base = (tile / num_n) * T::BM + q * 32;
       const int n0 = (tile % num_n) * BN;
+      // global row offsets (in elements) of the 8 rows this lane stores: row i*4 + rr of the warp's 32
+      long long obase[8], rbase[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m_base + i * 4 + rr;
+        long long orow = m;
+        if (ep.out_row_group > 0)
+          orow = (long long)(m / ep.out_row_group) * ep.out_group_stride + (m % ep.out_row_group) + ep.out_row_off;
+        long long rrow = orow;
+        if (ep.res_row_mod > 0) rrow = (m % ep.res_row_mod) + ep.res_row_off;
+        obase[i] = orow * ep.ldo;
+        rbase[i] = rrow * ep.ldr;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
-      const bool row_ok = m < M;
-      long long orow = m;
-      if (ep.out_row_group > 0)
-        orow = (long long)(m / ep.out_row_group) * ep.out_group_stride + (m % ep.out_row_group) + ep.out_row_off;
-      long long rrow = orow;
-      if (ep.res_row_mod > 0) rrow = (m % ep.res_row_mod) + ep.res_row_off;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        if (row_ok) {
+      for (int g = 0; g < BN / 32; g += halves) {
+        const int col0 = n0 + g * 32;  // first output column of this 128-byte store group
+        if (col0 >= N) break;          // warp-uniform
+        // (a) residual tile: coalesced 16-byte loads, issued before the TMEM round trip so their latency overlaps it
+        float4 res[8];
+        if (ep.residual != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m_base + i * 4 + rr < M) res[i] = *reinterpret_cast<const float4*>(ep.residual + rbase[i] + col0 + uu * 4);
+          }
+        }
+        // (b) accumulator row (one per thread) -> bias / activation -> swizzled staging tile [32 rows][128 B]
+#pragma unroll 1
+        for (int h = 0; h < halves; ++h) {
+          const int c0 = col0 + h * 32;
+          if (c0 >= N) break;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)((g + h) * 32), r);
+          tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (ep.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
+            const float4* bp = reinterpret_cast<const float4*>(ep.bias + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b = __ldg(bp + j);
               v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           }
-          if (ep.act != ACT_NONE) {
+          if (ep.act == ACT_QUICKGELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-1.702f * v[j]));
+          } else if (ep.act != ACT_NONE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act, ep.slope);
           }
-          if (ep.residual != nullptr) {
-            const float4* rp = reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = rp[j];
-              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-          }
+          const uint32_t srow = stg_u + (uint32_t)(lane * 128);
           if (ep.out_bf16) {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow * ep.ldo + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
-              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
               uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&p0);
-              u.y = *reinterpret_cast<uint32_t*>(&p1);
-              u.z = *reinterpret_cast<uint32_t*>(&p2);
-              u.w = *reinterpret_cast<uint32_t*>(&p3);
-              op[j] = u;
+              u.x = pack2_bf16(v[8 * j + 0], v[8 * j + 1]);
+              u.y = pack2_bf16(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack2_bf16(v[8 * j + 4], v[8 * j + 5]);
+              u.w = pack2_bf16(v[8 * j + 6], v[8 * j + 7]);
+              st_shared_v4(srow + (uint32_t)((((h * 4 + j) ^ (lane & 7))) * 16), u);
             }
           } else {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow * ep.ldo + col0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) {
+              uint4 u;
+              u.x = __float_as_uint(v[4 * j]); u.y = __float_as_uint(v[4 * j + 1]);
+              u.z = __float_as_uint(v[4 * j + 2]); u.w = __float_as_uint(v[4 * j + 3]);
+              st_shared_v4(srow + (uint32_t)(((j ^ (lane & 7))) * 16), u);
+            }
           }
         }
+        __syncwarp();
+        // (c) read back row-contiguous: 8 lanes cover one row's 128 bytes -> full-line coalesced global stores
+        const bool col_ok = ep.out_bf16 ? (col0 + uu * 8 < N) : (col0 + uu * 4 < N);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + rr;
+          uint4 d = ld_shared_v4(stg_u + (uint32_t)(rl * 128 + ((uu ^ (rl & 7)) * 16)));
+          if (m_base + rl < M && col_ok) {
+            if (ep.out_bf16) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + obase[i] + col0 + uu * 8) = d;
+            } else {
+              if (ep.residual != nullptr) {
+                d.x = __float_as_uint(__uint_as_float(d.x) + res[i].x);
+                d.y = __float_as_uint(__uint_as_float(d.y) + res[i].y);
+                d.z = __float_as_uint(__uint_as_float(d.z) + res[i].z);
+                d.w = __float_as_uint(__uint_as_float(d.w) + res[i].w);
+              }
+              *reinterpret_cast<uint4*>(reinterpret_cast<float*>(ep.out) + obase[i] + col0 + uu * 4) = d;
+            }
+          }
+        }
+        __syncwarp();  // staging tile is reused by the next group
       }
       // accumulator buffer drained -> hand it back to the MMA warp
       tc_fence_before_sync();
@@ -296,6 +351,9 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   if (M <= 0 || N <= 0 || K <= 0) { *err = "GEMM: empty problem"; return 1; }
   if (N % 32 != 0) { *err = "GEMM: N must be a multiple of 32"; return 1; }
   if (ep.out == nullptr) { *err = "GEMM: null output"; return 1; }
+  if (ep.residual != nullptr && ep.out_bf16) { *err = "GEMM: a residual needs an fp32 output"; return 1; }
+  if (ep.out_bf16 ? (ep.ldo % 8 != 0) : (ep.ldo % 4 != 0)) { *err = "GEMM: output rows must be 16-byte aligned"; return 1; }
+  if (ep.residual != nullptr && ep.ldr % 4 != 0) { *err = "GEMM: residual rows must be 16-byte aligned"; return 1; }
   op->M = M; op->N = N; op->K = K; op->kind = kind; op->ep = ep;
   // Tile width: 256 for the big encoder GEMMs; 128 when that yields more CTAs than SMs can use otherwise
   const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
