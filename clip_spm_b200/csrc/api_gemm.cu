@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "kernels.cuh"
 #include "profile.cuh"
 
 namespace spm {
@@ -73,6 +74,25 @@ int spm_profile_end(double* flops4, double* ms4, int* count4) {
     flops4[t] += g_records[i].flops; ms4[t] += ms; count4[t] += 1;
   }
   g_used = 0;
+  return 0;
+}
+
+int spm_vit_attention(void* stream, const void* qkv, void* out, int n_frames, int use_mma_sync) {
+  static bool inited = false;
+  if (!inited) {
+    if (spm::k_vit_attention_init() != 0 || spm::k_vit_attention_tc_init() != 0) {
+      spm::set_error("spm_vit_attention: cudaFuncSetAttribute failed");
+      return 1;
+    }
+    inited = true;
+  }
+  int sms = 0;
+  SPM_TRY(spm::device_sm_count(&sms));
+  const int r = use_mma_sync
+                    ? spm::k_vit_attention((cudaStream_t)stream, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_frames)
+                    : spm::k_vit_attention_tc((cudaStream_t)stream, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out,
+                                              n_frames, sms);
+  if (r != 0) { spm::set_error("spm_vit_attention: launch failed"); return 1; }
   return 0;
 }
 

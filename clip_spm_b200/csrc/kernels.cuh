@@ -28,5 +28,9 @@ int k_layernorm(cudaStream_t st, const float* in, long long in_stride, int rows,
 //   qkv [F*197, 2304] bf16 (q | k | v, head h at columns h*64) -> out [F*197, 768] bf16
 int k_vit_attention(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames);
 int k_vit_attention_init();
+// same contract on tcgen05/TMEM (vit_attention_tc.cu): S and O accumulate in tensor memory, P feeds the second
+// MMA straight from TMEM.  `sms` = number of SMs (persistent grid).
+int k_vit_attention_tc(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, int sms);
+int k_vit_attention_tc_init();
 
 }  // namespace spm

@@ -94,6 +94,7 @@ struct spm_handle {
   int D = 512, HT = 768, HV = 256;
   int sms = 148;
   int frame_chunk = 256;
+  bool attn_mma = false;  // SPM_ATTN=mma selects the mma.sync attention kernel instead of the tcgen05 one
   bool weights_loaded = false, text_set = false;
   std::vector<void*> allocs;
   spm::VitW vit;
@@ -337,7 +338,10 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
     const VitLayerW& l = v.layer[i];
     SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln1_g, l.ln1_b, nullptr, 0, nullptr, h->xn, C));
     SPM_GEMM_RUN(pl->qkv[i]);
-    SPM_KERNEL(k_vit_attention(st, h->qkv, h->attn, F));
+    if (h->attn_mma)
+      SPM_KERNEL(k_vit_attention(st, h->qkv, h->attn, F));
+    else
+      SPM_KERNEL(k_vit_attention_tc(st, h->qkv, h->attn, F, h->sms));
     SPM_GEMM_RUN(pl->outp[i]);
     SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xn, C));
     SPM_GEMM_RUN(pl->fc[i]);
@@ -628,6 +632,8 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   const char* err = "";
   if (gemm_init(&err)) { set_error(err); return 1; }
   SPM_KERNEL(k_vit_attention_init());
+  SPM_KERNEL(k_vit_attention_tc_init());
+  if (const char* e = getenv("SPM_ATTN")) h->attn_mma = std::string(e) == "mma";
   SPM_KERNEL(k_seq_attention_init());
   SPM_KERNEL(k_otam_init());
   *out = h.release();

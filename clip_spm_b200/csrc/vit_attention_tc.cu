@@ -1,0 +1,335 @@
+// Frame-encoder self-attention on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//   softmax(Q K^T / sqrt(64)) V for 197 tokens x 64 dims per (frame, head): models/clip_fsar.py:626,638.
+//
+// Persistent CTA (one per SM, 12 warps) looping over (frame, head) items; two query tiles of 128 rows per item.
+//   warp 0      TMA producer : 3-D tensor map [col, token, frame] over the qkv buffer -> per item Q (2 x 128 rows),
+//                              K, V (208 rows; tokens >= 197 are zero-filled by TMA bounds), 128B-swizzled, 2 stages
+//   warp 1      MMA issuer   : S_b = Q_b K^T  (4 x tcgen05.mma 128x208x16, operands from smem descriptors)
+//                              O_b = P_b V    (13 x tcgen05.mma 128x64x16, A = P from TMEM, B = V as an MN-major
+//                                              smem operand -- no transpose of V is ever materialised)
+//   warp 2      TMEM allocator (2 buffers x 256 columns: S fp32 [0,208) -> P bf16 in place [0,104), O fp32 [128,192))
+//   warps 4-7   softmax group 0 (query tile 0), warps 8-11 softmax group 1 (query tile 1): one query row per thread
+//               (TMEM lane == row), so max / sum need no cross-thread reduction; two passes over the row
+//               (max, then exp2 + sum + bf16 pack written back to TMEM), then O is read, scaled by 1/sum and
+//               stored through a swizzled per-warp staging tile as full 128-byte rows.
+// The four roles are decoupled with mbarriers (kv_full/empty, s_full, p_ready, o_full, buf_free), so the tensor
+// pipe works on one query tile while the other tile's softmax runs on the MUFU/FMA pipes.
+#include <map>
+#include <tuple>
+
+#include "kernels.cuh"
+#include "profile.cuh"
+#include "ptx.cuh"
+
+namespace spm {
+
+namespace {
+constexpr int L = 197, KP = 208, HD = 64, HEADS = 12, C3 = 2304, C = 768;
+constexpr int QT_BYTES = 128 * 128;           // one query tile: 128 rows x 128 B
+constexpr int KV_BYTES = KP * 128;            // 26624
+constexpr int STAGE_BYTES = 2 * QT_BYTES + 2 * KV_BYTES;   // 86016 (multiple of 1024)
+constexpr int NSTAGE = 2;
+constexpr int STG_BYTES = 8 * 32 * 128;       // 8 softmax warps x (32 rows x 128 B)
+constexpr int BAR_OFF = NSTAGE * STAGE_BYTES + STG_BYTES;
+constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+constexpr int TMEM_COLS = 512, BUF_COLS = 256, O_COL = 128;
+constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(384, 1)
+vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                        __nv_bfloat16* __restrict__ out, int n_items) {
+  extern __shared__ uint8_t smem_raw_at[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_at) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* kv_full = bars;         // [2] TMA -> MMA
+  uint64_t* kv_empty = bars + 2;    // [2] MMA -> TMA
+  uint64_t* s_full = bars + 4;      // [2] MMA -> softmax group b
+  uint64_t* p_ready = bars + 6;     // [2] softmax group b -> MMA (4 warp arrivals)
+  uint64_t* o_full = bars + 8;      // [2] MMA -> softmax group b
+  uint64_t* buf_free = bars + 10;   // [2] softmax group b -> MMA (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&buf_free[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int frame = item / HEADS, head = item % HEADS;
+        uint8_t* s = smem + stage * STAGE_BYTES;
+        mbar_wait(&kv_empty[stage], ph ^ 1u);
+        mbar_expect_tx(&kv_full[stage], STAGE_BYTES);
+        tma_load_3d(s, &tmQ, &kv_full[stage], head * HD, 0, frame);
+        tma_load_3d(s + QT_BYTES, &tmQ, &kv_full[stage], head * HD, 128, frame);
+        tma_load_3d(s + 2 * QT_BYTES, &tmKV, &kv_full[stage], C + head * HD, 0, frame);
+        tma_load_3d(s + 2 * QT_BYTES + KV_BYTES, &tmKV, &kv_full[stage], 2 * C + head * HD, 0, frame);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_s = umma_idesc(1, 128, KP);                 // 128 x 208, both operands K-major
+      constexpr uint32_t idesc_pv = umma_idesc(1, 128, HD) | (1u << 16);   // 128 x 64, B (= V) MN-major
+      // O_b = P_b V for the query tile issued one step earlier (its softmax has had time to run)
+      auto issue_pv = [&](int b, int stage, uint32_t n, bool last_of_item) {
+        mbar_wait(&p_ready[b], n & 1u);
+        tc_fence_after_sync();
+        const uint32_t sv = smem_u32(smem + stage * STAGE_BYTES + 2 * QT_BYTES + KV_BYTES);
+        const uint64_t vdesc = umma_desc_mn_sw128(sv);
+        const uint32_t tb = tmem_base + (uint32_t)(b * BUF_COLS);
+#pragma unroll
+        for (int k = 0; k < KP / 16; ++k)  // 16 keys per MMA: 8 TMEM columns of packed bf16 pairs, 2048 B of V
+          mma_bf16_ts(tb + O_COL, tb + (uint32_t)(8 * k), vdesc + (uint64_t)(128 * k), idesc_pv, k != 0);
+        tc_commit(&o_full[b]);
+        if (last_of_item) tc_commit(&kv_empty[stage]);
+      };
+      int it = 0;
+      bool have_prev = false;
+      int pb = 0, pstage = 0;
+      uint32_t pn = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const uint32_t ph = (it >> 1) & 1, n = (uint32_t)it;
+        mbar_wait(&kv_full[stage], ph);
+        tc_fence_after_sync();
+        const uint32_t sq = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t kdesc = umma_desc_k_sw128(sq + 2 * QT_BYTES);
+        for (int b = 0; b < 2; ++b) {
+          mbar_wait(&buf_free[b], (n & 1u) ^ 1u);
+          tc_fence_after_sync();
+          const uint64_t qdesc = umma_desc_k_sw128(sq + b * QT_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_bf16_ss(tmem_base + (uint32_t)(b * BUF_COLS), qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0);
+          tc_commit(&s_full[b]);
+          if (have_prev) issue_pv(pb, pstage, pn, pb == 1);
+          have_prev = true; pb = b; pstage = stage; pn = n;
+        }
+      }
+      if (have_prev) issue_pv(pb, pstage, pn, true);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== softmax / output groups =====================
+    const int b = (warp - 4) >> 2;          // group == query tile == TMEM buffer
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int row0 = b * 128 + q * 32;      // first token of this warp
+    const bool active = row0 < L;           // warps whose 32 rows are all padding only keep the barriers moving
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BUF_COLS);
+    const uint32_t stg_u = smem_u32(smem + NSTAGE * STAGE_BYTES + (warp - 4) * (32 * 128));
+    const int rr = lane >> 3, uu = lane & 7;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t par = (uint32_t)it & 1u;
+      const int frame = item / HEADS, head = item % HEADS;
+      mbar_wait(&s_full[b], par);
+      tc_fence_after_sync();
+      float inv_l = 0.f;
+      if (active) {
+        // ---- pass 1: row maximum over the 197 real keys
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+        {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(taddr + 192u, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < L - 192; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+        const float mb = mx * SCALE_LOG2;
+        // ---- pass 2: p = 2^(s*scale - max*scale), row sum, bf16 pairs written back over S (P chunk c lands in
+        //      columns [16c, 16c+16) which only cover S chunks <= c, all consumed already)
+        float l = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), SCALE_LOG2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), SCALE_LOG2, -mb));
+            l += p0 + p1;
+            pk[j] = pack2(p0, p1);
+          }
+          tmem_st_32x32b_x16(taddr + (uint32_t)(c * 16), pk);
+        }
+        {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(taddr + 192u, r);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k0 = 192 + 2 * j;
+            const float p0 = k0 < L ? ex2_approx(fmaf(__uint_as_float(r[2 * j]), SCALE_LOG2, -mb)) : 0.f;
+            const float p1 = k0 + 1 < L ? ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), SCALE_LOG2, -mb)) : 0.f;
+            l += p0 + p1;
+            pk[j] = pack2(p0, p1);
+          }
+          tmem_st_32x32b_x8(taddr + 96u, pk);
+        }
+        tmem_st_wait();
+        inv_l = 1.f / l;
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[b]);
+      // ---- O = P V is ready: scale, bf16, coalesced store of the warp's 32 token rows (128 B each)
+      mbar_wait(&o_full[b], par);
+      tc_fence_after_sync();
+      if (active) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(O_COL + h * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack2(__uint_as_float(r[8 * j + 0]) * inv_l, __uint_as_float(r[8 * j + 1]) * inv_l);
+            u.y = pack2(__uint_as_float(r[8 * j + 2]) * inv_l, __uint_as_float(r[8 * j + 3]) * inv_l);
+            u.z = pack2(__uint_as_float(r[8 * j + 4]) * inv_l, __uint_as_float(r[8 * j + 5]) * inv_l);
+            u.w = pack2(__uint_as_float(r[8 * j + 6]) * inv_l, __uint_as_float(r[8 * j + 7]) * inv_l);
+            const uint32_t a = stg_u + (uint32_t)(lane * 128 + (((h * 4 + j) ^ (lane & 7)) * 16));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                         : "memory");
+          }
+        }
+      }
+      // the accumulator buffer can be overwritten by the next item's S as soon as O has left TMEM
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&buf_free[b]);
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + rr;
+          const int tok = row0 + rl;
+          uint4 d;
+          const uint32_t a = stg_u + (uint32_t)(rl * 128 + ((uu ^ (rl & 7)) * 16));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "r"(a)
+                       : "memory");
+          if (tok < L)
+            *reinterpret_cast<uint4*>(out + ((long long)frame * L + tok) * C + head * HD + uu * 8) = d;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+namespace {
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+PFN_tmapEncodeTiled get_encode_at() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  return fn;
+}
+struct AttnMaps {
+  CUtensorMap q, kv;
+};
+// qkv [F*197, 2304] bf16 viewed as [frame][token][col]: a box never crosses a frame, tokens >= 197 read as zero
+int make_maps(const __nv_bfloat16* qkv, int F, AttnMaps* m) {
+  PFN_tmapEncodeTiled enc = get_encode_at();
+  if (!enc) return -3;
+  cuuint64_t gdim[3] = {(cuuint64_t)C3, (cuuint64_t)L, (cuuint64_t)F};
+  cuuint64_t gstride[2] = {(cuuint64_t)C3 * 2, (cuuint64_t)L * C3 * 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint32_t boxq[3] = {HD, 128, 1}, boxkv[3] = {HD, KP, 1};
+  if (enc(&m->q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(qkv), gdim, gstride, boxq, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return -3;
+  if (enc(&m->kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(qkv), gdim, gstride, boxkv, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return -3;
+  return 0;
+}
+}  // namespace
+
+int k_vit_attention_tc_init() {
+  return (int)cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
+
+int k_vit_attention_tc(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, int sms) {
+  if (n_frames <= 0) return 0;
+  static std::map<std::tuple<const void*, int>, AttnMaps> cache;  // maps depend on (buffer, frame count) only
+  auto key = std::make_tuple((const void*)qkv, n_frames);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    AttnMaps m;
+    const int r = make_maps(qkv, n_frames, &m);
+    if (r != 0) return r;
+    it = cache.emplace(key, m).first;
+  }
+  const int n_items = n_frames * HEADS;
+  const int grid = n_items < sms ? n_items : sms;
+  vit_attention_tc_kernel<<<grid, 384, SMEM_BYTES, st>>>(it->second.q, it->second.kv, out, n_items);
+  cudaError_t e = cudaGetLastError();
+  count_launch();
+  return (int)e;
+}
+
+}  // namespace spm

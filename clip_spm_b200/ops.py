@@ -60,3 +60,13 @@ def otam_distance(support, target, single_direct=False, alpha=1.0, beta=0.0, out
     _lib.check(lib.spm_otam_distance(_stream(), P, W, Q, T, D, _ptr(support), _ptr(target), int(single_direct),
                                      float(alpha), float(beta), _ptr(out)))
     return out
+
+
+def vit_attention(qkv, n_frames, impl="tcgen05"):
+    """softmax(q k^T / 8) v per (frame, head) (models/clip_fsar.py:626,638): qkv [F*197, 2304] bf16 -> [F*197, 768]."""
+    lib = _lib.load()
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (n_frames * 197, 2304)
+    out = torch.empty(n_frames * 197, 768, device=qkv.device, dtype=torch.bfloat16)
+    _lib.check(lib.spm_vit_attention(_stream(), _ptr(qkv), _ptr(out), n_frames, 1 if impl == "mma" else 0))
+    return out

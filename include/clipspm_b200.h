@@ -115,6 +115,11 @@ int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const floa
 int spm_otam_distance(void* stream, int n_pairs, int W, int Q, int T, int D, const float* support,
                       const float* target, int single_direct, float alpha, float beta, float* out);
 
+/* Frame-encoder self-attention stage (models/clip_fsar.py:626,638): qkv [F*197, 2304] bf16 (q | k | v, head h at
+ * columns h*64 of each third) -> out [F*197, 768] bf16.  use_mma_sync = 0: tcgen05/TMEM kernel (product path),
+ * 1: the mma.sync kernel kept as a cross-check. */
+int spm_vit_attention(void* stream, const void* qkv, void* out, int n_frames, int use_mma_sync);
+
 /* out[orow(m), n] = act(sum_k A[m,k] B[n,k] + bias[n]) (+ residual[rrow(m), n]); see csrc/gemm.cuh.
  * kind: 0 = bf16 operands, 1 = tf32 (fp32 operands).  act: 0 none, 1 QuickGELU, 2 GELU(erf), 3 LeakyReLU, 4 sigmoid, 5 ReLU */
 int spm_gemm(void* stream, int kind, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,

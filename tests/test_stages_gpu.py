@@ -160,3 +160,18 @@ def test_eval_host_matches_device_path():
         assert torch.allclose(host["logits"][e], out["logits"][0].cpu(), atol=1e-5)
         loss, acc = net.evaluate(ep)
         assert abs(float(host["loss"][e]) - float(loss)) < 1e-5 and float(host["acc"][e]) == float(acc)
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+@pytest.mark.parametrize("F,scale", [(1, 1.0), (3, 1.0), (40, 3.0), (160, 1.0)])
+def test_vit_attention_matches_torch(impl, F, scale):
+    """both attention kernels against fp32 softmax attention on the same bf16 q, k, v"""
+    from clip_spm_b200 import ops
+    g = torch.Generator().manual_seed(F)
+    qkv = (torch.randn(F * 197, 2304, generator=g) * scale).cuda().bfloat16()
+    out = ops.vit_attention(qkv, F, impl)
+    x = qkv.float().view(F, 197, 3, 12, 64).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(x[0] @ x[1].transpose(-1, -2) / 8.0, dim=-1)
+    ref = (att @ x[2]).permute(0, 2, 1, 3).reshape(F * 197, 768)
+    err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-2, (impl, F, err)
