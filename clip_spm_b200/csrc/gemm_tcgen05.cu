@@ -3,11 +3,13 @@
 //   out[orow(m), n] = act( sum_k A[m,k] * B[n,k] + bias[n] ) (+ residual[rrow(m), n])
 //
 // A [M,K] and B [N,K] are K-contiguous (a torch.nn.Linear weight [out,in] is already "B").
-// Roles inside one 256-thread CTA (one CTA per SM, grid = min(#tiles, #SMs), static round-robin tiles):
+// Roles inside one 384-thread CTA (one CTA per SM, grid = min(#tiles, #SMs), static round-robin tiles):
 //   warp 0 (1 lane)  TMA producer: 128B-swizzled [128 x 128B] A box + [BN x 128B] B box per stage
 //   warp 1 (1 lane)  MMA issuer  : 4 x tcgen05.mma (128 x BN x 32 bytes of K) per stage, fp32 accum in TMEM
 //   warp 2           TMEM allocator (2 accumulator buffers of BN columns -> epilogue overlaps the next tile)
-//   warps 4..7       epilogue    : tcgen05.ld (one accumulator row per thread) -> bias/act/residual -> global
+//   warps 4..11      epilogue    : two warps per TMEM lane quarter, alternating 128-byte column groups:
+//                                  tcgen05.ld (one accumulator row per thread) -> bias/act -> swizzled smem staging
+//                                  -> row-contiguous read-back (+ prefetched residual) -> full-line global stores
 //
 // This replaces the cuBLASLt / cuDNN calls the reference makes through ATen for
 // models/clip_fsar.py:626-632,673,687 (ViT linears, patch-embed conv, projection) and
@@ -35,7 +37,8 @@ struct GemmTile {
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int STG_BYTES_PER_WARP = 32 * 128;  // epilogue staging tile of one warp
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 4 * STG_BYTES_PER_WARP + 1024;  // +1024: alignment slack
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024;  // +1024: alignment slack
 };
 
 __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
@@ -51,9 +54,17 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
+// x * sigmoid(1.702 x) = x * (0.5 + 0.5 * tanh(0.851 x)): one MUFU op (tanh.approx, rel. error ~2^-11, far below
+// the bf16 rounding of the stored activation) instead of ex2 + rcp
+__device__ __forceinline__ float quick_gelu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+
 __device__ __forceinline__ float apply_act(float x, int act, float slope) {
   switch (act) {
-    case ACT_QUICKGELU: return __fdividef(x, 1.f + __expf(-1.702f * x));
+    case ACT_QUICKGELU: return quick_gelu_fast(x);
     case ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
     case ACT_LEAKY: return x > 0.f ? x : slope * x;
     case ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-x));
@@ -62,8 +73,18 @@ __device__ __forceinline__ float apply_act(float x, int act, float slope) {
   }
 }
 
+__device__ __forceinline__ long long out_row(const GemmEpilogue& ep, int m) {
+  if (ep.out_row_group > 0)
+    return (long long)(m / ep.out_row_group) * ep.out_group_stride + (m % ep.out_row_group) + ep.out_row_off;
+  return m;
+}
+__device__ __forceinline__ long long res_row(const GemmEpilogue& ep, int m) {
+  if (ep.res_row_mod > 0) return (m % ep.res_row_mod) + ep.res_row_off;
+  return out_row(ep, m);
+}
+
 template <int BN, int KIND>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmArgs args) {
   using T = GemmTile<BN, KIND>;
@@ -94,7 +115,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], T::EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -166,7 +187,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const GemmEpilogue& ep = args.ep;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     // warp-private staging tile: 32 rows x 128 B, 16-byte units XOR-swizzled by (row & 7) -> conflict-free both ways
-    const uint32_t stg_u = smem_u32(smem + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES + q * T::STG_BYTES_PER_WARP);
+    const int half = (warp - 4) >> 2;  // which of the two warps of this lane quarter: takes column groups g % 2 == half
+    const uint32_t stg_u = smem_u32(smem + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES + (warp - 4) * T::STG_BYTES_PER_WARP);
     const int rr = lane >> 3, uu = lane & 7;  // read-back mapping: row i*4 + rr, 16-byte unit uu
     const int halves = ep.out_bf16 ? 2 : 1;   // 32-column accumulator chunks per 128-byte output group
     int t = 0;
@@ -175,24 +197,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t acc_phase = (t >> 1) & 1;
       const int m_base = (tile / num_n) * T::BM + q * 32;
       const int n0 = (tile % num_n) * BN;
-      // global row offsets (in elements) of the 8 rows this lane stores: row i*4 + rr of the warp's 32
-      long long obase[8], rbase[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m_base + i * 4 + rr;
-        long long orow = m;
-        if (ep.out_row_group > 0)
-          orow = (long long)(m / ep.out_row_group) * ep.out_group_stride + (m % ep.out_row_group) + ep.out_row_off;
-        long long rrow = orow;
-        if (ep.res_row_mod > 0) rrow = (m % ep.res_row_mod) + ep.res_row_off;
-        obase[i] = orow * ep.ldo;
-        rbase[i] = rrow * ep.ldr;
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int g = 0; g < BN / 32; g += halves) {
+      for (int g = half * halves; g < BN / 32; g += 2 * halves) {
         const int col0 = n0 + g * 32;  // first output column of this 128-byte store group
         if (col0 >= N) break;          // warp-uniform
         // (a) residual tile: coalesced 16-byte loads, issued before the TMEM round trip so their latency overlaps it
@@ -201,7 +210,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m_base + i * 4 + rr < M) res[i] = *reinterpret_cast<const float4*>(ep.residual + rbase[i] + col0 + uu * 4);
+            const int m = m_base + i * 4 + rr;
+            if (m < M) res[i] = *reinterpret_cast<const float4*>(ep.residual + res_row(ep, m) * ep.ldr + col0 + uu * 4);
           }
         }
         // (b) accumulator row (one per thread) -> bias / activation -> swizzled staging tile [32 rows][128 B]
@@ -225,7 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (ep.act == ACT_QUICKGELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-1.702f * v[j]));
+            for (int j = 0; j < 32; ++j) v[j] = quick_gelu_fast(v[j]);
           } else if (ep.act != ACT_NONE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act, ep.slope);
@@ -259,8 +269,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int rl = i * 4 + rr;
           uint4 d = ld_shared_v4(stg_u + (uint32_t)(rl * 128 + ((uu ^ (rl & 7)) * 16)));
           if (m_base + rl < M && col_ok) {
+            const long long obase = out_row(ep, m_base + rl) * ep.ldo;
             if (ep.out_bf16) {
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + obase[i] + col0 + uu * 8) = d;
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + obase + col0 + uu * 8) = d;
             } else {
               if (ep.residual != nullptr) {
                 d.x = __float_as_uint(__uint_as_float(d.x) + res[i].x);
@@ -268,7 +279,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 d.z = __float_as_uint(__uint_as_float(d.z) + res[i].z);
                 d.w = __float_as_uint(__uint_as_float(d.w) + res[i].w);
               }
-              *reinterpret_cast<uint4*>(reinterpret_cast<float*>(ep.out) + obase[i] + col0 + uu * 4) = d;
+              *reinterpret_cast<uint4*>(reinterpret_cast<float*>(ep.out) + obase + col0 + uu * 4) = d;
             }
           }
         }
@@ -372,7 +383,7 @@ int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
   const bool prof = profile_gemm_begin(stream, op->kind * 2 + (op->bn == 256 ? 1 : 0),
                                        2.0 * (double)op->M * (double)op->N * (double)op->K, &slot);
 #define SPM_LAUNCH(BN, KIND)                                                                                 \
-  gemm_tcgen05_kernel<BN, KIND><<<op->grid, 256, GemmTile<BN, KIND>::SMEM_BYTES, stream>>>(op->ta, op->tb, a)
+  gemm_tcgen05_kernel<BN, KIND><<<op->grid, 384, GemmTile<BN, KIND>::SMEM_BYTES, stream>>>(op->ta, op->tb, a)
   if (op->kind == GEMM_BF16) {
     if (op->bn == 256) SPM_LAUNCH(256, GEMM_BF16); else SPM_LAUNCH(128, GEMM_BF16);
   } else {
