@@ -15,6 +15,8 @@ struct GemmEpilogue {
   const float* bias = nullptr;      // [N] fp32 or null
   const float* residual = nullptr;  // fp32, leading dim ldr, added AFTER the activation
   int ldr = 0;
+  const void* residual_bf16 = nullptr;  // bf16 residual (needs a bf16 output), same row mapping / ldr
+  int relu_after_residual = 0;          // out = relu(act(acc + bias) + residual)  (ResNet bottleneck tail)
   int res_row_mod = 0;    // 0: rrow = orow ; >0: rrow = (m % res_row_mod) + res_row_off  (positional table)
   int res_row_off = 0;
   // 0: orow = m ; >0: orow = (m / out_row_group) * out_group_stride + (m % out_row_group) + out_row_off

@@ -206,7 +206,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (col0 >= N) break;          // warp-uniform
         // (a) residual tile: coalesced 16-byte loads, issued before the TMEM round trip so their latency overlaps it
         float4 res[8];
-        if (ep.residual != nullptr) {
+        if (ep.residual_bf16 != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int m = m_base + i * 4 + rr;
+            if (m < M && col0 + uu * 8 < N)
+              res[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const __nv_bfloat16*>(ep.residual_bf16) +
+                                                        res_row(ep, m) * ep.ldr + col0 + uu * 8);
+          }
+        } else if (ep.residual != nullptr) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -271,6 +280,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (m_base + rl < M && col_ok) {
             const long long obase = out_row(ep, m_base + rl) * ep.ldo;
             if (ep.out_bf16) {
+              if (ep.residual_bf16 != nullptr) {
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[i]);
+                uint32_t* dw = reinterpret_cast<uint32_t*>(&d);
+#pragma unroll
+                for (int w2 = 0; w2 < 4; ++w2) {
+                  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[w2]));
+                  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[w2]));
+                  float lo = a.x + b.x, hi = a.y + b.y;
+                  if (ep.relu_after_residual) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                  dw[w2] = pack2_bf16(lo, hi);
+                }
+              }
               *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + obase + col0 + uu * 8) = d;
             } else {
               if (ep.residual != nullptr) {
@@ -362,7 +383,11 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   if (M <= 0 || N <= 0 || K <= 0) { *err = "GEMM: empty problem"; return 1; }
   if (N % 32 != 0) { *err = "GEMM: N must be a multiple of 32"; return 1; }
   if (ep.out == nullptr) { *err = "GEMM: null output"; return 1; }
-  if (ep.residual != nullptr && ep.out_bf16) { *err = "GEMM: a residual needs an fp32 output"; return 1; }
+  if (ep.residual != nullptr && ep.out_bf16) { *err = "GEMM: an fp32 residual needs an fp32 output"; return 1; }
+  if (ep.residual_bf16 != nullptr && (!ep.out_bf16 || ep.ldr % 8 != 0)) {
+    *err = "GEMM: a bf16 residual needs a bf16 output and 16-byte aligned rows";
+    return 1;
+  }
   if (ep.out_bf16 ? (ep.ldo % 8 != 0) : (ep.ldo % 4 != 0)) { *err = "GEMM: output rows must be 16-byte aligned"; return 1; }
   if (ep.residual != nullptr && ep.ldr % 4 != 0) { *err = "GEMM: residual rows must be 16-byte aligned"; return 1; }
   op->M = M; op->N = N; op->K = K; op->kind = kind; op->ep = ep;

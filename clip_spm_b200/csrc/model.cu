@@ -77,6 +77,8 @@ struct HeadW {
 
 struct VitPlan {
   GemmOp patch, qkv[VIT_LAYERS], outp[VIT_LAYERS], fc[VIT_LAYERS], proj[VIT_LAYERS], fin;
+  // last block restricted to the class-token rows (the only rows ln_post reads, clip_fsar.py:684)
+  GemmOp outp_cls, fc_cls, proj_cls;
 };
 struct CtxPlan {
   GemmOp qkv, outp, ff0, ff3;
@@ -94,6 +96,7 @@ struct spm_handle {
   int D = 512, HT = 768, HV = 256;
   int sms = 148;
   int frame_chunk = 256;
+  bool prune_last = true;  // SPM_PRUNE_LAST=0 runs the last block on all tokens (same result, more work)
   bool attn_mma = false;  // SPM_ATTN=mma selects the mma.sync attention kernel instead of the tcgen05 one
   bool weights_loaded = false, text_set = false;
   std::vector<void*> allocs;
@@ -105,6 +108,8 @@ struct spm_handle {
   // encoder workspace (sized for frame_chunk frames)
   __nv_bfloat16 *patches = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hid = nullptr, *cls = nullptr;
   float* x = nullptr;
+  float* xc = nullptr;          // [frame_chunk, 768] class-token rows of the residual stream in the last block
+  __nv_bfloat16* xnc = nullptr; // their LayerNorm output
   float* feats = nullptr;  // [max frames per call, D]
   long long feats_cap = 0;
   std::map<int, std::unique_ptr<spm::VitPlan>> vit_plans;
@@ -284,6 +289,8 @@ int ensure_vit_workspace(spm_handle* h) {
   SPM_TRY(dalloc_t(h, &h->attn, M * VIT_C));
   SPM_TRY(dalloc_t(h, &h->hid, M * 4 * VIT_C));
   SPM_TRY(dalloc_t(h, &h->cls, (long long)h->frame_chunk * VIT_C));
+  SPM_TRY(dalloc_t(h, &h->xc, (long long)h->frame_chunk * VIT_C));
+  SPM_TRY(dalloc_t(h, &h->xnc, (long long)h->frame_chunk * VIT_C));
   return 0;
 }
 
@@ -316,6 +323,20 @@ int get_vit_plan(spm_handle* h, int F, VitPlan** out) {
     SPM_TRY(plan_gemm(&pl->proj[i], GEMM_BF16, h->hid, 4 * C, l.proj_w, 4 * C, M, C, 4 * C, e4, h->sms));
   }
   {
+    // Last block, class-token rows only: attention output / residual rows are taken with a row stride of 197 tokens
+    const VitLayerW& l = v.layer[VIT_LAYERS - 1];
+    const long long LC = (long long)VIT_L * C;
+    GemmEpilogue e2;
+    e2.bias = l.out_b; e2.residual = h->x; e2.ldr = (int)LC; e2.out = h->xc; e2.ldo = C;
+    SPM_TRY(plan_gemm(&pl->outp_cls, GEMM_BF16, h->attn, LC, l.out_w, C, F, C, C, e2, h->sms));
+    GemmEpilogue e3;
+    e3.bias = l.fc_b; e3.act = ACT_QUICKGELU; e3.out = h->hid; e3.ldo = 4 * C; e3.out_bf16 = 1;
+    SPM_TRY(plan_gemm(&pl->fc_cls, GEMM_BF16, h->xnc, C, l.fc_w, C, F, 4 * C, C, e3, h->sms));
+    GemmEpilogue e4;
+    e4.bias = l.proj_b; e4.residual = h->xc; e4.ldr = C; e4.out = h->xc; e4.ldo = C;
+    SPM_TRY(plan_gemm(&pl->proj_cls, GEMM_BF16, h->hid, 4 * C, l.proj_w, 4 * C, F, C, 4 * C, e4, h->sms));
+  }
+  {
     GemmEpilogue ep;
     ep.out = h->x;  // patched per call
     ep.ldo = VIT_OUT;
@@ -342,6 +363,18 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
       SPM_KERNEL(k_vit_attention(st, h->qkv, h->attn, F));
     else
       SPM_KERNEL(k_vit_attention_tc(st, h->qkv, h->attn, F, h->sms));
+    if (i == VIT_LAYERS - 1 && h->prune_last) {
+      // only x[:, 0, :] is read after the last block: run its out-proj / MLP on the F class-token rows
+      SPM_GEMM_RUN(pl->outp_cls);
+      SPM_KERNEL(k_layernorm(st, h->xc, C, F, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xnc, C));
+      SPM_GEMM_RUN(pl->fc_cls);
+      SPM_GEMM_RUN(pl->proj_cls);
+      SPM_KERNEL(k_layernorm(st, h->xc, C, F, C, v.ln_post_g, v.ln_post_b, nullptr, 0, nullptr, h->cls, C));
+      GemmOp fin = pl->fin;
+      fin.ep.out = feats_out;
+      SPM_GEMM_RUN(fin);
+      return 0;
+    }
     SPM_GEMM_RUN(pl->outp[i]);
     SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xn, C));
     SPM_GEMM_RUN(pl->fc[i]);
@@ -634,6 +667,7 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   SPM_KERNEL(k_vit_attention_init());
   SPM_KERNEL(k_vit_attention_tc_init());
   if (const char* e = getenv("SPM_ATTN")) h->attn_mma = std::string(e) == "mma";
+  if (const char* e = getenv("SPM_PRUNE_LAST")) h->prune_last = atoi(e) != 0;
   SPM_KERNEL(k_seq_attention_init());
   SPM_KERNEL(k_otam_init());
   *out = h.release();

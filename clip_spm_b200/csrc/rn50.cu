@@ -1,16 +1,484 @@
-// CLIP ModifiedResNet-50 frame encoder -- not built yet in this round.
-#include "rn50.cuh"
+// CLIP ModifiedResNet-50 frame encoder (models/clip_fsar.py:502-608 Bottleneck / ModifiedResNet, :396-500
+// AttentionPool2d) for sm_100a.
+//
+// Activations are NHWC bf16, so every convolution is a GEMM on the tcgen05 kernel of gemm_tcgen05.cu:
+//   1x1 conv            A = the activation matrix [F*H*W, Cin] as it lies in memory, B = folded weight [Cout, Cin]
+//   3x3 conv (pad 1)    A = im2col [F*H*W, 9*Cin] (tap-major, channel-minor), B = folded weight [Cout, 9*Cin]
+//   stem conv1 (s=2)    A = im2col straight from the fp32 NCHW image, K = 27 padded to 32
+// BatchNorm (eval, running statistics) is folded into the weights and a per-channel bias at load time; ReLU, the
+// bottleneck's residual add and the final ReLU run in the GEMM epilogue.  AvgPool2d(2) (stem, anti-aliased strides,
+// downsample branches) is a vectorised NHWC kernel.  The attention pool uses only the mean-token query
+// (clip_fsar.py:481-499): k/v projections as one fused GEMM over 50 tokens, q projection on the F mean tokens, a
+// one-warp-per-(frame, head) softmax, then c_proj.
+// This first version materialises the im2col matrices (HBM traffic ~2x the algorithmic minimum); a TMA-im2col
+// implicit GEMM is the follow-up.
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_bf16.h>
+
 #include "api_common.cuh"
+#include "gemm.cuh"
+#include "profile.cuh"
+#include "rn50.cuh"
 
 namespace spm {
-struct Rn50 { int unused; };
-int rn50_create(Rn50** out, cudaStream_t, int, const WeightGetter&) {
-  *out = new Rn50();  // head-only use (D = 1024) works; encoding frames reports the missing tower
+
+namespace {
+constexpr int RN_CHUNK = 64;
+constexpr int EMB = 2048, HEADS = 32, HD = 64, OUT_DIM = 1024, NTOK = 50;
+constexpr long long FRAME_ELEMS = 3LL * 224 * 224;
+constexpr long long SCRATCH_PER_FRAME = 12544LL * 64;   // largest activation: 112x112x64 == 56x56x256
+constexpr long long COL_PER_FRAME = 12544LL * 288;      // largest im2col: 112x112x(9*32) == 56x56x(9*128)
+
+#define RN_LAUNCH_CHECK()                                                         \
+  do {                                                                            \
+    cudaError_t _e = cudaGetLastError();                                          \
+    if (_e != cudaSuccess) { set_error(std::string("rn50 kernel launch: ") + cudaGetErrorString(_e)); return 1; } \
+    count_launch();                                                               \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// load-time folding:  w [Cout, Cin, kh, kw] fp32 + BN -> wout [Cout, Kpad] bf16 (k = (ky*kw + kx)*Cin + c), bias
+// ---------------------------------------------------------------------------------------------------------
+__global__ void fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b,
+                                 const float* __restrict__ mean, const float* __restrict__ var, int Cout, int Cin,
+                                 int kh, int kw, int Kpad, __nv_bfloat16* __restrict__ wout, float* __restrict__ bias) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * Kpad) return;
+  const int o = (int)(i / Kpad), k = (int)(i % Kpad);
+  const float scale = g[o] * rsqrtf(var[o] + 1e-5f);
+  float v = 0.f;
+  if (k < kh * kw * Cin) {
+    const int c = k % Cin, tap = k / Cin, ky = tap / kw, kx = tap % kw;
+    v = w[(((long long)o * Cin + c) * kh + ky) * kw + kx] * scale;
+  }
+  wout[i] = __float2bfloat16_rn(v);
+  if (k == 0) bias[o] = b[o] - mean[o] * scale;
+}
+__global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// activation-side kernels (NHWC bf16, 8 channels = 16 bytes per thread)
+// ---------------------------------------------------------------------------------------------------------
+// stem conv1: 3x3, stride 2, pad 1 on the fp32 NCHW image -> [F*112*112, 32] (27 taps, 5 zero columns)
+__global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, long long rows) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int ox = (int)(r % 112), oy = (int)((r / 112) % 112);
+  const long long f = r / (112 * 112);
+  const float* base = img + f * FRAME_ELEMS;
+  __align__(16) __nv_bfloat16 v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = __float2bfloat16_rn(0.f);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+      if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          v[(ky * 3 + kx) * 3 + c] = __float2bfloat16_rn(__ldg(base + ((long long)c * 224 + iy) * 224 + ix));
+      }
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + r * 32);
+  const uint4* s = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = s[j];
+}
+
+// 3x3, stride 1, pad 1: in [F,H,W,C] -> out [F*H*W, 9*C], column = tap*C + c
+__global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int H, int W,
+                                 int C, long long n_units) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_units) return;
+  const int c8 = C / 8;
+  const int cu = (int)(i % c8);
+  const int tap = (int)((i / c8) % 9);
+  const long long row = i / (9LL * c8);
+  const int x = (int)(row % W), y = (int)((row / W) % H);
+  const long long f = row / ((long long)W * H);
+  const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+    v = __ldg(reinterpret_cast<const uint4*>(in + ((f * H + iy) * W + ix) * C) + cu);
+  reinterpret_cast<uint4*>(out)[i] = v;
+}
+
+__device__ __forceinline__ float2 bf2(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ uint32_t pk(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+// AvgPool2d(2): [F,H,W,C] -> [F,H/2,W/2,C]
+__global__ void avgpool2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int H, int W,
+                                int C, long long n_units) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_units) return;
+  const int c8 = C / 8, Ho = H / 2, Wo = W / 2;
+  const int cu = (int)(i % c8);
+  const long long orow = i / c8;
+  const int ox = (int)(orow % Wo), oy = (int)((orow / Wo) % Ho);
+  const long long f = orow / ((long long)Wo * Ho);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((f * H + 2 * oy + dy) * W + 2 * ox + dx) * C) + cu);
+      const float2 a = bf2(v.x), b = bf2(v.y), c = bf2(v.z), d = bf2(v.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+  uint4 o;
+  o.x = pk(acc[0] * 0.25f, acc[1] * 0.25f); o.y = pk(acc[2] * 0.25f, acc[3] * 0.25f);
+  o.z = pk(acc[4] * 0.25f, acc[5] * 0.25f); o.w = pk(acc[6] * 0.25f, acc[7] * 0.25f);
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
+// attention-pool tokens (clip_fsar.py:407-410): tok[f,0] = mean_s x[f,s] + pos[0]; tok[f,1+s] = x[f,s] + pos[1+s]
+__global__ void attnpool_tokens_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ pos,
+                                       __nv_bfloat16* __restrict__ tok) {
+  const int f = blockIdx.x;
+  for (int c = threadIdx.x; c < EMB; c += blockDim.x) {
+    float mean = 0.f;
+    for (int s = 0; s < 49; ++s) {
+      const float v = __bfloat162float(x[((long long)f * 49 + s) * EMB + c]);
+      mean += v;
+      tok[((long long)f * NTOK + 1 + s) * EMB + c] = __float2bfloat16_rn(v + pos[(1 + s) * EMB + c]);
+    }
+    tok[(long long)f * NTOK * EMB + c] = __float2bfloat16_rn(mean * (1.f / 49.f) + pos[c]);
+  }
+}
+
+// one warp per (frame, head): q [F, 2048], kv [F*50, 4096] (k | v) -> o [F, 2048]
+__global__ void attnpool_attend_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
+                                       __nv_bfloat16* __restrict__ o, int n_pairs) {
+  const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pair >= n_pairs) return;
+  const int f = pair / HEADS, hh = pair % HEADS;
+  const __nv_bfloat16* qp = q + (long long)f * EMB + hh * HD;
+  float s[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int key = lane + 32 * r;
+    if (key < NTOK) {
+      const __nv_bfloat16* kp = kv + ((long long)f * NTOK + key) * (2 * EMB) + hh * HD;
+      float acc = 0.f;
+      for (int d = 0; d < HD; ++d) acc += __bfloat162float(qp[d]) * __bfloat162float(kp[d]);
+      s[r] = acc * 0.125f;
+    }
+  }
+  float m = fmaxf(s[0], s[1]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  const float p0 = expf(s[0] - m), p1 = (lane + 32 < NTOK) ? expf(s[1] - m) : 0.f;
+  float l = p0 + p1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+  float a0 = 0.f, a1 = 0.f;
+  for (int key = 0; key < NTOK; ++key) {
+    const float p = __shfl_sync(0xffffffffu, key < 32 ? p0 : p1, key & 31);
+    const __nv_bfloat16* vp = kv + ((long long)f * NTOK + key) * (2 * EMB) + EMB + hh * HD;
+    a0 += p * __bfloat162float(vp[lane]);
+    a1 += p * __bfloat162float(vp[lane + 32]);
+  }
+  const float inv = 1.f / l;
+  o[(long long)f * EMB + hh * HD + lane] = __float2bfloat16_rn(a0 * inv);
+  o[(long long)f * EMB + hh * HD + lane + 32] = __float2bfloat16_rn(a1 * inv);
+}
+
+struct Conv {
+  __nv_bfloat16* w = nullptr;
+  float* bias = nullptr;
+  int cout = 0, cin = 0, ksz = 1, kpad = 0;
+};
+struct Block {
+  Conv c1, c2, c3, down;
+  int inpl, planes, stride;
+  bool has_down;
+};
+struct Plan {
+  std::vector<GemmOp> ops;
+};
+}  // namespace
+
+struct Rn50 {
+  int sms = 148;
+  std::vector<void*> allocs;
+  Conv stem[3];
+  std::vector<Block> blocks;
+  float* pos = nullptr;
+  __nv_bfloat16 *q_w = nullptr, *kv_w = nullptr, *c_w = nullptr;
+  float *q_b = nullptr, *kv_b = nullptr, *c_b = nullptr;
+  // workspace (RN_CHUNK frames)
+  __nv_bfloat16 *xa = nullptr, *xb = nullptr, *t1 = nullptr, *t2 = nullptr, *t2p = nullptr, *xd = nullptr,
+                *idn = nullptr, *col = nullptr, *tok = nullptr, *qbuf = nullptr, *kvbuf = nullptr, *obuf = nullptr;
+  std::map<int, std::unique_ptr<Plan>> plans;
+};
+
+namespace {
+template <class T>
+int ralloc(Rn50* r, T** p, long long n) {
+  SPM_CUDA(cudaMalloc(reinterpret_cast<void**>(p), (size_t)std::max<long long>(n, 4) * sizeof(T)));
+  r->allocs.push_back(*p);
   return 0;
 }
-int rn50_encode(Rn50*, cudaStream_t, const float*, int, float*) {
-  set_error("the RN50 frame encoder is not implemented yet (ViT-B/16 only)");
-  return 1;
+
+int load_conv(Rn50* r, cudaStream_t st, const WeightGetter& get, const std::string& wname, const std::string& bn,
+              int cout, int cin, int ksz, Conv* c) {
+  const float *w, *g, *b, *mean, *var;
+  SPM_TRY(get(wname, (long long)cout * cin * ksz * ksz, &w));
+  SPM_TRY(get(bn + "weight", cout, &g));
+  SPM_TRY(get(bn + "bias", cout, &b));
+  SPM_TRY(get(bn + "running_mean", cout, &mean));
+  SPM_TRY(get(bn + "running_var", cout, &var));
+  c->cout = cout; c->cin = cin; c->ksz = ksz;
+  c->kpad = (cin * ksz * ksz + 31) / 32 * 32;
+  SPM_TRY(ralloc(r, &c->w, (long long)cout * c->kpad));
+  SPM_TRY(ralloc(r, &c->bias, cout));
+  const long long n = (long long)cout * c->kpad;
+  fold_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, b, mean, var, cout, cin, ksz, ksz, c->kpad, c->w,
+                                                                 c->bias);
+  RN_LAUNCH_CHECK();
+  return 0;
 }
-void rn50_destroy(Rn50* r) { delete r; }
+int load_linear(Rn50* r, cudaStream_t st, const WeightGetter& get, const std::string& name, int nout, int nin,
+                __nv_bfloat16* wdst, float* bdst) {
+  const float *w, *b;
+  SPM_TRY(get(name + ".weight", (long long)nout * nin, &w));
+  SPM_TRY(get(name + ".bias", nout, &b));
+  const long long n = (long long)nout * nin;
+  cast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, wdst, n);
+  RN_LAUNCH_CHECK();
+  SPM_CUDA(cudaMemcpyAsync(bdst, b, (size_t)nout * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int plan_conv(Rn50* r, Plan* pl, const Conv& c, const __nv_bfloat16* A, long long rows, __nv_bfloat16* out, bool relu,
+              const __nv_bfloat16* residual) {
+  GemmEpilogue ep;
+  ep.bias = c.bias; ep.out = out; ep.ldo = c.cout; ep.out_bf16 = 1;
+  if (residual != nullptr) {
+    ep.residual_bf16 = residual; ep.ldr = c.cout; ep.relu_after_residual = 1;
+  } else if (relu) {
+    ep.act = ACT_RELU;
+  }
+  GemmOp op;
+  const char* err = "";
+  if (gemm_plan(&op, GEMM_BF16, A, c.kpad, c.w, c.kpad, (int)rows, c.cout, c.kpad, ep, r->sms, &err)) {
+    set_error(std::string("rn50 gemm_plan: ") + err);
+    return 1;
+  }
+  pl->ops.push_back(op);
+  return 0;
+}
+
+// Builds the GEMM list in execution order for F frames.  The non-GEMM kernels are replayed in the same order by run().
+int build_plan(Rn50* r, int F, Plan* pl) {
+  const long long R112 = (long long)F * 112 * 112;
+  SPM_TRY(plan_conv(r, pl, r->stem[0], r->col, R112, r->t1, true, nullptr));
+  SPM_TRY(plan_conv(r, pl, r->stem[1], r->col, R112, r->t2, true, nullptr));
+  SPM_TRY(plan_conv(r, pl, r->stem[2], r->col, R112, r->t1, true, nullptr));
+  __nv_bfloat16 *x = r->xa, *y = r->xb;
+  int H = 56;
+  for (const Block& b : r->blocks) {
+    const long long rows_in = (long long)F * H * H;
+    const int Ho = H / b.stride;
+    const long long rows_out = (long long)F * Ho * Ho;
+    SPM_TRY(plan_conv(r, pl, b.c1, x, rows_in, r->t1, true, nullptr));
+    SPM_TRY(plan_conv(r, pl, b.c2, r->col, rows_in, r->t2, true, nullptr));
+    const __nv_bfloat16* c3_in = b.stride > 1 ? r->t2p : r->t2;
+    const __nv_bfloat16* idn = x;
+    if (b.has_down) {
+      SPM_TRY(plan_conv(r, pl, b.down, b.stride > 1 ? r->xd : x, rows_out, r->idn, false, nullptr));
+      idn = r->idn;
+    }
+    SPM_TRY(plan_conv(r, pl, b.c3, c3_in, rows_out, y, false, idn));
+    std::swap(x, y);
+    H = Ho;
+  }
+  // attention pool: kv over all 50 tokens, q over the mean tokens (row stride 50*2048), c_proj
+  const char* err = "";
+  {
+    GemmEpilogue ep;
+    ep.bias = r->kv_b; ep.out = r->kvbuf; ep.ldo = 2 * EMB; ep.out_bf16 = 1;
+    GemmOp op;
+    if (gemm_plan(&op, GEMM_BF16, r->tok, EMB, r->kv_w, EMB, F * NTOK, 2 * EMB, EMB, ep, r->sms, &err)) { set_error(err); return 1; }
+    pl->ops.push_back(op);
+  }
+  {
+    GemmEpilogue ep;
+    ep.bias = r->q_b; ep.out = r->qbuf; ep.ldo = EMB; ep.out_bf16 = 1;
+    GemmOp op;
+    if (gemm_plan(&op, GEMM_BF16, r->tok, (long long)NTOK * EMB, r->q_w, EMB, F, EMB, EMB, ep, r->sms, &err)) { set_error(err); return 1; }
+    pl->ops.push_back(op);
+  }
+  {
+    GemmEpilogue ep;
+    ep.bias = r->c_b; ep.out = r->qbuf /* patched per call */; ep.ldo = OUT_DIM;
+    GemmOp op;
+    if (gemm_plan(&op, GEMM_BF16, r->obuf, EMB, r->c_w, EMB, F, OUT_DIM, EMB, ep, r->sms, &err)) { set_error(err); return 1; }
+    pl->ops.push_back(op);
+  }
+  return 0;
+}
+
+int run_gemm(const GemmOp& op, cudaStream_t st) {
+  const char* err = "";
+  if (gemm_run(&op, st, &err)) { set_error(std::string("rn50 gemm_run: ") + err); return 1; }
+  return 0;
+}
+int im2col(cudaStream_t st, const __nv_bfloat16* in, __nv_bfloat16* out, int F, int H, int C) {
+  const long long n = (long long)F * H * H * 9 * (C / 8);
+  im2col3x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, H, H, C, n);
+  RN_LAUNCH_CHECK();
+  return 0;
+}
+int avgpool(cudaStream_t st, const __nv_bfloat16* in, __nv_bfloat16* out, int F, int H, int C) {
+  const long long n = (long long)F * (H / 2) * (H / 2) * (C / 8);
+  avgpool2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, H, H, C, n);
+  RN_LAUNCH_CHECK();
+  return 0;
+}
+
+int run_chunk(Rn50* r, cudaStream_t st, const float* images, int F, float* feats_out) {
+  auto it = r->plans.find(F);
+  if (it == r->plans.end()) {
+    std::unique_ptr<Plan> pl(new Plan());
+    SPM_TRY(build_plan(r, F, pl.get()));
+    it = r->plans.emplace(F, std::move(pl)).first;
+  }
+  const std::vector<GemmOp>& ops = it->second->ops;
+  size_t g = 0;
+  // ---- stem (clip_fsar.py:594-599)
+  const long long R112 = (long long)F * 112 * 112;
+  stem_im2col_kernel<<<(unsigned)((R112 + 127) / 128), 128, 0, st>>>(images, r->col, R112);
+  RN_LAUNCH_CHECK();
+  SPM_TRY(run_gemm(ops[g++], st));                         // conv1+bn1+relu -> t1 [.,32]
+  SPM_TRY(im2col(st, r->t1, r->col, F, 112, 32));
+  SPM_TRY(run_gemm(ops[g++], st));                         // conv2 -> t2 [.,32]
+  SPM_TRY(im2col(st, r->t2, r->col, F, 112, 32));
+  SPM_TRY(run_gemm(ops[g++], st));                         // conv3 -> t1 [.,64]
+  SPM_TRY(avgpool(st, r->t1, r->xa, F, 112, 64));          // -> x [F,56,56,64]
+  // ---- residual layers (clip_fsar.py:534-547)
+  __nv_bfloat16 *x = r->xa, *y = r->xb;
+  int H = 56;
+  for (const Block& b : r->blocks) {
+    SPM_TRY(run_gemm(ops[g++], st));                                   // conv1 1x1 -> t1
+    SPM_TRY(im2col(st, r->t1, r->col, F, H, b.planes));
+    SPM_TRY(run_gemm(ops[g++], st));                                   // conv2 3x3 -> t2
+    if (b.stride > 1) SPM_TRY(avgpool(st, r->t2, r->t2p, F, H, b.planes));
+    if (b.has_down) {
+      if (b.stride > 1) SPM_TRY(avgpool(st, x, r->xd, F, H, b.inpl));
+      SPM_TRY(run_gemm(ops[g++], st));                                 // downsample conv+bn -> idn
+    }
+    SPM_TRY(run_gemm(ops[g++], st));                                   // conv3 + bn3 + identity + relu -> y
+    std::swap(x, y);
+    H /= b.stride;
+  }
+  // ---- attention pool
+  attnpool_tokens_kernel<<<F, 256, 0, st>>>(x, r->pos, r->tok);
+  RN_LAUNCH_CHECK();
+  SPM_TRY(run_gemm(ops[g++], st));  // k | v
+  SPM_TRY(run_gemm(ops[g++], st));  // q (mean token)
+  attnpool_attend_kernel<<<(F * HEADS + 3) / 4, 128, 0, st>>>(r->qbuf, r->kvbuf, r->obuf, F * HEADS);
+  RN_LAUNCH_CHECK();
+  GemmOp fin = ops[g++];
+  fin.ep.out = feats_out;
+  SPM_TRY(run_gemm(fin, st));
+  return 0;
+}
+}  // namespace
+
+int rn50_create(Rn50** out, cudaStream_t st, int sms, const WeightGetter& get) {
+  std::unique_ptr<Rn50> r(new Rn50());
+  r->sms = sms;
+  const std::string p = "backbone.";
+  const float* probe;
+  if (get(p + "conv1.weight", 32LL * 3 * 9, &probe) != 0) {
+    // head-only use (no backbone tensors supplied): keep an empty encoder; encoding frames reports it
+    set_error("");
+    *out = r.release();
+    return 0;
+  }
+  SPM_TRY(load_conv(r.get(), st, get, p + "conv1.weight", p + "bn1.", 32, 3, 3, &r->stem[0]));
+  SPM_TRY(load_conv(r.get(), st, get, p + "conv2.weight", p + "bn2.", 32, 32, 3, &r->stem[1]));
+  SPM_TRY(load_conv(r.get(), st, get, p + "conv3.weight", p + "bn3.", 64, 32, 3, &r->stem[2]));
+  int inpl = 64;
+  const int nblk[4] = {3, 4, 6, 3};
+  for (int li = 0; li < 4; ++li) {
+    const int planes = 64 << li;
+    for (int bi = 0; bi < nblk[li]; ++bi) {
+      Block b;
+      b.inpl = inpl; b.planes = planes; b.stride = (li > 0 && bi == 0) ? 2 : 1;
+      b.has_down = b.stride > 1 || inpl != planes * 4;
+      const std::string bp = p + "layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".";
+      SPM_TRY(load_conv(r.get(), st, get, bp + "conv1.weight", bp + "bn1.", planes, inpl, 1, &b.c1));
+      SPM_TRY(load_conv(r.get(), st, get, bp + "conv2.weight", bp + "bn2.", planes, planes, 3, &b.c2));
+      SPM_TRY(load_conv(r.get(), st, get, bp + "conv3.weight", bp + "bn3.", planes * 4, planes, 1, &b.c3));
+      if (b.has_down)
+        SPM_TRY(load_conv(r.get(), st, get, bp + "downsample.0.weight", bp + "downsample.1.", planes * 4, inpl, 1, &b.down));
+      r->blocks.push_back(b);
+      inpl = planes * 4;
+    }
+  }
+  const std::string ap = p + "attnpool.";
+  const float* pos;
+  SPM_TRY(get(ap + "positional_embedding", (long long)NTOK * EMB, &pos));
+  SPM_TRY(ralloc(r.get(), &r->pos, (long long)NTOK * EMB));
+  SPM_CUDA(cudaMemcpyAsync(r->pos, pos, (size_t)NTOK * EMB * 4, cudaMemcpyDeviceToDevice, st));
+  SPM_TRY(ralloc(r.get(), &r->q_w, (long long)EMB * EMB));
+  SPM_TRY(ralloc(r.get(), &r->kv_w, 2LL * EMB * EMB));
+  SPM_TRY(ralloc(r.get(), &r->c_w, (long long)OUT_DIM * EMB));
+  SPM_TRY(ralloc(r.get(), &r->q_b, EMB));
+  SPM_TRY(ralloc(r.get(), &r->kv_b, 2 * EMB));
+  SPM_TRY(ralloc(r.get(), &r->c_b, OUT_DIM));
+  SPM_TRY(load_linear(r.get(), st, get, ap + "q_proj", EMB, EMB, r->q_w, r->q_b));
+  SPM_TRY(load_linear(r.get(), st, get, ap + "k_proj", EMB, EMB, r->kv_w, r->kv_b));
+  SPM_TRY(load_linear(r.get(), st, get, ap + "v_proj", EMB, EMB, r->kv_w + (long long)EMB * EMB, r->kv_b + EMB));
+  SPM_TRY(load_linear(r.get(), st, get, ap + "c_proj", OUT_DIM, EMB, r->c_w, r->c_b));
+  // workspace
+  const long long S = SCRATCH_PER_FRAME * RN_CHUNK;
+  SPM_TRY(ralloc(r.get(), &r->xa, S));
+  SPM_TRY(ralloc(r.get(), &r->xb, S));
+  SPM_TRY(ralloc(r.get(), &r->t1, S));
+  SPM_TRY(ralloc(r.get(), &r->t2, S));
+  SPM_TRY(ralloc(r.get(), &r->t2p, S));
+  SPM_TRY(ralloc(r.get(), &r->xd, S));
+  SPM_TRY(ralloc(r.get(), &r->idn, S));
+  SPM_TRY(ralloc(r.get(), &r->col, COL_PER_FRAME * RN_CHUNK));
+  SPM_TRY(ralloc(r.get(), &r->tok, (long long)RN_CHUNK * NTOK * EMB));
+  SPM_TRY(ralloc(r.get(), &r->qbuf, (long long)RN_CHUNK * EMB));
+  SPM_TRY(ralloc(r.get(), &r->kvbuf, (long long)RN_CHUNK * NTOK * 2 * EMB));
+  SPM_TRY(ralloc(r.get(), &r->obuf, (long long)RN_CHUNK * EMB));
+  *out = r.release();
+  return 0;
+}
+
+int rn50_encode(Rn50* r, cudaStream_t st, const float* images, int n_frames, float* feats_out) {
+  SPM_CHECK(r != nullptr && !r->blocks.empty(), "RN50 encoder: backbone weights were not loaded");
+  for (int f0 = 0; f0 < n_frames; f0 += RN_CHUNK) {
+    const int F = std::min(RN_CHUNK, n_frames - f0);
+    SPM_TRY(run_chunk(r, st, images + (long long)f0 * FRAME_ELEMS, F, feats_out + (long long)f0 * OUT_DIM));
+  }
+  return 0;
+}
+
+void rn50_destroy(Rn50* r) {
+  if (r == nullptr) return;
+  for (void* p : r->allocs) cudaFree(p);
+  delete r;
+}
+
 }  // namespace spm

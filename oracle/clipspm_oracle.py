@@ -408,8 +408,14 @@ def make_weights(backbone, seed=0, protocol="P1", head_only=False, params=DEFAUL
         elif leaf == "running_var":
             w[name] = _uniform(seed, name, shp, 0.5, 1.5)
         elif len(shp) == 1 and leaf == "weight":   # LayerNorm / BatchNorm scale
-            w[name] = (_uniform(seed, name, shp, 0.5, 1.5) if "bn" in name or "downsample" in name
-                       else 1.0 + _normal(seed, name, shp, 0.1))
+            if ".bn3." in name and "layer" in name:
+                # last BN of a bottleneck: a small (but non-zero: CLIP's default init zeroes it and hides every
+                # conv) scale keeps the residual stream O(1) through 16 blocks
+                w[name] = _uniform(seed, name, shp, 0.2, 0.5)
+            elif "bn" in name or "downsample" in name:
+                w[name] = _uniform(seed, name, shp, 0.5, 1.5)
+            else:
+                w[name] = 1.0 + _normal(seed, name, shp, 0.1)
         elif leaf == "bias" or leaf == "in_proj_bias":
             w[name] = _normal(seed, name, shp, 0.02)
         elif leaf in ("class_embedding", "positional_embedding", "proj"):

@@ -175,3 +175,31 @@ def test_vit_attention_matches_torch(impl, F, scale):
     ref = (att @ x[2]).permute(0, 2, 1, 3).reshape(F * 197, 768)
     err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-2, (impl, F, err)
+
+
+def test_last_block_cls_pruning_is_exact(monkeypatch):
+    """running the last transformer block on the class-token rows only (default) == running it on all tokens"""
+    ci = H.case_inputs("vit_2w1s_t2_p0")
+    imgs = ci["episode"]["context_images"].cuda()
+    pruned = H.build_cuda_model(ci).encode_frames(imgs)
+    monkeypatch.setenv("SPM_PRUNE_LAST", "0")
+    full = H.build_cuda_model(ci).encode_frames(imgs)
+    assert torch.allclose(pruned, full, atol=1e-5, rtol=1e-5)
+
+
+def test_rn50_encoder_and_forward_match_reference_golden():
+    """CLIP ModifiedResNet-50 tower (clip_fsar.py:593-608) + head with D=1024 (BASELINE config 4 architecture)"""
+    name = "rn50_2w1s_t2_p1"
+    ci, g = H.case_inputs(name), H.golden(name)
+    net = H.build_cuda_model(ci)
+    ep = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in ci["episode"].items()}
+    su = net.encode_frames(ep["context_images"])
+    err_f = H.rel_err(su.cpu().view(g["su"].shape), g["su"])
+    out = net(ep)
+    err_l = H.rel_err(out["logits"].cpu(), g["logits"])
+    print("\nrn50: feature rel err %.3e, logits rel err %.3e" % (err_f, err_l))
+    assert err_f < TOL_BF16, err_f
+    assert err_l < TOL_BF16, err_l
+    abs_err = float((out["logits"].cpu() - g["logits"]).abs().max())
+    safe = g["margin"] > 4 * abs_err
+    assert torch.equal(out["logits"][0].argmax(-1).cpu()[safe], g["pred"].long()[safe])
