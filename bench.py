@@ -152,7 +152,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--episodes-per-step", type=int, default=8)
-    ap.add_argument("--episodes-per-call", type=int, default=4)
+    ap.add_argument("--episodes-per-call", type=int, default=8)
     ap.add_argument("--ref-frames", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

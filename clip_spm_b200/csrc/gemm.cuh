@@ -38,6 +38,7 @@ struct GemmOp {
   int bn = 256;
   int kind = GEMM_BF16;
   int grid = 0;
+  int two_cta = 0;  // 1: launched as 2-CTA clusters (gemm2_tcgen05.cu), 256x256 tile per CTA pair
 };
 
 // A: [M, K] (row stride lda elements), B: [N, K] (row stride ldb) -- both K-contiguous ("K-major"),
@@ -47,5 +48,8 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
 int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err);
 // one-time: opt into large dynamic shared memory for every instantiation
 int gemm_init(const char** err);
+// 2-CTA kernel (gemm2_tcgen05.cu)
+int gemm2_init(const char** err);
+int gemm2_launch(const GemmOp* op, cudaStream_t stream);
 
 }  // namespace spm

@@ -1,0 +1,231 @@
+// 2-CTA (cta_group::2) variant of the persistent tcgen05 GEMM: a cluster of two CTAs on one TPC computes a
+// 256 x 256 output tile.  Each CTA stages ITS 128 rows of A and ITS half (128 rows) of B per k-block, so the shared
+// memory written by TMA and read by the tensor core per CTA drops from 48 KB to 32 KB per 128x256x64 of work
+// (the 1-CTA kernel is bound by that traffic: 96 B/clk in + 96 B/clk out against 128 B/clk of shared memory) and the
+// pipeline deepens from 4 to 6 stages.  The leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 (M = 256);
+// every CTA's TMEM receives its own 128 accumulator rows and runs the same epilogue as the 1-CTA kernel.
+//   producer (both CTAs)  TMA .cta_group::2 loads into the local smem, completion bytes counted on the LEADER's
+//                         full barrier (peer bit of the barrier address cleared)
+//   MMA (leader)          tcgen05.commit ... multicast::cluster frees the stage in both CTAs / publishes the
+//                         accumulator to both epilogues
+//   epilogue (both CTAs)  arrive remotely on the leader's tmem-empty barrier (16 warp arrivals)
+// bf16 operands only, N % 256 == 0; used for the large frame-encoder GEMMs.
+#include "gemm.cuh"
+#include "gemm_epilogue.cuh"
+#include "profile.cuh"
+#include "ptx.cuh"
+
+namespace spm {
+
+namespace {
+struct G2 {
+  static constexpr int BM = 128, BN = 256, BK = 64;
+  static constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int STG_BYTES_PER_WARP = 32 * 128;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024;
+};
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on a barrier that lives in the leader CTA's shared memory (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* local_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(local_bar) & PEER_MASK)
+               : "memory");
+}
+}  // namespace
+
+struct Gemm2Args {
+  GemmEpilogue ep;
+  int M, N, K;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const Gemm2Args args) {
+  using T = G2;
+  extern __shared__ uint8_t smem_raw2[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T::STAGES * T::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + T::STAGES;
+  uint64_t* tfull_bar = empty_bar + T::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int M = args.M, N = args.N, K = args.K;
+  const int num_n = N / T::BN;
+  const int num_tiles = ((M + 2 * T::BM - 1) / (2 * T::BM)) * num_n;
+  const int num_kb = (K + T::BK - 1) / T::BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < T::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * T::EPI_WARPS);  // epilogue warps of BOTH CTAs (only the leader's copy is used)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(tmem_slot, T::TMEM_COLS);
+  tc_fence_before_sync();
+  cluster_sync_all();  // both CTAs' barriers and TMEM exist before any cross-CTA signal
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      int pf_tile = cluster_id, pf_kb = 0;
+      auto prefetch_next = [&]() {
+        if (pf_tile < num_tiles) {
+          tma_prefetch_l2_2d(&tmA, pf_kb * T::BK, (pf_tile / num_n) * (2 * T::BM) + (int)rank * T::BM);
+          if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += n_clusters; }
+        }
+      };
+      for (int i = 0; i < GEMM_L2_PREFETCH_KB; ++i) prefetch_next();
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        const int m0 = (tile / num_n) * (2 * T::BM) + (int)rank * T::BM;
+        const int n0 = (tile % num_n) * T::BN + (int)rank * (T::BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          prefetch_next();
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * T::STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * T::STAGE_BYTES);  // bytes of both CTAs land on the leader
+          const uint32_t lbar = smem_u32(&full_bar[stage]) & PEER_MASK;
+          tma_load_2d_2sm(sa, &tmA, lbar, kb * T::BK, m0);
+          tma_load_2d_2sm(sa + T::A_BYTES, &tmB, lbar, kb * T::BK, n0);
+          if (++stage == T::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (leader CTA) =====================
+      constexpr uint32_t idesc = umma_idesc(1, 2 * T::BM, T::BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_phase = (t >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T::BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * T::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + T::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_bf16_ss_2cta(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0);
+          tc_commit_2cta_mc(&empty_bar[stage], 3);  // stage free in both CTAs once these MMAs have read it
+          if (++stage == T::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_2cta_mc(&tfull_bar[acc], 3);  // accumulator complete -> both epilogues
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const GemmEpilogue& ep = args.ep;
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const uint32_t stg_u =
+        smem_u32(smem + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES + (warp - 4) * T::STG_BYTES_PER_WARP);
+    int t = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++t) {
+      const int acc = t & 1;
+      const uint32_t acc_phase = (t >> 1) & 1;
+      const int m_base = (tile / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
+      const int n0 = (tile % num_n) * T::BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T::BN);
+      gemm_epilogue_tile<T::BN>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();  // nobody frees TMEM / exits while the peer may still signal or read
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc_2cta(tmem_base, T::TMEM_COLS);
+  }
+}
+
+int gemm2_init(const char** err) {
+  if (cudaFuncSetAttribute(gemm2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2::SMEM_BYTES) !=
+      cudaSuccess) {
+    *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the 2-CTA GEMM kernel";
+    return 1;
+  }
+  return 0;
+}
+
+int gemm2_launch(const GemmOp* op, cudaStream_t stream) {
+  Gemm2Args a;
+  a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K;
+  gemm2_tcgen05_kernel<<<op->grid, 384, G2::SMEM_BYTES, stream>>>(op->ta, op->tb, a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace spm

@@ -1,0 +1,175 @@
+// Epilogue of the tcgen05 GEMMs, shared by the 1-CTA (gemm_tcgen05.cu) and 2-CTA (gemm2_tcgen05.cu) kernels:
+// one warp drains its 32 accumulator rows (TMEM lane quarter) for the column groups it owns.
+#pragma once
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace spm {
+
+// TMA prefetch of one box into L2 (no shared-memory destination, no barrier): used by the producer warps to run a
+// few k-blocks ahead of the smem pipeline so the real loads hit L2 instead of paying HBM latency.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+constexpr int GEMM_L2_PREFETCH_KB = 8;  // k-blocks of A prefetched ahead of the TMA load pointer
+
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// x * sigmoid(1.702 x) = x * (0.5 + 0.5 * tanh(0.851 x)): one MUFU op (tanh.approx, rel. error ~2^-11, far below
+// the bf16 rounding of the stored activation) instead of ex2 + rcp
+__device__ __forceinline__ float quick_gelu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+
+__device__ __forceinline__ float apply_act(float x, int act, float slope) {
+  switch (act) {
+    case ACT_QUICKGELU: return quick_gelu_fast(x);
+    case ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    case ACT_LEAKY: return x > 0.f ? x : slope * x;
+    case ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-x));
+    case ACT_RELU: return fmaxf(x, 0.f);
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ long long out_row(const GemmEpilogue& ep, int m) {
+  if (ep.out_row_group > 0)
+    return (long long)(m / ep.out_row_group) * ep.out_group_stride + (m % ep.out_row_group) + ep.out_row_off;
+  return m;
+}
+__device__ __forceinline__ long long res_row(const GemmEpilogue& ep, int m) {
+  if (ep.res_row_mod > 0) return (m % ep.res_row_mod) + ep.res_row_off;
+  return out_row(ep, m);
+}
+
+// taddr: TMEM address of (lane quarter base, first accumulator column of the tile); stg_u: this warp's 4 KB staging
+// tile (32 rows x 128 B, 16-byte units XOR-swizzled by row & 7); half: which of the two warps of the lane quarter.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint32_t stg_u, uint32_t taddr, int m_base,
+                                                   int n0, int M, int N, int lane, int half) {
+  const int rr = lane >> 3, uu = lane & 7;  // read-back mapping: row i*4 + rr, 16-byte unit uu
+  const int halves = ep.out_bf16 ? 2 : 1;   // 32-column accumulator chunks per 128-byte output group
+#pragma unroll 1
+  for (int g = half * halves; g < BN / 32; g += 2 * halves) {
+    const int col0 = n0 + g * 32;  // first output column of this 128-byte store group
+    if (col0 >= N) break;          // warp-uniform
+    // (a) residual tile: coalesced 16-byte loads, issued before the TMEM round trip so their latency overlaps it
+    float4 res[8];
+    if (ep.residual_bf16 != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int m = m_base + i * 4 + rr;
+        if (m < M && col0 + uu * 8 < N)
+          res[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const __nv_bfloat16*>(ep.residual_bf16) +
+                                                    res_row(ep, m) * ep.ldr + col0 + uu * 8);
+      }
+    } else if (ep.residual != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int m = m_base + i * 4 + rr;
+        if (m < M) res[i] = *reinterpret_cast<const float4*>(ep.residual + res_row(ep, m) * ep.ldr + col0 + uu * 4);
+      }
+    }
+    // (b) accumulator row (one per thread) -> bias / activation -> swizzled staging tile [32 rows][128 B]
+#pragma unroll 1
+    for (int h = 0; h < halves; ++h) {
+      const int c0 = col0 + h * 32;
+      if (c0 >= N) break;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr + (uint32_t)((g + h) * 32), r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (ep.bias != nullptr) {
+        const float4* bp = reinterpret_cast<const float4*>(ep.bias + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(bp + j);
+          v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+      }
+      if (ep.act == ACT_QUICKGELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = quick_gelu_fast(v[j]);
+      } else if (ep.act != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act, ep.slope);
+      }
+      const uint32_t srow = stg_u + (uint32_t)(lane * 128);
+      if (ep.out_bf16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack2_bf16(v[8 * j + 0], v[8 * j + 1]);
+          u.y = pack2_bf16(v[8 * j + 2], v[8 * j + 3]);
+          u.z = pack2_bf16(v[8 * j + 4], v[8 * j + 5]);
+          u.w = pack2_bf16(v[8 * j + 6], v[8 * j + 7]);
+          st_shared_v4(srow + (uint32_t)((((h * 4 + j) ^ (lane & 7))) * 16), u);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 u;
+          u.x = __float_as_uint(v[4 * j]); u.y = __float_as_uint(v[4 * j + 1]);
+          u.z = __float_as_uint(v[4 * j + 2]); u.w = __float_as_uint(v[4 * j + 3]);
+          st_shared_v4(srow + (uint32_t)(((j ^ (lane & 7))) * 16), u);
+        }
+      }
+    }
+    __syncwarp();
+    // (c) read back row-contiguous: 8 lanes cover one row's 128 bytes -> full-line coalesced global stores
+    const bool col_ok = ep.out_bf16 ? (col0 + uu * 8 < N) : (col0 + uu * 4 < N);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = i * 4 + rr;
+      uint4 d = ld_shared_v4(stg_u + (uint32_t)(rl * 128 + ((uu ^ (rl & 7)) * 16)));
+      if (m_base + rl < M && col_ok) {
+        const long long obase = out_row(ep, m_base + rl) * ep.ldo;
+        if (ep.out_bf16) {
+          if (ep.residual_bf16 != nullptr) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[i]);
+            uint32_t* dw = reinterpret_cast<uint32_t*>(&d);
+#pragma unroll
+            for (int w2 = 0; w2 < 4; ++w2) {
+              const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[w2]));
+              const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[w2]));
+              float lo = a.x + b.x, hi = a.y + b.y;
+              if (ep.relu_after_residual) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+              dw[w2] = pack2_bf16(lo, hi);
+            }
+          }
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + obase + col0 + uu * 8) = d;
+        } else {
+          if (ep.residual != nullptr) {
+            d.x = __float_as_uint(__uint_as_float(d.x) + res[i].x);
+            d.y = __float_as_uint(__uint_as_float(d.y) + res[i].y);
+            d.z = __float_as_uint(__uint_as_float(d.z) + res[i].z);
+            d.w = __float_as_uint(__uint_as_float(d.w) + res[i].w);
+          }
+          *reinterpret_cast<uint4*>(reinterpret_cast<float*>(ep.out) + obase + col0 + uu * 4) = d;
+        }
+      }
+    }
+    __syncwarp();  // staging tile is reused by the next group
+  }
+}
+
+}  // namespace spm

@@ -14,7 +14,10 @@
 // This replaces the cuBLASLt / cuDNN calls the reference makes through ATen for
 // models/clip_fsar.py:626-632,673,687 (ViT linears, patch-embed conv, projection) and
 // models/myRes.py:944-996 + models/model_clipspm.py:76-99,171-174 (head linears, gates, temporal convs).
+#include <cstdlib>
+
 #include "gemm.cuh"
+#include "gemm_epilogue.cuh"
 #include "profile.cuh"
 #include "ptx.cuh"
 
@@ -40,48 +43,6 @@ struct GemmTile {
   static constexpr int EPI_WARPS = 8;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024;  // +1024: alignment slack
 };
-
-__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
-  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&p);
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-
-// x * sigmoid(1.702 x) = x * (0.5 + 0.5 * tanh(0.851 x)): one MUFU op (tanh.approx, rel. error ~2^-11, far below
-// the bf16 rounding of the stored activation) instead of ex2 + rcp
-__device__ __forceinline__ float quick_gelu_fast(float x) {
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
-  return x * fmaf(0.5f, t, 0.5f);
-}
-
-__device__ __forceinline__ float apply_act(float x, int act, float slope) {
-  switch (act) {
-    case ACT_QUICKGELU: return quick_gelu_fast(x);
-    case ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
-    case ACT_LEAKY: return x > 0.f ? x : slope * x;
-    case ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-x));
-    case ACT_RELU: return fmaxf(x, 0.f);
-    default: return x;
-  }
-}
-
-__device__ __forceinline__ long long out_row(const GemmEpilogue& ep, int m) {
-  if (ep.out_row_group > 0)
-    return (long long)(m / ep.out_row_group) * ep.out_group_stride + (m % ep.out_row_group) + ep.out_row_off;
-  return m;
-}
-__device__ __forceinline__ long long res_row(const GemmEpilogue& ep, int m) {
-  if (ep.res_row_mod > 0) return (m % ep.res_row_mod) + ep.res_row_off;
-  return out_row(ep, m);
-}
 
 template <int BN, int KIND>
 __global__ void __launch_bounds__(384, 1)
@@ -133,10 +94,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
+      // L2 prefetch iterator over this CTA's (tile, k-block) sequence, GEMM_L2_PREFETCH_KB ahead of the loads
+      int pf_tile = blockIdx.x, pf_kb = 0;
+      auto prefetch_next = [&]() {
+        if (pf_tile < num_tiles) {
+          tma_prefetch_l2_2d(&tmA, pf_kb * T::BK, (pf_tile / num_n) * T::BM);
+          if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += gridDim.x; }
+        }
+      };
+      for (int i = 0; i < GEMM_L2_PREFETCH_KB; ++i) prefetch_next();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / num_n) * T::BM;
         const int n0 = (tile % num_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          prefetch_next();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * T::STAGE_BYTES;
           uint8_t* sb = sa + T::A_BYTES;
@@ -189,8 +160,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // warp-private staging tile: 32 rows x 128 B, 16-byte units XOR-swizzled by (row & 7) -> conflict-free both ways
     const int half = (warp - 4) >> 2;  // which of the two warps of this lane quarter: takes column groups g % 2 == half
     const uint32_t stg_u = smem_u32(smem + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES + (warp - 4) * T::STG_BYTES_PER_WARP);
-    const int rr = lane >> 3, uu = lane & 7;  // read-back mapping: row i*4 + rr, 16-byte unit uu
-    const int halves = ep.out_bf16 ? 2 : 1;   // 32-column accumulator chunks per 128-byte output group
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
@@ -200,112 +169,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int g = half * halves; g < BN / 32; g += 2 * halves) {
-        const int col0 = n0 + g * 32;  // first output column of this 128-byte store group
-        if (col0 >= N) break;          // warp-uniform
-        // (a) residual tile: coalesced 16-byte loads, issued before the TMEM round trip so their latency overlaps it
-        float4 res[8];
-        if (ep.residual_bf16 != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int m = m_base + i * 4 + rr;
-            if (m < M && col0 + uu * 8 < N)
-              res[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const __nv_bfloat16*>(ep.residual_bf16) +
-                                                        res_row(ep, m) * ep.ldr + col0 + uu * 8);
-          }
-        } else if (ep.residual != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int m = m_base + i * 4 + rr;
-            if (m < M) res[i] = *reinterpret_cast<const float4*>(ep.residual + res_row(ep, m) * ep.ldr + col0 + uu * 4);
-          }
-        }
-        // (b) accumulator row (one per thread) -> bias / activation -> swizzled staging tile [32 rows][128 B]
-#pragma unroll 1
-        for (int h = 0; h < halves; ++h) {
-          const int c0 = col0 + h * 32;
-          if (c0 >= N) break;
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + (uint32_t)((g + h) * 32), r);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (ep.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(ep.bias + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(bp + j);
-              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-          }
-          if (ep.act == ACT_QUICKGELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = quick_gelu_fast(v[j]);
-          } else if (ep.act != ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act, ep.slope);
-          }
-          const uint32_t srow = stg_u + (uint32_t)(lane * 128);
-          if (ep.out_bf16) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack2_bf16(v[8 * j + 0], v[8 * j + 1]);
-              u.y = pack2_bf16(v[8 * j + 2], v[8 * j + 3]);
-              u.z = pack2_bf16(v[8 * j + 4], v[8 * j + 5]);
-              u.w = pack2_bf16(v[8 * j + 6], v[8 * j + 7]);
-              st_shared_v4(srow + (uint32_t)((((h * 4 + j) ^ (lane & 7))) * 16), u);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint4 u;
-              u.x = __float_as_uint(v[4 * j]); u.y = __float_as_uint(v[4 * j + 1]);
-              u.z = __float_as_uint(v[4 * j + 2]); u.w = __float_as_uint(v[4 * j + 3]);
-              st_shared_v4(srow + (uint32_t)(((j ^ (lane & 7))) * 16), u);
-            }
-          }
-        }
-        __syncwarp();
-        // (c) read back row-contiguous: 8 lanes cover one row's 128 bytes -> full-line coalesced global stores
-        const bool col_ok = ep.out_bf16 ? (col0 + uu * 8 < N) : (col0 + uu * 4 < N);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = i * 4 + rr;
-          uint4 d = ld_shared_v4(stg_u + (uint32_t)(rl * 128 + ((uu ^ (rl & 7)) * 16)));
-          if (m_base + rl < M && col_ok) {
-            const long long obase = out_row(ep, m_base + rl) * ep.ldo;
-            if (ep.out_bf16) {
-              if (ep.residual_bf16 != nullptr) {
-                const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[i]);
-                uint32_t* dw = reinterpret_cast<uint32_t*>(&d);
-#pragma unroll
-                for (int w2 = 0; w2 < 4; ++w2) {
-                  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[w2]));
-                  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[w2]));
-                  float lo = a.x + b.x, hi = a.y + b.y;
-                  if (ep.relu_after_residual) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-                  dw[w2] = pack2_bf16(lo, hi);
-                }
-              }
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + obase + col0 + uu * 8) = d;
-            } else {
-              if (ep.residual != nullptr) {
-                d.x = __float_as_uint(__uint_as_float(d.x) + res[i].x);
-                d.y = __float_as_uint(__uint_as_float(d.y) + res[i].y);
-                d.z = __float_as_uint(__uint_as_float(d.z) + res[i].z);
-                d.w = __float_as_uint(__uint_as_float(d.w) + res[i].w);
-              }
-              *reinterpret_cast<uint4*>(reinterpret_cast<float*>(ep.out) + obase + col0 + uu * 4) = d;
-            }
-          }
-        }
-        __syncwarp();  // staging tile is reused by the next group
-      }
+      gemm_epilogue_tile<BN>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
       // accumulator buffer drained -> hand it back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
@@ -375,7 +239,7 @@ int gemm_init(const char** err) {
   SPM_SET_SMEM(256, GEMM_TF32)
   SPM_SET_SMEM(128, GEMM_TF32)
 #undef SPM_SET_SMEM
-  return 0;
+  return gemm2_init(err);
 }
 
 int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
@@ -396,8 +260,17 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   op->bn = (N % 256 == 0 && tiles256 >= num_sms) ? 256 : 128;
   const long long tiles = (long long)((M + 127) / 128) * ((N + op->bn - 1) / op->bn);
   op->grid = (int)(tiles < num_sms ? tiles : num_sms);
+  // Large bf16 problems run on CTA pairs (cta_group::2): 256x256 tile per pair, each CTA stages half of B
+  static const bool allow_2cta = [] { const char* e = getenv("SPM_GEMM_2CTA"); return e == nullptr || atoi(e) != 0; }();
+  const long long pair_tiles = (long long)((M + 255) / 256) * (N / 256);
+  op->two_cta = (allow_2cta && kind == GEMM_BF16 && N % 256 == 0 && pair_tiles >= num_sms / 2) ? 1 : 0;
+  if (op->two_cta) {
+    op->bn = 256;
+    const long long pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+    op->grid = (int)(2 * pairs);
+  }
   if (make_operand_map(&op->ta, kind, A, lda, M, K, 128, err)) return 1;
-  if (make_operand_map(&op->tb, kind, B, ldb, N, K, op->bn, err)) return 1;
+  if (make_operand_map(&op->tb, kind, B, ldb, N, K, op->two_cta ? 128 : op->bn, err)) return 1;
   return 0;
 }
 
@@ -409,7 +282,9 @@ int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
                                        2.0 * (double)op->M * (double)op->N * (double)op->K, &slot);
 #define SPM_LAUNCH(BN, KIND)                                                                                 \
   gemm_tcgen05_kernel<BN, KIND><<<op->grid, 384, GemmTile<BN, KIND>::SMEM_BYTES, stream>>>(op->ta, op->tb, a)
-  if (op->kind == GEMM_BF16) {
+  if (op->two_cta) {
+    gemm2_launch(op, stream);
+  } else if (op->kind == GEMM_BF16) {
     if (op->bn == 256) SPM_LAUNCH(256, GEMM_BF16); else SPM_LAUNCH(128, GEMM_BF16);
   } else {
     if (op->bn == 256) SPM_LAUNCH(256, GEMM_TF32); else SPM_LAUNCH(128, GEMM_TF32);

@@ -132,6 +132,11 @@ struct spm_handle {
   } stage[2];
   long long stage_cap_frames_s = 0, stage_cap_frames_q = 0;
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+  std::vector<cudaEvent_t> ev_copied, ev_done;  // per chunk of one spm_eval_host call
+  // pinned host landing zone for the results: an async D2H into the caller's (possibly pageable) buffers would
+  // block the enqueueing thread until the chunk has finished and starve the GPU of the next chunk's launches
+  float* pin_res = nullptr;
+  long long pin_cap = 0;
 };
 
 namespace spm {
@@ -679,10 +684,9 @@ int spm_destroy(spm_handle* h) {
   cudaDeviceSynchronize();
   if (h->rn50) rn50_destroy(h->rn50);
   for (void* p : h->allocs) cudaFree(p);
-  for (auto& s : h->stage) {
-    if (s.copied) cudaEventDestroy(s.copied);
-    if (s.done) cudaEventDestroy(s.done);
-  }
+  if (h->pin_res) cudaFreeHost(h->pin_res);
+  for (cudaEvent_t e : h->ev_copied) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
   delete h;
@@ -770,58 +774,97 @@ int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const floa
   SPM_CHECK(h && su_h && qu_h && lab_h && rs_h && rt_h && tl_h, "spm_eval_host: null argument");
   SPM_TRY(check_shapes(h, 1, S, Q, W));
   const int T = h->cfg.seq_len;
-  const int EC = std::max(1, h->cfg.max_episodes);  // episodes per chunk
-  const long long fs = (long long)EC * S * T, fq = (long long)EC * Q * T;
+  const int EC = std::max(1, h->cfg.max_episodes);  // episodes per compute chunk
+  const int R = 2 * EC;                             // staging ring: R episode slots
+  const long long fs = (long long)S * T, fq = (long long)Q * T;  // frames per episode
   if (h->copy_stream == nullptr) {
     SPM_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     SPM_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
-    for (auto& s : h->stage) {
-      SPM_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
-      SPM_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-    }
   }
-  if (fs > h->stage_cap_frames_s || fq > h->stage_cap_frames_q) {
-    for (auto& s : h->stage) {
-      SPM_TRY(dalloc_t(h, &s.su, fs * FRAME_ELEMS));
-      SPM_TRY(dalloc_t(h, &s.qu, fq * FRAME_ELEMS));
-      SPM_TRY(dalloc_t(h, &s.lab, (long long)EC * S));
-      SPM_TRY(dalloc_t(h, &s.rs, (long long)EC * S));
-      SPM_TRY(dalloc_t(h, &s.rt, (long long)EC * Q));
-      SPM_TRY(dalloc_t(h, &s.tl, (long long)EC * Q));
-      SPM_TRY(dalloc_t(h, &s.logits, (long long)EC * Q * W));
-      SPM_TRY(dalloc_t(h, &s.dists, EC));
-      SPM_TRY(dalloc_t(h, &s.loss, EC));
-      SPM_TRY(dalloc_t(h, &s.acc, EC));
-      SPM_TRY(dalloc_t(h, &s.pred, (long long)EC * Q));
-    }
-    h->stage_cap_frames_s = fs; h->stage_cap_frames_q = fq;
+  spm_handle::Stage& s = h->stage[0];
+  if (R * fs > h->stage_cap_frames_s || R * fq > h->stage_cap_frames_q) {
+    SPM_TRY(dalloc_t(h, &s.su, R * fs * FRAME_ELEMS));
+    SPM_TRY(dalloc_t(h, &s.qu, R * fq * FRAME_ELEMS));
+    SPM_TRY(dalloc_t(h, &s.lab, (long long)R * S));
+    SPM_TRY(dalloc_t(h, &s.rs, (long long)R * S));
+    SPM_TRY(dalloc_t(h, &s.rt, (long long)R * Q));
+    SPM_TRY(dalloc_t(h, &s.tl, (long long)R * Q));
+    SPM_TRY(dalloc_t(h, &s.logits, (long long)R * Q * W));
+    SPM_TRY(dalloc_t(h, &s.dists, R));
+    SPM_TRY(dalloc_t(h, &s.loss, R));
+    SPM_TRY(dalloc_t(h, &s.acc, R));
+    SPM_TRY(dalloc_t(h, &s.pred, (long long)R * Q));
+    h->stage_cap_frames_s = R * fs; h->stage_cap_frames_q = R * fq;
   }
+  // Chunk schedule.  The H2D copy of a chunk can only overlap the compute of EARLIER chunks, so the first chunks
+  // are small (1, 1, 2, 4, ... up to EC when EC is a power of two: offsets stay aligned, a chunk never wraps the
+  // ring) -- only one episode's copy is exposed per call instead of EC episodes'.
+  std::vector<int> starts;
+  {
+    const bool pow2 = (EC & (EC - 1)) == 0;
+    int e = 0, sz = pow2 ? 1 : EC;
+    bool first = true;
+    while (e < n_episodes) {
+      starts.push_back(e);
+      e += std::min(sz, n_episodes - e);
+      if (pow2 && sz < EC) { if (first) first = false; else sz *= 2; }
+    }
+    starts.push_back(n_episodes);
+  }
+  const int n_chunks = (int)starts.size() - 1;
+  while ((int)h->ev_copied.size() < n_chunks) {
+    cudaEvent_t a, b;
+    SPM_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    SPM_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    h->ev_copied.push_back(a); h->ev_done.push_back(b);
+  }
+  const long long per_ep = (long long)Q * W + 3 + Q;  // logits, dists, loss, acc, pred (int32 in a float slot)
+  if ((long long)n_episodes * per_ep > h->pin_cap) {
+    if (h->pin_res) cudaFreeHost(h->pin_res);
+    SPM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->pin_res), (size_t)n_episodes * per_ep * 4));
+    h->pin_cap = (long long)n_episodes * per_ep;
+  }
+  float* p_logits = h->pin_res;
+  float* p_dists = p_logits + (long long)n_episodes * Q * W;
+  float* p_loss = p_dists + n_episodes;
+  float* p_acc = p_loss + n_episodes;
+  int32_t* p_pred = reinterpret_cast<int32_t*>(p_acc + n_episodes);
   cudaStream_t cs = h->copy_stream, ks = h->compute_stream;
-  int chunk = 0;
-  for (int e0 = 0; e0 < n_episodes; e0 += EC, ++chunk) {
-    const int E = std::min(EC, n_episodes - e0);
-    spm_handle::Stage& s = h->stage[chunk & 1];
-    if (chunk >= 2) SPM_CUDA(cudaStreamWaitEvent(cs, s.done, 0));  // buffer free once chunk-2 has been consumed
-    SPM_CUDA(cudaMemcpyAsync(s.su, su_h + (long long)e0 * S * T * FRAME_ELEMS, (size_t)E * S * T * FRAME_ELEMS * 4,
-                             cudaMemcpyHostToDevice, cs));
-    SPM_CUDA(cudaMemcpyAsync(s.qu, qu_h + (long long)e0 * Q * T * FRAME_ELEMS, (size_t)E * Q * T * FRAME_ELEMS * 4,
-                             cudaMemcpyHostToDevice, cs));
-    SPM_CUDA(cudaMemcpyAsync(s.lab, lab_h + (long long)e0 * S, (size_t)E * S * 4, cudaMemcpyHostToDevice, cs));
-    SPM_CUDA(cudaMemcpyAsync(s.rs, rs_h + (long long)e0 * S, (size_t)E * S * 4, cudaMemcpyHostToDevice, cs));
-    SPM_CUDA(cudaMemcpyAsync(s.rt, rt_h + (long long)e0 * Q, (size_t)E * Q * 4, cudaMemcpyHostToDevice, cs));
-    SPM_CUDA(cudaMemcpyAsync(s.tl, tl_h + (long long)e0 * Q, (size_t)E * Q * 8, cudaMemcpyHostToDevice, cs));
-    SPM_CUDA(cudaEventRecord(s.copied, cs));
-    SPM_CUDA(cudaStreamWaitEvent(ks, s.copied, 0));
-    SPM_TRY(forward_impl(h, ks, E, S, Q, W, s.su, s.qu, s.lab, s.rs, s.rt, s.tl, tasks_per_batch, s.logits, s.dists,
-                         s.loss, s.acc, s.pred));
-    if (logits_h) SPM_CUDA(cudaMemcpyAsync(logits_h + (long long)e0 * Q * W, s.logits, (size_t)E * Q * W * 4, cudaMemcpyDeviceToHost, ks));
-    if (dists_h) SPM_CUDA(cudaMemcpyAsync(dists_h + e0, s.dists, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
-    if (loss_h) SPM_CUDA(cudaMemcpyAsync(loss_h + e0, s.loss, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
-    if (acc_h) SPM_CUDA(cudaMemcpyAsync(acc_h + e0, s.acc, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
-    if (pred_h) SPM_CUDA(cudaMemcpyAsync(pred_h + (long long)e0 * Q, s.pred, (size_t)E * Q * 4, cudaMemcpyDeviceToHost, ks));
-    SPM_CUDA(cudaEventRecord(s.done, ks));
+  std::vector<int> chunk_of(n_episodes);
+  for (int c = 0; c < n_chunks; ++c)
+    for (int e = starts[c]; e < starts[c + 1]; ++e) chunk_of[e] = c;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int e0 = starts[c], E = starts[c + 1] - e0, slot = e0 % R;
+    // ring slot reuse: the chunk that last used these slots must have been consumed
+    if (e0 + E - 1 >= R) SPM_CUDA(cudaStreamWaitEvent(cs, h->ev_done[chunk_of[e0 + E - 1 - R]], 0));
+    SPM_CUDA(cudaMemcpyAsync(s.su + slot * fs * FRAME_ELEMS, su_h + e0 * fs * FRAME_ELEMS,
+                             (size_t)E * fs * FRAME_ELEMS * 4, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.qu + slot * fq * FRAME_ELEMS, qu_h + e0 * fq * FRAME_ELEMS,
+                             (size_t)E * fq * FRAME_ELEMS * 4, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.lab + (long long)slot * S, lab_h + (long long)e0 * S, (size_t)E * S * 4, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.rs + (long long)slot * S, rs_h + (long long)e0 * S, (size_t)E * S * 4, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.rt + (long long)slot * Q, rt_h + (long long)e0 * Q, (size_t)E * Q * 4, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.tl + (long long)slot * Q, tl_h + (long long)e0 * Q, (size_t)E * Q * 8, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaEventRecord(h->ev_copied[c], cs));
+    SPM_CUDA(cudaStreamWaitEvent(ks, h->ev_copied[c], 0));
+    float* lg = s.logits + (long long)slot * Q * W;
+    SPM_TRY(forward_impl(h, ks, E, S, Q, W, s.su + slot * fs * FRAME_ELEMS, s.qu + slot * fq * FRAME_ELEMS,
+                         s.lab + (long long)slot * S, s.rs + (long long)slot * S, s.rt + (long long)slot * Q,
+                         s.tl + (long long)slot * Q, tasks_per_batch, lg, s.dists + slot, s.loss + slot, s.acc + slot,
+                         s.pred + (long long)slot * Q));
+    SPM_CUDA(cudaMemcpyAsync(p_logits + (long long)e0 * Q * W, lg, (size_t)E * Q * W * 4, cudaMemcpyDeviceToHost, ks));
+    SPM_CUDA(cudaMemcpyAsync(p_dists + e0, s.dists + slot, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
+    SPM_CUDA(cudaMemcpyAsync(p_loss + e0, s.loss + slot, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
+    SPM_CUDA(cudaMemcpyAsync(p_acc + e0, s.acc + slot, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
+    SPM_CUDA(cudaMemcpyAsync(p_pred + (long long)e0 * Q, s.pred + (long long)slot * Q, (size_t)E * Q * 4, cudaMemcpyDeviceToHost, ks));
+    SPM_CUDA(cudaEventRecord(h->ev_done[c], ks));
   }
   SPM_CUDA(cudaStreamSynchronize(ks));
+  if (logits_h) memcpy(logits_h, p_logits, (size_t)n_episodes * Q * W * 4);
+  if (dists_h) memcpy(dists_h, p_dists, (size_t)n_episodes * 4);
+  if (loss_h) memcpy(loss_h, p_loss, (size_t)n_episodes * 4);
+  if (acc_h) memcpy(acc_h, p_acc, (size_t)n_episodes * 4);
+  if (pred_h) memcpy(pred_h, p_pred, (size_t)n_episodes * Q * 4);
   int flag = 0;
   SPM_CUDA(cudaMemcpy(&flag, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
   SPM_CHECK(flag == 0, "spm_eval_host: an episode's number of distinct support labels differs from `W`");

@@ -207,7 +207,7 @@ def otam_cum_dist_v2(d, lbda=0.5):
     """models/myRes.py:821-855 OTAM_cum_dist_v2 on d [..., L, M] (cum_dists is always fp32 there, :829)."""
     d = F.pad(d, (1, 1), "constant", 0.0)
     L, M2 = d.shape[-2], d.shape[-1]
-    c = torch.zeros(d.shape, dtype=torch.float32 if d.dtype != torch.float64 else torch.float64)
+    c = torch.zeros(d.shape, dtype=torch.float32 if d.dtype != torch.float64 else torch.float64, device=d.device)
     for m in range(1, M2):
         c[..., 0, m] = d[..., 0, m] + c[..., 0, m - 1]
     for l in range(1, L):

@@ -20,7 +20,8 @@ def _ref_act(x, act, slope):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 128, 128), (300, 768, 768), (197 * 8, 2304, 768),
-                                   (20000, 2304, 768), (4097, 768, 3072), (45, 512, 1536), (9, 6144, 512)])
+                                   (20000, 2304, 768), (4097, 768, 3072), (45, 512, 1536), (9, 6144, 512),
+                                   (10001, 768, 768), (47280, 3072, 768), (18945, 768, 3072)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_gemm_plain(M, N, K, dtype):
     from clip_spm_b200 import ops
@@ -94,3 +95,21 @@ def test_gemm_strided_rows():
     out = ops.gemm(a, w)
     ref = a.float() @ w.float().t()
     assert (out - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+
+
+def test_gemm_two_cta_path_with_epilogues():
+    """shapes large enough for the cta_group::2 kernel (pairs of CTAs, 256x256 tiles), odd M, every epilogue flavour"""
+    from clip_spm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(21)
+    M, N, K = 19999, 768, 768
+    a = torch.randn(M, K, generator=g).cuda().bfloat16()
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    x = torch.randn(M, N, generator=g).cuda()
+    ref = x + a.float() @ b.float().t() + bias
+    ops.gemm(a, b, bias=bias, residual=x, out=x)                      # in-place fp32 residual stream
+    assert (x - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+    out = ops.gemm(a, b, bias=bias, act="quickgelu", out_dtype=torch.bfloat16)
+    r2 = a.float() @ b.float().t() + bias
+    r2 = r2 * torch.sigmoid(1.702 * r2)
+    assert (out.float() - r2).abs().max().item() < 2e-2 * r2.abs().max().item()
