@@ -7,7 +7,8 @@
 
 namespace spm {
 
-enum GemmKind { GEMM_BF16 = 0, GEMM_TF32 = 1 };
+// GEMM_F32_SIMT: exact fp32 FFMA kernel (sgemm_f32.cu) used by the SPM_PRECISION_FP32 parity mode
+enum GemmKind { GEMM_BF16 = 0, GEMM_TF32 = 1, GEMM_F32_SIMT = 2 };
 enum GemmAct { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_GELU_ERF = 2, ACT_LEAKY = 3, ACT_SIGMOID = 4, ACT_RELU = 5 };
 
 // out[orow(m), n] = act(sum_k A[m,k] * B[n,k] + bias[n]) (+ residual[rrow(m), n])
@@ -38,6 +39,9 @@ struct GemmOp {
   int bn = 256;
   int kind = GEMM_BF16;
   int grid = 0;
+  const void* simt_a = nullptr;  // GEMM_F32_SIMT: raw operand pointers / row strides (no tensor maps)
+  const void* simt_b = nullptr;
+  long long simt_lda = 0, simt_ldb = 0;
   int two_cta = 0;  // 1: launched as 2-CTA clusters (gemm2_tcgen05.cu), 256x256 tile per CTA pair
 };
 
@@ -51,5 +55,7 @@ int gemm_init(const char** err);
 // 2-CTA kernel (gemm2_tcgen05.cu)
 int gemm2_init(const char** err);
 int gemm2_launch(const GemmOp* op, cudaStream_t stream);
+// fp32 SIMT kernel (sgemm_f32.cu)
+int sgemm_f32_run(const GemmOp* op, cudaStream_t stream);
 
 }  // namespace spm

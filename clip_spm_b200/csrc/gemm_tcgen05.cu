@@ -255,6 +255,12 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   if (ep.out_bf16 ? (ep.ldo % 8 != 0) : (ep.ldo % 4 != 0)) { *err = "GEMM: output rows must be 16-byte aligned"; return 1; }
   if (ep.residual != nullptr && ep.ldr % 4 != 0) { *err = "GEMM: residual rows must be 16-byte aligned"; return 1; }
   op->M = M; op->N = N; op->K = K; op->kind = kind; op->ep = ep;
+  if (kind == GEMM_F32_SIMT) {
+    if (ep.out_bf16 || ep.residual_bf16 != nullptr) { *err = "GEMM: the fp32 SIMT kernel has fp32 outputs only"; return 1; }
+    if (K % 4 != 0 || lda % 4 != 0 || ldb % 4 != 0) { *err = "GEMM: fp32 SIMT operands need 16-byte aligned rows"; return 1; }
+    op->simt_a = A; op->simt_b = B; op->simt_lda = lda; op->simt_ldb = ldb; op->two_cta = 0;
+    return 0;
+  }
   // Tile width: 256 for the big encoder GEMMs; 128 when that yields more CTAs than SMs can use otherwise
   const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
   op->bn = (N % 256 == 0 && tiles256 >= num_sms) ? 256 : 128;
@@ -278,11 +284,13 @@ int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
   GemmArgs a;
   a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K;
   int slot = -1;
-  const bool prof = profile_gemm_begin(stream, op->kind * 2 + (op->bn == 256 ? 1 : 0),
+  const bool prof = profile_gemm_begin(stream, (op->kind & 1) * 2 + (op->bn == 256 ? 1 : 0),
                                        2.0 * (double)op->M * (double)op->N * (double)op->K, &slot);
 #define SPM_LAUNCH(BN, KIND)                                                                                 \
   gemm_tcgen05_kernel<BN, KIND><<<op->grid, 384, GemmTile<BN, KIND>::SMEM_BYTES, stream>>>(op->ta, op->tb, a)
-  if (op->two_cta) {
+  if (op->kind == GEMM_F32_SIMT) {
+    sgemm_f32_run(op, stream);
+  } else if (op->two_cta) {
     gemm2_launch(op, stream);
   } else if (op->kind == GEMM_BF16) {
     if (op->bn == 256) SPM_LAUNCH(256, GEMM_BF16); else SPM_LAUNCH(128, GEMM_BF16);

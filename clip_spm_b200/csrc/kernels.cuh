@@ -33,4 +33,9 @@ int k_vit_attention_init();
 int k_vit_attention_tc(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, int sms);
 int k_vit_attention_tc_init();
 
+// fp32 parity-mode kernels (sgemm_f32.cu)
+int k_vit_attention_f32(cudaStream_t st, const float* qkv, float* out, int n_frames);
+int k_vit_attention_f32_init();
+int k_patch_im2col_f32(cudaStream_t st, const float* images, float* patches, int n_frames);
+
 }  // namespace spm

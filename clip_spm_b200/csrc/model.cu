@@ -64,6 +64,15 @@ struct VitW {
   __nv_bfloat16* projT = nullptr;  // [512, 768]
   VitLayerW layer[VIT_LAYERS];
 };
+// fp32 copies for the SPM_PRECISION_FP32 parity mode (same layouts, no bf16 rounding anywhere)
+struct VitLayerW32 {
+  float *qkv_w, *out_w, *fc_w, *proj_w;
+};
+struct VitW32 {
+  float* conv1_w = nullptr;  // [768, 768]
+  float* projT = nullptr;    // [512, 768]
+  VitLayerW32 layer[VIT_LAYERS];
+};
 struct CtxW {
   float *ln_g, *ln_b, *qkv_w, *out_w, *out_b, *ff0_w, *ff0_b, *ff3_w, *ff3_b;
 };
@@ -101,6 +110,9 @@ struct spm_handle {
   bool weights_loaded = false, text_set = false;
   std::vector<void*> allocs;
   spm::VitW vit;
+  spm::VitW32 vit32;
+  bool fp32 = false;  // SPM_PRECISION_FP32: CUDA-core fp32 GEMMs / attention, fp32 activations
+  float *patches32 = nullptr, *xn32 = nullptr, *qkv32 = nullptr, *attn32 = nullptr, *hid32 = nullptr, *cls32 = nullptr;
   spm::Rn50* rn50 = nullptr;
   spm::HeadW head;
   float* text = nullptr;
@@ -223,6 +235,35 @@ int load_vit(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
   return 0;
 }
 
+// [R, C] fp32 -> [C, R] fp32 (proj for the fp32 mode), tiny: done with a strided 2-D copy per column block
+__global__ void transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R * C) return;
+  const int r = (int)(i / C), c = (int)(i % C);
+  out[(long long)c * R + r] = in[i];
+}
+
+int load_vit32(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
+  VitW32& v = h->vit32;
+  const std::string p = "backbone.";
+  const int C = VIT_C;
+  SPM_TRY(copy_f32(h, st, wt, p + "conv1.weight", (long long)C * C, &v.conv1_w));
+  const float* proj;
+  SPM_TRY(wt.get(p + "proj", (long long)C * VIT_OUT, &proj));
+  SPM_TRY(dalloc_t(h, &v.projT, (long long)C * VIT_OUT));
+  transpose_f32_kernel<<<(C * VIT_OUT + 255) / 256, 256, 0, st>>>(proj, v.projT, C, VIT_OUT);
+  SPM_CUDA(cudaGetLastError());
+  for (int i = 0; i < VIT_LAYERS; ++i) {
+    const std::string b = p + "transformer.resblocks." + std::to_string(i) + ".";
+    VitLayerW32& l = v.layer[i];
+    SPM_TRY(copy_f32(h, st, wt, b + "attn.in_proj_weight", 3LL * C * C, &l.qkv_w));
+    SPM_TRY(copy_f32(h, st, wt, b + "attn.out_proj.weight", (long long)C * C, &l.out_w));
+    SPM_TRY(copy_f32(h, st, wt, b + "mlp.c_fc.weight", 4LL * C * C, &l.fc_w));
+    SPM_TRY(copy_f32(h, st, wt, b + "mlp.c_proj.weight", 4LL * C * C, &l.proj_w));
+  }
+  return 0;
+}
+
 int load_head(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
   HeadW& w = h->head;
   const long long D = h->D, HT = h->HT, HV = h->HV;
@@ -296,6 +337,14 @@ int ensure_vit_workspace(spm_handle* h) {
   SPM_TRY(dalloc_t(h, &h->cls, (long long)h->frame_chunk * VIT_C));
   SPM_TRY(dalloc_t(h, &h->xc, (long long)h->frame_chunk * VIT_C));
   SPM_TRY(dalloc_t(h, &h->xnc, (long long)h->frame_chunk * VIT_C));
+  if (h->fp32) {
+    SPM_TRY(dalloc_t(h, &h->patches32, (long long)h->frame_chunk * VIT_P * VIT_C));
+    SPM_TRY(dalloc_t(h, &h->xn32, M * VIT_C));
+    SPM_TRY(dalloc_t(h, &h->qkv32, M * 3 * VIT_C));
+    SPM_TRY(dalloc_t(h, &h->attn32, M * VIT_C));
+    SPM_TRY(dalloc_t(h, &h->hid32, M * 4 * VIT_C));
+    SPM_TRY(dalloc_t(h, &h->cls32, (long long)h->frame_chunk * VIT_C));
+  }
   return 0;
 }
 
@@ -305,29 +354,42 @@ int get_vit_plan(spm_handle* h, int F, VitPlan** out) {
   std::unique_ptr<VitPlan> pl(new VitPlan());
   const int C = VIT_C, M = F * VIT_L;
   const VitW& v = h->vit;
+  // operands of the two precisions: bf16 tensor-core path, or fp32 activations/weights on the exact SIMT kernel
+  const bool f32 = h->fp32;
+  const int kind = f32 ? GEMM_F32_SIMT : GEMM_BF16;
+  const int obf = f32 ? 0 : 1;
+  const void* a_patches = f32 ? (const void*)h->patches32 : (const void*)h->patches;
+  const void* a_xn = f32 ? (const void*)h->xn32 : (const void*)h->xn;
+  const void* a_attn = f32 ? (const void*)h->attn32 : (const void*)h->attn;
+  const void* a_hid = f32 ? (const void*)h->hid32 : (const void*)h->hid;
+  const void* a_cls = f32 ? (const void*)h->cls32 : (const void*)h->cls;
+  void* o_qkv = f32 ? (void*)h->qkv32 : (void*)h->qkv;
+  void* o_hid = f32 ? (void*)h->hid32 : (void*)h->hid;
   {
     GemmEpilogue ep;  // x[f*197 + 1 + p] = patch . W + pos[1 + p]
     ep.residual = v.pos; ep.ldr = C; ep.res_row_mod = VIT_P; ep.res_row_off = 1;
     ep.out_row_group = VIT_P; ep.out_group_stride = VIT_L; ep.out_row_off = 1;
     ep.out = h->x; ep.ldo = C;
-    SPM_TRY(plan_gemm(&pl->patch, GEMM_BF16, h->patches, C, v.conv1_w, C, F * VIT_P, C, C, ep, h->sms));
+    SPM_TRY(plan_gemm(&pl->patch, kind, a_patches, C, f32 ? (const void*)h->vit32.conv1_w : (const void*)v.conv1_w, C,
+                      F * VIT_P, C, C, ep, h->sms));
   }
   for (int i = 0; i < VIT_LAYERS; ++i) {
     const VitLayerW& l = v.layer[i];
+    const VitLayerW32& l32 = h->vit32.layer[i];
     GemmEpilogue e1;
-    e1.bias = l.qkv_b; e1.out = h->qkv; e1.ldo = 3 * C; e1.out_bf16 = 1;
-    SPM_TRY(plan_gemm(&pl->qkv[i], GEMM_BF16, h->xn, C, l.qkv_w, C, M, 3 * C, C, e1, h->sms));
+    e1.bias = l.qkv_b; e1.out = o_qkv; e1.ldo = 3 * C; e1.out_bf16 = obf;
+    SPM_TRY(plan_gemm(&pl->qkv[i], kind, a_xn, C, f32 ? (const void*)l32.qkv_w : (const void*)l.qkv_w, C, M, 3 * C, C, e1, h->sms));
     GemmEpilogue e2;
     e2.bias = l.out_b; e2.residual = h->x; e2.ldr = C; e2.out = h->x; e2.ldo = C;
-    SPM_TRY(plan_gemm(&pl->outp[i], GEMM_BF16, h->attn, C, l.out_w, C, M, C, C, e2, h->sms));
+    SPM_TRY(plan_gemm(&pl->outp[i], kind, a_attn, C, f32 ? (const void*)l32.out_w : (const void*)l.out_w, C, M, C, C, e2, h->sms));
     GemmEpilogue e3;
-    e3.bias = l.fc_b; e3.act = ACT_QUICKGELU; e3.out = h->hid; e3.ldo = 4 * C; e3.out_bf16 = 1;
-    SPM_TRY(plan_gemm(&pl->fc[i], GEMM_BF16, h->xn, C, l.fc_w, C, M, 4 * C, C, e3, h->sms));
+    e3.bias = l.fc_b; e3.act = ACT_QUICKGELU; e3.out = o_hid; e3.ldo = 4 * C; e3.out_bf16 = obf;
+    SPM_TRY(plan_gemm(&pl->fc[i], kind, a_xn, C, f32 ? (const void*)l32.fc_w : (const void*)l.fc_w, C, M, 4 * C, C, e3, h->sms));
     GemmEpilogue e4;
     e4.bias = l.proj_b; e4.residual = h->x; e4.ldr = C; e4.out = h->x; e4.ldo = C;
-    SPM_TRY(plan_gemm(&pl->proj[i], GEMM_BF16, h->hid, 4 * C, l.proj_w, 4 * C, M, C, 4 * C, e4, h->sms));
+    SPM_TRY(plan_gemm(&pl->proj[i], kind, a_hid, 4 * C, f32 ? (const void*)l32.proj_w : (const void*)l.proj_w, 4 * C, M, C, 4 * C, e4, h->sms));
   }
-  {
+  if (!f32) {
     // Last block, class-token rows only: attention output / residual rows are taken with a row stride of 197 tokens
     const VitLayerW& l = v.layer[VIT_LAYERS - 1];
     const long long LC = (long long)VIT_L * C;
@@ -345,7 +407,7 @@ int get_vit_plan(spm_handle* h, int F, VitPlan** out) {
     GemmEpilogue ep;
     ep.out = h->x;  // patched per call
     ep.ldo = VIT_OUT;
-    SPM_TRY(plan_gemm(&pl->fin, GEMM_BF16, h->cls, C, v.projT, C, F, VIT_OUT, C, ep, h->sms));
+    SPM_TRY(plan_gemm(&pl->fin, kind, a_cls, C, f32 ? (const void*)h->vit32.projT : (const void*)v.projT, C, F, VIT_OUT, C, ep, h->sms));
   }
   *out = pl.get();
   h->vit_plans[F] = std::move(pl);
@@ -358,6 +420,26 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
   SPM_TRY(get_vit_plan(h, F, &pl));
   const VitW& v = h->vit;
   const int C = VIT_C, M = F * VIT_L;
+  if (h->fp32) {
+    // parity mode: same graph, fp32 activations, exact FFMA GEMMs / attention, no pruning shortcuts
+    SPM_GEMM_RUN(pl->patch);
+    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, v.ln_pre_g, v.ln_pre_b, v.cls_pos, VIT_L, h->x, nullptr, C));
+    for (int i = 0; i < VIT_LAYERS; ++i) {
+      const VitLayerW& l = v.layer[i];
+      SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln1_g, l.ln1_b, nullptr, 0, h->xn32, nullptr, C));
+      SPM_GEMM_RUN(pl->qkv[i]);
+      SPM_KERNEL(k_vit_attention_f32(st, h->qkv32, h->attn32, F));
+      SPM_GEMM_RUN(pl->outp[i]);
+      SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln2_g, l.ln2_b, nullptr, 0, h->xn32, nullptr, C));
+      SPM_GEMM_RUN(pl->fc[i]);
+      SPM_GEMM_RUN(pl->proj[i]);
+    }
+    SPM_KERNEL(k_layernorm(st, h->x, (long long)VIT_L * C, F, C, v.ln_post_g, v.ln_post_b, nullptr, 0, h->cls32, nullptr, C));
+    GemmOp fin32 = pl->fin;
+    fin32.ep.out = feats_out;
+    SPM_GEMM_RUN(fin32);
+    return 0;
+  }
   SPM_GEMM_RUN(pl->patch);
   SPM_KERNEL(k_layernorm(st, h->x, C, M, C, v.ln_pre_g, v.ln_pre_b, v.cls_pos, VIT_L, h->x, nullptr, C));
   for (int i = 0; i < VIT_LAYERS; ++i) {
@@ -416,9 +498,14 @@ int encode_segments(spm_handle* h, cudaStream_t st, const Segment* segs, int nse
     long long seg0 = 0;
     for (int s = 0; s < nseg; ++s) {
       const long long a = std::max(f0, seg0), b = std::min(f1, seg0 + segs[s].n_frames);
-      if (a < b)
-        SPM_KERNEL(k_patch_im2col(st, segs[s].images + (a - seg0) * FRAME_ELEMS,
-                                  h->patches + (a - f0) * VIT_P * VIT_C, (int)(b - a)));
+      if (a < b) {
+        if (h->fp32)
+          SPM_KERNEL(k_patch_im2col_f32(st, segs[s].images + (a - seg0) * FRAME_ELEMS,
+                                        h->patches32 + (a - f0) * VIT_P * VIT_C, (int)(b - a)));
+        else
+          SPM_KERNEL(k_patch_im2col(st, segs[s].images + (a - seg0) * FRAME_ELEMS,
+                                    h->patches + (a - f0) * VIT_P * VIT_C, (int)(b - a)));
+      }
       seg0 += segs[s].n_frames;
     }
     SPM_TRY(vit_run(h, st, (int)(f1 - f0), feats_out + f0 * h->D));
@@ -475,16 +562,16 @@ int plan_ctx(spm_handle* h, CtxPlan* p, const CtxW& w, int R, float* seq, float*
   const int D = h->D;
   GemmEpilogue e1;
   e1.out = h->QKVH; e1.ldo = 3 * HEAD_INNER;
-  SPM_TRY(plan_gemm(&p->qkv, GEMM_TF32, h->HN, D, w.qkv_w, D, R, 3 * HEAD_INNER, D, e1, h->sms));
+  SPM_TRY(plan_gemm(&p->qkv, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->HN, D, w.qkv_w, D, R, 3 * HEAD_INNER, D, e1, h->sms));
   GemmEpilogue e2;  // to_out + bias + the un-normalised sequence (myRes.py:1040)
   e2.bias = w.out_b; e2.residual = seq; e2.ldr = D; e2.out = h->Y; e2.ldo = D;
-  SPM_TRY(plan_gemm(&p->outp, GEMM_TF32, h->AO, HEAD_INNER, w.out_w, HEAD_INNER, R, D, HEAD_INNER, e2, h->sms));
+  SPM_TRY(plan_gemm(&p->outp, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->AO, HEAD_INNER, w.out_w, HEAD_INNER, R, D, HEAD_INNER, e2, h->sms));
   GemmEpilogue e3;
   e3.bias = w.ff0_b; e3.act = ACT_GELU_ERF; e3.out = h->FFH; e3.ldo = HEAD_MLP;
-  SPM_TRY(plan_gemm(&p->ff0, GEMM_TF32, h->Y, D, w.ff0_w, D, R, HEAD_MLP, D, e3, h->sms));
+  SPM_TRY(plan_gemm(&p->ff0, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->Y, D, w.ff0_w, D, R, HEAD_MLP, D, e3, h->sms));
   GemmEpilogue e4;  // x = ff(x) + x (myRes.py:1069)
   e4.bias = w.ff3_b; e4.residual = h->Y; e4.ldr = D; e4.out = out; e4.ldo = D;
-  SPM_TRY(plan_gemm(&p->ff3, GEMM_TF32, h->FFH, HEAD_MLP, w.ff3_w, HEAD_MLP, R, D, HEAD_MLP, e4, h->sms));
+  SPM_TRY(plan_gemm(&p->ff3, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->FFH, HEAD_MLP, w.ff3_w, HEAD_MLP, R, D, HEAD_MLP, e4, h->sms));
   return 0;
 }
 
@@ -499,32 +586,32 @@ int get_head_plan(spm_handle* h, int E, int S, int Q, int W, HeadPlan** out) {
   {
     GemmEpilogue e;
     e.bias = w.mc1_b; e.out = h->C1; e.ldo = D;
-    SPM_TRY(plan_gemm(&pl->mc1, GEMM_TF32, h->XC, 3 * D, w.mc1_w, 3 * D, V * T, D, 3 * D, e, h->sms));
+    SPM_TRY(plan_gemm(&pl->mc1, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->XC, 3 * D, w.mc1_w, 3 * D, V * T, D, 3 * D, e, h->sms));
     e.bias = w.mc2_b; e.out = h->C2;
-    SPM_TRY(plan_gemm(&pl->mc2, GEMM_TF32, h->XC, 3 * D, w.mc2_w, 3 * D, V * T, D, 3 * D, e, h->sms));
+    SPM_TRY(plan_gemm(&pl->mc2, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->XC, 3 * D, w.mc2_w, 3 * D, V * T, D, 3 * D, e, h->sms));
   }
   {
     GemmEpilogue e;
     e.bias = w.tt0_b; e.act = ACT_GELU_ERF; e.out = h->TTH; e.ldo = HEAD_MLP;
-    SPM_TRY(plan_gemm(&pl->tt0, GEMM_TF32, h->TTIN, D, w.tt0_w, D, E * Q, HEAD_MLP, D, e, h->sms));
+    SPM_TRY(plan_gemm(&pl->tt0, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->TTIN, D, w.tt0_w, D, E * Q, HEAD_MLP, D, e, h->sms));
     GemmEpilogue e2;  // query tokens of the `sem` call land after the S support tokens of their episode
     e2.bias = w.tt3_b; e2.out = h->TOK + (long long)V * D; e2.ldo = D;
     e2.out_row_group = Q; e2.out_group_stride = N; e2.out_row_off = S;
-    SPM_TRY(plan_gemm(&pl->tt3, GEMM_TF32, h->TTH, HEAD_MLP, w.tt3_w, HEAD_MLP, E * Q, D, HEAD_MLP, e2, h->sms));
+    SPM_TRY(plan_gemm(&pl->tt3, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->TTH, HEAD_MLP, w.tt3_w, HEAD_MLP, E * Q, D, HEAD_MLP, e2, h->sms));
   }
   {
     GemmEpilogue e;
     e.bias = w.gt0_b; e.act = ACT_LEAKY; e.slope = h->cfg.negative_slope; e.out = h->GTH; e.ldo = h->HT;
-    SPM_TRY(plan_gemm(&pl->gt0, GEMM_TF32, h->TOK, D, w.gt0_w, D, 2 * V, h->HT, D, e, h->sms));
+    SPM_TRY(plan_gemm(&pl->gt0, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->TOK, D, w.gt0_w, D, 2 * V, h->HT, D, e, h->sms));
     GemmEpilogue e2;
     e2.bias = w.gt2_b; e2.act = ACT_SIGMOID; e2.out = h->GT; e2.ldo = D;
-    SPM_TRY(plan_gemm(&pl->gt2, GEMM_TF32, h->GTH, h->HT, w.gt2_w, h->HT, 2 * V, D, h->HT, e2, h->sms));
+    SPM_TRY(plan_gemm(&pl->gt2, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->GTH, h->HT, w.gt2_w, h->HT, 2 * V, D, h->HT, e2, h->sms));
     GemmEpilogue e3;
     e3.bias = w.gv0_b; e3.act = ACT_LEAKY; e3.slope = h->cfg.negative_slope; e3.out = h->GVH; e3.ldo = h->HV;
-    SPM_TRY(plan_gemm(&pl->gv0, GEMM_TF32, h->X, D, w.gv0_w, D, V * T, h->HV, D, e3, h->sms));
+    SPM_TRY(plan_gemm(&pl->gv0, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->X, D, w.gv0_w, D, V * T, h->HV, D, e3, h->sms));
     GemmEpilogue e4;
     e4.bias = w.gv2_b; e4.act = ACT_SIGMOID; e4.out = h->GV; e4.ldo = D;
-    SPM_TRY(plan_gemm(&pl->gv2, GEMM_TF32, h->GVH, h->HV, w.gv2_w, h->HV, V * T, D, h->HV, e4, h->sms));
+    SPM_TRY(plan_gemm(&pl->gv2, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->GVH, h->HV, w.gv2_w, h->HV, V * T, D, h->HV, e4, h->sms));
   }
   SPM_TRY(plan_ctx(h, &pl->c2, w.ctx[1], 2 * V * (T + 1), h->SEQ, h->Z));
   SPM_TRY(plan_ctx(h, &pl->c1, w.ctx[0], E * T * (W + S + 1 + Q), h->SEQ, h->Z1));
@@ -648,7 +735,9 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   SPM_CHECK(cfg != nullptr && out != nullptr, "spm_create: null argument");
   SPM_CHECK(cfg->backbone == SPM_BACKBONE_VIT_B16 || cfg->backbone == SPM_BACKBONE_RN50, "spm_create: unknown backbone");
   SPM_CHECK(cfg->seq_len >= 2 && cfg->seq_len <= 30, "spm_create: seq_len must be in [2, 30]");
-  SPM_CHECK(cfg->precision == SPM_PRECISION_BF16, "spm_create: only SPM_PRECISION_BF16 is implemented");
+  SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->precision == SPM_PRECISION_FP32, "spm_create: unknown precision");
+  SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->backbone == SPM_BACKBONE_VIT_B16,
+            "spm_create: SPM_PRECISION_FP32 is implemented for the ViT-B/16 backbone only");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error("spm_create: no CUDA device -- this library has no CPU path");
@@ -660,6 +749,7 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   SPM_CHECK(major == 10, "spm_create: the kernels are built for sm_100a (B200) only");
   std::unique_ptr<spm_handle> h(new spm_handle());
   h->cfg = *cfg;
+  h->fp32 = cfg->precision == SPM_PRECISION_FP32;
   h->D = cfg->backbone == SPM_BACKBONE_VIT_B16 ? 512 : 1024;
   h->HT = (int)(h->D * cfg->mid_dim_text);
   h->HV = (int)(h->D * cfg->mid_dim_vision);
@@ -671,6 +761,7 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   if (gemm_init(&err)) { set_error(err); return 1; }
   SPM_KERNEL(k_vit_attention_init());
   SPM_KERNEL(k_vit_attention_tc_init());
+  SPM_KERNEL(k_vit_attention_f32_init());
   if (const char* e = getenv("SPM_ATTN")) h->attn_mma = std::string(e) == "mma";
   if (const char* e = getenv("SPM_PRUNE_LAST")) h->prune_last = atoi(e) != 0;
   SPM_KERNEL(k_seq_attention_init());
@@ -702,6 +793,7 @@ int spm_load_weights(spm_handle* h, void* stream, int n, const char* const* name
   for (int i = 0; i < n; ++i) wt.m[names[i]] = {static_cast<const float*>(dev_ptrs[i]), (long long)numel[i]};
   if (h->cfg.backbone == SPM_BACKBONE_VIT_B16) {
     SPM_TRY(load_vit(h, st, wt));
+    if (h->fp32) SPM_TRY(load_vit32(h, st, wt));
   } else {
     auto getter = [&](const std::string& name, long long ne, const float** out) { return wt.get(name, ne, out); };
     SPM_TRY(rn50_create(&h->rn50, st, h->sms, getter));

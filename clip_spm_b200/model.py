@@ -123,11 +123,17 @@ class CNN(nn.Module):
     params{mid_dim_text, mid_dim_vision, negative_slope, alpha, motion_alpha}, optional MODEL.SINGLE_DIRECT,
     optional TRAIN.WAY (number of classes per episode; derived with torch.unique, a host sync, when absent).
     The text tower is not run here: pass the [n_cls, D] prompt features the reference keeps
-    in `text_features_test` / `text_features_train`."""
+    in `text_features_test` / `text_features_train`.
+    precision="bf16": bf16 tcgen05 encoder + tf32 head (what autocast(bfloat16) is to the reference);
+    precision="fp32": every product in fp32 FFMA (the reference's default fp32 arithmetic; slow, for parity)."""
 
-    def __init__(self, cfg, text_features_test=None, text_features_train=None, max_episodes=1, device="cuda"):
+    def __init__(self, cfg, text_features_test=None, text_features_train=None, max_episodes=1, device="cuda",
+                 precision="bf16"):
         super().__init__()
         self.args = cfg
+        if precision not in ("bf16", "fp32"):
+            raise RuntimeError("precision must be 'bf16' (tensor-core path) or 'fp32' (exact-arithmetic parity mode)")
+        self.precision = precision
         self.backbone_name = _cfg_get(cfg, "MODEL.BACKBONE")
         if self.backbone_name not in ("ViT-B/16", "RN50"):
             raise RuntimeError("unsupported MODEL.BACKBONE %r" % (self.backbone_name,))
@@ -192,7 +198,7 @@ class CNN(nn.Module):
             n_text_classes=0 if self.text_features_test is None else int(self.text_features_test.shape[0]),
             mid_dim_text=float(self.params["mid_dim_text"]), mid_dim_vision=float(self.params["mid_dim_vision"]),
             negative_slope=float(self.params["negative_slope"]), alpha=float(self.params["alpha"]),
-            single_direct=int(self.single_direct), precision=0, max_episodes=self.max_episodes, max_support=0,
+            single_direct=int(self.single_direct), precision=0 if self.precision == "bf16" else 1, max_episodes=self.max_episodes, max_support=0,
             max_query=0, max_way=0)
         h = ctypes.c_void_p()
         with torch.cuda.device(self._dev):

@@ -50,10 +50,10 @@ def case_inputs(name):
                 feats=feats, single=single, head_only=head_only)
 
 
-def build_cuda_model(ci, max_episodes=1):
+def build_cuda_model(ci, max_episodes=1, precision="bf16"):
     from clip_spm_b200 import CNN
     net = CNN(make_cfg(ci["backbone"], ci["T"], ci["single"], ci["way"]), text_features_test=ci["text"],
-              max_episodes=max_episodes)
+              max_episodes=max_episodes, precision=precision)
     missing, unexpected = net.load_state_dict(ci["weights"], strict=False)
     assert not unexpected, unexpected
     if not ci["head_only"]:

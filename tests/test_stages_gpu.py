@@ -203,3 +203,40 @@ def test_rn50_encoder_and_forward_match_reference_golden():
     abs_err = float((out["logits"].cpu() - g["logits"]).abs().max())
     safe = g["margin"] > 4 * abs_err
     assert torch.equal(out["logits"][0].argmax(-1).cpu()[safe], g["pred"].long()[safe])
+
+
+TOL_FP32 = 1e-4   # north_star: logits and features within 1e-4 relative in the fp32 mode
+
+
+@pytest.mark.parametrize("name", ["vit_2w1s_t2_p0", "vit_5w1s_t8_p1"])
+def test_fp32_mode_matches_reference_golden(name):
+    """SPM_PRECISION_FP32 (exact FFMA arithmetic): features, logits, dists, loss and EVERY predicted class"""
+    ci, g = H.case_inputs(name), H.golden(name)
+    net = H.build_cuda_model(ci, precision="fp32")
+    ep = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in ci["episode"].items()}
+    su = net.encode_frames(ep["context_images"])
+    err_f = H.rel_err(su.cpu().view(g["su"].shape), g["su"])
+    out = net(ep)
+    err_l = H.rel_err(out["logits"].cpu(), g["logits"])
+    print("\n%s fp32 mode: feature rel err %.2e, logits rel err %.2e" % (name, err_f, err_l))
+    assert err_f < TOL_FP32 and err_l < TOL_FP32
+    assert H.rel_err(out["dists"].cpu(), g["dists"]) < 1e-3
+    abs_err = float((out["logits"].cpu() - g["logits"]).abs().max())
+    safe = g["margin"] > 4 * abs_err
+    assert bool(safe.all()), "fp32 mode must resolve every query of the golden episodes"
+    assert torch.equal(out["logits"][0].argmax(-1).cpu(), g["pred"].long())
+    loss, acc = net.evaluate(ep)
+    assert float(acc) == float(g["acc"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-3 * max(1.0, abs(float(g["loss"])))
+
+
+@pytest.mark.parametrize("name", ["head_5w5s_t8", "head_5w1s_t16", "head_5w2s_t8_q3_single"])
+def test_fp32_mode_head_matches_reference_golden(name):
+    ci, g = H.case_inputs(name), H.golden(name)
+    net = H.build_cuda_model(ci, precision="fp32")
+    ep = ci["episode"]
+    su, qu = ci["feats"]
+    out = net.head(su.cuda(), qu.cuda(), ep["context_labels"], ep["real_support_labels"], ep["real_target_labels"])
+    assert H.rel_err(out["logits"].cpu().unsqueeze(0), g["logits"]) < TOL_FP32
+    assert H.rel_err(out["dists"][0].cpu(), g["dists"]) < 1e-3
+    assert torch.equal(out["logits"][0].argmax(-1).cpu(), g["pred"].long())
