@@ -27,7 +27,13 @@ import torch  # noqa: E402
 WAY, SHOT, QPC, T, N_TEXT = 5, 5, 1, 8, 24           # BASELINE.json configs[1]: Kinetics-shape 5-way 5-shot
 S, Q = WAY * SHOT, WAY * QPC
 FRAMES = (S + Q) * T                                  # 240 frames per episode
-VIT_GFLOP_PER_FRAME = 35.127
+VIT_GFLOP_PER_FRAME = 35.127                          # BASELINE.md section 3 (full tower)
+# executed: the last block's out-proj / MLP run on the class token only (exact pruning, SURVEY 8d asks to count
+# executed FLOPs): 35.127 - (0.2324 + 0.9296 + 0.9296) * 196/197
+VIT_GFLOP_PER_FRAME_EXECUTED = 33.046
+# DRAM bytes per launch of the dominant kernel (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean of
+# the four encoder GEMM flavours at 240 frames; profiles/r01_ncu_gemm_2cta_vs_1cta.txt).  Algorithmic mean: 403 MB.
+GEMM_DRAM_BYTES_PER_LAUNCH_NCU = 356.3e6
 WORKLOAD = "CLIP-SPM ViT-B/16 5-way 5-shot Kinetics-shape eval (S=25,Q=5,T=8: 240 frames@224 per episode), bf16"
 
 
@@ -267,9 +273,11 @@ def main():
                 "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
                 "frac": (achieved / peaks["bf16"]) if achieved else None, "peak_source": peaks["which"] +
                 " bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks["which"] == "measured" else "fallback 1590",
-                "traffic": None, "launches_timed": int(cnt4[dom]),
+                "traffic": GEMM_DRAM_BYTES_PER_LAUNCH_NCU, "traffic_unit": "bytes/launch (ncu, mean of the 4 encoder GEMMs)",
+                "launches_timed": int(cnt4[dom]),
                 "gemm_share_of_step": gemm_ms_all / (ms if ms > 0 else 1.0),
-                "whole_step_tflops": value / world * FRAMES * VIT_GFLOP_PER_FRAME / 1e3}
+                "whole_step_tflops_executed": value / world * FRAMES * VIT_GFLOP_PER_FRAME_EXECUTED / 1e3,
+                "whole_step_tflops_nominal": value / world * FRAMES * VIT_GFLOP_PER_FRAME / 1e3}
     line = {"metric": "episodes_per_sec", "value": value, "unit": "episodes/s", "frames_per_s": value * FRAMES,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",

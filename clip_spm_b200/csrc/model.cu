@@ -816,8 +816,9 @@ int spm_set_text_features(spm_handle* h, void* stream, const float* table, int n
 }
 
 int spm_encode_frames(spm_handle* h, void* stream, const float* images, int n_frames, float* feats_out) {
-  SPM_CHECK(h != nullptr && images != nullptr && feats_out != nullptr, "spm_encode_frames: null argument");
-  if (n_frames <= 0) return 0;
+  SPM_CHECK(h != nullptr, "spm_encode_frames: null handle");
+  if (n_frames <= 0) return 0;  // empty input: nothing to do (pointers may be null)
+  SPM_CHECK(images != nullptr && feats_out != nullptr, "spm_encode_frames: null argument");
   Segment seg{images, n_frames};
   return encode_segments(h, (cudaStream_t)stream, &seg, 1, feats_out);
 }

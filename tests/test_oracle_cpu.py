@@ -124,3 +124,35 @@ def test_library_exports_every_declared_symbol():
     loaded = _lib.load()
     assert loaded.spm_abi_version() == 1
     assert isinstance(loaded.spm_last_error(), bytes)
+
+
+def _c_otam():
+    import subprocess
+    so = os.path.join(ROOT, "oracle", "_ref", "libotam_ref.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    lib = ctypes.CDLL(so)
+    lib.otam_distance_ref.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    return lib
+
+
+def c_otam_distance(support, target, single_direct=False):
+    """oracle/otam_ref.c (plain C, double accumulation) on [W,T,D] / [Q,T,D] float tensors -> [Q,W]"""
+    lib = _c_otam()
+    support, target = support.contiguous().float(), target.contiguous().float()
+    W, T, D = support.shape
+    Q = target.shape[0]
+    out = torch.empty(Q, W)
+    lib.otam_distance_ref(support.data_ptr(), target.data_ptr(), W, Q, T, D, int(single_direct), out.data_ptr())
+    return out
+
+
+@pytest.mark.parametrize("W,Q,T,D,single", [(5, 5, 8, 512, False), (3, 2, 16, 64, False), (4, 1, 8, 128, True),
+                                            (1, 1, 2, 32, False)])
+def test_c_restatement_of_otam_matches_python_oracle(W, Q, T, D, single):
+    """two independent restatements of myRes.py:756-765,821-855 (C / torch) agree"""
+    g = torch.Generator().manual_seed(W * 10 + T)
+    sup, tgt = torch.randn(W, T, D, generator=g), torch.randn(Q, T, D, generator=g)
+    a = c_otam_distance(sup, tgt, single)
+    b = O.otam_distance(sup.double(), tgt.double(), single).float()
+    assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)

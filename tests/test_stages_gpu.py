@@ -240,3 +240,48 @@ def test_fp32_mode_head_matches_reference_golden(name):
     assert H.rel_err(out["logits"].cpu().unsqueeze(0), g["logits"]) < TOL_FP32
     assert H.rel_err(out["dists"][0].cpu(), g["dists"]) < 1e-3
     assert torch.equal(out["logits"][0].argmax(-1).cpu(), g["pred"].long())
+
+
+def test_otam_matches_c_restatement():
+    """CUDA wavefront kernel against the plain-C oracle (oracle/otam_ref.c)"""
+    from clip_spm_b200 import ops
+    from tests.test_oracle_cpu import c_otam_distance
+    g = torch.Generator().manual_seed(17)
+    sup, tgt = torch.randn(5, 8, 512, generator=g), torch.randn(5, 8, 512, generator=g)
+    out = ops.otam_distance(sup[None].cuda(), tgt[None].cuda(), False)[0].cpu()
+    assert H.rel_err(out, c_otam_distance(sup, tgt)) < TOL_OTAM
+
+
+def test_encoder_edge_cases():
+    """single frame, frame counts that are not tile multiples, more frames than one workspace chunk (256)"""
+    ci = H.case_inputs("vit_2w1s_t2_p0")
+    net = H.build_cuda_model(ci)
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.rand(3, 3, 224, 224, generator=g).cuda()
+    one = net.encode_frames(imgs[:1])
+    three = net.encode_frames(imgs)
+    assert one.shape == (1, 512) and torch.allclose(one, three[:1], atol=2e-3, rtol=2e-3)
+    big = imgs.repeat(87, 1, 1, 1)[:259]                      # 259 frames: chunks of 256 + 3
+    out = net.encode_frames(big)
+    assert out.shape == (259, 512)
+    assert torch.allclose(out[256:259], three[(torch.arange(256, 259) % 3)], atol=2e-3, rtol=2e-3)
+    assert torch.isfinite(out).all()
+    assert net.encode_frames(imgs[:0]).shape == (0, 512)      # empty input: no launch, empty result
+
+
+def test_head_ragged_episode_shapes():
+    """1 query, unequal shots per class (the reference's torch.stack in taskM cannot even run this), W == S"""
+    ci = H.case_inputs("head_5w5s_t8")
+    g = torch.Generator().manual_seed(9)
+    for labels, Q in ((torch.tensor([2., 0., 1., 0., 2., 2., 1.]), 1), (torch.tensor([0., 1., 2.]), 4)):
+        ci2 = dict(ci); ci2["way"] = 3
+        net = H.build_cuda_model(ci2)
+        S = labels.numel()
+        su, qu = torch.randn(S, 8, 512, generator=g), torch.randn(Q, 8, 512, generator=g)
+        rs, rt = labels.clone(), torch.zeros(Q)
+        out = net.head(su.cuda(), qu.cuda(), labels, rs, rt)
+        assert out["logits"].shape == (1, Q, 3) and torch.isfinite(out["logits"]).all()
+        if S == 3:   # equal shots: the oracle (like the reference) can run it
+            with torch.no_grad():
+                ref = O.head_forward(ci["weights"], ci["text"], su, qu, labels, rs, rt, O.DEFAULT_PARAMS)
+            assert H.rel_err(out["logits"].cpu(), ref["logits"]) < TOL_HEAD
