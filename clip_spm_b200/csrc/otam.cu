@@ -16,24 +16,32 @@ namespace spm {
 
 namespace {
 constexpr float LBDA = 0.5f;
+constexpr float INV_LBDA = 2.0f;
 
+// soft-min with lambda = 0.5 in the min-shifted form: -l*log(sum exp(-x/l)) = min - l*log(sum exp(-(x-min)/l)).
+// Mathematically identical to the reference's expression (myRes.py:838-853), better conditioned (all exponents <= 0,
+// the sum lies in [1, 3]) -- which also makes the fast intrinsics accurate to ~1e-6 here.
 __device__ __forceinline__ float softmin2(float a, float b) {
-  return -LBDA * logf(expf(-a / LBDA) + expf(-b / LBDA));
+  const float mn = fminf(a, b), mx = fmaxf(a, b);
+  return mn - LBDA * __logf(1.f + __expf((mn - mx) * INV_LBDA));
 }
 __device__ __forceinline__ float softmin3(float a, float b, float c) {
-  return -LBDA * logf(expf(-a / LBDA) + expf(-b / LBDA) + expf(-c / LBDA));
+  const float mn = fminf(a, fminf(b, c));
+  const float s = __expf((mn - a) * INV_LBDA) + __expf((mn - b) * INV_LBDA) + __expf((mn - c) * INV_LBDA);
+  return mn - LBDA * __logf(s);
 }
 
-// One warp, one DP.  dist(l, j): l = row (0..T-1), j = unpadded column (0..T-1).  Returns C[T-1, T+1] in every lane.
-template <class DistFn>
-__device__ __forceinline__ float otam_wavefront(int T, DistFn dist) {
-  const int m = threadIdx.x & 31;  // padded column owned by this lane
-  float v1 = 0.f, v2 = 0.f;        // this lane's last / second-to-last computed cells
+// One DP per SEG-lane segment of a warp (SEG = 16: two DPs per warp when T + 2 <= 16, else SEG = 32).
+// dist(l, j): l = row (0..T-1), j = unpadded column (0..T-1).  Returns C[T-1, T+1] in every lane of the segment.
+template <int SEG, class DistFn>
+__device__ __forceinline__ float otam_wavefront(int T, bool valid, DistFn dist) {
+  const int m = threadIdx.x & (SEG - 1);  // padded column owned by this lane
+  float v1 = 0.f, v2 = 0.f;               // this lane's last / second-to-last computed cells
   for (int k = 0; k <= 2 * T; ++k) {
-    const float left = __shfl_up_sync(0xffffffffu, v1, 1);   // C[l,   m-1]
-    const float diag = __shfl_up_sync(0xffffffffu, v2, 1);   // C[l-1, m-1]
+    const float left = __shfl_up_sync(0xffffffffu, v1, 1, SEG);   // C[l,   m-1]
+    const float diag = __shfl_up_sync(0xffffffffu, v2, 1, SEG);   // C[l-1, m-1]
     const int l = k - m;
-    if (l >= 0 && l < T && m <= T + 1) {
+    if (valid && l >= 0 && l < T && m <= T + 1) {
       const float d = (m >= 1 && m <= T) ? dist(l, m - 1) : 0.f;
       float c;
       if (m == 0) c = 0.f;                                    // column 0 is never written (stays 0)
@@ -44,12 +52,13 @@ __device__ __forceinline__ float otam_wavefront(int T, DistFn dist) {
       v1 = c;
     }
   }
-  return __shfl_sync(0xffffffffu, v1, T + 1);
+  return __shfl_sync(0xffffffffu, v1, T + 1, SEG);
 }
 }  // namespace
 
-template <int NV>  // D = NV * 128
-__global__ void __launch_bounds__(256)
+// NV: D = NV*128.  TP: number of dot-product accumulators kept per lane (power of two >= T).
+template <int NV, int TP>
+__global__ void __launch_bounds__(256, (TP <= 8 ? 5 : (TP <= 16 ? 4 : 2)))
 otam_kernel(const float* __restrict__ sup, long long s_p, long long s_w, long long s_t, const float* __restrict__ tgt,
             long long t_p, long long t_q, long long t_t, int W, int Q, int T, int single_direct, float alpha,
             float beta, float* __restrict__ out) {
@@ -70,7 +79,7 @@ otam_kernel(const float* __restrict__ sup, long long s_p, long long s_w, long lo
   for (int t = warp; t < T; t += 8) {
     float a = 0.f;
     for (int c = lane; c < D / 4; c += 32) {
-      const float4 v = reinterpret_cast<const float4*>(sq + t * D)[c];
+      const float4 v = reinterpret_cast<float4*>(sq + t * D)[c];
       a += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
     }
 #pragma unroll
@@ -78,7 +87,9 @@ otam_kernel(const float* __restrict__ sup, long long s_p, long long s_w, long lo
     if (lane == 0) qn[t] = sqrtf(a);
   }
   __syncthreads();
-  // ---- phase 1: cosine distances
+  // ---- phase 1: cosine distances.  A warp streams one support frame (coalesced float4, kept in registers) and
+  // accumulates its dot product with every query frame; the TP partial sums per lane are then combined with a
+  // reduce-scatter butterfly (TP-1 + log2(32/TP) shuffles instead of 5 per dot product).
   for (int j = warp; j < W * T; j += 8) {
     const int w = j / T, ts = j % T;
     const float4* sp = reinterpret_cast<const float4*>(sup + p * s_p + w * s_w + ts * s_t);
@@ -86,34 +97,66 @@ otam_kernel(const float* __restrict__ sup, long long s_p, long long s_w, long lo
     float nn = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      sv[i] = sp[i * 32 + lane];
+      sv[i] = __ldg(sp + i * 32 + lane);
       nn += (sv[i].x * sv[i].x + sv[i].y * sv[i].y) + (sv[i].z * sv[i].z + sv[i].w * sv[i].w);
+    }
+    float acc[TP];
+#pragma unroll
+    for (int t = 0; t < TP; ++t) {
+      float a = 0.f;
+      if (t < T) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float4 qv = reinterpret_cast<const float4*>(sq + t * D)[i * 32 + lane];
+          a = fmaf(sv[i].x, qv.x, a); a = fmaf(sv[i].y, qv.y, a); a = fmaf(sv[i].z, qv.z, a); a = fmaf(sv[i].w, qv.w, a);
+        }
+      }
+      acc[t] = a;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
-    const float sn = sqrtf(nn);
-    for (int t = 0; t < T; ++t) {
-      float a = 0.f;
+    // reduce-scatter: after the round with offset `off`, a lane keeps the half of the accumulators selected by
+    // its bit `off`; the index it finally owns is t_own (built from the same bits)
+    int t_own = 0;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float4 qv = reinterpret_cast<const float4*>(sq + t * D)[i * 32 + lane];
-        a += (sv[i].x * qv.x + sv[i].y * qv.y) + (sv[i].z * qv.z + sv[i].w * qv.w);
+    for (int off = 16, n = TP; n > 1; off >>= 1, n >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int jj = 0; jj < n / 2; ++jj) {
+        const float mine = upper ? acc[jj + n / 2] : acc[jj];
+        const float other = upper ? acc[jj] : acc[jj + n / 2];
+        acc[jj] = mine + __shfl_xor_sync(0xffffffffu, other, off);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) dist[(w * T + t) * T + ts] = 1.f - a / (qn[t] * sn + 0.01f);
+      if (upper) t_own += n / 2;
     }
+    float tot = acc[0];
+#pragma unroll
+    for (int off = 16 / TP; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+    if ((lane & (32 / TP - 1)) == 0 && t_own < T)
+      dist[(w * T + t_own) * T + ts] = 1.f - tot / (qn[t_own] * sqrtf(nn) + 0.01f);
   }
   __syncthreads();
-  // ---- phase 2: one warp per (class, direction) DP
+  // ---- phase 2: the (class, direction) DPs as anti-diagonal wavefronts, two per warp when a DP fits 16 lanes
   const int ndir = single_direct ? 1 : 2;
-  for (int j = warp; j < W * ndir; j += 8) {
-    const int w = j / ndir, dir = j % ndir;
-    const float* dw = dist + w * T * T;
-    float r;
-    if (dir == 0) r = otam_wavefront(T, [&](int l, int c) { return dw[l * T + c]; });   // rows: query frames
-    else r = otam_wavefront(T, [&](int l, int c) { return dw[c * T + l]; });            // transposed
-    if (lane == 0) res[w * 2 + dir] = r;
+  const int n_dp = W * ndir;
+  if (T + 2 <= 16) {
+    for (int j0 = warp * 2; j0 < n_dp; j0 += 16) {
+      const int j = j0 + (lane >> 4);
+      const bool valid = j < n_dp;
+      const int w = valid ? j / ndir : 0, dir = valid ? j % ndir : 0;
+      const float* dw = dist + w * T * T;
+      const float r = (dir == 0) ? otam_wavefront<16>(T, valid, [&](int l, int c) { return dw[l * T + c]; })
+                                 : otam_wavefront<16>(T, valid, [&](int l, int c) { return dw[c * T + l]; });
+      if (valid && (lane & 15) == 0) res[w * 2 + dir] = r;
+    }
+  } else {
+    for (int j = warp; j < n_dp; j += 8) {
+      const int w = j / ndir, dir = j % ndir;
+      const float* dw = dist + w * T * T;
+      const float r = (dir == 0) ? otam_wavefront<32>(T, true, [&](int l, int c) { return dw[l * T + c]; })
+                                 : otam_wavefront<32>(T, true, [&](int l, int c) { return dw[c * T + l]; });
+      if (lane == 0) res[w * 2 + dir] = r;
+    }
   }
   __syncthreads();
   for (int w = threadIdx.x; w < W; w += blockDim.x) {
@@ -126,12 +169,18 @@ otam_kernel(const float* __restrict__ sup, long long s_p, long long s_w, long lo
 constexpr int OTAM_SMEM_MAX = 200 * 1024;
 static size_t otam_smem(int W, int T, int D) { return (size_t)(T * D + 32 + W * T * T + 2 * W) * sizeof(float); }
 
+#define SPM_OTAM_FOR_ALL(X) X(4, 8) X(4, 16) X(4, 32) X(8, 8) X(8, 16) X(8, 32)
+
 int k_otam_init() {
   const int bytes = OTAM_SMEM_MAX;
-  cudaError_t e = cudaFuncSetAttribute(otam_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(otam_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  return (int)e;
+#define SPM_OTAM_ATTR(NV, TP)                                                                                      \
+  {                                                                                                                \
+    cudaError_t e = cudaFuncSetAttribute(otam_kernel<NV, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    if (e != cudaSuccess) return (int)e;                                                                           \
+  }
+  SPM_OTAM_FOR_ALL(SPM_OTAM_ATTR)
+#undef SPM_OTAM_ATTR
+  return 0;
 }
 
 int k_otam(cudaStream_t st, const float* sup, long long s_p, long long s_w, long long s_t, const float* tgt,
@@ -142,10 +191,13 @@ int k_otam(cudaStream_t st, const float* sup, long long s_p, long long s_w, long
   dim3 grid(Q, P);
   const size_t smem = otam_smem(W, T, D);
   if (smem > (size_t)OTAM_SMEM_MAX) return -2;
-  if (D == 512)
-    otam_kernel<4><<<grid, 256, smem, st>>>(sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, W, Q, T, single_direct, alpha, beta, out);
-  else
-    otam_kernel<8><<<grid, 256, smem, st>>>(sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, W, Q, T, single_direct, alpha, beta, out);
+  const int nv = D / 128, tp = T <= 8 ? 8 : (T <= 16 ? 16 : 32);
+#define SPM_OTAM_LAUNCH(NV, TP)                                                                                    \
+  if (nv == NV && tp == TP)                                                                                        \
+    otam_kernel<NV, TP><<<grid, 256, smem, st>>>(sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, W, Q, T, single_direct,   \
+                                                 alpha, beta, out);
+  SPM_OTAM_FOR_ALL(SPM_OTAM_LAUNCH)
+#undef SPM_OTAM_LAUNCH
   cudaError_t e = cudaGetLastError();
   count_launch();
   return (int)e;
