@@ -18,6 +18,9 @@ struct GemmEpilogue {
   int ldr = 0;
   const void* residual_bf16 = nullptr;  // bf16 residual (needs a bf16 output), same row mapping / ldr
   int relu_after_residual = 0;          // out = relu(act(acc + bias) + residual)  (ResNet bottleneck tail)
+  // zero-bordered NHWC images (rn50.cu): rows are pixels of [H2 x W2] padded images; rows on the 1-pixel border are
+  // written as zeros so the tensor stays a valid zero-padded input of the next 3x3 convolution (0 = off)
+  int border_w2 = 0, border_h2w2 = 0;
   int res_row_mod = 0;    // 0: rrow = orow ; >0: rrow = (m % res_row_mod) + res_row_off  (positional table)
   int res_row_off = 0;
   // 0: orow = m ; >0: orow = (m / out_row_group) * out_group_stride + (m % out_row_group) + out_row_off
@@ -42,6 +45,10 @@ struct GemmOp {
   const void* simt_a = nullptr;  // GEMM_F32_SIMT: raw operand pointers / row strides (no tensor maps)
   const void* simt_b = nullptr;
   long long simt_lda = 0, simt_ldb = 0;
+  // implicit 3x3 convolution (stride 1, pad 1) over a zero-bordered NHWC image matrix [rows, C]: k-block kb reads
+  // channel block kb % conv_cblocks of tap kb / conv_cblocks, i.e. the same matrix at the constant row offset
+  // (tap/3 - 1) * conv_w2 + (tap%3 - 1) -- only the TMA coordinate changes, no im2col is materialised (0 = plain GEMM)
+  int conv_w2 = 0, conv_cblocks = 0;
   int two_cta = 0;  // 1: launched as 2-CTA clusters (gemm2_tcgen05.cu), 256x256 tile per CTA pair
 };
 
@@ -50,6 +57,10 @@ struct GemmOp {
 int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
               const GemmEpilogue& ep, int num_sms, const char** err);
 int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err);
+// 3x3/stride-1/pad-1 convolution as an implicit GEMM: A = zero-bordered NHWC activations [rows, C] bf16 (rows = all
+// padded pixels), B = folded weights [Cout, 9 * cpad] with column tap*cpad + c (cpad = C rounded up to 64)
+int gemm_plan_conv3x3(GemmOp* op, const void* A, int C, int rows, int W2, const void* B, int Cout, const GemmEpilogue& ep,
+                      int num_sms, const char** err);
 // one-time: opt into large dynamic shared memory for every instantiation
 int gemm_init(const char** err);
 // 2-CTA kernel (gemm2_tcgen05.cu)

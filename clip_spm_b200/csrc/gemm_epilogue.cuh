@@ -113,6 +113,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint3
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act, ep.slope);
       }
+      if (ep.border_w2 > 0) {  // zero-bordered image rows stay zero (thread == pixel row)
+        const int pr = (m_base + lane) % ep.border_h2w2, py = pr / ep.border_w2, px = pr - py * ep.border_w2;
+        if (py == 0 || px == 0 || px == ep.border_w2 - 1 || py == ep.border_h2w2 / ep.border_w2 - 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+      }
       const uint32_t srow = stg_u + (uint32_t)(lane * 128);
       if (ep.out_bf16) {
 #pragma unroll

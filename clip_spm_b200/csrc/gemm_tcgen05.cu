@@ -26,6 +26,7 @@ namespace spm {
 struct GemmArgs {
   GemmEpilogue ep;
   int M, N, K;
+  int conv_w2, conv_cblocks;  // implicit 3x3 convolution (see GemmOp), 0 = plain GEMM
 };
 
 template <int BN, int KIND>
@@ -102,17 +103,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += gridDim.x; }
         }
       };
-      for (int i = 0; i < GEMM_L2_PREFETCH_KB; ++i) prefetch_next();
+      const bool conv = args.conv_cblocks > 0;  // taps re-read an L2-resident activation: no prefetch needed
+      if (!conv)
+        for (int i = 0; i < GEMM_L2_PREFETCH_KB; ++i) prefetch_next();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / num_n) * T::BM;
         const int n0 = (tile % num_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          prefetch_next();
+          if (!conv) prefetch_next();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * T::STAGE_BYTES;
           uint8_t* sb = sa + T::A_BYTES;
           mbar_expect_tx(&full_bar[stage], T::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * T::BK, m0);
+          if (conv) {
+            const int tap = kb / args.conv_cblocks, cb = kb - tap * args.conv_cblocks;
+            const int roff = (tap / 3 - 1) * args.conv_w2 + (tap % 3 - 1);  // rows outside the matrix read as zeros
+            tma_load_2d(sa, &tmA, &full_bar[stage], cb * T::BK, m0 + roff);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * T::BK, m0);
+          }
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * T::BK, n0);
           if (++stage == T::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -285,9 +294,30 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   return 0;
 }
 
+int gemm_plan_conv3x3(GemmOp* op, const void* A, int C, int rows, int W2, const void* B, int Cout, const GemmEpilogue& ep,
+                      int num_sms, const char** err) {
+  if (C % 8 != 0 || Cout % 32 != 0) { *err = "conv3x3: C must be a multiple of 8 and Cout of 32"; return 1; }
+  const int cpad = (C + 63) / 64 * 64;
+  // plan as a [rows, 9*cpad] x [Cout, 9*cpad] GEMM (fictitious A stride), then describe the real A: [rows, C]
+  if (gemm_plan(op, GEMM_BF16, A, 9LL * cpad, B, 9LL * cpad, rows, Cout, 9 * cpad, ep, num_sms, err)) return 1;
+  // (columns >= C of a box read as zeros, rows outside [0, rows) too)
+  if (make_operand_map(&op->ta, GEMM_BF16, A, C, rows, C, 128, err)) return 1;
+  if (op->two_cta) {  // the pair kernel does not know about taps: fall back to the 1-CTA kernel
+    op->two_cta = 0;
+    op->bn = (Cout % 256 == 0) ? 256 : 128;
+    const long long tiles = (long long)((rows + 127) / 128) * ((Cout + op->bn - 1) / op->bn);
+    op->grid = (int)(tiles < num_sms ? tiles : num_sms);
+    if (make_operand_map(&op->tb, GEMM_BF16, B, 9LL * cpad, Cout, 9 * cpad, op->bn, err)) return 1;
+  }
+  op->conv_w2 = W2;
+  op->conv_cblocks = cpad / 64;
+  return 0;
+}
+
 int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
   GemmArgs a;
   a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K;
+  a.conv_w2 = op->conv_w2; a.conv_cblocks = op->conv_cblocks;
   int slot = -1;
   const bool prof = profile_gemm_begin(stream, (op->kind & 1) * 2 + (op->bn == 256 ? 1 : 0),
                                        2.0 * (double)op->M * (double)op->N * (double)op->K, &slot);

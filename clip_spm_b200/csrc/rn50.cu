@@ -1,17 +1,20 @@
 // CLIP ModifiedResNet-50 frame encoder (models/clip_fsar.py:502-608 Bottleneck / ModifiedResNet, :396-500
 // AttentionPool2d) for sm_100a.
 //
-// Activations are NHWC bf16, so every convolution is a GEMM on the tcgen05 kernel of gemm_tcgen05.cu:
-//   1x1 conv            A = the activation matrix [F*H*W, Cin] as it lies in memory, B = folded weight [Cout, Cin]
-//   3x3 conv (pad 1)    A = im2col [F*H*W, 9*Cin] (tap-major, channel-minor), B = folded weight [Cout, 9*Cin]
+// Activations are NHWC bf16 images with a 1-pixel ZERO BORDER ([F, H+2, W+2, C]), so every convolution is a GEMM on
+// the tcgen05 kernel of gemm_tcgen05.cu over the matrix [F*(H+2)*(W+2), C] exactly as it lies in memory:
+//   1x1 conv            A = that matrix, B = folded weight [Cout, Cin]
+//   3x3 conv (pad 1)    IMPLICIT GEMM: tap (dy,dx) of the window is the same matrix shifted by the constant row offset
+//                       dy*(W+2)+dx, so k-block kb just loads TMA box (channel block, m0 + offset(tap)); no im2col is
+//                       ever materialised and the 9 re-reads hit L2.  B = folded weight [Cout, 9*Cpad]
 //   stem conv1 (s=2)    A = im2col straight from the fp32 NCHW image, K = 27 padded to 32
+// Border rows are computed like any other row and written as zeros by the epilogue (GemmEpilogue::border_*), which
+// keeps every tensor a valid zero-padded input for the next 3x3 convolution.
 // BatchNorm (eval, running statistics) is folded into the weights and a per-channel bias at load time; ReLU, the
 // bottleneck's residual add and the final ReLU run in the GEMM epilogue.  AvgPool2d(2) (stem, anti-aliased strides,
 // downsample branches) is a vectorised NHWC kernel.  The attention pool uses only the mean-token query
 // (clip_fsar.py:481-499): k/v projections as one fused GEMM over 50 tokens, q projection on the F mean tokens, a
 // one-warp-per-(frame, head) softmax, then c_proj.
-// This first version materialises the im2col matrices (HBM traffic ~2x the algorithmic minimum); a TMA-im2col
-// implicit GEMM is the follow-up.
 #include <algorithm>
 #include <map>
 #include <memory>
@@ -31,8 +34,8 @@ namespace {
 constexpr int RN_CHUNK = 64;
 constexpr int EMB = 2048, HEADS = 32, HD = 64, OUT_DIM = 1024, NTOK = 50;
 constexpr long long FRAME_ELEMS = 3LL * 224 * 224;
-constexpr long long SCRATCH_PER_FRAME = 12544LL * 64;   // largest activation: 112x112x64 == 56x56x256
-constexpr long long COL_PER_FRAME = 12544LL * 288;      // largest im2col: 112x112x(9*32) == 56x56x(9*128)
+constexpr long long SCRATCH_PER_FRAME = 58LL * 58 * 256;   // largest padded activation: 58x58x256 (> 114x114x64)
+constexpr long long COL_PER_FRAME = 114LL * 114 * 32;      // stem conv1 im2col over the padded 114x114 grid
 
 #define RN_LAUNCH_CHECK()                                                         \
   do {                                                                            \
@@ -44,16 +47,19 @@ constexpr long long COL_PER_FRAME = 12544LL * 288;      // largest im2col: 112x1
 // ---------------------------------------------------------------------------------------------------------
 // load-time folding:  w [Cout, Cin, kh, kw] fp32 + BN -> wout [Cout, Kpad] bf16 (k = (ky*kw + kx)*Cin + c), bias
 // ---------------------------------------------------------------------------------------------------------
+// column k = tap * cpad + c (cpad >= Cin: channels of a tap padded with zero columns), zero beyond kh*kw*cpad
 __global__ void fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b,
                                  const float* __restrict__ mean, const float* __restrict__ var, int Cout, int Cin,
-                                 int kh, int kw, int Kpad, __nv_bfloat16* __restrict__ wout, float* __restrict__ bias) {
+                                 int kh, int kw, int cpad, int Kpad, __nv_bfloat16* __restrict__ wout,
+                                 float* __restrict__ bias) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Cout * Kpad) return;
   const int o = (int)(i / Kpad), k = (int)(i % Kpad);
   const float scale = g[o] * rsqrtf(var[o] + 1e-5f);
   float v = 0.f;
-  if (k < kh * kw * Cin) {
-    const int c = k % Cin, tap = k / Cin, ky = tap / kw, kx = tap % kw;
+  const int c = k % cpad, tap = k / cpad;
+  if (tap < kh * kw && c < Cin) {
+    const int ky = tap / kw, kx = tap % kw;
     v = w[(((long long)o * Cin + c) * kh + ky) * kw + kx] * scale;
   }
   wout[i] = __float2bfloat16_rn(v);
@@ -67,12 +73,14 @@ __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restr
 // ---------------------------------------------------------------------------------------------------------
 // activation-side kernels (NHWC bf16, 8 channels = 16 bytes per thread)
 // ---------------------------------------------------------------------------------------------------------
-// stem conv1: 3x3, stride 2, pad 1 on the fp32 NCHW image -> [F*112*112, 32] (27 taps, 5 zero columns)
+// stem conv1: 3x3, stride 2, pad 1 on the fp32 NCHW image -> rows of the zero-bordered 114x114 output grid,
+// [F*114*114, 32] (27 taps, 5 zero columns; border rows all zero)
 __global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, long long rows) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  const int ox = (int)(r % 112), oy = (int)((r / 112) % 112);
-  const long long f = r / (112 * 112);
+  const int ox = (int)(r % 114) - 1, oy = (int)((r / 114) % 114) - 1;
+  const long long f = r / (114 * 114);
+  const bool border = ox < 0 || oy < 0 || ox >= 112 || oy >= 112;
   const float* base = img + f * FRAME_ELEMS;
   __align__(16) __nv_bfloat16 v[32];
 #pragma unroll
@@ -82,7 +90,7 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16*
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
-      if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) {
+      if (!border && iy >= 0 && iy < 224 && ix >= 0 && ix < 224) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           v[(ky * 3 + kx) * 3 + c] = __float2bfloat16_rn(__ldg(base + ((long long)c * 224 + iy) * 224 + ix));
@@ -95,24 +103,6 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16*
   for (int j = 0; j < 4; ++j) o[j] = s[j];
 }
 
-// 3x3, stride 1, pad 1: in [F,H,W,C] -> out [F*H*W, 9*C], column = tap*C + c
-__global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int H, int W,
-                                 int C, long long n_units) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_units) return;
-  const int c8 = C / 8;
-  const int cu = (int)(i % c8);
-  const int tap = (int)((i / c8) % 9);
-  const long long row = i / (9LL * c8);
-  const int x = (int)(row % W), y = (int)((row / W) % H);
-  const long long f = row / ((long long)W * H);
-  const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-    v = __ldg(reinterpret_cast<const uint4*>(in + ((f * H + iy) * W + ix) * C) + cu);
-  reinterpret_cast<uint4*>(out)[i] = v;
-}
-
 __device__ __forceinline__ float2 bf2(uint32_t u) {
   return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
 }
@@ -120,22 +110,26 @@ __device__ __forceinline__ uint32_t pk(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
 }
-// AvgPool2d(2): [F,H,W,C] -> [F,H/2,W/2,C]
+// AvgPool2d(2) on zero-bordered images: [F,H+2,W+2,C] -> [F,H/2+2,W/2+2,C] (border of the output written as zeros)
 __global__ void avgpool2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int H, int W,
                                 int C, long long n_units) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_units) return;
-  const int c8 = C / 8, Ho = H / 2, Wo = W / 2;
+  const int c8 = C / 8, Ho = H / 2, Wo = W / 2, Wp = W + 2, Hp = H + 2;
   const int cu = (int)(i % c8);
   const long long orow = i / c8;
-  const int ox = (int)(orow % Wo), oy = (int)((orow / Wo) % Ho);
-  const long long f = orow / ((long long)Wo * Ho);
+  const int ox = (int)(orow % (Wo + 2)) - 1, oy = (int)((orow / (Wo + 2)) % (Ho + 2)) - 1;
+  const long long f = orow / ((long long)(Wo + 2) * (Ho + 2));
+  if (ox < 0 || oy < 0 || ox >= Wo || oy >= Ho) {
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(0, 0, 0, 0);
+    return;
+  }
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
     for (int dx = 0; dx < 2; ++dx) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((f * H + 2 * oy + dy) * W + 2 * ox + dx) * C) + cu);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((f * Hp + 2 * oy + dy + 1) * Wp + 2 * ox + dx + 1) * C) + cu);
       const float2 a = bf2(v.x), b = bf2(v.y), c = bf2(v.z), d = bf2(v.w);
       acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
     }
@@ -152,7 +146,7 @@ __global__ void attnpool_tokens_kernel(const __nv_bfloat16* __restrict__ x, cons
   for (int c = threadIdx.x; c < EMB; c += blockDim.x) {
     float mean = 0.f;
     for (int s = 0; s < 49; ++s) {
-      const float v = __bfloat162float(x[((long long)f * 49 + s) * EMB + c]);
+      const float v = __bfloat162float(x[((long long)f * 81 + (s / 7 + 1) * 9 + (s % 7 + 1)) * EMB + c]);
       mean += v;
       tok[((long long)f * NTOK + 1 + s) * EMB + c] = __float2bfloat16_rn(v + pos[(1 + s) * EMB + c]);
     }
@@ -202,6 +196,7 @@ struct Conv {
   __nv_bfloat16* w = nullptr;
   float* bias = nullptr;
   int cout = 0, cin = 0, ksz = 1, kpad = 0;
+  bool implicit3x3 = false;  // weights laid out [Cout, 9 * cpad] for the shifted-TMA implicit GEMM
 };
 struct Block {
   Conv c1, c2, c3, down;
@@ -236,20 +231,21 @@ int ralloc(Rn50* r, T** p, long long n) {
 }
 
 int load_conv(Rn50* r, cudaStream_t st, const WeightGetter& get, const std::string& wname, const std::string& bn,
-              int cout, int cin, int ksz, Conv* c) {
+              int cout, int cin, int ksz, Conv* c, bool implicit3x3 = false) {
   const float *w, *g, *b, *mean, *var;
   SPM_TRY(get(wname, (long long)cout * cin * ksz * ksz, &w));
   SPM_TRY(get(bn + "weight", cout, &g));
   SPM_TRY(get(bn + "bias", cout, &b));
   SPM_TRY(get(bn + "running_mean", cout, &mean));
   SPM_TRY(get(bn + "running_var", cout, &var));
-  c->cout = cout; c->cin = cin; c->ksz = ksz;
-  c->kpad = (cin * ksz * ksz + 31) / 32 * 32;
+  c->cout = cout; c->cin = cin; c->ksz = ksz; c->implicit3x3 = implicit3x3;
+  const int cpad = implicit3x3 ? (cin + 63) / 64 * 64 : cin;
+  c->kpad = implicit3x3 ? 9 * cpad : (cin * ksz * ksz + 31) / 32 * 32;
   SPM_TRY(ralloc(r, &c->w, (long long)cout * c->kpad));
   SPM_TRY(ralloc(r, &c->bias, cout));
   const long long n = (long long)cout * c->kpad;
-  fold_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, b, mean, var, cout, cin, ksz, ksz, c->kpad, c->w,
-                                                                 c->bias);
+  fold_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, b, mean, var, cout, cin, ksz, ksz, cpad, c->kpad,
+                                                                 c->w, c->bias);
   RN_LAUNCH_CHECK();
   return 0;
 }
@@ -265,10 +261,12 @@ int load_linear(Rn50* r, cudaStream_t st, const WeightGetter& get, const std::st
   return 0;
 }
 
-int plan_conv(Rn50* r, Plan* pl, const Conv& c, const __nv_bfloat16* A, long long rows, __nv_bfloat16* out, bool relu,
-              const __nv_bfloat16* residual) {
+// rows = F * H2 * H2 pixels of zero-bordered H2 x H2 images
+int plan_conv(Rn50* r, Plan* pl, const Conv& c, const __nv_bfloat16* A, long long rows, int H2, __nv_bfloat16* out,
+              bool relu, const __nv_bfloat16* residual) {
   GemmEpilogue ep;
   ep.bias = c.bias; ep.out = out; ep.ldo = c.cout; ep.out_bf16 = 1;
+  ep.border_w2 = H2; ep.border_h2w2 = H2 * H2;
   if (residual != nullptr) {
     ep.residual_bf16 = residual; ep.ldr = c.cout; ep.relu_after_residual = 1;
   } else if (relu) {
@@ -276,7 +274,9 @@ int plan_conv(Rn50* r, Plan* pl, const Conv& c, const __nv_bfloat16* A, long lon
   }
   GemmOp op;
   const char* err = "";
-  if (gemm_plan(&op, GEMM_BF16, A, c.kpad, c.w, c.kpad, (int)rows, c.cout, c.kpad, ep, r->sms, &err)) {
+  const int rc = c.implicit3x3 ? gemm_plan_conv3x3(&op, A, c.cin, (int)rows, H2, c.w, c.cout, ep, r->sms, &err)
+                               : gemm_plan(&op, GEMM_BF16, A, c.kpad, c.w, c.kpad, (int)rows, c.cout, c.kpad, ep, r->sms, &err);
+  if (rc) {
     set_error(std::string("rn50 gemm_plan: ") + err);
     return 1;
   }
@@ -286,25 +286,24 @@ int plan_conv(Rn50* r, Plan* pl, const Conv& c, const __nv_bfloat16* A, long lon
 
 // Builds the GEMM list in execution order for F frames.  The non-GEMM kernels are replayed in the same order by run().
 int build_plan(Rn50* r, int F, Plan* pl) {
-  const long long R112 = (long long)F * 112 * 112;
-  SPM_TRY(plan_conv(r, pl, r->stem[0], r->col, R112, r->t1, true, nullptr));
-  SPM_TRY(plan_conv(r, pl, r->stem[1], r->col, R112, r->t2, true, nullptr));
-  SPM_TRY(plan_conv(r, pl, r->stem[2], r->col, R112, r->t1, true, nullptr));
+  const long long R114 = (long long)F * 114 * 114;
+  SPM_TRY(plan_conv(r, pl, r->stem[0], r->col, R114, 114, r->t1, true, nullptr));   // explicit im2col (from the image)
+  SPM_TRY(plan_conv(r, pl, r->stem[1], r->t1, R114, 114, r->t2, true, nullptr));    // implicit 3x3
+  SPM_TRY(plan_conv(r, pl, r->stem[2], r->t2, R114, 114, r->t1, true, nullptr));    // implicit 3x3
   __nv_bfloat16 *x = r->xa, *y = r->xb;
   int H = 56;
   for (const Block& b : r->blocks) {
-    const long long rows_in = (long long)F * H * H;
     const int Ho = H / b.stride;
-    const long long rows_out = (long long)F * Ho * Ho;
-    SPM_TRY(plan_conv(r, pl, b.c1, x, rows_in, r->t1, true, nullptr));
-    SPM_TRY(plan_conv(r, pl, b.c2, r->col, rows_in, r->t2, true, nullptr));
+    const long long rows_in = (long long)F * (H + 2) * (H + 2), rows_out = (long long)F * (Ho + 2) * (Ho + 2);
+    SPM_TRY(plan_conv(r, pl, b.c1, x, rows_in, H + 2, r->t1, true, nullptr));
+    SPM_TRY(plan_conv(r, pl, b.c2, r->t1, rows_in, H + 2, r->t2, true, nullptr));   // implicit 3x3
     const __nv_bfloat16* c3_in = b.stride > 1 ? r->t2p : r->t2;
     const __nv_bfloat16* idn = x;
     if (b.has_down) {
-      SPM_TRY(plan_conv(r, pl, b.down, b.stride > 1 ? r->xd : x, rows_out, r->idn, false, nullptr));
+      SPM_TRY(plan_conv(r, pl, b.down, b.stride > 1 ? r->xd : x, rows_out, Ho + 2, r->idn, false, nullptr));
       idn = r->idn;
     }
-    SPM_TRY(plan_conv(r, pl, b.c3, c3_in, rows_out, y, false, idn));
+    SPM_TRY(plan_conv(r, pl, b.c3, c3_in, rows_out, Ho + 2, y, false, idn));
     std::swap(x, y);
     H = Ho;
   }
@@ -339,14 +338,8 @@ int run_gemm(const GemmOp& op, cudaStream_t st) {
   if (gemm_run(&op, st, &err)) { set_error(std::string("rn50 gemm_run: ") + err); return 1; }
   return 0;
 }
-int im2col(cudaStream_t st, const __nv_bfloat16* in, __nv_bfloat16* out, int F, int H, int C) {
-  const long long n = (long long)F * H * H * 9 * (C / 8);
-  im2col3x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, H, H, C, n);
-  RN_LAUNCH_CHECK();
-  return 0;
-}
 int avgpool(cudaStream_t st, const __nv_bfloat16* in, __nv_bfloat16* out, int F, int H, int C) {
-  const long long n = (long long)F * (H / 2) * (H / 2) * (C / 8);
+  const long long n = (long long)F * (H / 2 + 2) * (H / 2 + 2) * (C / 8);  // all pixels of the padded output
   avgpool2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, H, H, C, n);
   RN_LAUNCH_CHECK();
   return 0;
@@ -361,23 +354,20 @@ int run_chunk(Rn50* r, cudaStream_t st, const float* images, int F, float* feats
   }
   const std::vector<GemmOp>& ops = it->second->ops;
   size_t g = 0;
-  // ---- stem (clip_fsar.py:594-599)
-  const long long R112 = (long long)F * 112 * 112;
-  stem_im2col_kernel<<<(unsigned)((R112 + 127) / 128), 128, 0, st>>>(images, r->col, R112);
+  // ---- stem (clip_fsar.py:594-599); every tensor below is a zero-bordered image
+  const long long R114 = (long long)F * 114 * 114;
+  stem_im2col_kernel<<<(unsigned)((R114 + 127) / 128), 128, 0, st>>>(images, r->col, R114);
   RN_LAUNCH_CHECK();
   SPM_TRY(run_gemm(ops[g++], st));                         // conv1+bn1+relu -> t1 [.,32]
-  SPM_TRY(im2col(st, r->t1, r->col, F, 112, 32));
-  SPM_TRY(run_gemm(ops[g++], st));                         // conv2 -> t2 [.,32]
-  SPM_TRY(im2col(st, r->t2, r->col, F, 112, 32));
-  SPM_TRY(run_gemm(ops[g++], st));                         // conv3 -> t1 [.,64]
-  SPM_TRY(avgpool(st, r->t1, r->xa, F, 112, 64));          // -> x [F,56,56,64]
+  SPM_TRY(run_gemm(ops[g++], st));                         // conv2 (implicit 3x3) -> t2 [.,32]
+  SPM_TRY(run_gemm(ops[g++], st));                         // conv3 (implicit 3x3) -> t1 [.,64]
+  SPM_TRY(avgpool(st, r->t1, r->xa, F, 112, 64));          // -> x [F,58,58,64]
   // ---- residual layers (clip_fsar.py:534-547)
   __nv_bfloat16 *x = r->xa, *y = r->xb;
   int H = 56;
   for (const Block& b : r->blocks) {
     SPM_TRY(run_gemm(ops[g++], st));                                   // conv1 1x1 -> t1
-    SPM_TRY(im2col(st, r->t1, r->col, F, H, b.planes));
-    SPM_TRY(run_gemm(ops[g++], st));                                   // conv2 3x3 -> t2
+    SPM_TRY(run_gemm(ops[g++], st));                                   // conv2 3x3 (implicit) -> t2
     if (b.stride > 1) SPM_TRY(avgpool(st, r->t2, r->t2p, F, H, b.planes));
     if (b.has_down) {
       if (b.stride > 1) SPM_TRY(avgpool(st, x, r->xd, F, H, b.inpl));
@@ -413,8 +403,8 @@ int rn50_create(Rn50** out, cudaStream_t st, int sms, const WeightGetter& get) {
     return 0;
   }
   SPM_TRY(load_conv(r.get(), st, get, p + "conv1.weight", p + "bn1.", 32, 3, 3, &r->stem[0]));
-  SPM_TRY(load_conv(r.get(), st, get, p + "conv2.weight", p + "bn2.", 32, 32, 3, &r->stem[1]));
-  SPM_TRY(load_conv(r.get(), st, get, p + "conv3.weight", p + "bn3.", 64, 32, 3, &r->stem[2]));
+  SPM_TRY(load_conv(r.get(), st, get, p + "conv2.weight", p + "bn2.", 32, 32, 3, &r->stem[1], true));
+  SPM_TRY(load_conv(r.get(), st, get, p + "conv3.weight", p + "bn3.", 64, 32, 3, &r->stem[2], true));
   int inpl = 64;
   const int nblk[4] = {3, 4, 6, 3};
   for (int li = 0; li < 4; ++li) {
@@ -425,7 +415,7 @@ int rn50_create(Rn50** out, cudaStream_t st, int sms, const WeightGetter& get) {
       b.has_down = b.stride > 1 || inpl != planes * 4;
       const std::string bp = p + "layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".";
       SPM_TRY(load_conv(r.get(), st, get, bp + "conv1.weight", bp + "bn1.", planes, inpl, 1, &b.c1));
-      SPM_TRY(load_conv(r.get(), st, get, bp + "conv2.weight", bp + "bn2.", planes, planes, 3, &b.c2));
+      SPM_TRY(load_conv(r.get(), st, get, bp + "conv2.weight", bp + "bn2.", planes, planes, 3, &b.c2, true));
       SPM_TRY(load_conv(r.get(), st, get, bp + "conv3.weight", bp + "bn3.", planes * 4, planes, 1, &b.c3));
       if (b.has_down)
         SPM_TRY(load_conv(r.get(), st, get, bp + "downsample.0.weight", bp + "downsample.1.", planes * 4, inpl, 1, &b.down));
