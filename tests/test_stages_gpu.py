@@ -285,3 +285,36 @@ def test_head_ragged_episode_shapes():
             with torch.no_grad():
                 ref = O.head_forward(ci["weights"], ci["text"], su, qu, labels, rs, rt, O.DEFAULT_PARAMS)
             assert H.rel_err(out["logits"].cpu(), ref["logits"]) < TOL_HEAD
+
+
+def test_full_size_episodes_bf16_path_agrees_with_fp32_mode():
+    """BASELINE config 2 size (5-way 5-shot, 240 frames / episode), several episodes in one call: the bf16 tensor-core
+    path against the exact fp32 mode (which is itself pinned to the executed reference at the golden sizes)."""
+    E = 3
+    backbone, way, shot, qpc, T, ncls = "ViT-B/16", 5, 5, 1, 8, 24
+    w = O.make_weights(backbone, seed=0, protocol="P1")
+    text = O.make_text_features(ncls, 512, seed=0)
+    eps = [O.make_episode(4000 + e, way, shot, qpc, T, ncls, "P1") for e in range(E)]
+    cat = lambda k: torch.cat([e[k] for e in eps]).cuda()
+    stack = lambda k: torch.stack([e[k] for e in eps]).cuda()
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        from clip_spm_b200 import CNN
+        net = CNN(H.make_cfg(backbone, T, False, way), text_features_test=text, max_episodes=E, precision=prec)
+        net.load_state_dict(w, strict=True)
+        outs[prec] = net.forward_episodes(cat("context_images"), stack("context_labels"), cat("target_images"),
+                                          stack("real_support_labels"), stack("real_target_labels"), E,
+                                          stack("target_labels"))
+        torch.cuda.synchronize()
+        del net
+    ref, got = outs["fp32"], outs["bf16"]
+    err = H.rel_err(got["logits"], ref["logits"])
+    assert err < TOL_BF16, err
+    abs_err = float((got["logits"] - ref["logits"]).abs().max())
+    top2 = ref["logits"].topk(2, dim=-1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 4 * abs_err
+    agree = got["logits"].argmax(-1) == ref["logits"].argmax(-1)
+    assert bool(agree[safe].all())
+    assert H.rel_err(got["dists"], ref["dists"]) < 5e-2
+    print("\nfull-size: logits rel err %.2e (abs %.4f); %d/%d queries pass the margin filter, all agree; raw agreement %d/%d"
+          % (err, abs_err, int(safe.sum()), safe.numel(), int(agree.sum()), agree.numel()))
