@@ -187,7 +187,7 @@ def main():
     import __graft_entry__
     __graft_entry__.build()
     from clip_spm_b200 import CNN, _lib, sweep
-    from tests.helpers import make_cfg  # plain namespace builder (no oracle use)
+    from clip_spm_b200.config import make_cfg
     lib = _lib.load()
     EPS, EPC = args.episodes_per_step, args.episodes_per_call
     net = CNN(make_cfg("ViT-B/16", T, False, WAY), max_episodes=EPC, device=dev)
@@ -216,7 +216,9 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.spm_launch_count()
-    _lib.check(lib.spm_profile_begin(args.steps * EPS * 120 + 64))
+    # per-GEMM CUDA events (roofline): armed for the first two timed steps only -- tens of thousands of timed events
+    # per run were seen to coincide with sporadic host-side submission stalls; afterwards the hook is a no-op
+    _lib.check(lib.spm_profile_begin(min(args.steps, 2) * EPS * 70 + 16))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()

@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libclipspm_b200.so")
+# SPM_LIB overrides the library file (A/B comparisons of two builds on the same GPU box)
+LIB_PATH = os.environ.get("SPM_LIB") or os.path.join(_HERE, "lib", "libclipspm_b200.so")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int

@@ -59,7 +59,8 @@ __device__ __forceinline__ long long res_row(const GemmEpilogue& ep, int m) {
 
 // taddr: TMEM address of (lane quarter base, first accumulator column of the tile); stg_u: this warp's 4 KB staging
 // tile (32 rows x 128 B, 16-byte units XOR-swizzled by row & 7); half: which of the two warps of the lane quarter.
-template <int BN>
+// BORDER: compile the zero-border handling of the convolution path in (the plain-GEMM instantiations stay free of it)
+template <int BN, bool BORDER = false>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint32_t stg_u, uint32_t taddr, int m_base,
                                                    int n0, int M, int N, int lane, int half) {
   const int rr = lane >> 3, uu = lane & 7;  // read-back mapping: row i*4 + rr, 16-byte unit uu
@@ -113,7 +114,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint3
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act, ep.slope);
       }
-      if (ep.border_w2 > 0) {  // zero-bordered image rows stay zero (thread == pixel row)
+      if (BORDER && ep.border_w2 > 0) {  // zero-bordered image rows stay zero (thread == pixel row)
         const int pr = (m_base + lane) % ep.border_h2w2, py = pr / ep.border_w2, px = pr - py * ep.border_w2;
         if (py == 0 || px == 0 || px == ep.border_w2 - 1 || py == ep.border_h2w2 / ep.border_w2 - 1) {
 #pragma unroll

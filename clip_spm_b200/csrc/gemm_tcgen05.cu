@@ -45,7 +45,9 @@ struct GemmTile {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024;  // +1024: alignment slack
 };
 
-template <int BN, int KIND>
+// CONV: implicit-3x3-convolution addressing in the producer + zero-border epilogue (rn50.cu); the plain GEMM
+// instantiations (CONV = false) contain none of that code
+template <int BN, int KIND, bool CONV = false>
 __global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmArgs args) {
@@ -103,7 +105,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += gridDim.x; }
         }
       };
-      const bool conv = args.conv_cblocks > 0;  // taps re-read an L2-resident activation: no prefetch needed
+      constexpr bool conv = CONV;  // taps re-read an L2-resident activation: no prefetch needed
       if (!conv)
         for (int i = 0; i < GEMM_L2_PREFETCH_KB; ++i) prefetch_next();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -115,7 +117,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint8_t* sa = smem + stage * T::STAGE_BYTES;
           uint8_t* sb = sa + T::A_BYTES;
           mbar_expect_tx(&full_bar[stage], T::STAGE_BYTES);
-          if (conv) {
+          if (conv && args.conv_cblocks > 0) {
             const int tap = kb / args.conv_cblocks, cb = kb - tap * args.conv_cblocks;
             const int roff = (tap / 3 - 1) * args.conv_w2 + (tap % 3 - 1);  // rows outside the matrix read as zeros
             tma_load_2d(sa, &tmA, &full_bar[stage], cb * T::BK, m0 + roff);
@@ -178,7 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      gemm_epilogue_tile<BN>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+      gemm_epilogue_tile<BN, CONV>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
       // accumulator buffer drained -> hand it back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
@@ -248,6 +250,13 @@ int gemm_init(const char** err) {
   SPM_SET_SMEM(256, GEMM_TF32)
   SPM_SET_SMEM(128, GEMM_TF32)
 #undef SPM_SET_SMEM
+  if (cudaFuncSetAttribute(gemm_tcgen05_kernel<256, GEMM_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           GemmTile<256, GEMM_BF16>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tcgen05_kernel<128, GEMM_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           GemmTile<128, GEMM_BF16>::SMEM_BYTES) != cudaSuccess) {
+    *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the conv GEMM kernel";
+    return 1;
+  }
   return gemm2_init(err);
 }
 
@@ -282,7 +291,8 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   // 188 us, 75.6 % vs 70.3 % tensor-active) and loses on K = 768 (its cluster-wide barriers cost more per tile than
   // the deeper pipeline gains), so it is selected by K.  SPM_GEMM_2CTA=2 forces it everywhere, 0 disables it.
   static const int mode_2cta = [] { const char* e = getenv("SPM_GEMM_2CTA"); return e == nullptr ? 1 : atoi(e); }();
-  op->two_cta = (allow_2cta && kind == GEMM_BF16 && N % 256 == 0 && pair_tiles >= num_sms / 2 &&
+  // (zero-bordered convolution outputs are handled by the 1-CTA CONV instantiation only)
+  op->two_cta = (allow_2cta && kind == GEMM_BF16 && ep.border_w2 == 0 && N % 256 == 0 && pair_tiles >= num_sms / 2 &&
                  (K >= 2048 || mode_2cta == 2)) ? 1 : 0;
   if (op->two_cta) {
     op->bn = 256;
@@ -327,6 +337,11 @@ int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
     sgemm_f32_run(op, stream);
   } else if (op->two_cta) {
     gemm2_launch(op, stream);
+  } else if (op->conv_cblocks > 0 || op->ep.border_w2 > 0) {  // convolution path (bf16): taps / zero borders
+    if (op->bn == 256)
+      gemm_tcgen05_kernel<256, GEMM_BF16, true><<<op->grid, 384, GemmTile<256, GEMM_BF16>::SMEM_BYTES, stream>>>(op->ta, op->tb, a);
+    else
+      gemm_tcgen05_kernel<128, GEMM_BF16, true><<<op->grid, 384, GemmTile<128, GEMM_BF16>::SMEM_BYTES, stream>>>(op->ta, op->tb, a);
   } else if (op->kind == GEMM_BF16) {
     if (op->bn == 256) SPM_LAUNCH(256, GEMM_BF16); else SPM_LAUNCH(128, GEMM_BF16);
   } else {

@@ -686,6 +686,12 @@ int head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const f
   return 0;
 }
 
+// the label/W mismatch flag is per call: cleared (stream-ordered) when a public entry point starts
+int reset_err_flag(spm_handle* h, cudaStream_t st) {
+  if (h->err_flag != nullptr) SPM_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), st));
+  return 0;
+}
+
 int check_shapes(spm_handle* h, int E, int S, int Q, int W) {
   SPM_CHECK(h != nullptr, "null handle");
   SPM_CHECK(E >= 1 && S >= 1 && Q >= 1 && W >= 1, "episode shape must be positive");
@@ -831,6 +837,7 @@ int spm_head(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, c
   SPM_CHECK(h->weights_loaded, "spm_head: weights not loaded");
   cudaStream_t st = (cudaStream_t)stream;
   SPM_TRY(ensure_head_workspace(h, n_episodes, S, Q, W));
+  SPM_TRY(reset_err_flag(h, st));
   const int T = h->cfg.seq_len, D = h->D, N = S + Q;
   const size_t row = (size_t)T * D * 4;
   SPM_CUDA(cudaMemcpy2DAsync(h->X, (size_t)N * row, su, (size_t)S * row, (size_t)S * row, n_episodes,
@@ -846,6 +853,8 @@ int spm_forward(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W
                 const float* real_target, float* logits_out, float* dists_out) {
   SPM_CHECK(support_images && target_images && support_labels && real_support && real_target && logits_out && dists_out,
             "spm_forward: null argument");
+  SPM_CHECK(h != nullptr, "spm_forward: null handle");
+  SPM_TRY(reset_err_flag(h, (cudaStream_t)stream));
   return forward_impl(h, (cudaStream_t)stream, n_episodes, S, Q, W, support_images, target_images, support_labels,
                       real_support, real_target, nullptr, 1.f, logits_out, dists_out, nullptr, nullptr, nullptr);
 }
@@ -856,6 +865,8 @@ int spm_eval(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, c
              float* dists_out, float* loss_out, float* acc_out, int32_t* pred_out) {
   SPM_CHECK(support_images && target_images && support_labels && real_support && real_target && target_labels,
             "spm_eval: null argument");
+  SPM_CHECK(h != nullptr, "spm_eval: null handle");
+  SPM_TRY(reset_err_flag(h, (cudaStream_t)stream));
   return forward_impl(h, (cudaStream_t)stream, n_episodes, S, Q, W, support_images, target_images, support_labels,
                       real_support, real_target, reinterpret_cast<const long long*>(target_labels), tasks_per_batch,
                       logits_out, dists_out, loss_out, acc_out, pred_out);
@@ -923,6 +934,7 @@ int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const floa
   float* p_acc = p_loss + n_episodes;
   int32_t* p_pred = reinterpret_cast<int32_t*>(p_acc + n_episodes);
   cudaStream_t cs = h->copy_stream, ks = h->compute_stream;
+  SPM_TRY(reset_err_flag(h, ks));
   std::vector<int> chunk_of(n_episodes);
   for (int c = 0; c < n_chunks; ++c)
     for (int e = starts[c]; e < starts[c + 1]; ++e) chunk_of[e] = c;

@@ -319,6 +319,7 @@ int k_vit_attention_tc(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16*
   auto key = std::make_tuple((const void*)qkv, n_frames);
   auto it = cache.find(key);
   if (it == cache.end()) {
+    if (cache.size() >= 64) cache.clear();  // bounded: callers with ever-changing buffers only pay re-encoding
     AttnMaps m;
     const int r = make_maps(qkv, n_frames, &m);
     if (r != 0) return r;

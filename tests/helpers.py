@@ -27,14 +27,8 @@ def golden(name):
 
 
 def make_cfg(backbone, T, single_direct=False, way=None):
-    cfg = types.SimpleNamespace(
-        MODEL=types.SimpleNamespace(BACKBONE=backbone), DATA=types.SimpleNamespace(SEQ_LEN=T),
-        TRAIN=types.SimpleNamespace(TASKS_PER_BATCH=16), params=dict(O.DEFAULT_PARAMS))
-    if single_direct:
-        cfg.MODEL.SINGLE_DIRECT = True
-    if way is not None:
-        cfg.TRAIN.WAY = way
-    return cfg
+    from clip_spm_b200.config import make_cfg as _mk
+    return _mk(backbone, T, single_direct, way, params=O.DEFAULT_PARAMS)
 
 
 def case_inputs(name):

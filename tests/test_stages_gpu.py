@@ -103,6 +103,10 @@ def test_head_wrong_way_fails_loudly():
     su, qu = ci["feats"]
     out = net.head(su.cuda(), qu.cuda(), ep["context_labels"], ep["real_support_labels"], ep["real_target_labels"])
     assert bool(torch.isnan(out["logits"]).all())
+    # the failure is per call, not sticky: the same handle with the right W works again
+    net.way = 5
+    out = net.head(su.cuda(), qu.cuda(), ep["context_labels"], ep["real_support_labels"], ep["real_target_labels"])
+    assert bool(torch.isfinite(out["logits"]).all())
 
 
 @pytest.mark.parametrize("name", ["vit_2w1s_t2_p0", "vit_5w1s_t8_p1"])

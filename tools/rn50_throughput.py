@@ -2,7 +2,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from clip_spm_b200 import CNN, sweep
-from tests.helpers import make_cfg
+from clip_spm_b200.config import make_cfg
 net = CNN(make_cfg("RN50", 8, False, 5), max_episodes=2)
 net.init_random_(0); net.text_features_test = torch.randn(10, 1024)
 b = sweep.synthetic_episode_batch([0, 1], 5, 3, 1, 8, 10, "cuda")   # BASELINE config 4 shape: 5-way 3-shot, 160 frames

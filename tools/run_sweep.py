@@ -32,7 +32,7 @@ def main():
     import __graft_entry__
     __graft_entry__.build()
     from clip_spm_b200 import CNN, sweep
-    from tests.helpers import make_cfg
+    from clip_spm_b200.config import make_cfg
     D = 512 if args.backbone == "ViT-B/16" else 1024
     net = CNN(make_cfg(args.backbone, args.seq_len, False, args.way), max_episodes=args.episodes_per_call, device=dev)
     net.init_random_(seed=0)
