@@ -51,7 +51,11 @@ class ClockSampler:
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, index):
-        self.index, self.thread, self.stop_flag = index, None, False
+        import threading
+        self.index, self.thread, self.stop_evt = index, None, threading.Event()
+        # NVML queries were measured to perturb kernel submission when issued every 50 ms (episodes/s dips of 10-30 %
+        # in some runs); a few samples per second are enough for a median clock and the throttle-reason set
+        self.interval = min(5.0, float(os.environ.get("SPM_BENCH_CLOCK_INTERVAL", "0.4")))
         self.sm, self.mx, self.reasons = [], 0.0, set()
         try:
             import pynvml
@@ -64,7 +68,7 @@ class ClockSampler:
 
     def _loop(self):
         nv = self.nv
-        while not self.stop_flag:
+        while not self.stop_evt.is_set():
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 try:
@@ -76,7 +80,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            self.stop_evt.wait(self.interval)  # interruptible: stop() never waits for a full interval
 
     def start(self):
         if self.nv is None:
@@ -88,8 +92,8 @@ class ClockSampler:
     def stop(self):
         if self.thread is None:
             return None
-        self.stop_flag = True
-        self.thread.join()
+        self.stop_evt.set()
+        self.thread.join(timeout=10.0)
         if not self.sm:
             return None
         return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
@@ -210,28 +214,49 @@ def main():
             accs.append(o["acc"]); losses.append(o["loss"])
         return torch.cat(accs), torch.cat(losses)
 
+    # run on a dedicated non-default stream: kernel submission to the legacy NULL stream was seen to stall
+    # sporadically (the library takes whatever stream is current: CNN passes torch.cuda.current_stream())
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
     for _ in range(args.warmup):
-        device_step()
+        a, l = device_step()
+        # the sweep's final reduce (torch ops + one all-reduce) is part of the timed region: run it in the warm-up
+        # too, so that its first-use lazy kernel loading is not billed to the timed steps
+        sweep.summarize(sweep.reduce_stats(sweep.make_stats(a, l)))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.spm_launch_count()
-    # per-GEMM CUDA events (roofline): armed for the first two timed steps only -- tens of thousands of timed events
-    # per run were seen to coincide with sporadic host-side submission stalls; afterwards the hook is a no-op
-    _lib.check(lib.spm_profile_begin(min(args.steps, 2) * EPS * 70 + 16))
+    # per-GEMM CUDA events (roofline.achieved): armed for a window of timed steps in the middle of the region (not
+    # the first steps, where the launch queue is still shallow and event intervals include submission latency).
+    # The event pool is created here, outside the timed region; arming it later only resets two counters.
+    prof_first = min(2, args.steps - 1)
+    prof_steps = max(1, min(4, args.steps - prof_first))
+    prof_records = prof_steps * EPS * 140 + 64  # upper bound on GEMM launches of the window
+    flops4 = (ctypes.c_double * 4)(); ms4 = (ctypes.c_double * 4)(); cnt4 = (ctypes.c_int * 4)()
+    _lib.check(lib.spm_profile_begin(prof_records))
+    _lib.check(lib.spm_profile_end(flops4, ms4, cnt4))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     acc_all, loss_all = [], []
-    for _ in range(args.steps):
+    step_ev = [ev0]
+    for k in range(args.steps):
+        if k == prof_first:
+            _lib.check(lib.spm_profile_begin(prof_records))
         a, l = device_step()
+        if k == prof_first + prof_steps - 1:
+            lib.spm_profile_disarm()  # exactly steps [prof_first, prof_first + prof_steps) carry GEMM events
         acc_all.append(a); loss_all.append(l)
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        step_ev.append(e)
     stats = sweep.reduce_stats(sweep.make_stats(torch.cat(acc_all), torch.cat(loss_all)))  # the path's one collective
     ev1.record()
     barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
     launches = lib.spm_launch_count() - launches0
-    flops4 = (ctypes.c_double * 4)(); ms4 = (ctypes.c_double * 4)(); cnt4 = (ctypes.c_int * 4)()
     _lib.check(lib.spm_profile_end(flops4, ms4, cnt4))
     clocks = sampler.stop()
     if world > 1:
@@ -277,7 +302,8 @@ def main():
                 " bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks["which"] == "measured" else "fallback 1590",
                 "traffic": GEMM_DRAM_BYTES_PER_LAUNCH_NCU, "traffic_unit": "bytes/launch (ncu, mean of the 4 encoder GEMMs)",
                 "launches_timed": int(cnt4[dom]),
-                "gemm_share_of_step": gemm_ms_all / (ms if ms > 0 else 1.0),
+                "gemm_share_of_step": gemm_ms_all / max(sum(step_ms[prof_first:prof_first + prof_steps]), 1e-9),
+                "profiled_steps": [prof_first, prof_first + prof_steps],
                 "whole_step_tflops_executed": value / world * FRAMES * VIT_GFLOP_PER_FRAME_EXECUTED / 1e3,
                 "whole_step_tflops_nominal": value / world * FRAMES * VIT_GFLOP_PER_FRAME / 1e3}
     line = {"metric": "episodes_per_sec", "value": value, "unit": "episodes/s", "frames_per_s": value * FRAMES,
@@ -287,6 +313,7 @@ def main():
                        "episodes_per_step_per_gpu": EPS, "episodes_per_call": EPC,
                        "l2": "step inputs (%.0f MB) exceed the 126 MB L2; no explicit flush" % (EPS * FRAMES * 0.602112),
                        "weights": "random-init (no checkpoints offline)"},
+            "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
             "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "clocks": clocks,
             "sweep_stats": summary}
     if world == 1 and not args.no_cpu_baseline:

@@ -38,6 +38,7 @@ SIGNATURES = {
     "spm_abi_version": (c_int, []),
     "spm_launch_count": (c_ll, []),
     "spm_profile_begin": (c_int, [c_int]),
+    "spm_profile_disarm": (c_int, []),
     "spm_profile_end": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                 ctypes.POINTER(c_int)]),
     "spm_create": (c_int, [ctypes.POINTER(SpmConfig), ctypes.POINTER(c_void_p)]),

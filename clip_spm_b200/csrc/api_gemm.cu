@@ -62,6 +62,11 @@ int spm_profile_begin(int max_records) {
   return 0;
 }
 
+int spm_profile_disarm(void) {
+  spm::g_profiling = false;  // launches submitted from now on are not timed; recorded events stay readable
+  return 0;
+}
+
 int spm_profile_end(double* flops4, double* ms4, int* count4) {
   using namespace spm;
   g_profiling = false;

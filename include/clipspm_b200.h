@@ -62,6 +62,7 @@ int spm_abi_version(void);
  * launch durations in ms and the launch count. */
 long long spm_launch_count(void);
 int spm_profile_begin(int max_records);
+int spm_profile_disarm(void); /* stop timing further launches (no sync); spm_profile_end still reads what was recorded */
 int spm_profile_end(double* flops4, double* ms4, int* count4);
 
 int spm_create(const spm_config* cfg, spm_handle** out);
