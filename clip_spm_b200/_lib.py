@@ -56,6 +56,12 @@ SIGNATURES = {
     "spm_vit_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "spm_gemm": (c_int, [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_int,
                          c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int]),
+    "spm_text_create": (c_int, [c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "spm_text_destroy": (c_int, [c_void_p]),
+    "spm_text_load_weights": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_void_p),
+                                      ctypes.POINTER(ctypes.c_int64)]),
+    "spm_text_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "spm_text_class_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -166,6 +166,26 @@ class CNN(nn.Module):
         sharded across ranks instead (clip_spm_b200.sweep)."""
         return None
 
+    def build_text_features(self, clip_state_dict, test_class_names=None, train_class_names=None, vocab_path=None):
+        """What the reference constructor does with the CLIP text tower (models/model_clipspm.py:45-70): sets
+        `text_features_test` / `text_features_train` from class names (default: cfg.TEST.CLASS_NAME /
+        cfg.TRAIN.CLASS_NAME).  clip_state_dict: the CLIP checkpoint's state_dict (text-tower keys)."""
+        from .text import TextTower
+        test_class_names = test_class_names or _cfg_get(self.args, "TEST.CLASS_NAME")
+        train_class_names = train_class_names or _cfg_get(self.args, "TRAIN.CLASS_NAME")
+        tower = TextTower(clip_state_dict, precision=self.precision, device=self._dev, vocab_path=vocab_path)
+        if tower.embed_dim != self.mid_dim:
+            raise RuntimeError("text tower embed_dim %d does not match backbone %s" % (tower.embed_dim, self.backbone_name))
+        try:
+            if test_class_names:
+                self.text_features_test = tower.class_features(list(test_class_names))
+            if train_class_names:
+                self.text_features_train = tower.class_features(list(train_class_names))
+            torch.cuda.synchronize(self._dev)
+        finally:
+            tower.close()
+        return self
+
     def init_random_(self, seed=0):
         """Random-init weights of the architecture for benchmarking (checkpoints are unavailable offline): fan-in
         scaled normals for matrices / conv kernels, LayerNorm-BatchNorm scales near 1, small biases."""

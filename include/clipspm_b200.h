@@ -128,6 +128,25 @@ int spm_gemm(void* stream, int kind, const void* A, long long lda, const void* B
              int res_row_off, int out_row_group, int out_group_stride, int out_row_off, void* out, int ldo,
              int out_bf16);
 
+/* ---- text-prompt tower (class names -> text_features): models/model_clipspm.py:45-70, clip_fsar.py:793-805 ----
+ * What the reference's CNN.__init__ computes once per class list.  Tokenisation (byte-level BPE) stays on the host
+ * (clip_spm_b200/tokenizer.py mirrors clip_fsar.py:144-180,322-392); the device side starts from token ids. */
+typedef struct spm_text spm_text;
+
+/* embed_dim: 512 (ViT-B/16 checkpoint) or 1024 (RN50); precision as in spm_config */
+int spm_text_create(int embed_dim, int precision, spm_text** out);
+int spm_text_destroy(spm_text* h);
+/* fp32 device tensors named by the reference's CLIP state_dict keys: token_embedding.weight, positional_embedding,
+ * transformer.resblocks.{i}.{attn.in_proj_weight, attn.in_proj_bias, attn.out_proj.*, ln_1.*, ln_2.*, mlp.c_fc.*,
+ * mlp.c_proj.*}, ln_final.*, text_projection; other names are ignored, a missing or mis-sized one is an error */
+int spm_text_load_weights(spm_text* h, void* stream, int n, const char* const* names, const void* const* dev_ptrs,
+                          const int64_t* numel);
+/* CLIP.encode_text: tokens [n_texts, 77] int32 (device; <sot> ids <eot> 0...) -> out [n_texts, embed_dim] fp32 */
+int spm_text_encode(spm_text* h, void* stream, const int32_t* tokens, int n_texts, float* out);
+/* the constructor's loop: tokens [n_templates, n_classes, 77] -> out[c] = mean_t encode_text(tokens[t, c]) */
+int spm_text_class_features(spm_text* h, void* stream, const int32_t* tokens, int n_templates, int n_classes,
+                            float* out);
+
 #ifdef __cplusplus
 }
 #endif

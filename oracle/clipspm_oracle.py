@@ -501,3 +501,82 @@ def make_features(seed, n_support, n_query, T, D, labels_support=None, labels_ta
         return x
 
     return build(n_support, labels_support), build(n_query, labels_target)
+
+
+# =====================================================================================================
+# text-prompt tower: produces the text_features table the hot path consumes
+# =====================================================================================================
+TEXT = dict(width=512, layers=12, heads=8, ctx=77, vocab=49408)
+
+
+def text_weight_shapes(embed_dim):
+    C = TEXT["width"]
+    s = {"token_embedding.weight": (TEXT["vocab"], C), "positional_embedding": (TEXT["ctx"], C),
+         "ln_final.weight": (C,), "ln_final.bias": (C,), "text_projection": (C, embed_dim)}
+    for i in range(TEXT["layers"]):
+        p = "transformer.resblocks.%d." % i
+        s.update({p + "attn.in_proj_weight": (3 * C, C), p + "attn.in_proj_bias": (3 * C,),
+                  p + "attn.out_proj.weight": (C, C), p + "attn.out_proj.bias": (C,),
+                  p + "ln_1.weight": (C,), p + "ln_1.bias": (C,), p + "ln_2.weight": (C,), p + "ln_2.bias": (C,),
+                  p + "mlp.c_fc.weight": (4 * C, C), p + "mlp.c_fc.bias": (4 * C,),
+                  p + "mlp.c_proj.weight": (C, 4 * C), p + "mlp.c_proj.bias": (C,)})
+    return s
+
+
+def make_text_weights(embed_dim=512, seed=0):
+    """Seeded synthetic weights of CLIP's text tower, keyed by the names of the reference's `CLIP` module
+    (models/clip_fsar.py:737-746); scales follow CLIP.initialize_parameters (:749-776) with non-trivial LN/biases."""
+    C, L = TEXT["width"], TEXT["layers"]
+    w = {}
+    for name, shp in text_weight_shapes(embed_dim).items():
+        leaf = name.split(".")[-1]
+        nm = "text." + name
+        if name == "token_embedding.weight":
+            w[name] = _normal(seed, nm, shp, 0.02)
+        elif name == "positional_embedding":
+            w[name] = _normal(seed, nm, shp, 0.01)
+        elif name == "text_projection":
+            w[name] = _normal(seed, nm, shp, C ** -0.5)
+        elif len(shp) == 1 and leaf == "weight":
+            w[name] = 1.0 + _normal(seed, nm, shp, 0.1)
+        elif leaf in ("bias", "in_proj_bias"):
+            w[name] = _normal(seed, nm, shp, 0.02)
+        elif leaf == "in_proj_weight":
+            w[name] = _normal(seed, nm, shp, 2.0 * C ** -0.5)
+        elif name.endswith("c_fc.weight"):
+            w[name] = _normal(seed, nm, shp, (2 * C) ** -0.5)
+        else:  # out_proj / c_proj
+            w[name] = _normal(seed, nm, shp, C ** -0.5 * (2 * L) ** -0.5 * 4.0)
+    return w
+
+
+def encode_text(w, tokens):
+    """models/clip_fsar.py:793-805 CLIP.encode_text: tokens [B,77] int -> [B, embed_dim]; causal mask of :778-784."""
+    C, H = TEXT["width"], TEXT["heads"]
+    B, L = tokens.shape
+    x = w["token_embedding.weight"][tokens.long()] + w["positional_embedding"]
+    mask = torch.full((L, L), float("-inf")).triu_(1)
+    hd = C // H
+    for i in range(TEXT["layers"]):
+        p = "transformer.resblocks.%d." % i
+        h = layer_norm(x, w[p + "ln_1.weight"], w[p + "ln_1.bias"])
+        qkv = h @ w[p + "attn.in_proj_weight"].t() + w[p + "attn.in_proj_bias"]
+        q, k, v = qkv.split(C, dim=-1)
+        q = q.view(B, L, H, hd).transpose(1, 2)
+        k = k.view(B, L, H, hd).transpose(1, 2)
+        v = v.view(B, L, H, hd).transpose(1, 2)
+        att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd) + mask, dim=-1)
+        o = (att @ v).transpose(1, 2).reshape(B, L, C)
+        x = x + o @ w[p + "attn.out_proj.weight"].t() + w[p + "attn.out_proj.bias"]
+        h = layer_norm(x, w[p + "ln_2.weight"], w[p + "ln_2.bias"])
+        h = quick_gelu(h @ w[p + "mlp.c_fc.weight"].t() + w[p + "mlp.c_fc.bias"])
+        x = x + h @ w[p + "mlp.c_proj.weight"].t() + w[p + "mlp.c_proj.bias"]
+    x = layer_norm(x, w["ln_final.weight"], w["ln_final.bias"])
+    eot = tokens.argmax(dim=-1)                                   # <|endoftext|> has the highest id
+    return x[torch.arange(B), eot] @ w["text_projection"]
+
+
+def class_text_features(w, tokens_by_template):
+    """models/model_clipspm.py:52-70: tokens_by_template [n_templates, n_classes, 77] -> mean over templates of
+    encode_text -> [n_classes, embed_dim] (no normalisation)."""
+    return torch.stack([encode_text(w, t) for t in tokens_by_template]).mean(dim=0)

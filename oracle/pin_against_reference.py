@@ -165,8 +165,49 @@ def run_case(m, name):
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
 
 
+TEXT_CLASSES = ["run", "jumping jacks", "pour water into a glass", "riding a bike"]
+
+
+def run_text_case(m):
+    """Text-prompt tower: the reference's own constructor (model_clipspm.py:45-70: 16 templates x class names ->
+    tokenize -> CLIP.encode_text -> mean) with seeded text-tower weights, against the oracle + this repo's tokenizer."""
+    import models.clip_fsar as clip_fsar
+    from clip_spm_b200.tokenizer import ClipTokenizer, PROMPT_TEMPLATES
+    wt = O.make_text_weights(512, seed=0)
+
+    def fake_load(name, device="cpu", cfg=None, jit=False):
+        net = clip_fsar.CLIP(512, 224, 12, 768, 16, 77, 49408, 512, 8, 12).float().eval()
+        missing, unexpected = net.load_state_dict(wt, strict=False)
+        assert not unexpected and all(k.startswith("visual.") or k == "logit_scale" for k in missing), (missing, unexpected)
+        return net, None
+
+    old = m.load
+    m.load = fake_load
+    cfg = NS(MODEL=NS(BACKBONE="ViT-B/16"), TRAIN=NS(CLASS_NAME=["run"]), TEST=NS(CLASS_NAME=TEXT_CLASSES),
+             DATA=NS(SEQ_LEN=8), DEVICE=NS(NUM_GPUS=1), params=dict(O.DEFAULT_PARAMS))
+    with torch.no_grad():
+        net = m.CNN(cfg)
+    m.load = old
+    ref = net.text_features_test
+    tk = ClipTokenizer()
+    tokens = torch.stack([tk.tokenize([t.format(c) for c in TEXT_CLASSES]) for t in PROMPT_TEMPLATES])   # [16, n_cls, 77]
+    for ti, t in enumerate(PROMPT_TEMPLATES):
+        assert torch.equal(tokens[ti], clip_fsar.tokenize([t.format(c) for c in TEXT_CLASSES]).int())
+    with torch.no_grad():
+        mine = O.class_text_features(wt, tokens)
+    r = rel(mine, ref)
+    assert r < 2e-4, r
+    print("%-24s oracle==reference (text_features_test of CNN.__init__), rel err %.2e, |feat| max %.3f" %
+          ("text_tower_4cls", r, float(ref.abs().max())))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "text_tower_4cls.npz"), tokens=tokens.numpy(),
+                        text_features=ref.float().numpy())
+
+
 if __name__ == "__main__":
     m = import_reference()
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + ["text"])
     for n in names:
-        run_case(m, n)
+        if n == "text":
+            run_text_case(m)
+        else:
+            run_case(m, n)
