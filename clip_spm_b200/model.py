@@ -122,8 +122,9 @@ class CNN(nn.Module):
     cfg: the reference's config object (attribute tree or nested dict) -- reads MODEL.BACKBONE, DATA.SEQ_LEN,
     params{mid_dim_text, mid_dim_vision, negative_slope, alpha, motion_alpha}, optional MODEL.SINGLE_DIRECT,
     optional TRAIN.WAY (number of classes per episode; derived with torch.unique, a host sync, when absent).
-    The text tower is not run here: pass the [n_cls, D] prompt features the reference keeps
-    in `text_features_test` / `text_features_train`.
+    Prompt features: pass the [n_cls, D] tables the reference keeps in `text_features_test` /
+    `text_features_train`, or call `build_text_features(clip_state_dict)` to compute them from the class names with
+    the library's own text tower (the constructor work of model_clipspm.py:45-70).
     precision="bf16": bf16 tcgen05 encoder + tf32 head (what autocast(bfloat16) is to the reference);
     precision="fp32": every product in fp32 FFMA (the reference's default fp32 arithmetic; slow, for parity)."""
 
@@ -166,14 +167,16 @@ class CNN(nn.Module):
         sharded across ranks instead (clip_spm_b200.sweep)."""
         return None
 
-    def build_text_features(self, clip_state_dict, test_class_names=None, train_class_names=None, vocab_path=None):
+    def build_text_features(self, clip_state_dict, test_class_names=None, train_class_names=None, vocab_path=None,
+                            tokenizer=None):
         """What the reference constructor does with the CLIP text tower (models/model_clipspm.py:45-70): sets
         `text_features_test` / `text_features_train` from class names (default: cfg.TEST.CLASS_NAME /
         cfg.TRAIN.CLASS_NAME).  clip_state_dict: the CLIP checkpoint's state_dict (text-tower keys)."""
         from .text import TextTower
         test_class_names = test_class_names or _cfg_get(self.args, "TEST.CLASS_NAME")
         train_class_names = train_class_names or _cfg_get(self.args, "TRAIN.CLASS_NAME")
-        tower = TextTower(clip_state_dict, precision=self.precision, device=self._dev, vocab_path=vocab_path)
+        tower = TextTower(clip_state_dict, precision=self.precision, device=self._dev, vocab_path=vocab_path,
+                          tokenizer=tokenizer)
         if tower.embed_dim != self.mid_dim:
             raise RuntimeError("text tower embed_dim %d does not match backbone %s" % (tower.embed_dim, self.backbone_name))
         try:

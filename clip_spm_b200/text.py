@@ -22,7 +22,7 @@ class TextTower:
     """clip_state_dict: the CLIP checkpoint's state_dict (the keys of clip_fsar.CLIP; the `visual.*` entries are
     ignored).  embed_dim is read from text_projection (512 for ViT-B/16, 1024 for RN50)."""
 
-    def __init__(self, clip_state_dict, precision="bf16", device="cuda", vocab_path=None):
+    def __init__(self, clip_state_dict, precision="bf16", device="cuda", vocab_path=None, tokenizer=None):
         if not torch.cuda.is_available():
             raise RuntimeError("clip_spm_b200.TextTower needs a CUDA device (sm_100a); there is no CPU fallback")
         if precision not in ("bf16", "fp32"):
@@ -30,7 +30,7 @@ class TextTower:
         lib = _lib.load()
         self._dev = torch.device(device)
         self._h = None
-        self._tok = None
+        self._tok = tokenizer            # anything with .tokenize(list of str) -> [n, 77] ids; default: ClipTokenizer
         self._vocab_path = vocab_path
         if "text_projection" not in clip_state_dict:
             raise RuntimeError("clip_state_dict has no 'text_projection' (expected the CLIP checkpoint's state_dict)")

@@ -78,16 +78,40 @@ def test_text_tower_errors_are_loud():
         tw.encode_text(torch.zeros(2, 76, dtype=torch.int32))
 
 
+CLASSES = ["run", "jumping jacks", "pour water into a glass", "riding a bike"]   # pin_against_reference.py
+
+
+class GoldenTokenizer:
+    """stands in for the BPE tokenizer where the vocabulary file is absent (the GPU box): returns the token ids the
+    reference's tokenizer produced for exactly these sentences (stored in the golden file)"""
+
+    def __init__(self, tokens):
+        from clip_spm_b200.tokenizer import PROMPT_TEMPLATES
+        self.table = {t.format(c): tokens[ti, ci] for ti, t in enumerate(PROMPT_TEMPLATES) for ci, c in enumerate(CLASSES)}
+
+    def tokenize(self, texts):
+        return torch.stack([self.table[t] for t in texts]).int()
+
+
 def test_cnn_build_text_features_feeds_the_head():
-    """class names -> text features -> head, end to end through the CNN mirror (vocabulary file needed)"""
+    """class names -> text features -> episode head, end to end through the CNN mirror"""
     from clip_spm_b200.tokenizer import find_vocab
+    g = H.golden("text_tower_4cls")
     try:
         find_vocab()
+        tok = None                               # the real tokenizer where its vocabulary exists
     except FileNotFoundError:
-        pytest.skip("CLIP BPE vocabulary file not available on this machine")
-    g = H.golden("text_tower_4cls")
+        tok = GoldenTokenizer(g["tokens"])
     ci = H.case_inputs("head_5w5s_t8")
     m = H.build_cuda_model(ci, 1, "bf16")
-    m.build_text_features(O.make_text_weights(512, seed=0),
-                          ["run", "jumping jacks", "pour water into a glass", "riding a bike"], None)
+    m.build_text_features(O.make_text_weights(512, seed=0), CLASSES, None, tokenizer=tok)
     assert H.rel_err(m.text_features_test.cpu(), g["text_features"]) < TOL["bf16"]
+    # the head accepts the new class list: real labels now index 4 classes
+    ep = ci["episode"]
+    su, qu = ci["feats"]
+    out = m.head(su.cuda()[None], qu.cuda()[None], ep["context_labels"].cuda()[None],
+                 (ep["real_support_labels"] % 4).cuda()[None], (ep["real_target_labels"] % 4).cuda()[None])
+    with torch.no_grad():
+        st = O.head_forward(ci["weights"], g["text_features"], su, qu, ep["context_labels"],
+                            ep["real_support_labels"] % 4, ep["real_target_labels"] % 4, O.DEFAULT_PARAMS, ci["single"])
+    assert H.rel_err(out["logits"].cpu().reshape(st["logits"].shape), st["logits"]) < 2e-2
