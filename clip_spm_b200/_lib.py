@@ -62,6 +62,11 @@ SIGNATURES = {
                                       ctypes.POINTER(ctypes.c_int64)]),
     "spm_text_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "spm_text_class_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "spm_transform_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "spm_frame_geometry": (c_int, [c_int, c_int] + [ctypes.POINTER(c_int)] * 4),
+    "spm_encode_frames_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "spm_eval_host_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float]
+                         + [c_void_p] * 5),
 }
 
 _lib = None

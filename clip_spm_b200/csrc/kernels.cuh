@@ -38,4 +38,9 @@ int k_vit_attention_f32(cudaStream_t st, const float* qkv, float* out, int n_fra
 int k_vit_attention_f32_init();
 int k_patch_im2col_f32(cudaStream_t st, const float* images, float* patches, int n_frames);
 
+// decoded RGB frames [F,H,W,3] uint8 -> Resize(256) / CenterCrop(224) / ToTensor (frame_transform.cu): exactly one of
+// out_f32 [F,3,224,224] and out_patch (the bf16 patch matrix of k_patch_im2col) is non-null
+int k_frame_transform(cudaStream_t st, const uint8_t* frames, int n_frames, int H, int W, float* out_f32,
+                      __nv_bfloat16* out_patch);
+
 }  // namespace spm

@@ -124,6 +124,8 @@ struct spm_handle {
   __nv_bfloat16* xnc = nullptr; // their LayerNorm output
   float* feats = nullptr;  // [max frames per call, D]
   long long feats_cap = 0;
+  float* img_scratch = nullptr;  // fp32 images of uint8 input frames (fp32-mode ViT and RN50 paths)
+  long long img_scratch_cap = 0;
   std::map<int, std::unique_ptr<spm::VitPlan>> vit_plans;
   // head workspace
   long long head_cap_E = 0, head_cap_S = 0, head_cap_Q = 0, head_cap_W = 0;
@@ -136,13 +138,14 @@ struct spm_handle {
   // forward workspace: logits/dists when the caller only wants loss/acc, host staging for spm_eval_host
   float *tmp_logits = nullptr, *tmp_dists = nullptr;
   struct Stage {
-    float *su = nullptr, *qu = nullptr, *lab = nullptr, *rs = nullptr, *rt = nullptr;
+    uint8_t *su = nullptr, *qu = nullptr;  // staged input frames (fp32 images or uint8 frames), byte-addressed
+    float *lab = nullptr, *rs = nullptr, *rt = nullptr;
     long long* tl = nullptr;
     float *logits = nullptr, *dists = nullptr, *loss = nullptr, *acc = nullptr;
     int* pred = nullptr;
     cudaEvent_t copied = nullptr, done = nullptr;
   } stage[2];
-  long long stage_cap_frames_s = 0, stage_cap_frames_q = 0;
+  long long stage_cap_frames_s = 0, stage_cap_frames_q = 0, stage_cap_bytes_s = 0, stage_cap_bytes_q = 0;
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
   std::vector<cudaEvent_t> ev_copied, ev_done;  // per chunk of one spm_eval_host call
   // pinned host landing zone for the results: an async D2H into the caller's (possibly pageable) buffers would
@@ -474,10 +477,27 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
   return 0;
 }
 
+// A run of frames: fp32 images [n,3,224,224], or (frames_u8 != null) decoded RGB uint8 frames [n,H,W,3] that go
+// through the Resize/CenterCrop/ToTensor kernel first (frame_transform.cu)
 struct Segment {
   const float* images;
   long long n_frames;
+  const uint8_t* frames_u8 = nullptr;
+  int H = 0, W = 0;
 };
+
+// fp32 images of frames [a, b) of a segment: the caller's own, or transformed into the handle's scratch
+int segment_images(spm_handle* h, cudaStream_t st, const Segment& seg, long long a, long long b, const float** out) {
+  if (seg.frames_u8 == nullptr) { *out = seg.images + a * FRAME_ELEMS; return 0; }
+  if (b - a > h->img_scratch_cap) {
+    SPM_TRY(dalloc_t(h, &h->img_scratch, (b - a) * FRAME_ELEMS));
+    h->img_scratch_cap = b - a;
+  }
+  SPM_KERNEL(k_frame_transform(st, seg.frames_u8 + a * (long long)seg.H * seg.W * 3, (int)(b - a), seg.H, seg.W,
+                               h->img_scratch, nullptr));
+  *out = h->img_scratch;
+  return 0;
+}
 
 // Encode the concatenation of the segments; feature rows come out in segment order.
 int encode_segments(spm_handle* h, cudaStream_t st, const Segment* segs, int nseg, float* feats_out) {
@@ -485,7 +505,13 @@ int encode_segments(spm_handle* h, cudaStream_t st, const Segment* segs, int nse
   if (h->cfg.backbone == SPM_BACKBONE_RN50) {
     long long done = 0;
     for (int s = 0; s < nseg; ++s) {
-      SPM_TRY(rn50_encode(h->rn50, st, segs[s].images, (int)segs[s].n_frames, feats_out + done * h->D));
+      const long long step = segs[s].frames_u8 ? 256 : segs[s].n_frames;  // uint8 input: bounded fp32 scratch
+      for (long long a = 0; a < segs[s].n_frames; a += step) {
+        const long long b = std::min(segs[s].n_frames, a + step);
+        const float* img;
+        SPM_TRY(segment_images(h, st, segs[s], a, b, &img));
+        SPM_TRY(rn50_encode(h->rn50, st, img, (int)(b - a), feats_out + (done + a) * h->D));
+      }
       done += segs[s].n_frames;
     }
     return 0;
@@ -499,12 +525,18 @@ int encode_segments(spm_handle* h, cudaStream_t st, const Segment* segs, int nse
     for (int s = 0; s < nseg; ++s) {
       const long long a = std::max(f0, seg0), b = std::min(f1, seg0 + segs[s].n_frames);
       if (a < b) {
-        if (h->fp32)
-          SPM_KERNEL(k_patch_im2col_f32(st, segs[s].images + (a - seg0) * FRAME_ELEMS,
-                                        h->patches32 + (a - f0) * VIT_P * VIT_C, (int)(b - a)));
-        else
+        if (h->fp32) {
+          const float* img;
+          SPM_TRY(segment_images(h, st, segs[s], a - seg0, b - seg0, &img));
+          SPM_KERNEL(k_patch_im2col_f32(st, img, h->patches32 + (a - f0) * VIT_P * VIT_C, (int)(b - a)));
+        } else if (segs[s].frames_u8 != nullptr) {  // uint8 frames -> bf16 patch matrix in one kernel
+          SPM_KERNEL(k_frame_transform(st, segs[s].frames_u8 + (a - seg0) * (long long)segs[s].H * segs[s].W * 3,
+                                       (int)(b - a), segs[s].H, segs[s].W, nullptr,
+                                       h->patches + (a - f0) * VIT_P * VIT_C));
+        } else {
           SPM_KERNEL(k_patch_im2col(st, segs[s].images + (a - seg0) * FRAME_ELEMS,
                                     h->patches + (a - f0) * VIT_P * VIT_C, (int)(b - a)));
+        }
       }
       seg0 += segs[s].n_frames;
     }
@@ -702,9 +734,11 @@ int check_shapes(spm_handle* h, int E, int S, int Q, int W) {
   return 0;
 }
 
-int forward_impl(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const float* su_img, const float* qu_img,
+// su_img / qu_img: fp32 [.,3,224,224] images, or -- when img_h > 0 -- uint8 [., img_h, img_w, 3] decoded frames
+int forward_impl(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const void* su_img, const void* qu_img,
                  const float* labels, const float* real_s, const float* real_t, const long long* target_labels,
-                 float tasks_per_batch, float* logits, float* dists, float* loss, float* acc, int* pred) {
+                 float tasks_per_batch, float* logits, float* dists, float* loss, float* acc, int* pred, int img_h = 0,
+                 int img_w = 0) {
   SPM_TRY(check_shapes(h, E, S, Q, W));
   SPM_TRY(ensure_head_workspace(h, E, S, Q, W));
   const int T = h->cfg.seq_len, D = h->D, N = S + Q;
@@ -713,7 +747,18 @@ int forward_impl(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, con
     SPM_TRY(dalloc_t(h, &h->feats, nf * D));
     h->feats_cap = nf;
   }
-  Segment segs[2] = {{su_img, (long long)E * S * T}, {qu_img, (long long)E * Q * T}};
+  Segment segs[2];
+  segs[0].n_frames = (long long)E * S * T;
+  segs[1].n_frames = (long long)E * Q * T;
+  if (img_h > 0) {
+    segs[0].frames_u8 = static_cast<const uint8_t*>(su_img);
+    segs[1].frames_u8 = static_cast<const uint8_t*>(qu_img);
+    segs[0].H = segs[1].H = img_h;
+    segs[0].W = segs[1].W = img_w;
+  } else {
+    segs[0].images = static_cast<const float*>(su_img);
+    segs[1].images = static_cast<const float*>(qu_img);
+  }
   SPM_TRY(encode_segments(h, st, segs, 2, h->feats));
   // feature rows [E*S*T | E*Q*T] -> X [E, N, T, D] (supports first inside each episode)
   const size_t row = (size_t)T * D * 4;
@@ -825,7 +870,24 @@ int spm_encode_frames(spm_handle* h, void* stream, const float* images, int n_fr
   SPM_CHECK(h != nullptr, "spm_encode_frames: null handle");
   if (n_frames <= 0) return 0;  // empty input: nothing to do (pointers may be null)
   SPM_CHECK(images != nullptr && feats_out != nullptr, "spm_encode_frames: null argument");
-  Segment seg{images, n_frames};
+  Segment seg;
+  seg.images = images;
+  seg.n_frames = n_frames;
+  return encode_segments(h, (cudaStream_t)stream, &seg, 1, feats_out);
+}
+
+int spm_encode_frames_u8(spm_handle* h, void* stream, const uint8_t* frames, int n_frames, int H, int W,
+                         float* feats_out) {
+  SPM_CHECK(h != nullptr, "spm_encode_frames_u8: null handle");
+  if (n_frames <= 0) return 0;
+  SPM_CHECK(frames != nullptr && feats_out != nullptr, "spm_encode_frames_u8: null argument");
+  SPM_CHECK(H > 0 && W > 0, "spm_encode_frames_u8: bad frame size");
+  Segment seg;
+  seg.images = nullptr;
+  seg.n_frames = n_frames;
+  seg.frames_u8 = frames;
+  seg.H = H;
+  seg.W = W;
   return encode_segments(h, (cudaStream_t)stream, &seg, 1, feats_out);
 }
 
@@ -872,9 +934,11 @@ int spm_eval(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, c
                       logits_out, dists_out, loss_out, acc_out, pred_out);
 }
 
-int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const float* su_h, const float* qu_h,
-                  const float* lab_h, const float* rs_h, const float* rt_h, const int64_t* tl_h, float tasks_per_batch,
-                  float* logits_h, float* dists_h, float* loss_h, float* acc_h, int32_t* pred_h) {
+// frame_bytes: bytes of one input frame in host memory (fp32 image, or img_h x img_w x 3 uint8 when img_h > 0)
+static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, const uint8_t* su_h, const uint8_t* qu_h,
+                          long long frame_bytes, int img_h, int img_w, const float* lab_h, const float* rs_h,
+                          const float* rt_h, const int64_t* tl_h, float tasks_per_batch, float* logits_h,
+                          float* dists_h, float* loss_h, float* acc_h, int32_t* pred_h) {
   SPM_CHECK(h && su_h && qu_h && lab_h && rs_h && rt_h && tl_h, "spm_eval_host: null argument");
   SPM_TRY(check_shapes(h, 1, S, Q, W));
   const int T = h->cfg.seq_len;
@@ -886,9 +950,11 @@ int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const floa
     SPM_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
   }
   spm_handle::Stage& s = h->stage[0];
-  if (R * fs > h->stage_cap_frames_s || R * fq > h->stage_cap_frames_q) {
-    SPM_TRY(dalloc_t(h, &s.su, R * fs * FRAME_ELEMS));
-    SPM_TRY(dalloc_t(h, &s.qu, R * fq * FRAME_ELEMS));
+  if (R * fs * frame_bytes > h->stage_cap_bytes_s || R * fq * frame_bytes > h->stage_cap_bytes_q ||
+      R * fs > h->stage_cap_frames_s || R * fq > h->stage_cap_frames_q) {
+    SPM_TRY(dalloc_t(h, &s.su, R * fs * frame_bytes));
+    SPM_TRY(dalloc_t(h, &s.qu, R * fq * frame_bytes));
+    h->stage_cap_bytes_s = R * fs * frame_bytes; h->stage_cap_bytes_q = R * fq * frame_bytes;
     SPM_TRY(dalloc_t(h, &s.lab, (long long)R * S));
     SPM_TRY(dalloc_t(h, &s.rs, (long long)R * S));
     SPM_TRY(dalloc_t(h, &s.rt, (long long)R * Q));
@@ -942,10 +1008,10 @@ int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const floa
     const int e0 = starts[c], E = starts[c + 1] - e0, slot = e0 % R;
     // ring slot reuse: the chunk that last used these slots must have been consumed
     if (e0 + E - 1 >= R) SPM_CUDA(cudaStreamWaitEvent(cs, h->ev_done[chunk_of[e0 + E - 1 - R]], 0));
-    SPM_CUDA(cudaMemcpyAsync(s.su + slot * fs * FRAME_ELEMS, su_h + e0 * fs * FRAME_ELEMS,
-                             (size_t)E * fs * FRAME_ELEMS * 4, cudaMemcpyHostToDevice, cs));
-    SPM_CUDA(cudaMemcpyAsync(s.qu + slot * fq * FRAME_ELEMS, qu_h + e0 * fq * FRAME_ELEMS,
-                             (size_t)E * fq * FRAME_ELEMS * 4, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.su + slot * fs * frame_bytes, su_h + e0 * fs * frame_bytes,
+                             (size_t)(E * fs * frame_bytes), cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(s.qu + slot * fq * frame_bytes, qu_h + e0 * fq * frame_bytes,
+                             (size_t)(E * fq * frame_bytes), cudaMemcpyHostToDevice, cs));
     SPM_CUDA(cudaMemcpyAsync(s.lab + (long long)slot * S, lab_h + (long long)e0 * S, (size_t)E * S * 4, cudaMemcpyHostToDevice, cs));
     SPM_CUDA(cudaMemcpyAsync(s.rs + (long long)slot * S, rs_h + (long long)e0 * S, (size_t)E * S * 4, cudaMemcpyHostToDevice, cs));
     SPM_CUDA(cudaMemcpyAsync(s.rt + (long long)slot * Q, rt_h + (long long)e0 * Q, (size_t)E * Q * 4, cudaMemcpyHostToDevice, cs));
@@ -953,10 +1019,10 @@ int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const floa
     SPM_CUDA(cudaEventRecord(h->ev_copied[c], cs));
     SPM_CUDA(cudaStreamWaitEvent(ks, h->ev_copied[c], 0));
     float* lg = s.logits + (long long)slot * Q * W;
-    SPM_TRY(forward_impl(h, ks, E, S, Q, W, s.su + slot * fs * FRAME_ELEMS, s.qu + slot * fq * FRAME_ELEMS,
+    SPM_TRY(forward_impl(h, ks, E, S, Q, W, s.su + slot * fs * frame_bytes, s.qu + slot * fq * frame_bytes,
                          s.lab + (long long)slot * S, s.rs + (long long)slot * S, s.rt + (long long)slot * Q,
                          s.tl + (long long)slot * Q, tasks_per_batch, lg, s.dists + slot, s.loss + slot, s.acc + slot,
-                         s.pred + (long long)slot * Q));
+                         s.pred + (long long)slot * Q, img_h, img_w));
     SPM_CUDA(cudaMemcpyAsync(p_logits + (long long)e0 * Q * W, lg, (size_t)E * Q * W * 4, cudaMemcpyDeviceToHost, ks));
     SPM_CUDA(cudaMemcpyAsync(p_dists + e0, s.dists + slot, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
     SPM_CUDA(cudaMemcpyAsync(p_loss + e0, s.loss + slot, (size_t)E * 4, cudaMemcpyDeviceToHost, ks));
@@ -974,6 +1040,23 @@ int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const floa
   SPM_CUDA(cudaMemcpy(&flag, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
   SPM_CHECK(flag == 0, "spm_eval_host: an episode's number of distinct support labels differs from `W`");
   return 0;
+}
+
+int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const float* su_h, const float* qu_h,
+                  const float* lab_h, const float* rs_h, const float* rt_h, const int64_t* tl_h, float tasks_per_batch,
+                  float* logits_h, float* dists_h, float* loss_h, float* acc_h, int32_t* pred_h) {
+  return eval_host_impl(h, n_episodes, S, Q, W, reinterpret_cast<const uint8_t*>(su_h),
+                        reinterpret_cast<const uint8_t*>(qu_h), (long long)FRAME_ELEMS * 4, 0, 0, lab_h, rs_h, rt_h, tl_h,
+                        tasks_per_batch, logits_h, dists_h, loss_h, acc_h, pred_h);
+}
+
+int spm_eval_host_u8(spm_handle* h, int n_episodes, int S, int Q, int W, int img_h, int img_w, const uint8_t* su_h,
+                     const uint8_t* qu_h, const float* lab_h, const float* rs_h, const float* rt_h,
+                     const int64_t* tl_h, float tasks_per_batch, float* logits_h, float* dists_h, float* loss_h,
+                     float* acc_h, int32_t* pred_h) {
+  SPM_CHECK(img_h > 0 && img_w > 0, "spm_eval_host_u8: bad frame size");
+  return eval_host_impl(h, n_episodes, S, Q, W, su_h, qu_h, (long long)img_h * img_w * 3, img_h, img_w, lab_h, rs_h, rt_h,
+                        tl_h, tasks_per_batch, logits_h, dists_h, loss_h, acc_h, pred_h);
 }
 
 int spm_otam_distance(void* stream, int n_pairs, int W, int Q, int T, int D, const float* support, const float* target,

@@ -348,7 +348,46 @@ class CNN(nn.Module):
                                          self.tasks_per_batch, _p(logits), _p(dists), _p(loss), _p(acc), _p(pred)))
         return dict(logits=logits, dists=dists, loss=loss, acc=acc, pred=pred)
 
+    def evaluate_host_u8(self, context_frames, context_labels, target_frames, real_support_labels,
+                         real_target_labels, target_labels, n_episodes, way):
+        """evaluate_host on DECODED frames: uint8 [E*S*T, H, W, 3] / [E*Q*T, H, W, 3] host tensors (what the data
+        loader holds before its PIL Resize/CenterCrop/ToTensor chain, video_reader.py:265-272).  The transform runs
+        on the GPU, bit-exact with that chain; host->device traffic drops from 602 KB to H*W*3 bytes per frame."""
+        h = self._handle()
+        self._text()
+        lib = _lib.load()
+        E = int(n_episodes)
+        S, Q, W = context_labels.numel() // E, real_target_labels.numel() // E, int(way)
+        for t in (context_frames, target_frames):
+            assert not t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous() and t.dim() == 4 and t.shape[3] == 3
+        assert context_frames.shape[1:] == target_frames.shape[1:]
+        assert context_frames.shape[0] == E * S * self.seq_len and target_frames.shape[0] == E * Q * self.seq_len
+        for t in (context_labels, real_support_labels, real_target_labels):
+            assert not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        assert target_labels.dtype == torch.int64 and not target_labels.is_cuda
+        H, Wd = int(context_frames.shape[1]), int(context_frames.shape[2])
+        logits, dists = torch.empty(E, Q, W), torch.empty(E)
+        loss, acc, pred = torch.empty(E), torch.empty(E), torch.empty(E, Q, dtype=torch.int32)
+        with torch.cuda.device(self._dev):
+            _lib.check(lib.spm_eval_host_u8(h, E, S, Q, W, H, Wd, _p(context_frames), _p(target_frames),
+                                            _p(context_labels), _p(real_support_labels), _p(real_target_labels),
+                                            _p(target_labels), self.tasks_per_batch, _p(logits), _p(dists), _p(loss),
+                                            _p(acc), _p(pred)))
+        return dict(logits=logits, dists=dists, loss=loss, acc=acc, pred=pred)
+
     # --------------------------------------------------------------------------------------------- stage hooks
+    def encode_frames_u8(self, frames):
+        """decoded RGB frames uint8 [F, H, W, 3] (device) -> Resize/CenterCrop/ToTensor -> encoder -> [F, D]"""
+        h = self._handle()
+        if not frames.is_cuda or frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
+            raise RuntimeError("encode_frames_u8 takes a CUDA uint8 tensor [F, H, W, 3]")
+        frames = frames.contiguous()
+        out = torch.empty(frames.shape[0], self.mid_dim, device=self._dev)
+        _lib.check(_lib.load().spm_encode_frames_u8(h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
+                                                    _p(frames), frames.shape[0], frames.shape[1], frames.shape[2],
+                                                    _p(out)))
+        return out
+
     def encode_frames(self, images):
         """models/clip_fsar.py:672-689 / :593-608: [F,3,224,224] -> [F, D] (stage entry point for the tests)."""
         h = self._handle()

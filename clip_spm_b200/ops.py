@@ -70,3 +70,24 @@ def vit_attention(qkv, n_frames, impl="tcgen05"):
     out = torch.empty(n_frames * 197, 768, device=qkv.device, dtype=torch.bfloat16)
     _lib.check(lib.spm_vit_attention(_stream(), _ptr(qkv), _ptr(out), n_frames, 1 if impl == "mma" else 0))
     return out
+
+
+def frame_geometry(H, W):
+    """(resized_h, resized_w, crop_y, crop_x) the evaluation transform uses for an H x W frame (host arithmetic)."""
+    lib = _lib.load()
+    v = [ctypes.c_int() for _ in range(4)]
+    _lib.check(lib.spm_frame_geometry(int(H), int(W), *[ctypes.byref(x) for x in v]))
+    return tuple(x.value for x in v)
+
+
+def transform_frames(frames):
+    """Resize(256) -> CenterCrop(224) -> ToTensor of the reference's test pipeline (video_reader.py:83-111,265-272),
+    bit-exact: frames uint8 [F, H, W, 3] (decoded RGB) -> fp32 [F, 3, 224, 224] in [0, 1]."""
+    lib = _lib.load()
+    _need_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+    frames = frames.contiguous()
+    F, H, W, _ = frames.shape
+    out = torch.empty(F, 3, 224, 224, device=frames.device)
+    _lib.check(lib.spm_transform_frames(_stream(), _ptr(frames), F, H, W, _ptr(out)))
+    return out

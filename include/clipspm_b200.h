@@ -147,6 +147,25 @@ int spm_text_encode(spm_text* h, void* stream, const int32_t* tokens, int n_text
 int spm_text_class_features(spm_text* h, void* stream, const int32_t* tokens, int n_templates, int n_classes,
                             float* out);
 
+/* ---- evaluation-time frame transform (video_reader.py:83-111,265-272) ----
+ * Resize(256) [PIL BILINEAR with antialiasing, videotransforms/functional.py:24-73] -> CenterCrop(224)
+ * [video_transforms.py:204-247] -> ToTensor [uint8 HWC -> fp32 CHW / 255], bit-exact.
+ * frames: device uint8 [n_frames, H, W, 3] (decoded RGB, all of one size) -> images_out fp32 [n_frames, 3, 224, 224] */
+int spm_transform_frames(void* stream, const uint8_t* frames, int n_frames, int H, int W, float* images_out);
+/* spm_encode_frames on decoded frames: transform + encoder (on the bf16 ViT path the transform kernel writes the
+ * patch-embedding GEMM's bf16 operand directly; the fp32 image is never materialised) */
+int spm_encode_frames_u8(spm_handle* h, void* stream, const uint8_t* frames, int n_frames, int H, int W,
+                         float* feats_out);
+/* spm_eval_host on decoded frames in HOST memory: support frames uint8 [E, S*T, img_h, img_w, 3], target frames
+ * [E, Q*T, img_h, img_w, 3]; 4x fewer (or less) host->device bytes than fp32 images, same results bit for bit */
+int spm_eval_host_u8(spm_handle* h, int n_episodes, int S, int Q, int W, int img_h, int img_w,
+                     const uint8_t* support_frames_host, const uint8_t* target_frames_host,
+                     const float* support_labels_host, const float* real_support_host, const float* real_target_host,
+                     const int64_t* target_labels_host, float tasks_per_batch, float* logits_host, float* dists_host,
+                     float* loss_host, float* acc_host, int32_t* pred_host);
+/* the geometry that transform uses for an H x W frame (host arithmetic only; any output pointer may be null) */
+int spm_frame_geometry(int H, int W, int* resized_h, int* resized_w, int* crop_y, int* crop_x);
+
 #ifdef __cplusplus
 }
 #endif

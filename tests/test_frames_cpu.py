@@ -1,0 +1,46 @@
+"""CPU suite of the input-path row: the numpy restatement of Resize(256)/CenterCrop(224)/ToTensor against the golden
+hashes written from the reference's own transform chain (oracle/pin_preprocess.py), the frame sampler mirror against
+the reference's VideoDataset.get_seq outputs, and the library's host-side geometry arithmetic."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import preprocess_oracle as P
+from tests import helpers as H
+
+
+def _gold():
+    return {k: v.numpy() for k, v in H.golden("preprocess").items()}
+
+
+@pytest.mark.parametrize("name", ["k100_340x256", "up_320x240", "portrait_360x480", "tiny_176x100", "odd_427x241"])
+def test_oracle_transform_matches_reference_golden(name):
+    g = _gold()
+    frames = P.make_frames(name)
+    out = P.preprocess_frames(frames)
+    assert tuple(g[name + "/geometry"]) == P.geometry(*frames.shape[1:3])
+    assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).digest() == g[name + "/sha256"].tobytes()
+    assert np.array_equal(np.round(out[0, :, 100:116, :] * 255).astype(np.uint8), g[name + "/frame0_band"])
+
+
+def test_frame_sampler_matches_reference_golden():
+    from clip_spm_b200.frames import eval_frame_indices
+    g = _gold()
+    keys = [k for k in g if k.startswith("frame_idx/")]
+    assert len(keys) >= 9
+    for k in keys:
+        n, T = map(int, k.split("/")[1].split("_"))
+        assert eval_frame_indices(n, T) == list(g[k]), k
+        assert P.eval_frame_indices(n, T) == list(g[k]), k
+
+
+def test_library_geometry_matches_oracle():
+    """spm_frame_geometry is host arithmetic (no GPU): int() truncation of the long side, round-half-even crop origin"""
+    from clip_spm_b200.ops import frame_geometry
+    rng = np.random.RandomState(0)
+    sizes = [(256, 340), (240, 320), (720, 1280), (480, 360), (256, 256), (100, 176), (241, 427), (300, 256),
+             (224, 224), (1080, 1920), (257, 256), (256, 257), (255, 341)]
+    sizes += [tuple(int(v) for v in rng.randint(60, 2000, size=2)) for _ in range(300)]
+    for h, w in sizes:
+        assert frame_geometry(h, w) == P.geometry(h, w), (h, w)
