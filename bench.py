@@ -267,7 +267,7 @@ def main():
     summary = sweep.summarize(stats)
 
     # ---- e2e: host buffers through the public host call, copies inside the timed region
-    e2e = None
+    e2e = e2e_u8 = None
     if not args.no_e2e:
         hb = sweep.synthetic_episode_batch(ids, WAY, SHOT, QPC, T, N_TEXT, "cpu", pin=True)
         call = lambda: net.evaluate_host(hb["context_images"], hb["context_labels"].contiguous(), hb["target_images"],
@@ -286,6 +286,30 @@ def main():
         d2h = EPS * (Q * WAY * 4 + 3 * 4 + Q * 4)
         e2e = {"value": total_eps / float(dt), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h}
+        # ---- same call on DECODED frames (uint8 340x256, the size Kinetics frames are extracted at): the data
+        # loader's Resize/CenterCrop/ToTensor runs on the GPU (bit-exact, csrc/frame_transform.cu), H2D shrinks 2.3x
+        hl = {k: hb[k] for k in ("context_labels", "real_support_labels", "real_target_labels", "target_labels")}
+        del hb, call
+        FH, FW = 256, 340
+        g = torch.Generator().manual_seed(1234 + rank)
+        su8 = torch.randint(0, 256, (EPS * S * T, FH, FW, 3), dtype=torch.uint8, generator=g).pin_memory()
+        qu8 = torch.randint(0, 256, (EPS * Q * T, FH, FW, 3), dtype=torch.uint8, generator=g).pin_memory()
+        call8 = lambda: net.evaluate_host_u8(su8, hl["context_labels"].contiguous(), qu8,
+                                             hl["real_support_labels"].contiguous(),
+                                             hl["real_target_labels"].contiguous(), hl["target_labels"].contiguous(),
+                                             EPS, WAY)
+        call8(); call8()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = call8()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_u8 = {"value": total_eps / float(dt), "unit": "episodes/s", "input": "uint8 frames %dx%d" % (FW, FH),
+                  "h2d_bytes_per_step": EPS * (FRAMES * FH * FW * 3 + (2 * S + Q) * 4 + Q * 8),
+                  "d2h_bytes_per_step": d2h}
 
     if rank != 0:
         if world > 1:
@@ -314,7 +338,7 @@ def main():
                        "l2": "step inputs (%.0f MB) exceed the 126 MB L2; no explicit flush" % (EPS * FRAMES * 0.602112),
                        "weights": "random-init (no checkpoints offline)"},
             "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
-            "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "e2e_u8": e2e_u8, "clocks": clocks,
             "sweep_stats": summary}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
