@@ -23,6 +23,7 @@ static std::vector<GemmRecord> g_records;
 static int g_used = 0;
 static bool g_profiling = false;
 
+bool profile_armed() { return g_profiling; }
 bool profile_gemm_begin(cudaStream_t st, int tag, double flops, int* slot) {
   if (!g_profiling || g_used >= (int)g_records.size()) return false;
   GemmRecord& r = g_records[g_used];

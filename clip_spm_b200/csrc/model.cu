@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -18,6 +19,7 @@
 #include "gemm.cuh"
 #include "head_kernels.cuh"
 #include "kernels.cuh"
+#include "profile.cuh"
 #include "rn50.cuh"
 
 namespace spm {
@@ -94,6 +96,7 @@ struct CtxPlan {
 };
 struct HeadPlan {
   int E, S, Q, W;
+  const float* X;  // frame-feature base the plan's tensor maps point at
   GemmOp mc1, mc2, tt0, tt3, gt0, gt2, gv0, gv2;
   CtxPlan c2, c1;
 };
@@ -124,6 +127,15 @@ struct spm_handle {
   __nv_bfloat16* xnc = nullptr; // their LayerNorm output
   float* feats = nullptr;  // [max frames per call, D]
   long long feats_cap = 0;
+  // Two encoder workspaces: consecutive frame chunks alternate between two streams so that the ramp-up / tail of
+  // one chunk's persistent kernels and its memory-bound kernels (LayerNorm, attention) overlap the other chunk's GEMMs.
+  struct VitWs {
+    __nv_bfloat16 *patches, *xn, *qkv, *attn, *hid, *cls, *xnc;
+    float *x, *xc;
+  } vit_ws[2] = {};
+  int cur_ws = 0, enc_streams = 2;
+  cudaStream_t enc_stream[2] = {nullptr, nullptr};
+  cudaEvent_t enc_fork = nullptr, enc_join[2] = {nullptr, nullptr};
   float* img_scratch = nullptr;  // fp32 images of uint8 input frames (fp32-mode ViT and RN50 paths)
   long long img_scratch_cap = 0;
   std::map<int, std::unique_ptr<spm::VitPlan>> vit_plans;
@@ -135,6 +147,13 @@ struct spm_handle {
         *SUPRO2 = nullptr, *ACC = nullptr, *D3 = nullptr;
   int* err_flag = nullptr;
   std::vector<std::unique_ptr<spm::HeadPlan>> head_plans;
+  // `X` is the feature block the head currently reads: its own buffer (Xhead), or a group of episodes inside Xall
+  // when the forward pipelines episode groups (encoder of group g+1 overlaps the head of group g on head_stream)
+  float *Xhead = nullptr, *Xall = nullptr;
+  long long xall_cap = 0, tmp_out_cap = 0;
+  cudaStream_t head_stream = nullptr;
+  cudaEvent_t head_done = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
   // forward workspace: logits/dists when the caller only wants loss/acc, host staging for spm_eval_host
   float *tmp_logits = nullptr, *tmp_dists = nullptr;
   struct Stage {
@@ -328,18 +347,37 @@ int plan_gemm(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   return 0;
 }
 
+void select_vit_ws(spm_handle* h, int i) {
+  const spm_handle::VitWs& w = h->vit_ws[i];
+  h->patches = w.patches; h->xn = w.xn; h->qkv = w.qkv; h->attn = w.attn; h->hid = w.hid; h->cls = w.cls;
+  h->xnc = w.xnc; h->x = w.x; h->xc = w.xc;
+  h->cur_ws = i;
+}
+
 int ensure_vit_workspace(spm_handle* h) {
   if (h->x != nullptr) return 0;
   const long long M = (long long)h->frame_chunk * VIT_L;
-  SPM_TRY(dalloc_t(h, &h->patches, (long long)h->frame_chunk * VIT_P * VIT_C));
-  SPM_TRY(dalloc_t(h, &h->x, M * VIT_C));
-  SPM_TRY(dalloc_t(h, &h->xn, M * VIT_C));
-  SPM_TRY(dalloc_t(h, &h->qkv, M * 3 * VIT_C));
-  SPM_TRY(dalloc_t(h, &h->attn, M * VIT_C));
-  SPM_TRY(dalloc_t(h, &h->hid, M * 4 * VIT_C));
-  SPM_TRY(dalloc_t(h, &h->cls, (long long)h->frame_chunk * VIT_C));
-  SPM_TRY(dalloc_t(h, &h->xc, (long long)h->frame_chunk * VIT_C));
-  SPM_TRY(dalloc_t(h, &h->xnc, (long long)h->frame_chunk * VIT_C));
+  if (h->fp32) h->enc_streams = 1;
+  for (int i = 0; i < h->enc_streams; ++i) {
+    spm_handle::VitWs& w = h->vit_ws[i];
+    SPM_TRY(dalloc_t(h, &w.patches, (long long)h->frame_chunk * VIT_P * VIT_C));
+    SPM_TRY(dalloc_t(h, &w.x, M * VIT_C));
+    SPM_TRY(dalloc_t(h, &w.xn, M * VIT_C));
+    SPM_TRY(dalloc_t(h, &w.qkv, M * 3 * VIT_C));
+    SPM_TRY(dalloc_t(h, &w.attn, M * VIT_C));
+    SPM_TRY(dalloc_t(h, &w.hid, M * 4 * VIT_C));
+    SPM_TRY(dalloc_t(h, &w.cls, (long long)h->frame_chunk * VIT_C));
+    SPM_TRY(dalloc_t(h, &w.xc, (long long)h->frame_chunk * VIT_C));
+    SPM_TRY(dalloc_t(h, &w.xnc, (long long)h->frame_chunk * VIT_C));
+  }
+  if (h->enc_streams > 1) {
+    for (int i = 0; i < 2; ++i) {
+      SPM_CUDA(cudaStreamCreateWithFlags(&h->enc_stream[i], cudaStreamNonBlocking));
+      SPM_CUDA(cudaEventCreateWithFlags(&h->enc_join[i], cudaEventDisableTiming));
+    }
+    SPM_CUDA(cudaEventCreateWithFlags(&h->enc_fork, cudaEventDisableTiming));
+  }
+  select_vit_ws(h, 0);
   if (h->fp32) {
     SPM_TRY(dalloc_t(h, &h->patches32, (long long)h->frame_chunk * VIT_P * VIT_C));
     SPM_TRY(dalloc_t(h, &h->xn32, M * VIT_C));
@@ -352,7 +390,8 @@ int ensure_vit_workspace(spm_handle* h) {
 }
 
 int get_vit_plan(spm_handle* h, int F, VitPlan** out) {
-  auto it = h->vit_plans.find(F);
+  const int key = F * 2 + h->cur_ws;  // plans bake the workspace pointers into their tensor maps
+  auto it = h->vit_plans.find(key);
   if (it != h->vit_plans.end()) { *out = it->second.get(); return 0; }
   std::unique_ptr<VitPlan> pl(new VitPlan());
   const int C = VIT_C, M = F * VIT_L;
@@ -413,7 +452,7 @@ int get_vit_plan(spm_handle* h, int F, VitPlan** out) {
     SPM_TRY(plan_gemm(&pl->fin, kind, a_cls, C, f32 ? (const void*)h->vit32.projT : (const void*)v.projT, C, F, VIT_OUT, C, ep, h->sms));
   }
   *out = pl.get();
-  h->vit_plans[F] = std::move(pl);
+  h->vit_plans[key] = std::move(pl);
   return 0;
 }
 
@@ -500,7 +539,10 @@ int segment_images(spm_handle* h, cudaStream_t st, const Segment& seg, long long
 }
 
 // Encode the concatenation of the segments; feature rows come out in segment order.
-int encode_segments(spm_handle* h, cudaStream_t st, const Segment* segs, int nseg, float* feats_out) {
+// after_chunk(frames_done, chunk_no, chunk_stream) is called once the kernels of a chunk have been enqueued
+using ChunkHook = std::function<int(long long, int, cudaStream_t)>;
+int encode_segments(spm_handle* h, cudaStream_t st, const Segment* segs, int nseg, float* feats_out,
+                    const ChunkHook* after_chunk = nullptr) {
   SPM_CHECK(h->weights_loaded, "encode: weights not loaded (spm_load_weights)");
   if (h->cfg.backbone == SPM_BACKBONE_RN50) {
     long long done = 0;
@@ -519,8 +561,22 @@ int encode_segments(spm_handle* h, cudaStream_t st, const Segment* segs, int nse
   SPM_TRY(ensure_vit_workspace(h));
   long long total = 0;
   for (int s = 0; s < nseg; ++s) total += segs[s].n_frames;
-  for (long long f0 = 0; f0 < total; f0 += h->frame_chunk) {
+  // more than one chunk: alternate chunks between the two encoder streams (forked from / joined back into `st`)
+  const bool dual = h->enc_streams > 1 && total > h->frame_chunk && !profile_armed();
+  cudaStream_t caller = st;
+  if (dual) {
+    SPM_CUDA(cudaEventRecord(h->enc_fork, caller));
+    for (int i = 0; i < 2; ++i) SPM_CUDA(cudaStreamWaitEvent(h->enc_stream[i], h->enc_fork, 0));
+  }
+  int chunk_no = 0;
+  for (long long f0 = 0; f0 < total; f0 += h->frame_chunk, ++chunk_no) {
     const long long f1 = std::min(total, f0 + h->frame_chunk);
+    if (dual) {
+      select_vit_ws(h, chunk_no & 1);
+      st = h->enc_stream[chunk_no & 1];
+    } else if (h->cur_ws != 0) {
+      select_vit_ws(h, 0);
+    }
     long long seg0 = 0;
     for (int s = 0; s < nseg; ++s) {
       const long long a = std::max(f0, seg0), b = std::min(f1, seg0 + segs[s].n_frames);
@@ -541,6 +597,13 @@ int encode_segments(spm_handle* h, cudaStream_t st, const Segment* segs, int nse
       seg0 += segs[s].n_frames;
     }
     SPM_TRY(vit_run(h, st, (int)(f1 - f0), feats_out + f0 * h->D));
+    if (after_chunk != nullptr) SPM_TRY((*after_chunk)(f1, chunk_no, st));
+  }
+  if (dual) {
+    for (int i = 0; i < 2; ++i) {
+      SPM_CUDA(cudaEventRecord(h->enc_join[i], h->enc_stream[i]));
+      SPM_CUDA(cudaStreamWaitEvent(caller, h->enc_join[i], 0));
+    }
   }
   return 0;
 }
@@ -556,7 +619,8 @@ int ensure_head_workspace(spm_handle* h, int E, int S, int Q, int W) {
                   cQ = std::max<long long>(Q, h->head_cap_Q), cW = std::max<long long>(W, h->head_cap_W);
   const long long T = h->cfg.seq_len, D = h->D, N = cS + cQ, V = cE * N;
   const long long R2 = 2 * V * (T + 1), R1 = cE * T * (cW + cS + 1 + cQ), R = std::max(R1, R2);
-  SPM_TRY(dalloc_t(h, &h->X, V * T * D));
+  SPM_TRY(dalloc_t(h, &h->Xhead, V * T * D));
+  h->X = h->Xhead;
   SPM_TRY(dalloc_t(h, &h->XC, V * T * 3 * D));
   SPM_TRY(dalloc_t(h, &h->C1, V * T * D));
   SPM_TRY(dalloc_t(h, &h->C2, V * T * D));
@@ -580,8 +644,6 @@ int ensure_head_workspace(spm_handle* h, int E, int S, int Q, int W) {
   SPM_TRY(dalloc_t(h, &h->SUPRO2, cE * cW * T * D));
   SPM_TRY(dalloc_t(h, &h->ACC, cE * cQ * cW));
   SPM_TRY(dalloc_t(h, &h->D3, cE * cW));
-  SPM_TRY(dalloc_t(h, &h->tmp_logits, cE * cQ * cW));
-  SPM_TRY(dalloc_t(h, &h->tmp_dists, cE));
   if (h->err_flag == nullptr) {
     SPM_TRY(dalloc_t(h, &h->err_flag, 1));
     SPM_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
@@ -610,9 +672,9 @@ int plan_ctx(spm_handle* h, CtxPlan* p, const CtxW& w, int R, float* seq, float*
 int get_head_plan(spm_handle* h, int E, int S, int Q, int W, HeadPlan** out) {
   SPM_TRY(ensure_head_workspace(h, E, S, Q, W));
   for (auto& p : h->head_plans)
-    if (p->E == E && p->S == S && p->Q == Q && p->W == W) { *out = p.get(); return 0; }
+    if (p->E == E && p->S == S && p->Q == Q && p->W == W && p->X == h->X) { *out = p.get(); return 0; }
   std::unique_ptr<HeadPlan> pl(new HeadPlan());
-  pl->E = E; pl->S = S; pl->Q = Q; pl->W = W;
+  pl->E = E; pl->S = S; pl->Q = Q; pl->W = W; pl->X = h->X;
   const HeadW& w = h->head;
   const int T = h->cfg.seq_len, D = h->D, N = S + Q, V = E * N;
   {
@@ -740,36 +802,104 @@ int forward_impl(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, con
                  float tasks_per_batch, float* logits, float* dists, float* loss, float* acc, int* pred, int img_h = 0,
                  int img_w = 0) {
   SPM_TRY(check_shapes(h, E, S, Q, W));
-  SPM_TRY(ensure_head_workspace(h, E, S, Q, W));
   const int T = h->cfg.seq_len, D = h->D, N = S + Q;
   const long long nf = (long long)E * N * T;
-  if (nf > h->feats_cap) {
-    SPM_TRY(dalloc_t(h, &h->feats, nf * D));
-    h->feats_cap = nf;
+  if (nf > h->xall_cap) {
+    SPM_TRY(dalloc_t(h, &h->Xall, nf * D));
+    h->xall_cap = nf;
+    h->head_plans.clear();
   }
-  Segment segs[2];
-  segs[0].n_frames = (long long)E * S * T;
-  segs[1].n_frames = (long long)E * Q * T;
-  if (img_h > 0) {
-    segs[0].frames_u8 = static_cast<const uint8_t*>(su_img);
-    segs[1].frames_u8 = static_cast<const uint8_t*>(qu_img);
-    segs[0].H = segs[1].H = img_h;
-    segs[0].W = segs[1].W = img_w;
-  } else {
-    segs[0].images = static_cast<const float*>(su_img);
-    segs[1].images = static_cast<const float*>(qu_img);
+  if ((long long)E * Q * W > h->tmp_out_cap) {
+    SPM_TRY(dalloc_t(h, &h->tmp_logits, (long long)E * Q * W));
+    SPM_TRY(dalloc_t(h, &h->tmp_dists, E));
+    h->tmp_out_cap = (long long)E * Q * W;
   }
-  SPM_TRY(encode_segments(h, st, segs, 2, h->feats));
-  // feature rows [E*S*T | E*Q*T] -> X [E, N, T, D] (supports first inside each episode)
-  const size_t row = (size_t)T * D * 4;
-  SPM_CUDA(cudaMemcpy2DAsync(h->X, (size_t)N * row, h->feats, (size_t)S * row, (size_t)S * row, E,
-                             cudaMemcpyDeviceToDevice, st));
-  SPM_CUDA(cudaMemcpy2DAsync(h->X + (long long)S * T * D, (size_t)N * row, h->feats + (long long)E * S * T * D,
-                             (size_t)Q * row, (size_t)Q * row, E, cudaMemcpyDeviceToDevice, st));
   if (logits == nullptr) logits = h->tmp_logits;
   if (dists == nullptr) dists = h->tmp_dists;
-  return head_run(h, st, E, S, Q, W, labels, real_s, real_t, target_labels, tasks_per_batch, logits, dists, loss, acc,
-                  pred);
+  // frames in episode-major order (supports, then queries of each episode): the encoder writes X [E, N, T, D] directly
+  std::vector<Segment> segs(2 * (size_t)E);
+  const long long fb = img_h > 0 ? (long long)img_h * img_w * 3 : (long long)FRAME_ELEMS * 4;  // bytes per frame
+  for (int e = 0; e < E; ++e) {
+    Segment& a = segs[2 * e];
+    Segment& b = segs[2 * e + 1];
+    a.n_frames = (long long)S * T;
+    b.n_frames = (long long)Q * T;
+    const uint8_t* pa = static_cast<const uint8_t*>(su_img) + (long long)e * S * T * fb;
+    const uint8_t* pb = static_cast<const uint8_t*>(qu_img) + (long long)e * Q * T * fb;
+    if (img_h > 0) {
+      a.frames_u8 = pa; b.frames_u8 = pb;
+      a.H = b.H = img_h; a.W = b.W = img_w;
+    } else {
+      a.images = reinterpret_cast<const float*>(pa);
+      b.images = reinterpret_cast<const float*>(pb);
+    }
+  }
+  // Pipelined form (bf16 ViT, several chunks, not while GEMM launches are being event-timed): episodes are split
+  // into groups; as soon as the chunks holding a group's frames are enqueued its head is enqueued on head_stream,
+  // where it overlaps the encoder chunks of the following groups.  Only the last group's head is exposed.
+  const bool vit = h->cfg.backbone == SPM_BACKBONE_VIT_B16;
+  const bool pipelined = vit && !h->fp32 && h->enc_streams > 1 && !profile_armed() && E >= 2 && nf > h->frame_chunk;
+  if (!vit) {
+    // RN50 consumes contiguous runs of frames in its own 64-frame chunks: encode [all supports | all queries] and
+    // scatter the feature rows into the episode-major X
+    if (nf > h->feats_cap) {
+      SPM_TRY(dalloc_t(h, &h->feats, nf * D));
+      h->feats_cap = nf;
+    }
+    Segment two[2] = {segs[0], segs[1]};
+    two[0].n_frames = (long long)E * S * T;
+    two[1].n_frames = (long long)E * Q * T;
+    SPM_TRY(encode_segments(h, st, two, 2, h->feats));
+    const size_t row = (size_t)T * D * 4;
+    SPM_CUDA(cudaMemcpy2DAsync(h->Xall, (size_t)N * row, h->feats, (size_t)S * row, (size_t)S * row, E,
+                               cudaMemcpyDeviceToDevice, st));
+    SPM_CUDA(cudaMemcpy2DAsync(h->Xall + (long long)S * T * D, (size_t)N * row, h->feats + (long long)E * S * T * D,
+                               (size_t)Q * row, (size_t)Q * row, E, cudaMemcpyDeviceToDevice, st));
+  }
+  if (!pipelined) {
+    if (vit) SPM_TRY(encode_segments(h, st, segs.data(), (int)segs.size(), h->Xall));
+    SPM_TRY(ensure_head_workspace(h, E, S, Q, W));
+    h->X = h->Xall;
+    const int rc = head_run(h, st, E, S, Q, W, labels, real_s, real_t, target_labels, tasks_per_batch, logits, dists,
+                            loss, acc, pred);
+    h->X = h->Xhead;
+    return rc;
+  }
+  const int Eg = std::max(1, (E + 3) / 4), G = (E + Eg - 1) / Eg;
+  SPM_TRY(ensure_head_workspace(h, Eg, S, Q, W));
+  if (h->head_stream == nullptr) {
+    SPM_CUDA(cudaStreamCreateWithFlags(&h->head_stream, cudaStreamNonBlocking));
+    SPM_CUDA(cudaEventCreateWithFlags(&h->head_done, cudaEventDisableTiming));
+  }
+  const int n_chunks = (int)((nf + h->frame_chunk - 1) / h->frame_chunk);
+  while ((int)h->chunk_ev.size() < n_chunks) {
+    cudaEvent_t ev;
+    SPM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->chunk_ev.push_back(ev);
+  }
+  int next_group = 0;
+  ChunkHook hook = [&](long long frames_done, int chunk_no, cudaStream_t cs) -> int {
+    SPM_CUDA(cudaEventRecord(h->chunk_ev[chunk_no], cs));
+    while (next_group < G && (long long)std::min(E, (next_group + 1) * Eg) * N * T <= frames_done) {
+      const int e0 = next_group * Eg, ne = std::min(Eg, E - e0);
+      SPM_CUDA(cudaStreamWaitEvent(h->head_stream, h->chunk_ev[chunk_no], 0));
+      if (chunk_no > 0) SPM_CUDA(cudaStreamWaitEvent(h->head_stream, h->chunk_ev[chunk_no - 1], 0));
+      h->X = h->Xall + (long long)e0 * N * T * D;
+      const int rc = head_run(h, h->head_stream, ne, S, Q, W, labels + (long long)e0 * S, real_s + (long long)e0 * S,
+                              real_t + (long long)e0 * Q, target_labels ? target_labels + (long long)e0 * Q : nullptr,
+                              tasks_per_batch, logits + (long long)e0 * Q * W, dists + e0, loss ? loss + e0 : nullptr,
+                              acc ? acc + e0 : nullptr, pred ? pred + (long long)e0 * Q : nullptr);
+      h->X = h->Xhead;
+      if (rc) return rc;
+      ++next_group;
+    }
+    return 0;
+  };
+  SPM_TRY(encode_segments(h, st, segs.data(), (int)segs.size(), h->Xall, &hook));
+  SPM_CHECK(next_group == G, "forward: internal error (episode groups left without a head pass)");
+  SPM_CUDA(cudaEventRecord(h->head_done, h->head_stream));
+  SPM_CUDA(cudaStreamWaitEvent(st, h->head_done, 0));
+  return 0;
 }
 
 }  // namespace
@@ -808,6 +938,7 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
             "spm_create: gate hidden sizes must be positive multiples of 32");
   SPM_TRY(device_sm_count(&h->sms));
   if (const char* e = getenv("SPM_FRAME_CHUNK")) h->frame_chunk = std::max(1, atoi(e));
+  if (const char* e = getenv("SPM_ENC_STREAMS")) h->enc_streams = atoi(e) >= 2 ? 2 : 1;
   const char* err = "";
   if (gemm_init(&err)) { set_error(err); return 1; }
   SPM_KERNEL(k_vit_attention_init());
@@ -829,6 +960,14 @@ int spm_destroy(spm_handle* h) {
   if (h->pin_res) cudaFreeHost(h->pin_res);
   for (cudaEvent_t e : h->ev_copied) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (h->enc_stream[i]) cudaStreamDestroy(h->enc_stream[i]);
+    if (h->enc_join[i]) cudaEventDestroy(h->enc_join[i]);
+  }
+  if (h->enc_fork) cudaEventDestroy(h->enc_fork);
+  if (h->head_stream) cudaStreamDestroy(h->head_stream);
+  if (h->head_done) cudaEventDestroy(h->head_done);
+  for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
   delete h;

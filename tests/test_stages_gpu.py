@@ -322,3 +322,26 @@ def test_full_size_episodes_bf16_path_agrees_with_fp32_mode():
     assert H.rel_err(got["dists"], ref["dists"]) < 5e-2
     print("\nfull-size: logits rel err %.2e (abs %.4f); %d/%d queries pass the margin filter, all agree; raw agreement %d/%d"
           % (err, abs_err, int(safe.sum()), safe.numel(), int(agree.sum()), agree.numel()))
+
+
+@pytest.mark.parametrize("E,chunk", [(5, 4), (8, 6), (3, 8), (2, 3)])
+def test_pipelined_forward_equals_serial(monkeypatch, E, chunk):
+    """Several frame chunks + several episodes: the forward alternates chunks between two streams and runs the head
+    of each episode group on a third stream while later groups are still being encoded.  The results must equal the
+    single-stream schedule bit for bit (same kernels, same operands; only the overlap differs)."""
+    ci = H.case_inputs("vit_2w1s_t2_p0")
+    eps = [O.make_episode(4000 + e, 2, 1, 1, 2, 24, "P0") for e in range(E)]
+    cat = lambda k: torch.cat([e[k] for e in eps]).contiguous().cuda()
+    outs = []
+    for streams in ("1", "2"):
+        monkeypatch.setenv("SPM_ENC_STREAMS", streams)
+        monkeypatch.setenv("SPM_FRAME_CHUNK", str(chunk))      # 4 frames per episode -> several chunks per call
+        net = H.build_cuda_model(ci, E)
+        for _ in range(2):   # second call reuses every workspace / plan / event
+            out = net.forward_episodes(cat("context_images"), cat("context_labels"), cat("target_images"),
+                                       cat("real_support_labels"), cat("real_target_labels"), E, cat("target_labels"))
+        torch.cuda.synchronize()
+        outs.append({k: v.clone() for k, v in out.items() if torch.is_tensor(v)})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    assert torch.isfinite(outs[0]["logits"]).all()
