@@ -318,11 +318,12 @@ def main():
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
-    # dominant kernel = the 128x256 bf16 tcgen05 GEMM (tag 1); its algorithmic FLOPs / its summed launch time
+    # dominant kernel = the bf16 tcgen05 GEMM with 256-wide tiles (tag 1: gemm2_tcgen05_kernel, cta_group::2, a
+    # 256x256 tile per CTA pair -- plus the few 128x256 one-CTA launches); its algorithmic FLOPs / its launch time
     dom = 1
     achieved = (flops4[dom] / 1e12) / (ms4[dom] / 1e3) if ms4[dom] > 0 else None
     gemm_ms_all = sum(ms4)
-    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256,bf16> (frame-encoder linears)",
+    roofline = {"bound": "tensor", "kernel": "gemm2_tcgen05_kernel (bf16, cta_group::2, 256x256 per CTA pair; frame-encoder linears)",
                 "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
                 "frac": (achieved / peaks["bf16"]) if achieved else None, "peak_source": peaks["which"] +
                 " bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks["which"] == "measured" else "fallback 1590",

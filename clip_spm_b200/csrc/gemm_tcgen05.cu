@@ -287,10 +287,13 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   // Large bf16 problems run on CTA pairs (cta_group::2): 256x256 tile per pair, each CTA stages half of B
   static const bool allow_2cta = [] { const char* e = getenv("SPM_GEMM_2CTA"); return e == nullptr || atoi(e) != 0; }();
   const long long pair_tiles = (long long)((M + 255) / 256) * (N / 256);
-  // measured (profiles/r01_ncu_gemm_2cta_vs_1cta.txt): the pair kernel wins on long reductions (K = 3072: 178 vs
-  // 188 us, 75.6 % vs 70.3 % tensor-active) and loses on K = 768 (its cluster-wide barriers cost more per tile than
-  // the deeper pipeline gains), so it is selected by K.  SPM_GEMM_2CTA=2 forces it everywhere, 0 disables it.
-  static const int mode_2cta = [] { const char* e = getenv("SPM_GEMM_2CTA"); return e == nullptr ? 1 : atoi(e); }();
+  // Measured twice.  Kernel alone under ncu at max clock (profiles/r01_ncu_gemm_2cta_vs_1cta.txt): the pair kernel wins
+  // on long reductions (K = 3072: 178 vs 188 us) and loses on K = 768 (cluster-wide barriers per tile).  Inside the
+  // real step, which runs at the 1000 W power cap (~1.5 GHz), it wins everywhere: a pair stages 32 KB of operands per
+  // k-block and CTA instead of 48 KB, and the step gets 4 % faster (median 85.9 vs 89.5 ms, interleaved A/B runs on
+  // one box) -- energy per flop is what bounds a power-capped step.  So it is the default for every eligible shape;
+  // SPM_GEMM_2CTA=1 restricts it to K >= 2048, 0 disables it.
+  static const int mode_2cta = [] { const char* e = getenv("SPM_GEMM_2CTA"); return e == nullptr ? 2 : atoi(e); }();
   // (zero-bordered convolution outputs are handled by the 1-CTA CONV instantiation only)
   op->two_cta = (allow_2cta && kind == GEMM_BF16 && ep.border_w2 == 0 && N % 256 == 0 && pair_tiles >= num_sms / 2 &&
                  (K >= 2048 || mode_2cta == 2)) ? 1 : 0;

@@ -107,7 +107,7 @@ struct spm_handle {
   spm_config cfg;
   int D = 512, HT = 768, HV = 256;
   int sms = 148;
-  int frame_chunk = 256;
+  int frame_chunk = 512;
   bool prune_last = true;  // SPM_PRUNE_LAST=0 runs the last block on all tokens (same result, more work)
   bool attn_mma = false;  // SPM_ATTN=mma selects the mma.sync attention kernel instead of the tcgen05 one
   bool weights_loaded = false, text_set = false;
@@ -127,13 +127,15 @@ struct spm_handle {
   __nv_bfloat16* xnc = nullptr; // their LayerNorm output
   float* feats = nullptr;  // [max frames per call, D]
   long long feats_cap = 0;
-  // Two encoder workspaces: consecutive frame chunks alternate between two streams so that the ramp-up / tail of
-  // one chunk's persistent kernels and its memory-bound kernels (LayerNorm, attention) overlap the other chunk's GEMMs.
+  // Opt-in schedule (SPM_ENC_STREAMS=2): two encoder workspaces, consecutive frame chunks alternate between two streams
+  // and the heads of episode groups run on a third, so that ramp-up / tail / memory-bound kernels of one chunk overlap
+  // the other's GEMMs.  Bit-identical results (tests), but measured NOT faster: the step sits at the 1000 W power cap,
+  // where overlap buys nothing, and multi-stream runs showed sporadic 100-300 ms submission stalls.  Default: 1 stream.
   struct VitWs {
     __nv_bfloat16 *patches, *xn, *qkv, *attn, *hid, *cls, *xnc;
     float *x, *xc;
   } vit_ws[2] = {};
-  int cur_ws = 0, enc_streams = 2;
+  int cur_ws = 0, enc_streams = 1;  // 2 = opt-in (SPM_ENC_STREAMS): measured no faster under the power cap
   cudaStream_t enc_stream[2] = {nullptr, nullptr};
   cudaEvent_t enc_fork = nullptr, enc_join[2] = {nullptr, nullptr};
   float* img_scratch = nullptr;  // fp32 images of uint8 input frames (fp32-mode ViT and RN50 paths)
