@@ -50,6 +50,10 @@ struct GemmOp {
   // (tap/3 - 1) * conv_w2 + (tap%3 - 1) -- only the TMA coordinate changes, no im2col is materialised (0 = plain GEMM)
   int conv_w2 = 0, conv_cblocks = 0;
   int two_cta = 0;  // 1: launched as 2-CTA clusters (gemm2_tcgen05.cu), 256x256 tile per CTA pair
+  // 2-CTA kernel, fp32 out + fp32 residual with identity row mapping: the epilogue warps prefetch the residual tile
+  // by TMA (`tr`: fp32 [M, N], 32 x 32 boxes, SWIZZLE_128B) one column group ahead instead of loading it into registers
+  int res_tma = 0;
+  CUtensorMap tr;
 };
 
 // A: [M, K] (row stride lda elements), B: [N, K] (row stride ldb) -- both K-contiguous ("K-major"),

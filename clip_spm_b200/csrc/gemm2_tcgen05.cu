@@ -18,15 +18,19 @@
 namespace spm {
 
 namespace {
-struct G2 {
+// RES: residual boxes arrive by TMA into a ring of two 4 KB tiles per epilogue warp (which double as the staging
+// tiles); the operand pipeline gives up one stage for them.
+template <bool RES>
+struct G2T {
   static constexpr int BM = 128, BN = 256, BK = 64;
   static constexpr int A_BYTES = 128 * 128, B_BYTES = 128 * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = RES ? 5 : 6;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 1024;  // keeps the staging / residual tiles 1024-byte aligned (TMA SWIZZLE_128B)
   static constexpr int EPI_WARPS = 8;
-  static constexpr int STG_BYTES_PER_WARP = 32 * 128;
+  static constexpr int STG_BUFS = RES ? 2 : 1;
+  static constexpr int STG_BYTES_PER_WARP = STG_BUFS * 32 * 128;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024;
 };
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> leader CTA
@@ -83,17 +87,19 @@ struct Gemm2Args {
   int M, N, K;
 };
 
+template <bool RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const Gemm2Args args) {
-  using T = G2;
+                     const __grid_constant__ CUtensorMap tmR, const Gemm2Args args) {
+  using T = G2T<RES>;
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T::STAGES * T::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + T::STAGES;
   uint64_t* tfull_bar = empty_bar + T::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;  // [EPI_WARPS][2], RES only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * T::EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -116,6 +122,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * T::EPI_WARPS);  // epilogue warps of BOTH CTAs (only the leader's copy is used)
     }
+    if (RES)
+      for (int s = 0; s < 2 * T::EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_2cta(tmem_slot, T::TMEM_COLS);
@@ -189,18 +197,70 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t stg_u =
         smem_u32(smem + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES + (warp - 4) * T::STG_BYTES_PER_WARP);
     int t = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++t) {
-      const int acc = t & 1;
-      const uint32_t acc_phase = (t >> 1) & 1;
-      const int m_base = (tile / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
-      const int n0 = (tile % num_n) * T::BN;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T::BN);
-      gemm_epilogue_tile<T::BN>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+    if (RES) {
+      // This warp's column groups, in processing order: tile by tile, groups half, half+2, half+4, half+6 of the
+      // tile's eight 32-column groups.  The residual box of group i lands in ring buffer i & 1; it is requested when
+      // buffer i & 1 was last released, i.e. one whole group of work before it is needed.
+      constexpr int GPT = T::BN / 64;  // groups per tile and warp
+      uint64_t* my_bar = res_bar + (warp - 4) * 2;
+      int is_tile = cluster_id, is_g = 0;  // issue cursor
+      uint32_t n_issued = 0, n_done = 0;
+      auto issue = [&]() {
+        if (is_tile < num_tiles) {
+          if (lane == 0) {
+            const int b = n_issued & 1;
+            const int row0 = (is_tile / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
+            const int col0 = (is_tile % num_n) * T::BN + (half + 2 * is_g) * 32;
+            fence_proxy_async_smem();  // the buffer was last touched by generic-proxy loads/stores of this warp
+            mbar_expect_tx(&my_bar[b], 32 * 128);
+            tma_load_2d(reinterpret_cast<void*>(smem + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES +
+                                                (warp - 4) * T::STG_BYTES_PER_WARP + b * 4096),
+                        &tmR, &my_bar[b], col0, row0);
+          }
+          ++n_issued;
+          if (++is_g == GPT) { is_g = 0; is_tile += n_clusters; }
+        }
+      };
+      issue();
+      issue();
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_phase = (t >> 1) & 1;
+        const int m_base = (tile / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
+        const int n0 = (tile % num_n) * T::BN;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T::BN);
+#pragma unroll 1
+        for (int gi = 0; gi < GPT; ++gi) {
+          const int g = half + 2 * gi;
+          const int b = n_done & 1;
+          mbar_wait(&my_bar[b], (n_done >> 1) & 1);
+          gemm_epilogue_group_restma(ep, stg_u + (uint32_t)(b * 4096), taddr + (uint32_t)(g * 32), m_base, n0 + g * 32,
+                                     M, lane);
+          ++n_done;
+          if (gi == GPT - 1) {  // last TMEM read of this tile is done: hand the accumulator back before refilling
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+          }
+          issue();
+        }
+      }
+    } else {
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_phase = (t >> 1) & 1;
+        const int m_base = (tile / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
+        const int n0 = (tile % num_n) * T::BN;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T::BN);
+        gemm_epilogue_tile<T::BN>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+      }
     }
   }
 
@@ -213,8 +273,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 int gemm2_init(const char** err) {
-  if (cudaFuncSetAttribute(gemm2_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2::SMEM_BYTES) !=
-      cudaSuccess) {
+  if (cudaFuncSetAttribute(gemm2_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           G2T<false>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm2_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           G2T<true>::SMEM_BYTES) != cudaSuccess) {
     *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the 2-CTA GEMM kernel";
     return 1;
   }
@@ -224,7 +286,10 @@ int gemm2_init(const char** err) {
 int gemm2_launch(const GemmOp* op, cudaStream_t stream) {
   Gemm2Args a;
   a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K;
-  gemm2_tcgen05_kernel<<<op->grid, 384, G2::SMEM_BYTES, stream>>>(op->ta, op->tb, a);
+  if (op->res_tma)
+    gemm2_tcgen05_kernel<true><<<op->grid, 384, G2T<true>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->tr, a);
+  else
+    gemm2_tcgen05_kernel<false><<<op->grid, 384, G2T<false>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->ta, a);
   return (int)cudaGetLastError();
 }
 

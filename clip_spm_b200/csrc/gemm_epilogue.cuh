@@ -180,4 +180,48 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint3
   }
 }
 
+// Variant for fp32 output + fp32 residual (identity rows), used by the 2-CTA kernel: the residual box of this warp's
+// 32 rows x 32 columns has been TMA-loaded (SWIZZLE_128B: 16-byte unit u of row r sits at unit u ^ (r & 7), the same
+// permutation the staging tile uses) into `buf_u`; the thread owning accumulator row `lane` adds its row in place,
+// then the tile is read back row-contiguously and stored.  No residual registers, and the load was issued one column
+// group earlier, so its HBM latency is hidden behind the previous group's work.
+__device__ __forceinline__ void gemm_epilogue_group_restma(const GemmEpilogue& ep, uint32_t buf_u, uint32_t taddr_cols,
+                                                           int m_base, int col0, int M, int lane) {
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(taddr_cols, r);
+  tmem_ld_wait();
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (ep.bias != nullptr) {
+    const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(bp + j);
+      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  const uint32_t srow = buf_u + (uint32_t)(lane * 128);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t a = srow + (uint32_t)((j ^ (lane & 7)) * 16);
+    uint4 u = ld_shared_v4(a);
+    u.x = __float_as_uint(__uint_as_float(u.x) + v[4 * j]);
+    u.y = __float_as_uint(__uint_as_float(u.y) + v[4 * j + 1]);
+    u.z = __float_as_uint(__uint_as_float(u.z) + v[4 * j + 2]);
+    u.w = __float_as_uint(__uint_as_float(u.w) + v[4 * j + 3]);
+    st_shared_v4(a, u);
+  }
+  __syncwarp();
+  const int rr = lane >> 3, uu = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = i * 4 + rr;
+    const uint4 d = ld_shared_v4(buf_u + (uint32_t)(rl * 128 + ((uu ^ (rl & 7)) * 16)));
+    if (m_base + rl < M)
+      *reinterpret_cast<uint4*>(reinterpret_cast<float*>(ep.out) + (long long)(m_base + rl) * ep.ldo + col0 + uu * 4) = d;
+  }
+  __syncwarp();  // every lane has read the buffer: it may be refilled
+}
+
 }  // namespace spm

@@ -304,6 +304,14 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   }
   if (make_operand_map(&op->ta, kind, A, lda, M, K, 128, err)) return 1;
   if (make_operand_map(&op->tb, kind, B, ldb, N, K, op->two_cta ? 128 : op->bn, err)) return 1;
+  static const bool allow_res_tma = [] { const char* e = getenv("SPM_GEMM_RES_TMA"); return e == nullptr || atoi(e) != 0; }();
+  op->res_tma = 0;
+  if (allow_res_tma && op->two_cta && ep.residual != nullptr && !ep.out_bf16 && ep.act == ACT_NONE &&
+      !ep.relu_after_residual && ep.res_row_mod == 0 && ep.out_row_group == 0 &&
+      (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0 && (ep.ldr & 3) == 0) {
+    if (make_operand_map(&op->tr, GEMM_TF32, ep.residual, ep.ldr, M, N, 32, err)) return 1;
+    op->res_tma = 1;
+  }
   return 0;
 }
 

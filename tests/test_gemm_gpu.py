@@ -113,3 +113,28 @@ def test_gemm_two_cta_path_with_epilogues():
     r2 = a.float() @ b.float().t() + bias
     r2 = r2 * torch.sigmoid(1.702 * r2)
     assert (out.float() - r2).abs().max().item() < 2e-2 * r2.abs().max().item()
+
+
+@pytest.mark.parametrize("M,K", [(19999, 768), (25216, 3072), (18944, 64)])
+def test_gemm_two_cta_tma_residual(M, K):
+    """2-CTA kernel with the TMA-prefetched residual ring: separate (not in-place) residual with a row stride larger
+    than N, no bias, ragged and exact M, short and long reductions; each output element must get its own residual."""
+    from clip_spm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    N = 768
+    a = torch.randn(M, K, generator=g).cuda().bfloat16()
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    res_full = torch.randn(M, 1024, generator=g).cuda()
+    res = res_full[:, 128:128 + N]                       # 16-byte aligned view, row stride 1024
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(a, b, residual=res, out=out)
+    ref = res + a.float() @ b.float().t()
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+    # a residual that is an exact function of (row, col) makes any misplaced box visible even where the GEMM term is tiny
+    rows = torch.arange(M, device="cuda", dtype=torch.float32)[:, None]
+    cols = torch.arange(N, device="cuda", dtype=torch.float32)[None, :]
+    res2 = (rows * 1024 + cols).contiguous()
+    z = torch.zeros(M, K, device="cuda", dtype=torch.bfloat16)
+    out2 = ops.gemm(z, b, residual=res2, out=torch.empty(M, N, device="cuda"))
+    assert torch.equal(out2, res2)
