@@ -32,8 +32,9 @@ VIT_GFLOP_PER_FRAME = 35.127                          # BASELINE.md section 3 (f
 # executed FLOPs): 35.127 - (0.2324 + 0.9296 + 0.9296) * 196/197
 VIT_GFLOP_PER_FRAME_EXECUTED = 33.046
 # DRAM bytes per launch of the dominant kernel (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean of
-# the four encoder GEMM flavours at 240 frames; profiles/r01_ncu_gemm_2cta_vs_1cta.txt).  Algorithmic mean: 403 MB.
-GEMM_DRAM_BYTES_PER_LAUNCH_NCU = 356.3e6
+# the four encoder GEMM flavours at 512-frame chunks, M = 100864: qkv 571 MB, out-proj 721, fc 728, proj 1239;
+# profiles/r01_ncu_full_gemm2_chunk512_summary.txt).  Algorithmic mean (operands + residual + output once): 856 MB.
+GEMM_DRAM_BYTES_PER_LAUNCH_NCU = 815e6
 WORKLOAD = "CLIP-SPM ViT-B/16 5-way 5-shot Kinetics-shape eval (S=25,Q=5,T=8: 240 frames@224 per episode), bf16"
 
 
