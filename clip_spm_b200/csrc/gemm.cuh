@@ -49,6 +49,10 @@ struct GemmOp {
   // channel block kb % conv_cblocks of tap kb / conv_cblocks, i.e. the same matrix at the constant row offset
   // (tap/3 - 1) * conv_w2 + (tap%3 - 1) -- only the TMA coordinate changes, no im2col is materialised (0 = plain GEMM)
   int conv_w2 = 0, conv_cblocks = 0;
+  // C == 32 variant ("pixel pairs"): A is described as [rows-1, 64] with a row stride of 32 elements, so that virtual row
+  // p holds the channels of pixels p and p+1 and every TMA box is a full 128-byte line; the 9 taps become 6 k-blocks
+  // (dy, {x-1, x}) and (dy, {x+1, -}) instead of 9 half-empty ones
+  int conv_pair = 0;
   int two_cta = 0;  // 1: launched as 2-CTA clusters (gemm2_tcgen05.cu), 256x256 tile per CTA pair
   // 2-CTA kernel, fp32 out + fp32 residual with identity row mapping: the epilogue warps prefetch the residual tile
   // by TMA (`tr`: fp32 [M, N], 32 x 32 boxes, SWIZZLE_128B) one column group ahead instead of loading it into registers
@@ -65,6 +69,8 @@ int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err);
 // padded pixels), B = folded weights [Cout, 9 * cpad] with column tap*cpad + c (cpad = C rounded up to 64)
 int gemm_plan_conv3x3(GemmOp* op, const void* A, int C, int rows, int W2, const void* B, int Cout, const GemmEpilogue& ep,
                       int num_sms, const char** err);
+// true if the driver accepts a tensor map whose row stride is smaller than its row extent (needed by conv_pair)
+bool gemm_conv_pair_supported();
 // one-time: opt into large dynamic shared memory for every instantiation
 int gemm_init(const char** err);
 // 2-CTA kernel (gemm2_tcgen05.cu)

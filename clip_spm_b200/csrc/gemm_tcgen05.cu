@@ -27,6 +27,7 @@ struct GemmArgs {
   GemmEpilogue ep;
   int M, N, K;
   int conv_w2, conv_cblocks;  // implicit 3x3 convolution (see GemmOp), 0 = plain GEMM
+  int conv_pair;
 };
 
 template <int BN, int KIND>
@@ -117,7 +118,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint8_t* sa = smem + stage * T::STAGE_BYTES;
           uint8_t* sb = sa + T::A_BYTES;
           mbar_expect_tx(&full_bar[stage], T::STAGE_BYTES);
-          if (conv && args.conv_cblocks > 0) {
+          if (conv && args.conv_pair) {
+            const int roff = ((kb >> 1) - 1) * args.conv_w2 + ((kb & 1) ? 1 : -1);
+            tma_load_2d(sa, &tmA, &full_bar[stage], 0, m0 + roff);
+          } else if (conv && args.conv_cblocks > 0) {
             const int tap = kb / args.conv_cblocks, cb = kb - tap * args.conv_cblocks;
             const int roff = (tap / 3 - 1) * args.conv_w2 + (tap % 3 - 1);  // rows outside the matrix read as zeros
             tma_load_2d(sa, &tmA, &full_bar[stage], cb * T::BK, m0 + roff);
@@ -238,6 +242,24 @@ static int make_operand_map(CUtensorMap* map, int kind, const void* ptr, long lo
   return 0;
 }
 
+bool gemm_conv_pair_supported() {
+  static const int ok = [] {
+    if (const char* e = getenv("SPM_CONV_PAIR")) if (atoi(e) == 0) return 0;
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) return 0;
+    alignas(64) static unsigned char dummy[64];
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {64, 1000};
+    cuuint64_t gstride[1] = {64};  // 32 bf16: consecutive rows overlap by half
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dummy, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 1 : 0;
+  }();
+  return ok != 0;
+}
+
 int gemm_init(const char** err) {
 #define SPM_SET_SMEM(BN, KIND)                                                                               \
   if (cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
@@ -318,27 +340,36 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
 int gemm_plan_conv3x3(GemmOp* op, const void* A, int C, int rows, int W2, const void* B, int Cout, const GemmEpilogue& ep,
                       int num_sms, const char** err) {
   if (C % 8 != 0 || Cout % 32 != 0) { *err = "conv3x3: C must be a multiple of 8 and Cout of 32"; return 1; }
+  const bool pair = C == 32 && gemm_conv_pair_supported();
   const int cpad = (C + 63) / 64 * 64;
-  // plan as a [rows, 9*cpad] x [Cout, 9*cpad] GEMM (fictitious A stride), then describe the real A: [rows, C]
-  if (gemm_plan(op, GEMM_BF16, A, 9LL * cpad, B, 9LL * cpad, rows, Cout, 9 * cpad, ep, num_sms, err)) return 1;
-  // (columns >= C of a box read as zeros, rows outside [0, rows) too)
-  if (make_operand_map(&op->ta, GEMM_BF16, A, C, rows, C, 128, err)) return 1;
+  const int Kv = pair ? 6 * 64 : 9 * cpad;  // k extent of the folded weight matrix
+  // plan as a [rows, Kv] x [Cout, Kv] GEMM (fictitious A stride), then describe the real A
+  if (gemm_plan(op, GEMM_BF16, A, Kv, B, Kv, rows, Cout, Kv, ep, num_sms, err)) return 1;
+  if (pair) {
+    // virtual row p = channels of pixels p and p+1 (row stride 32 elements, extent 64); the last pixel has no successor
+    if (make_operand_map(&op->ta, GEMM_BF16, A, C, rows - 1, 64, 128, err)) return 1;
+  } else {
+    // (columns >= C of a box read as zeros, rows outside [0, rows) too)
+    if (make_operand_map(&op->ta, GEMM_BF16, A, C, rows, C, 128, err)) return 1;
+  }
   if (op->two_cta) {  // the pair kernel does not know about taps: fall back to the 1-CTA kernel
     op->two_cta = 0;
+    op->res_tma = 0;
     op->bn = (Cout % 256 == 0) ? 256 : 128;
     const long long tiles = (long long)((rows + 127) / 128) * ((Cout + op->bn - 1) / op->bn);
     op->grid = (int)(tiles < num_sms ? tiles : num_sms);
-    if (make_operand_map(&op->tb, GEMM_BF16, B, 9LL * cpad, Cout, 9 * cpad, op->bn, err)) return 1;
+    if (make_operand_map(&op->tb, GEMM_BF16, B, Kv, Cout, Kv, op->bn, err)) return 1;
   }
   op->conv_w2 = W2;
-  op->conv_cblocks = cpad / 64;
+  op->conv_cblocks = pair ? 1 : cpad / 64;
+  op->conv_pair = pair ? 1 : 0;
   return 0;
 }
 
 int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
   GemmArgs a;
   a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K;
-  a.conv_w2 = op->conv_w2; a.conv_cblocks = op->conv_cblocks;
+  a.conv_w2 = op->conv_w2; a.conv_cblocks = op->conv_cblocks; a.conv_pair = op->conv_pair;
   int slot = -1;
   const bool prof = profile_gemm_begin(stream, (op->kind & 1) * 2 + (op->bn == 256 ? 1 : 0),
                                        2.0 * (double)op->M * (double)op->N * (double)op->K, &slot);

@@ -51,13 +51,20 @@ constexpr long long COL_PER_FRAME = 114LL * 114 * 32;      // stem conv1 im2col 
 __global__ void fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b,
                                  const float* __restrict__ mean, const float* __restrict__ var, int Cout, int Cin,
                                  int kh, int kw, int cpad, int Kpad, __nv_bfloat16* __restrict__ wout,
-                                 float* __restrict__ bias) {
+                                 float* __restrict__ bias, int pair) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Cout * Kpad) return;
   const int o = (int)(i / Kpad), k = (int)(i % Kpad);
   const float scale = g[o] * rsqrtf(var[o] + 1e-5f);
   float v = 0.f;
-  const int c = k % cpad, tap = k / cpad;
+  int c = k % cpad, tap = k / cpad;
+  if (pair) {
+    // pixel-pair layout of gemm_plan_conv3x3 (Cin == 32): k-block kb = k / 64 holds (dy = kb / 2; kb even: taps x-1 | x,
+    // kb odd: tap x+1 | zeros), 32 channels per tap
+    const int kb = k >> 6, w64 = k & 63, hf = w64 >> 5, kx = (kb & 1) ? (hf == 0 ? 2 : -1) : hf;
+    c = w64 & 31;
+    tap = kx < 0 ? kh * kw : (kb >> 1) * kw + kx;
+  }
   if (tap < kh * kw && c < Cin) {
     const int ky = tap / kw, kx = tap % kw;
     v = w[(((long long)o * Cin + c) * kh + ky) * kw + kx] * scale;
@@ -240,12 +247,13 @@ int load_conv(Rn50* r, cudaStream_t st, const WeightGetter& get, const std::stri
   SPM_TRY(get(bn + "running_var", cout, &var));
   c->cout = cout; c->cin = cin; c->ksz = ksz; c->implicit3x3 = implicit3x3;
   const int cpad = implicit3x3 ? (cin + 63) / 64 * 64 : cin;
-  c->kpad = implicit3x3 ? 9 * cpad : (cin * ksz * ksz + 31) / 32 * 32;
+  const int pair = (implicit3x3 && cin == 32 && gemm_conv_pair_supported()) ? 1 : 0;
+  c->kpad = pair ? 6 * 64 : implicit3x3 ? 9 * cpad : (cin * ksz * ksz + 31) / 32 * 32;
   SPM_TRY(ralloc(r, &c->w, (long long)cout * c->kpad));
   SPM_TRY(ralloc(r, &c->bias, cout));
   const long long n = (long long)cout * c->kpad;
   fold_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, b, mean, var, cout, cin, ksz, ksz, cpad, c->kpad,
-                                                                 c->w, c->bias);
+                                                                 c->w, c->bias, pair);
   RN_LAUNCH_CHECK();
   return 0;
 }
