@@ -53,6 +53,7 @@ struct GemmOp {
   // p holds the channels of pixels p and p+1 and every TMA box is a full 128-byte line; the 9 taps become 6 k-blocks
   // (dy, {x-1, x}) and (dy, {x+1, -}) instead of 9 half-empty ones
   int conv_pair = 0;
+  int reverse = 0;  // visit the output tiles in descending order (same results; L2 reuse between consecutive kernels)
   int two_cta = 0;  // 1: launched as 2-CTA clusters (gemm2_tcgen05.cu), 256x256 tile per CTA pair
   // 2-CTA kernel, fp32 out + fp32 residual with identity row mapping: the epilogue warps prefetch the residual tile
   // by TMA (`tr`: fp32 [M, N], 32 x 32 boxes, SWIZZLE_128B) one column group ahead instead of loading it into registers

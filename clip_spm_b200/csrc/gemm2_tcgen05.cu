@@ -85,6 +85,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* local_bar) {
 struct Gemm2Args {
   GemmEpilogue ep;
   int M, N, K;
+  int reverse;
 };
 
 template <bool RES>
@@ -140,14 +141,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int pf_tile = cluster_id, pf_kb = 0;
       auto prefetch_next = [&]() {
         if (pf_tile < num_tiles) {
-          tma_prefetch_l2_2d(&tmA, pf_kb * T::BK, (pf_tile / num_n) * (2 * T::BM) + (int)rank * T::BM);
+          tma_prefetch_l2_2d(&tmA, pf_kb * T::BK,
+                             ((args.reverse ? num_tiles - 1 - pf_tile : pf_tile) / num_n) * (2 * T::BM) + (int)rank * T::BM);
           if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += n_clusters; }
         }
       };
       for (int i = 0; i < GEMM_L2_PREFETCH_KB; ++i) prefetch_next();
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
-        const int m0 = (tile / num_n) * (2 * T::BM) + (int)rank * T::BM;
-        const int n0 = (tile % num_n) * T::BN + (int)rank * (T::BN / 2);
+        const int rt = args.reverse ? num_tiles - 1 - tile : tile;
+        const int m0 = (rt / num_n) * (2 * T::BM) + (int)rank * T::BM;
+        const int n0 = (rt % num_n) * T::BN + (int)rank * (T::BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           prefetch_next();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -209,8 +212,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (is_tile < num_tiles) {
           if (lane == 0) {
             const int b = n_issued & 1;
-            const int row0 = (is_tile / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
-            const int col0 = (is_tile % num_n) * T::BN + (half + 2 * is_g) * 32;
+            const int rt = args.reverse ? num_tiles - 1 - is_tile : is_tile;
+            const int row0 = (rt / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
+            const int col0 = (rt % num_n) * T::BN + (half + 2 * is_g) * 32;
             fence_proxy_async_smem();  // the buffer was last touched by generic-proxy loads/stores of this warp
             mbar_expect_tx(&my_bar[b], 32 * 128);
             tma_load_2d(reinterpret_cast<void*>(smem + T::STAGES * T::STAGE_BYTES + T::BAR_BYTES +
@@ -226,8 +230,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++t) {
         const int acc = t & 1;
         const uint32_t acc_phase = (t >> 1) & 1;
-        const int m_base = (tile / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
-        const int n0 = (tile % num_n) * T::BN;
+        const int rt = args.reverse ? num_tiles - 1 - tile : tile;
+        const int m_base = (rt / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
+        const int n0 = (rt % num_n) * T::BN;
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T::BN);
@@ -251,8 +256,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++t) {
         const int acc = t & 1;
         const uint32_t acc_phase = (t >> 1) & 1;
-        const int m_base = (tile / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
-        const int n0 = (tile % num_n) * T::BN;
+        const int rt = args.reverse ? num_tiles - 1 - tile : tile;
+        const int m_base = (rt / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
+        const int n0 = (rt % num_n) * T::BN;
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T::BN);
@@ -285,7 +291,7 @@ int gemm2_init(const char** err) {
 
 int gemm2_launch(const GemmOp* op, cudaStream_t stream) {
   Gemm2Args a;
-  a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K;
+  a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K; a.reverse = op->reverse;
   if (op->res_tma)
     gemm2_tcgen05_kernel<true><<<op->grid, 384, G2T<true>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->tr, a);
   else

@@ -28,6 +28,7 @@ struct GemmArgs {
   int M, N, K;
   int conv_w2, conv_cblocks;  // implicit 3x3 convolution (see GemmOp), 0 = plain GEMM
   int conv_pair;
+  int reverse;
 };
 
 template <int BN, int KIND>
@@ -102,7 +103,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int pf_tile = blockIdx.x, pf_kb = 0;
       auto prefetch_next = [&]() {
         if (pf_tile < num_tiles) {
-          tma_prefetch_l2_2d(&tmA, pf_kb * T::BK, (pf_tile / num_n) * T::BM);
+          tma_prefetch_l2_2d(&tmA, pf_kb * T::BK, ((args.reverse ? num_tiles - 1 - pf_tile : pf_tile) / num_n) * T::BM);
           if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += gridDim.x; }
         }
       };
@@ -110,8 +111,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (!conv)
         for (int i = 0; i < GEMM_L2_PREFETCH_KB; ++i) prefetch_next();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * T::BM;
-        const int n0 = (tile % num_n) * BN;
+        const int rt = args.reverse ? num_tiles - 1 - tile : tile;
+        const int m0 = (rt / num_n) * T::BM;
+        const int n0 = (rt % num_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!conv) prefetch_next();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -179,8 +181,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
-      const int m_base = (tile / num_n) * T::BM + q * 32;
-      const int n0 = (tile % num_n) * BN;
+      const int rt = args.reverse ? num_tiles - 1 - tile : tile;
+      const int m_base = (rt / num_n) * T::BM + q * 32;
+      const int n0 = (rt % num_n) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -369,7 +372,7 @@ int gemm_plan_conv3x3(GemmOp* op, const void* A, int C, int rows, int W2, const 
 int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
   GemmArgs a;
   a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K;
-  a.conv_w2 = op->conv_w2; a.conv_cblocks = op->conv_cblocks; a.conv_pair = op->conv_pair;
+  a.conv_w2 = op->conv_w2; a.conv_cblocks = op->conv_cblocks; a.conv_pair = op->conv_pair; a.reverse = op->reverse;
   int slot = -1;
   const bool prof = profile_gemm_begin(stream, (op->kind & 1) * 2 + (op->bn == 256 ? 1 : 0),
                                        2.0 * (double)op->M * (double)op->N * (double)op->K, &slot);

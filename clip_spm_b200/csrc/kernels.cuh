@@ -23,14 +23,17 @@ int k_patch_im2col(cudaStream_t st, const float* images, __nv_bfloat16* patches,
 //   Writes fp32 (out_f32) and/or bf16 (out_bf16), contiguous rows of C (row stride out_stride).
 int k_layernorm(cudaStream_t st, const float* in, long long in_stride, int rows, int C, const float* gamma,
                 const float* beta, const float* cls_row, int cls_period, float* out_f32, __nv_bfloat16* out_bf16,
-                long long out_stride);
+                long long out_stride, int reverse = 0);
 // softmax(Q K^T / 8) V for 12 heads x 64 dims over 197 tokens per frame (clip_fsar.py:626,638), bf16 tensor cores.
 //   qkv [F*197, 2304] bf16 (q | k | v, head h at columns h*64) -> out [F*197, 768] bf16
 int k_vit_attention(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames);
 int k_vit_attention_init();
 // same contract on tcgen05/TMEM (vit_attention_tc.cu): S and O accumulate in tensor memory, P feeds the second
 // MMA straight from TMEM.  `sms` = number of SMs (persistent grid).
-int k_vit_attention_tc(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, int sms);
+// reverse != 0: items / rows / tiles are visited in descending order (same results; used to alternate the sweep
+// direction of consecutive kernels so that each one starts on the rows its producer wrote last, still in L2)
+int k_vit_attention_tc(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, int sms,
+                       int reverse = 0);
 int k_vit_attention_tc_init();
 
 // fp32 parity-mode kernels (sgemm_f32.cu)

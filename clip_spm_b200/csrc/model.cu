@@ -108,6 +108,7 @@ struct spm_handle {
   int D = 512, HT = 768, HV = 256;
   int sms = 148;
   int frame_chunk = 512;
+  int alt_dir = 1;  // SPM_ALT_DIR=0: every kernel sweeps its rows in ascending order
   bool prune_last = true;  // SPM_PRUNE_LAST=0 runs the last block on all tokens (same result, more work)
   bool attn_mma = false;  // SPM_ATTN=mma selects the mma.sync attention kernel instead of the tcgen05 one
   bool weights_loaded = false, text_set = false;
@@ -484,16 +485,26 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
     SPM_GEMM_RUN(fin32);
     return 0;
   }
-  SPM_GEMM_RUN(pl->patch);
-  SPM_KERNEL(k_layernorm(st, h->x, C, M, C, v.ln_pre_g, v.ln_pre_b, v.cls_pos, VIT_L, h->x, nullptr, C));
+  // Consecutive kernels sweep their rows in OPPOSITE directions (h->alt_dir): a 512-frame chunk's tensors (155-620 MB)
+  // do not fit the 126 MB L2, but the rows a kernel wrote last are still there when the next kernel starts on them.
+  int dir = 0;
+  auto next_dir = [&]() { const int d = dir; dir ^= h->alt_dir; return d; };
+#define SPM_GEMM_RUN_DIR(op)            \
+  do {                                  \
+    GemmOp _op = (op);                  \
+    _op.reverse = next_dir();           \
+    SPM_GEMM_RUN(_op);                  \
+  } while (0)
+  SPM_GEMM_RUN_DIR(pl->patch);
+  SPM_KERNEL(k_layernorm(st, h->x, C, M, C, v.ln_pre_g, v.ln_pre_b, v.cls_pos, VIT_L, h->x, nullptr, C, next_dir()));
   for (int i = 0; i < VIT_LAYERS; ++i) {
     const VitLayerW& l = v.layer[i];
-    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln1_g, l.ln1_b, nullptr, 0, nullptr, h->xn, C));
-    SPM_GEMM_RUN(pl->qkv[i]);
+    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln1_g, l.ln1_b, nullptr, 0, nullptr, h->xn, C, next_dir()));
+    SPM_GEMM_RUN_DIR(pl->qkv[i]);
     if (h->attn_mma)
       SPM_KERNEL(k_vit_attention(st, h->qkv, h->attn, F));
     else
-      SPM_KERNEL(k_vit_attention_tc(st, h->qkv, h->attn, F, h->sms));
+      SPM_KERNEL(k_vit_attention_tc(st, h->qkv, h->attn, F, h->sms, next_dir()));
     if (i == VIT_LAYERS - 1 && h->prune_last) {
       // only x[:, 0, :] is read after the last block: run its out-proj / MLP on the F class-token rows
       SPM_GEMM_RUN(pl->outp_cls);
@@ -506,11 +517,12 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
       SPM_GEMM_RUN(fin);
       return 0;
     }
-    SPM_GEMM_RUN(pl->outp[i]);
-    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xn, C));
-    SPM_GEMM_RUN(pl->fc[i]);
-    SPM_GEMM_RUN(pl->proj[i]);
+    SPM_GEMM_RUN_DIR(pl->outp[i]);
+    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xn, C, next_dir()));
+    SPM_GEMM_RUN_DIR(pl->fc[i]);
+    SPM_GEMM_RUN_DIR(pl->proj[i]);
   }
+#undef SPM_GEMM_RUN_DIR
   SPM_KERNEL(k_layernorm(st, h->x, (long long)VIT_L * C, F, C, v.ln_post_g, v.ln_post_b, nullptr, 0, nullptr, h->cls, C));
   GemmOp fin = pl->fin;
   fin.ep.out = feats_out;
@@ -941,6 +953,7 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   SPM_TRY(device_sm_count(&h->sms));
   if (const char* e = getenv("SPM_FRAME_CHUNK")) h->frame_chunk = std::max(1, atoi(e));
   if (const char* e = getenv("SPM_ENC_STREAMS")) h->enc_streams = atoi(e) >= 2 ? 2 : 1;
+  if (const char* e = getenv("SPM_ALT_DIR")) h->alt_dir = atoi(e) != 0 ? 1 : 0;
   const char* err = "";
   if (gemm_init(&err)) { set_error(err); return 1; }
   SPM_KERNEL(k_vit_attention_init());

@@ -43,7 +43,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 
 __global__ void __launch_bounds__(384, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                        __nv_bfloat16* __restrict__ out, int n_items) {
+                        __nv_bfloat16* __restrict__ out, int n_items, int reverse) {
   extern __shared__ uint8_t smem_raw_at[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_at) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
@@ -87,7 +87,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int stage = it & 1;
         const uint32_t ph = (it >> 1) & 1;
-        const int frame = item / HEADS, head = item % HEADS;
+        const int ritem = reverse ? n_items - 1 - item : item;  // descending order: see vit_run (L2 reuse)
+        const int frame = ritem / HEADS, head = ritem % HEADS;
         uint8_t* s = smem + stage * STAGE_BYTES;
         mbar_wait(&kv_empty[stage], ph ^ 1u);
         mbar_expect_tx(&kv_full[stage], STAGE_BYTES);
@@ -154,7 +155,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t par = (uint32_t)it & 1u;
-      const int frame = item / HEADS, head = item % HEADS;
+      const int ritem = reverse ? n_items - 1 - item : item;
+      const int frame = ritem / HEADS, head = ritem % HEADS;
       mbar_wait(&s_full[b], par);
       tc_fence_after_sync();
       float inv_l = 0.f;
@@ -313,7 +315,8 @@ int k_vit_attention_tc_init() {
   return (int)cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 }
 
-int k_vit_attention_tc(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, int sms) {
+int k_vit_attention_tc(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, int sms,
+                       int reverse) {
   if (n_frames <= 0) return 0;
   static std::map<std::tuple<const void*, int>, AttnMaps> cache;  // maps depend on (buffer, frame count) only
   auto key = std::make_tuple((const void*)qkv, n_frames);
@@ -327,7 +330,7 @@ int k_vit_attention_tc(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16*
   }
   const int n_items = n_frames * HEADS;
   const int grid = n_items < sms ? n_items : sms;
-  vit_attention_tc_kernel<<<grid, 384, SMEM_BYTES, st>>>(it->second.q, it->second.kv, out, n_items);
+  vit_attention_tc_kernel<<<grid, 384, SMEM_BYTES, st>>>(it->second.q, it->second.kv, out, n_items, reverse);
   cudaError_t e = cudaGetLastError();
   count_launch();
   return (int)e;

@@ -113,11 +113,12 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ in, long long in_stride, int rows, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ cls_row, int cls_period,
-                 float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long long out_stride) {
+                 float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long long out_stride, int reverse) {
   constexpr int C = NV * 128;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  if (reverse) row = rows - 1 - row;
   const float* src = in + (long long)row * in_stride;
   if (cls_period > 0 && (row % cls_period) == 0) src = cls_row;
   float4 v[NV];
@@ -161,12 +162,12 @@ layernorm_kernel(const float* __restrict__ in, long long in_stride, int rows, co
 
 int k_layernorm(cudaStream_t st, const float* in, long long in_stride, int rows, int C, const float* gamma,
                 const float* beta, const float* cls_row, int cls_period, float* out_f32, __nv_bfloat16* out_bf16,
-                long long out_stride) {
+                long long out_stride, int reverse) {
   const int blocks = (rows + 7) / 8;
   if (rows <= 0) return 0;
 #define SPM_LN(NV)                                                                                             \
   layernorm_kernel<NV><<<blocks, 256, 0, st>>>(in, in_stride, rows, gamma, beta, cls_row, cls_period, out_f32, \
-                                               out_bf16, out_stride)
+                                               out_bf16, out_stride, reverse)
   switch (C) {
     case 512: SPM_LN(4); break;
     case 768: SPM_LN(6); break;
