@@ -53,6 +53,8 @@ SIGNATURES = {
     "spm_eval_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),
     "spm_otam_distance": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                   c_float, c_float, c_void_p]),
+    "spm_otam_distance_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                           c_float, c_void_p, c_void_p, c_void_p]),
     "spm_vit_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "spm_gemm": (c_int, [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_int,
                          c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int]),

@@ -47,12 +47,46 @@ def gemm(a, b, bias=None, act="none", slope=0.0, residual=None, res_row_mod=0, r
     return out
 
 
+class _OtamDistance(torch.autograd.Function):
+    """otam_distance with gradients: forward = spm_otam_distance, backward = spm_otam_distance_backward."""
+
+    @staticmethod
+    def forward(ctx, support, target, single_direct, alpha):
+        lib = _lib.load()
+        P, W, T, D = support.shape
+        Q = target.shape[1]
+        out = torch.zeros(P, Q, W, device=support.device)
+        _lib.check(lib.spm_otam_distance(_stream(), P, W, Q, T, D, _ptr(support), _ptr(target), int(single_direct),
+                                         float(alpha), 0.0, _ptr(out)))
+        ctx.save_for_backward(support, target)
+        ctx.cfg = (bool(single_direct), float(alpha))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        support, target = ctx.saved_tensors
+        single_direct, alpha = ctx.cfg
+        P, W, T, D = support.shape
+        Q = target.shape[1]
+        go = grad_out.contiguous().float()
+        gs, gt = torch.empty_like(support), torch.empty_like(target)
+        _lib.check(lib.spm_otam_distance_backward(_stream(), P, W, Q, T, D, _ptr(support), _ptr(target),
+                                                  int(single_direct), alpha, _ptr(go), _ptr(gs), _ptr(gt)))
+        return gs, gt, None, None
+
+
 def otam_distance(support, target, single_direct=False, alpha=1.0, beta=0.0, out=None):
     """cos_sim + (bi)directional OTAM (models/model_clipspm.py:348-362): support [P,W,T,D], target [P,Q,T,D] fp32
-    -> [P,Q,W]."""
+    -> [P,Q,W].  Differentiable: when an input requires grad the call goes through an autograd Function whose
+    backward is the library's own kernel (the accumulate form `out = beta*out + ...` is inference-only)."""
     lib = _lib.load()
     _need_cuda(support, target, out)
     support, target = support.contiguous().float(), target.contiguous().float()
+    if torch.is_grad_enabled() and (support.requires_grad or target.requires_grad):
+        if out is not None or beta != 0.0:
+            raise RuntimeError("otam_distance: `out` / `beta` cannot be combined with autograd")
+        return _OtamDistance.apply(support, target, bool(single_direct), float(alpha))
     P, W, T, D = support.shape
     Q = target.shape[1]
     if out is None:

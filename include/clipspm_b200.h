@@ -116,6 +116,13 @@ int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const floa
 int spm_otam_distance(void* stream, int n_pairs, int W, int Q, int T, int D, const float* support,
                       const float* target, int single_direct, float alpha, float beta, float* out);
 
+/* Backward of spm_otam_distance (first piece of the training step, run/main_run.py:245-254): given
+ * grad_out [P,Q,W] = d loss / d out, writes d loss / d support [P,W,T,D] and d loss / d target [P,Q,T,D]
+ * (overwritten, not accumulated) -- what autograd derives through otam_distance / cos_sim / OTAM_cum_dist_v2. */
+int spm_otam_distance_backward(void* stream, int n_pairs, int W, int Q, int T, int D, const float* support,
+                               const float* target, int single_direct, float alpha, const float* grad_out,
+                               float* grad_support, float* grad_target);
+
 /* Frame-encoder self-attention stage (models/clip_fsar.py:626,638): qkv [F*197, 2304] bf16 (q | k | v, head h at
  * columns h*64 of each third) -> out [F*197, 768] bf16.  use_mma_sync = 0: tcgen05/TMEM kernel (product path),
  * 1: the mma.sync kernel kept as a cross-check. */
