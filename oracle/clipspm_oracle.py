@@ -580,3 +580,14 @@ def class_text_features(w, tokens_by_template):
     """models/model_clipspm.py:52-70: tokens_by_template [n_templates, n_classes, 77] -> mean over templates of
     encode_text -> [n_classes, embed_dim] (no normalisation)."""
     return torch.stack([encode_text(w, t) for t in tokens_by_template]).mean(dim=0)
+
+
+def make_otam_grad_inputs(W, Q, T, D, seed):
+    """seeded inputs of the metric-tail gradient golden (pin_against_reference.py otam_grad): support [W,T,D],
+    target [Q,T,D] with a shared component (cosine similarities well above zero) and an upstream gradient [Q,W]"""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(1, 1, D, generator=g)
+    sup = torch.randn(W, T, D, generator=g) + 0.7 * base
+    tgt = torch.randn(Q, T, D, generator=g) + 0.7 * base
+    go = torch.randn(Q, W, generator=g)
+    return sup, tgt, go

@@ -203,11 +203,34 @@ def run_text_case(m):
                         text_features=ref.float().numpy())
 
 
+def run_otam_grad_case(m):
+    """Gradients of the metric tail: autograd through the REFERENCE's own CNN.otam_distance (model_clipspm.py:348-362:
+    cos_sim + OTAM_cum_dist_v2 in both directions) against autograd through the oracle restatement; the reference
+    gradients become the golden of the CUDA backward kernel (inputs regenerate from the seed)."""
+    W, Q, T, D, seed = 3, 2, 8, 512, 77
+    sup, tgt, go = O.make_otam_grad_inputs(W, Q, T, D, seed)
+    net = types.SimpleNamespace(args=NS(MODEL=NS()))
+    s1, t1 = sup.clone().requires_grad_(True), tgt.clone().requires_grad_(True)
+    out_ref = m.CNN.otam_distance(net, s1, t1)
+    (out_ref * go).sum().backward()
+    s2, t2 = sup.clone().requires_grad_(True), tgt.clone().requires_grad_(True)
+    out = O.otam_distance(s2, t2, False)
+    (out * go).sum().backward()
+    r = max(rel(out, out_ref.detach()), rel(s2.grad, s1.grad), rel(t2.grad, t1.grad))
+    assert r < 2e-4, r
+    print("%-24s oracle autograd == reference autograd (CNN.otam_distance), worst rel err %.2e" % ("otam_grad_3w2q_t8", r))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "otam_grad_3w2q_t8.npz"), out=out_ref.detach().numpy(),
+                        grad_support=s1.grad.numpy(), grad_target=t1.grad.numpy(),
+                        shape=np.array([W, Q, T, D, seed], np.int32))
+
+
 if __name__ == "__main__":
     m = import_reference()
-    names = sys.argv[1:] or (list(CASES) + ["text"])
+    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"])
     for n in names:
         if n == "text":
             run_text_case(m)
+        elif n == "otam_grad":
+            run_otam_grad_case(m)
         else:
             run_case(m, n)

@@ -156,3 +156,15 @@ def test_c_restatement_of_otam_matches_python_oracle(W, Q, T, D, single):
     a = c_otam_distance(sup, tgt, single)
     b = O.otam_distance(sup.double(), tgt.double(), single).float()
     assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+
+
+def test_oracle_otam_gradients_match_reference_golden():
+    """autograd through the oracle's otam_distance == autograd through the reference's CNN.otam_distance"""
+    g = H.golden("otam_grad_3w2q_t8")
+    W, Q, T, D, seed = [int(v) for v in g["shape"]]
+    sup, tgt, go = O.make_otam_grad_inputs(W, Q, T, D, seed)
+    s, t = sup.clone().requires_grad_(True), tgt.clone().requires_grad_(True)
+    out = O.otam_distance(s, t, False)
+    (out * go).sum().backward()
+    assert H.rel_err(out.detach(), g["out"]) < 1e-5
+    assert H.rel_err(s.grad, g["grad_support"]) < 1e-5 and H.rel_err(t.grad, g["grad_target"]) < 1e-5

@@ -66,3 +66,18 @@ def test_otam_backward_scaling_and_errors():
         ops.otam_distance(sup, tgt, beta=1.0, out=torch.zeros(1, 2, 3, device="cuda"))
     with torch.no_grad():
         assert ops.otam_distance(sup, tgt).shape == (1, 2, 3)     # inference path unchanged
+
+
+def test_otam_backward_matches_reference_golden():
+    """golden = autograd through the reference's own CNN.otam_distance (oracle/pin_against_reference.py otam_grad)"""
+    from clip_spm_b200 import ops
+    from tests import helpers as H
+    g = H.golden("otam_grad_3w2q_t8")
+    W, Q, T, D, seed = [int(v) for v in g["shape"]]
+    sup, tgt, go = O.make_otam_grad_inputs(W, Q, T, D, seed)
+    s, t = sup.cuda()[None].requires_grad_(True), tgt.cuda()[None].requires_grad_(True)
+    out = ops.otam_distance(s, t)
+    (out[0] * go.cuda()).sum().backward()
+    assert torch.allclose(out[0].detach().cpu(), g["out"], atol=1e-4, rtol=1e-5)
+    for mine, ref in ((s.grad[0].cpu(), g["grad_support"]), (t.grad[0].cpu(), g["grad_target"])):
+        assert (mine - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
