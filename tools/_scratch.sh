@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -2 gpurun_out/bench_final.err; cat gpurun_out/bench_final.json | cut -c1-1500
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_final.json 2>/dev/null; cat gpurun_out/bench_ref_final.json | cut -c1-600
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_frames_gpu.py tests/test_otam_backward_gpu.py -x -q -k "transform_frames or otam_backward_matches_autograd or golden" 2>&1 | tail -15
+echo "exit: $?"
