@@ -240,9 +240,10 @@ seq_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   const int off = g == 0 ? off0 : off1, n = g == 0 ? len0 : len1;
   const long long row0 = (long long)b * rows_per_batch + off;
   const int inner = heads * dh, ld = 3 * inner;
+  const int n_cap = len0 > len1 ? len0 : len1;  // the launch sizes shared memory for its longest group
   float* sK = sm_sa;                    // [n][dh+1]
-  float* sV = sK + SEQ_MAX * (dh + 1);  // [n][dh]
-  float* sQ = sV + SEQ_MAX * dh;        // [8 warps][dh]
+  float* sV = sK + n_cap * (dh + 1);    // [n][dh]
+  float* sQ = sV + n_cap * dh;          // [8 warps][dh]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
     const int j = i / dh, d = i % dh;
@@ -286,17 +287,18 @@ seq_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
     __syncwarp();
   }
 }
-static size_t seq_attention_smem(int dh) { return (size_t)(SEQ_MAX * (dh + 1) + SEQ_MAX * dh + 8 * dh) * sizeof(float); }
+// sized by the longest sequence of the launch (9 tokens for se_te: 27 KB, 8 CTAs per SM instead of 1 at SEQ_MAX)
+static size_t seq_attention_smem(int n, int dh) { return (size_t)(n * (dh + 1) + n * dh + 8 * dh) * sizeof(float); }
 int k_seq_attention_init() {
   return (int)cudaFuncSetAttribute(seq_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)seq_attention_smem(256));
+                                   (int)seq_attention_smem(SEQ_MAX, 256));
 }
 int k_seq_attention(cudaStream_t st, const float* qkv, float* out, int n_batch, int rows_per_batch, int n_groups,
                     int off0, int len0, int off1, int len1, int heads, int dh) {
   if (len0 > SEQ_MAX || len1 > SEQ_MAX || dh > 256 || dh % 32 != 0) return -2;
   if (n_batch <= 0) return 0;
   dim3 grid(n_batch * n_groups, heads);
-  seq_attention_kernel<<<grid, 256, seq_attention_smem(dh), st>>>(qkv, out, rows_per_batch, n_groups, off0, len0, off1,
+  seq_attention_kernel<<<grid, 256, seq_attention_smem(len0 > len1 ? len0 : len1, dh), st>>>(qkv, out, rows_per_batch, n_groups, off0, len0, off1,
                                                                    len1, heads, dh);
   SPM_LAUNCH_CHECK();
   return 0;

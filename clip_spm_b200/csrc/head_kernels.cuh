@@ -31,5 +31,9 @@ int k_otam_init();
 int k_otam(cudaStream_t st, const float* sup, long long s_p, long long s_w, long long s_t, const float* tgt,
            long long t_p, long long t_q, long long t_t, int P, int W, int Q, int T, int D, int single_direct,
            float alpha, float beta, float* out);
+// same contract on the tensor cores (3xTF32 products, one CTA per problem at batch scale); -3 = shape not instantiated
+int k_otam_mma(cudaStream_t st, const float* sup, long long s_p, long long s_w, long long s_t, const float* tgt,
+               long long t_p, long long t_q, long long t_t, int P, int W, int Q, int T, int D, int single_direct,
+               float alpha, float beta, float* out);
 
 }  // namespace spm

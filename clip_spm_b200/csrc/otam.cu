@@ -10,51 +10,14 @@
 // __shfl_up from lane m-1 (its last and second-to-last values) and from the lane's own last value:
 // 2T+1 dependent steps instead of the reference's T*(T+2) sequential host-launched cells.
 #include "head_kernels.cuh"
+#include "otam_dp.cuh"
 #include "profile.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace spm {
 
-namespace {
-constexpr float LBDA = 0.5f;
-constexpr float INV_LBDA = 2.0f;
-
-// soft-min with lambda = 0.5 in the min-shifted form: -l*log(sum exp(-x/l)) = min - l*log(sum exp(-(x-min)/l)).
-// Mathematically identical to the reference's expression (myRes.py:838-853), better conditioned (all exponents <= 0,
-// the sum lies in [1, 3]) -- which also makes the fast intrinsics accurate to ~1e-6 here.
-__device__ __forceinline__ float softmin2(float a, float b) {
-  const float mn = fminf(a, b), mx = fmaxf(a, b);
-  return mn - LBDA * __logf(1.f + __expf((mn - mx) * INV_LBDA));
-}
-__device__ __forceinline__ float softmin3(float a, float b, float c) {
-  const float mn = fminf(a, fminf(b, c));
-  const float s = __expf((mn - a) * INV_LBDA) + __expf((mn - b) * INV_LBDA) + __expf((mn - c) * INV_LBDA);
-  return mn - LBDA * __logf(s);
-}
-
-// One DP per SEG-lane segment of a warp (SEG = 16: two DPs per warp when T + 2 <= 16, else SEG = 32).
-// dist(l, j): l = row (0..T-1), j = unpadded column (0..T-1).  Returns C[T-1, T+1] in every lane of the segment.
-template <int SEG, class DistFn>
-__device__ __forceinline__ float otam_wavefront(int T, bool valid, DistFn dist) {
-  const int m = threadIdx.x & (SEG - 1);  // padded column owned by this lane
-  float v1 = 0.f, v2 = 0.f;               // this lane's last / second-to-last computed cells
-  for (int k = 0; k <= 2 * T; ++k) {
-    const float left = __shfl_up_sync(0xffffffffu, v1, 1, SEG);   // C[l,   m-1]
-    const float diag = __shfl_up_sync(0xffffffffu, v2, 1, SEG);   // C[l-1, m-1]
-    const int l = k - m;
-    if (valid && l >= 0 && l < T && m <= T + 1) {
-      const float d = (m >= 1 && m <= T) ? dist(l, m - 1) : 0.f;
-      float c;
-      if (m == 0) c = 0.f;                                    // column 0 is never written (stays 0)
-      else if (l == 0) c = d + left;                          // top row: plain prefix sum
-      else if (m == 1 || m == T + 1) c = d + softmin3(diag, v1, left);   // (l-1,m-1), (l-1,m), (l,m-1)
-      else c = d + softmin2(diag, left);                      // interior: no vertical neighbour
-      v2 = v1;
-      v1 = c;
-    }
-  }
-  return __shfl_sync(0xffffffffu, v1, T + 1, SEG);
-}
-}  // namespace
+using namespace otam_dp;
 
 // NV: D = NV*128.  TP: number of dot-product accumulators kept per lane (power of two >= T).
 template <int NV, int TP>
@@ -145,16 +108,14 @@ otam_kernel(const float* __restrict__ sup, long long s_p, long long s_w, long lo
       const bool valid = j < n_dp;
       const int w = valid ? j / ndir : 0, dir = valid ? j % ndir : 0;
       const float* dw = dist + w * T * T;
-      const float r = (dir == 0) ? otam_wavefront<16>(T, valid, [&](int l, int c) { return dw[l * T + c]; })
-                                 : otam_wavefront<16>(T, valid, [&](int l, int c) { return dw[c * T + l]; });
+      const float r = otam_wavefront<16>(T, valid, dw, dir);
       if (valid && (lane & 15) == 0) res[w * 2 + dir] = r;
     }
   } else {
     for (int j = warp; j < n_dp; j += 8) {
       const int w = j / ndir, dir = j % ndir;
       const float* dw = dist + w * T * T;
-      const float r = (dir == 0) ? otam_wavefront<32>(T, true, [&](int l, int c) { return dw[l * T + c]; })
-                                 : otam_wavefront<32>(T, true, [&](int l, int c) { return dw[c * T + l]; });
+      const float r = otam_wavefront<32>(T, true, dw, dir);
       if (lane == 0) res[w * 2 + dir] = r;
     }
   }
@@ -188,6 +149,12 @@ int k_otam(cudaStream_t st, const float* sup, long long s_p, long long s_w, long
            float alpha, float beta, float* out) {
   if (T < 2 || T > 30 || W > 32 || (D != 512 && D != 1024)) return -2;
   if (P <= 0 || Q <= 0) return 0;
+  // tensor-core kernel (otam_mma.cu) for every shape it is instantiated for; SPM_OTAM=stream keeps this kernel
+  static const bool allow_mma = [] { const char* e = getenv("SPM_OTAM"); return e == nullptr || strcmp(e, "stream") != 0; }();
+  if (allow_mma) {
+    const int r = k_otam_mma(st, sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, P, W, Q, T, D, single_direct, alpha, beta, out);
+    if (r != -3) return r;
+  }
   dim3 grid(Q, P);
   const size_t smem = otam_smem(W, T, D);
   if (smem > (size_t)OTAM_SMEM_MAX) return -2;

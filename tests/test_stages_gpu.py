@@ -20,7 +20,11 @@ TOL_OTAM = 1e-5
 
 @pytest.mark.parametrize("P,W,Q,T,D,single", [(1, 5, 5, 8, 512, False), (3, 5, 5, 16, 512, False),
                                               (2, 5, 1, 8, 1024, False), (4, 7, 3, 8, 512, True),
-                                              (1, 1, 1, 2, 512, False), (2, 32, 2, 30, 512, False)])
+                                              (1, 1, 1, 2, 512, False), (2, 32, 2, 30, 512, False),
+                                              # >= 2 x 148 problems: one CTA per problem (all queries) on the tensor cores
+                                              (300, 5, 5, 8, 512, False), (296, 5, 5, 16, 512, False),
+                                              (300, 5, 6, 8, 1024, True), (297, 3, 2, 8, 512, False),
+                                              (296, 10, 12, 8, 512, False)])
 def test_otam_distance_matches_oracle(P, W, Q, T, D, single):
     from clip_spm_b200 import ops
     g = torch.Generator().manual_seed(P * 100 + T)

@@ -9,7 +9,10 @@ peak = 6550.7
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
 if os.path.exists(p):
     peak = json.load(open(p))["hbm_gbs"]
-for P, W, Q, T, D in ((1000, 5, 5, 8, 512), (4000, 5, 5, 8, 512), (1000, 5, 5, 16, 512), (1000, 5, 5, 8, 1024)):
+shapes = ((1000, 5, 5, 8, 512), (4000, 5, 5, 8, 512), (1000, 5, 5, 16, 512), (1000, 5, 5, 8, 1024))
+if "--one" in sys.argv:   # a single shape: the command profiled under ncu
+    shapes = shapes[:1]
+for P, W, Q, T, D in shapes:
     sup = torch.randn(P, W, T, D, device="cuda"); tgt = torch.randn(P, Q, T, D, device="cuda")
     out = torch.zeros(P, Q, W, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
