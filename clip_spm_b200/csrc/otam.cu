@@ -99,25 +99,16 @@ otam_kernel(const float* __restrict__ sup, long long s_p, long long s_w, long lo
       dist[(w * T + t_own) * T + ts] = 1.f - tot / (qn[t_own] * sqrtf(nn) + 0.01f);
   }
   __syncthreads();
-  // ---- phase 2: the (class, direction) DPs as anti-diagonal wavefronts, two per warp when a DP fits 16 lanes
+  // ---- phase 2: the (class, direction) DPs as anti-diagonal wavefronts, 32 / (T + 2) of them per warp
   const int ndir = single_direct ? 1 : 2;
   const int n_dp = W * ndir;
-  if (T + 2 <= 16) {
-    for (int j0 = warp * 2; j0 < n_dp; j0 += 16) {
-      const int j = j0 + (lane >> 4);
-      const bool valid = j < n_dp;
-      const int w = valid ? j / ndir : 0, dir = valid ? j % ndir : 0;
-      const float* dw = dist + w * T * T;
-      const float r = otam_wavefront<16>(T, valid, dw, dir);
-      if (valid && (lane & 15) == 0) res[w * 2 + dir] = r;
-    }
-  } else {
-    for (int j = warp; j < n_dp; j += 8) {
-      const int w = j / ndir, dir = j % ndir;
-      const float* dw = dist + w * T * T;
-      const float r = otam_wavefront<32>(T, true, dw, dir);
-      if (lane == 0) res[w * 2 + dir] = r;
-    }
+  const int per_warp = otam_dps_per_warp(T), seg = lane / (T + 2), m = lane % (T + 2);
+  for (int j0 = warp * per_warp; j0 < n_dp; j0 += 8 * per_warp) {
+    const int j = j0 + seg;
+    const bool valid = seg < per_warp && j < n_dp;
+    const int w = valid ? j / ndir : 0, dir = valid ? j % ndir : 0;
+    const float r = otam_wavefront(T, m, valid, dist + w * T * T, dir);
+    if (valid && m == T + 1) res[w * 2 + dir] = r;
   }
   __syncthreads();
   for (int w = threadIdx.x; w < W; w += blockDim.x) {
