@@ -29,6 +29,8 @@ class SpmConfig(ctypes.Structure):
         ("max_support", c_int),
         ("max_query", c_int),
         ("max_way", c_int),
+        ("head", c_int),
+        ("cls_value", c_float),
     ]
 
 
@@ -46,6 +48,8 @@ SIGNATURES = {
     "spm_load_weights": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(ctypes.c_char_p),
                                  ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_int64)]),
     "spm_set_text_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
+    "spm_set_text_features_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
+    "spm_class_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "spm_encode_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "spm_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7),
     "spm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7),

@@ -25,6 +25,15 @@ int k_class_mean_padm(cudaStream_t st, const float* z1, const float* labels, int
 int k_finalize(cudaStream_t st, const float* accd, const float* d3, int E, int Q, int W, const long long* target,
                float tasks_per_batch, const float* dists, float* logits, float* loss, float* accuracy, int* pred,
                const int* err_flag);
+// ---- sibling head CLIP-FSAR (fsar_kernels.cu; models/model_clipfsar.py:325-383)
+int k_fsar_seq_build(cudaStream_t st, const float* X, const float* text, int n_cls, const float* real_s, int E, int S,
+                     int Q, int T, int D, float* seq);
+int k_fsar_class_mean(cudaStream_t st, const float* z, const float* labels, int E, int S, int W, int T, int D,
+                      float* su_pro, int* err_flag);
+int k_fsar_class_logits(cudaStream_t st, const float* X, const float* text_train, int n_cls, const float* scale, int V,
+                        int T, int D, float* out);
+int k_fsar_class_ce_add(cudaStream_t st, const float* cls, const float* real_s, const float* real_t, int E, int S, int Q,
+                        int n_cls, float coef, float* loss);
 int k_otam_init();
 // out[p,q,w] = beta*out + alpha * otam(support[p,w,:,:], target[p,q,:,:]); element (p,w,t,d) of the support set is at
 // sup + p*s_p + w*s_w + t*s_t + d (strides in floats), likewise for the target set.

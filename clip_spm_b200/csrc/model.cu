@@ -94,6 +94,10 @@ struct VitPlan {
 struct CtxPlan {
   GemmOp qkv, outp, ff0, ff3;
 };
+struct FsarPlan {   // sibling head CLIP-FSAR: one context2 pass over E*S*(T+1) + E*Q*T rows
+  int E, S, Q;
+  CtxPlan c2;
+};
 struct HeadPlan {
   int E, S, Q, W;
   const float* X;  // frame-feature base the plan's tensor maps point at
@@ -150,6 +154,14 @@ struct spm_handle {
         *SUPRO2 = nullptr, *ACC = nullptr, *D3 = nullptr;
   int* err_flag = nullptr;
   std::vector<std::unique_ptr<spm::HeadPlan>> head_plans;
+  // sibling head CLIP-FSAR (cfg.head == SPM_HEAD_CLIPFSAR; models/model_clipfsar.py)
+  spm::CtxW fsar_ctx = {};
+  float* fsar_scale = nullptr;
+  float* text_train = nullptr;   // [n_cls_train, D] text_features_train (class_text_logits)
+  int n_cls_train = 0;
+  float* CLS = nullptr;          // [E, S+Q, n_cls_train] class_text_logits of the last head call
+  long long cls_cap = 0, cls_rows = 0;
+  std::vector<std::unique_ptr<spm::FsarPlan>> fsar_plans;
   // `X` is the feature block the head currently reads: its own buffer (Xhead), or a group of episodes inside Xall
   // when the forward pipelines episode groups (encoder of group g+1 overlaps the head of group g on head_stream)
   float *Xhead = nullptr, *Xall = nullptr;
@@ -289,6 +301,35 @@ int load_vit32(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
   return 0;
 }
 
+// one Transformer_v1 layer (models/myRes.py:1053-1064): LayerNorm, to_q/k/v fused into one [3*inner, D] B operand
+// (myRes.py:957-959), to_out, FeedForward
+int load_ctx(spm_handle* h, cudaStream_t st, const WeightTable& wt, const std::string& p, long long inner, CtxW* out) {
+  const long long D = h->D;
+  CtxW& x = *out;
+  const float* src;
+  SPM_TRY(copy_f32(h, st, wt, p + "0.norm.weight", D, &x.ln_g));
+  SPM_TRY(copy_f32(h, st, wt, p + "0.norm.bias", D, &x.ln_b));
+  SPM_TRY(dalloc_t(h, &x.qkv_w, 3LL * inner * D));
+  const char* names[3] = {"0.fn.to_q.weight", "0.fn.to_k.weight", "0.fn.to_v.weight"};
+  for (int i = 0; i < 3; ++i) {
+    SPM_TRY(wt.get(p + names[i], inner * D, &src));
+    SPM_CUDA(cudaMemcpyAsync(x.qkv_w + (long long)i * inner * D, src, (size_t)inner * D * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  SPM_TRY(copy_f32(h, st, wt, p + "0.fn.to_out.0.weight", D * inner, &x.out_w));
+  SPM_TRY(copy_f32(h, st, wt, p + "0.fn.to_out.0.bias", D, &x.out_b));
+  SPM_TRY(copy_f32(h, st, wt, p + "1.net.0.weight", HEAD_MLP * D, &x.ff0_w));
+  SPM_TRY(copy_f32(h, st, wt, p + "1.net.0.bias", HEAD_MLP, &x.ff0_b));
+  SPM_TRY(copy_f32(h, st, wt, p + "1.net.3.weight", D * HEAD_MLP, &x.ff3_w));
+  SPM_TRY(copy_f32(h, st, wt, p + "1.net.3.bias", D, &x.ff3_b));
+  return 0;
+}
+
+// CNN_OTAM_CLIPFSAR's own parameters (models/model_clipfsar.py:137-145): scale, context2 with inner width D
+int load_head_fsar(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
+  SPM_TRY(copy_f32(h, st, wt, "scale", 1, &h->fsar_scale));
+  return load_ctx(h, st, wt, "context2.layers.0.", h->D, &h->fsar_ctx);
+}
+
 int load_head(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
   HeadW& w = h->head;
   const long long D = h->D, HT = h->HT, HV = h->HV;
@@ -314,26 +355,8 @@ int load_head(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
   SPM_TRY(copy_f32(h, st, wt, "gate_vision.2.weight", D * HV, &w.gv2_w));
   SPM_TRY(copy_f32(h, st, wt, "gate_vision.2.bias", D, &w.gv2_b));
   SPM_TRY(copy_f32(h, st, wt, "mo_alpha1", 1, &w.mo_alpha1));
-  for (int c = 0; c < 2; ++c) {
-    const std::string p = c == 0 ? "context1.layers.0." : "context2.layers.0.";
-    CtxW& x = w.ctx[c];
-    SPM_TRY(copy_f32(h, st, wt, p + "0.norm.weight", D, &x.ln_g));
-    SPM_TRY(copy_f32(h, st, wt, p + "0.norm.bias", D, &x.ln_b));
-    // fused [Wq; Wk; Wv] : one [3*2048, D] B operand (myRes.py:957-959)
-    SPM_TRY(dalloc_t(h, &x.qkv_w, 3LL * HEAD_INNER * D));
-    const char* names[3] = {"0.fn.to_q.weight", "0.fn.to_k.weight", "0.fn.to_v.weight"};
-    for (int i = 0; i < 3; ++i) {
-      SPM_TRY(wt.get(p + names[i], HEAD_INNER * D, &src));
-      SPM_CUDA(cudaMemcpyAsync(x.qkv_w + (long long)i * HEAD_INNER * D, src, (size_t)HEAD_INNER * D * 4,
-                               cudaMemcpyDeviceToDevice, st));
-    }
-    SPM_TRY(copy_f32(h, st, wt, p + "0.fn.to_out.0.weight", D * HEAD_INNER, &x.out_w));
-    SPM_TRY(copy_f32(h, st, wt, p + "0.fn.to_out.0.bias", D, &x.out_b));
-    SPM_TRY(copy_f32(h, st, wt, p + "1.net.0.weight", HEAD_MLP * D, &x.ff0_w));
-    SPM_TRY(copy_f32(h, st, wt, p + "1.net.0.bias", HEAD_MLP, &x.ff0_b));
-    SPM_TRY(copy_f32(h, st, wt, p + "1.net.3.weight", D * HEAD_MLP, &x.ff3_w));
-    SPM_TRY(copy_f32(h, st, wt, p + "1.net.3.bias", D, &x.ff3_b));
-  }
+  SPM_TRY(load_ctx(h, st, wt, "context1.layers.0.", HEAD_INNER, &w.ctx[0]));
+  SPM_TRY(load_ctx(h, st, wt, "context2.layers.0.", HEAD_INNER, &w.ctx[1]));
   return 0;
 }
 
@@ -629,6 +652,7 @@ int ensure_head_workspace(spm_handle* h, int E, int S, int Q, int W) {
   if (E <= h->head_cap_E && S <= h->head_cap_S && Q <= h->head_cap_Q && W <= h->head_cap_W) return 0;
   // grow-only: plans that point into the old buffers are dropped
   h->head_plans.clear();
+  h->fsar_plans.clear();
   const long long cE = std::max<long long>(E, h->head_cap_E), cS = std::max<long long>(S, h->head_cap_S),
                   cQ = std::max<long long>(Q, h->head_cap_Q), cW = std::max<long long>(W, h->head_cap_W);
   const long long T = h->cfg.seq_len, D = h->D, N = cS + cQ, V = cE * N;
@@ -666,14 +690,15 @@ int ensure_head_workspace(spm_handle* h, int E, int S, int Q, int W) {
   return 0;
 }
 
-int plan_ctx(spm_handle* h, CtxPlan* p, const CtxW& w, int R, float* seq, float* out) {
+// inner = heads * dim_head of the attention (2048 for CLIP-SPM's context1/2, D for CLIP-FSAR's context2)
+int plan_ctx(spm_handle* h, CtxPlan* p, const CtxW& w, int R, float* seq, float* out, int inner = HEAD_INNER) {
   const int D = h->D;
   GemmEpilogue e1;
-  e1.out = h->QKVH; e1.ldo = 3 * HEAD_INNER;
-  SPM_TRY(plan_gemm(&p->qkv, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->HN, D, w.qkv_w, D, R, 3 * HEAD_INNER, D, e1, h->sms));
+  e1.out = h->QKVH; e1.ldo = 3 * inner;
+  SPM_TRY(plan_gemm(&p->qkv, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->HN, D, w.qkv_w, D, R, 3 * inner, D, e1, h->sms));
   GemmEpilogue e2;  // to_out + bias + the un-normalised sequence (myRes.py:1040)
   e2.bias = w.out_b; e2.residual = seq; e2.ldr = D; e2.out = h->Y; e2.ldo = D;
-  SPM_TRY(plan_gemm(&p->outp, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->AO, HEAD_INNER, w.out_w, HEAD_INNER, R, D, HEAD_INNER, e2, h->sms));
+  SPM_TRY(plan_gemm(&p->outp, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->AO, inner, w.out_w, inner, R, D, inner, e2, h->sms));
   GemmEpilogue e3;
   e3.bias = w.ff0_b; e3.act = ACT_GELU_ERF; e3.out = h->FFH; e3.ldo = HEAD_MLP;
   SPM_TRY(plan_gemm(&p->ff0, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, h->Y, D, w.ff0_w, D, R, HEAD_MLP, D, e3, h->sms));
@@ -741,11 +766,70 @@ int run_ctx(spm_handle* h, cudaStream_t st, const CtxPlan& p, const CtxW& w, int
   return 0;
 }
 
+// CLIP-FSAR head (models/model_clipfsar.py:325-383) on frame features in h->X [E, N, T, D]:
+//   target  = context2(target)                       self-attention over the T frames of each query video
+//   support = context2(cat[support, prompt])[:, :T]  T frames + the class prompt of the video's real label
+//   prototypes = per-class mean;  logits = -(OTAM(d) + OTAM(d^T));  class_logits = cos_sim(mean_t feats, text_train)*scale
+int fsar_head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const float* labels, const float* real_s,
+                  const float* real_t, const long long* target_labels, float tasks_per_batch, float* logits,
+                  float* dists, float* loss, float* acc, int* pred) {
+  SPM_CHECK(h->text_set, "head: text features not set (spm_set_text_features)");
+  SPM_TRY(ensure_head_workspace(h, E, S, Q, W));
+  const int T = h->cfg.seq_len, D = h->D, N = S + Q, V = E * N, dh = D / HEAD_HEADS;
+  const long long RS = (long long)E * S * (T + 1), R = RS + (long long)E * Q * T, TD = (long long)T * D;
+  FsarPlan* pl = nullptr;
+  for (auto& p : h->fsar_plans)
+    if (p->E == E && p->S == S && p->Q == Q) pl = p.get();
+  if (pl == nullptr) {
+    std::unique_ptr<FsarPlan> np(new FsarPlan());
+    np->E = E; np->S = S; np->Q = Q;
+    SPM_TRY(plan_ctx(h, &np->c2, h->fsar_ctx, (int)R, h->SEQ, h->Z, D));
+    pl = np.get();
+    h->fsar_plans.push_back(std::move(np));
+  }
+  const CtxW& w = h->fsar_ctx;
+  SPM_KERNEL(k_fsar_seq_build(st, h->X, h->text, h->n_cls, real_s, E, S, Q, T, D, h->SEQ));
+  SPM_KERNEL(k_layernorm(st, h->SEQ, D, (int)R, D, w.ln_g, w.ln_b, nullptr, 0, h->HN, nullptr, D));
+  SPM_GEMM_RUN(pl->c2.qkv);
+  SPM_KERNEL(k_seq_attention(st, h->QKVH, h->AO, E * S, T + 1, 1, 0, T + 1, 0, 0, HEAD_HEADS, dh));
+  SPM_KERNEL(k_seq_attention(st, h->QKVH + RS * 3 * D, h->AO + RS * D, E * Q, T, 1, 0, T, 0, 0, HEAD_HEADS, dh));
+  SPM_GEMM_RUN(pl->c2.outp);
+  SPM_GEMM_RUN(pl->c2.ff0);
+  SPM_GEMM_RUN(pl->c2.ff3);
+  SPM_KERNEL(k_fsar_class_mean(st, h->Z, labels, E, S, W, T, D, h->SUPRO, h->err_flag));
+  SPM_KERNEL(k_otam(st, h->SUPRO, (long long)W * TD, TD, D, h->Z + RS * D, (long long)Q * TD, TD, D, E, W, Q, T, D,
+                    h->cfg.single_direct, 1.f, 0.f, h->ACC));
+  SPM_CUDA(cudaMemsetAsync(h->D3, 0, (size_t)E * W * sizeof(float), st));
+  SPM_CUDA(cudaMemsetAsync(dists, 0, (size_t)E * sizeof(float), st));   // this head has no auxiliary distance
+  h->cls_rows = 0;
+  if (h->text_train != nullptr) {
+    const long long need = (long long)V * h->n_cls_train;
+    if (need > h->cls_cap) {
+      SPM_TRY(dalloc_t(h, &h->CLS, need));
+      h->cls_cap = need;
+    }
+    SPM_KERNEL(k_fsar_class_logits(st, h->X, h->text_train, h->n_cls_train, h->fsar_scale, V, T, D, h->CLS));
+    h->cls_rows = V;
+  }
+  SPM_KERNEL(k_finalize(st, h->ACC, h->D3, E, Q, W, target_labels, tasks_per_batch, dists, logits, loss, acc, pred,
+                        h->err_flag));
+  if (loss != nullptr && target_labels != nullptr) {
+    // run/main_run.py:355-356: (CE(logits) + USE_CLASSIFICATION_VALUE * CE(class_logits, real labels)) / TASKS_PER_BATCH
+    SPM_CHECK(h->text_train != nullptr, "CLIP-FSAR loss needs text_features_train (spm_set_text_features_train)");
+    SPM_KERNEL(k_fsar_class_ce_add(st, h->CLS, real_s, real_t, E, S, Q, h->n_cls_train,
+                                   h->cfg.cls_value / tasks_per_batch, loss));
+  }
+  return 0;
+}
+
 // Frame features already in h->X as [E, N, T, D] (supports first).  Produces logits [E,Q,W], dists [E] and, when
 // target_labels is given, loss / accuracy / predictions.
 int head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const float* labels, const float* real_s,
              const float* real_t, const long long* target_labels, float tasks_per_batch, float* logits, float* dists,
              float* loss, float* acc, int* pred) {
+  if (h->cfg.head == SPM_HEAD_CLIPFSAR)
+    return fsar_head_run(h, st, E, S, Q, W, labels, real_s, real_t, target_labels, tasks_per_batch, logits, dists, loss,
+                         acc, pred);
   SPM_CHECK(h->text_set, "head: text features not set (spm_set_text_features)");
   HeadPlan* pl;
   SPM_TRY(get_head_plan(h, E, S, Q, W, &pl));
@@ -931,6 +1015,7 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   SPM_CHECK(cfg->backbone == SPM_BACKBONE_VIT_B16 || cfg->backbone == SPM_BACKBONE_RN50, "spm_create: unknown backbone");
   SPM_CHECK(cfg->seq_len >= 2 && cfg->seq_len <= 30, "spm_create: seq_len must be in [2, 30]");
   SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->precision == SPM_PRECISION_FP32, "spm_create: unknown precision");
+  SPM_CHECK(cfg->head == SPM_HEAD_CLIPSPM || cfg->head == SPM_HEAD_CLIPFSAR, "spm_create: unknown head");
   SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->backbone == SPM_BACKBONE_VIT_B16,
             "spm_create: SPM_PRECISION_FP32 is implemented for the ViT-B/16 backbone only");
   int ndev = 0;
@@ -1003,7 +1088,8 @@ int spm_load_weights(spm_handle* h, void* stream, int n, const char* const* name
     auto getter = [&](const std::string& name, long long ne, const float** out) { return wt.get(name, ne, out); };
     SPM_TRY(rn50_create(&h->rn50, st, h->sms, getter));
   }
-  SPM_TRY(load_head(h, st, wt));
+  if (h->cfg.head == SPM_HEAD_CLIPFSAR) SPM_TRY(load_head_fsar(h, st, wt));
+  else SPM_TRY(load_head(h, st, wt));
   SPM_CUDA(cudaStreamSynchronize(st));
   h->weights_loaded = true;
   return 0;
@@ -1017,6 +1103,25 @@ int spm_set_text_features(spm_handle* h, void* stream, const float* table, int n
   SPM_CUDA(cudaMemcpyAsync(h->text, table, (size_t)n_cls * dim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   h->n_cls = n_cls;
   h->text_set = true;
+  return 0;
+}
+
+int spm_set_text_features_train(spm_handle* h, void* stream, const float* table, int n_cls, int dim) {
+  SPM_CHECK(h != nullptr && table != nullptr, "spm_set_text_features_train: null argument");
+  SPM_CHECK(dim == h->D, "spm_set_text_features_train: feature dim does not match the backbone's mid_dim");
+  SPM_CHECK(n_cls >= 1, "spm_set_text_features_train: empty table");
+  if (n_cls > h->n_cls_train) SPM_TRY(dalloc_t(h, &h->text_train, (long long)n_cls * dim));
+  SPM_CUDA(cudaMemcpyAsync(h->text_train, table, (size_t)n_cls * dim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  h->n_cls_train = n_cls;
+  return 0;
+}
+
+int spm_class_logits(spm_handle* h, void* stream, int n_rows, int n_cls, float* out) {
+  SPM_CHECK(h != nullptr && out != nullptr, "spm_class_logits: null argument");
+  SPM_CHECK(h->cfg.head == SPM_HEAD_CLIPFSAR, "spm_class_logits: only the CLIP-FSAR head produces class logits");
+  SPM_CHECK(h->cls_rows > 0, "spm_class_logits: no class logits available (no head call yet, or text_features_train not set)");
+  SPM_CHECK(n_rows == h->cls_rows && n_cls == h->n_cls_train, "spm_class_logits: shape does not match the last head call");
+  SPM_CUDA(cudaMemcpyAsync(out, h->CLS, (size_t)n_rows * n_cls * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 

@@ -23,9 +23,28 @@ def _p(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
-def _param_shapes(backbone, D, params):
+def _fsar_head_shapes(D):
+    """Parameters of models/model_clipfsar.py::CNN_OTAM_CLIPFSAR besides the backbone (:137-145): `scale` and
+    context2 = Transformer_v1(dim=D, heads=8, dim_head_k=D//8): inner width D, mlp 2048."""
+    p = "context2.layers.0."
+    return {"scale": (1,), p + "0.norm.weight": (D,), p + "0.norm.bias": (D,), p + "0.fn.to_q.weight": (D, D),
+            p + "0.fn.to_k.weight": (D, D), p + "0.fn.to_v.weight": (D, D), p + "0.fn.to_out.0.weight": (D, D),
+            p + "0.fn.to_out.0.bias": (D,), p + "1.net.0.weight": (2048, D), p + "1.net.0.bias": (2048,),
+            p + "1.net.3.weight": (D, 2048), p + "1.net.3.bias": (D,)}
+
+
+def _param_shapes(backbone, D, params, head="clipspm"):
     """Names and shapes of the reference CNN's parameters/buffers (models/model_clipspm.py:72-99 and the CLIP visual
     tower of models/clip_fsar.py:549-689), written out here from the module definitions."""
+    if head == "clipfsar":
+        s = _fsar_head_shapes(D)
+    else:
+        s = _spm_head_shapes(D, params)
+    s.update(_backbone_shapes(backbone))
+    return s
+
+
+def _spm_head_shapes(D, params):
     ht, hv = int(D * params["mid_dim_text"]), int(D * params["mid_dim_vision"])
     s = {"scale": (1,), "mo_alpha1": ()}
     for n in ("motion_conv1", "motion_conv2"):
@@ -43,6 +62,11 @@ def _param_shapes(backbone, D, params):
     s.update({"gate_text.0.weight": (ht, D), "gate_text.0.bias": (ht,), "gate_text.2.weight": (D, ht),
               "gate_text.2.bias": (D,), "gate_vision.0.weight": (hv, D), "gate_vision.0.bias": (hv,),
               "gate_vision.2.weight": (D, hv), "gate_vision.2.bias": (D,)})
+    return s
+
+
+def _backbone_shapes(backbone):
+    s = {}
     b = "backbone."
     if backbone == "ViT-B/16":
         C = 768
@@ -128,6 +152,8 @@ class CNN(nn.Module):
     precision="bf16": bf16 tcgen05 encoder + tf32 head (what autocast(bfloat16) is to the reference);
     precision="fp32": every product in fp32 FFMA (the reference's default fp32 arithmetic; slow, for parity)."""
 
+    HEAD = "clipspm"   # which metric head runs behind the shared entry points (SPM_HEAD_*)
+
     def __init__(self, cfg, text_features_test=None, text_features_train=None, max_episodes=1, device="cuda",
                  precision="bf16"):
         super().__init__()
@@ -139,14 +165,17 @@ class CNN(nn.Module):
         if self.backbone_name not in ("ViT-B/16", "RN50"):
             raise RuntimeError("unsupported MODEL.BACKBONE %r" % (self.backbone_name,))
         self.mid_dim = 512 if self.backbone_name == "ViT-B/16" else 1024
-        self.params = dict(_cfg_get(cfg, "params"))
+        self.params = dict(_cfg_get(cfg, "params", None) or {})
+        if self.HEAD == "clipspm" and not self.params:
+            raise RuntimeError("cfg.params (mid_dim_text, mid_dim_vision, negative_slope, alpha) is required")
         self.seq_len = int(_cfg_get(cfg, "DATA.SEQ_LEN"))
         self.single_direct = bool(_cfg_get(cfg, "MODEL.SINGLE_DIRECT", False))
         self.way = _cfg_get(cfg, "TRAIN.WAY", None)
         self.tasks_per_batch = float(_cfg_get(cfg, "TRAIN.TASKS_PER_BATCH", 16))
         self.max_episodes = int(max_episodes)
         self._dev = torch.device(device)
-        for name, shape in _param_shapes(self.backbone_name, self.mid_dim, self.params).items():
+        self.cls_value = float(_cfg_get(cfg, "MODEL.USE_CLASSIFICATION_VALUE", 0.0) or 0.0)
+        for name, shape in _param_shapes(self.backbone_name, self.mid_dim, self.params, self.HEAD).items():
             if shape is None:
                 _register(self, name, torch.zeros((), dtype=torch.long), buffer=True)
             elif name.split(".")[-1] in ("running_mean", "running_var"):
@@ -154,7 +183,8 @@ class CNN(nn.Module):
             else:
                 _register(self, name, torch.zeros(shape))
         self.scale.data.fill_(1.0)
-        self.mo_alpha1.data.fill_(1.0)
+        if hasattr(self, "mo_alpha1"):
+            self.mo_alpha1.data.fill_(1.0)
         self.text_features_test = text_features_test
         self.text_features_train = text_features_train
         self._h = None
@@ -219,10 +249,12 @@ class CNN(nn.Module):
         c = _lib.SpmConfig(
             backbone=0 if self.backbone_name == "ViT-B/16" else 1, seq_len=self.seq_len,
             n_text_classes=0 if self.text_features_test is None else int(self.text_features_test.shape[0]),
-            mid_dim_text=float(self.params["mid_dim_text"]), mid_dim_vision=float(self.params["mid_dim_vision"]),
-            negative_slope=float(self.params["negative_slope"]), alpha=float(self.params["alpha"]),
-            single_direct=int(self.single_direct), precision=0 if self.precision == "bf16" else 1, max_episodes=self.max_episodes, max_support=0,
-            max_query=0, max_way=0)
+            mid_dim_text=float(self.params.get("mid_dim_text", 1.5)),
+            mid_dim_vision=float(self.params.get("mid_dim_vision", 0.5)),
+            negative_slope=float(self.params.get("negative_slope", 0.0)), alpha=float(self.params.get("alpha", 0.0)),
+            single_direct=int(self.single_direct), precision=0 if self.precision == "bf16" else 1,
+            max_episodes=self.max_episodes, max_support=0, max_query=0, max_way=0,
+            head=1 if self.HEAD == "clipfsar" else 0, cls_value=self.cls_value)
         h = ctypes.c_void_p()
         with torch.cuda.device(self._dev):
             _lib.check(lib.spm_create(ctypes.byref(c), ctypes.byref(h)))

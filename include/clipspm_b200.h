@@ -17,6 +17,7 @@
  *   spm_encode_frames             models/clip_fsar.py:672-689 VisionTransformer.forward / :593-608 ModifiedResNet
  *   spm_head                      models/model_clipspm.py:125-143  (everything after get_feats)
  *   spm_otam_distance             models/model_clipspm.py:348-362 + models/myRes.py:756-765,821-855
+ *   spm_set_text_features_train / spm_class_logits   models/model_clipfsar.py:127,329-331 (sibling head CLIP-FSAR)
  *   spm_gemm                      ATen linear / conv-as-GEMM calls (cuBLASLt) under all of the above
  */
 #ifndef CLIPSPM_B200_H
@@ -28,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SPM_ABI_VERSION 1
+#define SPM_ABI_VERSION 2 /* 2: spm_config gained `head`, `cls_value` */
 
 typedef struct spm_handle spm_handle;
 
@@ -36,6 +37,10 @@ enum { SPM_BACKBONE_VIT_B16 = 0, SPM_BACKBONE_RN50 = 1 };
 /* arithmetic of the dense contractions: bf16 tensor cores (the reference's autocast(bfloat16) mode) or the
  * fp32-equivalent mode (split-precision tensor-core products, fp32 accumulate) */
 enum { SPM_PRECISION_BF16 = 0, SPM_PRECISION_FP32 = 1 };
+/* metric head behind the same entry points: CLIP-SPM (models/model_clipspm.py, the hot path) or its sibling
+ * CLIP-FSAR (models/model_clipfsar.py CNN_OTAM_CLIPFSAR, evaluation branch :325-383), which reuses the same
+ * transformer-block, class-mean and OTAM kernels */
+enum { SPM_HEAD_CLIPSPM = 0, SPM_HEAD_CLIPFSAR = 1 };
 
 typedef struct spm_config {
   int backbone;         /* cfg.MODEL.BACKBONE: SPM_BACKBONE_*                         model_clipspm.py:18,24 */
@@ -51,6 +56,8 @@ typedef struct spm_config {
   int max_support;      /* S = way*shot support videos per episode (upper bound)                             */
   int max_query;        /* Q query videos per episode (upper bound)                                          */
   int max_way;          /* W distinct support labels per episode (upper bound)                               */
+  int head;             /* SPM_HEAD_* (cfg.MODEL.NAME 'clipspm' / 'clipfsar')          run/main_run.py:123-130 */
+  float cls_value;      /* cfg.MODEL.USE_CLASSIFICATION_VALUE (CLIP-FSAR loss only)    run/main_run.py:356    */
 } spm_config;
 
 const char* spm_last_error(void);
@@ -76,6 +83,14 @@ int spm_load_weights(spm_handle* h, void* stream, int n, const char* const* name
                      const int64_t* numel);
 /* text feature table [n_cls, D] fp32 (the reference's text_features_test / _train) */
 int spm_set_text_features(spm_handle* h, void* stream, const float* table, int n_cls, int dim);
+
+/* CLIP-FSAR only: text_features_train [n_cls, D] (models/model_clipfsar.py:127) for class_text_logits (:331), and the
+ * class_text_logits [n_rows = E*(S+Q), n_cls] of the most recent spm_head / spm_forward / spm_eval call (rows of an
+ * episode: its S supports, then its Q queries -- torch.cat([support_features, target_features]), :329).
+ * With SPM_HEAD_CLIPFSAR, spm_eval's loss is run/main_run.py:355-356:
+ *   (sum_q CE(logits) + cls_value * sum_v CE(class_logits[v], real label of v)) / tasks_per_batch, dists_out = 0. */
+int spm_set_text_features_train(spm_handle* h, void* stream, const float* table, int n_cls, int dim);
+int spm_class_logits(spm_handle* h, void* stream, int n_rows, int n_cls, float* out);
 
 /* Frame encoder: images [F,3,224,224] fp32 NCHW in [0,1] -> features [F, D] fp32 */
 int spm_encode_frames(spm_handle* h, void* stream, const float* images, int n_frames, float* feats_out);

@@ -287,6 +287,71 @@ def forward(w, text_features, inputs, cfg):
     return st
 
 
+# =====================================================================================================
+# sibling head: CLIP-FSAR (models/model_clipfsar.py) -- SURVEY.md 8(f) rank 4, same kernels, other wiring
+# =====================================================================================================
+def fsar_weight_shapes(D):
+    """Parameters of CNN_OTAM_CLIPFSAR besides the backbone (models/model_clipfsar.py:137-145): `scale` and
+    context2 = Transformer_v1(dim=D, heads=8, dim_head_k=D//8) -> inner width D, mlp 2048."""
+    c = "context2."
+    return {"scale": (1,),
+            c + "layers.0.0.norm.weight": (D,), c + "layers.0.0.norm.bias": (D,),
+            c + "layers.0.0.fn.to_q.weight": (D, D), c + "layers.0.0.fn.to_k.weight": (D, D),
+            c + "layers.0.0.fn.to_v.weight": (D, D),
+            c + "layers.0.0.fn.to_out.0.weight": (D, D), c + "layers.0.0.fn.to_out.0.bias": (D,),
+            c + "layers.0.1.net.0.weight": (2048, D), c + "layers.0.1.net.0.bias": (2048,),
+            c + "layers.0.1.net.3.weight": (D, 2048), c + "layers.0.1.net.3.bias": (D,)}
+
+
+def make_fsar_weights(D, seed=0, scale=1.7):
+    """Seeded head weights of the CLIP-FSAR sibling (per-tensor generators, like make_weights; the generator key
+    carries an 'fsar.' prefix so these never alias CLIP-SPM's context2 of another shape)."""
+    w = {}
+    for name, shp in fsar_weight_shapes(D).items():
+        leaf = name.split(".")[-1]
+        if name == "scale":
+            w[name] = torch.full((1,), float(scale))
+        elif len(shp) == 1 and leaf == "weight":
+            w[name] = 1.0 + _normal(seed, "fsar." + name, shp, 0.1)
+        elif leaf == "bias":
+            w[name] = _normal(seed, "fsar." + name, shp, 0.02)
+        else:
+            w[name] = _normal(seed, "fsar." + name, shp, (3.0 * shp[1]) ** -0.5)
+    return w
+
+
+def fsar_head_forward(w, text_test, text_train, su, qu, support_labels, real_support, real_target,
+                      single_direct=False):
+    """models/model_clipfsar.py:325-381, the evaluation branch taken with the shipped configs (no EVAL_TEXT /
+    COMBINE / MERGE_BEFORE; configs/clipfsar/*.yaml): su [S,T,D], qu [Q,T,D] -> logits [1,Q,W],
+    class_logits [1,S+Q,n_train]."""
+    S, T, D = su.shape
+    dh = D // 8
+    feat_cls = torch.cat([su, qu], dim=0).mean(1)                      # :329-330 (classification_layer is empty)
+    class_logits = cos_sim(feat_cls, text_train) * w["scale"]          # :331
+    ctx = text_test[real_support.long()].unsqueeze(1)                  # :338
+    qu2 = transformer_v1(qu, w, "context2.", heads=8, dim_head=dh)     # :340
+    su2 = transformer_v1(torch.cat([su, ctx], dim=1), w, "context2.", heads=8, dim_head=dh)[:, :T]   # :347-348
+    su_pro = class_means(su2, support_labels)                          # :352-354
+    cum = otam_distance(su_pro, qu2, single_direct)                    # :360-375
+    # :381-383: per-class mean over the (already one-per-class) prototype columns, transposed back -> identity
+    return dict(qu_ctx=qu2, su_ctx=su2, su_pro=su_pro, logits=-cum.unsqueeze(0), class_logits=class_logits.unsqueeze(0))
+
+
+def fsar_loss_and_acc(logits, class_logits, target_labels, real_support, real_target, tasks_per_batch, cls_value):
+    """run/main_run.py:355-359 (MODEL.NAME == 'clipfsar'): (CE(logits) + USE_CLASSIFICATION_VALUE * CE(class_logits,
+    cat[real_support, real_target])) / TASKS_PER_BATCH with utils/utils.py:174-186 `loss` (sum over rows)."""
+    lg = logits[0].double()
+    ce = -(lg.log_softmax(-1).gather(1, target_labels.long().view(-1, 1)).squeeze(1)).sum()
+    cl = class_logits[0].double()
+    real = torch.cat([real_support, real_target]).long()
+    ce_cls = -(cl.log_softmax(-1).gather(1, real.view(-1, 1)).squeeze(1)).sum()
+    loss = (ce + cls_value * ce_cls) / tasks_per_batch
+    pred = lg.argmax(-1)
+    acc = (pred == target_labels.long()).double().mean()
+    return loss.float(), acc.float(), pred
+
+
 def loss_and_acc(logits, dists, target_labels, tasks_per_batch=16):
     """utils/utils.py:174-186 loss (CE summed over queries for the single logit sample), :259-264
     aggregate_accuracy, combined as run/main_run.py:390-392."""

@@ -224,13 +224,115 @@ def run_otam_grad_case(m):
                         shape=np.array([W, Q, T, D, seed], np.int32))
 
 
+FSAR_CASES = {
+    # name: (backbone, way, shot, qpc, T, n_test_cls, n_train_cls, head_only, single_direct, seed)
+    "fsar_head_5w5s_t8": ("ViT-B/16", 5, 5, 1, 8, 24, 30, True, False, 2002),
+    "fsar_head_5w3s_t8_d1024_q2": ("RN50", 5, 3, 2, 8, 10, 12, True, False, 2004),
+    "fsar_head_5w1s_t16_single": ("ViT-B/16", 5, 1, 1, 16, 24, 30, True, True, 2005),
+    "fsar_vit_2w1s_t2_p1": ("ViT-B/16", 2, 1, 1, 2, 24, 30, False, False, 2001),
+}
+FSAR_TASKS_PER_BATCH, FSAR_CLS_VALUE = 4, 3.0   # configs/clipfsar/ssv2_otam.yaml: TASKS_PER_BATCH, USE_CLASSIFICATION_VALUE
+
+
+def import_reference_fsar(m):
+    """models/model_clipfsar.py as shipped only binds load / tokenize / Transformer_v1 / cos_sim /
+    extract_class_indices when run as __main__ (its module-level imports are commented out, :8-9, :402-403); the
+    runner therefore cannot construct it unmodified.  The shim binds exactly those names from the reference's own
+    modules -- what the commented lines say -- before the class is used."""
+    import models.clip_fsar as clip_fsar
+    import models.myRes as myres
+    import models.model_clipfsar as f
+    f.load, f.tokenize = m.load, clip_fsar.tokenize
+    f.Transformer_v1, f.cos_sim, f.extract_class_indices = myres.Transformer_v1, myres.cos_sim, myres.extract_class_indices
+    return f
+
+
+def run_fsar_case(m, name):
+    backbone, way, shot, qpc, T, ncls, ntrain, head_only, single, seed = FSAR_CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    f = import_reference_fsar(m)
+    cfg = NS(MODEL=NS(BACKBONE=backbone), TRAIN=NS(CLASS_NAME=["run"]), TEST=NS(CLASS_NAME=["run"]),
+             DATA=NS(SEQ_LEN=T), DEVICE=NS(NUM_GPUS=1))
+    if single:
+        cfg.MODEL.SINGLE_DIRECT = True
+    torch.manual_seed(0)
+    with torch.no_grad():
+        net = f.CNN_OTAM_CLIPFSAR(cfg).eval()
+    w = O.make_fsar_weights(D, seed=0)
+    if not head_only:
+        w.update({k: v for k, v in O.make_weights(backbone, seed=0, protocol="P1").items() if k.startswith("backbone.")})
+    missing, unexpected = net.load_state_dict(w, strict=False)
+    assert not unexpected and all(k.startswith("backbone.") for k in missing) and (head_only or not missing), (missing, unexpected)
+    text_test = O.make_text_features(ncls, D, seed=0)
+    text_train = O.make_text_features(ntrain, D, seed=1)
+    net.text_features_test, net.text_features_train = text_test, text_train
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, "P1", images=not head_only)
+    st_ref = {}
+    ctx_calls = []
+    orig_ctx = net.context2.forward
+    net.context2.forward = lambda q, k, v: (ctx_calls.append(orig_ctx(q, k, v)), ctx_calls[-1])[1]
+    if head_only:
+        su, qu = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+        net.get_feats = lambda *a, **k: (su, qu, None)
+        ep["context_images"] = torch.zeros(1)
+        ep["target_images"] = torch.zeros(1)
+    else:
+        orig_gf = net.get_feats
+
+        def get_feats(*a, **k):
+            r = orig_gf(*a, **k)
+            st_ref["su"], st_ref["qu"] = r[0].clone(), r[1].clone()
+            return r
+        net.get_feats = get_feats
+    with torch.no_grad():
+        out = net(ep)
+        if not head_only:
+            su, qu = st_ref["su"], st_ref["qu"]
+            enc = O.vit_forward if backbone == "ViT-B/16" else O.rn50_forward
+            mine_su = enc(w, ep["context_images"]).reshape(-1, T, D)
+            mine_qu = enc(w, ep["target_images"]).reshape(-1, T, D)
+            assert rel(mine_su, su) < 2e-4 and rel(mine_qu, qu) < 2e-4
+        st = O.fsar_head_forward(w, text_test, text_train, su, qu, ep["context_labels"], ep["real_support_labels"],
+                                 ep["real_target_labels"], single)
+    st_ref["qu_ctx"], st_ref["su_ctx"] = ctx_calls[0], ctx_calls[1][:, :T]
+    st_ref["logits"], st_ref["class_logits"] = out["logits"], out["class_logits"]
+    for mod in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    import utils.utils as U
+    real = torch.cat([ep["real_support_labels"], ep["real_target_labels"]], 0).long()
+    loss_ref = (U.loss(out["logits"], ep["target_labels"].long(), "cpu")
+                + FSAR_CLS_VALUE * U.loss(out["class_logits"], real, "cpu")) / FSAR_TASKS_PER_BATCH   # main_run.py:355-356
+    acc_ref = U.aggregate_accuracy(out["logits"], ep["target_labels"])
+    loss, acc, pred = O.fsar_loss_and_acc(st["logits"], st["class_logits"], ep["target_labels"], ep["real_support_labels"],
+                                          ep["real_target_labels"], FSAR_TASKS_PER_BATCH, FSAR_CLS_VALUE)
+    st_ref["loss"], st_ref["acc"] = loss_ref.reshape(()), acc_ref.reshape(())
+    st["loss"], st["acc"] = loss.reshape(()), acc.reshape(())
+    st.update(su=su, qu=qu)
+    worst = 0.0
+    for k, v in st_ref.items():
+        r = rel(st[k].reshape(v.shape), v)
+        worst = max(worst, r)
+        assert r < 2e-4, "oracle disagrees with the reference on %s/%s: rel err %.3e" % (name, k, r)
+    lg = st_ref["logits"][0]
+    top2 = lg.topk(2, dim=-1).values
+    margin = top2[:, 0] - top2[:, 1]
+    print("%-28s oracle==reference (CNN_OTAM_CLIPFSAR), worst stage rel err %.2e | min top1-top2 margin %.4f, ref acc %.2f"
+          % (name, worst, float(margin.min()), float(acc_ref)))
+    gold = {k: v.detach().float().numpy() for k, v in st_ref.items()}
+    gold["pred"] = lg.argmax(-1).numpy()
+    gold["margin"] = margin.numpy()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
+
+
 if __name__ == "__main__":
     m = import_reference()
-    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"])
+    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES))
     for n in names:
         if n == "text":
             run_text_case(m)
         elif n == "otam_grad":
             run_otam_grad_case(m)
+        elif n in FSAR_CASES:
+            run_fsar_case(m, n)
         else:
             run_case(m, n)

@@ -58,3 +58,43 @@ def build_cuda_model(ci, max_episodes=1, precision="bf16"):
 def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ---- sibling head CLIP-FSAR: must match oracle/pin_against_reference.py::FSAR_CASES
+# name: (backbone, way, shot, qpc, T, n_test_cls, n_train_cls, head_only, single_direct, seed)
+FSAR_CASES = {
+    "fsar_head_5w5s_t8": ("ViT-B/16", 5, 5, 1, 8, 24, 30, True, False, 2002),
+    "fsar_head_5w3s_t8_d1024_q2": ("RN50", 5, 3, 2, 8, 10, 12, True, False, 2004),
+    "fsar_head_5w1s_t16_single": ("ViT-B/16", 5, 1, 1, 16, 24, 30, True, True, 2005),
+    "fsar_vit_2w1s_t2_p1": ("ViT-B/16", 2, 1, 1, 2, 24, 30, False, False, 2001),
+}
+FSAR_TASKS_PER_BATCH, FSAR_CLS_VALUE = 4, 3.0
+
+
+def fsar_case_inputs(name):
+    backbone, way, shot, qpc, T, ncls, ntrain, head_only, single, seed = FSAR_CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    w = O.make_fsar_weights(D, seed=0)
+    if not head_only:
+        w.update({k: v for k, v in O.make_weights(backbone, seed=0, protocol="P1").items() if k.startswith("backbone.")})
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, "P1", images=not head_only)
+    feats = None
+    if head_only:
+        feats = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+    return dict(backbone=backbone, way=way, shot=shot, qpc=qpc, T=T, D=D, weights=w, episode=ep, feats=feats,
+                text=O.make_text_features(ncls, D, seed=0), text_train=O.make_text_features(ntrain, D, seed=1),
+                single=single, head_only=head_only)
+
+
+def build_cuda_fsar_model(ci, max_episodes=1, precision="bf16"):
+    from clip_spm_b200 import CNN_OTAM_CLIPFSAR
+    from clip_spm_b200.config import make_cfg as _mk
+    cfg = _mk(ci["backbone"], ci["T"], ci["single"], ci["way"], params={}, tasks_per_batch=FSAR_TASKS_PER_BATCH,
+              cls_value=FSAR_CLS_VALUE)
+    net = CNN_OTAM_CLIPFSAR(cfg, text_features_test=ci["text"], text_features_train=ci["text_train"],
+                            max_episodes=max_episodes, precision=precision)
+    missing, unexpected = net.load_state_dict(ci["weights"], strict=False)
+    assert not unexpected, unexpected
+    if not ci["head_only"]:
+        assert not missing, missing
+    return net
