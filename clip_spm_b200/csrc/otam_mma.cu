@@ -18,7 +18,8 @@
 //
 // Operand path: every warp owns a K slice and feeds itself -- a private ring of cp.async stages (16 floats of every
 // row per stage), so a warp needs no block-wide barrier until its slice is done and keeps one stage in flight while
-// it computes on the other.  Fragment trick: a dot product does not care in which order k is visited, so lane (g, t)
+// it computes on the other.  16 warps per SM (128 registers each), as CTAs of 4 warps where the tile shape allows:
+// four independent CTAs per SM de-phase their load / MMA / reduce phases better than two of 8 warps (82 -> 76 us).  Fragment trick: a dot product does not care in which order k is visited, so lane (g, t)
 // reads ONE float2 -- columns 2t, 2t + 1 of an 8-float half stage of row g -- as its (k = t, k = t + 4) elements of
 // the k-step; A and B use the same permutation, and the 32 lanes read 256 contiguous bytes (no bank conflicts).
 #include "head_kernels.cuh"
@@ -53,25 +54,24 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 constexpr int NS = 2;        // ring stages per warp
 constexpr int STAGE_K = 16;  // floats of every row per stage (two k-steps)
 
-// MT x NT: m16 / n8 tiles per warp.  MG x NG x KG = 8 warps.  The CTA covers QG queries (rows = QG*T <= MG*MT*16)
+// MT x NT: m16 / n8 tiles per warp.  MG x NG x KG = NW warps (4 or 8; 16 warps per SM either way).  The CTA covers QG queries (rows = QG*T <= MG*MT*16)
 // against all W classes (columns = W*T <= NG*NT*8).
 template <int MT, int NT, int MG, int NG, int KG>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(32 * MG * NG * KG, 16 / (MG * NG * KG))
 cos_dist_mma_kernel(const float* __restrict__ sup, long long s_p, long long s_w, long long s_t,
                     const float* __restrict__ tgt, long long t_p, long long t_q, long long t_t, int W, int Q, int QG,
                     int T, int D, float* __restrict__ dist) {
-  static_assert(MG * NG * KG == 8, "8 warps");
+  constexpr int NW = MG * NG * KG;
+  static_assert(NW == 4 || NW == 8, "4 or 8 warps");
   constexpr int MP = MG * MT * 16, NP = NG * NT * 8;
   constexpr int R = MT * 16 + NT * 8;           // rows a warp stages: its A rows, then its B rows
   constexpr int STAGE = 2 * R * 8;              // floats per stage: [2 halves][R rows][8]
-  constexpr int RING = 8 * NS * STAGE, PART = KG * MP * NP;
+  constexpr int RING = NW * NS * STAGE, PART = KG * MP * NP;
   extern __shared__ __align__(16) float sm_om[];
-  float* ring = sm_om;                          // [8 warps][NS][STAGE]; reused as `part` once every slice is done
+  float* ring = sm_om;                          // [NW warps][NS][STAGE]; reused as `part` once every slice is done
   float* part = sm_om;                          // [KG][MP][NP] partial products of the K slices
   float* an = sm_om + (RING > PART ? RING : PART);   // [KG][MP] partial squared norms of the query frames
   float* bn = an + KG * MP;                     // [KG][NP] ... of the support frames
-  int* aoff = reinterpret_cast<int*>(bn + KG * NP);  // [MP] row offsets (floats) from the problem's base, -1 = no row
-  int* boff = aoff + MP;                        // [NP]
   const int p = blockIdx.y, q0 = blockIdx.x * QG;
   const int nq = min(QG, Q - q0);
   const int QT = nq * T, WT = W * T;
@@ -79,30 +79,33 @@ cos_dist_mma_kernel(const float* __restrict__ sup, long long s_p, long long s_w,
   const int kg = warp % KG, ng = (warp / KG) % NG, mg = warp / (KG * NG);
   const float* tgt_p = tgt + p * t_p + q0 * t_q;
   const float* sup_p = sup + p * s_p;
-  for (int i = threadIdx.x; i < MP + NP; i += blockDim.x) {
-    if (i < MP) aoff[i] = i < QT ? (i / T) * (int)t_q + (i % T) * (int)t_t : -1;
-    else { const int c = i - MP; boff[c] = c < WT ? (c / T) * (int)s_w + (c % T) * (int)s_t : -1; }
-  }
-  __syncthreads();
 
-  // this lane's share of a stage: piece x = it*32 + lane -> row x/4, 16-byte piece x%4 of the row's 64 bytes.
-  // Rows past the end are not loaded: whatever the ring holds there only reaches result rows/columns nobody reads.
-  constexpr int NPIECE = (R * 4 + 31) / 32;
+  // This lane's share of a stage: piece `it` = 16 bytes (column quarter c = lane & 3) of staged row it*8 + (lane >> 2).
+  // Staged rows 0 .. MT*16-1 are the warp's A rows, the rest its B rows; MT*16 is a multiple of 8, so whether a piece
+  // is A or B depends on `it` alone.  Offsets (floats, from the problem's base) are resolved once; rows past the end
+  // are not loaded: whatever the ring holds there only reaches result rows/columns nobody reads.
+  constexpr int NPIECE = R / 8;
+  int goff[NPIECE];
+#pragma unroll
+  for (int it = 0; it < NPIECE; ++it) {
+    if (it < MT * 2) {
+      const int r = mg * MT * 16 + it * 8 + g;
+      goff[it] = r < QT ? (r / T) * (int)t_q + (r % T) * (int)t_t + t * 4 : -1;
+    } else {
+      const int c = ng * NT * 8 + (it - MT * 2) * 8 + g;
+      goff[it] = c < WT ? (c / T) * (int)s_w + (c % T) * (int)s_t + t * 4 : -1;
+    }
+  }
   float* my_ring = ring + warp * NS * STAGE;
+  // destination of piece 0 inside a stage: half (t >> 1), row g, 16-byte part (t & 1); piece `it` is 8 rows further
+  const int dst0 = (t >> 1) * (R * 8) + g * 8 + (t & 1) * 4;
   const int k_begin = kg * (D / KG), n_stage = (D / KG) / STAGE_K;
   auto issue = [&](int stage_idx) {
-    float* dst = my_ring + (stage_idx % NS) * STAGE;
+    float* dst = my_ring + (stage_idx % NS) * STAGE + dst0;
     const int kc = k_begin + stage_idx * STAGE_K;
 #pragma unroll
-    for (int it = 0; it < NPIECE; ++it) {
-      const int x = it * 32 + lane, row = x >> 2, c = x & 3;
-      if (row < R) {
-        const bool is_a = row < MT * 16;
-        const int off = is_a ? aoff[mg * MT * 16 + row] : boff[ng * NT * 8 + row - MT * 16];
-        if (off >= 0)
-          cp_async16(dst + (c >> 1) * (R * 8) + row * 8 + (c & 1) * 4, (is_a ? tgt_p : sup_p) + off + kc + c * 4);
-      }
-    }
+    for (int it = 0; it < NPIECE; ++it)
+      if (goff[it] >= 0) cp_async16(dst + it * 64, (it < MT * 2 ? tgt_p : sup_p) + goff[it] + kc);
     cp_async_commit();
   };
 
@@ -201,15 +204,22 @@ cos_dist_mma_kernel(const float* __restrict__ sup, long long s_p, long long s_w,
     v[0] = sqrtf(s);
   }
   __syncthreads();
-  // dist[p][q][w][tq][ts] = 1 - cos_sim  (myRes.py:756-765: x.y / (|x||y| + 0.01)); consecutive threads walk ts
+  // dist[p][q][w][tq][ts] = 1 - cos_sim  (myRes.py:756-765: x.y / (|x||y| + 0.01)).  A warp per (query, class) pair,
+  // lanes walk the pair's T*T table in storage order; (tq, ts) advance incrementally (no division per element).
   float* dp = dist + ((long long)p * Q + q0) * W * T * T;
-  for (int i = threadIdx.x; i < QT * WT; i += blockDim.x) {
-    const int ts = i % T, tq = (i / T) % T, w = (i / (T * T)) % W, q = i / (T * T * W);
-    const int m = q * T + tq, n = w * T + ts;
-    float s = part[m * NP + n];
+  const int TT = T * T, step_q = 32 / T, step_s = 32 % T;
+  for (int pair = warp; pair < nq * W; pair += NW) {
+    const int q = pair / W, w = pair - q * W;
+    int tq = lane / T, ts = lane - tq * T;
+    for (int c = lane; c < TT; c += 32) {
+      const int m = q * T + tq, n = w * T + ts;
+      float s = part[m * NP + n];
 #pragma unroll
-    for (int k = 1; k < KG; ++k) s += part[k * MP * NP + m * NP + n];
-    dp[i] = 1.f - s / (an[m] * bn[n] + 0.01f);
+      for (int k = 1; k < KG; ++k) s += part[k * MP * NP + m * NP + n];
+      dp[pair * TT + c] = 1.f - s / (an[m] * bn[n] + 0.01f);
+      tq += step_q; ts += step_s;
+      if (ts >= T) { ts -= T; ++tq; }
+    }
   }
 }
 
@@ -269,9 +279,10 @@ template <int MT, int NT, int MG, int NG, int KG>
 int launch(cudaStream_t st, const float* sup, long long s_p, long long s_w, long long s_t, const float* tgt,
            long long t_p, long long t_q, long long t_t, int P, int W, int Q, int QG, int T, int D, float* dist) {
   constexpr int MP = MG * MT * 16, NP = NG * NT * 8, R = MT * 16 + NT * 8;
-  constexpr int RING = 8 * NS * 2 * R * 8, PART = KG * MP * NP;
-  constexpr size_t smem = (size_t)((RING > PART ? RING : PART) + KG * MP + KG * NP + MP + NP) * sizeof(float);
-  static_assert(smem <= 113 * 1024, "two CTAs per SM");
+  constexpr int NW = MG * NG * KG;
+  constexpr int RING = NW * NS * 2 * R * 8, PART = KG * MP * NP;
+  constexpr size_t smem = (size_t)((RING > PART ? RING : PART) + KG * MP + KG * NP) * sizeof(float);
+  static_assert(smem * (16 / NW) <= 226 * 1024, "16 warps per SM");
   if ((D / KG) % STAGE_K != 0) return -3;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
@@ -281,7 +292,7 @@ int launch(cudaStream_t st, const float* sup, long long s_p, long long s_w, long
     attr_set = true;
   }
   dim3 grid((Q + QG - 1) / QG, P);
-  cos_dist_mma_kernel<MT, NT, MG, NG, KG><<<grid, 256, smem, st>>>(sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, W, Q, QG, T,
+  cos_dist_mma_kernel<MT, NT, MG, NG, KG><<<grid, 32 * NW, smem, st>>>(sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, W, Q, QG, T,
                                                                   D, dist);
   cudaError_t e = cudaGetLastError();
   count_launch();
@@ -322,7 +333,7 @@ int k_otam_mma(cudaStream_t st, const float* sup, long long s_p, long long s_w, 
   r = launch<MT, NT, MG, NG, KG>(st, sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, P, W, Q, QG, T, D, dist)
   if (WT <= 40) {
     if (QT <= 16) SPM_OTAM_MMA(1, 5, 1, 1, 8);
-    else if (QT <= 48) SPM_OTAM_MMA(3, 5, 1, 1, 8);
+    else if (QT <= 48) SPM_OTAM_MMA(3, 5, 1, 1, 4);   // K slices of 1, 2, 4, 8 warps measured within 5 % of each other
     else SPM_OTAM_MMA(3, 5, 2, 1, 4);
   } else {
     if (QT <= 16) SPM_OTAM_MMA(1, 5, 1, 2, 4);
