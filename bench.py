@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--episodes-per-step", type=int, default=8)
+    ap.add_argument("--episodes-per-step", type=int, default=16)
     ap.add_argument("--episodes-per-call", type=int, default=8)
     ap.add_argument("--ref-frames", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
