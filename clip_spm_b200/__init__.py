@@ -2,8 +2,8 @@
 (reference: models/model_clipspm.py::CNN.forward), behind a C-ABI shared library."""
 from . import _lib  # noqa: F401
 from .model import CNN  # noqa: F401
-from .model_clipfsar import CNN_OTAM_CLIPFSAR  # noqa: F401
+from .model_clipfsar import CNN_OTAM_CLIPFSAR, CNN_STEN  # noqa: F401
 from .text import TextTower  # noqa: F401
 from .tokenizer import ClipTokenizer  # noqa: F401
 
-__all__ = ["CNN", "CNN_OTAM_CLIPFSAR", "TextTower", "ClipTokenizer", "_lib"]
+__all__ = ["CNN", "CNN_OTAM_CLIPFSAR", "CNN_STEN", "TextTower", "ClipTokenizer", "_lib"]

@@ -186,3 +186,125 @@ int k_fsar_class_ce_add(cudaStream_t st, const float* cls, const float* real_s, 
 }
 
 }  // namespace spm
+
+// ======================================================================================================
+// Sibling head STEN as shipped (models/model_sten.py:62-113): no learned head at all --
+//   su_f, qu_f = mean over the T frames; per class (sorted distinct support labels) the mean support feature and the
+//   mean prompt; logits[q, w] = softmax_w(cos_sim(qu_f, t_f))[q, w] * softmax_w(cos_sim(qu_f, su_f))[q, w]
+// ======================================================================================================
+namespace spm {
+
+// out[v, :] = mean_t X[v, t, :]
+__global__ void sten_frame_mean_kernel(const float* __restrict__ X, int T, int D, float* __restrict__ out) {
+  const long long v = blockIdx.x;
+  const float4* x = reinterpret_cast<const float4*>(X + v * T * D);
+  const int d4 = D / 4;
+  const float r = 1.f / (float)T;
+  for (int c = threadIdx.x; c < d4; c += blockDim.x) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+      const float4 q = x[(long long)t * d4 + c];
+      a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+    }
+    reinterpret_cast<float4*>(out + v * D)[c] = make_float4(a.x * r, a.y * r, a.z * r, a.w * r);
+  }
+}
+
+// One CTA per episode.  m [E, S+Q, D] frame means (supports first).  proto [E, W, 2, D] scratch: class means of the
+// support features and of their prompts.  negsim [E, Q, W] = -(softmax(cos qt) * softmax(cos qs)) (the finalize
+// kernel negates its input).
+__global__ void __launch_bounds__(256)
+sten_sim_kernel(const float* __restrict__ m, const float* __restrict__ text, int n_cls,
+                const float* __restrict__ labels, const float* __restrict__ real_s, int S, int Q, int W, int D,
+                float* __restrict__ proto, float* __restrict__ negsim, int* __restrict__ err_flag) {
+  __shared__ int cls[256];
+  __shared__ float pn[64];        // [W][2] prototype norms
+  __shared__ float cs[4096];      // [Q][W][2] cosines (Q*W <= 2048, checked by the launcher)
+  const int e = blockIdx.x, N = S + Q, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* lab = labels + (long long)e * S;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {   // rank among the sorted distinct labels (torch.unique, :97)
+    const float me = lab[s];
+    int rank = 0;
+    for (int j = 0; j < S; ++j) {
+      const float o = lab[j];
+      if (o < me) {
+        bool first = true;
+        for (int k = 0; k < j; ++k) first = first && (lab[k] != o);
+        rank += first ? 1 : 0;
+      }
+    }
+    cls[s] = rank;
+  }
+  __syncthreads();
+  int Wd = 0;
+  for (int s = 0; s < S; ++s) Wd = max(Wd, cls[s] + 1);
+  if (Wd != W) {
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  float* pr = proto + (long long)e * W * 2 * D;
+  const float* me_ = m + (long long)e * N * D;
+  // class means (:98-102), one warp per class; the norms fall out of the same pass
+  for (int w = warp; w < W; w += nw) {
+    float ns = 0.f, nt = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      float a = 0.f, b = 0.f;
+      int cnt = 0;
+      for (int s = 0; s < S; ++s)
+        if (cls[s] == w) {
+          a += me_[(long long)s * D + d];
+          const int c = min(max((int)real_s[(long long)e * S + s], 0), n_cls - 1);
+          b += text[(long long)c * D + d];
+          ++cnt;
+        }
+      a /= (float)cnt; b /= (float)cnt;
+      pr[((long long)w * 2 + 0) * D + d] = a;
+      pr[((long long)w * 2 + 1) * D + d] = b;
+      ns = fmaf(a, a, ns); nt = fmaf(b, b, nt);
+    }
+    ns = warp_sum_f(ns); nt = warp_sum_f(nt);
+    if (lane == 0) { pn[w * 2] = sqrtf(ns); pn[w * 2 + 1] = sqrtf(nt); }
+  }
+  __syncthreads();   // the prototypes were written by this CTA: visible to it after the barrier
+  // cosines (myRes.py:756-765), one warp per (query, class)
+  for (int i = warp; i < Q * W; i += nw) {
+    const int q = i / W, w = i - q * W;
+    const float* x = me_ + (long long)(S + q) * D;
+    float ds = 0.f, dt = 0.f, xx = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float xv = x[d];
+      ds = fmaf(xv, pr[((long long)w * 2 + 0) * D + d], ds);
+      dt = fmaf(xv, pr[((long long)w * 2 + 1) * D + d], dt);
+      xx = fmaf(xv, xv, xx);
+    }
+    ds = warp_sum_f(ds); dt = warp_sum_f(dt); xx = warp_sum_f(xx);
+    if (lane == 0) {
+      const float xn = sqrtf(xx);
+      cs[i * 2 + 0] = ds / (xn * pn[w * 2] + 0.01f);
+      cs[i * 2 + 1] = dt / (xn * pn[w * 2 + 1] + 0.01f);
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < Q; q += blockDim.x) {   // the two softmaxes over the classes, multiplied (:104-106)
+    float ms = -INFINITY, mt = -INFINITY;
+    for (int w = 0; w < W; ++w) { ms = fmaxf(ms, cs[(q * W + w) * 2]); mt = fmaxf(mt, cs[(q * W + w) * 2 + 1]); }
+    float ss = 0.f, st = 0.f;
+    for (int w = 0; w < W; ++w) { ss += expf(cs[(q * W + w) * 2] - ms); st += expf(cs[(q * W + w) * 2 + 1] - mt); }
+    for (int w = 0; w < W; ++w)
+      negsim[((long long)e * Q + q) * W + w] =
+          -((expf(cs[(q * W + w) * 2 + 1] - mt) / st) * (expf(cs[(q * W + w) * 2] - ms) / ss));
+  }
+}
+
+int k_sten_head(cudaStream_t st, const float* X, const float* text, int n_cls, const float* labels,
+                const float* real_s, int E, int S, int Q, int W, int T, int D, float* frame_mean, float* proto,
+                float* negsim, int* err_flag) {
+  if (S > 256 || Q * W > 2048 || W > 32) return -2;
+  sten_frame_mean_kernel<<<E * (S + Q), 128, 0, st>>>(X, T, D, frame_mean);
+  SPM_LAUNCH_CHECK();
+  sten_sim_kernel<<<E, 256, 0, st>>>(frame_mean, text, n_cls, labels, real_s, S, Q, W, D, proto, negsim, err_flag);
+  SPM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace spm

@@ -34,6 +34,11 @@ int k_fsar_class_logits(cudaStream_t st, const float* X, const float* text_train
                         int T, int D, float* out);
 int k_fsar_class_ce_add(cudaStream_t st, const float* cls, const float* real_s, const float* real_t, int E, int S, int Q,
                         int n_cls, float coef, float* loss);
+// sibling head STEN as shipped (models/model_sten.py:62-113): frame means, class-mean prototypes of features and
+// prompts, product of the two cosine softmaxes; negsim = -logits (k_finalize negates)
+int k_sten_head(cudaStream_t st, const float* X, const float* text, int n_cls, const float* labels,
+                const float* real_s, int E, int S, int Q, int W, int T, int D, float* frame_mean, float* proto,
+                float* negsim, int* err_flag);
 int k_otam_init();
 // out[p,q,w] = beta*out + alpha * otam(support[p,w,:,:], target[p,q,:,:]); element (p,w,t,d) of the support set is at
 // sup + p*s_p + w*s_w + t*s_t + d (strides in floats), likewise for the target set.

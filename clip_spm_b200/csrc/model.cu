@@ -186,6 +186,14 @@ struct spm_handle {
   // block the enqueueing thread until the chunk has finished and starve the GPU of the next chunk's launches
   float* pin_res = nullptr;
   long long pin_cap = 0;
+  // spm_eval_host_set_next: the first chunk of the NEXT spm_eval_host call is copied to these buffers behind the
+  // current call's own copies, so that call starts computing at once (its one exposed H2D copy disappears)
+  const void *next_su = nullptr, *next_qu = nullptr;   // hint given by the caller, consumed by the next call
+  uint8_t *pf_su = nullptr, *pf_qu = nullptr;
+  long long pf_cap_s = 0, pf_cap_q = 0;
+  const void *pf_src_su = nullptr, *pf_src_qu = nullptr;   // what the buffers hold (null = nothing)
+  long long pf_bytes_s = 0, pf_bytes_q = 0;
+  cudaEvent_t pf_event = nullptr;
 };
 
 namespace spm {
@@ -766,6 +774,23 @@ int run_ctx(spm_handle* h, cudaStream_t st, const CtxPlan& p, const CtxW& w, int
   return 0;
 }
 
+// STEN head as shipped (models/model_sten.py:62-113) on frame features in h->X [E, N, T, D]; no learned parameters
+int sten_head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const float* labels, const float* real_s,
+                  const long long* target_labels, float tasks_per_batch, float* logits, float* dists, float* loss,
+                  float* acc, int* pred) {
+  SPM_CHECK(h->text_set, "head: text features not set (spm_set_text_features)");
+  SPM_TRY(ensure_head_workspace(h, E, S, Q, W));
+  const int T = h->cfg.seq_len, D = h->D;
+  // scratch: NEWM [V, D] frame means, SUPRO [E, W, T, D] >= [E, W, 2, D] prototypes, ACC [E, Q, W]
+  SPM_KERNEL(k_sten_head(st, h->X, h->text, h->n_cls, labels, real_s, E, S, Q, W, T, D, h->NEWM, h->SUPRO, h->ACC,
+                         h->err_flag));
+  SPM_CUDA(cudaMemsetAsync(h->D3, 0, (size_t)E * W * sizeof(float), st));
+  SPM_CUDA(cudaMemsetAsync(dists, 0, (size_t)E * sizeof(float), st));
+  SPM_KERNEL(k_finalize(st, h->ACC, h->D3, E, Q, W, target_labels, tasks_per_batch, dists, logits, loss, acc, pred,
+                        h->err_flag));
+  return 0;
+}
+
 // CLIP-FSAR head (models/model_clipfsar.py:325-383) on frame features in h->X [E, N, T, D]:
 //   target  = context2(target)                       self-attention over the T frames of each query video
 //   support = context2(cat[support, prompt])[:, :T]  T frames + the class prompt of the video's real label
@@ -827,6 +852,8 @@ int fsar_head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, co
 int head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const float* labels, const float* real_s,
              const float* real_t, const long long* target_labels, float tasks_per_batch, float* logits, float* dists,
              float* loss, float* acc, int* pred) {
+  if (h->cfg.head == SPM_HEAD_STEN)
+    return sten_head_run(h, st, E, S, Q, W, labels, real_s, target_labels, tasks_per_batch, logits, dists, loss, acc, pred);
   if (h->cfg.head == SPM_HEAD_CLIPFSAR)
     return fsar_head_run(h, st, E, S, Q, W, labels, real_s, real_t, target_labels, tasks_per_batch, logits, dists, loss,
                          acc, pred);
@@ -1015,7 +1042,10 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   SPM_CHECK(cfg->backbone == SPM_BACKBONE_VIT_B16 || cfg->backbone == SPM_BACKBONE_RN50, "spm_create: unknown backbone");
   SPM_CHECK(cfg->seq_len >= 2 && cfg->seq_len <= 30, "spm_create: seq_len must be in [2, 30]");
   SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->precision == SPM_PRECISION_FP32, "spm_create: unknown precision");
-  SPM_CHECK(cfg->head == SPM_HEAD_CLIPSPM || cfg->head == SPM_HEAD_CLIPFSAR, "spm_create: unknown head");
+  SPM_CHECK(cfg->head == SPM_HEAD_CLIPSPM || cfg->head == SPM_HEAD_CLIPFSAR || cfg->head == SPM_HEAD_STEN,
+            "spm_create: unknown head");
+  SPM_CHECK(cfg->head != SPM_HEAD_STEN || cfg->seq_len == 8,
+            "spm_create: the STEN head reshapes to 8 frames per video (models/model_sten.py:65-66)");
   SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->backbone == SPM_BACKBONE_VIT_B16,
             "spm_create: SPM_PRECISION_FP32 is implemented for the ViT-B/16 backbone only");
   int ndev = 0;
@@ -1068,6 +1098,7 @@ int spm_destroy(spm_handle* h) {
   if (h->head_stream) cudaStreamDestroy(h->head_stream);
   if (h->head_done) cudaEventDestroy(h->head_done);
   for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
+  if (h->pf_event) cudaEventDestroy(h->pf_event);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
   delete h;
@@ -1089,7 +1120,8 @@ int spm_load_weights(spm_handle* h, void* stream, int n, const char* const* name
     SPM_TRY(rn50_create(&h->rn50, st, h->sms, getter));
   }
   if (h->cfg.head == SPM_HEAD_CLIPFSAR) SPM_TRY(load_head_fsar(h, st, wt));
-  else SPM_TRY(load_head(h, st, wt));
+  else if (h->cfg.head == SPM_HEAD_CLIPSPM) SPM_TRY(load_head(h, st, wt));
+  // SPM_HEAD_STEN: the shipped model has no parameters besides the backbone
   SPM_CUDA(cudaStreamSynchronize(st));
   h->weights_loaded = true;
   return 0;
@@ -1225,12 +1257,29 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
     SPM_TRY(dalloc_t(h, &s.pred, (long long)R * Q));
     h->stage_cap_frames_s = R * fs; h->stage_cap_frames_q = R * fq;
   }
+  // prefetch buffers for the first chunk of the next call (allocated before anything is enqueued: cudaMalloc syncs)
+  // (a whole compute chunk: with its copy out of the way the call can run full-size chunks from the start)
+  const int first_n = std::min(EC, n_episodes);
+  const long long pf_s = (long long)first_n * fs * frame_bytes, pf_q = (long long)first_n * fq * frame_bytes;
+  const void *hint_su = h->next_su, *hint_qu = h->next_qu;
+  h->next_su = h->next_qu = nullptr;   // a hint is consumed by exactly one call
+  if (hint_su != nullptr && (pf_s > h->pf_cap_s || pf_q > h->pf_cap_q)) {
+    SPM_CUDA(cudaStreamSynchronize(h->copy_stream));   // nobody may still be writing the old buffers
+    SPM_TRY(dalloc_t(h, &h->pf_su, pf_s));
+    SPM_TRY(dalloc_t(h, &h->pf_qu, pf_q));
+    h->pf_cap_s = pf_s; h->pf_cap_q = pf_q;
+    h->pf_src_su = h->pf_src_qu = nullptr;
+  }
+  if (h->pf_event == nullptr) SPM_CUDA(cudaEventCreateWithFlags(&h->pf_event, cudaEventDisableTiming));
+  // does the prefetch made by the previous call hold this call's first chunk?
+  const bool use_pf = h->pf_src_su == (const void*)su_h && h->pf_src_qu == (const void*)qu_h && h->pf_bytes_s == pf_s &&
+                      h->pf_bytes_q == pf_q && su_h != nullptr;
   // Chunk schedule.  The H2D copy of a chunk can only overlap the compute of EARLIER chunks, so the first chunks
   // are small (1, 1, 2, 4, ... up to EC when EC is a power of two: offsets stay aligned, a chunk never wraps the
   // ring) -- only one episode's copy is exposed per call instead of EC episodes'.
   std::vector<int> starts;
   {
-    const bool pow2 = (EC & (EC - 1)) == 0;
+    const bool pow2 = (EC & (EC - 1)) == 0 && !use_pf;   // first chunk prefetched: full-size chunks throughout
     int e = 0, sz = pow2 ? 1 : EC;
     bool first = true;
     while (e < n_episodes) {
@@ -1267,10 +1316,17 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
     const int e0 = starts[c], E = starts[c + 1] - e0, slot = e0 % R;
     // ring slot reuse: the chunk that last used these slots must have been consumed
     if (e0 + E - 1 >= R) SPM_CUDA(cudaStreamWaitEvent(cs, h->ev_done[chunk_of[e0 + E - 1 - R]], 0));
-    SPM_CUDA(cudaMemcpyAsync(s.su + slot * fs * frame_bytes, su_h + e0 * fs * frame_bytes,
-                             (size_t)(E * fs * frame_bytes), cudaMemcpyHostToDevice, cs));
-    SPM_CUDA(cudaMemcpyAsync(s.qu + slot * fq * frame_bytes, qu_h + e0 * fq * frame_bytes,
-                             (size_t)(E * fq * frame_bytes), cudaMemcpyHostToDevice, cs));
+    const bool from_pf = use_pf && c == 0 && E == first_n;   // this chunk's frames were copied by the previous call
+    const uint8_t* su_d = from_pf ? h->pf_su : s.su + slot * fs * frame_bytes;
+    const uint8_t* qu_d = from_pf ? h->pf_qu : s.qu + slot * fq * frame_bytes;
+    if (from_pf) {
+      SPM_CUDA(cudaStreamWaitEvent(ks, h->pf_event, 0));
+    } else {
+      SPM_CUDA(cudaMemcpyAsync(s.su + slot * fs * frame_bytes, su_h + e0 * fs * frame_bytes,
+                               (size_t)(E * fs * frame_bytes), cudaMemcpyHostToDevice, cs));
+      SPM_CUDA(cudaMemcpyAsync(s.qu + slot * fq * frame_bytes, qu_h + e0 * fq * frame_bytes,
+                               (size_t)(E * fq * frame_bytes), cudaMemcpyHostToDevice, cs));
+    }
     SPM_CUDA(cudaMemcpyAsync(s.lab + (long long)slot * S, lab_h + (long long)e0 * S, (size_t)E * S * 4, cudaMemcpyHostToDevice, cs));
     SPM_CUDA(cudaMemcpyAsync(s.rs + (long long)slot * S, rs_h + (long long)e0 * S, (size_t)E * S * 4, cudaMemcpyHostToDevice, cs));
     SPM_CUDA(cudaMemcpyAsync(s.rt + (long long)slot * Q, rt_h + (long long)e0 * Q, (size_t)E * Q * 4, cudaMemcpyHostToDevice, cs));
@@ -1278,7 +1334,7 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
     SPM_CUDA(cudaEventRecord(h->ev_copied[c], cs));
     SPM_CUDA(cudaStreamWaitEvent(ks, h->ev_copied[c], 0));
     float* lg = s.logits + (long long)slot * Q * W;
-    SPM_TRY(forward_impl(h, ks, E, S, Q, W, s.su + slot * fs * frame_bytes, s.qu + slot * fq * frame_bytes,
+    SPM_TRY(forward_impl(h, ks, E, S, Q, W, su_d, qu_d,
                          s.lab + (long long)slot * S, s.rs + (long long)slot * S, s.rt + (long long)slot * Q,
                          s.tl + (long long)slot * Q, tasks_per_batch, lg, s.dists + slot, s.loss + slot, s.acc + slot,
                          s.pred + (long long)slot * Q, img_h, img_w));
@@ -1289,6 +1345,17 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
     SPM_CUDA(cudaMemcpyAsync(p_pred + (long long)e0 * Q, s.pred + (long long)slot * Q, (size_t)E * Q * 4, cudaMemcpyDeviceToHost, ks));
     SPM_CUDA(cudaEventRecord(h->ev_done[c], ks));
   }
+  // Behind this call's own copies (same FIFO copy stream): the first chunk of the next call, while the last chunks of
+  // this one compute.  The buffers may still be read by this call's chunk 0.
+  h->pf_src_su = h->pf_src_qu = nullptr;
+  if (hint_su != nullptr && hint_qu != nullptr) {
+    SPM_CUDA(cudaStreamWaitEvent(cs, h->ev_done[0], 0));
+    SPM_CUDA(cudaMemcpyAsync(h->pf_su, hint_su, (size_t)pf_s, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaMemcpyAsync(h->pf_qu, hint_qu, (size_t)pf_q, cudaMemcpyHostToDevice, cs));
+    SPM_CUDA(cudaEventRecord(h->pf_event, cs));
+    h->pf_src_su = hint_su; h->pf_src_qu = hint_qu;
+    h->pf_bytes_s = pf_s; h->pf_bytes_q = pf_q;
+  }
   SPM_CUDA(cudaStreamSynchronize(ks));
   if (logits_h) memcpy(logits_h, p_logits, (size_t)n_episodes * Q * W * 4);
   if (dists_h) memcpy(dists_h, p_dists, (size_t)n_episodes * 4);
@@ -1298,6 +1365,13 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
   int flag = 0;
   SPM_CUDA(cudaMemcpy(&flag, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
   SPM_CHECK(flag == 0, "spm_eval_host: an episode's number of distinct support labels differs from `W`");
+  return 0;
+}
+
+int spm_eval_host_set_next(spm_handle* h, const void* next_support_host, const void* next_target_host) {
+  SPM_CHECK(h != nullptr, "spm_eval_host_set_next: null handle");
+  h->next_su = next_support_host;
+  h->next_qu = next_target_host;
   return 0;
 }
 

@@ -38,6 +38,8 @@ def _param_shapes(backbone, D, params, head="clipspm"):
     tower of models/clip_fsar.py:549-689), written out here from the module definitions."""
     if head == "clipfsar":
         s = _fsar_head_shapes(D)
+    elif head == "sten":
+        s = {}   # models/model_sten.py: every head module is commented out, only the backbone has parameters
     else:
         s = _spm_head_shapes(D, params)
     s.update(_backbone_shapes(backbone))
@@ -182,7 +184,8 @@ class CNN(nn.Module):
                 _register(self, name, torch.zeros(shape) if name.endswith("mean") else torch.ones(shape), buffer=True)
             else:
                 _register(self, name, torch.zeros(shape))
-        self.scale.data.fill_(1.0)
+        if hasattr(self, "scale"):
+            self.scale.data.fill_(1.0)
         if hasattr(self, "mo_alpha1"):
             self.mo_alpha1.data.fill_(1.0)
         self.text_features_test = text_features_test
@@ -254,7 +257,7 @@ class CNN(nn.Module):
             negative_slope=float(self.params.get("negative_slope", 0.0)), alpha=float(self.params.get("alpha", 0.0)),
             single_direct=int(self.single_direct), precision=0 if self.precision == "bf16" else 1,
             max_episodes=self.max_episodes, max_support=0, max_query=0, max_way=0,
-            head=1 if self.HEAD == "clipfsar" else 0, cls_value=self.cls_value)
+            head={"clipspm": 0, "clipfsar": 1, "sten": 2}[self.HEAD], cls_value=self.cls_value)
         h = ctypes.c_void_p()
         with torch.cuda.device(self._dev):
             _lib.check(lib.spm_create(ctypes.byref(c), ctypes.byref(h)))
@@ -360,13 +363,22 @@ class CNN(nn.Module):
                                     inputs["target_labels"])
         return out["loss"][0], out["acc"][0]
 
+    def _set_next(self, lib, h, next_images):
+        """next_images = (context_images, target_images) host tensors of the NEXT evaluate_host call (a prefetching
+        DataLoader knows them): their first chunk is copied to the device while this call's tail computes."""
+        if next_images is not None:
+            a, b = next_images
+            assert not a.is_cuda and not b.is_cuda and a.is_contiguous() and b.is_contiguous()
+            _lib.check(lib.spm_eval_host_set_next(h, _p(a), _p(b)))
+
     def evaluate_host(self, context_images, context_labels, target_images, real_support_labels, real_target_labels,
-                      target_labels, n_episodes, way):
+                      target_labels, n_episodes, way, next_images=None):
         """Episodes in HOST memory (pinned for overlap): chunked H2D on a copy stream overlapped with compute
         (spm_eval_host); returns host tensors.  This is the call the end-to-end benchmark times."""
         h = self._handle()
         self._text()
         lib = _lib.load()
+        self._set_next(lib, h, next_images)
         E, T = int(n_episodes), self.seq_len
         S, Q, W = context_labels.numel() // E, real_target_labels.numel() // E, int(way)
         for t in (context_images, target_images, context_labels, real_support_labels, real_target_labels):
@@ -381,13 +393,14 @@ class CNN(nn.Module):
         return dict(logits=logits, dists=dists, loss=loss, acc=acc, pred=pred)
 
     def evaluate_host_u8(self, context_frames, context_labels, target_frames, real_support_labels,
-                         real_target_labels, target_labels, n_episodes, way):
+                         real_target_labels, target_labels, n_episodes, way, next_images=None):
         """evaluate_host on DECODED frames: uint8 [E*S*T, H, W, 3] / [E*Q*T, H, W, 3] host tensors (what the data
         loader holds before its PIL Resize/CenterCrop/ToTensor chain, video_reader.py:265-272).  The transform runs
         on the GPU, bit-exact with that chain; host->device traffic drops from 602 KB to H*W*3 bytes per frame."""
         h = self._handle()
         self._text()
         lib = _lib.load()
+        self._set_next(lib, h, next_images)
         E = int(n_episodes)
         S, Q, W = context_labels.numel() // E, real_target_labels.numel() // E, int(way)
         for t in (context_frames, target_frames):

@@ -71,3 +71,17 @@ class CNN_OTAM_CLIPFSAR(CNN):
             E = int(n_episodes)
             out["class_logits"] = self._class_logits(E, (context_labels.numel() + real_target_labels.numel()) // E)
         return out
+
+
+class CNN_STEN(CNN):
+    """models/model_sten.py:11 (class CNN_OTAM_CLIPFSAR of that file, cfg.MODEL.NAME == 'sten', run/main_run.py:127-128) as
+    shipped: frame features averaged over the 8 frames, class-mean support features and prompts, logits =
+    softmax(cos_sim(query, prompts)) * softmax(cos_sim(query, support prototypes)) (:97-108).  No parameters besides
+    `backbone.*`; forward returns {"logits": [1,Q,W]}; loss / accuracy are the runner's generic branch
+    (run/main_run.py:394-396)."""
+    HEAD = "sten"
+
+    def forward(self, inputs):
+        out = self.forward_episodes(inputs["context_images"], inputs["context_labels"], inputs["target_images"],
+                                    inputs["real_support_labels"], inputs["real_target_labels"], n_episodes=1)
+        return {"logits": out["logits"][0].unsqueeze(0)}

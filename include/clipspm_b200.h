@@ -14,6 +14,7 @@
  *   spm_forward                   models/model_clipspm.py:111-144  CNN.forward(inputs) -> logits, dists
  *   spm_eval                      run/main_run.py:390-392 + utils/utils.py:174-186,259-264 (loss, accuracy)
  *   spm_eval_host                 run/main_run.py:266-279 (prepare_task H2D + forward + loss/acc + .item())
+ *   spm_eval_host_set_next        run/main_run.py:71 (DataLoader prefetch: the next batch is known while this one runs)
  *   spm_encode_frames             models/clip_fsar.py:672-689 VisionTransformer.forward / :593-608 ModifiedResNet
  *   spm_head                      models/model_clipspm.py:125-143  (everything after get_feats)
  *   spm_otam_distance             models/model_clipspm.py:348-362 + models/myRes.py:756-765,821-855
@@ -40,7 +41,7 @@ enum { SPM_PRECISION_BF16 = 0, SPM_PRECISION_FP32 = 1 };
 /* metric head behind the same entry points: CLIP-SPM (models/model_clipspm.py, the hot path) or its sibling
  * CLIP-FSAR (models/model_clipfsar.py CNN_OTAM_CLIPFSAR, evaluation branch :325-383), which reuses the same
  * transformer-block, class-mean and OTAM kernels */
-enum { SPM_HEAD_CLIPSPM = 0, SPM_HEAD_CLIPFSAR = 1 };
+enum { SPM_HEAD_CLIPSPM = 0, SPM_HEAD_CLIPFSAR = 1, SPM_HEAD_STEN = 2 /* models/model_sten.py:62-113 as shipped */ };
 
 typedef struct spm_config {
   int backbone;         /* cfg.MODEL.BACKBONE: SPM_BACKBONE_*                         model_clipspm.py:18,24 */
@@ -125,6 +126,12 @@ int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const floa
                   const float* target_images_host, const float* support_labels_host, const float* real_support_host,
                   const float* real_target_host, const int64_t* target_labels_host, float tasks_per_batch,
                   float* logits_host, float* dists_host, float* loss_host, float* acc_host, int32_t* pred_host);
+/* Double buffering across calls (what a DataLoader with prefetching gives the reference's Learner.test loop,
+ * run/main_run.py:71,266): tell the library which host image buffers the NEXT spm_eval_host / spm_eval_host_u8 call
+ * will read.  The current call then copies that call's first chunk host->device behind its own copies, while its last
+ * chunks compute, and the next call starts computing at once.  The hint is consumed by one call; the buffers must
+ * not change until the call that reads them returns; a call whose buffers do not match the prefetch ignores it. */
+int spm_eval_host_set_next(spm_handle* h, const void* next_support_host, const void* next_target_host);
 
 /* cos_sim + (bi)directional OTAM soft-DTW of n_pairs independent problems:
  *   support [P,W,T,D], target [P,Q,T,D] fp32 -> out [P,Q,W] (accumulated: out = beta*out + alpha*otam) */

@@ -352,6 +352,17 @@ def fsar_loss_and_acc(logits, class_logits, target_labels, real_support, real_ta
     return loss.float(), acc.float(), pred
 
 
+def sten_head_forward(text_test, su, qu, support_labels, real_support):
+    """models/model_sten.py:62-113 as shipped (all learned head modules are commented out there): su [S,8,D],
+    qu [Q,8,D] -> logits [1,Q,W]."""
+    su_f, qu_f = su.mean(1), qu.mean(1)                       # :65-66
+    t_f = text_test[real_support.long()]                      # :71
+    t_p = class_means(t_f, support_labels)                    # :97-99
+    su_p = class_means(su_f, support_labels)                  # :101-102
+    sim = cos_sim(qu_f, t_p).softmax(-1) * cos_sim(qu_f, su_p).softmax(-1)   # :104-106
+    return dict(su_f=su_f, qu_f=qu_f, logits=sim.unsqueeze(0))
+
+
 def loss_and_acc(logits, dists, target_labels, tasks_per_batch=16):
     """utils/utils.py:174-186 loss (CE summed over queries for the single logit sample), :259-264
     aggregate_accuracy, combined as run/main_run.py:390-392."""

@@ -324,9 +324,59 @@ def run_fsar_case(m, name):
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
 
 
+STEN_CASES = {
+    # name: (backbone, way, shot, qpc, n_test_cls, head_only, seed)   -- T is 8 (models/model_sten.py:65 hard-codes it)
+    "sten_head_5w5s": ("ViT-B/16", 5, 5, 1, 24, True, 2102),
+    "sten_head_5w3s_d1024_q2": ("RN50", 5, 3, 2, 10, True, 2104),
+}
+
+
+def run_sten_case(m, name):
+    """models/model_sten.py (its relative imports work as shipped).  Its constructor needs `load`; the forward only
+    uses the backbone, so head-only cases replace the backbone by a lookup of seeded features."""
+    backbone, way, shot, qpc, ncls, head_only, seed = STEN_CASES[name]
+    T, D = 8, 512 if backbone == "ViT-B/16" else 1024
+    import models.model_sten as sten
+    sten.load = m.load
+    cfg = NS(MODEL=NS(BACKBONE=backbone), TRAIN=NS(CLASS_NAME=["run"]), TEST=NS(CLASS_NAME=["run"]),
+             DATA=NS(SEQ_LEN=T), DEVICE=NS(NUM_GPUS=1))
+    torch.manual_seed(0)
+    with torch.no_grad():
+        net = sten.CNN_OTAM_CLIPFSAR(cfg).eval()
+    text = O.make_text_features(ncls, D, seed=0)
+    net.text_features_test = text
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, "P1", images=False)
+    su, qu = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+    feats = {"s": su.reshape(-1, D), "q": qu.reshape(-1, D)}
+    ep["context_images"], ep["target_images"] = "s", "q"
+    class Lookup(torch.nn.Module):
+        def forward(self, key):
+            return feats[key]
+    net.backbone = Lookup()
+    with torch.no_grad():
+        out = net(ep)
+        st = O.sten_head_forward(text, su, qu, ep["context_labels"], ep["real_support_labels"])
+    for mod in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    import utils.utils as U
+    loss_ref = U.loss(out["logits"], ep["target_labels"].long(), "cpu") / 16          # run/main_run.py:394-395
+    acc_ref = U.aggregate_accuracy(out["logits"], ep["target_labels"])
+    loss, acc, pred = O.loss_and_acc(st["logits"], torch.zeros(()), ep["target_labels"])
+    r = max(rel(st["logits"], out["logits"]), rel(loss.reshape(()), loss_ref.reshape(())))
+    assert r < 2e-4 and float(acc) == float(acc_ref), (r, acc, acc_ref)
+    lg = out["logits"][0]
+    top2 = lg.topk(2, dim=-1).values
+    margin = top2[:, 0] - top2[:, 1]
+    print("%-28s oracle==reference (models/model_sten.py), rel err %.2e | min top1-top2 margin %.4f, ref acc %.2f"
+          % (name, r, float(margin.min()), float(acc_ref)))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), logits=out["logits"].numpy(),
+                        loss=loss_ref.reshape(()).numpy(), acc=acc_ref.reshape(()).numpy(), pred=lg.argmax(-1).numpy(),
+                        margin=margin.numpy())
+
+
 if __name__ == "__main__":
     m = import_reference()
-    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES))
+    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + list(STEN_CASES))
     for n in names:
         if n == "text":
             run_text_case(m)
@@ -334,5 +384,7 @@ if __name__ == "__main__":
             run_otam_grad_case(m)
         elif n in FSAR_CASES:
             run_fsar_case(m, n)
+        elif n in STEN_CASES:
+            run_sten_case(m, n)
         else:
             run_case(m, n)

@@ -98,3 +98,19 @@ def build_cuda_fsar_model(ci, max_episodes=1, precision="bf16"):
     if not ci["head_only"]:
         assert not missing, missing
     return net
+
+
+# ---- sibling head STEN: must match oracle/pin_against_reference.py::STEN_CASES (T = 8)
+# name: (backbone, way, shot, qpc, n_test_cls, head_only, seed)
+STEN_CASES = {
+    "sten_head_5w5s": ("ViT-B/16", 5, 5, 1, 24, True, 2102),
+    "sten_head_5w3s_d1024_q2": ("RN50", 5, 3, 2, 10, True, 2104),
+}
+
+
+def sten_case_inputs(name):
+    backbone, way, shot, qpc, ncls, head_only, seed = STEN_CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    ep = O.make_episode(seed, way, shot, qpc, 8, ncls, "P1", images=False)
+    feats = O.make_features(seed, way * shot, way * qpc, 8, D, ep["context_labels"], ep["target_labels"].float())
+    return dict(backbone=backbone, way=way, T=8, D=D, episode=ep, feats=feats, text=O.make_text_features(ncls, D, seed=0))

@@ -70,3 +70,22 @@ def test_fsar_fails_loudly_without_gpu():
     ep = ci["episode"]
     with pytest.raises(RuntimeError):
         net.head(su, qu, ep["context_labels"], ep["real_support_labels"], ep["real_target_labels"])
+
+
+@pytest.mark.parametrize("name", list(H.STEN_CASES))
+def test_oracle_sten_head_matches_reference_golden(name):
+    ci, g = H.sten_case_inputs(name), H.golden(name)
+    ep = ci["episode"]
+    su, qu = ci["feats"]
+    st = O.sten_head_forward(ci["text"], su, qu, ep["context_labels"], ep["real_support_labels"])
+    assert H.rel_err(st["logits"], g["logits"]) < 1e-5
+    loss, acc, pred = O.loss_and_acc(st["logits"], torch.zeros(()), ep["target_labels"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 and float(acc) == float(g["acc"])
+    assert torch.equal(pred, g["pred"].long())
+
+
+def test_sten_state_dict_is_backbone_only():
+    from clip_spm_b200 import CNN_STEN
+    from clip_spm_b200.config import make_cfg
+    net = CNN_STEN(make_cfg("ViT-B/16", 8, params={}))
+    assert all(k.startswith("backbone.") for k in net.state_dict())

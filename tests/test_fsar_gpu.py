@@ -87,3 +87,25 @@ def test_fsar_wrong_way_fails_loudly():
     out = net.head(su.cuda(), qu.cuda(), ep["context_labels"].cuda(), ep["real_support_labels"].cuda(),
                    ep["real_target_labels"].cuda())
     assert bool(torch.isnan(out["logits"]).all())
+
+
+@pytest.mark.parametrize("name", list(H.STEN_CASES))
+def test_sten_head_matches_reference_golden(name):
+    """models/model_sten.py as shipped: pure fp32 kernels -> 1e-5"""
+    from clip_spm_b200 import CNN_STEN
+    from clip_spm_b200.config import make_cfg
+    ci, g = H.sten_case_inputs(name), H.golden(name)
+    net = CNN_STEN(make_cfg(ci["backbone"], 8, False, ci["way"], params={}), text_features_test=ci["text"])
+    ep = ci["episode"]
+    su, qu = ci["feats"]
+    out = net.head(su.cuda(), qu.cuda(), ep["context_labels"].cuda(), ep["real_support_labels"].cuda(),
+                   ep["real_target_labels"].cuda())
+    assert H.rel_err(out["logits"], g["logits"]) < 1e-5
+    assert _check_pred(out["logits"][0], g) >= 1
+    # two episodes in one call == one at a time
+    two = net.head(torch.stack([su, su.flip(0)]).cuda(), torch.stack([qu, qu]).cuda(),
+                   torch.cat([ep["context_labels"], ep["context_labels"].flip(0)]).cuda(),
+                   torch.cat([ep["real_support_labels"], ep["real_support_labels"].flip(0)]).cuda(),
+                   torch.cat([ep["real_target_labels"]] * 2).cuda(), n_episodes=2)
+    assert H.rel_err(two["logits"][0], g["logits"][0]) < 1e-5
+    assert H.rel_err(two["logits"][1], g["logits"][0]) < 1e-5     # support order does not matter

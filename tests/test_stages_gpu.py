@@ -170,6 +170,30 @@ def test_eval_host_matches_device_path():
         assert abs(float(host["loss"][e]) - float(loss)) < 1e-5 and float(host["acc"][e]) == float(acc)
 
 
+def test_eval_host_next_call_prefetch_changes_nothing():
+    """spm_eval_host_set_next: the first chunk of the next call is copied behind the current call's copies; a call
+    that consumes the prefetch, one whose buffers do not match it, and one without any hint give identical results."""
+    ci = H.case_inputs("vit_2w1s_t2_p0")
+    net = H.build_cuda_model(ci, max_episodes=2)
+    def batch(seed0):
+        eps = [O.make_episode(seed0 + e, 2, 1, 1, 2, 24, "P0") for e in range(4)]
+        cat = lambda k: torch.cat([e[k] for e in eps]).contiguous()
+        return dict(su=cat("context_images").pin_memory(), qu=cat("target_images").pin_memory(), lab=cat("context_labels"),
+                    rs=cat("real_support_labels"), rt=cat("real_target_labels"), tl=cat("target_labels"))
+    A, B = batch(4000), batch(5000)
+    run = lambda b, nxt=None: net.evaluate_host(b["su"], b["lab"], b["qu"], b["rs"], b["rt"], b["tl"], 4, 2,
+                                                next_images=None if nxt is None else (nxt["su"], nxt["qu"]))
+    plain_a, plain_b = run(A), run(B)
+    r1 = run(A, nxt=B)          # prefetches B's first chunk
+    r2 = run(B, nxt=B)          # consumes it, prefetches B again
+    r3 = run(A)                 # prefetch present but for other buffers: ignored
+    r4 = run(B)                 # no prefetch left (a hint lasts one call)
+    for got, want in ((r1, plain_a), (r2, plain_b), (r3, plain_a), (r4, plain_b)):
+        for k in ("logits", "dists", "loss", "acc", "pred"):
+            assert torch.equal(got[k], want[k]), k
+    assert not torch.equal(plain_a["logits"], plain_b["logits"])
+
+
 @pytest.mark.parametrize("impl", ["tcgen05", "mma"])
 @pytest.mark.parametrize("F,scale", [(1, 1.0), (3, 1.0), (40, 3.0), (160, 1.0)])
 def test_vit_attention_matches_torch(impl, F, scale):
