@@ -193,6 +193,8 @@ def main():
     __graft_entry__.build()
     from clip_spm_b200 import CNN, _lib, sweep
     from clip_spm_b200.config import make_cfg
+    # several ranks on one box: keep each rank (and the pinned buffers it allocates) on its GPU's NUMA node
+    bound = sweep.bind_to_gpu_cpus(local) if world > 1 else None
     lib = _lib.load()
     EPS, EPC = args.episodes_per_step, args.episodes_per_call
     net = CNN(make_cfg("ViT-B/16", T, False, WAY), max_episodes=EPC, device=dev)
@@ -344,6 +346,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "way": WAY, "shot": SHOT, "seq_len": T,
                        "episodes_per_step_per_gpu": EPS, "episodes_per_call": EPC,
+                       "rank0_cpu_binding": ("%d CPUs local to its GPU (NVML)" % len(bound)) if bound else "none",
                        "l2": "step inputs (%.0f MB) exceed the 126 MB L2; no explicit flush" % (EPS * FRAMES * 0.602112),
                        "weights": "random-init (no checkpoints offline)"},
             "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},

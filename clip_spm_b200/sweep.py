@@ -13,6 +13,32 @@ def shard_episodes(n_episodes, rank, world_size):
     return list(range(rank, n_episodes, world_size))
 
 
+def bind_to_gpu_cpus(gpu_index):
+    """One process per GPU: restrict this process to the CPUs NVML reports as local to its GPU (same NUMA node / PCIe
+    root), so the pinned staging buffers it allocates afterwards are first-touched next to the GPU and the host->device
+    copies of 8 ranks do not cross the socket interconnect.  Returns the CPU set it bound to, or None when nothing was
+    changed (no NVML, no usable CPUs inside the current cpuset).  Never raises."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:   # CUDA_VISIBLE_DEVICES may renumber the GPUs: resolve the CUDA device through its PCI address
+            pr = torch.cuda.get_device_properties(int(gpu_index))
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def make_stats(acc, loss):
     """Per-rank sufficient statistics from per-episode accuracy / loss tensors (any device)."""
     acc, loss = acc.double().flatten(), loss.double().flatten()

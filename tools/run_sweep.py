@@ -33,6 +33,8 @@ def main():
     __graft_entry__.build()
     from clip_spm_b200 import CNN, sweep
     from clip_spm_b200.config import make_cfg
+    if world > 1:
+        sweep.bind_to_gpu_cpus(local)   # keep each rank on its GPU's NUMA node
     D = 512 if args.backbone == "ViT-B/16" else 1024
     net = CNN(make_cfg(args.backbone, args.seq_len, False, args.way), max_episodes=args.episodes_per_call, device=dev)
     net.init_random_(seed=0)
