@@ -60,6 +60,8 @@ SIGNATURES = {
                                   c_float, c_float, c_void_p]),
     "spm_otam_distance_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                            c_float, c_void_p, c_void_p, c_void_p]),
+    "spm_softdtw_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p]),
+    "spm_softdtw_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p]),
     "spm_vit_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "spm_gemm": (c_int, [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_int,
                          c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int]),

@@ -39,6 +39,11 @@ int k_fsar_class_ce_add(cudaStream_t st, const float* cls, const float* real_s, 
 int k_sten_head(cudaStream_t st, const float* X, const float* text, int n_cls, const float* labels,
                 const float* real_s, int E, int S, int Q, int W, int T, int D, float* frame_mean, float* proto,
                 float* negsim, int* err_flag);
+// soft-DTW of TA2N (softdtw.cu; models/OTAM.py:34-203): D [B,N,M] -> R [B,N+2,M+2], out [B]; backward -> E [B,N,M]
+int k_softdtw_forward(cudaStream_t st, const float* D, int B, int N, int M, float gamma, float bandwidth, float* R,
+                      float* out);
+int k_softdtw_backward(cudaStream_t st, const float* D, const float* R, int B, int N, int M, float gamma,
+                       float bandwidth, float* E);
 int k_otam_init();
 // out[p,q,w] = beta*out + alpha * otam(support[p,w,:,:], target[p,q,:,:]); element (p,w,t,d) of the support set is at
 // sup + p*s_p + w*s_w + t*s_t + d (strides in floats), likewise for the target set.

@@ -1392,6 +1392,24 @@ int spm_eval_host_u8(spm_handle* h, int n_episodes, int S, int Q, int W, int img
                         tl_h, tasks_per_batch, logits_h, dists_h, loss_h, acc_h, pred_h);
 }
 
+int spm_softdtw_forward(void* stream, int n_pairs, int N, int M, const float* D, float gamma, float bandwidth, float* R,
+                        float* out) {
+  SPM_CHECK(D && R, "spm_softdtw_forward: null argument");
+  SPM_CHECK(gamma > 0.f, "spm_softdtw_forward: gamma must be positive");
+  SPM_CHECK(N >= 1 && M >= 1 && N <= 1024 && M <= 1024, "spm_softdtw_forward: sequence lengths must be in [1, 1024]");
+  SPM_KERNEL(k_softdtw_forward((cudaStream_t)stream, D, n_pairs, N, M, gamma, bandwidth, R, out));
+  return 0;
+}
+
+int spm_softdtw_backward(void* stream, int n_pairs, int N, int M, const float* D, const float* R, float gamma,
+                         float bandwidth, float* E) {
+  SPM_CHECK(D && R && E, "spm_softdtw_backward: null argument");
+  SPM_CHECK(gamma > 0.f, "spm_softdtw_backward: gamma must be positive");
+  SPM_CHECK(N >= 1 && M >= 1 && N <= 1024 && M <= 1024, "spm_softdtw_backward: sequence lengths must be in [1, 1024]");
+  SPM_KERNEL(k_softdtw_backward((cudaStream_t)stream, D, R, n_pairs, N, M, gamma, bandwidth, E));
+  return 0;
+}
+
 int spm_otam_distance(void* stream, int n_pairs, int W, int Q, int T, int D, const float* support, const float* target,
                       int single_direct, float alpha, float beta, float* out) {
   SPM_CHECK(support && target && out, "spm_otam_distance: null argument");

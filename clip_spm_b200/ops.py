@@ -125,3 +125,75 @@ def transform_frames(frames):
     out = torch.empty(F, 3, 224, 224, device=frames.device)
     _lib.check(lib.spm_transform_frames(_stream(), _ptr(frames), F, H, W, _ptr(out)))
     return out
+
+
+class _SoftDTWFunction(torch.autograd.Function):
+    """models/OTAM.py:134-203 `_SoftDTWCUDA`: D [B,N,M] -> R[:, N, M]; backward = E * grad (spm_softdtw_backward)."""
+
+    @staticmethod
+    def forward(ctx, D, gamma, bandwidth):
+        lib = _lib.load()
+        _need_cuda(D)
+        D = D.contiguous().float()
+        B, N, M = D.shape
+        R = torch.empty(B, N + 2, M + 2, device=D.device)
+        out = torch.empty(B, device=D.device)
+        _lib.check(lib.spm_softdtw_forward(_stream(), B, N, M, _ptr(D), float(gamma), float(bandwidth), _ptr(R), _ptr(out)))
+        ctx.save_for_backward(D, R)
+        ctx.cfg = (float(gamma), float(bandwidth))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        lib = _lib.load()
+        D, R = ctx.saved_tensors
+        gamma, bandwidth = ctx.cfg
+        B, N, M = D.shape
+        E = torch.empty_like(D)
+        _lib.check(lib.spm_softdtw_backward(_stream(), B, N, M, _ptr(D), _ptr(R), gamma, bandwidth, _ptr(E)))
+        return grad_output.reshape(-1, 1, 1) * E, None, None
+
+
+def softdtw(D, gamma=1.0, bandwidth=0.0):
+    """soft-DTW value of every [N, M] distance matrix of D [B,N,M] (differentiable in D)."""
+    return _SoftDTWFunction.apply(D, gamma, bandwidth)
+
+
+class SoftDTW(torch.nn.Module):
+    """Mirror of models/OTAM.py:318-424 `SoftDTW` (TA2N's metric, models/model_ta2n.py:87) with the DP on this
+    library's kernels.  Same constructor (`use_cuda` is accepted for signature compatibility: there is no CPU path
+    here), same forward contract: X [B,n,d], Y [B,m,d] -> [B,1] (bi-directional mean, :414-424), or the normalised
+    variant (:405-413).  The point-wise distance is the caller's `dist_func` (default: the reference's
+    1 - cosine_similarity, :381-388, plain torch ops as there)."""
+
+    def __init__(self, use_cuda=True, gamma=1.0, normalize=False, bandwidth=None, dist_func=None):
+        super().__init__()
+        self.normalize = normalize
+        self.gamma = gamma
+        self.bandwidth = 0 if bandwidth is None else float(bandwidth)
+        self.use_cuda = use_cuda
+        self.dist_func = dist_func if dist_func is not None else SoftDTW._similarity_dist_func
+
+    @staticmethod
+    def _euclidean_dist_func(x, y):
+        return torch.pow(x.unsqueeze(2) - y.unsqueeze(1), 2).sum(3)
+
+    @staticmethod
+    def _similarity_dist_func(x, y):
+        n, m, d = x.size(1), y.size(1), x.size(2)
+        return 1 - torch.cosine_similarity(x.unsqueeze(2).expand(-1, n, m, d), y.unsqueeze(1).expand(-1, n, m, d), dim=3)
+
+    def forward(self, X, Y):
+        if X.shape[2] != Y.shape[2]:
+            raise RuntimeError("SoftDTW: feature dimensions differ")
+        if self.normalize:
+            x, y = torch.cat([X, X, Y]), torch.cat([Y, X, Y])
+            out = softdtw(self.dist_func(x, y), self.gamma, self.bandwidth)
+            out_xy, out_xx, out_yy = torch.split(out, X.shape[0])
+            return out_xy - 1 / 2 * (out_xx + out_yy)
+        pad = torch.nn.functional.pad
+        D_xy = pad(self.dist_func(X, Y), (0, 0, 1, 1), "constant", 0)           # zero first / last row (:416)
+        D_yx = pad(self.dist_func(Y, X), (0, 0, 1, 1), "constant", 0)
+        a = softdtw(D_xy, self.gamma, self.bandwidth).unsqueeze(-1)
+        b = softdtw(D_yx, self.gamma, self.bandwidth).unsqueeze(-1)
+        return (a + b) / 2

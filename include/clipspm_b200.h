@@ -19,6 +19,7 @@
  *   spm_head                      models/model_clipspm.py:125-143  (everything after get_feats)
  *   spm_otam_distance             models/model_clipspm.py:348-362 + models/myRes.py:756-765,821-855
  *   spm_set_text_features_train / spm_class_logits   models/model_clipfsar.py:127,329-331 (sibling head CLIP-FSAR)
+ *   spm_softdtw_forward/backward  models/OTAM.py:34-203 (TA2N's numba.cuda soft-DTW kernels, _SoftDTWCUDA)
  *   spm_gemm                      ATen linear / conv-as-GEMM calls (cuBLASLt) under all of the above
  */
 #ifndef CLIPSPM_B200_H
@@ -137,6 +138,17 @@ int spm_eval_host_set_next(spm_handle* h, const void* next_support_host, const v
  *   support [P,W,T,D], target [P,Q,T,D] fp32 -> out [P,Q,W] (accumulated: out = beta*out + alpha*otam) */
 int spm_otam_distance(void* stream, int n_pairs, int W, int Q, int T, int D, const float* support,
                       const float* target, int single_direct, float alpha, float beta, float* out);
+
+/* Soft-DTW of TA2N: the sm_100a counterparts of the reference's two numba.cuda kernels (models/OTAM.py:34-130) behind
+ * _SoftDTWCUDA.forward / .backward (:134-203).  D [n_pairs, N, M] fp32 pairwise distances; bandwidth = Sakoe-Chiba
+ * pruning (0 = none).  Forward writes the whole cumulative table R [n_pairs, N+2, M+2] (+inf borders, R[0,0] = 0;
+ * the tensor _SoftDTWCUDA saves for backward) and out [n_pairs] = R[:, N, M] (out may be null).  Backward takes that
+ * R unmodified (the reference's in-place edits :160-162 are applied on the fly) and writes E [n_pairs, N, M] =
+ * d out / d D. */
+int spm_softdtw_forward(void* stream, int n_pairs, int N, int M, const float* D, float gamma, float bandwidth, float* R,
+                        float* out);
+int spm_softdtw_backward(void* stream, int n_pairs, int N, int M, const float* D, const float* R, float gamma,
+                         float bandwidth, float* E);
 
 /* Backward of spm_otam_distance (first piece of the training step, run/main_run.py:245-254): given
  * grad_out [P,Q,W] = d loss / d out, writes d loss / d support [P,W,T,D] and d loss / d target [P,Q,T,D]

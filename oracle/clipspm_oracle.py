@@ -363,6 +363,77 @@ def sten_head_forward(text_test, su, qu, support_labels, real_support):
     return dict(su_f=su_f, qu_f=qu_f, logits=sim.unsqueeze(0))
 
 
+# =====================================================================================================
+# TA2N's soft-DTW (models/OTAM.py) -- the reference's own numba.cuda kernels, restated in numpy (fp64 like the
+# reference's CPU path, :234-289)
+# =====================================================================================================
+def softdtw_forward_np(D, gamma, bandwidth=0.0):
+    """models/OTAM.py:234-250 compute_softdtw: D [B,N,M] -> R [B,N+2,M+2] (the value is R[:, -2, -2])."""
+    import numpy as np
+    D = np.asarray(D, dtype=np.float64)
+    B, N, M = D.shape
+    R = np.full((B, N + 2, M + 2), np.inf)
+    R[:, 0, 0] = 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for j in range(1, M + 1):
+            for i in range(1, N + 1):
+                if 0 < bandwidth < abs(i - j):
+                    continue
+                r = np.stack([-R[:, i - 1, j - 1], -R[:, i - 1, j], -R[:, i, j - 1]]) / gamma     # :207-215
+                rmax = r.max(0)
+                R[:, i, j] = D[:, i - 1, j - 1] - gamma * (np.log(np.exp(r - rmax).sum(0)) + rmax)
+    return R
+
+
+def softdtw_backward_np(D_, R, gamma, bandwidth=0.0):
+    """models/OTAM.py:254-289 compute_softdtw_backward: -> E [B,N,M] = d R[:, N, M] / d D."""
+    import numpy as np
+    D_ = np.asarray(D_, dtype=np.float64)
+    R = np.array(R, dtype=np.float64)
+    B, N, M = D_.shape
+    D = np.zeros((B, N + 2, M + 2))
+    E = np.zeros((B, N + 2, M + 2))
+    D[:, 1:N + 1, 1:M + 1] = D_
+    E[:, -1, -1] = 1
+    R[:, :, -1] = -np.inf
+    R[:, -1, :] = -np.inf
+    R[:, -1, -1] = R[:, -2, -2]
+    with np.errstate(invalid="ignore", over="ignore"):
+        for j in range(M, 0, -1):
+            for i in range(N, 0, -1):
+                inf = np.isinf(R[:, i, j])
+                R[inf, i, j] = -np.inf
+                if 0 < bandwidth < abs(i - j):
+                    continue
+                a = np.exp((R[:, i + 1, j] - R[:, i, j] - D[:, i + 1, j]) / gamma)
+                b = np.exp((R[:, i, j + 1] - R[:, i, j] - D[:, i, j + 1]) / gamma)
+                c = np.exp((R[:, i + 1, j + 1] - R[:, i, j] - D[:, i + 1, j + 1]) / gamma)
+                E[:, i, j] = E[:, i + 1, j] * a + E[:, i, j + 1] * b + E[:, i + 1, j + 1] * c
+    return E[:, 1:N + 1, 1:M + 1]
+
+
+def softdtw_module(X, Y, gamma=1.0, normalize=False, bandwidth=0.0):
+    """models/OTAM.py:390-424 SoftDTW.forward with the default distance 1 - cosine_similarity (:381-388)."""
+    def dist(x, y):
+        n, m, d = x.size(1), y.size(1), x.size(2)
+        return 1 - torch.cosine_similarity(x.unsqueeze(2).expand(-1, n, m, d), y.unsqueeze(1).expand(-1, n, m, d), dim=3)
+
+    def value(D):
+        return torch.from_numpy(softdtw_forward_np(D.numpy(), gamma, bandwidth)[:, -2, -2]).float()
+    if normalize:
+        out = value(dist(torch.cat([X, X, Y]), torch.cat([Y, X, Y])))
+        a, b, c = torch.split(out, X.shape[0])
+        return a - 0.5 * (b + c)
+    d1 = F.pad(dist(X, Y), (0, 0, 1, 1), "constant", 0)
+    d2 = F.pad(dist(Y, X), (0, 0, 1, 1), "constant", 0)
+    return (value(d1).unsqueeze(-1) + value(d2).unsqueeze(-1)) / 2
+
+
+def make_softdtw_inputs(B, N, M, d, seed):
+    g = _gen(seed, "softdtw")
+    return torch.rand(B, N, d, generator=g), torch.rand(B, M, d, generator=g), torch.rand(B, N, M, generator=g)
+
+
 def loss_and_acc(logits, dists, target_labels, tasks_per_batch=16):
     """utils/utils.py:174-186 loss (CE summed over queries for the single logit sample), :259-264
     aggregate_accuracy, combined as run/main_run.py:390-392."""

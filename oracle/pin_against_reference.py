@@ -374,9 +374,44 @@ def run_sten_case(m, name):
                         margin=margin.numpy())
 
 
+SOFTDTW_CASES = {
+    # name: (B, N, M, d, gamma, bandwidth, seed)
+    "softdtw_8x8_g01": (6, 8, 8, 64, 0.1, 0.0, 3101),        # TA2N's setting: SoftDTW(gamma=0.1), models/model_ta2n.py:87
+    "softdtw_17x15_g1": (4, 17, 15, 8, 1.0, 0.0, 3102),      # the reference's own profile() shape, models/OTAM.py:517
+    "softdtw_40x38_bw5": (3, 40, 38, 8, 0.5, 5.0, 3103),     # more rows than a warp, Sakoe-Chiba band
+}
+
+
+def run_softdtw_case(name):
+    """models/OTAM.py executed here through its CPU path (numba @jit compute_softdtw / compute_softdtw_backward and the
+    SoftDTW module with use_cuda=False) -- the path its own test (profile(), :461-505) holds the CUDA kernels against."""
+    import models.OTAM as ref
+    B, N, M, d, gamma, bw, seed = SOFTDTW_CASES[name]
+    X, Y, D = O.make_softdtw_inputs(B, N, M, d, seed)
+    R_ref = ref.compute_softdtw(D.numpy(), gamma, bw)
+    E_ref = ref.compute_softdtw_backward(D.numpy(), R_ref.copy(), gamma, bw)
+    R = O.softdtw_forward_np(D.numpy(), gamma, bw)
+    E = O.softdtw_backward_np(D.numpy(), R, gamma, bw)
+    fin = np.isfinite(R_ref)
+    assert (np.isfinite(R) == fin).all() and np.abs(R[fin] - R_ref[fin]).max() < 1e-9 and np.abs(E - E_ref).max() < 1e-9
+    mod = ref.SoftDTW(use_cuda=False, gamma=gamma, bandwidth=bw if bw > 0 else None)
+    x = X.clone().requires_grad_(True)
+    val = mod(x, Y)
+    val.sum().backward()
+    mine = O.softdtw_module(X, Y, gamma, False, bw)
+    nrm = ref.SoftDTW(use_cuda=False, gamma=gamma, normalize=True, bandwidth=bw if bw > 0 else None)(X[:, :min(N, M)], Y[:, :min(N, M)])
+    mine_n = O.softdtw_module(X[:, :min(N, M)], Y[:, :min(N, M)], gamma, True, bw)
+    r = max(rel(mine, val.detach()), rel(mine_n, nrm))
+    assert r < 1e-5, r
+    print("%-28s oracle==reference (models/OTAM.py CPU path): table/gradient exact to 1e-9, module rel err %.2e" % (name, r))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), R=R_ref.astype(np.float32),
+                        E=E_ref.astype(np.float32), module=val.detach().numpy(), module_norm=nrm.numpy(),
+                        grad_x=x.grad.numpy())
+
+
 if __name__ == "__main__":
     m = import_reference()
-    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + list(STEN_CASES))
+    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + list(STEN_CASES) + list(SOFTDTW_CASES))
     for n in names:
         if n == "text":
             run_text_case(m)
@@ -386,5 +421,7 @@ if __name__ == "__main__":
             run_fsar_case(m, n)
         elif n in STEN_CASES:
             run_sten_case(m, n)
+        elif n in SOFTDTW_CASES:
+            run_softdtw_case(n)
         else:
             run_case(m, n)

@@ -114,3 +114,12 @@ def sten_case_inputs(name):
     ep = O.make_episode(seed, way, shot, qpc, 8, ncls, "P1", images=False)
     feats = O.make_features(seed, way * shot, way * qpc, 8, D, ep["context_labels"], ep["target_labels"].float())
     return dict(backbone=backbone, way=way, T=8, D=D, episode=ep, feats=feats, text=O.make_text_features(ncls, D, seed=0))
+
+
+# ---- TA2N soft-DTW (models/OTAM.py): must match oracle/pin_against_reference.py::SOFTDTW_CASES
+# name: (B, N, M, d, gamma, bandwidth, seed)
+SOFTDTW_CASES = {
+    "softdtw_8x8_g01": (6, 8, 8, 64, 0.1, 0.0, 3101),
+    "softdtw_17x15_g1": (4, 17, 15, 8, 1.0, 0.0, 3102),
+    "softdtw_40x38_bw5": (3, 40, 38, 8, 0.5, 5.0, 3103),
+}
