@@ -25,7 +25,7 @@ int k_class_mean_padm(cudaStream_t st, const float* z1, const float* labels, int
 int k_finalize(cudaStream_t st, const float* accd, const float* d3, int E, int Q, int W, const long long* target,
                float tasks_per_batch, const float* dists, float* logits, float* loss, float* accuracy, int* pred,
                const int* err_flag);
-// ---- sibling head CLIP-FSAR (fsar_kernels.cu; models/model_clipfsar.py:325-383)
+// ---- sibling head CLIP-FSAR (sibling_heads.cu; models/model_clipfsar.py:325-383)
 int k_fsar_seq_build(cudaStream_t st, const float* X, const float* text, int n_cls, const float* real_s, int E, int S,
                      int Q, int T, int D, float* seq);
 int k_fsar_class_mean(cudaStream_t st, const float* z, const float* labels, int E, int S, int W, int T, int D,

@@ -1,6 +1,8 @@
-// Sibling head CLIP-FSAR (models/model_clipfsar.py:325-383, evaluation branch): the non-GEMM kernels around the shared
-// transformer block / OTAM kernels.  fp32, float4-vectorised, labels resolved on the device (no host sync).
+// Sibling heads on the library's kernels.  CLIP-FSAR (models/model_clipfsar.py:325-383, evaluation
+// branch): the non-GEMM kernels around the shared transformer block / OTAM kernels; STEN (models/model_sten.py:62-113 as
+// shipped): the whole head.  fp32, float4-vectorised, labels resolved on the device (no host sync).
 #include "head_kernels.cuh"
+#include "head_device.cuh"
 #include "profile.cuh"
 
 namespace spm {
@@ -12,13 +14,6 @@ namespace spm {
     count_launch();                                          \
   } while (0)
 
-namespace {
-__device__ __forceinline__ float warp_sum_f(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-}  // namespace
 
 // ------------------------------------------------------------------------------------------------------
 // context2 input sequences (model_clipfsar.py:338-348).  X [E, S+Q, T, D], supports first.
@@ -61,23 +56,7 @@ __global__ void fsar_class_mean_kernel(const float* __restrict__ z, const float*
   __shared__ int cls[256];
   const int e = blockIdx.x, t = blockIdx.y, d4 = D / 4;
   // rank of each label among the episode's sorted distinct labels == position in torch.unique (:352)
-  const float* lab = labels + (long long)e * S;
-  for (int s = threadIdx.x; s < S; s += blockDim.x) {
-    const float me = lab[s];
-    int rank = 0;
-    for (int j = 0; j < S; ++j) {
-      const float o = lab[j];
-      if (o < me) {
-        bool first = true;
-        for (int k = 0; k < j; ++k) first = first && (lab[k] != o);
-        rank += first ? 1 : 0;
-      }
-    }
-    cls[s] = rank;
-  }
-  __syncthreads();
-  int Wd = 0;
-  for (int s = 0; s < S; ++s) Wd = max(Wd, cls[s] + 1);
+  const int Wd = class_indices(labels + (long long)e * S, S, cls);
   if (Wd != W) {
     if (threadIdx.x == 0 && t == 0) atomicExch(err_flag, 1);
     return;
@@ -126,7 +105,7 @@ __global__ void fsar_class_logits_kernel(const float* __restrict__ X, const floa
     m[d] = a;
     nn += a * a;
   }
-  nn = warp_sum_f(nn);
+  nn = warp_sum(nn);
   if (lane == 0) red[warp] = nn;
   __syncthreads();
   float tot = 0.f;
@@ -140,8 +119,8 @@ __global__ void fsar_class_logits_kernel(const float* __restrict__ X, const floa
       dot = fmaf(m[d], yv, dot);
       yy = fmaf(yv, yv, yy);
     }
-    dot = warp_sum_f(dot);
-    yy = warp_sum_f(yy);
+    dot = warp_sum(dot);
+    yy = warp_sum(yy);
     if (lane == 0) out[(long long)v * n_cls + c] = sc * dot / (mnorm * sqrtf(yy) + 0.01f);
   }
 }
@@ -221,23 +200,7 @@ sten_sim_kernel(const float* __restrict__ m, const float* __restrict__ text, int
   __shared__ float pn[64];        // [W][2] prototype norms
   __shared__ float cs[4096];      // [Q][W][2] cosines (Q*W <= 2048, checked by the launcher)
   const int e = blockIdx.x, N = S + Q, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const float* lab = labels + (long long)e * S;
-  for (int s = threadIdx.x; s < S; s += blockDim.x) {   // rank among the sorted distinct labels (torch.unique, :97)
-    const float me = lab[s];
-    int rank = 0;
-    for (int j = 0; j < S; ++j) {
-      const float o = lab[j];
-      if (o < me) {
-        bool first = true;
-        for (int k = 0; k < j; ++k) first = first && (lab[k] != o);
-        rank += first ? 1 : 0;
-      }
-    }
-    cls[s] = rank;
-  }
-  __syncthreads();
-  int Wd = 0;
-  for (int s = 0; s < S; ++s) Wd = max(Wd, cls[s] + 1);
+  const int Wd = class_indices(labels + (long long)e * S, S, cls);   // rank among the sorted distinct labels (:97)
   if (Wd != W) {
     if (threadIdx.x == 0) atomicExch(err_flag, 1);
     return;
@@ -262,7 +225,7 @@ sten_sim_kernel(const float* __restrict__ m, const float* __restrict__ text, int
       pr[((long long)w * 2 + 1) * D + d] = b;
       ns = fmaf(a, a, ns); nt = fmaf(b, b, nt);
     }
-    ns = warp_sum_f(ns); nt = warp_sum_f(nt);
+    ns = warp_sum(ns); nt = warp_sum(nt);
     if (lane == 0) { pn[w * 2] = sqrtf(ns); pn[w * 2 + 1] = sqrtf(nt); }
   }
   __syncthreads();   // the prototypes were written by this CTA: visible to it after the barrier
@@ -277,7 +240,7 @@ sten_sim_kernel(const float* __restrict__ m, const float* __restrict__ text, int
       dt = fmaf(xv, pr[((long long)w * 2 + 1) * D + d], dt);
       xx = fmaf(xv, xv, xx);
     }
-    ds = warp_sum_f(ds); dt = warp_sum_f(dt); xx = warp_sum_f(xx);
+    ds = warp_sum(ds); dt = warp_sum(dt); xx = warp_sum(xx);
     if (lane == 0) {
       const float xn = sqrtf(xx);
       cs[i * 2 + 0] = ds / (xn * pn[w * 2] + 0.01f);
