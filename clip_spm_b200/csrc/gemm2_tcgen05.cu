@@ -11,6 +11,8 @@
 //   epilogue (both CTAs)  arrive remotely on the leader's tmem-empty barrier (16 warp arrivals)
 // bf16 operands only, N % 256 == 0; used for the large frame-encoder GEMMs.
 #include "gemm.cuh"
+#include <cstdlib>
+
 #include "gemm_epilogue.cuh"
 #include "profile.cuh"
 #include "ptx.cuh"
@@ -88,7 +90,8 @@ struct Gemm2Args {
   int reverse;
 };
 
-template <bool RES>
+// EPI: 0 = general epilogue; 1 / 2 = bf16 output + bias (+ QuickGELU) with identity rows (gemm_epilogue_tile_bf16_bias)
+template <bool RES, int EPI = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmR, const Gemm2Args args) {
@@ -262,7 +265,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T::BN);
-        gemm_epilogue_tile<T::BN>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+        if (EPI == 1) gemm_epilogue_tile_bf16_bias<T::BN, ACT_NONE>(ep, stg_u, taddr, m_base, n0, M, lane, half);
+        else if (EPI == 2) gemm_epilogue_tile_bf16_bias<T::BN, ACT_QUICKGELU>(ep, stg_u, taddr, m_base, n0, M, lane, half);
+        else gemm_epilogue_tile<T::BN>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
@@ -281,6 +286,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 int gemm2_init(const char** err) {
   if (cudaFuncSetAttribute(gemm2_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            G2T<false>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm2_tcgen05_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           G2T<false>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm2_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           G2T<false>::SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(gemm2_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            G2T<true>::SMEM_BYTES) != cudaSuccess) {
     *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the 2-CTA GEMM kernel";
@@ -294,8 +303,21 @@ int gemm2_launch(const GemmOp* op, cudaStream_t stream) {
   a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K; a.reverse = op->reverse;
   if (op->res_tma)
     gemm2_tcgen05_kernel<true><<<op->grid, 384, G2T<true>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->tr, a);
-  else
-    gemm2_tcgen05_kernel<false><<<op->grid, 384, G2T<false>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->ta, a);
+  else {
+    // the two hot consumer shapes of the ViT encoder get the compile-time-specialised epilogue (SPM_GEMM_EPI=0: off)
+    static const bool allow_spec = [] { const char* e = getenv("SPM_GEMM_EPI"); return e == nullptr || atoi(e) != 0; }();
+    const GemmEpilogue& e = op->ep;
+    const bool simple = allow_spec && e.out_bf16 && e.bias != nullptr && e.residual == nullptr &&
+                        e.residual_bf16 == nullptr && e.out_row_group == 0 && e.border_w2 == 0 &&
+                        op->N % G2T<false>::BN == 0 && (e.ldo % 8) == 0 &&
+                        (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
+    if (simple && e.act == ACT_NONE)
+      gemm2_tcgen05_kernel<false, 1><<<op->grid, 384, G2T<false>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->ta, a);
+    else if (simple && e.act == ACT_QUICKGELU)
+      gemm2_tcgen05_kernel<false, 2><<<op->grid, 384, G2T<false>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->ta, a);
+    else
+      gemm2_tcgen05_kernel<false><<<op->grid, 384, G2T<false>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->ta, a);
+  }
   return (int)cudaGetLastError();
 }
 

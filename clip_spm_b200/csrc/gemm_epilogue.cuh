@@ -195,6 +195,61 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint3
   }
 }
 
+// Specialisation for the two hot consumer GEMMs of the ViT encoder (QKV: bias; fc: bias + QuickGELU): bf16 output,
+// identity rows, no residual, N a multiple of BN.  Same arithmetic and the same staging scheme as gemm_epilogue_tile,
+// but every option is a compile-time constant: no residual registers, no activation dispatch, no row-map arithmetic
+// (the general epilogue sits at the 168-register cap; an A/B run showed the encoder GEMMs lose 4 % to ~10 extra
+// registers' worth of code in it).
+template <int BN, int ACT>
+__device__ __forceinline__ void gemm_epilogue_tile_bf16_bias(const GemmEpilogue& ep, uint32_t stg_u, uint32_t taddr,
+                                                             int m_base, int n0, int M, int lane, int half) {
+  const int rr = lane >> 3, uu = lane & 7;  // read-back mapping: row i*4 + rr, 16-byte unit uu
+  __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.out);
+  const uint32_t srow = stg_u + (uint32_t)(lane * 128);
+#pragma unroll 1
+  for (int g = half * 2; g < BN / 32; g += 4) {
+    const int col0 = n0 + g * 32;  // first output column of this 128-byte store group (64 bf16)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr + (uint32_t)((g + h) * 32), r);
+      tmem_ld_wait();
+      const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0 + h * 32);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(bp + j);
+        v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+      }
+      if (ACT == ACT_QUICKGELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = quick_gelu_fast(v[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack2_bf16(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack2_bf16(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack2_bf16(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack2_bf16(v[8 * j + 6], v[8 * j + 7]);
+        st_shared_v4(srow + (uint32_t)((((h * 4 + j) ^ (lane & 7))) * 16), u);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = i * 4 + rr;
+      const uint4 d = ld_shared_v4(stg_u + (uint32_t)(rl * 128 + ((uu ^ (rl & 7)) * 16)));
+      if (m_base + rl < M)
+        *reinterpret_cast<uint4*>(outp + (long long)(m_base + rl) * ep.ldo + col0 + uu * 8) = d;
+    }
+    __syncwarp();  // staging tile is reused by the next group
+  }
+}
+
 // Variant for fp32 output + fp32 residual (identity rows), used by the 2-CTA kernel: the residual box of this warp's
 // 32 rows x 32 columns has been TMA-loaded (SWIZZLE_128B: 16-byte unit u of row r sits at unit u ^ (r & 7), the same
 // permutation the staging tile uses) into `buf_u`; the thread owning accumulator row `lane` adds its row in place,
