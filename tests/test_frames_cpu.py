@@ -44,3 +44,33 @@ def test_library_geometry_matches_oracle():
     sizes += [tuple(int(v) for v in rng.randint(60, 2000, size=2)) for _ in range(300)]
     for h, w in sizes:
         assert frame_geometry(h, w) == P.geometry(h, w), (h, w)
+
+
+# must match oracle/pin_sampler.py::CASES: (n_classes, videos per class, way, shot, queries, seq_len, train, seed)
+SAMPLER_CASES = {
+    "eval_5w5s_t8": (12, 9, 5, 5, 1, 8, False, 11),
+    "eval_5w1s_t16": (7, 4, 5, 1, 2, 16, False, 12),
+    "train_5w3s_t8": (9, 8, 5, 3, 2, 8, True, 13),
+    "train_3w1s_t1": (4, 3, 3, 1, 1, 1, True, 14),
+}
+
+
+@pytest.mark.parametrize("name", list(SAMPLER_CASES))
+def test_episode_sampler_matches_reference_golden(name):
+    """frames.sample_episode_plan against what the reference's VideoDataset.__getitem__ picked for the same seed on the
+    same listing (oracle/pin_sampler.py -> tests/golden/sampler.npz): frames, their order, and the four label lists"""
+    import random
+    from clip_spm_b200 import frames as F
+    n_cls, per_cls, way, shot, nq, T, train, seed = SAMPLER_CASES[name]
+    g = {k.split("/", 1)[1]: v.numpy() for k, v in H.golden("sampler").items() if k.startswith(name + "/")}
+    sp = F.Split()
+    for vid in range(per_cls):
+        for cls in range(n_cls):
+            sp.add_vid([(cls, vid, f) for f in range(8 + (cls * 7 + vid * 5) % 23)], cls)
+    plan = F.sample_episode_plan(sp, way, shot, nq, T, train=train, rng=random.Random(seed))
+    trip = lambda items: np.array([sp.videos[v][f] for v, fr in items for f in fr], np.int32)
+    assert np.array_equal(trip(plan["support"]), g["support_set"])
+    assert np.array_equal(trip(plan["target"]), g["target_set"])
+    for k in ("support_labels", "target_labels", "real_support_labels", "real_target_labels", "batch_class_list"):
+        assert np.array_equal(np.array(plan[k], np.float32), g[k]), k
+    assert len(plan["support"]) == way * shot and all(len(fr) == T for _, fr in plan["support"] + plan["target"])
