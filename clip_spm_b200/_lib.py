@@ -55,7 +55,7 @@ SIGNATURES = {
     "spm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7),
     "spm_eval": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),
     "spm_eval_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),
-    "spm_eval_host_set_next": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "spm_eval_host_set_next": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "spm_otam_distance": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                   c_float, c_float, c_void_p]),
     "spm_otam_distance_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,

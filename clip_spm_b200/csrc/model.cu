@@ -189,6 +189,7 @@ struct spm_handle {
   // spm_eval_host_set_next: the first chunk of the NEXT spm_eval_host call is copied to these buffers behind the
   // current call's own copies, so that call starts computing at once (its one exposed H2D copy disappears)
   const void *next_su = nullptr, *next_qu = nullptr;   // hint given by the caller, consumed by the next call
+  int next_n = 0;                                      // episodes the hinted call will evaluate
   uint8_t *pf_su = nullptr, *pf_qu = nullptr;
   long long pf_cap_s = 0, pf_cap_q = 0;
   const void *pf_src_su = nullptr, *pf_src_qu = nullptr;   // what the buffers hold (null = nothing)
@@ -1260,9 +1261,12 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
   // prefetch buffers for the first chunk of the next call (allocated before anything is enqueued: cudaMalloc syncs)
   // (a whole compute chunk: with its copy out of the way the call can run full-size chunks from the start)
   const int first_n = std::min(EC, n_episodes);
-  const long long pf_s = (long long)first_n * fs * frame_bytes, pf_q = (long long)first_n * fq * frame_bytes;
   const void *hint_su = h->next_su, *hint_qu = h->next_qu;
+  const int hint_n = std::min(EC, h->next_n);   // first chunk of the hinted call (it may hold fewer episodes)
   h->next_su = h->next_qu = nullptr;   // a hint is consumed by exactly one call
+  h->next_n = 0;
+  const long long pf_s = (long long)hint_n * fs * frame_bytes, pf_q = (long long)hint_n * fq * frame_bytes;
+  const long long my_s = (long long)first_n * fs * frame_bytes, my_q = (long long)first_n * fq * frame_bytes;
   if (hint_su != nullptr && (pf_s > h->pf_cap_s || pf_q > h->pf_cap_q)) {
     SPM_CUDA(cudaStreamSynchronize(h->copy_stream));   // nobody may still be writing the old buffers
     SPM_TRY(dalloc_t(h, &h->pf_su, pf_s));
@@ -1272,8 +1276,8 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
   }
   if (h->pf_event == nullptr) SPM_CUDA(cudaEventCreateWithFlags(&h->pf_event, cudaEventDisableTiming));
   // does the prefetch made by the previous call hold this call's first chunk?
-  const bool use_pf = h->pf_src_su == (const void*)su_h && h->pf_src_qu == (const void*)qu_h && h->pf_bytes_s == pf_s &&
-                      h->pf_bytes_q == pf_q && su_h != nullptr;
+  const bool use_pf = h->pf_src_su == (const void*)su_h && h->pf_src_qu == (const void*)qu_h && h->pf_bytes_s == my_s &&
+                      h->pf_bytes_q == my_q && su_h != nullptr;
   // Chunk schedule.  The H2D copy of a chunk can only overlap the compute of EARLIER chunks, so the first chunks
   // are small (1, 1, 2, 4, ... up to EC when EC is a power of two: offsets stay aligned, a chunk never wraps the
   // ring) -- only one episode's copy is exposed per call instead of EC episodes'.
@@ -1348,7 +1352,7 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
   // Behind this call's own copies (same FIFO copy stream): the first chunk of the next call, while the last chunks of
   // this one compute.  The buffers may still be read by this call's chunk 0.
   h->pf_src_su = h->pf_src_qu = nullptr;
-  if (hint_su != nullptr && hint_qu != nullptr) {
+  if (hint_su != nullptr && hint_qu != nullptr && hint_n > 0) {
     SPM_CUDA(cudaStreamWaitEvent(cs, h->ev_done[0], 0));
     SPM_CUDA(cudaMemcpyAsync(h->pf_su, hint_su, (size_t)pf_s, cudaMemcpyHostToDevice, cs));
     SPM_CUDA(cudaMemcpyAsync(h->pf_qu, hint_qu, (size_t)pf_q, cudaMemcpyHostToDevice, cs));
@@ -1368,10 +1372,14 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
   return 0;
 }
 
-int spm_eval_host_set_next(spm_handle* h, const void* next_support_host, const void* next_target_host) {
+int spm_eval_host_set_next(spm_handle* h, const void* next_support_host, const void* next_target_host,
+                           int next_n_episodes) {
   SPM_CHECK(h != nullptr, "spm_eval_host_set_next: null handle");
-  h->next_su = next_support_host;
-  h->next_qu = next_target_host;
+  SPM_CHECK(next_n_episodes >= 0, "spm_eval_host_set_next: negative episode count");
+  const bool on = next_support_host != nullptr && next_target_host != nullptr && next_n_episodes > 0;
+  h->next_su = on ? next_support_host : nullptr;
+  h->next_qu = on ? next_target_host : nullptr;
+  h->next_n = on ? next_n_episodes : 0;
   return 0;
 }
 

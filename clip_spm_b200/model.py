@@ -363,13 +363,14 @@ class CNN(nn.Module):
                                     inputs["target_labels"])
         return out["loss"][0], out["acc"][0]
 
-    def _set_next(self, lib, h, next_images):
+    def _set_next(self, lib, h, next_images, support_frames_per_episode):
         """next_images = (context_images, target_images) host tensors of the NEXT evaluate_host call (a prefetching
-        DataLoader knows them): their first chunk is copied to the device while this call's tail computes."""
+        DataLoader knows them; same S, Q and frame format as this call, any number of episodes): their first chunk
+        is copied to the device while this call's tail computes."""
         if next_images is not None:
             a, b = next_images
             assert not a.is_cuda and not b.is_cuda and a.is_contiguous() and b.is_contiguous()
-            _lib.check(lib.spm_eval_host_set_next(h, _p(a), _p(b)))
+            _lib.check(lib.spm_eval_host_set_next(h, _p(a), _p(b), int(a.shape[0]) // int(support_frames_per_episode)))
 
     def evaluate_host(self, context_images, context_labels, target_images, real_support_labels, real_target_labels,
                       target_labels, n_episodes, way, next_images=None):
@@ -378,9 +379,9 @@ class CNN(nn.Module):
         h = self._handle()
         self._text()
         lib = _lib.load()
-        self._set_next(lib, h, next_images)
         E, T = int(n_episodes), self.seq_len
         S, Q, W = context_labels.numel() // E, real_target_labels.numel() // E, int(way)
+        self._set_next(lib, h, next_images, S * T)
         for t in (context_images, target_images, context_labels, real_support_labels, real_target_labels):
             assert not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
         assert target_labels.dtype == torch.int64 and not target_labels.is_cuda
@@ -400,9 +401,9 @@ class CNN(nn.Module):
         h = self._handle()
         self._text()
         lib = _lib.load()
-        self._set_next(lib, h, next_images)
         E = int(n_episodes)
         S, Q, W = context_labels.numel() // E, real_target_labels.numel() // E, int(way)
+        self._set_next(lib, h, next_images, S * self.seq_len)
         for t in (context_frames, target_frames):
             assert not t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous() and t.dim() == 4 and t.shape[3] == 3
         assert context_frames.shape[1:] == target_frames.shape[1:]

@@ -106,3 +106,47 @@ def run_sweep(net, n_episodes, way, shot, query_per_class, n_text_cls, rank=0, w
     acc = torch.cat(accs) if accs else torch.zeros(0, device=dev)
     loss = torch.cat(losses) if losses else torch.zeros(0, device=dev)
     return summarize(reduce_stats(make_stats(acc, loss)))
+
+
+def run_listing_sweep(net, split, load_frame, n_episodes, way, shot, n_queries, seed=0, episodes_per_call=8, rank=0,
+                      world_size=1):
+    """The reference's test loop (run/main_run.py:256-293 `Learner.test` over `VideoDataset` episodes) on this library,
+    from DECODED frames: episode e is sampled with `frames.sample_episode_plan` (rng seeded `seed + e`, so any sharding
+    sees the same episodes), its frames come from `load_frame(handle) -> uint8 [H, W, 3]` (the handles stored in
+    `split.videos`), the Resize/CenterCrop/ToTensor chain, the encoder, the head, loss and accuracy run on the GPU
+    (`CNN.evaluate_host_u8`), and while one batch of episodes computes the first chunk of the next is already being
+    copied (`next_images`).  All frames must share one size.  Returns the reduced statistics of `summarize`."""
+    import random
+    from . import frames as F
+    T = net.seq_len
+    mine = shard_episodes(n_episodes, rank, world_size)
+
+    def build(ids):
+        su, qu, lab, rs, rt, tl = [], [], [], [], [], []
+        for e in ids:
+            plan = F.sample_episode_plan(split, way, shot, n_queries, T, train=False, rng=random.Random(seed + e))
+            su += [load_frame(split.videos[v][f]) for v, fr in plan["support"] for f in fr]
+            qu += [load_frame(split.videos[v][f]) for v, fr in plan["target"] for f in fr]
+            lab.append(plan["support_labels"]); rs.append(plan["real_support_labels"])
+            rt.append(plan["real_target_labels"]); tl.append([int(x) for x in plan["target_labels"]])
+        pin = lambda t: t.pin_memory() if torch.cuda.is_available() else t
+        return dict(su=pin(torch.stack([torch.as_tensor(x) for x in su]).contiguous()),
+                    qu=pin(torch.stack([torch.as_tensor(x) for x in qu]).contiguous()),
+                    lab=torch.tensor(lab, dtype=torch.float32), rs=torch.tensor(rs, dtype=torch.float32),
+                    rt=torch.tensor(rt, dtype=torch.float32), tl=torch.tensor(tl, dtype=torch.int64), n=len(ids))
+
+    batches = [mine[i:i + episodes_per_call] for i in range(0, len(mine), episodes_per_call)]
+    accs, losses = [], []
+    cur = build(batches[0]) if batches else None
+    for bi in range(len(batches)):
+        nxt = build(batches[bi + 1]) if bi + 1 < len(batches) else None
+        out = net.evaluate_host_u8(cur["su"], cur["lab"], cur["qu"], cur["rs"], cur["rt"], cur["tl"], cur["n"], way,
+                                   next_images=None if nxt is None else (nxt["su"], nxt["qu"]))
+        accs.append(out["acc"]); losses.append(out["loss"])
+        cur = nxt
+    acc = torch.cat(accs) if accs else torch.zeros(0)
+    loss = torch.cat(losses) if losses else torch.zeros(0)
+    stats = make_stats(acc, loss)
+    if torch.cuda.is_available():
+        stats = stats.to(net._dev)
+    return summarize(reduce_stats(stats))

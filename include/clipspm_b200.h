@@ -129,10 +129,12 @@ int spm_eval_host(spm_handle* h, int n_episodes, int S, int Q, int W, const floa
                   float* logits_host, float* dists_host, float* loss_host, float* acc_host, int32_t* pred_host);
 /* Double buffering across calls (what a DataLoader with prefetching gives the reference's Learner.test loop,
  * run/main_run.py:71,266): tell the library which host image buffers the NEXT spm_eval_host / spm_eval_host_u8 call
- * will read.  The current call then copies that call's first chunk host->device behind its own copies, while its last
- * chunks compute, and the next call starts computing at once.  The hint is consumed by one call; the buffers must
- * not change until the call that reads them returns; a call whose buffers do not match the prefetch ignores it. */
-int spm_eval_host_set_next(spm_handle* h, const void* next_support_host, const void* next_target_host);
+ * will read and how many episodes they hold (same S, Q, frame format as the current call).  The current call then
+ * copies that call's first chunk host->device behind its own copies, while its last chunks compute, and the next call
+ * starts computing at once.  The hint is consumed by one call; the buffers must not change until the call that reads
+ * them returns; a call whose buffers or episode count do not match the prefetch ignores it. */
+int spm_eval_host_set_next(spm_handle* h, const void* next_support_host, const void* next_target_host,
+                           int next_n_episodes);
 
 /* cos_sim + (bi)directional OTAM soft-DTW of n_pairs independent problems:
  *   support [P,W,T,D], target [P,Q,T,D] fp32 -> out [P,Q,W] (accumulated: out = beta*out + alpha*otam) */

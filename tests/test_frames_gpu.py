@@ -95,3 +95,35 @@ def test_rn50_encode_frames_u8():
     from clip_spm_b200.ops import transform_frames
     frames = torch.from_numpy(P.make_frames("portrait_360x480")).cuda()
     assert torch.equal(m.encode_frames(transform_frames(frames)), m.encode_frames_u8(frames))
+
+
+def test_listing_sweep_matches_per_episode_forward():
+    """sampler plan -> decoded uint8 frames -> evaluate_host_u8 batches with next-call prefetch (sweep.run_listing_sweep)
+    == the same episodes one at a time through transform_frames + CNN.evaluate (the reference loop's granularity)"""
+    import random
+    from clip_spm_b200 import frames as F, ops, sweep
+    from oracle import clipspm_oracle as O
+    ci = H.case_inputs("vit_2w1s_t2_p0")
+    net = H.build_cuda_model(ci, max_episodes=2)
+    g = torch.Generator().manual_seed(3)
+    sp = F.Split()
+    for vid in range(3):
+        for cls in range(4):
+            n = 4 + (cls + vid) % 3
+            sp.add_vid([torch.randint(0, 256, (120, 160, 3), dtype=torch.uint8, generator=g) for _ in range(n)], cls)
+    n_ep, way, shot, nq, T = 5, 2, 1, 1, 2
+    res = sweep.run_listing_sweep(net, sp, lambda fr: fr, n_ep, way, shot, nq, seed=50, episodes_per_call=2)
+    accs, losses = [], []
+    for e in range(n_ep):
+        plan = F.sample_episode_plan(sp, way, shot, nq, T, train=False, rng=random.Random(50 + e))
+        grab = lambda items: ops.transform_frames(torch.stack([sp.videos[v][f] for v, fr in items for f in fr]).cuda())
+        ep = dict(context_images=grab(plan["support"]), target_images=grab(plan["target"]),
+                  context_labels=torch.tensor(plan["support_labels"]).cuda(),
+                  real_support_labels=torch.tensor(plan["real_support_labels"]).cuda(),
+                  real_target_labels=torch.tensor(plan["real_target_labels"]).cuda(),
+                  target_labels=torch.tensor([int(x) for x in plan["target_labels"]]).cuda())
+        loss, acc = net.evaluate(ep)
+        accs.append(float(acc)); losses.append(float(loss))
+    assert res["n"] == n_ep
+    assert abs(res["accuracy"] - 100.0 * sum(accs) / n_ep) < 1e-4
+    assert abs(res["loss"] - sum(losses) / n_ep) < 2e-3 * max(1.0, abs(sum(losses) / n_ep))
