@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SPM_ABI_VERSION 2 /* 2: spm_config gained `head`, `cls_value` */
+#define SPM_ABI_VERSION 2 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next */
 
 typedef struct spm_handle spm_handle;
 
