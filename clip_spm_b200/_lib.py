@@ -52,6 +52,7 @@ SIGNATURES = {
     "spm_class_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "spm_encode_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "spm_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7),
+    "spm_head_stage": (c_int, [c_void_p, c_void_p, ctypes.c_char_p, c_void_p, c_ll, ctypes.POINTER(c_ll)]),
     "spm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7),
     "spm_eval": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),
     "spm_eval_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float] + [c_void_p] * 5),

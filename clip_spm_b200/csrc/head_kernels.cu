@@ -111,20 +111,30 @@ int k_mo_dist(cudaStream_t st, const float* new_m, const float* z_tok, long long
 // X: [E, N, T, D] with the S support videos first.  tok_b: [E*N, D] (rows e*N+s written here; rows of queries
 // are written later by the token_tr GEMM epilogue).
 // ------------------------------------------------------------------------------------------------------
-__global__ void token_prepare_kernel(const float* __restrict__ text, const float* __restrict__ real_support,
+__global__ void token_prepare_kernel(const float* __restrict__ text, int n_cls, const float* __restrict__ real_support,
                                      const float* __restrict__ real_target, const float* __restrict__ X, int S, int Q,
-                                     int T, int D, float* __restrict__ tok_b, float* __restrict__ tt_in) {
+                                     int T, int D, float* __restrict__ tok_b, float* __restrict__ tt_in,
+                                     int* __restrict__ err_flag) {
   extern __shared__ float sm_tp[];  // token[D] + red[32] + qmean[Q]
   float* token = sm_tp;
   float* red = token + D;
   float* qmean = red + 32;
   const int e = blockIdx.x, N = S + Q;
+  // a class id outside the text table (the reference would raise an IndexError, model_clipspm.py:116-121): flag the
+  // call (NaN logits + an error from the host entry points) and read row 0 instead of out of bounds
+  if (threadIdx.x == 0) {
+    bool bad = false;
+    for (int q = 0; q < Q; ++q) { const float r = real_target[e * Q + q]; bad |= !(r >= 0.f && r < (float)n_cls); }
+    for (int s = 0; s < S; ++s) { const float r = real_support[e * S + s]; bad |= !(r >= 0.f && r < (float)n_cls); }
+    if (bad && err_flag != nullptr) atomicExch(err_flag, 2);
+  }
+  auto row = [n_cls](float r) { return (r >= 0.f && r < (float)n_cls) ? (long long)r : 0LL; };
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float acc = 0.f;
     // torch.concat([target_context_support, context_support]).mean(0): targets first (summation order)
-    for (int q = 0; q < Q; ++q) acc += text[(long long)real_target[e * Q + q] * D + d];
+    for (int q = 0; q < Q; ++q) acc += text[row(real_target[e * Q + q]) * D + d];
     for (int s = 0; s < S; ++s) {
-      const float v = text[(long long)real_support[e * S + s] * D + d];
+      const float v = text[row(real_support[e * S + s]) * D + d];
       acc += v;
       tok_b[((long long)e * N + s) * D + d] = v;
     }
@@ -142,10 +152,11 @@ __global__ void token_prepare_kernel(const float* __restrict__ text, const float
     for (int d = threadIdx.x; d < D; d += blockDim.x)
       tt_in[((long long)e * Q + q) * D + d] = token[d] * qmean[q];
 }
-int k_token_prepare(cudaStream_t st, const float* text, const float* real_support, const float* real_target,
-                    const float* X, int E, int S, int Q, int T, int D, float* tok_b, float* tt_in) {
+int k_token_prepare(cudaStream_t st, const float* text, int n_cls, const float* real_support, const float* real_target,
+                    const float* X, int E, int S, int Q, int T, int D, float* tok_b, float* tt_in, int* err_flag) {
   const size_t smem = (size_t)(D + 32 + Q) * sizeof(float);
-  token_prepare_kernel<<<E, 256, smem, st>>>(text, real_support, real_target, X, S, Q, T, D, tok_b, tt_in);
+  token_prepare_kernel<<<E, 256, smem, st>>>(text, n_cls, real_support, real_target, X, S, Q, T, D, tok_b, tt_in,
+                                             err_flag);
   SPM_LAUNCH_CHECK();
   return 0;
 }
@@ -396,6 +407,31 @@ int k_finalize(cudaStream_t st, const float* accd, const float* d3, int E, int Q
   if (Q > 64) return -2;
   finalize_kernel<<<E, 64, 0, st>>>(accd, d3, Q, W, target, tasks_per_batch, dists, logits, loss, accuracy, pred,
                                     err_flag);
+  SPM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// strided 4-D gather (spm_head_stage: copies one stage tensor of the head workspace out in the reference's layout)
+//   out[i0, i1, i2, :n3] = src[i0*s0 + i1*s1 + i2*s2 + (0..n3)]      n3 % 4 == 0, strides in floats (% 4 == 0)
+// ------------------------------------------------------------------------------------------------------
+__global__ void gather4_kernel(const float* __restrict__ src, int n1, int n2, int n3, long long s0, long long s1,
+                               long long s2, long long total4, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int d4 = n3 / 4;
+  const int c = (int)(i % d4);
+  const int i2 = (int)((i / d4) % n2);
+  const int i1 = (int)((i / ((long long)d4 * n2)) % n1);
+  const long long i0 = i / ((long long)d4 * n2 * n1);
+  reinterpret_cast<float4*>(out)[i] = *reinterpret_cast<const float4*>(src + i0 * s0 + i1 * s1 + i2 * s2 + c * 4);
+}
+int k_gather4(cudaStream_t st, const float* src, int n0, int n1, int n2, int n3, long long s0, long long s1,
+              long long s2, float* out) {
+  if (n3 % 4 != 0 || s0 % 4 != 0 || s1 % 4 != 0 || s2 % 4 != 0) return -2;
+  const long long total4 = (long long)n0 * n1 * n2 * (n3 / 4);
+  if (total4 <= 0) return 0;
+  gather4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(src, n1, n2, n3, s0, s1, s2, total4, out);
   SPM_LAUNCH_CHECK();
   return 0;
 }

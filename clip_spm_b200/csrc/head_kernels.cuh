@@ -11,8 +11,10 @@ int k_motion_reduce(cudaStream_t st, const float* conv, const float* x, long lon
                     float* out);
 int k_mo_dist(cudaStream_t st, const float* new_m, const float* z_tok, long long tok_stride, int E, int S, int Q, int D,
               const float* mo_alpha1, float* dists);
-int k_token_prepare(cudaStream_t st, const float* text, const float* real_support, const float* real_target,
-                    const float* X, int E, int S, int Q, int T, int D, float* tok_b, float* tt_in);
+int k_token_prepare(cudaStream_t st, const float* text, int n_cls, const float* real_support, const float* real_target,
+                    const float* X, int E, int S, int Q, int T, int D, float* tok_b, float* tt_in, int* err_flag);
+int k_gather4(cudaStream_t st, const float* src, int n0, int n1, int n2, int n3, long long s0, long long s1,
+              long long s2, float* out);
 int k_seq_build(cudaStream_t st, const float* tok, const float* gt, const float* X, const float* gv, int n_calls,
                 int V, int T, int D, float alpha, float* seq);
 int k_seq_attention_init();

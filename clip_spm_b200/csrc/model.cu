@@ -18,14 +18,19 @@ int forward_impl(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, con
   const int T = h->cfg.seq_len, D = h->D, N = S + Q;
   const long long nf = (long long)E * N * T;
   if (nf > h->xall_cap) {
-    SPM_TRY(dalloc_t(h, &h->Xall, nf * D));
+    SPM_TRY(drealloc_t(h, &h->Xall, nf * D));
     h->xall_cap = nf;
     h->head_plans.clear();
   }
-  if ((long long)E * Q * W > h->tmp_out_cap) {
-    SPM_TRY(dalloc_t(h, &h->tmp_logits, (long long)E * Q * W));
-    SPM_TRY(dalloc_t(h, &h->tmp_dists, E));
-    h->tmp_out_cap = (long long)E * Q * W;
+  // scratch outputs for callers that only want loss / accuracy: each buffer has its own capacity (a call with fewer
+  // episodes but more logits per episode, or the reverse, must not reuse a buffer sized for the other)
+  if (logits == nullptr && (long long)E * Q * W > h->tmp_logits_cap) {
+    SPM_TRY(drealloc_t(h, &h->tmp_logits, (long long)E * Q * W));
+    h->tmp_logits_cap = (long long)E * Q * W;
+  }
+  if (dists == nullptr && E > h->tmp_dists_cap) {
+    SPM_TRY(drealloc_t(h, &h->tmp_dists, E));
+    h->tmp_dists_cap = E;
   }
   if (logits == nullptr) logits = h->tmp_logits;
   if (dists == nullptr) dists = h->tmp_dists;
@@ -56,7 +61,7 @@ int forward_impl(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, con
     // RN50 consumes contiguous runs of frames in its own 64-frame chunks: encode [all supports | all queries] and
     // scatter the feature rows into the episode-major X
     if (nf > h->feats_cap) {
-      SPM_TRY(dalloc_t(h, &h->feats, nf * D));
+      SPM_TRY(drealloc_t(h, &h->feats, nf * D));
       h->feats_cap = nf;
     }
     Segment two[2] = {segs[0], segs[1]};
@@ -220,7 +225,7 @@ int spm_set_text_features(spm_handle* h, void* stream, const float* table, int n
   SPM_CHECK(h != nullptr && table != nullptr, "spm_set_text_features: null argument");
   SPM_CHECK(dim == h->D, "spm_set_text_features: feature dim does not match the backbone's mid_dim");
   SPM_CHECK(n_cls >= 1, "spm_set_text_features: empty table");
-  if (n_cls > h->n_cls) SPM_TRY(dalloc_t(h, &h->text, (long long)n_cls * dim));
+  if (n_cls > h->n_cls) SPM_TRY(drealloc_t(h, &h->text, (long long)n_cls * dim));
   SPM_CUDA(cudaMemcpyAsync(h->text, table, (size_t)n_cls * dim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   h->n_cls = n_cls;
   h->text_set = true;
@@ -231,7 +236,7 @@ int spm_set_text_features_train(spm_handle* h, void* stream, const float* table,
   SPM_CHECK(h != nullptr && table != nullptr, "spm_set_text_features_train: null argument");
   SPM_CHECK(dim == h->D, "spm_set_text_features_train: feature dim does not match the backbone's mid_dim");
   SPM_CHECK(n_cls >= 1, "spm_set_text_features_train: empty table");
-  if (n_cls > h->n_cls_train) SPM_TRY(dalloc_t(h, &h->text_train, (long long)n_cls * dim));
+  if (n_cls > h->n_cls_train) SPM_TRY(drealloc_t(h, &h->text_train, (long long)n_cls * dim));
   SPM_CUDA(cudaMemcpyAsync(h->text_train, table, (size_t)n_cls * dim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   h->n_cls_train = n_cls;
   return 0;
@@ -290,6 +295,11 @@ int spm_head(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, c
                   dists_out, nullptr, nullptr, nullptr);
 }
 
+int spm_head_stage(spm_handle* h, void* stream, const char* name, float* out, long long capacity, long long* numel) {
+  SPM_CHECK(h != nullptr && name != nullptr, "spm_head_stage: null argument");
+  return head_stage(h, (cudaStream_t)stream, name, out, capacity, numel);
+}
+
 int spm_forward(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, const float* support_images,
                 const float* target_images, const float* support_labels, const float* real_support,
                 const float* real_target, float* logits_out, float* dists_out) {
@@ -330,21 +340,41 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
     SPM_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
   }
   spm_handle::Stage& s = h->stage[0];
+  // every ring has its own capacity: the image rings are sized in bytes, the label / result rings by S, Q, Q*W and R
+  // (a later call with the same frame counts but a larger Q*W must regrow the logits ring, not write past it)
   if (R * fs * frame_bytes > h->stage_cap_bytes_s || R * fq * frame_bytes > h->stage_cap_bytes_q ||
-      R * fs > h->stage_cap_frames_s || R * fq > h->stage_cap_frames_q) {
-    SPM_TRY(dalloc_t(h, &s.su, R * fs * frame_bytes));
-    SPM_TRY(dalloc_t(h, &s.qu, R * fq * frame_bytes));
-    h->stage_cap_bytes_s = R * fs * frame_bytes; h->stage_cap_bytes_q = R * fq * frame_bytes;
-    SPM_TRY(dalloc_t(h, &s.lab, (long long)R * S));
-    SPM_TRY(dalloc_t(h, &s.rs, (long long)R * S));
-    SPM_TRY(dalloc_t(h, &s.rt, (long long)R * Q));
-    SPM_TRY(dalloc_t(h, &s.tl, (long long)R * Q));
-    SPM_TRY(dalloc_t(h, &s.logits, (long long)R * Q * W));
-    SPM_TRY(dalloc_t(h, &s.dists, R));
-    SPM_TRY(dalloc_t(h, &s.loss, R));
-    SPM_TRY(dalloc_t(h, &s.acc, R));
-    SPM_TRY(dalloc_t(h, &s.pred, (long long)R * Q));
-    h->stage_cap_frames_s = R * fs; h->stage_cap_frames_q = R * fq;
+      (long long)R * S > h->stage_cap_S || (long long)R * Q > h->stage_cap_Q || (long long)R * Q * W > h->stage_cap_QW ||
+      R > h->stage_cap_R) {
+    SPM_CUDA(cudaDeviceSynchronize());   // nothing may still be using the rings that are being replaced
+    if (R * fs * frame_bytes > h->stage_cap_bytes_s) {
+      SPM_TRY(drealloc_t(h, &s.su, R * fs * frame_bytes));
+      h->stage_cap_bytes_s = R * fs * frame_bytes;
+    }
+    if (R * fq * frame_bytes > h->stage_cap_bytes_q) {
+      SPM_TRY(drealloc_t(h, &s.qu, R * fq * frame_bytes));
+      h->stage_cap_bytes_q = R * fq * frame_bytes;
+    }
+    if ((long long)R * S > h->stage_cap_S) {
+      SPM_TRY(drealloc_t(h, &s.lab, (long long)R * S));
+      SPM_TRY(drealloc_t(h, &s.rs, (long long)R * S));
+      h->stage_cap_S = (long long)R * S;
+    }
+    if ((long long)R * Q > h->stage_cap_Q) {
+      SPM_TRY(drealloc_t(h, &s.rt, (long long)R * Q));
+      SPM_TRY(drealloc_t(h, &s.tl, (long long)R * Q));
+      SPM_TRY(drealloc_t(h, &s.pred, (long long)R * Q));
+      h->stage_cap_Q = (long long)R * Q;
+    }
+    if ((long long)R * Q * W > h->stage_cap_QW) {
+      SPM_TRY(drealloc_t(h, &s.logits, (long long)R * Q * W));
+      h->stage_cap_QW = (long long)R * Q * W;
+    }
+    if (R > h->stage_cap_R) {
+      SPM_TRY(drealloc_t(h, &s.dists, R));
+      SPM_TRY(drealloc_t(h, &s.loss, R));
+      SPM_TRY(drealloc_t(h, &s.acc, R));
+      h->stage_cap_R = R;
+    }
   }
   // prefetch buffers for the first chunk of the next call (allocated before anything is enqueued: cudaMalloc syncs)
   // (a whole compute chunk: with its copy out of the way the call can run full-size chunks from the start)
@@ -357,8 +387,8 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
   const long long my_s = (long long)first_n * fs * frame_bytes, my_q = (long long)first_n * fq * frame_bytes;
   if (hint_su != nullptr && (pf_s > h->pf_cap_s || pf_q > h->pf_cap_q)) {
     SPM_CUDA(cudaStreamSynchronize(h->copy_stream));   // nobody may still be writing the old buffers
-    SPM_TRY(dalloc_t(h, &h->pf_su, pf_s));
-    SPM_TRY(dalloc_t(h, &h->pf_qu, pf_q));
+    SPM_TRY(drealloc_t(h, &h->pf_su, pf_s));
+    SPM_TRY(drealloc_t(h, &h->pf_qu, pf_q));
     h->pf_cap_s = pf_s; h->pf_cap_q = pf_q;
     h->pf_src_su = h->pf_src_qu = nullptr;
   }
@@ -456,6 +486,7 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
   if (pred_h) memcpy(pred_h, p_pred, (size_t)n_episodes * Q * 4);
   int flag = 0;
   SPM_CUDA(cudaMemcpy(&flag, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  SPM_CHECK(flag != 2, "spm_eval_host: a real_support / real_target class id lies outside the text-feature table");
   SPM_CHECK(flag == 0, "spm_eval_host: an episode's number of distinct support labels differs from `W`");
   return 0;
 }

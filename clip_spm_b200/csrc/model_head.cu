@@ -78,31 +78,31 @@ int ensure_head_workspace(spm_handle* h, int E, int S, int Q, int W) {
                   cQ = std::max<long long>(Q, h->head_cap_Q), cW = std::max<long long>(W, h->head_cap_W);
   const long long T = h->cfg.seq_len, D = h->D, N = cS + cQ, V = cE * N;
   const long long R2 = 2 * V * (T + 1), R1 = cE * T * (cW + cS + 1 + cQ), R = std::max(R1, R2);
-  SPM_TRY(dalloc_t(h, &h->Xhead, V * T * D));
+  SPM_TRY(drealloc_t(h, &h->Xhead, V * T * D));
   h->X = h->Xhead;
-  SPM_TRY(dalloc_t(h, &h->XC, V * T * 3 * D));
-  SPM_TRY(dalloc_t(h, &h->C1, V * T * D));
-  SPM_TRY(dalloc_t(h, &h->C2, V * T * D));
-  SPM_TRY(dalloc_t(h, &h->TOK, 2 * V * D));
-  SPM_TRY(dalloc_t(h, &h->TTIN, cE * cQ * D));
-  SPM_TRY(dalloc_t(h, &h->TTH, cE * cQ * HEAD_MLP));
-  SPM_TRY(dalloc_t(h, &h->GTH, 2 * V * h->HT));
-  SPM_TRY(dalloc_t(h, &h->GT, 2 * V * D));
-  SPM_TRY(dalloc_t(h, &h->GVH, V * T * h->HV));
-  SPM_TRY(dalloc_t(h, &h->GV, V * T * D));
-  SPM_TRY(dalloc_t(h, &h->SEQ, R * D));
-  SPM_TRY(dalloc_t(h, &h->HN, R * D));
-  SPM_TRY(dalloc_t(h, &h->QKVH, R * 3 * HEAD_INNER));
-  SPM_TRY(dalloc_t(h, &h->AO, R * HEAD_INNER));
-  SPM_TRY(dalloc_t(h, &h->Y, R * D));
-  SPM_TRY(dalloc_t(h, &h->FFH, R * HEAD_MLP));
-  SPM_TRY(dalloc_t(h, &h->Z, R2 * D));
-  SPM_TRY(dalloc_t(h, &h->Z1, R1 * D));
-  SPM_TRY(dalloc_t(h, &h->NEWM, V * D));
-  SPM_TRY(dalloc_t(h, &h->SUPRO, cE * cW * T * D));
-  SPM_TRY(dalloc_t(h, &h->SUPRO2, cE * cW * T * D));
-  SPM_TRY(dalloc_t(h, &h->ACC, cE * cQ * cW));
-  SPM_TRY(dalloc_t(h, &h->D3, cE * cW));
+  SPM_TRY(drealloc_t(h, &h->XC, V * T * 3 * D));
+  SPM_TRY(drealloc_t(h, &h->C1, V * T * D));
+  SPM_TRY(drealloc_t(h, &h->C2, V * T * D));
+  SPM_TRY(drealloc_t(h, &h->TOK, 2 * V * D));
+  SPM_TRY(drealloc_t(h, &h->TTIN, cE * cQ * D));
+  SPM_TRY(drealloc_t(h, &h->TTH, cE * cQ * HEAD_MLP));
+  SPM_TRY(drealloc_t(h, &h->GTH, 2 * V * h->HT));
+  SPM_TRY(drealloc_t(h, &h->GT, 2 * V * D));
+  SPM_TRY(drealloc_t(h, &h->GVH, V * T * h->HV));
+  SPM_TRY(drealloc_t(h, &h->GV, V * T * D));
+  SPM_TRY(drealloc_t(h, &h->SEQ, R * D));
+  SPM_TRY(drealloc_t(h, &h->HN, R * D));
+  SPM_TRY(drealloc_t(h, &h->QKVH, R * 3 * HEAD_INNER));
+  SPM_TRY(drealloc_t(h, &h->AO, R * HEAD_INNER));
+  SPM_TRY(drealloc_t(h, &h->Y, R * D));
+  SPM_TRY(drealloc_t(h, &h->FFH, R * HEAD_MLP));
+  SPM_TRY(drealloc_t(h, &h->Z, R2 * D));
+  SPM_TRY(drealloc_t(h, &h->Z1, R1 * D));
+  SPM_TRY(drealloc_t(h, &h->NEWM, V * D));
+  SPM_TRY(drealloc_t(h, &h->SUPRO, cE * cW * T * D));
+  SPM_TRY(drealloc_t(h, &h->SUPRO2, cE * cW * T * D));
+  SPM_TRY(drealloc_t(h, &h->ACC, cE * cQ * cW));
+  SPM_TRY(drealloc_t(h, &h->D3, cE * cW));
   if (h->err_flag == nullptr) {
     SPM_TRY(dalloc_t(h, &h->err_flag, 1));
     SPM_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
@@ -243,7 +243,7 @@ int fsar_head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, co
   if (h->text_train != nullptr) {
     const long long need = (long long)V * h->n_cls_train;
     if (need > h->cls_cap) {
-      SPM_TRY(dalloc_t(h, &h->CLS, need));
+      SPM_TRY(drealloc_t(h, &h->CLS, need));
       h->cls_cap = need;
     }
     SPM_KERNEL(k_fsar_class_logits(st, h->X, h->text_train, h->n_cls_train, h->fsar_scale, V, T, D, h->CLS));
@@ -283,7 +283,8 @@ int head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const f
   SPM_GEMM_RUN(pl->mc2);
   SPM_KERNEL(k_motion_reduce(st, h->C2, h->X, TD, V, T, D, h->TOK));  // tokens of the `mo` se_te call
   // ---- SPM tokens (model_clipspm.py:120-121,213-216)
-  SPM_KERNEL(k_token_prepare(st, h->text, real_s, real_t, h->X, E, S, Q, T, D, h->TOK + (long long)V * D, h->TTIN));
+  SPM_KERNEL(k_token_prepare(st, h->text, h->n_cls, real_s, real_t, h->X, E, S, Q, T, D, h->TOK + (long long)V * D,
+                             h->TTIN, h->err_flag));
   SPM_GEMM_RUN(pl->tt0);
   SPM_GEMM_RUN(pl->tt3);
   // ---- gates + the two live se_te batches (mo: tokens = motion; sem: tokens = prompts), one context2 pass
@@ -315,6 +316,50 @@ int head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const f
                     E, W, 1, T, D, h->cfg.single_direct, 1.f, 0.f, h->D3));
   SPM_KERNEL(k_finalize(st, h->ACC, h->D3, E, Q, W, target_labels, tasks_per_batch, dists, logits, loss, acc, pred,
                         h->err_flag));
+  h->last_E = E; h->last_S = S; h->last_Q = Q; h->last_W = W;
+  return 0;
+}
+
+// Stage tensors of the most recent CLIP-SPM head pass, gathered out of the workspace in the reference's layouts
+// (the tensors SURVEY.md 8(c) lists; tests compare each with the golden written from the executed reference).
+int head_stage(spm_handle* h, cudaStream_t st, const char* name, float* out, long long capacity, long long* numel) {
+  SPM_CHECK(h->cfg.head == SPM_HEAD_CLIPSPM, "spm_head_stage: only the CLIP-SPM head keeps named stage tensors");
+  SPM_CHECK(h->last_E > 0, "spm_head_stage: no head pass has run on this handle yet");
+  const int E = h->last_E, S = h->last_S, Q = h->last_Q, W = h->last_W;
+  const int T = h->cfg.seq_len, D = h->D, N = S + Q, V = E * N, L1 = W + S + 1 + Q;
+  const long long TD = (long long)T * D, T1D = (long long)(T + 1) * D, L1D = (long long)L1 * D;
+  const float* Zb = h->Z + (long long)V * T1D;            // outputs of the `sem` se_te batch
+  const float* Zm = h->Z;                                 // outputs of the `mo` se_te batch
+  const float* tokb = h->TOK + (long long)V * D;          // tokens of the `sem` batch
+  struct View { const float* p; int n0, n1, n2; long long s0, s1, s2; };
+  const std::string n(name ? name : "");
+  View v{};
+  if (n == "su_mo") v = {h->TOK, E, S, 1, (long long)N * D, D, 0};                       // model_clipspm.py:195 (b1)
+  else if (n == "qu_mo") v = {h->TOK + (long long)S * D, E, Q, 1, (long long)N * D, D, 0};
+  else if (n == "support_token") v = {tokb, E, S, 1, (long long)N * D, D, 0};           // :120 (a4)
+  else if (n == "target_token") v = {tokb + (long long)S * D, E, Q, 1, (long long)N * D, D, 0};   // :216 token_tr (c3)
+  else if (n == "su_mo_refined") v = {Zm + D, E, S, T, N * T1D, T1D, D};                // :197 x' of the mo se_te (c1)
+  else if (n == "qu_mo_refined") v = {Zm + S * T1D + D, E, Q, T, N * T1D, T1D, D};
+  else if (n == "su_mo_token") v = {Zm, E, S, 1, N * T1D, T1D, 0};                      // m' (c1)
+  else if (n == "qu_mo_token") v = {Zm + S * T1D, E, Q, 1, N * T1D, T1D, 0};
+  else if (n == "su_mo2") v = {h->NEWM, E, S, 1, (long long)N * D, D, 0};               // :200 m'' (b1 on refined frames)
+  else if (n == "qu_mo2") v = {h->NEWM + (long long)S * D, E, Q, 1, (long long)N * D, D, 0};
+  else if (n == "su_real") v = {Zb + D, E, S, T, N * T1D, T1D, D};                      // :218,221 (c1/c4)
+  else if (n == "qu_fake") v = {Zb + S * T1D + D, E, Q, T, N * T1D, T1D, D};
+  else if (n == "token_s_real") v = {Zb, E, S, 1, N * T1D, T1D, 0};
+  else if (n == "token_q_fake") v = {Zb + S * T1D, E, Q, 1, N * T1D, T1D, 0};
+  else if (n == "su_pro") v = {h->SUPRO, E, W, T, W * TD, TD, D};                       // :231-239 (c6)
+  else if (n == "su_t2") v = {h->Z1, E, W, T, T * L1D, D, L1D};                         // :275-294 (c5)
+  else if (n == "su_2") v = {h->Z1 + (long long)W * D, E, S, T, T * L1D, D, L1D};
+  else if (n == "qu_t2") v = {h->Z1 + (long long)(W + S) * D, E, 1, T, T * L1D, D, L1D};
+  else if (n == "qu_2") v = {h->Z1 + (long long)(W + S + 1) * D, E, Q, T, T * L1D, D, L1D};
+  else if (n == "su_pro2") v = {h->SUPRO2, E, W, T, W * TD, TD, D};                     // :133-137 on the PADM output
+  else { set_error("spm_head_stage: unknown stage '" + n + "'"); return 1; }
+  const long long total = (long long)v.n0 * v.n1 * v.n2 * D;
+  if (numel != nullptr) *numel = total;
+  if (out == nullptr) return 0;   // size query
+  SPM_CHECK(capacity >= total, "spm_head_stage: output buffer too small");
+  SPM_KERNEL(k_gather4(st, v.p, v.n0, v.n1, v.n2, D, v.s0, v.s1, v.s2, out));
   return 0;
 }
 

@@ -152,6 +152,7 @@ struct spm_handle {
         *AO = nullptr, *Y = nullptr, *FFH = nullptr, *Z = nullptr, *Z1 = nullptr, *NEWM = nullptr, *SUPRO = nullptr,
         *SUPRO2 = nullptr, *ACC = nullptr, *D3 = nullptr;
   int* err_flag = nullptr;
+  int last_E = 0, last_S = 0, last_Q = 0, last_W = 0;   // shape of the most recent CLIP-SPM head pass (spm_head_stage)
   std::vector<std::unique_ptr<spm::HeadPlan>> head_plans;
   // sibling head CLIP-FSAR (cfg.head == SPM_HEAD_CLIPFSAR; models/model_clipfsar.py)
   spm::CtxW fsar_ctx = {};
@@ -164,7 +165,7 @@ struct spm_handle {
   // `X` is the feature block the head currently reads: its own buffer (Xhead), or a group of episodes inside Xall
   // when the forward pipelines episode groups (encoder of group g+1 overlaps the head of group g on head_stream)
   float *Xhead = nullptr, *Xall = nullptr;
-  long long xall_cap = 0, tmp_out_cap = 0;
+  long long xall_cap = 0, tmp_logits_cap = 0, tmp_dists_cap = 0;
   cudaStream_t head_stream = nullptr;
   cudaEvent_t head_done = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
@@ -178,7 +179,8 @@ struct spm_handle {
     int* pred = nullptr;
     cudaEvent_t copied = nullptr, done = nullptr;
   } stage[2];
-  long long stage_cap_frames_s = 0, stage_cap_frames_q = 0, stage_cap_bytes_s = 0, stage_cap_bytes_q = 0;
+  long long stage_cap_bytes_s = 0, stage_cap_bytes_q = 0;            // image staging rings
+  long long stage_cap_S = 0, stage_cap_Q = 0, stage_cap_QW = 0, stage_cap_R = 0;   // label / result rings (R slots each)
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
   std::vector<cudaEvent_t> ev_copied, ev_done;  // per chunk of one spm_eval_host call
   // pinned host landing zone for the results: an async D2H into the caller's (possibly pageable) buffers would
@@ -207,6 +209,19 @@ inline int dalloc(spm_handle* h, void** p, size_t bytes) {
 template <class T>
 int dalloc_t(spm_handle* h, T** p, long long n) {
   return dalloc(h, reinterpret_cast<void**>(p), (size_t)n * sizeof(T));
+}
+// Regrow: the superseded buffer is freed (after a device sync -- work enqueued earlier may still read it) instead of
+// staying in `allocs` until spm_destroy, so a sweep over varying episode shapes does not accumulate dead workspace.
+template <class T>
+int drealloc_t(spm_handle* h, T** p, long long n) {
+  if (*p != nullptr) {
+    SPM_CUDA(cudaDeviceSynchronize());
+    auto it = std::find(h->allocs.begin(), h->allocs.end(), static_cast<void*>(*p));
+    if (it != h->allocs.end()) h->allocs.erase(it);
+    SPM_CUDA(cudaFree(*p));
+    *p = nullptr;
+  }
+  return dalloc_t(h, p, n);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -281,6 +296,7 @@ int head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const f
              const float* real_t, const long long* target_labels, float tasks_per_batch, float* logits, float* dists,
              float* loss, float* acc, int* pred);
 int reset_err_flag(spm_handle* h, cudaStream_t st);
+int head_stage(spm_handle* h, cudaStream_t st, const char* name, float* out, long long capacity, long long* numel);
 int check_shapes(spm_handle* h, int E, int S, int Q, int W);
 
 }  // namespace detail

@@ -258,7 +258,7 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
 int segment_images(spm_handle* h, cudaStream_t st, const Segment& seg, long long a, long long b, const float** out) {
   if (seg.frames_u8 == nullptr) { *out = seg.images + a * FRAME_ELEMS; return 0; }
   if (b - a > h->img_scratch_cap) {
-    SPM_TRY(dalloc_t(h, &h->img_scratch, (b - a) * FRAME_ELEMS));
+    SPM_TRY(drealloc_t(h, &h->img_scratch, (b - a) * FRAME_ELEMS));
     h->img_scratch_cap = b - a;
   }
   SPM_KERNEL(k_frame_transform(st, seg.frames_u8 + a * (long long)seg.H * seg.W * 3, (int)(b - a), seg.H, seg.W,

@@ -456,3 +456,14 @@ class CNN(nn.Module):
         _lib.check(_lib.load().spm_head(h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), E, S, Q, W,
                                         _p(su), _p(qu), _p(lab), _p(rs), _p(rt), _p(logits), _p(dists)))
         return {"logits": logits, "dists": dists}
+
+    def head_stage(self, name):
+        """Test hook: a named intermediate tensor of the most recent head pass (spm_head_stage), flat [numel]."""
+        h = self._handle()
+        lib = _lib.load()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        n = ctypes.c_longlong(0)
+        _lib.check(lib.spm_head_stage(h, st, name.encode(), None, 0, ctypes.byref(n)))
+        out = torch.empty(n.value, device=self._dev)
+        _lib.check(lib.spm_head_stage(h, st, name.encode(), _p(out), n.value, ctypes.byref(n)))
+        return out

@@ -92,20 +92,51 @@ def synthetic_episode_batch(episode_ids, way, shot, query_per_class, T, n_text_c
     return out
 
 
-def run_sweep(net, n_episodes, way, shot, query_per_class, n_text_cls, rank=0, world_size=1, episodes_per_call=1):
-    """Evaluate this rank's shard on the CUDA path and return the REDUCED statistics (identical on every rank)."""
+def gather_predictions(pred, episode_ids, n_episodes, group=None):
+    """Per-episode predictions of every rank, in global episode order (the optional gather used to check
+    that a sharded sweep predicts exactly what the unsharded one does).  pred [n_local, Q] int; rows of episodes this
+    rank does not own are -1 before the exchange, so one all-reduce(MAX) assembles the table on every rank."""
+    import torch.distributed as dist
+    Q = pred.shape[1] if pred.dim() == 2 else 0
+    table = torch.full((n_episodes, Q), -1, dtype=torch.int32, device=pred.device)
+    if len(episode_ids):
+        table[torch.as_tensor(list(episode_ids), device=pred.device, dtype=torch.long)] = pred.to(torch.int32)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(table, op=dist.ReduceOp.MAX, group=group)
+    return table
+
+
+def run_sweep(net, n_episodes, way, shot, query_per_class, n_text_cls, rank=0, world_size=1, episodes_per_call=1,
+              return_predictions=False, local_only=False):
+    """Evaluate this rank's shard on the CUDA path and return the REDUCED statistics (identical on every rank); with
+    return_predictions also the gathered [n_episodes, Q] prediction table and this rank's logits (by episode id)."""
     mine = shard_episodes(n_episodes, rank, world_size)
-    accs, losses = [], []
+    accs, losses, preds, logits = [], [], [], {}
     for i in range(0, len(mine), episodes_per_call):
         ids = mine[i:i + episodes_per_call]
         b = synthetic_episode_batch(ids, way, shot, query_per_class, net.seq_len, n_text_cls, net._dev)
         out = net.forward_episodes(b["context_images"], b["context_labels"], b["target_images"],
                                    b["real_support_labels"], b["real_target_labels"], len(ids), b["target_labels"])
         accs.append(out["acc"]); losses.append(out["loss"])
+        if return_predictions:
+            preds.append(out["pred"])
+            for j, e in enumerate(ids):
+                logits[e] = out["logits"][j].clone()
     dev = net._dev
     acc = torch.cat(accs) if accs else torch.zeros(0, device=dev)
     loss = torch.cat(losses) if losses else torch.zeros(0, device=dev)
-    return summarize(reduce_stats(make_stats(acc, loss)))
+    stats = make_stats(acc, loss)
+    res = summarize(stats if local_only else reduce_stats(stats))
+    if not return_predictions:
+        return res
+    Q = way * query_per_class
+    pred = torch.cat(preds) if preds else torch.zeros(0, Q, dtype=torch.int32, device=dev)
+    if local_only:
+        table = torch.full((n_episodes, Q), -1, dtype=torch.int32, device=dev)
+        if mine:
+            table[torch.as_tensor(mine, device=dev, dtype=torch.long)] = pred.to(torch.int32)
+        return res, table, logits
+    return res, gather_predictions(pred, mine, n_episodes), logits
 
 
 def run_listing_sweep(net, split, load_frame, n_episodes, way, shot, n_queries, seed=0, episodes_per_call=8, rank=0,

@@ -17,6 +17,7 @@
  *   spm_eval_host_set_next        run/main_run.py:71 (DataLoader prefetch: the next batch is known while this one runs)
  *   spm_encode_frames             models/clip_fsar.py:672-689 VisionTransformer.forward / :593-608 ModifiedResNet
  *   spm_head                      models/model_clipspm.py:125-143  (everything after get_feats)
+ *   spm_head_stage                the intermediate tensors of :125-143 (test hook; the reference exposes them as locals)
  *   spm_otam_distance             models/model_clipspm.py:348-362 + models/myRes.py:756-765,821-855
  *   spm_set_text_features_train / spm_class_logits   models/model_clipfsar.py:127,329-331 (sibling head CLIP-FSAR)
  *   spm_softdtw_forward/backward  models/OTAM.py:34-203 (TA2N's numba.cuda soft-DTW kernels, _SoftDTWCUDA)
@@ -31,13 +32,15 @@
 extern "C" {
 #endif
 
-#define SPM_ABI_VERSION 2 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next */
+#define SPM_ABI_VERSION 3 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
+                           * 3: spm_head_stage (per-stage taps for the parity tests) */
 
 typedef struct spm_handle spm_handle;
 
 enum { SPM_BACKBONE_VIT_B16 = 0, SPM_BACKBONE_RN50 = 1 };
-/* arithmetic of the dense contractions: bf16 tensor cores (the reference's autocast(bfloat16) mode) or the
- * fp32-equivalent mode (split-precision tensor-core products, fp32 accumulate) */
+/* arithmetic of the dense contractions: bf16 tensor cores with fp32 accumulation (the reference's autocast(bfloat16)
+ * mode), or the exact-arithmetic parity mode: fp32 operands, every product an fp32 FFMA on the CUDA cores
+ * (csrc/sgemm_f32.cu; Blackwell has no fp32 tensor-core MMA), ViT-B/16 backbone only */
 enum { SPM_PRECISION_BF16 = 0, SPM_PRECISION_FP32 = 1 };
 /* metric head behind the same entry points: CLIP-SPM (models/model_clipspm.py, the hot path) or its sibling
  * CLIP-FSAR (models/model_clipfsar.py CNN_OTAM_CLIPFSAR, evaluation branch :325-383), which reuses the same
@@ -106,6 +109,17 @@ int spm_encode_frames(spm_handle* h, void* stream, const float* images, int n_fr
 int spm_head(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, const float* su, const float* qu,
              const float* support_labels, const float* real_support, const float* real_target, float* logits_out,
              float* dists_out);
+
+/* Test hook (SURVEY.md 8b "per-stage entry points for tests"): one named stage tensor of the most recent CLIP-SPM head
+ * pass (spm_head / spm_forward / spm_eval, any episode count), gathered into the
+ * reference's layout, episodes stacked along dim 0.  Names and the reference lines that produce them
+ * (models/model_clipspm.py): su_mo, qu_mo [E,S|Q,D] :195 get_motion_feats; support_token [E,S,D] :120;
+ * target_token [E,Q,D] :216 token_tr; su_real [E,S,T,D], qu_fake [E,Q,T,D], token_s_real [E,S,D],
+ * token_q_fake [E,Q,D] :218-223 se_te; su_pro [E,W,T,D] :231-239; su_2 [E,S,T,D], qu_2 [E,Q,T,D], su_t2 [E,W,T,D],
+ * qu_t2 [E,1,T,D] :275-294 taskM; su_pro2 [E,W,T,D] :133-137; su_mo_refined / qu_mo_refined, su_mo_token /
+ * qu_mo_token :197 (se_te of the mo call), su_mo2 / qu_mo2 :200.
+ * *numel receives the element count; out == NULL only queries it; capacity is out's size in floats. */
+int spm_head_stage(spm_handle* h, void* stream, const char* name, float* out, long long capacity, long long* numel);
 
 /* CNN.forward for n_episodes episodes: support_images [E,S*T,3,224,224], target_images [E,Q*T,3,224,224] */
 int spm_forward(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, const float* support_images,

@@ -109,6 +109,11 @@ CASES = {
     "head_5w3s_t8_d1024": ("RN50", 5, 3, 1, 8, 10, "P1", True, False, 1004),       # config 4 head shape
     "head_5w2s_t8_q3_single": ("ViT-B/16", 5, 2, 3, 8, 24, "P1", True, True, 1005),  # SINGLE_DIRECT, 3 queries/class
     "rn50_2w1s_t2_p1": ("RN50", 2, 1, 1, 2, 10, "P1", False, False, 1006),         # RN50 tower
+    # full BASELINE shapes, tower + head together (r02): ~20 s / 15 s / 10 s of reference CPU time each
+    "vit_5w5s_t8_p1": ("ViT-B/16", 5, 5, 1, 8, 24, "P1", False, False, 1007),      # BASELINE config 2 / 5 (240 frames)
+    "vit_5w1s_t16_p1": ("ViT-B/16", 5, 1, 1, 16, 24, "P1", False, False, 1008),    # BASELINE config 3 (160 frames, OTAM 16x18)
+    "rn50_5w3s_t8_p1": ("RN50", 5, 3, 1, 8, 10, "P1", False, False, 1009),         # BASELINE config 4 (160 frames; 120 support
+                                                                                   # frames cross the tower's frame-chunk boundary)
 }
 
 

@@ -20,7 +20,7 @@ def _run(args, env=None, timeout=600):
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-frames", "2"])
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-frames", "2", "--no-full-episode"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -31,10 +31,28 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # both arms describe the same workload with the same `config` dict
+    import bench
+    assert d["config"] == bench.bench_config(16, 8)
+
+
+def test_eager_baseline_tower_is_the_reference_tower():
+    """tools/eager_baseline.py (the torch.nn restatement bench.py times as the existing-library bar) reproduces the
+    executed reference's frame features on the golden case -- same modules, same state_dict keys."""
+    import importlib.util
+    from tests import helpers as H
+    spec = importlib.util.spec_from_file_location("eb", os.path.join(ROOT, "tools", "eager_baseline.py"))
+    eb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(eb)
+    ci, g = H.case_inputs("vit_2w1s_t2_p0"), H.golden("vit_2w1s_t2_p0")
+    tower = eb.build_from(ci["weights"], "cpu")
+    with torch.no_grad():
+        su = tower(ci["episode"]["context_images"])
+    assert H.rel_err(su.view(g["su"].shape), g["su"]) < 1e-4
 
 
 def test_reference_arm_only_rank0_works():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-frames", "2"],
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-frames", "2", "--no-full-episode"],
              env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, timeout=120)
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
 

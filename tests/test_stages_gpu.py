@@ -373,3 +373,174 @@ def test_pipelined_forward_equals_serial(monkeypatch, E, chunk):
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
     assert torch.isfinite(outs[0]["logits"]).all()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# r02: BASELINE configs 2 / 3 / 4 at their full shapes against goldens written from the executed reference, and
+# per-stage taps of the head (every SURVEY 8a row has its own assertion)
+# ------------------------------------------------------------------------------------------------------------------
+FULL_CASES = ["vit_5w5s_t8_p1", "vit_5w1s_t16_p1", "rn50_5w3s_t8_p1"]
+
+
+def _check_forward_against_golden(net, ci, g, tol, tol_dists, all_argmax):
+    ep = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in ci["episode"].items()}
+    su = net.encode_frames(ep["context_images"])
+    qu = net.encode_frames(ep["target_images"])
+    err_f = max(H.rel_err(su.cpu().view(g["su"].shape), g["su"]), H.rel_err(qu.cpu().view(g["qu"].shape), g["qu"]))
+    out = net(ep)
+    torch.cuda.synchronize()
+    err_l = H.rel_err(out["logits"].cpu(), g["logits"])
+    abs_err = float((out["logits"].cpu() - g["logits"]).abs().max())
+    pred = out["logits"][0].argmax(-1).cpu()
+    safe = g["margin"] > 4 * abs_err
+    print("\nfeatures rel err %.2e, logits rel err %.2e (abs %.4f), %d/%d queries above the margin filter, raw agreement "
+          "%d/%d" % (err_f, err_l, abs_err, int(safe.sum()), safe.numel(), int((pred == g["pred"].long()).sum()),
+                     safe.numel()))
+    assert err_f < tol, err_f
+    assert err_l < tol, err_l
+    assert H.rel_err(out["dists"].cpu(), g["dists"]) < tol_dists
+    assert torch.equal(pred[safe], g["pred"].long()[safe])
+    if all_argmax:
+        assert bool(safe.all()) and torch.equal(pred, g["pred"].long())
+    loss, acc = net.evaluate(ep)
+    if bool(safe.all()):
+        assert float(acc) == float(g["acc"])
+    assert abs(float(loss) - float(g["loss"])) < max(tol_dists, tol) * max(1.0, abs(float(g["loss"])))
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_full_shape_forward_matches_reference_golden(name):
+    """tower + head together at the BASELINE shape: 240 frames (config 2), 160 frames T=16 (config 3), RN50 160 frames
+    (config 4; its 120 support frames cross the tower's frame-chunk boundary)"""
+    ci, g = H.case_inputs(name), H.golden(name)
+    _check_forward_against_golden(H.build_cuda_model(ci), ci, g, TOL_BF16, 5e-2, False)
+
+
+@pytest.mark.parametrize("name", ["vit_5w5s_t8_p1", "vit_5w1s_t16_p1"])
+def test_full_shape_fp32_mode_matches_reference_golden(name):
+    ci, g = H.case_inputs(name), H.golden(name)
+    _check_forward_against_golden(H.build_cuda_model(ci, precision="fp32"), ci, g, TOL_FP32, 1e-3, True)
+
+
+def test_rn50_encoder_frame_count_edges():
+    """frame counts around the RN50 tower's chunk size: rows are independent of how many frames share a launch"""
+    ci = H.case_inputs("rn50_2w1s_t2_p1")
+    net = H.build_cuda_model(ci)
+    g = torch.Generator().manual_seed(11)
+    imgs = torch.rand(5, 3, 224, 224, generator=g).cuda()
+    base = net.encode_frames(imgs)
+    assert net.encode_frames(imgs[:1]).shape == (1, 1024)
+    for n in (63, 64, 65, 129):
+        big = imgs.repeat((n + 4) // 5, 1, 1, 1)[:n]
+        out = net.encode_frames(big)
+        assert out.shape == (n, 1024) and torch.isfinite(out).all()
+        want = base[torch.arange(n) % 5]
+        assert H.rel_err(out, want) < 2e-3, n
+    assert net.encode_frames(imgs[:0]).shape == (0, 1024)
+
+
+# golden key -> (spm_head_stage name, SURVEY 8a row)
+STAGES = [("su_mo", "su_mo", "b1"), ("qu_mo", "qu_mo", "b1"), ("target_token", "target_token", "c3"),
+          ("su_real", "su_real", "c1"), ("qu_fake", "qu_fake", "c1"), ("token_s_real", "token_s_real", "c1"),
+          ("token_q_fake", "token_q_fake", "c1"), ("su_pro", "su_pro", "c6"), ("su_2", "su_2", "c5"),
+          ("qu_2", "qu_2", "c5"), ("su_t2", "su_t2", "c5"), ("qu_t2", "qu_t2", "c5")]
+
+
+def _check_head_stages(net, ci, g, tol):
+    ep = ci["episode"]
+    su, qu = ci["feats"] if ci["feats"] is not None else (g["su"], g["qu"])
+    out = net.head(su.cuda(), qu.cuda(), ep["context_labels"], ep["real_support_labels"], ep["real_target_labels"])
+    worst = {}
+    for key, stage, row in STAGES:
+        got = net.head_stage(stage).cpu()
+        assert got.numel() == g[key].numel(), (key, got.numel(), tuple(g[key].shape))
+        err = H.rel_err(got.view(g[key].shape), g[key])
+        worst[row] = max(worst.get(row, 0.0), err)
+        assert err < tol, (key, row, err)
+    # b2 / b3: mo() returns the distance before mo_alpha1 (model_clipspm.py:205,141)
+    alpha1 = float(ci["weights"]["mo_alpha1"])
+    err = abs(float(out["dists"][0]) / alpha1 - float(g["mo_dist_pre"])) / abs(float(g["mo_dist_pre"]))
+    worst["b2/b3"] = err
+    assert err < tol, ("mo_dist_pre", err)
+    # a4: the support prompts are a plain gather of the text table
+    tok = net.head_stage("support_token").cpu().view(-1, ci["D"])
+    assert torch.equal(tok, ci["text"][ep["real_support_labels"].long()])
+    print("\nper-row worst rel err: " + ", ".join("%s %.1e" % kv for kv in sorted(worst.items())))
+
+
+@pytest.mark.parametrize("name", ["head_5w5s_t8", "head_5w1s_t16", "head_5w2s_t8_q3_single", "head_5w3s_t8_d1024"])
+def test_head_stage_tensors_match_reference_golden(name):
+    """rows b1-b3, c1, c3, c5, c6, a4 one by one (tf32 tensor-core products: 5e-3)"""
+    ci, g = H.case_inputs(name), H.golden(name)
+    _check_head_stages(H.build_cuda_model(ci), ci, g, TOL_HEAD)
+
+
+@pytest.mark.parametrize("name", ["head_5w5s_t8", "head_5w1s_t16", "head_5w2s_t8_q3_single"])
+def test_head_stage_tensors_fp32_mode(name):
+    ci, g = H.case_inputs(name), H.golden(name)
+    _check_head_stages(H.build_cuda_model(ci, precision="fp32"), ci, g, TOL_FP32)
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_head_stage_tensors_on_reference_features_full_shape(name):
+    """the head alone on the REFERENCE's own frame features of the full-shape goldens (isolates it from the tower)"""
+    ci, g = H.case_inputs(name), H.golden(name)
+    _check_head_stages(H.build_cuda_model(ci), ci, g, TOL_HEAD)
+
+
+def test_head_stage_batched_and_errors():
+    ci, g = H.case_inputs("head_5w5s_t8"), H.golden("head_5w5s_t8")
+    net = H.build_cuda_model(ci)
+    with pytest.raises(RuntimeError):
+        net.head_stage("su_real")            # no head pass yet
+    ep = ci["episode"]
+    su, qu = ci["feats"]
+    rep = lambda t: torch.stack([t, t])
+    net.head(rep(su).cuda(), rep(qu).cuda(), rep(ep["context_labels"]), rep(ep["real_support_labels"]),
+             rep(ep["real_target_labels"]), n_episodes=2)
+    got = net.head_stage("su_2").cpu().view(2, *g["su_2"].shape)
+    assert H.rel_err(got[0], g["su_2"]) < TOL_HEAD and H.rel_err(got[1], g["su_2"]) < TOL_HEAD
+    with pytest.raises(RuntimeError):
+        net.head_stage("no_such_stage")
+
+
+def test_class_id_outside_text_table_fails_loudly():
+    """a real_* label beyond the text table is an IndexError in the reference (model_clipspm.py:116-121): NaN logits
+    here (device path, no host sync) instead of an out-of-bounds read"""
+    ci = H.case_inputs("head_5w5s_t8")
+    net = H.build_cuda_model(ci)
+    ep = ci["episode"]
+    su, qu = ci["feats"]
+    bad = ep["real_target_labels"].clone()
+    bad[0] = 1000.0
+    out = net.head(su.cuda(), qu.cuda(), ep["context_labels"], ep["real_support_labels"], bad)
+    assert bool(torch.isnan(out["logits"]).all())
+    out = net.head(su.cuda(), qu.cuda(), ep["context_labels"], ep["real_support_labels"], ep["real_target_labels"])
+    assert bool(torch.isfinite(out["logits"]).all())
+
+
+def test_eval_host_regrows_every_staging_ring():
+    """a later call with the same frame counts but more logits per episode (larger Q*W) must not write past
+    the staging rings sized by an earlier call; results must equal the device path for both shapes."""
+    ci = H.case_inputs("vit_2w1s_t2_p0")
+    net = H.build_cuda_model(ci, max_episodes=2)
+    net.way = None
+    def run(way, shot, qpc, seed0, E=3):
+        eps = [O.make_episode(seed0 + e, way, shot, qpc, 2, 24, "P0") for e in range(E)]
+        cat = lambda k: torch.cat([e[k] for e in eps]).contiguous()
+        host = net.evaluate_host(cat("context_images").pin_memory(), cat("context_labels"),
+                                 cat("target_images").pin_memory(), cat("real_support_labels"),
+                                 cat("real_target_labels"), cat("target_labels"), E, way)
+        for e in range(E):
+            ep = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in eps[e].items()}
+            out = net(ep)
+            assert torch.allclose(host["logits"][e], out["logits"][0].cpu(), atol=1e-5)
+    run(2, 2, 1, 6000)      # S=4, Q=2, W=2: Q*W = 4
+    run(4, 1, 1, 6100)      # S=4, Q=4, W=4: same support frames, Q*W = 16
+    run(2, 1, 2, 6200, 5)   # S=2, Q=4, W=2, more episodes than before
+    # device path: scratch logits / dists (loss-only callers) regrow independently
+    eps = [O.make_episode(6300 + e, 2, 1, 1, 2, 24, "P0") for e in range(4)]
+    cat = lambda k: torch.cat([e[k] for e in eps]).contiguous().cuda()
+    out = net.forward_episodes(cat("context_images"), cat("context_labels"), cat("target_images"),
+                               cat("real_support_labels"), cat("real_target_labels"), 4, cat("target_labels"))
+    assert torch.isfinite(out["loss"]).all()

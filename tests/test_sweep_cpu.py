@@ -60,6 +60,9 @@ def _worker(rank, world, port, n, out):
     loss = torch.tensor([1.0 + 0.01 * e for e in ids], dtype=torch.float32)
     stats = sweep.reduce_stats(sweep.make_stats(acc, loss))
     out[rank] = sweep.summarize(stats)
+    # the optional prediction gather: every rank ends up with the full table in global episode order
+    pred = torch.tensor([[(e + q) % 5 for q in range(3)] for e in ids], dtype=torch.int32).view(len(ids), 3)
+    out[("pred", rank)] = sweep.gather_predictions(pred, ids, n).tolist()
     dist.destroy_process_group()
 
 
@@ -76,3 +79,4 @@ def test_two_rank_sweep_equals_unsharded(n):
         assert out[r]["n"] == n
         for k in ("accuracy", "confidence", "loss"):
             assert abs(out[r][k] - ref[k]) < 1e-9, (r, k)
+        assert out[("pred", r)] == [[(e + q) % 5 for q in range(3)] for e in range(n)]

@@ -16,7 +16,42 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_wait_per_warp_active.pct']
 
 
+def _to_bytes(val, unit):
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    return float(val.replace(",", "")) * mult.get(unit, 1.0)
+
+
+def _to_us(val, unit):
+    mult = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    return float(val.replace(",", "")) * mult.get(unit.replace("second", "s").replace("usecond", "us"), 1.0)
+
+
+def write_json(path, out, source):
+    """--json: per kernel name (template arguments kept, parameter list cut) the mean duration and DRAM bytes per
+    launch -- the file bench.py reads `roofline.traffic` from."""
+    import collections, json, re
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    agg = collections.OrderedDict()
+    for r in rows[2:]:
+        full = re.sub(r"\(.*", "", r[col["Kernel Name"]])
+        base = re.sub(r"<.*", "", full).replace("void ", "").strip()
+        dur = _to_us(r[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]])
+        byt = _to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + \
+            _to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+        for key in {full.replace("void ", "").strip(), base}:
+            a = agg.setdefault(key, [0, 0.0, 0.0])
+            a[0] += 1; a[1] += dur; a[2] += byt
+    d = {"source": source, "kernels": {k: {"launches": v[0], "duration_us": v[1] / v[0], "dram_bytes_per_launch": v[2] / v[0],
+                                           "dram_gbs": v[2] / v[1] / 1e3} for k, v in agg.items()}}
+    json.dump(d, open(out, "w"), indent=1)
+    print("wrote", out, "(%d kernel names)" % len(agg))
+
+
 def main(path, extra=()):
+    if len(extra) >= 2 and extra[0] == "--json":
+        return write_json(path, extra[1], extra[2] if len(extra) > 2 else "ncu --set full")
     rows = list(csv.reader(open(path)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}

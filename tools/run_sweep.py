@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--seq-len", type=int, default=8)
     ap.add_argument("--text-classes", type=int, default=24)
     ap.add_argument("--episodes-per-call", type=int, default=4)
+    ap.add_argument("--check-sharding", action="store_true",
+                    help="gather every rank's predictions and compare them, on rank 0, with an unsharded run of the same "
+                         "episodes (SURVEY.md 8e); exits non-zero on any difference")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -51,6 +54,34 @@ def main():
     dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if args.check_sharding:
+        res2, table, my_logits = sweep.run_sweep(net, args.episodes, args.way, args.shot, args.query_per_class,
+                                                 args.text_classes, rank, world, args.episodes_per_call, True)
+        ok = True
+        if rank == 0:
+            # the unsharded run: this ONE GPU evaluates every rank's shard in turn (same episodes per call as the sharded
+            # run, no collective), so equality must be exact
+            ref_table, ref_logits, st = None, {}, None
+            for r in range(world):
+                part, t, lg = sweep.run_sweep(net, args.episodes, args.way, args.shot, args.query_per_class,
+                                              args.text_classes, r, world, args.episodes_per_call, True, local_only=True)
+                ref_table = t if ref_table is None else torch.maximum(ref_table, t)
+                ref_logits.update(lg)
+                n_r = part["n"]
+                v = torch.tensor([n_r, part["accuracy"] / 100 * n_r, 0.0, part["loss"] * n_r], dtype=torch.float64)
+                st = v if st is None else st + v
+            ref = dict(n=int(st[0]), accuracy=100.0 * float(st[1] / st[0]), loss=float(st[3] / st[0]))
+            same_pred = bool(torch.equal(table, ref_table))
+            same_logits = all(torch.equal(v, ref_logits[e]) for e, v in my_logits.items())
+            same_stats = all(abs(res2[k] - ref[k]) < 1e-9 for k in ("accuracy", "loss")) and res2["n"] == ref["n"]
+            ok = same_pred and same_logits and same_stats and int((table < 0).sum()) == 0
+            print(json.dumps({"check_sharding": "ok" if ok else "MISMATCH", "world_size": world, "episodes": args.episodes,
+                              "predictions_equal": same_pred, "rank0_logits_bit_equal": same_logits,
+                              "reduced_stats_equal": same_stats, "sharded": res2, "unsharded": ref}))
+        if world > 1:
+            dist.barrier()
+        if not ok:
+            sys.exit(1)
     if rank == 0:
         res.update(world_size=world, seconds=float(dt), episodes_per_s=args.episodes / float(dt),
                    note="includes on-device synthetic episode generation between calls")

@@ -1,4 +1,5 @@
-"""__graft_entry__.smoke(): one small episode through the CUDA path on cuda:0, checked against the oracle."""
+"""__graft_entry__.smoke(): one small episode through the CUDA path on cuda:0, checked against the oracle.
+Lives outside the product package: it imports the oracle (the checker), which nothing in clip_spm_b200/ may do."""
 import os
 import sys
 
@@ -6,7 +7,7 @@ import torch
 
 
 def run():
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tools/ -> repo root
     if root not in sys.path:
         sys.path.insert(0, root)
     from oracle import clipspm_oracle as O  # checker only
