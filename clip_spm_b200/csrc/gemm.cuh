@@ -72,6 +72,10 @@ int gemm_plan_conv3x3(GemmOp* op, const void* A, int C, int rows, int W2, const 
                       int num_sms, const char** err);
 // true if the driver accepts a tensor map whose row stride is smaller than its row extent (needed by conv_pair)
 bool gemm_conv_pair_supported();
+// fp32 tensor map of rank 2..5 (dims / box innermost first, strides in BYTES for dims 1..rank-1, each a multiple of 16),
+// SWIZZLE_128B (the box's innermost extent must be 32 floats = 128 bytes); 0 on success
+int make_tensor_map_f32_nd(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
+                           const unsigned long long* strides_bytes, const unsigned* box);
 // one-time: opt into large dynamic shared memory for every instantiation
 int gemm_init(const char** err);
 // 2-CTA kernel (gemm2_tcgen05.cu)

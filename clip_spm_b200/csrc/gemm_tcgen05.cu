@@ -245,6 +245,23 @@ static int make_operand_map(CUtensorMap* map, int kind, const void* ptr, long lo
   return 0;
 }
 
+int make_tensor_map_f32_nd(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
+                           const unsigned long long* strides_bytes, const unsigned* box) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc || rank < 2 || rank > 5) return 1;
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    if (strides_bytes[i] % 16 != 0) return 1;
+    gstride[i] = strides_bytes[i];
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || box[0] != 32) return 1;
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bx, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
+}
+
 bool gemm_conv_pair_supported() {
   static const int ok = [] {
     if (const char* e = getenv("SPM_CONV_PAIR")) if (atoi(e) == 0) return 0;

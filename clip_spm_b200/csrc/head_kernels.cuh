@@ -57,4 +57,10 @@ int k_otam_mma(cudaStream_t st, const float* sup, long long s_p, long long s_w, 
                long long t_p, long long t_q, long long t_t, int P, int W, int Q, int T, int D, int single_direct,
                float alpha, float beta, float* out);
 
+// same contract as ONE persistent warp-specialised kernel (TMA ring across problems, 3xTF32 products, wavefronts on their
+// own warps; otam_fused.cu) for P >= 2 x #SM problems of the headline shapes; -3 = outside its envelope
+int k_otam_fused(cudaStream_t st, const float* sup, long long s_p, long long s_w, long long s_t, const float* tgt,
+                 long long t_p, long long t_q, long long t_t, int P, int W, int Q, int T, int D, int single_direct,
+                 float alpha, float beta, float* out);
+
 }  // namespace spm
