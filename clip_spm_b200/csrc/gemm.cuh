@@ -76,6 +76,7 @@ bool gemm_conv_pair_supported();
 // SWIZZLE_128B (the box's innermost extent must be 32 floats = 128 bytes); 0 on success
 int make_tensor_map_f32_nd(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
                            const unsigned long long* strides_bytes, const unsigned* box);
+bool gemm_pdl_enabled();   // programmatic dependent launch of the GEMM kernels (SPM_PDL=0 turns it off)
 // one-time: opt into large dynamic shared memory for every instantiation
 int gemm_init(const char** err);
 // 2-CTA kernel (gemm2_tcgen05.cu)

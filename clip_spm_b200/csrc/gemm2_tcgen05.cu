@@ -88,9 +88,12 @@ struct Gemm2Args {
   GemmEpilogue ep;
   int M, N, K;
   int reverse;
+  int conv_w2, conv_cblocks;   // EPI == 3: implicit 3x3 convolution taps (see GemmOp), 0 = 1x1 convolution
 };
 
-// EPI: 0 = general epilogue; 1 / 2 = bf16 output + bias (+ QuickGELU) with identity rows (gemm_epilogue_tile_bf16_bias)
+// EPI: 0 = general epilogue; 1 / 2 = bf16 output + bias (+ QuickGELU) with identity rows (gemm_epilogue_tile_bf16_bias);
+// 3 = convolution (rn50.cu): the producer addresses the 3x3 taps as row offsets of the zero-bordered image matrix and
+// the general epilogue is compiled with its zero-border handling
 template <bool RES, int EPI = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -135,6 +138,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   cluster_sync_all();  // both CTAs' barriers and TMEM exist before any cross-CTA signal
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the prologue above overlapped the predecessor's tail; from here on its results are needed
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -149,17 +155,24 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += n_clusters; }
         }
       };
-      for (int i = 0; i < GEMM_L2_PREFETCH_KB; ++i) prefetch_next();
+      constexpr bool conv = EPI == 3;   // taps re-read an L2-resident activation: no prefetch needed
+      if (!conv)
+        for (int i = 0; i < GEMM_L2_PREFETCH_KB; ++i) prefetch_next();
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         const int rt = args.reverse ? num_tiles - 1 - tile : tile;
         const int m0 = (rt / num_n) * (2 * T::BM) + (int)rank * T::BM;
         const int n0 = (rt % num_n) * T::BN + (int)rank * (T::BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          prefetch_next();
+          if (!conv) prefetch_next();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * T::STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * T::STAGE_BYTES);  // bytes of both CTAs land on the leader
           const uint32_t lbar = smem_u32(&full_bar[stage]) & PEER_MASK;
+          if (conv && args.conv_cblocks > 0) {
+            const int tap = kb / args.conv_cblocks, cb = kb - tap * args.conv_cblocks;
+            const int roff = (tap / 3 - 1) * args.conv_w2 + (tap % 3 - 1);  // rows outside the matrix read as zeros
+            tma_load_2d_2sm(sa, &tmA, lbar, cb * T::BK, m0 + roff);
+          } else
           tma_load_2d_2sm(sa, &tmA, lbar, kb * T::BK, m0);
           tma_load_2d_2sm(sa + T::A_BYTES, &tmB, lbar, kb * T::BK, n0);
           if (++stage == T::STAGES) { stage = 0; phase ^= 1u; }
@@ -262,11 +275,20 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int rt = args.reverse ? num_tiles - 1 - tile : tile;
         const int m_base = (rt / num_n) * (2 * T::BM) + (int)rank * T::BM + q * 32;
         const int n0 = (rt % num_n) * T::BN;
+        if (EPI == 3) prefetch_residual_bf16<T::BN>(ep, m_base, n0, M, N, lane, half);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T::BN);
         if (EPI == 1) gemm_epilogue_tile_bf16_bias<T::BN, ACT_NONE>(ep, stg_u, taddr, m_base, n0, M, lane, half);
         else if (EPI == 2) gemm_epilogue_tile_bf16_bias<T::BN, ACT_QUICKGELU>(ep, stg_u, taddr, m_base, n0, M, lane, half);
+        else if (EPI == 3) {
+          if (conv_epilogue_applies(ep)) {   // (warp-uniform) compile-time specialised convolution epilogue
+            if (ep.residual_bf16 != nullptr) gemm_epilogue_tile_conv<T::BN, true>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+            else gemm_epilogue_tile_conv<T::BN, false>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+          } else {
+            gemm_epilogue_tile<T::BN, true>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+          }
+        }
         else gemm_epilogue_tile<T::BN>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
         tc_fence_before_sync();
         __syncwarp();
@@ -290,6 +312,8 @@ int gemm2_init(const char** err) {
                            G2T<false>::SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(gemm2_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            G2T<false>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm2_tcgen05_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           G2T<false>::SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(gemm2_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            G2T<true>::SMEM_BYTES) != cudaSuccess) {
     *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the 2-CTA GEMM kernel";
@@ -298,11 +322,25 @@ int gemm2_init(const char** err) {
   return 0;
 }
 
+template <class... KArgs, class... Args>
+static void launch2_pdl(void (*kernel)(KArgs...), int grid, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = gemm_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 int gemm2_launch(const GemmOp* op, cudaStream_t stream) {
   Gemm2Args a;
   a.ep = op->ep; a.M = op->M; a.N = op->N; a.K = op->K; a.reverse = op->reverse;
-  if (op->res_tma)
-    gemm2_tcgen05_kernel<true><<<op->grid, 384, G2T<true>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->tr, a);
+  a.conv_w2 = op->conv_w2; a.conv_cblocks = op->conv_cblocks;
+  if (op->conv_cblocks > 0 || op->ep.border_w2 > 0)
+    launch2_pdl(gemm2_tcgen05_kernel<false, 3>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);
+  else if (op->res_tma)
+    launch2_pdl(gemm2_tcgen05_kernel<true>, op->grid, G2T<true>::SMEM_BYTES, stream, op->ta, op->tb, op->tr, a);
   else {
     // the two hot consumer shapes of the ViT encoder get the compile-time-specialised epilogue (SPM_GEMM_EPI=0: off)
     static const bool allow_spec = [] { const char* e = getenv("SPM_GEMM_EPI"); return e == nullptr || atoi(e) != 0; }();
@@ -312,11 +350,11 @@ int gemm2_launch(const GemmOp* op, cudaStream_t stream) {
                         op->N % G2T<false>::BN == 0 && (e.ldo % 8) == 0 &&
                         (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
     if (simple && e.act == ACT_NONE)
-      gemm2_tcgen05_kernel<false, 1><<<op->grid, 384, G2T<false>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->ta, a);
+      launch2_pdl(gemm2_tcgen05_kernel<false, 1>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);
     else if (simple && e.act == ACT_QUICKGELU)
-      gemm2_tcgen05_kernel<false, 2><<<op->grid, 384, G2T<false>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->ta, a);
+      launch2_pdl(gemm2_tcgen05_kernel<false, 2>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);
     else
-      gemm2_tcgen05_kernel<false><<<op->grid, 384, G2T<false>::SMEM_BYTES, stream>>>(op->ta, op->tb, op->ta, a);
+      launch2_pdl(gemm2_tcgen05_kernel<false>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);
   }
   return (int)cudaGetLastError();
 }

@@ -57,6 +57,23 @@ __device__ __forceinline__ long long res_row(const GemmEpilogue& ep, int m) {
   return out_row(ep, m);
 }
 
+// bf16 residual of a convolution tile (ResNet bottleneck identity): the epilogue loads it with plain 16-byte loads at the
+// start of every 64-column group, which exposes one HBM latency per group (4 per 256-wide tile: ~6 of the ~8 us a
+// K = 64 / 128 tile takes).  Called BEFORE the wait for the accumulator: every lane asks L2 for the 128-byte lines of its
+// row that this warp will read, so the loads later hit L2 while the tile's MMAs are still running.
+template <int BN>
+__device__ __forceinline__ void prefetch_residual_bf16(const GemmEpilogue& ep, int m_base, int n0, int M, int N, int lane,
+                                                       int half) {
+  const int m = m_base + lane;
+  if (ep.residual_bf16 == nullptr || m >= M) return;
+  const __nv_bfloat16* row = reinterpret_cast<const __nv_bfloat16*>(ep.residual_bf16) + res_row(ep, m) * ep.ldr;
+#pragma unroll
+  for (int g = half * 2; g < BN / 32; g += 4) {
+    const int col0 = n0 + g * 32;
+    if (col0 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + col0));
+  }
+}
+
 // taddr: TMEM address of (lane quarter base, first accumulator column of the tile); stg_u: this warp's 4 KB staging
 // tile (32 rows x 128 B, 16-byte units XOR-swizzled by row & 7); half: which of the two warps of the lane quarter.
 // BORDER: compile the zero-border handling of the convolution path in (the plain-GEMM instantiations stay free of it)
@@ -248,6 +265,96 @@ __device__ __forceinline__ void gemm_epilogue_tile_bf16_bias(const GemmEpilogue&
     }
     __syncwarp();  // staging tile is reused by the next group
   }
+}
+
+// Specialisation for the convolutions of the RN50 tower (rn50.cu): bf16 output with identity rows, bias, zero-bordered
+// images, and either an optional ReLU (RESID = false) or the bottleneck tail out = relu(acc + bias + identity) with a
+// bf16 identity tensor (RESID = true).  The short-K convolutions (K = 64 .. 576) are bound by this epilogue, not by their
+// MMAs: ncu showed ~7 k cycles per 32 x 64 group in the general epilogue (~1000 warp instructions: per-row row-map
+// arithmetic, a border test with two integer divisions per 32-column chunk, activation dispatch), one warp per scheduler
+// with nothing to overlap.  Here the border test is done once per tile, rows are addressed incrementally, the bias is
+// requested before the TMEM wait, ReLU runs on packed bf16x2, and every option is a compile-time constant.
+template <int BN, bool RESID>
+__device__ __forceinline__ void gemm_epilogue_tile_conv(const GemmEpilogue& ep, uint32_t stg_u, uint32_t taddr, int m_base,
+                                                        int n0, int M, int N, int lane, int half) {
+  const int rr = lane >> 3, uu = lane & 7;  // read-back mapping: row i*4 + rr, 16-byte unit uu
+  __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.out);
+  const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(ep.residual_bf16);
+  // zero-bordered image rows stay zero (thread == pixel row m_base + lane): one test per tile
+  const int pr = (m_base + lane) % ep.border_h2w2, py = pr / ep.border_w2, px = pr - py * ep.border_w2;
+  const bool border = py == 0 || px == 0 || px == ep.border_w2 - 1 || py == ep.border_h2w2 / ep.border_w2 - 1;
+  const bool relu_now = !RESID && ep.act == ACT_RELU;
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+  const uint32_t srow = stg_u + (uint32_t)(lane * 128);
+  const int m_rd = m_base + rr;             // first row of this lane in the read-back mapping (then +4 per step)
+#pragma unroll 1
+  for (int g = half * 2; g < BN / 32; g += 4) {
+    const int col0 = n0 + g * 32;           // first output column of this 128-byte store group (64 bf16)
+    if (col0 >= N) break;                   // warp-uniform
+    const bool col_ok = col0 + uu * 8 < N;
+    uint4 res[8];
+    if (RESID) {
+      const __nv_bfloat16* rp = resp + (long long)m_rd * ep.ldr + col0 + uu * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        res[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (m_rd + i * 4 < M && col_ok) res[i] = *reinterpret_cast<const uint4*>(rp + (long long)(i * 4) * ep.ldr);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c0 = col0 + h * 32;
+      if (c0 < N) {                         // warp-uniform
+        float4 b[8];
+        const float4* bp = reinterpret_cast<const float4*>(ep.bias + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = __ldg(bp + j);   // in flight while the accumulator chunk arrives
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)((g + h) * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t u[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 bb = b[2 * j + (e >> 1)];
+            const float lo = __uint_as_float(r[8 * j + 2 * e]) + ((e & 1) ? bb.z : bb.x);
+            const float hi = __uint_as_float(r[8 * j + 2 * e + 1]) + ((e & 1) ? bb.w : bb.y);
+            __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+            if (relu_now) p = __hmax2(p, zero2);
+            u[e] = border ? 0u : *reinterpret_cast<uint32_t*>(&p);
+          }
+          st_shared_v4(srow + (uint32_t)((((h * 4 + j) ^ (lane & 7))) * 16), make_uint4(u[0], u[1], u[2], u[3]));
+        }
+      }
+    }
+    __syncwarp();
+    __nv_bfloat16* op = outp + (long long)m_rd * ep.ldo + col0 + uu * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = i * 4 + rr;
+      uint4 d = ld_shared_v4(stg_u + (uint32_t)(rl * 128 + ((uu ^ (rl & 7)) * 16)));
+      if (RESID) {
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[i]);
+        uint32_t* dw = reinterpret_cast<uint32_t*>(&d);
+#pragma unroll
+        for (int w2 = 0; w2 < 4; ++w2) {
+          __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&dw[w2]),
+                                       *reinterpret_cast<const __nv_bfloat162*>(&rw[w2]));
+          sum = __hmax2(sum, zero2);
+          dw[w2] = *reinterpret_cast<uint32_t*>(&sum);
+        }
+      }
+      if (m_rd + i * 4 < M && col_ok) *reinterpret_cast<uint4*>(op + (long long)(i * 4) * ep.ldo) = d;
+    }
+    __syncwarp();  // staging tile is reused by the next group
+  }
+}
+// the convolution epilogue applies when the plan has exactly the options it hard-codes
+__device__ __forceinline__ bool conv_epilogue_applies(const GemmEpilogue& ep) {
+  return ep.out_bf16 && ep.bias != nullptr && ep.residual == nullptr && ep.border_w2 > 0 && ep.out_row_group == 0 &&
+         ep.res_row_mod == 0 && (ep.act == ACT_NONE || ep.act == ACT_RELU) &&
+         (ep.residual_bf16 == nullptr || (ep.relu_after_residual && ep.act == ACT_NONE));
 }
 
 // Variant for fp32 output + fp32 residual (identity rows), used by the 2-CTA kernel: the residual box of this warp's

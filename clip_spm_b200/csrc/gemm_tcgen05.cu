@@ -39,7 +39,7 @@ struct GemmTile {
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 7 : 8));   // 32 / 64-wide tiles: small-N convolutions
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int STG_BYTES_PER_WARP = 32 * 128;  // epilogue staging tile of one warp
@@ -93,6 +93,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the prologue above overlapped the predecessor's tail; from here on its results are needed
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -184,10 +187,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int rt = args.reverse ? num_tiles - 1 - tile : tile;
       const int m_base = (rt / num_n) * T::BM + q * 32;
       const int n0 = (rt % num_n) * BN;
+      if (CONV) prefetch_residual_bf16<BN>(ep, m_base, n0, M, N, lane, half);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      gemm_epilogue_tile<BN, CONV>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+      if (CONV && conv_epilogue_applies(ep)) {   // (warp-uniform) compile-time specialised convolution epilogue
+        if (ep.residual_bf16 != nullptr) gemm_epilogue_tile_conv<BN, true>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+        else gemm_epilogue_tile_conv<BN, false>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+      } else {
+        gemm_epilogue_tile<BN, CONV>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
+      }
       // accumulator buffer drained -> hand it back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
@@ -295,7 +304,11 @@ int gemm_init(const char** err) {
   if (cudaFuncSetAttribute(gemm_tcgen05_kernel<256, GEMM_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            GemmTile<256, GEMM_BF16>::SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(gemm_tcgen05_kernel<128, GEMM_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           GemmTile<128, GEMM_BF16>::SMEM_BYTES) != cudaSuccess) {
+                           GemmTile<128, GEMM_BF16>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tcgen05_kernel<64, GEMM_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           GemmTile<64, GEMM_BF16>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tcgen05_kernel<32, GEMM_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           GemmTile<32, GEMM_BF16>::SMEM_BYTES) != cudaSuccess) {
     *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the conv GEMM kernel";
     return 1;
   }
@@ -324,6 +337,10 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   // Tile width: 256 for the big encoder GEMMs; 128 when that yields more CTAs than SMs can use otherwise
   const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
   op->bn = (N % 256 == 0 && tiles256 >= num_sms) ? 256 : 128;
+  // convolutions with few output channels (RN50 stem: 32 / 64, layer1: 64): a tile as wide as the layer instead of a
+  // 128-wide one whose B rows are mostly TMA zero fill (4x / 2x the tensor, shared-memory and L2 work for nothing)
+  static const bool allow_narrow = [] { const char* e = getenv("SPM_CONV_NARROW"); return e == nullptr || atoi(e) != 0; }();
+  if (allow_narrow && kind == GEMM_BF16 && ep.border_w2 > 0 && N <= 64) op->bn = N <= 32 ? 32 : 64;
   const long long tiles = (long long)((M + 127) / 128) * ((N + op->bn - 1) / op->bn);
   op->grid = (int)(tiles < num_sms ? tiles : num_sms);
   // Large bf16 problems run on CTA pairs (cta_group::2): 256x256 tile per pair, each CTA stages half of B
@@ -336,9 +353,14 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   // one box) -- energy per flop is what bounds a power-capped step.  So it is the default for every eligible shape;
   // SPM_GEMM_2CTA=1 restricts it to K >= 2048, 0 disables it.
   static const int mode_2cta = [] { const char* e = getenv("SPM_GEMM_2CTA"); return e == nullptr ? 2 : atoi(e); }();
-  // (zero-bordered convolution outputs are handled by the 1-CTA CONV instantiation only)
-  op->two_cta = (allow_2cta && kind == GEMM_BF16 && ep.border_w2 == 0 && N % 256 == 0 && pair_tiles >= num_sms / 2 &&
-                 (K >= 2048 || mode_2cta == 2)) ? 1 : 0;
+  // Convolutions (zero-bordered outputs, rn50.cu) with N % 256 == 0 take the pair kernel whatever their tile count: the
+  // alternative, 128-wide 1-CTA tiles, is bound by shared-memory traffic at half the tensor rate (SPM_CONV_2CTA=0: off)
+  static const bool conv_2cta = [] { const char* e = getenv("SPM_CONV_2CTA"); return e == nullptr || atoi(e) != 0; }();
+  if (ep.border_w2 > 0)
+    op->two_cta = (allow_2cta && conv_2cta && kind == GEMM_BF16 && N % 256 == 0) ? 1 : 0;
+  else
+    op->two_cta = (allow_2cta && kind == GEMM_BF16 && N % 256 == 0 && pair_tiles >= num_sms / 2 &&
+                   (K >= 2048 || mode_2cta == 2)) ? 1 : 0;
   if (op->two_cta) {
     op->bn = 256;
     const long long pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
@@ -372,18 +394,27 @@ int gemm_plan_conv3x3(GemmOp* op, const void* A, int C, int rows, int W2, const 
     // (columns >= C of a box read as zeros, rows outside [0, rows) too)
     if (make_operand_map(&op->ta, GEMM_BF16, A, C, rows, C, 128, err)) return 1;
   }
-  if (op->two_cta) {  // the pair kernel does not know about taps: fall back to the 1-CTA kernel
-    op->two_cta = 0;
-    op->res_tma = 0;
-    op->bn = (Cout % 256 == 0) ? 256 : 128;
-    const long long tiles = (long long)((rows + 127) / 128) * ((Cout + op->bn - 1) / op->bn);
-    op->grid = (int)(tiles < num_sms ? tiles : num_sms);
-    if (make_operand_map(&op->tb, GEMM_BF16, B, Kv, Cout, Kv, op->bn, err)) return 1;
-  }
+  op->res_tma = 0;   // (both kernels address the taps in their producers; the pair kernel's A box is the same 128 rows)
   op->conv_w2 = W2;
   op->conv_cblocks = pair ? 1 : cpad / 64;
   op->conv_pair = pair ? 1 : 0;
   return 0;
+}
+
+// Launch with the programmatic-stream-serialization attribute (PDL, ptx.cuh) unless SPM_PDL=0.
+bool gemm_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SPM_PDL"); return e == nullptr || atoi(e) != 0; }();
+  return on;
+}
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = gemm_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
@@ -393,17 +424,20 @@ int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
   int slot = -1;
   const bool prof = profile_gemm_begin(stream, (op->kind & 1) * 2 + (op->bn == 256 ? 1 : 0),
                                        2.0 * (double)op->M * (double)op->N * (double)op->K, &slot);
-#define SPM_LAUNCH(BN, KIND)                                                                                 \
-  gemm_tcgen05_kernel<BN, KIND><<<op->grid, 384, GemmTile<BN, KIND>::SMEM_BYTES, stream>>>(op->ta, op->tb, a)
+#define SPM_LAUNCH(BN, KIND) \
+  launch_pdl(gemm_tcgen05_kernel<BN, KIND>, op->grid, 384, GemmTile<BN, KIND>::SMEM_BYTES, stream, op->ta, op->tb, a)
   if (op->kind == GEMM_F32_SIMT) {
     sgemm_f32_run(op, stream);
   } else if (op->two_cta) {
     gemm2_launch(op, stream);
   } else if (op->conv_cblocks > 0 || op->ep.border_w2 > 0) {  // convolution path (bf16): taps / zero borders
-    if (op->bn == 256)
-      gemm_tcgen05_kernel<256, GEMM_BF16, true><<<op->grid, 384, GemmTile<256, GEMM_BF16>::SMEM_BYTES, stream>>>(op->ta, op->tb, a);
-    else
-      gemm_tcgen05_kernel<128, GEMM_BF16, true><<<op->grid, 384, GemmTile<128, GEMM_BF16>::SMEM_BYTES, stream>>>(op->ta, op->tb, a);
+#define SPM_LAUNCH_CONV(BN) \
+  launch_pdl(gemm_tcgen05_kernel<BN, GEMM_BF16, true>, op->grid, 384, GemmTile<BN, GEMM_BF16>::SMEM_BYTES, stream, op->ta, op->tb, a)
+    if (op->bn == 256) SPM_LAUNCH_CONV(256);
+    else if (op->bn == 128) SPM_LAUNCH_CONV(128);
+    else if (op->bn == 64) SPM_LAUNCH_CONV(64);
+    else SPM_LAUNCH_CONV(32);
+#undef SPM_LAUNCH_CONV
   } else if (op->kind == GEMM_BF16) {
     if (op->bn == 256) SPM_LAUNCH(256, GEMM_BF16); else SPM_LAUNCH(128, GEMM_BF16);
   } else {

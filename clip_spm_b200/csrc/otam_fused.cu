@@ -8,7 +8,7 @@
 //   warp 0      producer: per 32-column chunk two TMA boxes ([Q,T,32] query rows, [W,T,32] class rows; 4-D tensor
 //               maps, so arbitrary 16-byte-aligned strides work) into a 10-stage SWIZZLE_128B ring -- ~110 KB in
 //               flight per SM, running across problem boundaries
-//   warps 1-8   products: chunk n belongs to warp n % 8 (a K split); 3xTF32 mma.sync m16n8k8 (hi*hi + hi*lo + lo*hi,
+//   warps 1-8   products: chunk n belongs to warp n % 8 (a K split); 3xTF32 mma.sync m16n8k8 (lo*hi + hi*lo + hi*hi,
 //               fp32-accurate: the distances are 1 - cos of nearly parallel frames), fragments read conflict-free from the
 //               swizzled rows, squared norms accumulated on the way; per problem the eight partial tiles are summed
 //               in a fixed order (deterministic) into the [Q*W][T][T] distance tables of a double-buffered smem slot
@@ -50,9 +50,8 @@ constexpr int OFF_BAR = OFF_RES + 2 * 64 * 4;                            // mbar
 constexpr int F_SMEM_BYTES = OFF_BAR + (2 * F_STAGES + 4) * 8 + 1024;    // + alignment slack
 static_assert(F_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -141,15 +140,18 @@ otam_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
           // element (row r, column kk*8 + x) of a SWIZZLE_128B row sits in 16-byte unit ((kk*2 + x/4) ^ (r & 7)); every
           // fragment row of this lane has r & 7 == g, so the 32 lanes of a load hit 32 different banks
           const int o0 = (((2 * kk) ^ g) << 2) + t, o1 = (((2 * kk + 1) ^ g) << 2) + t;
-          uint32_t bh[F_NT][2], bl[F_NT][2];
+          // x = hi + lo with hi = x truncated to tf32 (one LOP3; masked explicitly so the split does not depend on how the
+          // tensor core treats the low mantissa bits of a raw fp32 operand) and lo = x - hi (|lo| < 2^-10 |x|, exact)
+          uint32_t bx[F_NT][2], bl[F_NT][2];
 #pragma unroll
           for (int j = 0; j < F_NT; ++j) {
             const float* row = sb + (j * 8 + g) * 32;
             const float x0 = row[o0], x1 = row[o1];
             nb[j] = fmaf(x0, x0, fmaf(x1, x1, nb[j]));
-            bh[j][0] = tf32_hi(x0); bl[j][0] = __float_as_uint(x0 - __uint_as_float(bh[j][0]));
-            bh[j][1] = tf32_hi(x1); bl[j][1] = __float_as_uint(x1 - __uint_as_float(bh[j][1]));
+            bx[j][0] = __float_as_uint(x0) & 0xffffe000u; bl[j][0] = __float_as_uint(x0 - __uint_as_float(bx[j][0]));
+            bx[j][1] = __float_as_uint(x1) & 0xffffe000u; bl[j][1] = __float_as_uint(x1 - __uint_as_float(bx[j][1]));
           }
+          uint32_t ax[F_MT][4], al[F_MT][4];
 #pragma unroll
           for (int i = 0; i < F_MT; ++i) {
             const float* r0 = sa + (i * 16 + g) * 32;
@@ -158,19 +160,26 @@ otam_fused_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
             const float x[4] = {r0[o0], r1[o0], r0[o1], r1[o1]};
             na[i][0] = fmaf(x[0], x[0], fmaf(x[2], x[2], na[i][0]));
             na[i][1] = fmaf(x[1], x[1], fmaf(x[3], x[3], na[i][1]));
-            uint32_t ah[4], al[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              ah[e] = tf32_hi(x[e]);
-              al[e] = __float_as_uint(x[e] - __uint_as_float(ah[e]));
-            }
-#pragma unroll
-            for (int j = 0; j < F_NT; ++j) {
-              mma_tf32(acc[i][j], al, bh[j][0], bh[j][1]);
-              mma_tf32(acc[i][j], ah, bl[j][0], bl[j][1]);
-              mma_tf32(acc[i][j], ah, bh[j][0], bh[j][1]);
+              ax[i][e] = __float_as_uint(x[e]) & 0xffffe000u;
+              al[i][e] = __float_as_uint(x[e] - __uint_as_float(ax[i][e]));
             }
           }
+          // three passes over the 15 accumulator tiles: consecutive MMAs never touch the same accumulator, so the tensor
+          // pipe is not serialised on the accumulate dependency (two product warps per scheduler cannot hide it otherwise)
+#pragma unroll
+          for (int i = 0; i < F_MT; ++i)
+#pragma unroll
+            for (int j = 0; j < F_NT; ++j) mma_tf32(acc[i][j], al[i], bx[j][0], bx[j][1]);
+#pragma unroll
+          for (int i = 0; i < F_MT; ++i)
+#pragma unroll
+            for (int j = 0; j < F_NT; ++j) mma_tf32(acc[i][j], ax[i], bl[j][0], bl[j][1]);
+#pragma unroll
+          for (int i = 0; i < F_MT; ++i)
+#pragma unroll
+            for (int j = 0; j < F_NT; ++j) mma_tf32(acc[i][j], ax[i], bx[j][0], bx[j][1]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);   // the stage may be refilled
@@ -267,7 +276,12 @@ int k_otam_fused(cudaStream_t st, const float* sup, long long s_p, long long s_w
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
   }();
-  static const bool enabled = [] { const char* e = getenv("SPM_OTAM_FUSED"); return e == nullptr || atoi(e) != 0; }();
+  // Opt-in (SPM_OTAM_FUSED=1).  Measured r02 (tools/time_head_kernels.py, P = 1000): 88 us against 76 us for the
+  // two-kernel path -- correct, every operand byte read once (ncu: 164 MB), but the four wavefront warps run their five
+  // rounds of 17 dependent diagonal steps at ~270 cycles per step, ~23 k cycles per problem, where the product warps need
+  // ~6 k; hiding that chain takes >= 16 wavefront warps, which the register budget of one CTA per SM (8 product warps at
+  // 128 registers) does not leave without setmaxnreg re-balancing.  Kept for that next step; the default stays two kernels.
+  static const bool enabled = [] { const char* e = getenv("SPM_OTAM_FUSED"); return e != nullptr && atoi(e) != 0; }();
   if (!enabled || P < 2 * sms) return -3;
   if (T < 2 || T > 30 || Q * T > F_MP || W * T > F_NP || Q * W * (single_direct ? 1 : 2) > 64) return -3;
   if (D % (32 * F_MMA_WARPS) != 0) return -3;

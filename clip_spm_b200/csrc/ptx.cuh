@@ -30,6 +30,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining; pdl_wait() blocks until the predecessor has completed and
+// its memory is visible (a no-op for ordinary launches), pdl_launch_dependents() lets the successor's CTAs be scheduled
+// as soon as this grid's CTAs free their SM resources.  Everything before pdl_wait() must not touch global memory that
+// an earlier kernel writes (barrier init, TMEM allocation, tensor-map prefetch are fine).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

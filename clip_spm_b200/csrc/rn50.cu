@@ -31,10 +31,18 @@
 namespace spm {
 
 namespace {
-constexpr int RN_CHUNK = 64;
+// Frames per launch, in two granularities (r02).  The FRONT (stem, layer1, layer2: 3364 .. 900 pixel rows per frame) runs
+// in sub-chunks small enough that consecutive kernels meet their operands in the 126 MB L2; the BACK (layer3, layer4,
+// attention pool: 256 / 81 rows per frame) runs over several front sub-chunks at once, so that its GEMMs have enough
+// 256-row pair tiles for all 74 CTA pairs (216 frames: layer3 216 pair rows = 2.9 rounds, layer4 69 x 2 = 1.9 rounds;
+// at 64 frames layer4's 512-channel convolutions were 164 tiles of 128 x 128 = 1.1 rounds).
+// SPM_RN50_FRONT_CHUNK / SPM_RN50_BACK_CHUNK override (back is rounded to a multiple of front).
+constexpr int RN_FRONT_DEFAULT = 216, RN_BACK_DEFAULT = 216;
+constexpr int N_FRONT_BLOCKS = 7;   // layer1 (3) + layer2 (4)
 constexpr int EMB = 2048, HEADS = 32, HD = 64, OUT_DIM = 1024, NTOK = 50;
 constexpr long long FRAME_ELEMS = 3LL * 224 * 224;
 constexpr long long SCRATCH_PER_FRAME = 58LL * 58 * 256;   // largest padded activation: 58x58x256 (> 114x114x64)
+constexpr long long MID_PER_FRAME = 30LL * 30 * 512;       // layer2 output = layer3 input (and the back's largest tensor)
 constexpr long long COL_PER_FRAME = 114LL * 114 * 32;      // stem conv1 im2col over the padded 114x114 grid
 
 #define RN_LAUNCH_CHECK()                                                         \
@@ -147,18 +155,30 @@ __global__ void avgpool2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloa
 }
 
 // attention-pool tokens (clip_fsar.py:407-410): tok[f,0] = mean_s x[f,s] + pos[0]; tok[f,1+s] = x[f,s] + pos[1+s]
-__global__ void attnpool_tokens_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ pos,
-                                       __nv_bfloat16* __restrict__ tok) {
-  const int f = blockIdx.x;
-  for (int c = threadIdx.x; c < EMB; c += blockDim.x) {
-    float mean = 0.f;
-    for (int s = 0; s < 49; ++s) {
-      const float v = __bfloat162float(x[((long long)f * 81 + (s / 7 + 1) * 9 + (s % 7 + 1)) * EMB + c]);
-      mean += v;
-      tok[((long long)f * NTOK + 1 + s) * EMB + c] = __float2bfloat16_rn(v + pos[(1 + s) * EMB + c]);
-    }
-    tok[(long long)f * NTOK * EMB + c] = __float2bfloat16_rn(mean * (1.f / 49.f) + pos[c]);
+// grid (F, EMB / 1024): a thread owns 8 channels (16 bytes) of one frame; the 49 spatial rows stream through it once
+__global__ void __launch_bounds__(128)
+attnpool_tokens_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ pos,
+                       __nv_bfloat16* __restrict__ tok) {
+  const int f = blockIdx.x, c = (blockIdx.y * 128 + threadIdx.x) * 8;
+  float mean[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < 49; ++s) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((long long)f * 81 + (s / 7 + 1) * 9 + (s % 7 + 1)) * EMB + c));
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + (1 + s) * EMB + c));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + (1 + s) * EMB + c + 4));
+    const float2 a = bf2(v.x), b = bf2(v.y), cc = bf2(v.z), d = bf2(v.w);
+    mean[0] += a.x; mean[1] += a.y; mean[2] += b.x; mean[3] += b.y;
+    mean[4] += cc.x; mean[5] += cc.y; mean[6] += d.x; mean[7] += d.y;
+    uint4 o;
+    o.x = pk(a.x + p0.x, a.y + p0.y); o.y = pk(b.x + p0.z, b.y + p0.w);
+    o.z = pk(cc.x + p1.x, cc.y + p1.y); o.w = pk(d.x + p1.z, d.y + p1.w);
+    *reinterpret_cast<uint4*>(tok + ((long long)f * NTOK + 1 + s) * EMB + c) = o;
   }
+  const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + c)), p1 = __ldg(reinterpret_cast<const float4*>(pos + c + 4));
+  const float k = 1.f / 49.f;
+  uint4 o;
+  o.x = pk(mean[0] * k + p0.x, mean[1] * k + p0.y); o.y = pk(mean[2] * k + p0.z, mean[3] * k + p0.w);
+  o.z = pk(mean[4] * k + p1.x, mean[5] * k + p1.y); o.w = pk(mean[6] * k + p1.z, mean[7] * k + p1.w);
+  *reinterpret_cast<uint4*>(tok + (long long)f * NTOK * EMB + c) = o;
 }
 
 // one warp per (frame, head): q [F, 2048], kv [F*50, 4096] (k | v) -> o [F, 2048]
@@ -217,6 +237,8 @@ struct Plan {
 
 struct Rn50 {
   int sms = 148;
+  int front = RN_FRONT_DEFAULT, back = RN_BACK_DEFAULT;
+  __nv_bfloat16* mid = nullptr;   // [back, 30, 30, 512] layer2 outputs of the current back chunk
   std::vector<void*> allocs;
   Conv stem[3];
   std::vector<Block> blocks;
@@ -226,7 +248,8 @@ struct Rn50 {
   // workspace (RN_CHUNK frames)
   __nv_bfloat16 *xa = nullptr, *xb = nullptr, *t1 = nullptr, *t2 = nullptr, *t2p = nullptr, *xd = nullptr,
                 *idn = nullptr, *col = nullptr, *tok = nullptr, *qbuf = nullptr, *kvbuf = nullptr, *obuf = nullptr;
-  std::map<int, std::unique_ptr<Plan>> plans;
+  std::map<int, std::unique_ptr<Plan>> plans;        // front, by frame count
+  std::map<int, std::unique_ptr<Plan>> back_plans;   // back, by frame count
 };
 
 namespace {
@@ -292,15 +315,10 @@ int plan_conv(Rn50* r, Plan* pl, const Conv& c, const __nv_bfloat16* A, long lon
   return 0;
 }
 
-// Builds the GEMM list in execution order for F frames.  The non-GEMM kernels are replayed in the same order by run().
-int build_plan(Rn50* r, int F, Plan* pl) {
-  const long long R114 = (long long)F * 114 * 114;
-  SPM_TRY(plan_conv(r, pl, r->stem[0], r->col, R114, 114, r->t1, true, nullptr));   // explicit im2col (from the image)
-  SPM_TRY(plan_conv(r, pl, r->stem[1], r->t1, R114, 114, r->t2, true, nullptr));    // implicit 3x3
-  SPM_TRY(plan_conv(r, pl, r->stem[2], r->t2, R114, 114, r->t1, true, nullptr));    // implicit 3x3
-  __nv_bfloat16 *x = r->xa, *y = r->xb;
-  int H = 56;
-  for (const Block& b : r->blocks) {
+// GEMM lists in execution order.  The non-GEMM kernels are replayed in the same order by run_front / run_back.
+int plan_blocks(Rn50* r, Plan* pl, int F, int b_begin, int b_end, __nv_bfloat16*& x, __nv_bfloat16*& y, int& H) {
+  for (int bi = b_begin; bi < b_end; ++bi) {
+    const Block& b = r->blocks[bi];
     const int Ho = H / b.stride;
     const long long rows_in = (long long)F * (H + 2) * (H + 2), rows_out = (long long)F * (Ho + 2) * (Ho + 2);
     SPM_TRY(plan_conv(r, pl, b.c1, x, rows_in, H + 2, r->t1, true, nullptr));
@@ -315,6 +333,25 @@ int build_plan(Rn50* r, int F, Plan* pl) {
     std::swap(x, y);
     H = Ho;
   }
+  return 0;
+}
+
+// stem + layer1 + layer2 for F frames; the last convolution's output pointer is patched per call (-> r->mid + offset)
+int build_front_plan(Rn50* r, int F, Plan* pl) {
+  const long long R114 = (long long)F * 114 * 114;
+  SPM_TRY(plan_conv(r, pl, r->stem[0], r->col, R114, 114, r->t1, true, nullptr));   // explicit im2col (from the image)
+  SPM_TRY(plan_conv(r, pl, r->stem[1], r->t1, R114, 114, r->t2, true, nullptr));    // implicit 3x3
+  SPM_TRY(plan_conv(r, pl, r->stem[2], r->t2, R114, 114, r->t1, true, nullptr));    // implicit 3x3
+  __nv_bfloat16 *x = r->xa, *y = r->xb;
+  int H = 56;
+  return plan_blocks(r, pl, F, 0, N_FRONT_BLOCKS, x, y, H);
+}
+
+// layer3 + layer4 + attention pool for F frames, reading r->mid
+int build_back_plan(Rn50* r, int F, Plan* pl) {
+  __nv_bfloat16 *x = r->mid, *y = r->xb;
+  int H = 28;
+  SPM_TRY(plan_blocks(r, pl, F, N_FRONT_BLOCKS, (int)r->blocks.size(), x, y, H));
   // attention pool: kv over all 50 tokens, q over the mean tokens (row stride 50*2048), c_proj
   const char* err = "";
   {
@@ -353,11 +390,37 @@ int avgpool(cudaStream_t st, const __nv_bfloat16* in, __nv_bfloat16* out, int F,
   return 0;
 }
 
-int run_chunk(Rn50* r, cudaStream_t st, const float* images, int F, float* feats_out) {
+// the residual blocks [b_begin, b_end) in plan order
+int run_blocks(Rn50* r, cudaStream_t st, const std::vector<GemmOp>& ops, size_t& g, int F, int b_begin, int b_end,
+               __nv_bfloat16*& x, __nv_bfloat16*& y, int& H, __nv_bfloat16* last_out) {
+  for (int bi = b_begin; bi < b_end; ++bi) {
+    const Block& b = r->blocks[bi];
+    SPM_TRY(run_gemm(ops[g++], st));                                   // conv1 1x1 -> t1
+    SPM_TRY(run_gemm(ops[g++], st));                                   // conv2 3x3 (implicit) -> t2
+    if (b.stride > 1) SPM_TRY(avgpool(st, r->t2, r->t2p, F, H, b.planes));
+    if (b.has_down) {
+      if (b.stride > 1) SPM_TRY(avgpool(st, x, r->xd, F, H, b.inpl));
+      SPM_TRY(run_gemm(ops[g++], st));                                 // downsample conv+bn -> idn
+    }
+    if (bi == b_end - 1 && last_out != nullptr) {                      // conv3 + bn3 + identity + relu -> caller's buffer
+      GemmOp c3 = ops[g++];
+      c3.ep.out = last_out;
+      SPM_TRY(run_gemm(c3, st));
+    } else {
+      SPM_TRY(run_gemm(ops[g++], st));                                 // conv3 + bn3 + identity + relu -> y
+    }
+    std::swap(x, y);
+    H /= b.stride;
+  }
+  return 0;
+}
+
+// stem + layer1 + layer2 of F frames -> out [F, 30, 30, 512] (zero-bordered)
+int run_front(Rn50* r, cudaStream_t st, const float* images, int F, __nv_bfloat16* out) {
   auto it = r->plans.find(F);
   if (it == r->plans.end()) {
     std::unique_ptr<Plan> pl(new Plan());
-    SPM_TRY(build_plan(r, F, pl.get()));
+    SPM_TRY(build_front_plan(r, F, pl.get()));
     it = r->plans.emplace(F, std::move(pl)).first;
   }
   const std::vector<GemmOp>& ops = it->second->ops;
@@ -370,23 +433,27 @@ int run_chunk(Rn50* r, cudaStream_t st, const float* images, int F, float* feats
   SPM_TRY(run_gemm(ops[g++], st));                         // conv2 (implicit 3x3) -> t2 [.,32]
   SPM_TRY(run_gemm(ops[g++], st));                         // conv3 (implicit 3x3) -> t1 [.,64]
   SPM_TRY(avgpool(st, r->t1, r->xa, F, 112, 64));          // -> x [F,58,58,64]
-  // ---- residual layers (clip_fsar.py:534-547)
+  // ---- layer1, layer2 (clip_fsar.py:534-547)
   __nv_bfloat16 *x = r->xa, *y = r->xb;
   int H = 56;
-  for (const Block& b : r->blocks) {
-    SPM_TRY(run_gemm(ops[g++], st));                                   // conv1 1x1 -> t1
-    SPM_TRY(run_gemm(ops[g++], st));                                   // conv2 3x3 (implicit) -> t2
-    if (b.stride > 1) SPM_TRY(avgpool(st, r->t2, r->t2p, F, H, b.planes));
-    if (b.has_down) {
-      if (b.stride > 1) SPM_TRY(avgpool(st, x, r->xd, F, H, b.inpl));
-      SPM_TRY(run_gemm(ops[g++], st));                                 // downsample conv+bn -> idn
-    }
-    SPM_TRY(run_gemm(ops[g++], st));                                   // conv3 + bn3 + identity + relu -> y
-    std::swap(x, y);
-    H /= b.stride;
+  return run_blocks(r, st, ops, g, F, 0, N_FRONT_BLOCKS, x, y, H, out);
+}
+
+// layer3 + layer4 + attention pool of the F frames in r->mid -> feats_out [F, 1024]
+int run_back(Rn50* r, cudaStream_t st, int F, float* feats_out) {
+  auto it = r->back_plans.find(F);
+  if (it == r->back_plans.end()) {
+    std::unique_ptr<Plan> pl(new Plan());
+    SPM_TRY(build_back_plan(r, F, pl.get()));
+    it = r->back_plans.emplace(F, std::move(pl)).first;
   }
+  const std::vector<GemmOp>& ops = it->second->ops;
+  size_t g = 0;
+  __nv_bfloat16 *x = r->mid, *y = r->xb;
+  int H = 28;
+  SPM_TRY(run_blocks(r, st, ops, g, F, N_FRONT_BLOCKS, (int)r->blocks.size(), x, y, H, nullptr));
   // ---- attention pool
-  attnpool_tokens_kernel<<<F, 256, 0, st>>>(x, r->pos, r->tok);
+  attnpool_tokens_kernel<<<dim3(F, EMB / 1024), 128, 0, st>>>(x, r->pos, r->tok);
   RN_LAUNCH_CHECK();
   SPM_TRY(run_gemm(ops[g++], st));  // k | v
   SPM_TRY(run_gemm(ops[g++], st));  // q (mean token)
@@ -446,8 +513,12 @@ int rn50_create(Rn50** out, cudaStream_t st, int sms, const WeightGetter& get) {
   SPM_TRY(load_linear(r.get(), st, get, ap + "k_proj", EMB, EMB, r->kv_w, r->kv_b));
   SPM_TRY(load_linear(r.get(), st, get, ap + "v_proj", EMB, EMB, r->kv_w + (long long)EMB * EMB, r->kv_b + EMB));
   SPM_TRY(load_linear(r.get(), st, get, ap + "c_proj", OUT_DIM, EMB, r->c_w, r->c_b));
-  // workspace
-  const long long S = SCRATCH_PER_FRAME * RN_CHUNK;
+  // workspace: the buffers are shared by the front (sized per front sub-chunk) and the back (per back chunk)
+  if (const char* e = getenv("SPM_RN50_FRONT_CHUNK")) r->front = std::max(1, atoi(e));
+  if (const char* e = getenv("SPM_RN50_BACK_CHUNK")) r->back = std::max(1, atoi(e));
+  r->back = std::max(r->front, r->back / r->front * r->front);
+  const long long S = std::max(SCRATCH_PER_FRAME * r->front, MID_PER_FRAME * r->back);
+  SPM_TRY(ralloc(r.get(), &r->mid, MID_PER_FRAME * r->back));
   SPM_TRY(ralloc(r.get(), &r->xa, S));
   SPM_TRY(ralloc(r.get(), &r->xb, S));
   SPM_TRY(ralloc(r.get(), &r->t1, S));
@@ -455,20 +526,24 @@ int rn50_create(Rn50** out, cudaStream_t st, int sms, const WeightGetter& get) {
   SPM_TRY(ralloc(r.get(), &r->t2p, S));
   SPM_TRY(ralloc(r.get(), &r->xd, S));
   SPM_TRY(ralloc(r.get(), &r->idn, S));
-  SPM_TRY(ralloc(r.get(), &r->col, COL_PER_FRAME * RN_CHUNK));
-  SPM_TRY(ralloc(r.get(), &r->tok, (long long)RN_CHUNK * NTOK * EMB));
-  SPM_TRY(ralloc(r.get(), &r->qbuf, (long long)RN_CHUNK * EMB));
-  SPM_TRY(ralloc(r.get(), &r->kvbuf, (long long)RN_CHUNK * NTOK * 2 * EMB));
-  SPM_TRY(ralloc(r.get(), &r->obuf, (long long)RN_CHUNK * EMB));
+  SPM_TRY(ralloc(r.get(), &r->col, COL_PER_FRAME * r->front));
+  SPM_TRY(ralloc(r.get(), &r->tok, (long long)r->back * NTOK * EMB));
+  SPM_TRY(ralloc(r.get(), &r->qbuf, (long long)r->back * EMB));
+  SPM_TRY(ralloc(r.get(), &r->kvbuf, (long long)r->back * NTOK * 2 * EMB));
+  SPM_TRY(ralloc(r.get(), &r->obuf, (long long)r->back * EMB));
   *out = r.release();
   return 0;
 }
 
 int rn50_encode(Rn50* r, cudaStream_t st, const float* images, int n_frames, float* feats_out) {
   SPM_CHECK(r != nullptr && !r->blocks.empty(), "RN50 encoder: backbone weights were not loaded");
-  for (int f0 = 0; f0 < n_frames; f0 += RN_CHUNK) {
-    const int F = std::min(RN_CHUNK, n_frames - f0);
-    SPM_TRY(run_chunk(r, st, images + (long long)f0 * FRAME_ELEMS, F, feats_out + (long long)f0 * OUT_DIM));
+  for (int b0 = 0; b0 < n_frames; b0 += r->back) {
+    const int FB = std::min(r->back, n_frames - b0);
+    for (int f0 = 0; f0 < FB; f0 += r->front) {
+      const int F = std::min(r->front, FB - f0);
+      SPM_TRY(run_front(r, st, images + (long long)(b0 + f0) * FRAME_ELEMS, F, r->mid + (long long)f0 * MID_PER_FRAME));
+    }
+    SPM_TRY(run_back(r, st, FB, feats_out + (long long)b0 * OUT_DIM));
   }
   return 0;
 }
