@@ -75,6 +75,11 @@ SIGNATURES = {
     "spm_transform_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "spm_frame_geometry": (c_int, [c_int, c_int] + [ctypes.POINTER(c_int)] * 4),
     "spm_encode_frames_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "spm_eval_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float]
+                    + [c_void_p] * 5),
+    "spm_jpeg_info": (c_int, [c_void_p, c_ll] + [ctypes.POINTER(c_int)] * 4),
+    "spm_jpeg_decode": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_int64), c_int, c_int,
+                                c_void_p]),
     "spm_eval_host_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float]
                          + [c_void_p] * 5),
 }

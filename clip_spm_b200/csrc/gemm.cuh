@@ -53,6 +53,10 @@ struct GemmOp {
   // p holds the channels of pixels p and p+1 and every TMA box is a full 128-byte line; the 9 taps become 6 k-blocks
   // (dy, {x-1, x}) and (dy, {x+1, -}) instead of 9 half-empty ones
   int conv_pair = 0;
+  // 3x3 convolutions with few channels (conv_win.cu): all nine taps served from one shared-memory window per tile, the
+  // folded weights resident in shared memory; `tr` then holds the window tensor map
+  int conv_win = 0, conv_win_rows = 0, conv_win_stages = 0, conv_win_taps = 0, conv_win_halo = 0;
+  int conv_win_roff[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // row offset of each tap
   int reverse = 0;  // visit the output tiles in descending order (same results; L2 reuse between consecutive kernels)
   int two_cta = 0;  // 1: launched as 2-CTA clusters (gemm2_tcgen05.cu), 256x256 tile per CTA pair
   // 2-CTA kernel, fp32 out + fp32 residual with identity row mapping: the epilogue warps prefetch the residual tile
@@ -72,6 +76,14 @@ int gemm_plan_conv3x3(GemmOp* op, const void* A, int C, int rows, int W2, const 
                       int num_sms, const char** err);
 // true if the driver accepts a tensor map whose row stride is smaller than its row extent (needed by conv_pair)
 bool gemm_conv_pair_supported();
+// conv_win.cu
+bool conv_win_plan(GemmOp* op, const void* A, int C, int rows, int W2, int Cout, int num_sms);
+bool conv_win_plan_1x1(GemmOp* op, const void* A, long long lda, int num_sms);
+int conv_win_init();
+void conv_win_launch(const GemmOp* op, cudaStream_t stream);
+// K-contiguous 2-D operand map with a caller-chosen box height (gemm_tcgen05.cu)
+int make_operand_map_rows(CUtensorMap* map, int kind, const void* ptr, long long ld, int rows, int K, int box_rows,
+                          const char** err);
 // fp32 tensor map of rank 2..5 (dims / box innermost first, strides in BYTES for dims 1..rank-1, each a multiple of 16),
 // SWIZZLE_128B (the box's innermost extent must be 32 floats = 128 bytes); 0 on success
 int make_tensor_map_f32_nd(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,

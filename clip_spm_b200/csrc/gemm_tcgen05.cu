@@ -271,6 +271,11 @@ int make_tensor_map_f32_nd(CUtensorMap* map, const void* base, int rank, const u
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
 }
 
+int make_operand_map_rows(CUtensorMap* map, int kind, const void* ptr, long long ld, int rows, int K, int box_rows,
+                          const char** err) {
+  return make_operand_map(map, kind, ptr, ld, rows, K, box_rows, err);
+}
+
 bool gemm_conv_pair_supported() {
   static const int ok = [] {
     if (const char* e = getenv("SPM_CONV_PAIR")) if (atoi(e) == 0) return 0;
@@ -312,6 +317,7 @@ int gemm_init(const char** err) {
     *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the conv GEMM kernel";
     return 1;
   }
+  if (conv_win_init()) { *err = "cudaFuncSetAttribute failed for the window convolution kernel"; return 1; }
   return gemm2_init(err);
 }
 
@@ -376,6 +382,8 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
     if (make_operand_map(&op->tr, GEMM_TF32, ep.residual, ep.ldr, M, N, 32, err)) return 1;
     op->res_tma = 1;
   }
+  op->conv_win = 0;
+  if (ep.border_w2 > 0 && !op->two_cta) conv_win_plan_1x1(op, A, lda, num_sms);   // few-channel 1x1 convolutions (conv_win.cu)
   return 0;
 }
 
@@ -398,6 +406,7 @@ int gemm_plan_conv3x3(GemmOp* op, const void* A, int C, int rows, int W2, const 
   op->conv_w2 = W2;
   op->conv_cblocks = pair ? 1 : cpad / 64;
   op->conv_pair = pair ? 1 : 0;
+  if (!op->two_cta) conv_win_plan(op, A, C, rows, W2, Cout, num_sms);   // few-channel layers: one shared-memory window per tile
   return 0;
 }
 
@@ -428,6 +437,8 @@ int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
   launch_pdl(gemm_tcgen05_kernel<BN, KIND>, op->grid, 384, GemmTile<BN, KIND>::SMEM_BYTES, stream, op->ta, op->tb, a)
   if (op->kind == GEMM_F32_SIMT) {
     sgemm_f32_run(op, stream);
+  } else if (op->conv_win) {
+    conv_win_launch(op, stream);
   } else if (op->two_cta) {
     gemm2_launch(op, stream);
   } else if (op->conv_cblocks > 0 || op->ep.border_w2 > 0) {  // convolution path (bf16): taps / zero borders

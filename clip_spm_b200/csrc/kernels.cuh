@@ -24,6 +24,8 @@ int k_patch_im2col(cudaStream_t st, const float* images, __nv_bfloat16* patches,
 int k_layernorm(cudaStream_t st, const float* in, long long in_stride, int rows, int C, const float* gamma,
                 const float* beta, const float* cls_row, int cls_period, float* out_f32, __nv_bfloat16* out_bf16,
                 long long out_stride, int reverse = 0);
+int k_layernorm_bf16in(cudaStream_t st, const __nv_bfloat16* in, long long in_stride, int rows, int C, const float* gamma,
+                       const float* beta, __nv_bfloat16* out_bf16, long long out_stride, int reverse = 0);
 // softmax(Q K^T / 8) V for 12 heads x 64 dims over 197 tokens per frame (clip_fsar.py:626,638), bf16 tensor cores.
 //   qkv [F*197, 2304] bf16 (q | k | v, head h at columns h*64) -> out [F*197, 768] bf16
 int k_vit_attention(cudaStream_t st, const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames);

@@ -135,13 +135,14 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   SPM_CHECK(cfg != nullptr && out != nullptr, "spm_create: null argument");
   SPM_CHECK(cfg->backbone == SPM_BACKBONE_VIT_B16 || cfg->backbone == SPM_BACKBONE_RN50, "spm_create: unknown backbone");
   SPM_CHECK(cfg->seq_len >= 2 && cfg->seq_len <= 30, "spm_create: seq_len must be in [2, 30]");
-  SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->precision == SPM_PRECISION_FP32, "spm_create: unknown precision");
+  SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->precision == SPM_PRECISION_FP32 ||
+            cfg->precision == SPM_PRECISION_BF16_RESID, "spm_create: unknown precision");
   SPM_CHECK(cfg->head == SPM_HEAD_CLIPSPM || cfg->head == SPM_HEAD_CLIPFSAR || cfg->head == SPM_HEAD_STEN,
             "spm_create: unknown head");
   SPM_CHECK(cfg->head != SPM_HEAD_STEN || cfg->seq_len == 8,
             "spm_create: the STEN head reshapes to 8 frames per video (models/model_sten.py:65-66)");
   SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->backbone == SPM_BACKBONE_VIT_B16,
-            "spm_create: SPM_PRECISION_FP32 is implemented for the ViT-B/16 backbone only");
+            "spm_create: SPM_PRECISION_FP32 / SPM_PRECISION_BF16_RESID are implemented for the ViT-B/16 backbone only");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error("spm_create: no CUDA device -- this library has no CPU path");
@@ -154,6 +155,7 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   std::unique_ptr<spm_handle> h(new spm_handle());
   h->cfg = *cfg;
   h->fp32 = cfg->precision == SPM_PRECISION_FP32;
+  h->resid_bf16 = cfg->precision == SPM_PRECISION_BF16_RESID;
   h->D = cfg->backbone == SPM_BACKBONE_VIT_B16 ? 512 : 1024;
   h->HT = (int)(h->D * cfg->mid_dim_text);
   h->HV = (int)(h->D * cfg->mid_dim_vision);
@@ -322,6 +324,19 @@ int spm_eval(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, c
   return forward_impl(h, (cudaStream_t)stream, n_episodes, S, Q, W, support_images, target_images, support_labels,
                       real_support, real_target, reinterpret_cast<const long long*>(target_labels), tasks_per_batch,
                       logits_out, dists_out, loss_out, acc_out, pred_out);
+}
+
+int spm_eval_u8(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, int img_h, int img_w,
+                const uint8_t* support_frames, const uint8_t* target_frames, const float* support_labels,
+                const float* real_support, const float* real_target, const int64_t* target_labels, float tasks_per_batch,
+                float* logits_out, float* dists_out, float* loss_out, float* acc_out, int32_t* pred_out) {
+  SPM_CHECK(support_frames && target_frames && support_labels && real_support && real_target, "spm_eval_u8: null argument");
+  SPM_CHECK(h != nullptr, "spm_eval_u8: null handle");
+  SPM_CHECK(img_h > 0 && img_w > 0, "spm_eval_u8: bad frame size");
+  SPM_TRY(reset_err_flag(h, (cudaStream_t)stream));
+  return forward_impl(h, (cudaStream_t)stream, n_episodes, S, Q, W, support_frames, target_frames, support_labels,
+                      real_support, real_target, reinterpret_cast<const long long*>(target_labels), tasks_per_batch,
+                      logits_out, dists_out, loss_out, acc_out, pred_out, img_h, img_w);
 }
 
 // frame_bytes: bytes of one input frame in host memory (fp32 image, or img_h x img_w x 3 uint8 when img_h > 0)

@@ -119,6 +119,8 @@ struct spm_handle {
   spm::VitW vit;
   spm::VitW32 vit32;
   bool fp32 = false;  // SPM_PRECISION_FP32: CUDA-core fp32 GEMMs / attention, fp32 activations
+  bool resid_bf16 = false;  // SPM_PRECISION_BF16_RESID: bf16 residual stream (xb / xcb below)
+  __nv_bfloat16 *xb = nullptr, *xcb = nullptr;
   float *patches32 = nullptr, *xn32 = nullptr, *qkv32 = nullptr, *attn32 = nullptr, *hid32 = nullptr, *cls32 = nullptr;
   spm::Rn50* rn50 = nullptr;
   spm::HeadW head;
@@ -136,7 +138,7 @@ struct spm_handle {
   // the other's GEMMs.  Bit-identical results (tests), but measured NOT faster: the step sits at the 1000 W power cap,
   // where overlap buys nothing, and multi-stream runs showed sporadic 100-300 ms submission stalls.  Default: 1 stream.
   struct VitWs {
-    __nv_bfloat16 *patches, *xn, *qkv, *attn, *hid, *cls, *xnc;
+    __nv_bfloat16 *patches, *xn, *qkv, *attn, *hid, *cls, *xnc, *xb, *xcb;
     float *x, *xc;
   } vit_ws[2] = {};
   int cur_ws = 0, enc_streams = 1;  // 2 = opt-in (SPM_ENC_STREAMS): measured no faster under the power cap

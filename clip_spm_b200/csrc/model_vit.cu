@@ -76,7 +76,7 @@ namespace {
 void select_vit_ws(spm_handle* h, int i) {
   const spm_handle::VitWs& w = h->vit_ws[i];
   h->patches = w.patches; h->xn = w.xn; h->qkv = w.qkv; h->attn = w.attn; h->hid = w.hid; h->cls = w.cls;
-  h->xnc = w.xnc; h->x = w.x; h->xc = w.xc;
+  h->xnc = w.xnc; h->x = w.x; h->xc = w.xc; h->xb = w.xb; h->xcb = w.xcb;
   h->cur_ws = i;
 }
 
@@ -95,6 +95,11 @@ int ensure_vit_workspace(spm_handle* h) {
     SPM_TRY(dalloc_t(h, &w.cls, (long long)h->frame_chunk * VIT_C));
     SPM_TRY(dalloc_t(h, &w.xc, (long long)h->frame_chunk * VIT_C));
     SPM_TRY(dalloc_t(h, &w.xnc, (long long)h->frame_chunk * VIT_C));
+    w.xb = w.xcb = nullptr;
+    if (h->resid_bf16) {
+      SPM_TRY(dalloc_t(h, &w.xb, M * VIT_C));
+      SPM_TRY(dalloc_t(h, &w.xcb, (long long)h->frame_chunk * VIT_C));
+    }
   }
   if (h->enc_streams > 1) {
     for (int i = 0; i < 2; ++i) {
@@ -149,12 +154,18 @@ int get_vit_plan(spm_handle* h, int F, VitPlan** out) {
     SPM_TRY(plan_gemm(&pl->qkv[i], kind, a_xn, C, f32 ? (const void*)l32.qkv_w : (const void*)l.qkv_w, C, M, 3 * C, C, e1, h->sms));
     GemmEpilogue e2;
     e2.bias = l.out_b; e2.residual = h->x; e2.ldr = C; e2.out = h->x; e2.ldo = C;
+    if (h->resid_bf16) {   // x (bf16) += out_proj(attn): bf16 residual in, bf16 out, in place
+      e2.residual = nullptr; e2.residual_bf16 = h->xb; e2.out = h->xb; e2.out_bf16 = 1;
+    }
     SPM_TRY(plan_gemm(&pl->outp[i], kind, a_attn, C, f32 ? (const void*)l32.out_w : (const void*)l.out_w, C, M, C, C, e2, h->sms));
     GemmEpilogue e3;
     e3.bias = l.fc_b; e3.act = ACT_QUICKGELU; e3.out = o_hid; e3.ldo = 4 * C; e3.out_bf16 = obf;
     SPM_TRY(plan_gemm(&pl->fc[i], kind, a_xn, C, f32 ? (const void*)l32.fc_w : (const void*)l.fc_w, C, M, 4 * C, C, e3, h->sms));
     GemmEpilogue e4;
     e4.bias = l.proj_b; e4.residual = h->x; e4.ldr = C; e4.out = h->x; e4.ldo = C;
+    if (h->resid_bf16) {
+      e4.residual = nullptr; e4.residual_bf16 = h->xb; e4.out = h->xb; e4.out_bf16 = 1;
+    }
     SPM_TRY(plan_gemm(&pl->proj[i], kind, a_hid, 4 * C, f32 ? (const void*)l32.proj_w : (const void*)l.proj_w, 4 * C, M, C, 4 * C, e4, h->sms));
   }
   if (!f32) {
@@ -163,12 +174,18 @@ int get_vit_plan(spm_handle* h, int F, VitPlan** out) {
     const long long LC = (long long)VIT_L * C;
     GemmEpilogue e2;
     e2.bias = l.out_b; e2.residual = h->x; e2.ldr = (int)LC; e2.out = h->xc; e2.ldo = C;
+    if (h->resid_bf16) {
+      e2.residual = nullptr; e2.residual_bf16 = h->xb; e2.out = h->xcb; e2.out_bf16 = 1;
+    }
     SPM_TRY(plan_gemm(&pl->outp_cls, GEMM_BF16, h->attn, LC, l.out_w, C, F, C, C, e2, h->sms));
     GemmEpilogue e3;
     e3.bias = l.fc_b; e3.act = ACT_QUICKGELU; e3.out = h->hid; e3.ldo = 4 * C; e3.out_bf16 = 1;
     SPM_TRY(plan_gemm(&pl->fc_cls, GEMM_BF16, h->xnc, C, l.fc_w, C, F, 4 * C, C, e3, h->sms));
     GemmEpilogue e4;
     e4.bias = l.proj_b; e4.residual = h->xc; e4.ldr = C; e4.out = h->xc; e4.ldo = C;
+    if (h->resid_bf16) {
+      e4.residual = nullptr; e4.residual_bf16 = h->xcb; e4.out = h->xcb; e4.out_bf16 = 1;
+    }
     SPM_TRY(plan_gemm(&pl->proj_cls, GEMM_BF16, h->hid, 4 * C, l.proj_w, 4 * C, F, C, 4 * C, e4, h->sms));
   }
   {
@@ -219,10 +236,13 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
     SPM_GEMM_RUN(_op);                  \
   } while (0)
   SPM_GEMM_RUN_DIR(pl->patch);
-  SPM_KERNEL(k_layernorm(st, h->x, C, M, C, v.ln_pre_g, v.ln_pre_b, v.cls_pos, VIT_L, h->x, nullptr, C, next_dir()));
+  const bool rb = h->resid_bf16;   // bf16 residual stream: ln_pre writes it, every later LayerNorm reads it
+  SPM_KERNEL(k_layernorm(st, h->x, C, M, C, v.ln_pre_g, v.ln_pre_b, v.cls_pos, VIT_L, rb ? nullptr : h->x, rb ? h->xb : nullptr,
+                         C, next_dir()));
   for (int i = 0; i < VIT_LAYERS; ++i) {
     const VitLayerW& l = v.layer[i];
-    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln1_g, l.ln1_b, nullptr, 0, nullptr, h->xn, C, next_dir()));
+    if (rb) SPM_KERNEL(k_layernorm_bf16in(st, h->xb, C, M, C, l.ln1_g, l.ln1_b, h->xn, C, next_dir()));
+    else SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln1_g, l.ln1_b, nullptr, 0, nullptr, h->xn, C, next_dir()));
     SPM_GEMM_RUN_DIR(pl->qkv[i]);
     if (h->attn_mma)
       SPM_KERNEL(k_vit_attention(st, h->qkv, h->attn, F));
@@ -231,22 +251,26 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
     if (i == VIT_LAYERS - 1 && h->prune_last) {
       // only x[:, 0, :] is read after the last block: run its out-proj / MLP on the F class-token rows
       SPM_GEMM_RUN(pl->outp_cls);
-      SPM_KERNEL(k_layernorm(st, h->xc, C, F, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xnc, C));
+      if (rb) SPM_KERNEL(k_layernorm_bf16in(st, h->xcb, C, F, C, l.ln2_g, l.ln2_b, h->xnc, C));
+      else SPM_KERNEL(k_layernorm(st, h->xc, C, F, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xnc, C));
       SPM_GEMM_RUN(pl->fc_cls);
       SPM_GEMM_RUN(pl->proj_cls);
-      SPM_KERNEL(k_layernorm(st, h->xc, C, F, C, v.ln_post_g, v.ln_post_b, nullptr, 0, nullptr, h->cls, C));
+      if (rb) SPM_KERNEL(k_layernorm_bf16in(st, h->xcb, C, F, C, v.ln_post_g, v.ln_post_b, h->cls, C));
+      else SPM_KERNEL(k_layernorm(st, h->xc, C, F, C, v.ln_post_g, v.ln_post_b, nullptr, 0, nullptr, h->cls, C));
       GemmOp fin = pl->fin;
       fin.ep.out = feats_out;
       SPM_GEMM_RUN(fin);
       return 0;
     }
     SPM_GEMM_RUN_DIR(pl->outp[i]);
-    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xn, C, next_dir()));
+    if (rb) SPM_KERNEL(k_layernorm_bf16in(st, h->xb, C, M, C, l.ln2_g, l.ln2_b, h->xn, C, next_dir()));
+    else SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xn, C, next_dir()));
     SPM_GEMM_RUN_DIR(pl->fc[i]);
     SPM_GEMM_RUN_DIR(pl->proj[i]);
   }
 #undef SPM_GEMM_RUN_DIR
-  SPM_KERNEL(k_layernorm(st, h->x, (long long)VIT_L * C, F, C, v.ln_post_g, v.ln_post_b, nullptr, 0, nullptr, h->cls, C));
+  if (rb) SPM_KERNEL(k_layernorm_bf16in(st, h->xb, (long long)VIT_L * C, F, C, v.ln_post_g, v.ln_post_b, h->cls, C));
+  else SPM_KERNEL(k_layernorm(st, h->x, (long long)VIT_L * C, F, C, v.ln_post_g, v.ln_post_b, nullptr, 0, nullptr, h->cls, C));
   GemmOp fin = pl->fin;
   fin.ep.out = feats_out;
   SPM_GEMM_RUN(fin);

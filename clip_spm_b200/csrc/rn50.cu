@@ -31,13 +31,15 @@
 namespace spm {
 
 namespace {
-// Frames per launch, in two granularities (r02).  The FRONT (stem, layer1, layer2: 3364 .. 900 pixel rows per frame) runs
-// in sub-chunks small enough that consecutive kernels meet their operands in the 126 MB L2; the BACK (layer3, layer4,
-// attention pool: 256 / 81 rows per frame) runs over several front sub-chunks at once, so that its GEMMs have enough
-// 256-row pair tiles for all 74 CTA pairs (216 frames: layer3 216 pair rows = 2.9 rounds, layer4 69 x 2 = 1.9 rounds;
-// at 64 frames layer4's 512-channel convolutions were 164 tiles of 128 x 128 = 1.1 rounds).
+// Frames per launch (r02), set separately for the FRONT (stem, layer1, layer2: 3364 .. 900 pixel rows per frame) and the
+// BACK (layer3, layer4, attention pool: 256 / 81 rows per frame; it runs over one or several front sub-chunks at once).
+// Measured on the config-4 shape (tools/rn50_throughput.py, 8 episodes = 1280 frames per call): 64 / 64 frames 131
+// episodes/s -> 216 / 216 233 -> 320 / 320 240; small FRONT chunks that would keep layer1's tensors inside the 126 MB L2
+// lose more to the fixed cost of ~30 extra launches than they gain (27: 190, 72: 219, 108: 226 episodes/s), and the
+// BACK needs hundreds of frames for its GEMMs to fill 74 CTA pairs for more than one round (at 64 frames layer4's
+// 512-channel convolutions were 164 tiles of 128 x 128 = 1.1 rounds).
 // SPM_RN50_FRONT_CHUNK / SPM_RN50_BACK_CHUNK override (back is rounded to a multiple of front).
-constexpr int RN_FRONT_DEFAULT = 216, RN_BACK_DEFAULT = 216;
+constexpr int RN_FRONT_DEFAULT = 320, RN_BACK_DEFAULT = 320;
 constexpr int N_FRONT_BLOCKS = 7;   // layer1 (3) + layer2 (4)
 constexpr int EMB = 2048, HEADS = 32, HD = 64, OUT_DIM = 1024, NTOK = 50;
 constexpr long long FRAME_ELEMS = 3LL * 224 * 224;

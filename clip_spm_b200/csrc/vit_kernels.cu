@@ -160,6 +160,70 @@ layernorm_kernel(const float* __restrict__ in, long long in_stride, int rows, co
   }
 }
 
+// same LayerNorm on a bf16 input row (the bf16 residual stream of SPM_PRECISION_BF16_RESID): 8 elements per 16-byte load,
+// statistics in fp32 exactly as above
+template <int NV8>
+__global__ void __launch_bounds__(256)
+layernorm_bf16in_kernel(const __nv_bfloat16* __restrict__ in, long long in_stride, int rows, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16, long long out_stride,
+                        int reverse) {
+  constexpr int C = NV8 * 256;
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  if (reverse) row = rows - 1 - row;
+  const __nv_bfloat16* src = in + (long long)row * in_stride;
+  float v[NV8][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src + (i * 32 + lane) * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+      v[i][2 * e] = f.x; v[i][2 * e + 1] = f.y;
+      s += f.x + f.y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV8; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; q += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.f / C) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NV8; ++i) {
+    const int col = (i * 32 + lane) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 p = __floats2bfloat162_rn((v[i][2 * e] - mean) * rstd * g[2 * e] + b[2 * e],
+                                               (v[i][2 * e + 1] - mean) * rstd * g[2 * e + 1] + b[2 * e + 1]);
+      o[e] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    *reinterpret_cast<uint4*>(out_bf16 + (long long)row * out_stride + col) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+int k_layernorm_bf16in(cudaStream_t st, const __nv_bfloat16* in, long long in_stride, int rows, int C, const float* gamma,
+                       const float* beta, __nv_bfloat16* out_bf16, long long out_stride, int reverse) {
+  if (rows <= 0) return 0;
+  if (C != 768) return -1;
+  layernorm_bf16in_kernel<3><<<(rows + 7) / 8, 256, 0, st>>>(in, in_stride, rows, gamma, beta, out_bf16, out_stride, reverse);
+  SPM_LAUNCH_CHECK();
+  return 0;
+}
+
 int k_layernorm(cudaStream_t st, const float* in, long long in_stride, int rows, int C, const float* gamma,
                 const float* beta, const float* cls_row, int cls_period, float* out_f32, __nv_bfloat16* out_bf16,
                 long long out_stride, int reverse) {

@@ -152,6 +152,8 @@ class CNN(nn.Module):
     `text_features_train`, or call `build_text_features(clip_state_dict)` to compute them from the class names with
     the library's own text tower (the constructor work of model_clipspm.py:45-70).
     precision="bf16": bf16 tcgen05 encoder + tf32 head (what autocast(bfloat16) is to the reference);
+    precision="bf16_resid" (ViT-B/16): additionally a bf16 residual stream, i.e. exactly what autocast(bfloat16) makes of
+    the reference's tower (conv1, every Linear and every `x + ...` yield bf16); ~8 % faster, feature error ~1e-2;
     precision="fp32": every product in fp32 FFMA (the reference's default fp32 arithmetic; slow, for parity)."""
 
     HEAD = "clipspm"   # which metric head runs behind the shared entry points (SPM_HEAD_*)
@@ -160,8 +162,9 @@ class CNN(nn.Module):
                  precision="bf16"):
         super().__init__()
         self.args = cfg
-        if precision not in ("bf16", "fp32"):
-            raise RuntimeError("precision must be 'bf16' (tensor-core path) or 'fp32' (exact-arithmetic parity mode)")
+        if precision not in ("bf16", "fp32", "bf16_resid"):
+            raise RuntimeError("precision must be 'bf16' (tensor-core path, fp32 residual stream), 'bf16_resid' (bf16 "
+                               "residual stream: the reference's own autocast arithmetic) or 'fp32' (exact parity mode)")
         self.precision = precision
         self.backbone_name = _cfg_get(cfg, "MODEL.BACKBONE")
         if self.backbone_name not in ("ViT-B/16", "RN50"):
@@ -208,7 +211,7 @@ class CNN(nn.Module):
         from .text import TextTower
         test_class_names = test_class_names or _cfg_get(self.args, "TEST.CLASS_NAME")
         train_class_names = train_class_names or _cfg_get(self.args, "TRAIN.CLASS_NAME")
-        tower = TextTower(clip_state_dict, precision=self.precision, device=self._dev, vocab_path=vocab_path,
+        tower = TextTower(clip_state_dict, precision="fp32" if self.precision == "fp32" else "bf16", device=self._dev, vocab_path=vocab_path,
                           tokenizer=tokenizer)
         if tower.embed_dim != self.mid_dim:
             raise RuntimeError("text tower embed_dim %d does not match backbone %s" % (tower.embed_dim, self.backbone_name))
@@ -255,7 +258,7 @@ class CNN(nn.Module):
             mid_dim_text=float(self.params.get("mid_dim_text", 1.5)),
             mid_dim_vision=float(self.params.get("mid_dim_vision", 0.5)),
             negative_slope=float(self.params.get("negative_slope", 0.0)), alpha=float(self.params.get("alpha", 0.0)),
-            single_direct=int(self.single_direct), precision=0 if self.precision == "bf16" else 1,
+            single_direct=int(self.single_direct), precision={"bf16": 0, "fp32": 1, "bf16_resid": 2}[self.precision],
             max_episodes=self.max_episodes, max_support=0, max_query=0, max_way=0,
             head={"clipspm": 0, "clipfsar": 1, "sten": 2}[self.HEAD], cls_value=self.cls_value)
         h = ctypes.c_void_p()
@@ -420,6 +423,43 @@ class CNN(nn.Module):
                                             _p(target_labels), self.tasks_per_batch, _p(logits), _p(dists), _p(loss),
                                             _p(acc), _p(pred)))
         return dict(logits=logits, dists=dists, loss=loss, acc=acc, pred=pred)
+
+    def evaluate_frames_u8(self, context_frames, context_labels, target_frames, real_support_labels,
+                           real_target_labels, target_labels, n_episodes=1):
+        """evaluate on DECODED frames already on the device (uint8 [E*S*T, H, W, 3] / [E*Q*T, H, W, 3], e.g. from
+        ops.decode_jpegs): transform + encoder + head + loss / accuracy in one library call (spm_eval_u8)."""
+        h = self._handle()
+        self._text()
+        lib = _lib.load()
+        E = int(n_episodes)
+        for t in (context_frames, target_frames):
+            if not t.is_cuda or t.dtype != torch.uint8 or t.dim() != 4 or t.shape[3] != 3:
+                raise RuntimeError("evaluate_frames_u8 takes CUDA uint8 tensors [F, H, W, 3]")
+        su, qu = context_frames.contiguous(), target_frames.contiguous()
+        lab = self._f32(context_labels).view(E, -1)
+        rs, rt = self._f32(real_support_labels).view(E, -1), self._f32(real_target_labels).view(E, -1)
+        S, Q, W = lab.shape[1], rt.shape[1], self._way(lab[0])
+        if su.shape[0] != E * S * self.seq_len or qu.shape[0] != E * Q * self.seq_len or su.shape[1:] != qu.shape[1:]:
+            raise RuntimeError("frame tensors do not match [E*S*T, H, W, 3] / [E*Q*T, H, W, 3]")
+        tl = target_labels.to(self._dev, torch.int64).contiguous()
+        logits, dists = torch.empty(E, Q, W, device=self._dev), torch.empty(E, device=self._dev)
+        loss, acc = torch.empty(E, device=self._dev), torch.empty(E, device=self._dev)
+        pred = torch.empty(E, Q, device=self._dev, dtype=torch.int32)
+        _lib.check(lib.spm_eval_u8(h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), E, S, Q, W,
+                                   int(su.shape[1]), int(su.shape[2]), _p(su), _p(qu), _p(lab), _p(rs), _p(rt), _p(tl),
+                                   self.tasks_per_batch, _p(logits), _p(dists), _p(loss), _p(acc), _p(pred)))
+        return dict(logits=logits, dists=dists, loss=loss, acc=acc, pred=pred)
+
+    def evaluate_jpeg(self, context_files, context_labels, target_files, real_support_labels, real_target_labels,
+                      target_labels, n_episodes=1):
+        """The reference's whole per-episode input path from the FILES (video_reader.py:227-273: PIL decode ->
+        Resize(256) -> CenterCrop(224) -> ToTensor) + forward + loss / accuracy: `context_files` / `target_files` are
+        lists of JPEG file contents (bytes) in the sampler's stacking order (frames.sample_episode_plan)."""
+        from . import ops
+        su = ops.decode_jpegs(list(context_files), self._dev)
+        qu = ops.decode_jpegs(list(target_files), self._dev)
+        return self.evaluate_frames_u8(su, context_labels, qu, real_support_labels, real_target_labels, target_labels,
+                                       n_episodes)
 
     # --------------------------------------------------------------------------------------------- stage hooks
     def encode_frames_u8(self, frames):

@@ -127,6 +127,35 @@ def transform_frames(frames):
     return out
 
 
+def jpeg_info(data):
+    """Header of one JPEG file (bytes): (height, width, luma h sampling, luma v sampling)."""
+    lib = _lib.load()
+    buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
+    v = [ctypes.c_int() for _ in range(4)]
+    _lib.check(lib.spm_jpeg_info(ctypes.cast(buf, ctypes.c_void_p), len(data), *[ctypes.byref(x) for x in v]))
+    return tuple(x.value for x in v)
+
+
+def decode_jpegs(files, device="cuda"):
+    """What the reference's data loader does with PIL for every frame (video_reader.py:227-230 `Image.open(p).load()`),
+    on the GPU and bit-identical to it: `files` = list of JPEG file contents (bytes), all of one size and chroma
+    subsampling -> uint8 CUDA tensor [n, H, W, 3] (RGB), ready for transform_frames / CNN.encode_frames_u8."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("clip_spm_b200.ops.decode_jpegs needs a CUDA device; there is no CPU fallback")
+    n = len(files)
+    if n == 0:
+        return torch.empty(0, 0, 0, 3, dtype=torch.uint8, device=device)
+    H, W, _, _ = jpeg_info(files[0])
+    bufs = [(ctypes.c_ubyte * len(f)).from_buffer_copy(f) for f in files]
+    ptrs = (ctypes.c_void_p * n)(*[ctypes.cast(b, ctypes.c_void_p) for b in bufs])
+    sizes = (ctypes.c_int64 * n)(*[len(f) for f in files])
+    out = torch.empty(n, H, W, 3, dtype=torch.uint8, device=device)
+    with torch.cuda.device(out.device):
+        _lib.check(lib.spm_jpeg_decode(_stream(), n, ptrs, sizes, H, W, _ptr(out)))
+    return out
+
+
 class _SoftDTWFunction(torch.autograd.Function):
     """models/OTAM.py:134-203 `_SoftDTWCUDA`: D [B,N,M] -> R[:, N, M]; backward = E * grad (spm_softdtw_backward)."""
 

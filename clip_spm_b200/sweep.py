@@ -140,13 +140,16 @@ def run_sweep(net, n_episodes, way, shot, query_per_class, n_text_cls, rank=0, w
 
 
 def run_listing_sweep(net, split, load_frame, n_episodes, way, shot, n_queries, seed=0, episodes_per_call=8, rank=0,
-                      world_size=1):
+                      world_size=1, jpeg=False):
     """The reference's test loop (run/main_run.py:256-293 `Learner.test` over `VideoDataset` episodes) on this library,
     from DECODED frames: episode e is sampled with `frames.sample_episode_plan` (rng seeded `seed + e`, so any sharding
     sees the same episodes), its frames come from `load_frame(handle) -> uint8 [H, W, 3]` (the handles stored in
     `split.videos`), the Resize/CenterCrop/ToTensor chain, the encoder, the head, loss and accuracy run on the GPU
     (`CNN.evaluate_host_u8`), and while one batch of episodes computes the first chunk of the next is already being
-    copied (`next_images`).  All frames must share one size.  Returns the reduced statistics of `summarize`."""
+    copied (`next_images`).  All frames must share one size.  Returns the reduced statistics of `summarize`.
+    jpeg=True: `load_frame(handle)` returns the JPEG FILE CONTENTS (bytes) instead of decoded pixels -- the files are
+    decoded on the GPU (CNN.evaluate_jpeg -> spm_jpeg_decode, bit-identical to the PIL decode of video_reader.py:227-230),
+    so the whole input path of the reference's loader from the file on runs in the library."""
     import random
     from . import frames as F
     T = net.seq_len
@@ -168,6 +171,19 @@ def run_listing_sweep(net, split, load_frame, n_episodes, way, shot, n_queries, 
 
     batches = [mine[i:i + episodes_per_call] for i in range(0, len(mine), episodes_per_call)]
     accs, losses = [], []
+    if jpeg:
+        for ids in batches:
+            su, qu, lab, rs, rt, tl = [], [], [], [], [], []
+            for e in ids:
+                plan = F.sample_episode_plan(split, way, shot, n_queries, T, train=False, rng=random.Random(seed + e))
+                su += [load_frame(split.videos[v][f]) for v, fr in plan["support"] for f in fr]
+                qu += [load_frame(split.videos[v][f]) for v, fr in plan["target"] for f in fr]
+                lab.append(plan["support_labels"]); rs.append(plan["real_support_labels"])
+                rt.append(plan["real_target_labels"]); tl.append([int(x) for x in plan["target_labels"]])
+            out = net.evaluate_jpeg(su, torch.tensor(lab, dtype=torch.float32), qu, torch.tensor(rs, dtype=torch.float32),
+                                    torch.tensor(rt, dtype=torch.float32), torch.tensor(tl, dtype=torch.int64), len(ids))
+            accs.append(out["acc"].cpu()); losses.append(out["loss"].cpu())
+        batches = []
     cur = build(batches[0]) if batches else None
     for bi in range(len(batches)):
         nxt = build(batches[bi + 1]) if bi + 1 < len(batches) else None

@@ -21,6 +21,7 @@
  *   spm_otam_distance             models/model_clipspm.py:348-362 + models/myRes.py:756-765,821-855
  *   spm_set_text_features_train / spm_class_logits   models/model_clipfsar.py:127,329-331 (sibling head CLIP-FSAR)
  *   spm_softdtw_forward/backward  models/OTAM.py:34-203 (TA2N's numba.cuda soft-DTW kernels, _SoftDTWCUDA)
+ *   spm_jpeg_info / spm_jpeg_decode   video_reader.py:227-230 read_single_image (PIL JPEG decode of every frame)
  *   spm_gemm                      ATen linear / conv-as-GEMM calls (cuBLASLt) under all of the above
  */
 #ifndef CLIPSPM_B200_H
@@ -32,8 +33,9 @@
 extern "C" {
 #endif
 
-#define SPM_ABI_VERSION 3 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
-                           * 3: spm_head_stage (per-stage taps for the parity tests) */
+#define SPM_ABI_VERSION 4 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
+                           * 3: spm_head_stage (per-stage taps for the parity tests)
+                           * 4: spm_jpeg_info / spm_jpeg_decode, spm_eval_u8 */
 
 typedef struct spm_handle spm_handle;
 
@@ -41,7 +43,12 @@ enum { SPM_BACKBONE_VIT_B16 = 0, SPM_BACKBONE_RN50 = 1 };
 /* arithmetic of the dense contractions: bf16 tensor cores with fp32 accumulation (the reference's autocast(bfloat16)
  * mode), or the exact-arithmetic parity mode: fp32 operands, every product an fp32 FFMA on the CUDA cores
  * (csrc/sgemm_f32.cu; Blackwell has no fp32 tensor-core MMA), ViT-B/16 backbone only */
-enum { SPM_PRECISION_BF16 = 0, SPM_PRECISION_FP32 = 1 };
+enum { SPM_PRECISION_BF16 = 0, SPM_PRECISION_FP32 = 1,
+       /* bf16 tensor cores AND a bf16 residual stream (ViT-B/16 only): the arithmetic the reference's own
+        * autocast(bfloat16) forward has (run/main_run.py:274 around models/clip_fsar.py:672-689: conv1, every Linear and
+        * every `x + ...` produce bf16).  SPM_PRECISION_BF16 keeps the residual stream and LayerNorm inputs in fp32 instead
+        * (tighter parity, ~8 % slower); both stay inside the 2e-2 tolerance of the goldens. */
+       SPM_PRECISION_BF16_RESID = 2 };
 /* metric head behind the same entry points: CLIP-SPM (models/model_clipspm.py, the hot path) or its sibling
  * CLIP-FSAR (models/model_clipfsar.py CNN_OTAM_CLIPFSAR, evaluation branch :325-383), which reuses the same
  * transformer-block, class-mean and OTAM kernels */
@@ -220,6 +227,24 @@ int spm_eval_host_u8(spm_handle* h, int n_episodes, int S, int Q, int W, int img
                      const float* support_labels_host, const float* real_support_host, const float* real_target_host,
                      const int64_t* target_labels_host, float tasks_per_batch, float* logits_host, float* dists_host,
                      float* loss_host, float* acc_host, int32_t* pred_host);
+/* spm_eval on decoded frames already in DEVICE memory (e.g. the output of spm_jpeg_decode): support frames uint8
+ * [E, S*T, img_h, img_w, 3], target frames [E, Q*T, img_h, img_w, 3]; everything else as spm_eval */
+int spm_eval_u8(spm_handle* h, void* stream, int n_episodes, int S, int Q, int W, int img_h, int img_w,
+                const uint8_t* support_frames, const uint8_t* target_frames, const float* support_labels,
+                const float* real_support, const float* real_target, const int64_t* target_labels, float tasks_per_batch,
+                float* logits_out, float* dists_out, float* loss_out, float* acc_out, int32_t* pred_out);
+
+/* ---- JPEG decode (video_reader.py:227-230 read_single_image: PIL Image.open(path).load(), one file per frame) ----
+ * Baseline / extended-sequential Huffman JPEG, 8-bit YCbCr, 4:4:4 / 4:2:2 / 4:2:0, one interleaved scan, restart
+ * intervals allowed (what ffmpeg-extracted frame dumps contain); progressive / arithmetic / CMYK files are rejected
+ * with an error.  The decoded RGB bytes are identical to PIL's (libjpeg-turbo: ISLOW IDCT, fancy upsampling).
+ * spm_jpeg_info: header of one file in HOST memory -> size and luma sampling factors (any output pointer may be null).
+ * spm_jpeg_decode: n_images files in HOST memory (all H x W with the same chroma subsampling) -> frames_out, DEVICE
+ * uint8 [n_images, H, W, 3].  Container parsing and byte un-stuffing run on host threads, entropy decoding, IDCT,
+ * upsampling and colour conversion on the GPU; the call returns after the stream has consumed the host buffers. */
+int spm_jpeg_info(const uint8_t* jpeg_host, long long n_bytes, int* height, int* width, int* h_samp, int* v_samp);
+int spm_jpeg_decode(void* stream, int n_images, const uint8_t* const* jpeg_host, const int64_t* jpeg_bytes, int H, int W,
+                    uint8_t* frames_out);
 /* the geometry that transform uses for an H x W frame (host arithmetic only; any output pointer may be null) */
 int spm_frame_geometry(int H, int W, int* resized_h, int* resized_w, int* crop_y, int* crop_x);
 

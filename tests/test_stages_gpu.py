@@ -544,3 +544,11 @@ def test_eval_host_regrows_every_staging_ring():
     out = net.forward_episodes(cat("context_images"), cat("context_labels"), cat("target_images"),
                                cat("real_support_labels"), cat("real_target_labels"), 4, cat("target_labels"))
     assert torch.isfinite(out["loss"]).all()
+
+
+@pytest.mark.parametrize("name", ["vit_2w1s_t2_p0", "vit_5w1s_t8_p1", "vit_5w5s_t8_p1"])
+def test_bf16_residual_stream_mode_matches_reference_golden(name):
+    """precision="bf16_resid": bf16 residual stream, i.e. the arithmetic of the reference's own autocast(bfloat16)
+    forward (run/main_run.py:274); same 2e-2 tolerance and margin-filtered argmax as the default bf16 mode"""
+    ci, g = H.case_inputs(name), H.golden(name)
+    _check_forward_against_golden(H.build_cuda_model(ci, precision="bf16_resid"), ci, g, TOL_BF16, 5e-2, False)
