@@ -31,6 +31,11 @@ class SpmConfig(ctypes.Structure):
         ("max_way", c_int),
         ("head", c_int),
         ("cls_value", c_float),
+        ("motion_residual_ratio", c_float),
+        ("lambdas", c_float * 4),
+        ("motion_coeff", c_float),
+        ("normal_coeff", c_float),
+        ("use_classification", c_int),
     ]
 
 
@@ -50,6 +55,7 @@ SIGNATURES = {
     "spm_set_text_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "spm_set_text_features_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "spm_class_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "spm_cpm2c_outputs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "spm_encode_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "spm_head": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7),
     "spm_head_stage": (c_int, [c_void_p, c_void_p, ctypes.c_char_p, c_void_p, c_ll, ctypes.POINTER(c_ll)]),

@@ -41,6 +41,20 @@ int k_fsar_class_ce_add(cudaStream_t st, const float* cls, const float* real_s, 
 int k_sten_head(cudaStream_t st, const float* X, const float* text, int n_cls, const float* labels,
                 const float* real_s, int E, int S, int Q, int W, int T, int D, float* frame_mean, float* proto,
                 float* negsim, int* err_flag);
+// ---- sibling head CPM2C (cpm2c_kernels.cu; models/model_cpm2c.py:207-312); Z = context2 outputs [2][V][L][D]
+int k_temporal_im2col_dil(cudaStream_t st, const float* x, int V, int T, int D, int dil, float* out);
+int k_cpm2c_motion_diff(cudaStream_t st, const float* conv, const float* x, int V, int T, int D, float* out);
+int k_cpm2c_tokens(cudaStream_t st, const float* text, int n_cls, const float* real_s, const float* real_t,
+                   const float* cls_token, int E, int S, int Q, int D, float* tok, int* err_flag);
+int k_cpm2c_class_mean(cudaStream_t st, const float* z, const float* labels, int E, int S, int Q, int W, int L, int D,
+                       float* su_pro, int* err_flag);
+int k_cpm2c_consist(cudaStream_t st, const float* z, int E, int S, int Q, int L, int D, float coeff, float beta, float* consist);
+int k_cpm2c_global(cudaStream_t st, const float* z, const float* labels, int E, int S, int Q, int W, int L, int D,
+                   float coeff, float beta, float* g);
+int k_cpm2c_finalize(cudaStream_t st, const float* loc, const float* glob, const float* cls, int n_cls, const float* real_s,
+                     const float* real_t, int E, int S, int Q, int W, const long long* target, float l0, float l1, float l2,
+                     float tasks_per_batch, float* out_local, float* out_global, float* out_total, float* loss,
+                     float* accuracy, int* pred, const int* err_flag);
 // soft-DTW of TA2N (softdtw.cu; models/OTAM.py:34-203): D [B,N,M] -> R [B,N+2,M+2], out [B]; backward -> E [B,N,M]
 int k_softdtw_forward(cudaStream_t st, const float* D, int B, int N, int M, float gamma, float bandwidth, float* R,
                       float* out);

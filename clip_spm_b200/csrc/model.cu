@@ -137,8 +137,8 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   SPM_CHECK(cfg->seq_len >= 2 && cfg->seq_len <= 30, "spm_create: seq_len must be in [2, 30]");
   SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->precision == SPM_PRECISION_FP32 ||
             cfg->precision == SPM_PRECISION_BF16_RESID, "spm_create: unknown precision");
-  SPM_CHECK(cfg->head == SPM_HEAD_CLIPSPM || cfg->head == SPM_HEAD_CLIPFSAR || cfg->head == SPM_HEAD_STEN,
-            "spm_create: unknown head");
+  SPM_CHECK(cfg->head == SPM_HEAD_CLIPSPM || cfg->head == SPM_HEAD_CLIPFSAR || cfg->head == SPM_HEAD_STEN ||
+            cfg->head == SPM_HEAD_CPM2C, "spm_create: unknown head");
   SPM_CHECK(cfg->head != SPM_HEAD_STEN || cfg->seq_len == 8,
             "spm_create: the STEN head reshapes to 8 frames per video (models/model_sten.py:65-66)");
   SPM_CHECK(cfg->precision == SPM_PRECISION_BF16 || cfg->backbone == SPM_BACKBONE_VIT_B16,
@@ -216,6 +216,7 @@ int spm_load_weights(spm_handle* h, void* stream, int n, const char* const* name
     SPM_TRY(rn50_create(&h->rn50, st, h->sms, getter));
   }
   if (h->cfg.head == SPM_HEAD_CLIPFSAR) SPM_TRY(load_head_fsar(h, st, wt));
+  else if (h->cfg.head == SPM_HEAD_CPM2C) SPM_TRY(load_head_cpm2c(h, st, wt));
   else if (h->cfg.head == SPM_HEAD_CLIPSPM) SPM_TRY(load_head(h, st, wt));
   // SPM_HEAD_STEN: the shipped model has no parameters besides the backbone
   SPM_CUDA(cudaStreamSynchronize(st));
@@ -246,10 +247,23 @@ int spm_set_text_features_train(spm_handle* h, void* stream, const float* table,
 
 int spm_class_logits(spm_handle* h, void* stream, int n_rows, int n_cls, float* out) {
   SPM_CHECK(h != nullptr && out != nullptr, "spm_class_logits: null argument");
-  SPM_CHECK(h->cfg.head == SPM_HEAD_CLIPFSAR, "spm_class_logits: only the CLIP-FSAR head produces class logits");
-  SPM_CHECK(h->cls_rows > 0, "spm_class_logits: no class logits available (no head call yet, or text_features_train not set)");
-  SPM_CHECK(n_rows == h->cls_rows && n_cls == h->n_cls_train, "spm_class_logits: shape does not match the last head call");
+  SPM_CHECK(h->cfg.head == SPM_HEAD_CLIPFSAR || h->cfg.head == SPM_HEAD_CPM2C,
+            "spm_class_logits: only the CLIP-FSAR and CPM2C heads produce class logits");
+  SPM_CHECK(h->cls_rows > 0, "spm_class_logits: no class logits available (no head call yet, or the text table / USE_CLASSIFICATION is not set)");
+  const int want_cls = h->cfg.head == SPM_HEAD_CPM2C ? h->n_cls : h->n_cls_train;   // CPM2C evaluates on the test prompts
+  SPM_CHECK(n_rows == h->cls_rows && n_cls == want_cls, "spm_class_logits: shape does not match the last head call");
   SPM_CUDA(cudaMemcpyAsync(out, h->CLS, (size_t)n_rows * n_cls * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int spm_cpm2c_outputs(spm_handle* h, void* stream, int n_episodes, int Q, int W, float* logits_local, float* logits_global) {
+  SPM_CHECK(h != nullptr && logits_local != nullptr && logits_global != nullptr, "spm_cpm2c_outputs: null argument");
+  SPM_CHECK(h->cfg.head == SPM_HEAD_CPM2C, "spm_cpm2c_outputs: the handle does not run the CPM2C head");
+  SPM_CHECK(h->cp_last_E == n_episodes && h->cp_last_Q == Q && h->cp_last_W == W && n_episodes > 0,
+            "spm_cpm2c_outputs: shape does not match the last head call");
+  const size_t bytes = (size_t)n_episodes * Q * W * 4;
+  SPM_CUDA(cudaMemcpyAsync(logits_local, h->CP_OUT_L, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  SPM_CUDA(cudaMemcpyAsync(logits_global, h->CP_OUT_G, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 

@@ -35,6 +35,53 @@ int load_head_fsar(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
   return load_ctx(h, st, wt, "context2.layers.0.", h->D, &h->fsar_ctx);
 }
 
+// CLIP_CPMMC_FSAR's parameters the forward reads (models/model_cpm2c.py:73-141): scale, context2 (inner width D), the
+// gates, the two class tokens, the multi-scale motion convolutions (k = 1, 3, 3 dilated) and their 1x1 fusion, whose
+// `* motion_residual_ratio` (:175) is folded into its weights and bias here.
+__global__ void scale_copy_kernel(const float* __restrict__ in, float s, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * s;
+}
+int load_head_cpm2c(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
+  HeadW& w = h->head;
+  spm_handle::Cpm2cW& c = h->cpm;
+  const long long D = h->D, HT = h->HT, HV = h->HV;
+  SPM_TRY(copy_f32(h, st, wt, "scale", 1, &h->fsar_scale));
+  SPM_TRY(load_ctx(h, st, wt, "context2.layers.0.", D, &h->fsar_ctx));
+  SPM_TRY(copy_f32(h, st, wt, "gate_text.0.weight", HT * D, &w.gt0_w));
+  SPM_TRY(copy_f32(h, st, wt, "gate_text.0.bias", HT, &w.gt0_b));
+  SPM_TRY(copy_f32(h, st, wt, "gate_text.2.weight", D * HT, &w.gt2_w));
+  SPM_TRY(copy_f32(h, st, wt, "gate_text.2.bias", D, &w.gt2_b));
+  SPM_TRY(copy_f32(h, st, wt, "gate_vision.0.weight", HV * D, &w.gv0_w));
+  SPM_TRY(copy_f32(h, st, wt, "gate_vision.0.bias", HV, &w.gv0_b));
+  SPM_TRY(copy_f32(h, st, wt, "gate_vision.2.weight", D * HV, &w.gv2_w));
+  SPM_TRY(copy_f32(h, st, wt, "gate_vision.2.bias", D, &w.gv2_b));
+  SPM_TRY(copy_f32(h, st, wt, "class_token", D, &c.cls_tok));
+  SPM_TRY(copy_f32(h, st, wt, "class_token_motion", D, &c.cls_tok_motion));
+  SPM_TRY(copy_f32(h, st, wt, "motion_conv1_1.weight", D * D, &c.m1_w));   // [D, D, 1] is already the GEMM's B operand
+  SPM_TRY(copy_f32(h, st, wt, "motion_conv1_1.bias", D, &c.m1_b));
+  const float* src;
+  SPM_TRY(wt.get("motion_conv1_3.weight", D * D * 3, &src));
+  SPM_TRY(dalloc_t(h, &c.m3_w, D * D * 3));
+  SPM_KERNEL(k_repack_conv1d(st, src, c.m3_w, (int)D, (int)D));
+  SPM_TRY(copy_f32(h, st, wt, "motion_conv1_3.bias", D, &c.m3_b));
+  SPM_TRY(wt.get("motion_conv1_5.weight", D * D * 3, &src));
+  SPM_TRY(dalloc_t(h, &c.m5_w, D * D * 3));
+  SPM_KERNEL(k_repack_conv1d(st, src, c.m5_w, (int)D, (int)D));
+  SPM_TRY(copy_f32(h, st, wt, "motion_conv1_5.bias", D, &c.m5_b));
+  const float ratio = h->cfg.motion_residual_ratio;
+  SPM_TRY(wt.get("scale_conv.weight", D * 3 * D, &src));
+  SPM_TRY(dalloc_t(h, &c.sc_w, D * 3 * D));
+  scale_copy_kernel<<<(unsigned)((D * 3 * D + 255) / 256), 256, 0, st>>>(src, ratio, c.sc_w, D * 3 * D);
+  count_launch();
+  SPM_TRY(wt.get("scale_conv.bias", D, &src));
+  SPM_TRY(dalloc_t(h, &c.sc_b, D));
+  scale_copy_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(src, ratio, c.sc_b, D);
+  count_launch();
+  SPM_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int load_head(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
   HeadW& w = h->head;
   const long long D = h->D, HT = h->HT, HV = h->HV;
@@ -74,6 +121,7 @@ int ensure_head_workspace(spm_handle* h, int E, int S, int Q, int W) {
   // grow-only: plans that point into the old buffers are dropped
   h->head_plans.clear();
   h->fsar_plans.clear();
+  h->cpm2c_plans.clear();
   const long long cE = std::max<long long>(E, h->head_cap_E), cS = std::max<long long>(S, h->head_cap_S),
                   cQ = std::max<long long>(Q, h->head_cap_Q), cW = std::max<long long>(W, h->head_cap_W);
   const long long T = h->cfg.seq_len, D = h->D, N = cS + cQ, V = cE * N;
@@ -260,6 +308,132 @@ int fsar_head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, co
   return 0;
 }
 
+// CPM2C head (models/model_cpm2c.py:207-312, evaluation) on frame features in h->X [E, N, T, D]:
+//   motion = multi-scale temporal convolutions + frame differences [V, T-1, D]
+//   per branch (motion with class_token_motion, normal with class_token): gates, two context2 batches (sequences on the
+//   real prompt / on the class token), class prototypes, consistency distance, global (token) and local (OTAM) distances
+//   logits_out = lambdas1 * (-local) + lambdas2 * (-global); dists_out = target_consist_distance
+int cpm2c_head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const float* labels, const float* real_s,
+                   const float* real_t, const long long* target_labels, float tasks_per_batch, float* logits, float* dists,
+                   float* loss, float* acc, int* pred) {
+  SPM_CHECK(h->text_set, "head: text features not set (spm_set_text_features)");
+  SPM_TRY(ensure_head_workspace(h, E, S, Q, W));
+  const int T = h->cfg.seq_len, D = h->D, N = S + Q, V = E * N, dh = D / HEAD_HEADS;
+  SPM_CHECK(T >= 3, "CPM2C head: seq_len must be at least 3 (its motion branch aligns T-1 frame differences)");
+  const int kind = h->fp32 ? GEMM_F32_SIMT : GEMM_TF32;
+  // ---- workspace of this head
+  if (V > h->cp_cap_V) {
+    SPM_TRY(drealloc_t(h, &h->CP_FCAT, (long long)V * T * 3 * D));
+    SPM_TRY(drealloc_t(h, &h->CP_CONV, (long long)V * T * D));
+    SPM_TRY(drealloc_t(h, &h->CP_MOT, (long long)V * T * D));
+    SPM_TRY(drealloc_t(h, &h->CP_TOK, 2LL * V * D));
+    SPM_TRY(drealloc_t(h, &h->CP_GT, 2LL * V * D));
+    h->cp_cap_V = V;
+    h->cpm2c_plans.clear();
+  }
+  if ((long long)E * Q * W > h->cp_cap_EQW) {
+    for (float** p : {&h->CP_LOC, &h->CP_GLOB, &h->CP_OUT_L, &h->CP_OUT_G}) SPM_TRY(drealloc_t(h, p, (long long)E * Q * W));
+    h->cp_cap_EQW = (long long)E * Q * W;
+  }
+  if ((long long)E * W > h->cp_cap_EW) {
+    SPM_TRY(drealloc_t(h, &h->CP_PRO, (long long)E * W * (T + 1) * D));
+    h->cp_cap_EW = (long long)E * W;
+  }
+  const long long need_cls = (long long)V * h->n_cls;
+  if (need_cls > h->cls_cap) { SPM_TRY(drealloc_t(h, &h->CLS, need_cls)); h->cls_cap = need_cls; }
+  // ---- plans
+  Cpm2cPlan* pl = nullptr;
+  for (auto& p : h->cpm2c_plans)
+    if (p->E == E && p->S == S && p->Q == Q && p->X == h->X) pl = p.get();
+  if (pl == nullptr) {
+    std::unique_ptr<Cpm2cPlan> np(new Cpm2cPlan());
+    np->E = E; np->S = S; np->Q = Q; np->X = h->X;
+    const spm_handle::Cpm2cW& c = h->cpm;
+    const HeadW& w = h->head;
+    GemmEpilogue e;
+    e.ldo = 3 * D;
+    e.bias = c.m1_b; e.out = h->CP_FCAT;
+    SPM_TRY(plan_gemm(&np->f1, kind, h->X, D, c.m1_w, D, V * T, D, D, e, h->sms));
+    e.bias = c.m3_b; e.out = h->CP_FCAT + D;
+    SPM_TRY(plan_gemm(&np->f3, kind, h->XC, 3 * D, c.m3_w, 3 * D, V * T, D, 3 * D, e, h->sms));
+    e.bias = c.m5_b; e.out = h->CP_FCAT + 2 * D;
+    SPM_TRY(plan_gemm(&np->f5, kind, h->XC, 3 * D, c.m5_w, 3 * D, V * T, D, 3 * D, e, h->sms));
+    GemmEpilogue es;   // fused * ratio + residual (ratio folded into the weights)
+    es.bias = c.sc_b; es.residual = h->X; es.ldr = D; es.out = h->CP_CONV; es.ldo = D;
+    SPM_TRY(plan_gemm(&np->sc, kind, h->CP_FCAT, 3 * D, c.sc_w, 3 * D, V * T, D, 3 * D, es, h->sms));
+    GemmEpilogue g0;
+    g0.bias = w.gt0_b; g0.act = ACT_LEAKY; g0.slope = h->cfg.negative_slope; g0.out = h->GTH; g0.ldo = h->HT;
+    SPM_TRY(plan_gemm(&np->gt0, kind, h->CP_TOK, D, w.gt0_w, D, 2 * V, h->HT, D, g0, h->sms));
+    GemmEpilogue g2;
+    g2.bias = w.gt2_b; g2.act = ACT_SIGMOID; g2.out = h->CP_GT; g2.ldo = D;
+    SPM_TRY(plan_gemm(&np->gt2, kind, h->GTH, h->HT, w.gt2_w, h->HT, 2 * V, D, h->HT, g2, h->sms));
+    for (int b = 0; b < 2; ++b) {   // branch 0: motion (T-1 frames of CP_MOT), branch 1: normal (T frames of X)
+      const int Tp = b == 0 ? T - 1 : T;
+      const float* F = b == 0 ? h->CP_MOT : h->X;
+      GemmEpilogue v0;
+      v0.bias = w.gv0_b; v0.act = ACT_LEAKY; v0.slope = h->cfg.negative_slope; v0.out = h->GVH; v0.ldo = h->HV;
+      SPM_TRY(plan_gemm(&np->gv0[b], kind, F, D, w.gv0_w, D, V * Tp, h->HV, D, v0, h->sms));
+      GemmEpilogue v2;
+      v2.bias = w.gv2_b; v2.act = ACT_SIGMOID; v2.out = h->GV; v2.ldo = D;
+      SPM_TRY(plan_gemm(&np->gv2[b], kind, h->GVH, h->HV, w.gv2_w, h->HV, V * Tp, D, h->HV, v2, h->sms));
+      SPM_TRY(plan_ctx(h, &np->c2[b], h->fsar_ctx, 2 * V * (Tp + 1), h->SEQ, h->Z, D));
+    }
+    pl = np.get();
+    h->cpm2c_plans.push_back(std::move(np));
+  }
+  const spm_handle::Cpm2cW& c = h->cpm;
+  const CtxW& cw = h->fsar_ctx;
+  const float nc = h->cfg.normal_coeff, mc = h->cfg.motion_coeff;
+  // ---- multi-scale motion features (:165-199)
+  SPM_GEMM_RUN(pl->f1);
+  SPM_KERNEL(k_temporal_im2col_dil(st, h->X, V, T, D, 1, h->XC));
+  SPM_GEMM_RUN(pl->f3);
+  SPM_KERNEL(k_temporal_im2col_dil(st, h->X, V, T, D, 2, h->XC));
+  SPM_GEMM_RUN(pl->f5);
+  SPM_GEMM_RUN(pl->sc);
+  SPM_KERNEL(k_cpm2c_motion_diff(st, h->CP_CONV, h->X, V, T, D, h->CP_MOT));
+  // ---- class_text_logits on the raw frames (:222, :420-432)
+  if (h->cfg.use_classification) {
+    SPM_KERNEL(k_fsar_class_logits(st, h->X, h->text, h->n_cls, h->fsar_scale, V, T, D, h->CLS));
+    h->cls_rows = V;
+  } else {
+    h->cls_rows = 0;
+  }
+  // ---- the two branches (:238-241): motion first, then normal
+  for (int b = 0; b < 2; ++b) {
+    const int Tp = b == 0 ? T - 1 : T, L = Tp + 1;
+    const float* F = b == 0 ? h->CP_MOT : h->X;
+    const float coeff = b == 0 ? mc : nc, beta = b == 0 ? 0.f : 1.f;
+    const long long LD = (long long)L * D;
+    SPM_KERNEL(k_cpm2c_tokens(st, h->text, h->n_cls, real_s, real_t, b == 0 ? c.cls_tok_motion : c.cls_tok, E, S, Q, D,
+                              h->CP_TOK, h->err_flag));
+    SPM_GEMM_RUN(pl->gt0);
+    SPM_GEMM_RUN(pl->gt2);
+    SPM_GEMM_RUN(pl->gv0[b]);
+    SPM_GEMM_RUN(pl->gv2[b]);
+    SPM_KERNEL(k_seq_build(st, h->CP_TOK, h->CP_GT, F, h->GV, 2, V, Tp, D, h->cfg.alpha, h->SEQ));
+    const int R = 2 * V * L;
+    SPM_KERNEL(k_layernorm(st, h->SEQ, D, R, D, cw.ln_g, cw.ln_b, nullptr, 0, h->HN, nullptr, D));
+    SPM_GEMM_RUN(pl->c2[b].qkv);
+    SPM_KERNEL(k_seq_attention(st, h->QKVH, h->AO, 2 * V, L, 1, 0, L, 0, 0, HEAD_HEADS, dh));
+    SPM_GEMM_RUN(pl->c2[b].outp);
+    SPM_GEMM_RUN(pl->c2[b].ff0);
+    SPM_GEMM_RUN(pl->c2[b].ff3);
+    SPM_KERNEL(k_cpm2c_class_mean(st, h->Z, labels, E, S, Q, W, L, D, h->CP_PRO, h->err_flag));
+    SPM_KERNEL(k_cpm2c_consist(st, h->Z, E, S, Q, L, D, coeff, beta, dists));
+    SPM_KERNEL(k_cpm2c_global(st, h->Z, labels, E, S, Q, W, L, D, coeff, beta, h->CP_GLOB));
+    // local: OTAM over rows 1.. of the prototypes and of the fake-token query sequences (:292-296)
+    SPM_KERNEL(k_otam(st, h->CP_PRO + D, (long long)W * LD, LD, D, h->Z + ((long long)V + S) * LD + D, (long long)N * LD, LD, D,
+                      E, W, Q, Tp, D, h->cfg.single_direct, coeff, beta, h->CP_LOC));
+  }
+  SPM_KERNEL(k_cpm2c_finalize(st, h->CP_LOC, h->CP_GLOB, h->cfg.use_classification ? h->CLS : nullptr, h->n_cls, real_s, real_t,
+                              E, S, Q, W, target_labels, h->cfg.lambdas[0], h->cfg.lambdas[1], h->cfg.lambdas[2],
+                              tasks_per_batch, h->CP_OUT_L, h->CP_OUT_G, logits, loss, acc, pred, h->err_flag));
+  h->cp_last_E = E; h->cp_last_Q = Q; h->cp_last_W = W;
+  h->last_E = E; h->last_S = S; h->last_Q = Q; h->last_W = W;
+  return 0;
+}
+
 // Frame features already in h->X as [E, N, T, D] (supports first).  Produces logits [E,Q,W], dists [E] and, when
 // target_labels is given, loss / accuracy / predictions.
 int head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const float* labels, const float* real_s,
@@ -267,6 +441,9 @@ int head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const f
              float* loss, float* acc, int* pred) {
   if (h->cfg.head == SPM_HEAD_STEN)
     return sten_head_run(h, st, E, S, Q, W, labels, real_s, target_labels, tasks_per_batch, logits, dists, loss, acc, pred);
+  if (h->cfg.head == SPM_HEAD_CPM2C)
+    return cpm2c_head_run(h, st, E, S, Q, W, labels, real_s, real_t, target_labels, tasks_per_batch, logits, dists, loss,
+                          acc, pred);
   if (h->cfg.head == SPM_HEAD_CLIPFSAR)
     return fsar_head_run(h, st, E, S, Q, W, labels, real_s, real_t, target_labels, tasks_per_batch, logits, dists, loss,
                          acc, pred);
@@ -323,9 +500,30 @@ int head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const f
 // Stage tensors of the most recent CLIP-SPM head pass, gathered out of the workspace in the reference's layouts
 // (the tensors SURVEY.md 8(c) lists; tests compare each with the golden written from the executed reference).
 int head_stage(spm_handle* h, cudaStream_t st, const char* name, float* out, long long capacity, long long* numel) {
-  SPM_CHECK(h->cfg.head == SPM_HEAD_CLIPSPM, "spm_head_stage: only the CLIP-SPM head keeps named stage tensors");
+  SPM_CHECK(h->cfg.head == SPM_HEAD_CLIPSPM || h->cfg.head == SPM_HEAD_CPM2C,
+            "spm_head_stage: only the CLIP-SPM and CPM2C heads keep named stage tensors");
   SPM_CHECK(h->last_E > 0, "spm_head_stage: no head pass has run on this handle yet");
   const int E = h->last_E, S = h->last_S, Q = h->last_Q, W = h->last_W;
+  if (h->cfg.head == SPM_HEAD_CPM2C) {
+    // model_cpm2c.py:165-199 (motion features) and :315-360 on the normal branch, whose buffers are the ones left over
+    const int T = h->cfg.seq_len, D = h->D, N = S + Q, V = E * N, L = T + 1;
+    const long long MD = (long long)(T - 1) * D, LD = (long long)L * D;
+    struct View { const float* p; int n0, n1, n2; long long s0, s1, s2; };
+    const std::string n(name ? name : "");
+    View v{};
+    if (n == "su_motion") v = {h->CP_MOT, E, S, T - 1, N * MD, MD, D};
+    else if (n == "qu_motion") v = {h->CP_MOT + S * MD, E, Q, T - 1, N * MD, MD, D};
+    else if (n == "su_real") v = {h->Z, E, S, L, N * LD, LD, D};
+    else if (n == "qu_fake") v = {h->Z + ((long long)V + S) * LD, E, Q, L, N * LD, LD, D};
+    else if (n == "su_pro") v = {h->CP_PRO, E, W, L, W * LD, LD, D};
+    else { set_error("spm_head_stage: unknown CPM2C stage '" + n + "'"); return 1; }
+    const long long total = (long long)v.n0 * v.n1 * v.n2 * D;
+    if (numel != nullptr) *numel = total;
+    if (out == nullptr) return 0;
+    SPM_CHECK(capacity >= total, "spm_head_stage: output buffer too small");
+    SPM_KERNEL(k_gather4(st, v.p, v.n0, v.n1, v.n2, D, v.s0, v.s1, v.s2, out));
+    return 0;
+  }
   const int T = h->cfg.seq_len, D = h->D, N = S + Q, V = E * N, L1 = W + S + 1 + Q;
   const long long TD = (long long)T * D, T1D = (long long)(T + 1) * D, L1D = (long long)L1 * D;
   const float* Zb = h->Z + (long long)V * T1D;            // outputs of the `sem` se_te batch

@@ -92,6 +92,13 @@ struct VitPlan {
 struct CtxPlan {
   GemmOp qkv, outp, ff0, ff3;
 };
+struct Cpm2cPlan {   // sibling head CPM2C: motion fusion GEMMs, gates and one context2 pass per branch (motion, normal)
+  int E, S, Q;
+  const float* X;
+  GemmOp f1, f3, f5, sc, gt0, gt2;
+  GemmOp gv0[2], gv2[2];
+  CtxPlan c2[2];
+};
 struct FsarPlan {   // sibling head CLIP-FSAR: one context2 pass over E*S*(T+1) + E*Q*T rows
   int E, S, Q;
   CtxPlan c2;
@@ -164,6 +171,17 @@ struct spm_handle {
   float* CLS = nullptr;          // [E, S+Q, n_cls_train] class_text_logits of the last head call
   long long cls_cap = 0, cls_rows = 0;
   std::vector<std::unique_ptr<spm::FsarPlan>> fsar_plans;
+  // sibling head CPM2C (cfg.head == SPM_HEAD_CPM2C; models/model_cpm2c.py): context2 / scale share fsar_ctx / fsar_scale,
+  // the gates share head.g*; motion fusion weights, class tokens and its own workspace below
+  struct Cpm2cW {
+    float *m1_w = nullptr, *m1_b = nullptr, *m3_w = nullptr, *m3_b = nullptr, *m5_w = nullptr, *m5_b = nullptr,
+          *sc_w = nullptr, *sc_b = nullptr, *cls_tok = nullptr, *cls_tok_motion = nullptr;
+  } cpm;
+  float *CP_FCAT = nullptr, *CP_CONV = nullptr, *CP_MOT = nullptr, *CP_TOK = nullptr, *CP_GT = nullptr, *CP_PRO = nullptr,
+        *CP_LOC = nullptr, *CP_GLOB = nullptr, *CP_OUT_L = nullptr, *CP_OUT_G = nullptr;
+  long long cp_cap_V = 0, cp_cap_EQW = 0, cp_cap_EW = 0;
+  int cp_last_E = 0, cp_last_Q = 0, cp_last_W = 0;
+  std::vector<std::unique_ptr<spm::Cpm2cPlan>> cpm2c_plans;
   // `X` is the feature block the head currently reads: its own buffer (Xhead), or a group of episodes inside Xall
   // when the forward pipelines episode groups (encoder of group g+1 overlaps the head of group g on head_stream)
   float *Xhead = nullptr, *Xall = nullptr;
@@ -291,6 +309,7 @@ int encode_segments(spm_handle* h, cudaStream_t st, const Segment* segs, int nse
 // ---- model_head.cu
 int load_head(spm_handle* h, cudaStream_t st, const WeightTable& wt);
 int load_head_fsar(spm_handle* h, cudaStream_t st, const WeightTable& wt);
+int load_head_cpm2c(spm_handle* h, cudaStream_t st, const WeightTable& wt);
 int ensure_head_workspace(spm_handle* h, int E, int S, int Q, int W);
 // Frame features already in h->X as [E, N, T, D] (supports first).  Produces logits [E,Q,W], dists [E] and, when
 // target_labels is given, loss / accuracy / predictions (the head is chosen by cfg.head).

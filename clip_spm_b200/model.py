@@ -38,11 +38,29 @@ def _param_shapes(backbone, D, params, head="clipspm"):
     tower of models/clip_fsar.py:549-689), written out here from the module definitions."""
     if head == "clipfsar":
         s = _fsar_head_shapes(D)
+    elif head == "cpm2c":
+        s = _cpm2c_head_shapes(D, params)
     elif head == "sten":
         s = {}   # models/model_sten.py: every head module is commented out, only the backbone has parameters
     else:
         s = _spm_head_shapes(D, params)
     s.update(_backbone_shapes(backbone))
+    return s
+
+
+def _cpm2c_head_shapes(D, params):
+    """Parameters models/model_cpm2c.py::CLIP_CPMMC_FSAR.forward reads (:75-81, :88-89, :103-114, :135-138): scale, context2
+    (inner width D), the two class tokens, the gates, and the multi-scale motion convolutions with their 1x1 fusion."""
+    ht, hv = int(D * params["mid_dim_text"]), int(D * params["mid_dim_vision"])
+    s = _fsar_head_shapes(D)
+    s.update({"class_token": (1, 1, D), "class_token_motion": (1, 1, D),
+              "gate_text.0.weight": (ht, D), "gate_text.0.bias": (ht,), "gate_text.2.weight": (D, ht),
+              "gate_text.2.bias": (D,), "gate_vision.0.weight": (hv, D), "gate_vision.0.bias": (hv,),
+              "gate_vision.2.weight": (D, hv), "gate_vision.2.bias": (D,),
+              "motion_conv1_1.weight": (D, D, 1), "motion_conv1_1.bias": (D,),
+              "motion_conv1_3.weight": (D, D, 3), "motion_conv1_3.bias": (D,),
+              "motion_conv1_5.weight": (D, D, 3), "motion_conv1_5.bias": (D,),
+              "scale_conv.weight": (D, 3 * D, 1), "scale_conv.bias": (D,)})
     return s
 
 
@@ -171,7 +189,7 @@ class CNN(nn.Module):
             raise RuntimeError("unsupported MODEL.BACKBONE %r" % (self.backbone_name,))
         self.mid_dim = 512 if self.backbone_name == "ViT-B/16" else 1024
         self.params = dict(_cfg_get(cfg, "params", None) or {})
-        if self.HEAD == "clipspm" and not self.params:
+        if self.HEAD in ("clipspm", "cpm2c") and not self.params:
             raise RuntimeError("cfg.params (mid_dim_text, mid_dim_vision, negative_slope, alpha) is required")
         self.seq_len = int(_cfg_get(cfg, "DATA.SEQ_LEN"))
         self.single_direct = bool(_cfg_get(cfg, "MODEL.SINGLE_DIRECT", False))
@@ -260,7 +278,8 @@ class CNN(nn.Module):
             negative_slope=float(self.params.get("negative_slope", 0.0)), alpha=float(self.params.get("alpha", 0.0)),
             single_direct=int(self.single_direct), precision={"bf16": 0, "fp32": 1, "bf16_resid": 2}[self.precision],
             max_episodes=self.max_episodes, max_support=0, max_query=0, max_way=0,
-            head={"clipspm": 0, "clipfsar": 1, "sten": 2}[self.HEAD], cls_value=self.cls_value)
+            head={"clipspm": 0, "clipfsar": 1, "sten": 2, "cpm2c": 3}[self.HEAD], cls_value=self.cls_value,
+            **self._extra_config())
         h = ctypes.c_void_p()
         with torch.cuda.device(self._dev):
             _lib.check(lib.spm_create(ctypes.byref(c), ctypes.byref(h)))
@@ -278,6 +297,10 @@ class CNN(nn.Module):
                 raise
         self._h = h
         return h
+
+    def _extra_config(self):
+        """Head-specific trailing fields of spm_config (include/clipspm_b200.h)."""
+        return {}
 
     def _text(self):
         tf = self.text_features_train if self.training else self.text_features_test  # model_clipspm.py:116-121

@@ -33,9 +33,10 @@
 extern "C" {
 #endif
 
-#define SPM_ABI_VERSION 4 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
+#define SPM_ABI_VERSION 5 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
                            * 3: spm_head_stage (per-stage taps for the parity tests)
-                           * 4: spm_jpeg_info / spm_jpeg_decode, spm_eval_u8 */
+                           * 4: spm_jpeg_info / spm_jpeg_decode, spm_eval_u8
+                           * 5: SPM_HEAD_CPM2C: spm_config gained its parameters; spm_cpm2c_outputs */
 
 typedef struct spm_handle spm_handle;
 
@@ -52,7 +53,8 @@ enum { SPM_PRECISION_BF16 = 0, SPM_PRECISION_FP32 = 1,
 /* metric head behind the same entry points: CLIP-SPM (models/model_clipspm.py, the hot path) or its sibling
  * CLIP-FSAR (models/model_clipfsar.py CNN_OTAM_CLIPFSAR, evaluation branch :325-383), which reuses the same
  * transformer-block, class-mean and OTAM kernels */
-enum { SPM_HEAD_CLIPSPM = 0, SPM_HEAD_CLIPFSAR = 1, SPM_HEAD_STEN = 2 /* models/model_sten.py:62-113 as shipped */ };
+enum { SPM_HEAD_CLIPSPM = 0, SPM_HEAD_CLIPFSAR = 1, SPM_HEAD_STEN = 2 /* models/model_sten.py:62-113 as shipped */,
+       SPM_HEAD_CPM2C = 3 /* models/model_cpm2c.py CLIP_CPMMC_FSAR, evaluation forward :207-312 */ };
 
 typedef struct spm_config {
   int backbone;         /* cfg.MODEL.BACKBONE: SPM_BACKBONE_*                         model_clipspm.py:18,24 */
@@ -70,6 +72,12 @@ typedef struct spm_config {
   int max_way;          /* W distinct support labels per episode (upper bound)                               */
   int head;             /* SPM_HEAD_* (cfg.MODEL.NAME 'clipspm' / 'clipfsar')          run/main_run.py:123-130 */
   float cls_value;      /* cfg.MODEL.USE_CLASSIFICATION_VALUE (CLIP-FSAR loss only)    run/main_run.py:356    */
+  /* SPM_HEAD_CPM2C only (ABI 5) */
+  float motion_residual_ratio; /* cfg.params['motion_residual_ratio']                  model_cpm2c.py:175     */
+  float lambdas[4];     /* cfg.params['lambdas0'..'lambdas3'] (loss / total-logit weights) run/main_run.py:372-376 */
+  float motion_coeff;   /* cfg.MODEL.MOTION_COFF                                        model_cpm2c.py:87      */
+  float normal_coeff;   /* cfg.MODEL.NORMAL_COFF                                        model_cpm2c.py:88      */
+  int use_classification; /* cfg.MODEL.USE_CLASSIFICATION (class_logits branch)          model_cpm2c.py:426     */
 } spm_config;
 
 const char* spm_last_error(void);
@@ -103,6 +111,12 @@ int spm_set_text_features(spm_handle* h, void* stream, const float* table, int n
  *   (sum_q CE(logits) + cls_value * sum_v CE(class_logits[v], real label of v)) / tasks_per_batch, dists_out = 0. */
 int spm_set_text_features_train(spm_handle* h, void* stream, const float* table, int n_cls, int dim);
 int spm_class_logits(spm_handle* h, void* stream, int n_rows, int n_cls, float* out);
+
+/* CPM2C only: the per-branch outputs of the most recent head / forward / eval call (models/model_cpm2c.py:229-236):
+ * logits_local [E,Q,W] (frame alignment), logits_global [E,Q,W] (token matching); the generic logits_out of that call
+ * is lambdas1 * local + lambdas2 * global (the logits run/main_run.py:373 takes the accuracy on), dists_out is
+ * target_consist_distance, and spm_class_logits returns class_logits [E*(S+Q), n_cls] (test prompts). */
+int spm_cpm2c_outputs(spm_handle* h, void* stream, int n_episodes, int Q, int W, float* logits_local, float* logits_global);
 
 /* Frame encoder: images [F,3,224,224] fp32 NCHW in [0,1] -> features [F, D] fp32 */
 int spm_encode_frames(spm_handle* h, void* stream, const float* images, int n_frames, float* feats_out);

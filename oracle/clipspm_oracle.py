@@ -352,6 +352,128 @@ def fsar_loss_and_acc(logits, class_logits, target_labels, real_support, real_ta
     return loss.float(), acc.float(), pred
 
 
+# -----------------------------------------------------------------------------------------------------
+# sibling head CPM2C (models/model_cpm2c.py CLIP_CPMMC_FSAR), evaluation forward
+# -----------------------------------------------------------------------------------------------------
+CPM2C_PARAMS = dict(mid_dim_vision=0.5, mid_dim_text=1.5, negative_slope=0.0025, alpha=0.2, motion_residual_ratio=0.5,
+                    lambdas0=0.5, lambdas1=1.0, lambdas2=0.3, lambdas3=0.0,
+                    # constructor-only sizes of the visual-prompt nets the forward never calls (:116-133)
+                    prompt_patch=16, hid_dim=8, prompt_patch_2=3, prompt_patch_22=3, hid_dim_2=4)
+
+
+def cpm2c_weight_shapes(D, params=CPM2C_PARAMS):
+    """Head parameters the CPM2C forward reads (models/model_cpm2c.py:73-141): scale, context2 (inner width D), the two
+    class tokens, the gates and the multi-scale motion convolutions."""
+    ht, hv = int(D * params["mid_dim_text"]), int(D * params["mid_dim_vision"])
+    s = dict(fsar_weight_shapes(D))
+    s.update({"class_token": (1, 1, D), "class_token_motion": (1, 1, D),
+              "gate_text.0.weight": (ht, D), "gate_text.0.bias": (ht,), "gate_text.2.weight": (D, ht), "gate_text.2.bias": (D,),
+              "gate_vision.0.weight": (hv, D), "gate_vision.0.bias": (hv,), "gate_vision.2.weight": (D, hv),
+              "gate_vision.2.bias": (D,),
+              "motion_conv1_1.weight": (D, D, 1), "motion_conv1_1.bias": (D,),
+              "motion_conv1_3.weight": (D, D, 3), "motion_conv1_3.bias": (D,),
+              "motion_conv1_5.weight": (D, D, 3), "motion_conv1_5.bias": (D,),
+              "scale_conv.weight": (D, 3 * D, 1), "scale_conv.bias": (D,)})
+    return s
+
+
+def make_cpm2c_weights(D, seed=0, scale=1.7, params=CPM2C_PARAMS):
+    w = {}
+    for name, shp in cpm2c_weight_shapes(D, params).items():
+        leaf = name.split(".")[-1]
+        if name == "scale":
+            w[name] = torch.full((1,), float(scale))
+        elif name.startswith("class_token"):
+            w[name] = _normal(seed, "cpm2c." + name, shp, 0.5)
+        elif len(shp) == 1 and leaf == "weight":
+            w[name] = 1.0 + _normal(seed, "cpm2c." + name, shp, 0.1)
+        elif leaf == "bias":
+            w[name] = _normal(seed, "cpm2c." + name, shp, 0.02)
+        else:
+            fan_in = shp[1] * (shp[2] if len(shp) == 3 else 1)
+            w[name] = _normal(seed, "cpm2c." + name, shp, (3.0 * fan_in) ** -0.5)
+    return w
+
+
+def cpm2c_motion(x, w, ratio):
+    """models/model_cpm2c.py:165-199: multi-scale temporal convolutions (k=1, k=3, k=3 dilated by 2) -> 1x1 fusion ->
+    * ratio + residual; then the forward / backward frame differences.  x [N,T,D] -> [N,T-1,D]."""
+    xt = x.permute(0, 2, 1)
+    f1 = F.conv1d(xt, w["motion_conv1_1.weight"], w["motion_conv1_1.bias"])
+    f3 = F.conv1d(xt, w["motion_conv1_3.weight"], w["motion_conv1_3.bias"], padding=1)
+    f5 = F.conv1d(xt, w["motion_conv1_5.weight"], w["motion_conv1_5.bias"], padding=2, dilation=2)
+    c = F.conv1d(torch.cat([f1, f3, f5], dim=1), w["scale_conv.weight"], w["scale_conv.bias"]) * ratio + xt
+    fwd = c[:, :, 1:] - xt[:, :, :-1]
+    bwd = c[:, :, :-1] - xt[:, :, 1:]
+    return (0.5 * (fwd + bwd)).permute(0, 2, 1)
+
+
+def cpm2c_modulate(x, tok, w, params):
+    """the gate / mix / context2 step models/model_cpm2c.py repeats four times per call (:337-346 etc.):
+    x [N,T,D], tok [N,1,D] -> context2(cat[tok, tok*gate_text(tok)*alpha + x*gate_vision(x)]) [N,T+1,D]"""
+    gt = gate(tok, w, "gate_text.", params["negative_slope"])
+    gv = gate(x, w, "gate_vision.", params["negative_slope"])
+    seq = torch.cat([tok, tok * gt * params["alpha"] + x * gv], dim=1)
+    return transformer_v1(seq, w, "context2.", heads=8, dim_head=x.shape[-1] // 8)
+
+
+def cpm2c_text_eh(ctx_support, ctx_target, su, qu, labels, token, w, params):
+    """text_eh_temporal_transformer (:327-418, no MERGE_BEFORE)"""
+    qu_contra = cpm2c_modulate(qu, ctx_target, w, params)                      # real target prompt
+    su_contra = cpm2c_modulate(su, token.expand(su.shape[0], -1, -1), w, params)   # class token
+    qu_fake = cpm2c_modulate(qu, token.expand(qu.shape[0], -1, -1), w, params)
+    su_real = cpm2c_modulate(su, ctx_support, w, params)
+    return su_real, qu_fake, class_means(su_real, labels), su_contra, qu_contra
+
+
+def cpm2c_global_distance(su_g, labels, qu):
+    """global_distance (:315-325): su_g [S,D] (token rows), qu [Q,T+1,D] -> [W,Q]"""
+    d = 1 - cos_sim(qu, su_g)                                                   # [Q,T+1,S]
+    out = []
+    for c in torch.unique(labels):
+        idx = (labels == c).nonzero().reshape(-1)
+        out.append(d.index_select(2, idx).sum(2).sum(1))
+    return torch.stack(out)
+
+
+def cpm2c_head_forward(w, text, su, qu, support_labels, real_support, real_target, params=CPM2C_PARAMS,
+                       motion_coeff=1.0, normal_coeff=1.0, use_classification=True, single_direct=False):
+    """models/model_cpm2c.py:207-312 (evaluation): su [S,T,D], qu [Q,T,D] -> class_logits [1,S+Q,n_cls],
+    logits_local [1,Q,W], logits_global [1,Q,W], target_consist_distance []."""
+    ctx_s = text[real_support.long()].unsqueeze(1)
+    ctx_t = text[real_target.long()].unsqueeze(1)
+    su_m, qu_m = cpm2c_motion(su, w, params["motion_residual_ratio"]), cpm2c_motion(qu, w, params["motion_residual_ratio"])
+    class_logits = cos_sim(torch.cat([su, qu], dim=0).mean(1), text) * w["scale"] if use_classification else None
+    m = cpm2c_text_eh(ctx_s, ctx_t, su_m, qu_m, support_labels, w["class_token_motion"], w, params)
+    n = cpm2c_text_eh(ctx_s, ctx_t, su, qu, support_labels, w["class_token"], w, params)
+
+    def consist(r):   # :246-255 / :260-268
+        su_real, qu_fake, _, su_contra, qu_contra = r
+        return ((su_real - su_contra) ** 2).sum((-2, -1)).mean() + ((qu_fake - qu_contra) ** 2).sum((-2, -1)).mean()
+    consist_distance = normal_coeff * consist(n) + motion_coeff * consist(m)
+    g = normal_coeff * cpm2c_global_distance(n[0][:, 0, :], support_labels, n[1]) + \
+        motion_coeff * cpm2c_global_distance(m[0][:, 0, :], support_labels, m[1])
+    loc = normal_coeff * otam_distance(n[2][:, 1:, :], n[1][:, 1:, :], single_direct) + \
+        motion_coeff * otam_distance(m[2][:, 1:, :], m[1][:, 1:, :], single_direct)
+    return dict(su_motion=su_m, qu_motion=qu_m, su_real=n[0], qu_fake=n[1], su_pro=n[2], su_real_motion=m[0],
+                qu_fake_motion=m[1], class_logits=None if class_logits is None else class_logits.unsqueeze(0),
+                logits_local=-loc.unsqueeze(0), logits_global=-g.t().unsqueeze(0),
+                target_consist_distance=consist_distance)
+
+
+def cpm2c_loss_and_acc(out, target_labels, real_support, real_target, params=CPM2C_PARAMS, tasks_per_batch=16):
+    """run/main_run.py:370-380 (mode 'test'): lambdas-weighted sum of three cross entropies; accuracy of
+    lambdas1 * logits_local + lambdas2 * logits_global"""
+    def ce(lg, y):
+        return -(lg[0].double().log_softmax(-1).gather(1, y.long().view(-1, 1)).squeeze(1)).sum()
+    real = torch.cat([real_support, real_target])
+    total = params["lambdas1"] * out["logits_local"] + params["lambdas2"] * out["logits_global"]
+    loss = (params["lambdas0"] * ce(out["class_logits"], real) + params["lambdas1"] * ce(out["logits_local"], target_labels)
+            + params["lambdas2"] * ce(out["logits_global"], target_labels)) / tasks_per_batch
+    pred = total[0].argmax(-1)
+    return loss.float(), (pred == target_labels.long()).double().mean().float(), pred, total
+
+
 def sten_head_forward(text_test, su, qu, support_labels, real_support):
     """models/model_sten.py:62-113 as shipped (all learned head modules are commented out there): su [S,8,D],
     qu [Q,8,D] -> logits [1,Q,W]."""

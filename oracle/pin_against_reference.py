@@ -379,6 +379,113 @@ def run_sten_case(m, name):
                         margin=margin.numpy())
 
 
+CPM2C_CASES = {
+    # name: (backbone, way, shot, qpc, T, n_test_cls, head_only, single_direct, seed)
+    "cpm2c_head_5w3s_t8": ("ViT-B/16", 5, 3, 1, 8, 24, True, False, 2202),          # configs/cpm2c/hmdb.yaml shape (3-shot)
+    "cpm2c_head_5w1s_t8_d1024_q2": ("RN50", 5, 1, 2, 8, 10, True, False, 2204),     # the shipped backbone (RN50, D=1024)
+    "cpm2c_head_5w2s_t6_single": ("ViT-B/16", 5, 2, 1, 6, 24, True, True, 2205),    # SINGLE_DIRECT, even T-1... odd motion length 5
+    "cpm2c_vit_2w1s_t4_p1": ("ViT-B/16", 2, 1, 1, 4, 24, False, False, 2201),       # tower + head
+}
+CPM2C_TASKS_PER_BATCH = 16
+
+
+def run_cpm2c_case(m, name):
+    """models/model_cpm2c.py::CLIP_CPMMC_FSAR.  run/run.py's params dict lacks the keys this class reads
+    (prompt_patch, hid_dim, ..., motion_residual_ratio, lambdas0-3), so the shipped runner cannot construct it; the
+    values used here are O.CPM2C_PARAMS (the constructor-only ones size nets the forward never calls)."""
+    backbone, way, shot, qpc, T, ncls, head_only, single, seed = CPM2C_CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    import models.model_cpm2c as c2
+    c2.load = m.load
+    cfg = NS(MODEL=NS(BACKBONE=backbone, MOTION_COFF=1.0, NORMAL_COFF=0.7, USE_CLASSIFICATION=True),
+             TRAIN=NS(CLASS_NAME=["run"]), TEST=NS(CLASS_NAME=["run"]), DATA=NS(SEQ_LEN=T), DEVICE=NS(NUM_GPUS=1),
+             params=dict(O.CPM2C_PARAMS))
+    if single:
+        cfg.MODEL.SINGLE_DIRECT = True
+    torch.manual_seed(0)
+    with torch.no_grad():
+        net = c2.CLIP_CPMMC_FSAR(cfg).eval()
+    w = O.make_cpm2c_weights(D, seed=0)
+    if not head_only:
+        w.update({k: v for k, v in O.make_weights(backbone, seed=0, protocol="P1").items() if k.startswith("backbone.")})
+    missing, unexpected = net.load_state_dict(w, strict=False)
+    head_keys = set(O.cpm2c_weight_shapes(D))
+    assert not unexpected and not (set(missing) & head_keys) and (head_only or not [k for k in missing if k.startswith("backbone.")]), \
+        (missing, unexpected)
+    text = O.make_text_features(ncls, D, seed=0)
+    net.text_features_test = text
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, "P1", images=not head_only)
+    st_ref = {}
+    if head_only:
+        su, qu = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+        net.get_feats = lambda *a, **k: (su, qu, None)
+        ep["context_images"] = torch.zeros(1)
+        ep["target_images"] = torch.zeros(1)
+    else:
+        orig_gf = net.get_feats
+
+        def get_feats(*a, **k):
+            r = orig_gf(*a, **k)
+            st_ref["su"], st_ref["qu"] = r[0].clone(), r[1].clone()
+            return r
+        net.get_feats = get_feats
+    orig_mo, orig_eh = net.get_motion_feats, net.text_eh_temporal_transformer
+    eh_calls = []
+
+    def gmf(*a, **k):
+        r = orig_mo(*a, **k)
+        st_ref["su_motion"], st_ref["qu_motion"] = r[0].clone(), r[1].clone()
+        return r
+
+    def eh(*a, **k):
+        r = orig_eh(*a, **k)
+        eh_calls.append([x.clone() for x in r])
+        return r
+    net.get_motion_feats, net.text_eh_temporal_transformer = gmf, eh
+    with torch.no_grad():
+        out = net(ep)
+        if not head_only:
+            su, qu = st_ref["su"], st_ref["qu"]
+            enc = O.vit_forward if backbone == "ViT-B/16" else O.rn50_forward
+            assert rel(enc(w, ep["context_images"]).reshape(-1, T, D), su) < 2e-4
+        st = O.cpm2c_head_forward(w, text, su, qu, ep["context_labels"], ep["real_support_labels"], ep["real_target_labels"],
+                                  O.CPM2C_PARAMS, motion_coeff=1.0, normal_coeff=0.7, single_direct=single)
+    st_ref["su_real_motion"], st_ref["qu_fake_motion"] = eh_calls[0][0], eh_calls[0][1]
+    st_ref["su_real"], st_ref["qu_fake"], st_ref["su_pro"] = eh_calls[1][0], eh_calls[1][1], eh_calls[1][2]
+    for k in ("class_logits", "logits_local", "logits_global"):
+        st_ref[k] = out[k]
+    st_ref["target_consist_distance"] = out["target_consist_distance"].reshape(())
+    st["target_consist_distance"] = st["target_consist_distance"].reshape(())
+    for mod in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    import utils.utils as U
+    P = O.CPM2C_PARAMS
+    real = torch.cat([ep["real_support_labels"], ep["real_target_labels"]], 0).long()
+    total_ref = P["lambdas1"] * out["logits_local"] + P["lambdas2"] * out["logits_global"]      # run/main_run.py:373
+    loss_ref = (P["lambdas0"] * U.loss(out["class_logits"], real, "cpu") + P["lambdas1"] * U.loss(out["logits_local"], ep["target_labels"].long(), "cpu")
+                + P["lambdas2"] * U.loss(out["logits_global"], ep["target_labels"].long(), "cpu")) / CPM2C_TASKS_PER_BATCH
+    acc_ref = U.aggregate_accuracy(total_ref, ep["target_labels"])
+    loss, acc, pred, total = O.cpm2c_loss_and_acc(st, ep["target_labels"], ep["real_support_labels"], ep["real_target_labels"],
+                                                  P, CPM2C_TASKS_PER_BATCH)
+    st_ref["loss"], st_ref["acc"], st_ref["logits_total"] = loss_ref.reshape(()), acc_ref.reshape(()), total_ref
+    st["loss"], st["acc"], st["logits_total"] = loss.reshape(()), acc.reshape(()), total
+    st.update(su=su, qu=qu)
+    worst = 0.0
+    for k, v in st_ref.items():
+        r = rel(st[k].reshape(v.shape), v)
+        worst = max(worst, r)
+        assert r < 2e-4, "oracle disagrees with the reference on %s/%s: rel err %.3e" % (name, k, r)
+    lg = total_ref[0]
+    top2 = lg.topk(2, dim=-1).values
+    margin = top2[:, 0] - top2[:, 1]
+    print("%-28s oracle==reference (CLIP_CPMMC_FSAR), worst stage rel err %.2e | min top1-top2 margin %.4f, ref acc %.2f"
+          % (name, worst, float(margin.min()), float(acc_ref)))
+    gold = {k: v.detach().float().numpy() for k, v in st_ref.items()}
+    gold["pred"] = lg.argmax(-1).numpy()
+    gold["margin"] = margin.numpy()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
+
+
 SOFTDTW_CASES = {
     # name: (B, N, M, d, gamma, bandwidth, seed)
     "softdtw_8x8_g01": (6, 8, 8, 64, 0.1, 0.0, 3101),        # TA2N's setting: SoftDTW(gamma=0.1), models/model_ta2n.py:87
@@ -416,7 +523,7 @@ def run_softdtw_case(name):
 
 if __name__ == "__main__":
     m = import_reference()
-    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + list(STEN_CASES) + list(SOFTDTW_CASES))
+    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + list(STEN_CASES) + list(CPM2C_CASES) + list(SOFTDTW_CASES))
     for n in names:
         if n == "text":
             run_text_case(m)
@@ -426,6 +533,8 @@ if __name__ == "__main__":
             run_fsar_case(m, n)
         elif n in STEN_CASES:
             run_sten_case(m, n)
+        elif n in CPM2C_CASES:
+            run_cpm2c_case(m, n)
         elif n in SOFTDTW_CASES:
             run_softdtw_case(n)
         else:

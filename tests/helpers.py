@@ -103,6 +103,58 @@ def build_cuda_fsar_model(ci, max_episodes=1, precision="bf16"):
     return net
 
 
+# ---- sibling head CPM2C: must match oracle/pin_against_reference.py::CPM2C_CASES
+# name: (backbone, way, shot, qpc, T, n_test_cls, head_only, single_direct, seed)
+CPM2C_CASES = {
+    "cpm2c_head_5w3s_t8": ("ViT-B/16", 5, 3, 1, 8, 24, True, False, 2202),
+    "cpm2c_head_5w1s_t8_d1024_q2": ("RN50", 5, 1, 2, 8, 10, True, False, 2204),
+    "cpm2c_head_5w2s_t6_single": ("ViT-B/16", 5, 2, 1, 6, 24, True, True, 2205),
+    "cpm2c_vit_2w1s_t4_p1": ("ViT-B/16", 2, 1, 1, 4, 24, False, False, 2201),
+}
+CPM2C_TASKS_PER_BATCH, CPM2C_MOTION_COEFF, CPM2C_NORMAL_COEFF = 16, 1.0, 0.7
+
+
+def cpm2c_case_inputs(name):
+    backbone, way, shot, qpc, T, ncls, head_only, single, seed = CPM2C_CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    w = O.make_cpm2c_weights(D, seed=0)
+    if not head_only:
+        w.update({k: v for k, v in O.make_weights(backbone, seed=0, protocol="P1").items() if k.startswith("backbone.")})
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, "P1", images=not head_only)
+    feats = None
+    if head_only:
+        feats = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+    return dict(backbone=backbone, way=way, shot=shot, qpc=qpc, T=T, D=D, weights=w, episode=ep, feats=feats,
+                text=O.make_text_features(ncls, D, seed=0), single=single, head_only=head_only)
+
+
+def cpm2c_cfg(ci, use_classification=True):
+    from clip_spm_b200.config import make_cfg as _mk
+    cfg = _mk(ci["backbone"], ci["T"], ci["single"], ci["way"], params=dict(O.CPM2C_PARAMS),
+              tasks_per_batch=CPM2C_TASKS_PER_BATCH)
+    cfg.MODEL.MOTION_COFF, cfg.MODEL.NORMAL_COFF = CPM2C_MOTION_COEFF, CPM2C_NORMAL_COEFF
+    cfg.MODEL.USE_CLASSIFICATION = use_classification
+    return cfg
+
+
+def build_cuda_cpm2c_model(ci, max_episodes=1, precision="bf16", use_classification=True):
+    from clip_spm_b200 import CLIP_CPMMC_FSAR
+    net = CLIP_CPMMC_FSAR(cpm2c_cfg(ci, use_classification), text_features_test=ci["text"], max_episodes=max_episodes,
+                          precision=precision)
+    missing, unexpected = net.load_state_dict(ci["weights"], strict=False)
+    assert not unexpected, unexpected
+    if not ci["head_only"]:
+        assert not missing, missing
+    return net
+
+
+def cpm2c_oracle(ci, su, qu):
+    ep = ci["episode"]
+    return O.cpm2c_head_forward(ci["weights"], ci["text"], su, qu, ep["context_labels"], ep["real_support_labels"],
+                                ep["real_target_labels"], O.CPM2C_PARAMS, motion_coeff=CPM2C_MOTION_COEFF,
+                                normal_coeff=CPM2C_NORMAL_COEFF, single_direct=ci["single"])
+
+
 # ---- sibling head STEN: must match oracle/pin_against_reference.py::STEN_CASES (T = 8)
 # name: (backbone, way, shot, qpc, n_test_cls, head_only, seed)
 STEN_CASES = {
