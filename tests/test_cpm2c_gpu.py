@@ -36,6 +36,8 @@ def _check_outputs(out, g, tol):
 @pytest.mark.parametrize("precision,tol", [("bf16", TOL_HEAD), ("fp32", 1e-4)])
 def test_cpm2c_head_matches_reference_golden(name, precision, tol):
     ci, g = H.cpm2c_case_inputs(name), H.golden(name)
+    if precision == "fp32" and ci["backbone"] != "ViT-B/16":
+        pytest.skip("the fp32 parity mode exists for the ViT-B/16 backbone only (spm_create says so)")
     net = H.build_cuda_cpm2c_model(ci, precision=precision)
     out = _run_head(net, ci)
     assert _check_outputs(out, g, tol) >= 1
