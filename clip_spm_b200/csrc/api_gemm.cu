@@ -3,6 +3,8 @@
 #include "../../include/clipspm_b200.h"
 #include "api_common.cuh"
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "gemm.cuh"
@@ -18,16 +20,16 @@ const char* get_error() { return g_err.c_str(); }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct GemmRecord { cudaEvent_t a, b; int tag; double flops; };
+struct GemmRecord { cudaEvent_t a, b; int tag; double flops; int M, N, K; };
 static std::vector<GemmRecord> g_records;
 static int g_used = 0;
 static bool g_profiling = false;
 
 bool profile_armed() { return g_profiling; }
-bool profile_gemm_begin(cudaStream_t st, int tag, double flops, int* slot) {
+bool profile_gemm_begin(cudaStream_t st, int tag, double flops, int* slot, int M, int N, int K) {
   if (!g_profiling || g_used >= (int)g_records.size()) return false;
   GemmRecord& r = g_records[g_used];
-  r.tag = tag; r.flops = flops;
+  r.tag = tag; r.flops = flops; r.M = M; r.N = N; r.K = K;
   if (cudaEventRecord(r.a, st) != cudaSuccess) return false;
   *slot = g_used++;
   return true;
@@ -78,6 +80,22 @@ int spm_profile_end(double* flops4, double* ms4, int* count4) {
     SPM_CUDA(cudaEventElapsedTime(&ms, g_records[i].a, g_records[i].b));
     const int t = g_records[i].tag & 3;
     flops4[t] += g_records[i].flops; ms4[t] += ms; count4[t] += 1;
+  }
+  if (getenv("SPM_PROFILE_SHAPES") != nullptr) {   // per-shape totals on stderr (tools/: in-situ A/B of one GEMM)
+    struct Agg { int M, N, K, n; double ms, flops; };
+    std::vector<Agg> aggs;
+    for (int i = 0; i < g_used; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_records[i].a, g_records[i].b);
+      Agg* hit = nullptr;
+      for (auto& a : aggs)
+        if (a.M == g_records[i].M && a.N == g_records[i].N && a.K == g_records[i].K) hit = &a;
+      if (hit == nullptr) { aggs.push_back({g_records[i].M, g_records[i].N, g_records[i].K, 0, 0.0, 0.0}); hit = &aggs.back(); }
+      hit->n += 1; hit->ms += ms; hit->flops += g_records[i].flops;
+    }
+    for (const auto& a : aggs)
+      fprintf(stderr, "[spm profile] M=%d N=%d K=%d launches=%d avg_us=%.1f tflops=%.1f\n", a.M, a.N, a.K, a.n,
+              1e3 * a.ms / a.n, a.flops / 1e12 / (a.ms / 1e3));
   }
   g_used = 0;
   return 0;

@@ -33,7 +33,18 @@ struct GemmEpilogue {
   int out_bf16 = 0;
   int act = ACT_NONE;
   float slope = 0.f;      // LeakyReLU negative slope
+  // LayerNorm folded into the neighbouring GEMMs (2-CTA kernel only, N == LN_FOLD_C on the producer side):
+  //   producer (fp32 residual GEMM): also writes a bf16 copy of its output rows (out2_bf16, leading dim ldo) and, per row
+  //   and (256-column tile, epilogue half), the partial sums {sum x, sum x^2} of the columns it produced (ln_stats_out);
+  //   consumer (bf16 + bias GEMM whose A operand is that bf16 copy and whose weights carry gamma): out = act(rstd * (acc -
+  //   mean * ln_colsum[n]) + bias[n]) with mean / rstd rebuilt from the row's partial sums (ln_stats_in).
+  void* out2_bf16 = nullptr;
+  float* ln_stats_out = nullptr;
+  const float* ln_stats_in = nullptr;
+  const float* ln_colsum = nullptr;
 };
+constexpr int LN_FOLD_C = 768;                        // row width the statistics cover (ViT-B/16 residual stream)
+constexpr int LN_FOLD_SLOTS = 2 * (LN_FOLD_C / 256);  // partial sums per row: (n-tile, epilogue half)
 
 struct GemmOp {
   CUtensorMap ta, tb;

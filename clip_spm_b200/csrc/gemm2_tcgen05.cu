@@ -94,7 +94,9 @@ struct Gemm2Args {
 // EPI: 0 = general epilogue; 1 / 2 = bf16 output + bias (+ QuickGELU) with identity rows (gemm_epilogue_tile_bf16_bias);
 // 3 = convolution (rn50.cu): the producer addresses the 3x3 taps as row offsets of the zero-bordered image matrix and
 // the general epilogue is compiled with its zero-border handling
-template <bool RES, int EPI = 0>
+// LNF: LayerNorm folded into the epilogues (GemmEpilogue::ln_*): RES kernels also emit the bf16 copy and the row statistics,
+// EPI 1 / 2 kernels normalise their accumulator rows with them
+template <bool RES, int EPI = 0, int LNF = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmR, const Gemm2Args args) {
@@ -252,14 +254,18 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T::BN);
+        float s1 = 0.f, s2 = 0.f;   // LNF: row sums over this warp's 128 columns of the tile
 #pragma unroll 1
         for (int gi = 0; gi < GPT; ++gi) {
           const int g = half + 2 * gi;
           const int b = n_done & 1;
           mbar_wait(&my_bar[b], (n_done >> 1) & 1);
-          gemm_epilogue_group_restma(ep, stg_u + (uint32_t)(b * 4096), taddr + (uint32_t)(g * 32), m_base, n0 + g * 32,
-                                     M, lane);
+          gemm_epilogue_group_restma<(LNF != 0)>(ep, stg_u + (uint32_t)(b * 4096), taddr + (uint32_t)(g * 32), m_base,
+                                          n0 + g * 32, M, lane, s1, s2);
           ++n_done;
+          if (LNF && gi == GPT - 1 && m_base + lane < M)
+            *reinterpret_cast<float2*>(ep.ln_stats_out + ((long long)(m_base + lane) * LN_FOLD_SLOTS +
+                                                          (n0 / T::BN) * 2 + half) * 2) = make_float2(s1, s2);
           if (gi == GPT - 1) {  // last TMEM read of this tile is done: hand the accumulator back before refilling
             tc_fence_before_sync();
             __syncwarp();
@@ -279,8 +285,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T::BN);
-        if (EPI == 1) gemm_epilogue_tile_bf16_bias<T::BN, ACT_NONE>(ep, stg_u, taddr, m_base, n0, M, lane, half);
-        else if (EPI == 2) gemm_epilogue_tile_bf16_bias<T::BN, ACT_QUICKGELU>(ep, stg_u, taddr, m_base, n0, M, lane, half);
+        if (EPI == 1) gemm_epilogue_tile_bf16_bias<T::BN, ACT_NONE, LNF>(ep, stg_u, taddr, m_base, n0, M, lane, half);
+        else if (EPI == 2) gemm_epilogue_tile_bf16_bias<T::BN, ACT_QUICKGELU, LNF>(ep, stg_u, taddr, m_base, n0, M, lane, half);
         else if (EPI == 3) {
           if (conv_epilogue_applies(ep)) {   // (warp-uniform) compile-time specialised convolution epilogue
             if (ep.residual_bf16 != nullptr) gemm_epilogue_tile_conv<T::BN, true>(ep, stg_u, taddr, m_base, n0, M, N, lane, half);
@@ -314,6 +320,16 @@ int gemm2_init(const char** err) {
                            G2T<false>::SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(gemm2_tcgen05_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            G2T<false>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm2_tcgen05_kernel<false, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           G2T<false>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm2_tcgen05_kernel<false, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           G2T<false>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm2_tcgen05_kernel<false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           G2T<false>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm2_tcgen05_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           G2T<false>::SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm2_tcgen05_kernel<true, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           G2T<true>::SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(gemm2_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            G2T<true>::SMEM_BYTES) != cudaSuccess) {
     *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the 2-CTA GEMM kernel";
@@ -339,6 +355,8 @@ int gemm2_launch(const GemmOp* op, cudaStream_t stream) {
   a.conv_w2 = op->conv_w2; a.conv_cblocks = op->conv_cblocks;
   if (op->conv_cblocks > 0 || op->ep.border_w2 > 0)
     launch2_pdl(gemm2_tcgen05_kernel<false, 3>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);
+  else if (op->res_tma && op->ep.ln_stats_out != nullptr)
+    launch2_pdl(gemm2_tcgen05_kernel<true, 0, 1>, op->grid, G2T<true>::SMEM_BYTES, stream, op->ta, op->tb, op->tr, a);
   else if (op->res_tma)
     launch2_pdl(gemm2_tcgen05_kernel<true>, op->grid, G2T<true>::SMEM_BYTES, stream, op->ta, op->tb, op->tr, a);
   else {
@@ -349,7 +367,15 @@ int gemm2_launch(const GemmOp* op, cudaStream_t stream) {
                         e.residual_bf16 == nullptr && e.out_row_group == 0 && e.border_w2 == 0 &&
                         op->N % G2T<false>::BN == 0 && (e.ldo % 8) == 0 &&
                         (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0;
-    if (simple && e.act == ACT_NONE)
+    if (simple && e.ln_stats_in != nullptr && e.ln_colsum == nullptr && e.act == ACT_NONE)
+      launch2_pdl(gemm2_tcgen05_kernel<false, 1, 2>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);
+    else if (simple && e.ln_stats_in != nullptr && e.ln_colsum == nullptr && e.act == ACT_QUICKGELU)
+      launch2_pdl(gemm2_tcgen05_kernel<false, 2, 2>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);
+    else if (simple && e.ln_stats_in != nullptr && e.act == ACT_NONE)
+      launch2_pdl(gemm2_tcgen05_kernel<false, 1, 1>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);
+    else if (simple && e.ln_stats_in != nullptr && e.act == ACT_QUICKGELU)
+      launch2_pdl(gemm2_tcgen05_kernel<false, 2, 1>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);
+    else if (simple && e.act == ACT_NONE)
       launch2_pdl(gemm2_tcgen05_kernel<false, 1>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);
     else if (simple && e.act == ACT_QUICKGELU)
       launch2_pdl(gemm2_tcgen05_kernel<false, 2>, op->grid, G2T<false>::SMEM_BYTES, stream, op->ta, op->tb, op->ta, a);

@@ -217,12 +217,28 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint3
 // but every option is a compile-time constant: no residual registers, no activation dispatch, no row-map arithmetic
 // (the general epilogue sits at the 168-register cap; an A/B run showed the encoder GEMMs lose 4 % to ~10 extra
 // registers' worth of code in it).
-template <int BN, int ACT>
+// LNF: the A operand was the raw (not normalised) bf16 residual stream and the weights carry gamma; the row's LayerNorm
+// is applied here, out = act(rstd * acc - rstd * mean * colsum[n] + bias[n]) (see GemmEpilogue::ln_stats_in).
+template <int BN, int ACT, int LNF = 0>
 __device__ __forceinline__ void gemm_epilogue_tile_bf16_bias(const GemmEpilogue& ep, uint32_t stg_u, uint32_t taddr,
                                                              int m_base, int n0, int M, int lane, int half) {
   const int rr = lane >> 3, uu = lane & 7;  // read-back mapping: row i*4 + rr, 16-byte unit uu
   __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.out);
   const uint32_t srow = stg_u + (uint32_t)(lane * 128);
+  float rstd = 1.f, nmr = 0.f;   // this thread's accumulator row: 1/std and -mean/std
+  if (LNF) {
+    const int m = min(m_base + lane, M - 1);
+    const float4* sp = reinterpret_cast<const float4*>(ep.ln_stats_in + (long long)m * (2 * LN_FOLD_SLOTS));
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_FOLD_SLOTS / 2; ++j) {   // fixed order: deterministic
+      const float4 a = __ldg(sp + j);
+      s1 += a.x; s2 += a.y; s1 += a.z; s2 += a.w;
+    }
+    const float mean = s1 * (1.f / LN_FOLD_C);
+    rstd = rsqrtf(fmaxf(s2 * (1.f / LN_FOLD_C) - mean * mean, 0.f) + 1e-5f);
+    nmr = -rstd * mean;
+  }
 #pragma unroll 1
   for (int g = half * 2; g < BN / 32; g += 4) {
     const int col0 = n0 + g * 32;  // first output column of this 128-byte store group (64 bf16)
@@ -233,13 +249,34 @@ __device__ __forceinline__ void gemm_epilogue_tile_bf16_bias(const GemmEpilogue&
       tmem_ld_wait();
       const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0 + h * 32);
       float v[32];
+      if (LNF == 2) {   // weight rows centred (zero column sums): the mean term vanishes
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(bp + j);
-        v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(bp + j);
+          v[4 * j + 0] = fmaf(rstd, __uint_as_float(r[4 * j + 0]), b.x);
+          v[4 * j + 1] = fmaf(rstd, __uint_as_float(r[4 * j + 1]), b.y);
+          v[4 * j + 2] = fmaf(rstd, __uint_as_float(r[4 * j + 2]), b.z);
+          v[4 * j + 3] = fmaf(rstd, __uint_as_float(r[4 * j + 3]), b.w);
+        }
+      } else if (LNF) {
+        const float4* cp = reinterpret_cast<const float4*>(ep.ln_colsum + col0 + h * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(bp + j), c = __ldg(cp + j);
+          v[4 * j + 0] = fmaf(rstd, __uint_as_float(r[4 * j + 0]), fmaf(nmr, c.x, b.x));
+          v[4 * j + 1] = fmaf(rstd, __uint_as_float(r[4 * j + 1]), fmaf(nmr, c.y, b.y));
+          v[4 * j + 2] = fmaf(rstd, __uint_as_float(r[4 * j + 2]), fmaf(nmr, c.z, b.z));
+          v[4 * j + 3] = fmaf(rstd, __uint_as_float(r[4 * j + 3]), fmaf(nmr, c.w, b.w));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(bp + j);
+          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+        }
       }
       if (ACT == ACT_QUICKGELU) {
 #pragma unroll
@@ -362,8 +399,11 @@ __device__ __forceinline__ bool conv_epilogue_applies(const GemmEpilogue& ep) {
 // permutation the staging tile uses) into `buf_u`; the thread owning accumulator row `lane` adds its row in place,
 // then the tile is read back row-contiguously and stored.  No residual registers, and the load was issued one column
 // group earlier, so its HBM latency is hidden behind the previous group's work.
+// LNF: additionally accumulates this thread's row sums (s1 += sum x, s2 += sum x^2 over the 32 final values) and writes a
+// bf16 copy of the rows (GemmEpilogue::out2_bf16) -- the operand and the statistics of the LayerNorm folded into the next GEMM.
+template <bool LNF = false>
 __device__ __forceinline__ void gemm_epilogue_group_restma(const GemmEpilogue& ep, uint32_t buf_u, uint32_t taddr_cols,
-                                                           int m_base, int col0, int M, int lane) {
+                                                           int m_base, int col0, int M, int lane, float& s1, float& s2) {
   uint32_t r[32];
   tmem_ld_32x32b_x32(taddr_cols, r);
   tmem_ld_wait();
@@ -388,6 +428,11 @@ __device__ __forceinline__ void gemm_epilogue_group_restma(const GemmEpilogue& e
     u.z = __float_as_uint(__uint_as_float(u.z) + v[4 * j + 2]);
     u.w = __float_as_uint(__uint_as_float(u.w) + v[4 * j + 3]);
     st_shared_v4(a, u);
+    if (LNF) {
+      const float x0 = __uint_as_float(u.x), x1 = __uint_as_float(u.y), x2 = __uint_as_float(u.z), x3 = __uint_as_float(u.w);
+      s1 += (x0 + x1) + (x2 + x3);
+      s2 = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, s2))));
+    }
   }
   __syncwarp();
   const int rr = lane >> 3, uu = lane & 7;
@@ -395,8 +440,16 @@ __device__ __forceinline__ void gemm_epilogue_group_restma(const GemmEpilogue& e
   for (int i = 0; i < 8; ++i) {
     const int rl = i * 4 + rr;
     const uint4 d = ld_shared_v4(buf_u + (uint32_t)(rl * 128 + ((uu ^ (rl & 7)) * 16)));
-    if (m_base + rl < M)
+    if (m_base + rl < M) {
       *reinterpret_cast<uint4*>(reinterpret_cast<float*>(ep.out) + (long long)(m_base + rl) * ep.ldo + col0 + uu * 4) = d;
+      if (LNF) {
+        uint2 p;
+        p.x = pack2_bf16(__uint_as_float(d.x), __uint_as_float(d.y));
+        p.y = pack2_bf16(__uint_as_float(d.z), __uint_as_float(d.w));
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out2_bf16) + (long long)(m_base + rl) * ep.ldo + col0 +
+                                  uu * 4) = p;
+      }
+    }
   }
   __syncwarp();  // every lane has read the buffer: it may be refilled
 }

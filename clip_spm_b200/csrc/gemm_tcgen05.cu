@@ -367,6 +367,16 @@ int gemm_plan(GemmOp* op, int kind, const void* A, long long lda, const void* B,
   else
     op->two_cta = (allow_2cta && kind == GEMM_BF16 && N % 256 == 0 && pair_tiles >= num_sms / 2 &&
                    (K >= 2048 || mode_2cta == 2)) ? 1 : 0;
+  // LayerNorm folding (GemmEpilogue::ln_*) lives in the pair kernel's epilogues only: taken whatever the tile count, so that
+  // a frame's features do not depend on the size of the chunk it was encoded in
+  const bool ln_fold = ep.ln_stats_in != nullptr || ep.ln_stats_out != nullptr;
+  if (ln_fold) {
+    if (kind != GEMM_BF16 || N % 256 != 0 || (ep.ln_stats_out != nullptr && N != LN_FOLD_C)) {
+      *err = "LayerNorm folding needs the bf16 pair kernel (N % 256 == 0; producer N == 768)";
+      return 1;
+    }
+    op->two_cta = 1;
+  }
   if (op->two_cta) {
     op->bn = 256;
     const long long pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
@@ -432,7 +442,7 @@ int gemm_run(const GemmOp* op, cudaStream_t stream, const char** err) {
   a.conv_w2 = op->conv_w2; a.conv_cblocks = op->conv_cblocks; a.conv_pair = op->conv_pair; a.reverse = op->reverse;
   int slot = -1;
   const bool prof = profile_gemm_begin(stream, (op->kind & 1) * 2 + (op->bn == 256 ? 1 : 0),
-                                       2.0 * (double)op->M * (double)op->N * (double)op->K, &slot);
+                                       2.0 * (double)op->M * (double)op->N * (double)op->K, &slot, op->M, op->N, op->K);
 #define SPM_LAUNCH(BN, KIND) \
   launch_pdl(gemm_tcgen05_kernel<BN, KIND>, op->grid, 384, GemmTile<BN, KIND>::SMEM_BYTES, stream, op->ta, op->tb, a)
   if (op->kind == GEMM_F32_SIMT) {

@@ -23,7 +23,10 @@ int k_patch_im2col(cudaStream_t st, const float* images, __nv_bfloat16* patches,
 //   Writes fp32 (out_f32) and/or bf16 (out_bf16), contiguous rows of C (row stride out_stride).
 int k_layernorm(cudaStream_t st, const float* in, long long in_stride, int rows, int C, const float* gamma,
                 const float* beta, const float* cls_row, int cls_period, float* out_f32, __nv_bfloat16* out_bf16,
-                long long out_stride, int reverse = 0);
+                long long out_stride, int reverse = 0, float* stats_out = nullptr);
+// LayerNorm folded into the next GEMM (GemmEpilogue::ln_*): gamma into the weights, beta into the bias, column sums
+int k_fold_ln(cudaStream_t st, const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
+              __nv_bfloat16* Wf, float* colsum, float* bias2, int center = 0);
 int k_layernorm_bf16in(cudaStream_t st, const __nv_bfloat16* in, long long in_stride, int rows, int C, const float* gamma,
                        const float* beta, __nv_bfloat16* out_bf16, long long out_stride, int reverse = 0);
 // softmax(Q K^T / 8) V for 12 heads x 64 dims over 197 tokens per frame (clip_fsar.py:626,638), bf16 tensor cores.

@@ -172,6 +172,8 @@ int spm_create(const spm_config* cfg, spm_handle** out) {
   SPM_KERNEL(k_vit_attention_f32_init());
   if (const char* e = getenv("SPM_ATTN")) h->attn_mma = std::string(e) == "mma";
   if (const char* e = getenv("SPM_PRUNE_LAST")) h->prune_last = atoi(e) != 0;
+  if (const char* e = getenv("SPM_LN_FOLD")) h->ln_fold = atoi(e);
+  if (h->fp32 || h->resid_bf16 || cfg->backbone != SPM_BACKBONE_VIT_B16) h->ln_fold = 0;
   SPM_KERNEL(k_seq_attention_init());
   SPM_KERNEL(k_otam_init());
   *out = h.release();

@@ -56,6 +56,9 @@ struct Buf {
 struct VitLayerW {
   __nv_bfloat16 *qkv_w, *out_w, *fc_w, *proj_w;
   float *qkv_b, *out_b, *fc_b, *proj_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  // ln_1 folded into the QKV projection and ln_2 into c_fc (k_fold_ln): weights * gamma, column sums, bias + W beta
+  __nv_bfloat16 *qkv_wf = nullptr, *fc_wf = nullptr;
+  float *qkv_c = nullptr, *qkv_bf = nullptr, *fc_c = nullptr, *fc_bf = nullptr;
 };
 struct VitW {
   __nv_bfloat16* conv1_w = nullptr;  // [768, 768]
@@ -88,6 +91,7 @@ struct VitPlan {
   GemmOp patch, qkv[VIT_LAYERS], outp[VIT_LAYERS], fc[VIT_LAYERS], proj[VIT_LAYERS], fin;
   // last block restricted to the class-token rows (the only rows ln_post reads, clip_fsar.py:684)
   GemmOp outp_cls, fc_cls, proj_cls;
+  bool ln_fold = false;   // qkv / fc normalise in their epilogues, outp / proj emit the bf16 rows + statistics: no LayerNorm kernels
 };
 struct CtxPlan {
   GemmOp qkv, outp, ff0, ff3;
@@ -146,8 +150,10 @@ struct spm_handle {
   // where overlap buys nothing, and multi-stream runs showed sporadic 100-300 ms submission stalls.  Default: 1 stream.
   struct VitWs {
     __nv_bfloat16 *patches, *xn, *qkv, *attn, *hid, *cls, *xnc, *xb, *xcb;
-    float *x, *xc;
+    float *x, *xc, *ln_stats;
   } vit_ws[2] = {};
+  int ln_fold = 1;          // 2 = centred weights (no column-sum term); SPM_LN_FOLD=0: separate LayerNorm kernels everywhere (bf16 precision, fp32 residual stream only)
+  float* ln_stats = nullptr;
   int cur_ws = 0, enc_streams = 1;  // 2 = opt-in (SPM_ENC_STREAMS): measured no faster under the power cap
   cudaStream_t enc_stream[2] = {nullptr, nullptr};
   cudaEvent_t enc_fork = nullptr, enc_join[2] = {nullptr, nullptr};

@@ -39,6 +39,19 @@ int load_vit(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
     SPM_TRY(copy_f32(h, st, wt, b + "ln_1.bias", C, &l.ln1_b));
     SPM_TRY(copy_f32(h, st, wt, b + "ln_2.weight", C, &l.ln2_g));
     SPM_TRY(copy_f32(h, st, wt, b + "ln_2.bias", C, &l.ln2_b));
+    if (h->ln_fold) {
+      const float* w;
+      SPM_TRY(wt.get(b + "attn.in_proj_weight", 3LL * C * C, &w));
+      SPM_TRY(dalloc_t(h, &l.qkv_wf, 3LL * C * C));
+      SPM_TRY(dalloc_t(h, &l.qkv_c, 3 * C));
+      SPM_TRY(dalloc_t(h, &l.qkv_bf, 3 * C));
+      SPM_KERNEL(k_fold_ln(st, w, l.ln1_g, l.ln1_b, l.qkv_b, 3 * C, C, l.qkv_wf, l.qkv_c, l.qkv_bf, h->ln_fold == 2));
+      SPM_TRY(wt.get(b + "mlp.c_fc.weight", 4LL * C * C, &w));
+      SPM_TRY(dalloc_t(h, &l.fc_wf, 4LL * C * C));
+      SPM_TRY(dalloc_t(h, &l.fc_c, 4 * C));
+      SPM_TRY(dalloc_t(h, &l.fc_bf, 4 * C));
+      SPM_KERNEL(k_fold_ln(st, w, l.ln2_g, l.ln2_b, l.fc_b, 4 * C, C, l.fc_wf, l.fc_c, l.fc_bf, h->ln_fold == 2));
+    }
   }
   return 0;
 }
@@ -76,7 +89,7 @@ namespace {
 void select_vit_ws(spm_handle* h, int i) {
   const spm_handle::VitWs& w = h->vit_ws[i];
   h->patches = w.patches; h->xn = w.xn; h->qkv = w.qkv; h->attn = w.attn; h->hid = w.hid; h->cls = w.cls;
-  h->xnc = w.xnc; h->x = w.x; h->xc = w.xc; h->xb = w.xb; h->xcb = w.xcb;
+  h->xnc = w.xnc; h->x = w.x; h->xc = w.xc; h->xb = w.xb; h->xcb = w.xcb; h->ln_stats = w.ln_stats;
   h->cur_ws = i;
 }
 
@@ -96,6 +109,11 @@ int ensure_vit_workspace(spm_handle* h) {
     SPM_TRY(dalloc_t(h, &w.xc, (long long)h->frame_chunk * VIT_C));
     SPM_TRY(dalloc_t(h, &w.xnc, (long long)h->frame_chunk * VIT_C));
     w.xb = w.xcb = nullptr;
+    w.ln_stats = nullptr;
+    if (h->ln_fold) {
+      SPM_TRY(dalloc_t(h, &w.xb, M * VIT_C));
+      SPM_TRY(dalloc_t(h, &w.ln_stats, M * 2 * LN_FOLD_SLOTS));
+    }
     if (h->resid_bf16) {
       SPM_TRY(dalloc_t(h, &w.xb, M * VIT_C));
       SPM_TRY(dalloc_t(h, &w.xcb, (long long)h->frame_chunk * VIT_C));
@@ -168,6 +186,28 @@ int get_vit_plan(spm_handle* h, int F, VitPlan** out) {
     }
     SPM_TRY(plan_gemm(&pl->proj[i], kind, a_hid, 4 * C, f32 ? (const void*)l32.proj_w : (const void*)l.proj_w, 4 * C, M, C, 4 * C, e4, h->sms));
   }
+  // LayerNorm folding: every block GEMM runs on the pair kernel with the epilogues that implement it (TMA residual epilogue
+  // for out_proj / c_proj, bf16 + bias epilogue for QKV / c_fc), whatever the chunk size
+  if (h->ln_fold && !f32 && !h->resid_bf16) {
+    for (int i = 0; i < VIT_LAYERS; ++i) {
+      const VitLayerW& l = v.layer[i];
+      GemmEpilogue e1 = pl->qkv[i].ep;
+      e1.bias = l.qkv_bf; e1.ln_stats_in = h->ln_stats; e1.ln_colsum = h->ln_fold == 2 ? nullptr : l.qkv_c;
+      SPM_TRY(plan_gemm(&pl->qkv[i], kind, h->xb, C, l.qkv_wf, C, M, 3 * C, C, e1, h->sms));
+      GemmEpilogue e3 = pl->fc[i].ep;
+      e3.bias = l.fc_bf; e3.ln_stats_in = h->ln_stats; e3.ln_colsum = h->ln_fold == 2 ? nullptr : l.fc_c;
+      SPM_TRY(plan_gemm(&pl->fc[i], kind, h->xb, C, l.fc_wf, C, M, 4 * C, C, e3, h->sms));
+      GemmEpilogue e2 = pl->outp[i].ep;
+      e2.out2_bf16 = h->xb; e2.ln_stats_out = h->ln_stats;
+      SPM_TRY(plan_gemm(&pl->outp[i], kind, a_attn, C, l.out_w, C, M, C, C, e2, h->sms));
+      GemmEpilogue e4 = pl->proj[i].ep;
+      e4.out2_bf16 = h->xb; e4.ln_stats_out = h->ln_stats;
+      SPM_TRY(plan_gemm(&pl->proj[i], kind, a_hid, 4 * C, l.proj_w, 4 * C, M, C, 4 * C, e4, h->sms));
+      SPM_CHECK(pl->qkv[i].two_cta && pl->fc[i].two_cta && pl->outp[i].res_tma && pl->proj[i].res_tma,
+                "vit plan: LayerNorm folding lost its kernels");
+    }
+    pl->ln_fold = true;
+  }
   if (!f32) {
     // Last block, class-token rows only: attention output / residual rows are taken with a row stride of 197 tokens
     const VitLayerW& l = v.layer[VIT_LAYERS - 1];
@@ -237,11 +277,16 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
   } while (0)
   SPM_GEMM_RUN_DIR(pl->patch);
   const bool rb = h->resid_bf16;   // bf16 residual stream: ln_pre writes it, every later LayerNorm reads it
-  SPM_KERNEL(k_layernorm(st, h->x, C, M, C, v.ln_pre_g, v.ln_pre_b, v.cls_pos, VIT_L, rb ? nullptr : h->x, rb ? h->xb : nullptr,
-                         C, next_dir()));
+  const bool lf = pl->ln_fold;     // ln_1 / ln_2 live in the GEMM epilogues: ln_pre also emits the bf16 rows + row statistics
+  if (lf)
+    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, v.ln_pre_g, v.ln_pre_b, v.cls_pos, VIT_L, h->x, h->xb, C, next_dir(), h->ln_stats));
+  else
+    SPM_KERNEL(k_layernorm(st, h->x, C, M, C, v.ln_pre_g, v.ln_pre_b, v.cls_pos, VIT_L, rb ? nullptr : h->x, rb ? h->xb : nullptr,
+                           C, next_dir()));
   for (int i = 0; i < VIT_LAYERS; ++i) {
     const VitLayerW& l = v.layer[i];
-    if (rb) SPM_KERNEL(k_layernorm_bf16in(st, h->xb, C, M, C, l.ln1_g, l.ln1_b, h->xn, C, next_dir()));
+    if (lf) {}
+    else if (rb) SPM_KERNEL(k_layernorm_bf16in(st, h->xb, C, M, C, l.ln1_g, l.ln1_b, h->xn, C, next_dir()));
     else SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln1_g, l.ln1_b, nullptr, 0, nullptr, h->xn, C, next_dir()));
     SPM_GEMM_RUN_DIR(pl->qkv[i]);
     if (h->attn_mma)
@@ -263,7 +308,8 @@ int vit_run(spm_handle* h, cudaStream_t st, int F, float* feats_out) {
       return 0;
     }
     SPM_GEMM_RUN_DIR(pl->outp[i]);
-    if (rb) SPM_KERNEL(k_layernorm_bf16in(st, h->xb, C, M, C, l.ln2_g, l.ln2_b, h->xn, C, next_dir()));
+    if (lf) {}
+    else if (rb) SPM_KERNEL(k_layernorm_bf16in(st, h->xb, C, M, C, l.ln2_g, l.ln2_b, h->xn, C, next_dir()));
     else SPM_KERNEL(k_layernorm(st, h->x, C, M, C, l.ln2_g, l.ln2_b, nullptr, 0, nullptr, h->xn, C, next_dir()));
     SPM_GEMM_RUN_DIR(pl->fc[i]);
     SPM_GEMM_RUN_DIR(pl->proj[i]);

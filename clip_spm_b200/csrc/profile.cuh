@@ -6,7 +6,7 @@
 namespace spm {
 void count_launch();
 // returns false when profiling is off or the record pool is exhausted
-bool profile_gemm_begin(cudaStream_t st, int tag, double flops, int* slot);
+bool profile_gemm_begin(cudaStream_t st, int tag, double flops, int* slot, int M = 0, int N = 0, int K = 0);
 void profile_gemm_end(cudaStream_t st, int slot);
 // true while GEMM launches are being event-timed: the encoder then keeps to one stream so that an event pair
 // brackets exactly one kernel (with two streams the other chunk's kernels would run inside the bracket)

@@ -1,6 +1,7 @@
 // Bandwidth-bound kernels around the frame-encoder GEMMs: weight packing, patch im2col, LayerNorm.
 // All are coalesced, 128-bit vectorised, one pass over their input.
 #include "kernels.cuh"
+#include "gemm.cuh"
 #include "profile.cuh"
 
 namespace spm {
@@ -113,7 +114,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ in, long long in_stride, int rows, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ cls_row, int cls_period,
-                 float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long long out_stride, int reverse) {
+                 float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long long out_stride, int reverse,
+                 float* __restrict__ stats_out) {
   constexpr int C = NV * 128;
   int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -157,7 +159,62 @@ layernorm_kernel(const float* __restrict__ in, long long in_stride, int rows, co
       u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
       *reinterpret_cast<uint2*>(out_bf16 + (long long)row * out_stride + col) = u;
     }
+    v[i] = o;
   }
+  if (stats_out != nullptr) {
+    // {sum y, sum y^2} of the OUTPUT row in partial-sum slot 0 (the other slots zero): statistics of the LayerNorm folded
+    // into the GEMM that reads this row next (GemmEpilogue::ln_stats_in)
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      t1 += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      t2 = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, t2))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+      t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    if (lane < LN_FOLD_SLOTS)
+      *reinterpret_cast<float2*>(stats_out + ((long long)row * LN_FOLD_SLOTS + lane) * 2) =
+          lane == 0 ? make_float2(t1, t2) : make_float2(0.f, 0.f);
+  }
+}
+
+// LayerNorm folded into the GEMM that follows it: W'[n,k] = bf16(W[n,k] * gamma[k]), colsum[n] = sum_k W'[n,k] (of the
+// ROUNDED weights, so that acc - mean * colsum == sum_k (x_k - mean) W'[n,k] exactly), bias'[n] = bias[n] + sum_k beta[k] W[n,k]
+__global__ void __launch_bounds__(256)
+fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ bias, int N, int K, __nv_bfloat16* __restrict__ Wf, float* __restrict__ colsum,
+               float* __restrict__ bias2, int center) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float c = 0.f, b = 0.f, wm = 0.f;
+  if (center) {   // centred rows: sum_k W'[n,k] = 0 in fp32, so the mean term of the LayerNorm drops out of the product
+    for (int k = lane; k < K; k += 32) wm += W[(long long)n * K + k] * gamma[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wm += __shfl_xor_sync(0xffffffffu, wm, o);
+    wm /= (float)K;
+  }
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[(long long)n * K + k];
+    const __nv_bfloat16 wf = __float2bfloat16_rn(w * gamma[k] - wm);
+    Wf[(long long)n * K + k] = wf;
+    c += __bfloat162float(wf);
+    b = fmaf(beta[k], w, b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) { colsum[n] = c; bias2[n] = bias[n] + b; }
+}
+int k_fold_ln(cudaStream_t st, const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
+              __nv_bfloat16* Wf, float* colsum, float* bias2, int center) {
+  fold_ln_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, gamma, beta, bias, N, K, Wf, colsum, bias2, center);
+  SPM_LAUNCH_CHECK();
+  return 0;
 }
 
 // same LayerNorm on a bf16 input row (the bf16 residual stream of SPM_PRECISION_BF16_RESID): 8 elements per 16-byte load,
@@ -226,12 +283,12 @@ int k_layernorm_bf16in(cudaStream_t st, const __nv_bfloat16* in, long long in_st
 
 int k_layernorm(cudaStream_t st, const float* in, long long in_stride, int rows, int C, const float* gamma,
                 const float* beta, const float* cls_row, int cls_period, float* out_f32, __nv_bfloat16* out_bf16,
-                long long out_stride, int reverse) {
+                long long out_stride, int reverse, float* stats_out) {
   const int blocks = (rows + 7) / 8;
   if (rows <= 0) return 0;
 #define SPM_LN(NV)                                                                                             \
   layernorm_kernel<NV><<<blocks, 256, 0, st>>>(in, in_stride, rows, gamma, beta, cls_row, cls_period, out_f32, \
-                                               out_bf16, out_stride, reverse)
+                                               out_bf16, out_stride, reverse, stats_out)
   switch (C) {
     case 512: SPM_LN(4); break;
     case 768: SPM_LN(6); break;
