@@ -36,6 +36,8 @@ class SpmConfig(ctypes.Structure):
         ("motion_coeff", c_float),
         ("normal_coeff", c_float),
         ("use_classification", c_int),
+        ("fsar_depth", c_int),
+        ("fsar_merge_before", c_int),
     ]
 
 

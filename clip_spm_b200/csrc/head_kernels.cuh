@@ -30,6 +30,8 @@ int k_finalize(cudaStream_t st, const float* accd, const float* d3, int E, int Q
 // ---- sibling head CLIP-FSAR (sibling_heads.cu; models/model_clipfsar.py:325-383)
 int k_fsar_seq_build(cudaStream_t st, const float* X, const float* text, int n_cls, const float* real_s, int E, int S,
                      int Q, int T, int D, float* seq);
+int k_fsar_merge_seq_build(cudaStream_t st, const float* X, const float* text, int n_cls, const float* labels,
+                           const float* real_s, int E, int S, int Q, int W, int T, int D, float* seq, int* err_flag);
 int k_fsar_class_mean(cudaStream_t st, const float* z, const float* labels, int E, int S, int W, int T, int D,
                       float* su_pro, int* err_flag);
 int k_fsar_class_logits(cudaStream_t st, const float* X, const float* text_train, int n_cls, const float* scale, int V,

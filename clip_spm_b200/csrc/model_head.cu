@@ -32,7 +32,11 @@ int load_ctx(spm_handle* h, cudaStream_t st, const WeightTable& wt, const std::s
 // CNN_OTAM_CLIPFSAR's own parameters (models/model_clipfsar.py:137-145): scale, context2 with inner width D
 int load_head_fsar(spm_handle* h, cudaStream_t st, const WeightTable& wt) {
   SPM_TRY(copy_f32(h, st, wt, "scale", 1, &h->fsar_scale));
-  return load_ctx(h, st, wt, "context2.layers.0.", h->D, &h->fsar_ctx);
+  SPM_TRY(load_ctx(h, st, wt, "context2.layers.0.", h->D, &h->fsar_ctx));
+  h->fsar_ctx_more.assign(std::max(h->cfg.fsar_depth, 1) - 1, CtxW{});
+  for (size_t i = 0; i < h->fsar_ctx_more.size(); ++i)
+    SPM_TRY(load_ctx(h, st, wt, "context2.layers." + std::to_string(i + 1) + ".", h->D, &h->fsar_ctx_more[i]));
+  return 0;
 }
 
 // CLIP_CPMMC_FSAR's parameters the forward reads (models/model_cpm2c.py:73-141): scale, context2 (inner width D), the
@@ -256,35 +260,54 @@ int sten_head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, co
 //   target  = context2(target)                       self-attention over the T frames of each query video
 //   support = context2(cat[support, prompt])[:, :T]  T frames + the class prompt of the video's real label
 //   prototypes = per-class mean;  logits = -(OTAM(d) + OTAM(d^T));  class_logits = cos_sim(mean_t feats, text_train)*scale
+// cfg.fsar_merge_before (:341-349): the per-class means move in front of context2 (E*W support sequences, their outputs are
+// the prototypes); cfg.fsar_depth (:143-144): context2 has that many layers, run back to back between SEQ and Z.
 int fsar_head_run(spm_handle* h, cudaStream_t st, int E, int S, int Q, int W, const float* labels, const float* real_s,
                   const float* real_t, const long long* target_labels, float tasks_per_batch, float* logits,
                   float* dists, float* loss, float* acc, int* pred) {
   SPM_CHECK(h->text_set, "head: text features not set (spm_set_text_features)");
   SPM_TRY(ensure_head_workspace(h, E, S, Q, W));
   const int T = h->cfg.seq_len, D = h->D, N = S + Q, V = E * N, dh = D / HEAD_HEADS;
-  const long long RS = (long long)E * S * (T + 1), R = RS + (long long)E * Q * T, TD = (long long)T * D;
+  const bool merge = h->cfg.fsar_merge_before != 0;
+  const int depth = 1 + (int)h->fsar_ctx_more.size();
+  const int SB = merge ? W : S;   // support sequences per episode that go through context2
+  const long long RS = (long long)E * SB * (T + 1), R = RS + (long long)E * Q * T, TD = (long long)T * D;
   FsarPlan* pl = nullptr;
   for (auto& p : h->fsar_plans)
-    if (p->E == E && p->S == S && p->Q == Q) pl = p.get();
+    if (p->E == E && p->S == S && p->Q == Q && p->W == W) pl = p.get();
   if (pl == nullptr) {
     std::unique_ptr<FsarPlan> np(new FsarPlan());
-    np->E = E; np->S = S; np->Q = Q;
-    SPM_TRY(plan_ctx(h, &np->c2, h->fsar_ctx, (int)R, h->SEQ, h->Z, D));
+    np->E = E; np->S = S; np->Q = Q; np->W = W;
+    np->c2.resize(depth);
+    for (int l = 0; l < depth; ++l)   // layer l reads buf[l % 2], writes buf[(l + 1) % 2]  (buf = {SEQ, Z})
+      SPM_TRY(plan_ctx(h, &np->c2[l], l == 0 ? h->fsar_ctx : h->fsar_ctx_more[l - 1], (int)R, l % 2 ? h->Z : h->SEQ,
+                       l % 2 ? h->SEQ : h->Z, D));
     pl = np.get();
     h->fsar_plans.push_back(std::move(np));
   }
-  const CtxW& w = h->fsar_ctx;
-  SPM_KERNEL(k_fsar_seq_build(st, h->X, h->text, h->n_cls, real_s, E, S, Q, T, D, h->SEQ));
-  SPM_KERNEL(k_layernorm(st, h->SEQ, D, (int)R, D, w.ln_g, w.ln_b, nullptr, 0, h->HN, nullptr, D));
-  SPM_GEMM_RUN(pl->c2.qkv);
-  SPM_KERNEL(k_seq_attention(st, h->QKVH, h->AO, E * S, T + 1, 1, 0, T + 1, 0, 0, HEAD_HEADS, dh));
-  SPM_KERNEL(k_seq_attention(st, h->QKVH + RS * 3 * D, h->AO + RS * D, E * Q, T, 1, 0, T, 0, 0, HEAD_HEADS, dh));
-  SPM_GEMM_RUN(pl->c2.outp);
-  SPM_GEMM_RUN(pl->c2.ff0);
-  SPM_GEMM_RUN(pl->c2.ff3);
-  SPM_KERNEL(k_fsar_class_mean(st, h->Z, labels, E, S, W, T, D, h->SUPRO, h->err_flag));
-  SPM_KERNEL(k_otam(st, h->SUPRO, (long long)W * TD, TD, D, h->Z + RS * D, (long long)Q * TD, TD, D, E, W, Q, T, D,
-                    h->cfg.single_direct, 1.f, 0.f, h->ACC));
+  if (merge)
+    SPM_KERNEL(k_fsar_merge_seq_build(st, h->X, h->text, h->n_cls, labels, real_s, E, S, Q, W, T, D, h->SEQ, h->err_flag));
+  else
+    SPM_KERNEL(k_fsar_seq_build(st, h->X, h->text, h->n_cls, real_s, E, S, Q, T, D, h->SEQ));
+  for (int l = 0; l < depth; ++l) {
+    const CtxW& w = l == 0 ? h->fsar_ctx : h->fsar_ctx_more[l - 1];
+    SPM_KERNEL(k_layernorm(st, l % 2 ? h->Z : h->SEQ, D, (int)R, D, w.ln_g, w.ln_b, nullptr, 0, h->HN, nullptr, D));
+    SPM_GEMM_RUN(pl->c2[l].qkv);
+    SPM_KERNEL(k_seq_attention(st, h->QKVH, h->AO, E * SB, T + 1, 1, 0, T + 1, 0, 0, HEAD_HEADS, dh));
+    SPM_KERNEL(k_seq_attention(st, h->QKVH + RS * 3 * D, h->AO + RS * D, E * Q, T, 1, 0, T, 0, 0, HEAD_HEADS, dh));
+    SPM_GEMM_RUN(pl->c2[l].outp);
+    SPM_GEMM_RUN(pl->c2[l].ff0);
+    SPM_GEMM_RUN(pl->c2[l].ff3);
+  }
+  const float* Zout = depth % 2 ? h->Z : h->SEQ;
+  if (merge) {   // the class sequences' frame rows are the prototypes: rows 1..T of each (T+1)-row sequence
+    SPM_KERNEL(k_otam(st, Zout + D, (long long)W * (T + 1) * D, (long long)(T + 1) * D, D, Zout + RS * D,
+                      (long long)Q * TD, TD, D, E, W, Q, T, D, h->cfg.single_direct, 1.f, 0.f, h->ACC));
+  } else {
+    SPM_KERNEL(k_fsar_class_mean(st, Zout, labels, E, S, W, T, D, h->SUPRO, h->err_flag));
+    SPM_KERNEL(k_otam(st, h->SUPRO, (long long)W * TD, TD, D, Zout + RS * D, (long long)Q * TD, TD, D, E, W, Q, T, D,
+                      h->cfg.single_direct, 1.f, 0.f, h->ACC));
+  }
   SPM_CUDA(cudaMemsetAsync(h->D3, 0, (size_t)E * W * sizeof(float), st));
   SPM_CUDA(cudaMemsetAsync(dists, 0, (size_t)E * sizeof(float), st));   // this head has no auxiliary distance
   h->cls_rows = 0;

@@ -103,9 +103,9 @@ struct Cpm2cPlan {   // sibling head CPM2C: motion fusion GEMMs, gates and one c
   GemmOp gv0[2], gv2[2];
   CtxPlan c2[2];
 };
-struct FsarPlan {   // sibling head CLIP-FSAR: one context2 pass over E*S*(T+1) + E*Q*T rows
-  int E, S, Q;
-  CtxPlan c2;
+struct FsarPlan {   // sibling head CLIP-FSAR: context2 (one plan per layer) over E*S*(T+1) + E*Q*T rows (E*W with MERGE_BEFORE)
+  int E, S, Q, W;
+  std::vector<CtxPlan> c2;
 };
 struct HeadPlan {
   int E, S, Q, W;
@@ -170,7 +170,8 @@ struct spm_handle {
   int last_E = 0, last_S = 0, last_Q = 0, last_W = 0;   // shape of the most recent CLIP-SPM head pass (spm_head_stage)
   std::vector<std::unique_ptr<spm::HeadPlan>> head_plans;
   // sibling head CLIP-FSAR (cfg.head == SPM_HEAD_CLIPFSAR; models/model_clipfsar.py)
-  spm::CtxW fsar_ctx = {};
+  spm::CtxW fsar_ctx = {};                 // context2.layers.0 (shared with the CPM2C head)
+  std::vector<spm::CtxW> fsar_ctx_more;    // context2.layers.1.. (cfg.fsar_depth > 1, model_clipfsar.py:143-144)
   float* fsar_scale = nullptr;
   float* text_train = nullptr;   // [n_cls_train, D] text_features_train (class_text_logits)
   int n_cls_train = 0;

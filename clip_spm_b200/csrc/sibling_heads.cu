@@ -49,6 +49,61 @@ int k_fsar_seq_build(cudaStream_t st, const float* X, const float* text, int n_c
 }
 
 // ------------------------------------------------------------------------------------------------------
+// MODEL.MERGE_BEFORE (model_clipfsar.py:341-348): the class means are taken BEFORE context2 -- of the support frames and
+// of the supports' prompts -- so the support batch is E*W sequences of (mean prompt, T mean frames):
+//   class sequence cw = e*W + w : rows cw*(T+1) + {0: mean_s text[real_s[s]], 1+t: mean_s X[e,s,t]},  s in class w
+//   query video   qv = e*Q + q : rows E*W*(T+1) + qv*T + t = X[e,S+q,t]
+// grid (E*(W+Q), T+1); class w = rank among the episode's sorted distinct labels (torch.unique, :342)
+// ------------------------------------------------------------------------------------------------------
+__global__ void fsar_merge_seq_build_kernel(const float* __restrict__ X, const float* __restrict__ text, int n_cls,
+                                            const float* __restrict__ labels, const float* __restrict__ real_s, int E,
+                                            int S, int Q, int W, int T, int D, float* __restrict__ seq,
+                                            int* __restrict__ err_flag) {
+  __shared__ int cls[256];
+  const int e = blockIdx.x / (W + Q), i = blockIdx.x % (W + Q), r = blockIdx.y, N = S + Q, d4 = D / 4;
+  if (i >= W) {   // query rows are copied; (T+1)-th grid row has nothing to do
+    if (r >= T) return;
+    const float4* src = reinterpret_cast<const float4*>(X + (((long long)e * N + S + (i - W)) * T + r) * D);
+    float4* dst = reinterpret_cast<float4*>(seq + ((long long)E * W * (T + 1) + ((long long)e * Q + (i - W)) * T + r) * D);
+    for (int k = threadIdx.x; k < d4; k += blockDim.x) dst[k] = src[k];
+    return;
+  }
+  const int Wd = class_indices(labels + (long long)e * S, S, cls);
+  if (Wd != W) {
+    if (threadIdx.x == 0 && r == 0 && i == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  float4* dst = reinterpret_cast<float4*>(seq + (((long long)e * W + i) * (T + 1) + r) * D);
+  for (int k = threadIdx.x; k < d4; k += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    for (int s = 0; s < S; ++s)
+      if (cls[s] == i) {
+        const float* row;
+        if (r == 0) {
+          const int c = min(max((int)real_s[(long long)e * S + s], 0), n_cls - 1);
+          row = text + (long long)c * D;
+        } else {
+          row = X + (((long long)e * N + s) * T + (r - 1)) * D;
+        }
+        const float4 v = reinterpret_cast<const float4*>(row)[k];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        ++cnt;
+      }
+    const float inv = 1.f / (float)max(cnt, 1);
+    dst[k] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
+}
+int k_fsar_merge_seq_build(cudaStream_t st, const float* X, const float* text, int n_cls, const float* labels,
+                           const float* real_s, int E, int S, int Q, int W, int T, int D, float* seq, int* err_flag) {
+  if (S > 256) return -2;
+  dim3 grid(E * (W + Q), T + 1);
+  fsar_merge_seq_build_kernel<<<grid, 128, 0, st>>>(X, text, n_cls, labels, real_s, E, S, Q, W, T, D, seq, err_flag);
+  SPM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // class prototypes (model_clipfsar.py:352-354): su_pro[e,w,t] = mean_{s in class w} z[(e*S+s)*(T+1) + 1 + t]
 // ------------------------------------------------------------------------------------------------------
 __global__ void fsar_class_mean_kernel(const float* __restrict__ z, const float* __restrict__ labels, int S, int W,

@@ -23,21 +23,24 @@ def _p(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
-def _fsar_head_shapes(D):
+def _fsar_head_shapes(D, depth=1):
     """Parameters of models/model_clipfsar.py::CNN_OTAM_CLIPFSAR besides the backbone (:137-145): `scale` and
-    context2 = Transformer_v1(dim=D, heads=8, dim_head_k=D//8): inner width D, mlp 2048."""
-    p = "context2.layers.0."
-    return {"scale": (1,), p + "0.norm.weight": (D,), p + "0.norm.bias": (D,), p + "0.fn.to_q.weight": (D, D),
-            p + "0.fn.to_k.weight": (D, D), p + "0.fn.to_v.weight": (D, D), p + "0.fn.to_out.0.weight": (D, D),
-            p + "0.fn.to_out.0.bias": (D,), p + "1.net.0.weight": (2048, D), p + "1.net.0.bias": (2048,),
-            p + "1.net.3.weight": (D, 2048), p + "1.net.3.bias": (D,)}
+    context2 = Transformer_v1(dim=D, heads=8, dim_head_k=D//8[, depth]): inner width D, mlp 2048."""
+    s = {"scale": (1,)}
+    for i in range(depth):
+        p = "context2.layers.%d." % i
+        s.update({p + "0.norm.weight": (D,), p + "0.norm.bias": (D,), p + "0.fn.to_q.weight": (D, D),
+                  p + "0.fn.to_k.weight": (D, D), p + "0.fn.to_v.weight": (D, D), p + "0.fn.to_out.0.weight": (D, D),
+                  p + "0.fn.to_out.0.bias": (D,), p + "1.net.0.weight": (2048, D), p + "1.net.0.bias": (2048,),
+                  p + "1.net.3.weight": (D, 2048), p + "1.net.3.bias": (D,)})
+    return s
 
 
-def _param_shapes(backbone, D, params, head="clipspm"):
+def _param_shapes(backbone, D, params, head="clipspm", depth=1):
     """Names and shapes of the reference CNN's parameters/buffers (models/model_clipspm.py:72-99 and the CLIP visual
     tower of models/clip_fsar.py:549-689), written out here from the module definitions."""
     if head == "clipfsar":
-        s = _fsar_head_shapes(D)
+        s = _fsar_head_shapes(D, depth)
     elif head == "cpm2c":
         s = _cpm2c_head_shapes(D, params)
     elif head == "sten":
@@ -198,7 +201,14 @@ class CNN(nn.Module):
         self.max_episodes = int(max_episodes)
         self._dev = torch.device(device)
         self.cls_value = float(_cfg_get(cfg, "MODEL.USE_CLASSIFICATION_VALUE", 0.0) or 0.0)
-        for name, shape in _param_shapes(self.backbone_name, self.mid_dim, self.params, self.HEAD).items():
+        # CLIP-FSAR only (models/model_clipfsar.py:143-144, :341): MODEL.TRANSFORMER_DEPTH is the switch, TRAIN.TRANSFORMER_DEPTH
+        # the value the constructor reads; MODEL.MERGE_BEFORE averages each class before context2
+        self.transformer_depth = 1
+        if self.HEAD == "clipfsar" and _cfg_get(cfg, "MODEL.TRANSFORMER_DEPTH", None):
+            self.transformer_depth = int(_cfg_get(cfg, "TRAIN.TRANSFORMER_DEPTH"))
+        self.merge_before = self.HEAD == "clipfsar" and bool(_cfg_get(cfg, "MODEL.MERGE_BEFORE", False))
+        for name, shape in _param_shapes(self.backbone_name, self.mid_dim, self.params, self.HEAD,
+                                         self.transformer_depth).items():
             if shape is None:
                 _register(self, name, torch.zeros((), dtype=torch.long), buffer=True)
             elif name.split(".")[-1] in ("running_mean", "running_var"):

@@ -6,8 +6,11 @@ library -- SURVEY.md 8(f) rank 4 ("sibling heads reusing the same kernels").
     :183 forward(inputs) -> {"logits", "class_logits"}      forward(inputs) -> same keys ([1,Q,W], [1,S+Q,n_train])
     run/main_run.py:355-359 loss / accuracy                  evaluate(inputs) -> loss, accuracy
 
-The branch implemented is the one every shipped config takes (configs/clipfsar/*.yaml: no EVAL_TEXT / COMBINE /
-MERGE_BEFORE / TRANSFORMER_DEPTH): model_clipfsar.py:325-383.  `state_dict()` has the reference's keys (`scale`,
+The branch implemented is the one every shipped config takes (configs/clipfsar/*.yaml), model_clipfsar.py:325-383, with
+its two working options: MODEL.TRANSFORMER_DEPTH (:143-144, layers of context2; the count is TRAIN.TRANSFORMER_DEPTH) and
+MODEL.MERGE_BEFORE (:341-346, class means before context2).  MODEL.EVAL_TEXT and MODEL.COMBINE (:235-322) end in
+`None.unsqueeze(0)` (:384) in the reference -- executed and recorded by oracle/pin_against_reference.py
+fsar_dead_branches -- so this class raises for them as well.  `state_dict()` has the reference's keys (`scale`,
 `context2.layers.0.*` with inner width D, `backbone.*`).  cfg additionally reads MODEL.USE_CLASSIFICATION_VALUE and
 TRAIN.TASKS_PER_BATCH for the loss.  No CPU / eager fallback (see model.py)."""
 import ctypes
@@ -15,7 +18,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .model import CNN, _p
+from .model import CNN, _cfg_get, _p
 
 
 class CNN_OTAM_CLIPFSAR(CNN):
@@ -26,6 +29,14 @@ class CNN_OTAM_CLIPFSAR(CNN):
         super().__init__(cfg, text_features_test=text_features_test, text_features_train=text_features_train,
                          max_episodes=max_episodes, device=device, precision=precision)
         self._packed_train = None
+        for flag in ("EVAL_TEXT", "COMBINE"):
+            if _cfg_get(cfg, "MODEL." + flag, False):
+                raise AttributeError("MODEL.%s: the reference's branch ends in `class_text_logits = None; "
+                                     "class_text_logits.unsqueeze(0)` (models/model_clipfsar.py:322,384) and never "
+                                     "returns; not part of the path" % flag)
+
+    def _extra_config(self):
+        return dict(fsar_depth=self.transformer_depth, fsar_merge_before=int(self.merge_before))
 
     def _text(self):
         tf = super()._text()   # evaluation: prompts come from text_features_test (model_clipfsar.py:338)

@@ -33,10 +33,11 @@
 extern "C" {
 #endif
 
-#define SPM_ABI_VERSION 5 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
+#define SPM_ABI_VERSION 6 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
                            * 3: spm_head_stage (per-stage taps for the parity tests)
                            * 4: spm_jpeg_info / spm_jpeg_decode, spm_eval_u8
-                           * 5: SPM_HEAD_CPM2C: spm_config gained its parameters; spm_cpm2c_outputs */
+                           * 5: SPM_HEAD_CPM2C: spm_config gained its parameters; spm_cpm2c_outputs
+                           * 6: spm_config gained fsar_depth, fsar_merge_before (CLIP-FSAR's optional branches) */
 
 typedef struct spm_handle spm_handle;
 
@@ -78,6 +79,11 @@ typedef struct spm_config {
   float motion_coeff;   /* cfg.MODEL.MOTION_COFF                                        model_cpm2c.py:87      */
   float normal_coeff;   /* cfg.MODEL.NORMAL_COFF                                        model_cpm2c.py:88      */
   int use_classification; /* cfg.MODEL.USE_CLASSIFICATION (class_logits branch)          model_cpm2c.py:426     */
+  /* SPM_HEAD_CLIPFSAR only (ABI 6); 0 reads as the default (one layer, no merge) */
+  int fsar_depth;       /* layers of context2: cfg.TRAIN.TRANSFORMER_DEPTH when cfg.MODEL.TRANSFORMER_DEPTH is set
+                         *                                                            model_clipfsar.py:143-144 */
+  int fsar_merge_before; /* cfg.MODEL.MERGE_BEFORE: class means of frames and prompts BEFORE context2
+                         *                                                            model_clipfsar.py:341-349 */
 } spm_config;
 
 const char* spm_last_error(void);

@@ -138,19 +138,22 @@ def feed_forward(x, w, p):
     return h @ w[p + "net.3.weight"].t() + w[p + "net.3.bias"]
 
 
-def transformer_v1(x, w, p, heads=8, dim_head=256):
-    """models/myRes.py:1066-1075 Transformer_v1.forward with q=k=v=x, depth 1:
+def transformer_v1(x, w, p, heads=8, dim_head=256, depth=1):
+    """models/myRes.py:1066-1075 Transformer_v1.forward with q=k=v=x:
     PreNormattention_qkv (:1039-1040, the SAME LayerNorm on q,k,v, residual is the un-normalised q),
-    Attention_qkv.forward (:964-982), then x = ff(x) + x."""
+    Attention_qkv.forward (:964-982), then x = ff(x) + x; layers 1.. (depth > 1, :1070-1073) repeat it on the output."""
     B, n, _ = x.shape
-    h = layer_norm(x, w[p + "layers.0.0.norm.weight"], w[p + "layers.0.0.norm.bias"])
-    q = (h @ w[p + "layers.0.0.fn.to_q.weight"].t()).view(B, n, heads, dim_head).transpose(1, 2)
-    k = (h @ w[p + "layers.0.0.fn.to_k.weight"].t()).view(B, n, heads, dim_head).transpose(1, 2)
-    v = (h @ w[p + "layers.0.0.fn.to_v.weight"].t()).view(B, n, heads, dim_head).transpose(1, 2)
-    att = torch.softmax((q @ k.transpose(-1, -2)) * dim_head ** -0.5, dim=-1)
-    o = (att @ v).transpose(1, 2).reshape(B, n, heads * dim_head)
-    y = o @ w[p + "layers.0.0.fn.to_out.0.weight"].t() + w[p + "layers.0.0.fn.to_out.0.bias"] + x
-    return feed_forward(y, w, p + "layers.0.1.") + y
+    for i in range(depth):
+        l = p + "layers.%d." % i
+        h = layer_norm(x, w[l + "0.norm.weight"], w[l + "0.norm.bias"])
+        q = (h @ w[l + "0.fn.to_q.weight"].t()).view(B, n, heads, dim_head).transpose(1, 2)
+        k = (h @ w[l + "0.fn.to_k.weight"].t()).view(B, n, heads, dim_head).transpose(1, 2)
+        v = (h @ w[l + "0.fn.to_v.weight"].t()).view(B, n, heads, dim_head).transpose(1, 2)
+        att = torch.softmax((q @ k.transpose(-1, -2)) * dim_head ** -0.5, dim=-1)
+        o = (att @ v).transpose(1, 2).reshape(B, n, heads * dim_head)
+        y = o @ w[l + "0.fn.to_out.0.weight"].t() + w[l + "0.fn.to_out.0.bias"] + x
+        x = feed_forward(y, w, l + "1.") + y
+    return x
 
 
 def motion_feats(x, w):
@@ -290,24 +293,25 @@ def forward(w, text_features, inputs, cfg):
 # =====================================================================================================
 # sibling head: CLIP-FSAR (models/model_clipfsar.py) -- SURVEY.md 8(f) rank 4, same kernels, other wiring
 # =====================================================================================================
-def fsar_weight_shapes(D):
+def fsar_weight_shapes(D, depth=1):
     """Parameters of CNN_OTAM_CLIPFSAR besides the backbone (models/model_clipfsar.py:137-145): `scale` and
-    context2 = Transformer_v1(dim=D, heads=8, dim_head_k=D//8) -> inner width D, mlp 2048."""
-    c = "context2."
-    return {"scale": (1,),
-            c + "layers.0.0.norm.weight": (D,), c + "layers.0.0.norm.bias": (D,),
-            c + "layers.0.0.fn.to_q.weight": (D, D), c + "layers.0.0.fn.to_k.weight": (D, D),
-            c + "layers.0.0.fn.to_v.weight": (D, D),
-            c + "layers.0.0.fn.to_out.0.weight": (D, D), c + "layers.0.0.fn.to_out.0.bias": (D,),
-            c + "layers.0.1.net.0.weight": (2048, D), c + "layers.0.1.net.0.bias": (2048,),
-            c + "layers.0.1.net.3.weight": (D, 2048), c + "layers.0.1.net.3.bias": (D,)}
+    context2 = Transformer_v1(dim=D, heads=8, dim_head_k=D//8[, depth]) -> inner width D, mlp 2048."""
+    s = {"scale": (1,)}
+    for i in range(depth):
+        c = "context2.layers.%d." % i
+        s.update({c + "0.norm.weight": (D,), c + "0.norm.bias": (D,),
+                  c + "0.fn.to_q.weight": (D, D), c + "0.fn.to_k.weight": (D, D), c + "0.fn.to_v.weight": (D, D),
+                  c + "0.fn.to_out.0.weight": (D, D), c + "0.fn.to_out.0.bias": (D,),
+                  c + "1.net.0.weight": (2048, D), c + "1.net.0.bias": (2048,),
+                  c + "1.net.3.weight": (D, 2048), c + "1.net.3.bias": (D,)})
+    return s
 
 
-def make_fsar_weights(D, seed=0, scale=1.7):
+def make_fsar_weights(D, seed=0, scale=1.7, depth=1):
     """Seeded head weights of the CLIP-FSAR sibling (per-tensor generators, like make_weights; the generator key
     carries an 'fsar.' prefix so these never alias CLIP-SPM's context2 of another shape)."""
     w = {}
-    for name, shp in fsar_weight_shapes(D).items():
+    for name, shp in fsar_weight_shapes(D, depth).items():
         leaf = name.split(".")[-1]
         if name == "scale":
             w[name] = torch.full((1,), float(scale))
@@ -321,18 +325,21 @@ def make_fsar_weights(D, seed=0, scale=1.7):
 
 
 def fsar_head_forward(w, text_test, text_train, su, qu, support_labels, real_support, real_target,
-                      single_direct=False):
-    """models/model_clipfsar.py:325-381, the evaluation branch taken with the shipped configs (no EVAL_TEXT /
-    COMBINE / MERGE_BEFORE; configs/clipfsar/*.yaml): su [S,T,D], qu [Q,T,D] -> logits [1,Q,W],
-    class_logits [1,S+Q,n_train]."""
+                      single_direct=False, merge_before=False, depth=1):
+    """models/model_clipfsar.py:325-381, the evaluation branch that works (EVAL_TEXT / COMBINE end in
+    `None.unsqueeze(0)`, :384): su [S,T,D], qu [Q,T,D] -> logits [1,Q,W], class_logits [1,S+Q,n_train].
+    merge_before (MODEL.MERGE_BEFORE, :341-346): class means of the frames and of the prompts BEFORE context2 instead of
+    class means of its outputs; depth (MODEL/TRAIN.TRANSFORMER_DEPTH, :143-144): layers of context2."""
     S, T, D = su.shape
     dh = D // 8
     feat_cls = torch.cat([su, qu], dim=0).mean(1)                      # :329-330 (classification_layer is empty)
     class_logits = cos_sim(feat_cls, text_train) * w["scale"]          # :331
     ctx = text_test[real_support.long()].unsqueeze(1)                  # :338
-    qu2 = transformer_v1(qu, w, "context2.", heads=8, dim_head=dh)     # :340
-    su2 = transformer_v1(torch.cat([su, ctx], dim=1), w, "context2.", heads=8, dim_head=dh)[:, :T]   # :347-348
-    su_pro = class_means(su2, support_labels)                          # :352-354
+    qu2 = transformer_v1(qu, w, "context2.", heads=8, dim_head=dh, depth=depth)     # :340
+    if merge_before:
+        su, ctx = class_means(su, support_labels), class_means(ctx, support_labels)  # :341-346
+    su2 = transformer_v1(torch.cat([su, ctx], dim=1), w, "context2.", heads=8, dim_head=dh, depth=depth)[:, :T]   # :347-348
+    su_pro = su2 if merge_before else class_means(su2, support_labels)               # :349-354
     cum = otam_distance(su_pro, qu2, single_direct)                    # :360-375
     # :381-383: per-class mean over the (already one-per-class) prototype columns, transposed back -> identity
     return dict(qu_ctx=qu2, su_ctx=su2, su_pro=su_pro, logits=-cum.unsqueeze(0), class_logits=class_logits.unsqueeze(0))

@@ -235,7 +235,11 @@ FSAR_CASES = {
     "fsar_head_5w3s_t8_d1024_q2": ("RN50", 5, 3, 2, 8, 10, 12, True, False, 2004),
     "fsar_head_5w1s_t16_single": ("ViT-B/16", 5, 1, 1, 16, 24, 30, True, True, 2005),
     "fsar_vit_2w1s_t2_p1": ("ViT-B/16", 2, 1, 1, 2, 24, 30, False, False, 2001),
+    # the two optional branches that work in the reference (EVAL_TEXT / COMBINE raise at model_clipfsar.py:384)
+    "fsar_head_5w3s_t8_merge": ("ViT-B/16", 5, 3, 1, 8, 24, 30, True, False, 2006),      # MODEL.MERGE_BEFORE
+    "fsar_head_5w2s_t8_depth2": ("ViT-B/16", 5, 2, 2, 8, 24, 30, True, False, 2007),     # TRANSFORMER_DEPTH = 2
 }
+FSAR_OPTIONS = {"fsar_head_5w3s_t8_merge": dict(merge_before=True), "fsar_head_5w2s_t8_depth2": dict(depth=2)}
 FSAR_TASKS_PER_BATCH, FSAR_CLS_VALUE = 4, 3.0   # configs/clipfsar/ssv2_otam.yaml: TASKS_PER_BATCH, USE_CLASSIFICATION_VALUE
 
 
@@ -260,10 +264,16 @@ def run_fsar_case(m, name):
              DATA=NS(SEQ_LEN=T), DEVICE=NS(NUM_GPUS=1))
     if single:
         cfg.MODEL.SINGLE_DIRECT = True
+    opt = FSAR_OPTIONS.get(name, {})
+    if opt.get("merge_before"):
+        cfg.MODEL.MERGE_BEFORE = True
+    if opt.get("depth", 1) > 1:
+        cfg.MODEL.TRANSFORMER_DEPTH = opt["depth"]   # the flag (model_clipfsar.py:143) ...
+        cfg.TRAIN.TRANSFORMER_DEPTH = opt["depth"]   # ... and the value the constructor actually reads (:144)
     torch.manual_seed(0)
     with torch.no_grad():
         net = f.CNN_OTAM_CLIPFSAR(cfg).eval()
-    w = O.make_fsar_weights(D, seed=0)
+    w = O.make_fsar_weights(D, seed=0, depth=opt.get("depth", 1))
     if not head_only:
         w.update({k: v for k, v in O.make_weights(backbone, seed=0, protocol="P1").items() if k.startswith("backbone.")})
     missing, unexpected = net.load_state_dict(w, strict=False)
@@ -298,7 +308,7 @@ def run_fsar_case(m, name):
             mine_qu = enc(w, ep["target_images"]).reshape(-1, T, D)
             assert rel(mine_su, su) < 2e-4 and rel(mine_qu, qu) < 2e-4
         st = O.fsar_head_forward(w, text_test, text_train, su, qu, ep["context_labels"], ep["real_support_labels"],
-                                 ep["real_target_labels"], single)
+                                 ep["real_target_labels"], single, **opt)
     st_ref["qu_ctx"], st_ref["su_ctx"] = ctx_calls[0], ctx_calls[1][:, :T]
     st_ref["logits"], st_ref["class_logits"] = out["logits"], out["class_logits"]
     for mod in ("matplotlib", "matplotlib.pyplot"):
@@ -327,6 +337,34 @@ def run_fsar_case(m, name):
     gold["pred"] = lg.argmax(-1).numpy()
     gold["margin"] = margin.numpy()
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
+
+
+def run_fsar_dead_branches(m):
+    """MODEL.EVAL_TEXT and MODEL.COMBINE (model_clipfsar.py:235-322) both finish with `class_text_logits = None` and then
+    `class_text_logits.unsqueeze(0)` at :384: executed here to record that they raise, i.e. are not part of the path."""
+    f = import_reference_fsar(m)
+    D, T = 512, 8
+    for flag in ("EVAL_TEXT", "COMBINE"):
+        cfg = NS(MODEL=NS(BACKBONE="ViT-B/16"), TRAIN=NS(CLASS_NAME=["run"]), TEST=NS(CLASS_NAME=["run"]),
+                 DATA=NS(SEQ_LEN=T), DEVICE=NS(NUM_GPUS=1))
+        setattr(cfg.MODEL, flag, True)
+        torch.manual_seed(0)
+        with torch.no_grad():
+            net = f.CNN_OTAM_CLIPFSAR(cfg).eval()
+        net.load_state_dict(O.make_fsar_weights(D, seed=0), strict=False)
+        net.text_features_test, net.text_features_train = O.make_text_features(24, D, seed=0), O.make_text_features(30, D, seed=1)
+        ep = O.make_episode(2002, 5, 1, 1, T, 24, "P1", images=False)
+        su, qu = O.make_features(2002, 5, 5, T, D, ep["context_labels"], ep["target_labels"].float())
+        text = net.text_features_test[ep["real_support_labels"].long()]
+        net.get_feats = lambda *a, **k: (su, qu, text)
+        ep["context_images"] = ep["target_images"] = torch.zeros(1)
+        try:
+            with torch.no_grad():
+                net(ep)
+        except AttributeError as e:
+            print("%-28s reference raises %s: %s" % ("fsar MODEL." + flag, type(e).__name__, e))
+        else:
+            raise AssertionError("MODEL.%s unexpectedly works in the reference" % flag)
 
 
 STEN_CASES = {
@@ -523,10 +561,12 @@ def run_softdtw_case(name):
 
 if __name__ == "__main__":
     m = import_reference()
-    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + list(STEN_CASES) + list(CPM2C_CASES) + list(SOFTDTW_CASES))
+    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + ["fsar_dead_branches"] + list(STEN_CASES) + list(CPM2C_CASES) + list(SOFTDTW_CASES))
     for n in names:
         if n == "text":
             run_text_case(m)
+        elif n == "fsar_dead_branches":
+            run_fsar_dead_branches(m)
         elif n == "otam_grad":
             run_otam_grad_case(m)
         elif n in FSAR_CASES:

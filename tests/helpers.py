@@ -70,14 +70,18 @@ FSAR_CASES = {
     "fsar_head_5w3s_t8_d1024_q2": ("RN50", 5, 3, 2, 8, 10, 12, True, False, 2004),
     "fsar_head_5w1s_t16_single": ("ViT-B/16", 5, 1, 1, 16, 24, 30, True, True, 2005),
     "fsar_vit_2w1s_t2_p1": ("ViT-B/16", 2, 1, 1, 2, 24, 30, False, False, 2001),
+    "fsar_head_5w3s_t8_merge": ("ViT-B/16", 5, 3, 1, 8, 24, 30, True, False, 2006),      # MODEL.MERGE_BEFORE
+    "fsar_head_5w2s_t8_depth2": ("ViT-B/16", 5, 2, 2, 8, 24, 30, True, False, 2007),     # TRANSFORMER_DEPTH = 2
 }
+FSAR_OPTIONS = {"fsar_head_5w3s_t8_merge": dict(merge_before=True), "fsar_head_5w2s_t8_depth2": dict(depth=2)}
 FSAR_TASKS_PER_BATCH, FSAR_CLS_VALUE = 4, 3.0
 
 
 def fsar_case_inputs(name):
     backbone, way, shot, qpc, T, ncls, ntrain, head_only, single, seed = FSAR_CASES[name]
     D = 512 if backbone == "ViT-B/16" else 1024
-    w = O.make_fsar_weights(D, seed=0)
+    opt = FSAR_OPTIONS.get(name, {})
+    w = O.make_fsar_weights(D, seed=0, depth=opt.get("depth", 1))
     if not head_only:
         w.update({k: v for k, v in O.make_weights(backbone, seed=0, protocol="P1").items() if k.startswith("backbone.")})
     ep = O.make_episode(seed, way, shot, qpc, T, ncls, "P1", images=not head_only)
@@ -86,7 +90,7 @@ def fsar_case_inputs(name):
         feats = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
     return dict(backbone=backbone, way=way, shot=shot, qpc=qpc, T=T, D=D, weights=w, episode=ep, feats=feats,
                 text=O.make_text_features(ncls, D, seed=0), text_train=O.make_text_features(ntrain, D, seed=1),
-                single=single, head_only=head_only)
+                single=single, head_only=head_only, options=opt)
 
 
 def build_cuda_fsar_model(ci, max_episodes=1, precision="bf16"):
@@ -94,6 +98,12 @@ def build_cuda_fsar_model(ci, max_episodes=1, precision="bf16"):
     from clip_spm_b200.config import make_cfg as _mk
     cfg = _mk(ci["backbone"], ci["T"], ci["single"], ci["way"], params={}, tasks_per_batch=FSAR_TASKS_PER_BATCH,
               cls_value=FSAR_CLS_VALUE)
+    opt = ci.get("options", {})
+    if opt.get("merge_before"):
+        cfg.MODEL.MERGE_BEFORE = True
+    if opt.get("depth", 1) > 1:   # the switch and the value the reference constructor reads (model_clipfsar.py:143-144)
+        cfg.MODEL.TRANSFORMER_DEPTH = opt["depth"]
+        cfg.TRAIN.TRANSFORMER_DEPTH = opt["depth"]
     net = CNN_OTAM_CLIPFSAR(cfg, text_features_test=ci["text"], text_features_train=ci["text_train"],
                             max_episodes=max_episodes, precision=precision)
     missing, unexpected = net.load_state_dict(ci["weights"], strict=False)

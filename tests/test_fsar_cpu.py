@@ -15,7 +15,7 @@ def test_oracle_fsar_head_matches_reference_golden(name):
     su, qu = ci["feats"] if ci["head_only"] else (g["su"], g["qu"])
     with torch.no_grad():
         st = O.fsar_head_forward(ci["weights"], ci["text"], ci["text_train"], su, qu, ep["context_labels"],
-                                 ep["real_support_labels"], ep["real_target_labels"], ci["single"])
+                                 ep["real_support_labels"], ep["real_target_labels"], ci["single"], **ci["options"])
     for k in ("qu_ctx", "su_ctx", "logits", "class_logits"):
         assert H.rel_err(st[k].reshape(g[k].shape), g[k]) < 1e-4, k
     loss, acc, pred = O.fsar_loss_and_acc(st["logits"], st["class_logits"], ep["target_labels"],
@@ -59,6 +59,25 @@ def test_fsar_state_dict_keys_match_reference_names():
         for k in ref:
             assert tuple(sd[k].shape) == tuple(ref[k].shape), k
         net.load_state_dict(ref, strict=True)
+
+
+def test_fsar_optional_branches_in_state_dict_and_config():
+    """MODEL.TRANSFORMER_DEPTH adds context2.layers.1.* (model_clipfsar.py:143-144); MODEL.EVAL_TEXT / MODEL.COMBINE raise
+    like the reference does (:384, recorded by pin_against_reference.py fsar_dead_branches)."""
+    ci = H.fsar_case_inputs("fsar_head_5w2s_t8_depth2")
+    net = H.build_cuda_fsar_model(ci)
+    head_keys = {k for k in net.state_dict() if not k.startswith("backbone.")}
+    assert head_keys == set(O.make_fsar_weights(512, seed=0, depth=2).keys())
+    assert net._extra_config() == dict(fsar_depth=2, fsar_merge_before=0)
+    assert H.build_cuda_fsar_model(H.fsar_case_inputs("fsar_head_5w3s_t8_merge"))._extra_config() == \
+        dict(fsar_depth=1, fsar_merge_before=1)
+    from clip_spm_b200 import CNN_OTAM_CLIPFSAR
+    from clip_spm_b200.config import make_cfg
+    for flag in ("EVAL_TEXT", "COMBINE"):
+        cfg = make_cfg("ViT-B/16", 8, params={})
+        setattr(cfg.MODEL, flag, True)
+        with pytest.raises(AttributeError):
+            CNN_OTAM_CLIPFSAR(cfg)
 
 
 def test_fsar_fails_loudly_without_gpu():

@@ -21,7 +21,8 @@ def _check_pred(out_logits, g):
     return int(safe.sum())
 
 
-@pytest.mark.parametrize("name", ["fsar_head_5w5s_t8", "fsar_head_5w3s_t8_d1024_q2", "fsar_head_5w1s_t16_single"])
+@pytest.mark.parametrize("name", ["fsar_head_5w5s_t8", "fsar_head_5w3s_t8_d1024_q2", "fsar_head_5w1s_t16_single",
+                                  "fsar_head_5w3s_t8_merge", "fsar_head_5w2s_t8_depth2"])
 def test_fsar_head_matches_reference_golden(name):
     ci, g = H.fsar_case_inputs(name), H.golden(name)
     net = H.build_cuda_fsar_model(ci)
@@ -35,9 +36,9 @@ def test_fsar_head_matches_reference_golden(name):
     assert _check_pred(out["logits"][0], g) >= 1
 
 
-def test_fsar_head_batched_episodes_equal_single():
+@pytest.mark.parametrize("name", ["fsar_head_5w5s_t8", "fsar_head_5w3s_t8_merge", "fsar_head_5w2s_t8_depth2"])
+def test_fsar_head_batched_episodes_equal_single(name):
     """E episodes in one call == the same episodes one at a time (bit for bit: same kernels, same order per row)."""
-    name = "fsar_head_5w5s_t8"
     ci = H.fsar_case_inputs(name)
     net = H.build_cuda_fsar_model(ci, max_episodes=3)
     eps, sus, qus = [], [], []
@@ -56,7 +57,7 @@ def test_fsar_head_batched_episodes_equal_single():
         assert H.rel_err(both["class_logits"][k], one["class_logits"][0]) < 1e-6
         ref = O.fsar_head_forward(ci["weights"], ci["text"], ci["text_train"], sus[k], qus[k],
                                   eps[k]["context_labels"], eps[k]["real_support_labels"],
-                                  eps[k]["real_target_labels"], ci["single"])
+                                  eps[k]["real_target_labels"], ci["single"], **ci["options"])
         assert H.rel_err(both["logits"][k], ref["logits"][0]) < TOL_HEAD
 
 
