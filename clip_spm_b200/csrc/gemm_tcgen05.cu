@@ -265,9 +265,11 @@ int make_tensor_map_f32_nd(CUtensorMap* map, const void* base, int rank, const u
     if (strides_bytes[i] % 16 != 0) return 1;
     gstride[i] = strides_bytes[i];
   }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || box[0] != 32) return 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (box[0] != 32 && box[0] != 16)) return 1;
+  // the innermost box extent picks the swizzle: 32 floats = 128-byte rows, 16 floats = 64-byte rows
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bx, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, box[0] == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
 }
 

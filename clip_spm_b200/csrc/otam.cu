@@ -24,7 +24,7 @@ template <int NV, int TP>
 __global__ void __launch_bounds__(256, (TP <= 8 ? 5 : (TP <= 16 ? 4 : 2)))
 otam_kernel(const float* __restrict__ sup, long long s_p, long long s_w, long long s_t, const float* __restrict__ tgt,
             long long t_p, long long t_q, long long t_t, int W, int Q, int T, int single_direct, float alpha,
-            float beta, float* __restrict__ out) {
+            float beta, float* __restrict__ out, int dp_log) {
   constexpr int D = NV * 128;
   extern __shared__ __align__(16) float sm_ot[];
   float* sq = sm_ot;               // [T][D] query frames
@@ -107,7 +107,7 @@ otam_kernel(const float* __restrict__ sup, long long s_p, long long s_w, long lo
     const int j = j0 + seg;
     const bool valid = seg < per_warp && j < n_dp;
     const int w = valid ? j / ndir : 0, dir = valid ? j % ndir : 0;
-    const float r = otam_wavefront(T, m, valid, dist + w * T * T, dir);
+    const float r = otam_wavefront_auto(T, m, valid, dist + w * T * T, dir, dp_log);
     if (valid && m == T + 1) res[w * 2 + dir] = r;
   }
   __syncthreads();
@@ -156,7 +156,7 @@ int k_otam(cudaStream_t st, const float* sup, long long s_p, long long s_w, long
 #define SPM_OTAM_LAUNCH(NV, TP)                                                                                    \
   if (nv == NV && tp == TP)                                                                                        \
     otam_kernel<NV, TP><<<grid, 256, smem, st>>>(sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, W, Q, T, single_direct,   \
-                                                 alpha, beta, out);
+                                                 alpha, beta, out, otam_dp_force_log());
   SPM_OTAM_FOR_ALL(SPM_OTAM_LAUNCH)
 #undef SPM_OTAM_LAUNCH
   cudaError_t e = cudaGetLastError();

@@ -227,7 +227,7 @@ cos_dist_mma_kernel(const float* __restrict__ sup, long long s_p, long long s_w,
 // s + SL/2 are the two directions of the same (problem, query, class), so their sum is formed inside the CTA.
 __global__ void __launch_bounds__(256)
 otam_dp_kernel(const float* __restrict__ dist, long long n_pairs, int T, int single_direct, float alpha, float beta,
-               float* __restrict__ out) {
+               float* __restrict__ out, int dp_log) {
   extern __shared__ __align__(16) float sm_dp[];   // [pairs per CTA][T*T] distance tables, then [SL] results
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_warp = otam_dps_per_warp(T), SL = 8 * per_warp;
@@ -237,14 +237,19 @@ otam_dp_kernel(const float* __restrict__ dist, long long n_pairs, int T, int sin
   float* res = sm_dp + pairs_per_cta * T * T;
   // T is even (launcher), so every table is a whole number of float4 and 16-byte aligned
   const float4* src = reinterpret_cast<const float4*>(dist + pair0 * T * T);
-  for (int i = threadIdx.x; i < n_here * T * T / 4; i += blockDim.x)
-    reinterpret_cast<float4*>(sm_dp)[i] = __ldg(src + i);
+  const bool exp_mode = otam_exp_mode(T, dp_log);   // the exponentials are taken here, in parallel, off the wavefront's chain
+  for (int i = threadIdx.x; i < n_here * T * T / 4; i += blockDim.x) {
+    float4 v = __ldg(src + i);
+    v.x = otam_table_value(v.x, exp_mode); v.y = otam_table_value(v.y, exp_mode);
+    v.z = otam_table_value(v.z, exp_mode); v.w = otam_table_value(v.w, exp_mode);
+    reinterpret_cast<float4*>(sm_dp)[i] = v;
+  }
   __syncthreads();
   const int seg = lane / (T + 2), m = lane % (T + 2);
   const int slot = warp * per_warp + seg;
   const int pair = slot % pairs_per_cta, dir = slot / pairs_per_cta;
   const bool valid = seg < per_warp && pair < n_here;
-  const float r = otam_wavefront(T, m, valid, sm_dp + (valid ? pair : 0) * T * T, dir);
+  const float r = otam_wavefront_table(T, m, valid, sm_dp + (valid ? pair : 0) * T * T, dir, exp_mode);
   if (valid && m == T + 1) res[slot] = r;
   __syncthreads();
   for (int i = threadIdx.x; i < n_here; i += blockDim.x) {
@@ -345,7 +350,8 @@ int k_otam_mma(cudaStream_t st, const float* sup, long long s_p, long long s_w, 
     const int per_warp = 32 / (T + 2), ndir = single_direct ? 1 : 2, pairs_per_cta = 8 * per_warp / ndir;
     const size_t smem = (size_t)(pairs_per_cta * T * T + 8 * per_warp) * sizeof(float);
     const long long ctas = (n_pairs + pairs_per_cta - 1) / pairs_per_cta;
-    otam_dp_kernel<<<(unsigned)ctas, 256, smem, st>>>(dist, n_pairs, T, single_direct, alpha, beta, out);
+    otam_dp_kernel<<<(unsigned)ctas, 256, smem, st>>>(dist, n_pairs, T, single_direct, alpha, beta, out,
+                                                      otam_dp_force_log());
     r = (int)cudaGetLastError();
     count_launch();
   }

@@ -8,6 +8,7 @@ import torch
 from oracle import clipspm_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # name: (backbone, way, shot, qpc, T, n_text_cls, protocol, head_only, single_direct, seed) -- must match
 # oracle/pin_against_reference.py::CASES (the golden files were written by that script from the real reference)

@@ -38,6 +38,18 @@ def test_otam_distance_matches_oracle(P, W, Q, T, D, single):
     assert H.rel_err(acc, 2.5 * ref) < 1e-5
 
 
+@pytest.mark.parametrize("env", [{}, {"SPM_OTAM_DP": "log"}, {"SPM_OTAM": "stream"}, {"SPM_OTAM_FUSED": "0"}, {"SPM_OTAM_KC": "16"}])
+def test_otam_wavefront_formulations_agree(env):
+    """exponent-domain (default, T <= 16) and log-domain wavefronts, in the fused (default at batch scale, both ring geometries),
+    two-kernel and streaming kernels, against
+    the oracle at 1e-5 -- including inputs whose distances are all ~0 or all ~2 (the ends of the exponent-domain range)"""
+    import os, subprocess, sys
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, os.path.join(H.ROOT, "tools", "otam_dp_check.py")], env=e, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_otam_properties_full_size():
     """size-independent properties at the 1000-episode batch size of BASELINE config 2"""
     from clip_spm_b200 import ops
