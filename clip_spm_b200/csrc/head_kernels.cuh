@@ -79,4 +79,11 @@ int k_otam_fused(cudaStream_t st, const float* sup, long long s_p, long long s_w
                  long long t_p, long long t_q, long long t_t, int P, int W, int Q, int T, int D, int single_direct,
                  float alpha, float beta, float* out);
 
+
+// same contract on the tcgen05 tensor cores (otam_tc.cu): three problems stacked in a 128-row tile, 3xTF32 products into
+// tensor memory, for P >= 2 x #SM problems with 3*Q*T <= 128 (the headline 5-way, T = 8 shapes); -3 = outside its envelope
+int k_otam_tc(cudaStream_t st, const float* sup, long long s_p, long long s_w, long long s_t, const float* tgt, long long t_p,
+              long long t_q, long long t_t, int P, int W, int Q, int T, int D, int single_direct, float alpha, float beta,
+              float* out);
+
 }  // namespace spm

@@ -143,7 +143,9 @@ int k_otam(cudaStream_t st, const float* sup, long long s_p, long long s_w, long
   // tensor-core kernel (otam_mma.cu) for every shape it is instantiated for; SPM_OTAM=stream keeps this kernel
   static const bool allow_mma = [] { const char* e = getenv("SPM_OTAM"); return e == nullptr || strcmp(e, "stream") != 0; }();
   if (allow_mma) {
-    // batch scale (P >= 2 x #SM, headline shapes): the persistent fused kernel of otam_fused.cu
+    // batch scale (P >= 2 x #SM, headline shapes): the tcgen05 kernel of otam_tc.cu, then the persistent mma.sync kernel
+    const int rt = k_otam_tc(st, sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, P, W, Q, T, D, single_direct, alpha, beta, out);
+    if (rt != -3) return rt;
     const int rf = k_otam_fused(st, sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, P, W, Q, T, D, single_direct, alpha, beta, out);
     if (rf != -3) return rf;
     const int r = k_otam_mma(st, sup, s_p, s_w, s_t, tgt, t_p, t_q, t_t, P, W, Q, T, D, single_direct, alpha, beta, out);

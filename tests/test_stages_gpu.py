@@ -38,10 +38,12 @@ def test_otam_distance_matches_oracle(P, W, Q, T, D, single):
     assert H.rel_err(acc, 2.5 * ref) < 1e-5
 
 
-@pytest.mark.parametrize("env", [{}, {"SPM_OTAM_DP": "log"}, {"SPM_OTAM": "stream"}, {"SPM_OTAM_FUSED": "0"}, {"SPM_OTAM_KC": "16"}])
+@pytest.mark.parametrize("env", [{}, {"SPM_OTAM_TC_MINP": "296"}, {"SPM_OTAM_TC_MINP": "296", "SPM_OTAM_TC_MASK": "1", "SPM_OTAM_TC_PF": "1"},
+                                 {"SPM_OTAM_DP": "log"}, {"SPM_OTAM": "stream"}, {"SPM_OTAM_TC": "0", "SPM_OTAM_FUSED": "0"},
+                                 {"SPM_OTAM_TC": "0", "SPM_OTAM_KC": "16"}])
 def test_otam_wavefront_formulations_agree(env):
-    """exponent-domain (default, T <= 16) and log-domain wavefronts, in the fused (default at batch scale, both ring geometries),
-    two-kernel and streaming kernels, against
+    """exponent-domain (default, T <= 16) and log-domain wavefronts, in the tcgen05 (default from 12 x #SM problems), persistent mma.sync
+    (default from 2 x #SM, both ring geometries), two-kernel and streaming kernels, against
     the oracle at 1e-5 -- including inputs whose distances are all ~0 or all ~2 (the ends of the exponent-domain range)"""
     import os, subprocess, sys
     e = dict(os.environ, **env)
