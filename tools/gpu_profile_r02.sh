@@ -14,7 +14,7 @@ timeout 300 $B > $O/r02_prof_bench_plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2500 -c 1700 --csv --log-file $O/r02_launches_vit_16eps.csv $B > $O/r02_prof_bench_ncu.log 2>&1
 E="python tools/profile_encoder.py 512 3"
 timeout 300 $E > $O/r02_prof_enc_plain.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gemm2_tcgen05|vit_attention_tc|layernorm" -s 180 -c 16 -o $O/r02_enc $E > $O/r02_prof_enc_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gemm2_tcgen05|vit_attention_tc|layernorm" -s 70 -c 16 -o $O/r02_enc $E > $O/r02_prof_enc_ncu.log 2>&1
 export_rep r02_enc source
 for EH in 8 128; do
 H="python tools/time_head.py --episodes $EH --iters 2"
@@ -24,8 +24,12 @@ export_rep r02_head_e$EH
 done
 T="python tools/time_head_kernels.py --one"
 timeout 300 $T > $O/r02_prof_otam_plain.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"cos_dist|otam" -s 3 -c 3 -o $O/r02_otam $T > $O/r02_prof_otam_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"cos_dist|otam" -s 3 -c 2 -o $O/r02_otam $T > $O/r02_prof_otam_ncu.log 2>&1
 export_rep r02_otam source
+T4="python tools/time_head_kernels.py --p4000"
+timeout 300 $T4 > $O/r02_prof_otam4k_plain.log 2>&1 &&
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"cos_dist|otam" -s 3 -c 2 -o $O/r02_otam4k $T4 > $O/r02_prof_otam4k_ncu.log 2>&1
+export_rep r02_otam4k source
 R="python tools/rn50_throughput.py"
 timeout 300 $R > $O/r02_prof_rn50_plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 900 --csv --log-file $O/r02_launches_rn50.csv $R > $O/r02_prof_rn50_ncu.log 2>&1
