@@ -248,19 +248,6 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 
-// same with tf32 inputs: A in tensor memory as one 32-bit column per K element (8 columns per instruction)
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 // MN-major (the operand's M/N index is the contiguous one) SWIZZLE_128B tile: rows of 64 bf16 (128 B) along MN,
 // one row per K index, 8-row groups 1024 B apart (SBO); a single 64-element MN block, so LBO is unused.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {

@@ -22,6 +22,7 @@
  *   spm_set_text_features_train / spm_class_logits   models/model_clipfsar.py:127,329-331 (sibling head CLIP-FSAR)
  *   spm_softdtw_forward/backward  models/OTAM.py:34-203 (TA2N's numba.cuda soft-DTW kernels, _SoftDTWCUDA)
  *   spm_jpeg_info / spm_jpeg_decode   video_reader.py:227-230 read_single_image (PIL JPEG decode of every frame)
+ *   spm_adam_* / spm_scaler_update    run/main_run.py:84-88,76,207-209 (torch.optim.Adam + GradScaler of the training loop)
  *   spm_gemm                      ATen linear / conv-as-GEMM calls (cuBLASLt) under all of the above
  */
 #ifndef CLIPSPM_B200_H
@@ -33,11 +34,12 @@
 extern "C" {
 #endif
 
-#define SPM_ABI_VERSION 6 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
+#define SPM_ABI_VERSION 7 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
                            * 3: spm_head_stage (per-stage taps for the parity tests)
                            * 4: spm_jpeg_info / spm_jpeg_decode, spm_eval_u8
                            * 5: SPM_HEAD_CPM2C: spm_config gained its parameters; spm_cpm2c_outputs
-                           * 6: spm_config gained fsar_depth, fsar_merge_before (CLIP-FSAR's optional branches) */
+                           * 6: spm_config gained fsar_depth, fsar_merge_before (CLIP-FSAR's optional branches)
+                           * 7: spm_adam_*, spm_scaler_update */
 
 typedef struct spm_handle spm_handle;
 
@@ -199,6 +201,23 @@ int spm_softdtw_backward(void* stream, int n_pairs, int N, int M, const float* D
 int spm_otam_distance_backward(void* stream, int n_pairs, int W, int Q, int T, int D, const float* support,
                                const float* target, int single_direct, float alpha, const float* grad_out,
                                float* grad_support, float* grad_target);
+
+/* Optimiser half of the training step (run/main_run.py:84-88 torch.optim.Adam(betas=(0.5, 0.999), weight_decay); :76,207-209
+ * GradScaler.step / .update): multi-tensor kernels over all parameters, no host synchronisation.
+ *   spm_adam_create   n fp32 device tensors (the model's parameters); allocates exp_avg / exp_avg_sq (zero) and the step count
+ *   spm_adam_step     one optimiser step on grads[i] (device pointers, null = parameter without gradient).  scaler_state =
+ *                     device float[3] {scale, growth_tracker, found_inf} of a GradScaler, or null: with it the gradients are
+ *                     first unscaled IN PLACE (g *= 1/scale) and checked, and the whole step is skipped when any is inf / nan
+ *   spm_scaler_update torch's _amp_update_scale_ on that state (backoff on overflow, growth after `growth_interval` clean
+ *                     steps) and found_inf = 0
+ *   spm_adam_state    device pointers of tensor i's exp_avg / exp_avg_sq and of the fp32 step count (state_dict) */
+typedef struct spm_adam spm_adam;
+int spm_adam_create(int n_tensors, float* const* params, const long long* numel, spm_adam** out);
+int spm_adam_destroy(spm_adam* a);
+int spm_adam_step(spm_adam* a, void* stream, float* const* grads, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, float* scaler_state);   /* the hyper-parameters as the Python floats they are */
+int spm_adam_state(spm_adam* a, int i, float** exp_avg, float** exp_avg_sq, float** step);
+int spm_scaler_update(void* stream, float* scaler_state, float growth_factor, float backoff_factor, int growth_interval);
 
 /* Frame-encoder self-attention stage (models/clip_fsar.py:626,638): qkv [F*197, 2304] bf16 (q | k | v, head h at
  * columns h*64 of each third) -> out [F*197, 768] bf16.  use_mma_sync = 0: tcgen05/TMEM kernel (product path),

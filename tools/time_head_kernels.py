@@ -14,13 +14,17 @@ if "--one" in sys.argv:   # a single shape: the command profiled under ncu
     shapes = shapes[:1]
 if "--p4000" in sys.argv:
     shapes = shapes[1:2]
+if "--p444" in sys.argv:      # 3 problems per SM, 73 MB of operands: with --noflush they are served from the 126 MB L2
+    shapes = ((444, 5, 5, 8, 512),)
+NOFLUSH = "--noflush" in sys.argv
 for P, W, Q, T, D in shapes:
     sup = torch.randn(P, W, T, D, device="cuda"); tgt = torch.randn(P, Q, T, D, device="cuda")
     out = torch.zeros(P, Q, W, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
     ms = []
     for i in range(8):
-        flush.zero_()                      # evict the operands from the 126 MB L2
+        if not NOFLUSH:
+            flush.zero_()                  # evict the operands from the 126 MB L2
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); ops.otam_distance(sup, tgt, False, out=out); e1.record(); torch.cuda.synchronize()
         if i >= 3: ms.append(e0.elapsed_time(e1))
