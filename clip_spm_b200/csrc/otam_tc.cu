@@ -14,8 +14,8 @@
 //   warp 1       one thread issues, per 8-column step, three tcgen05.mma kind::tf32 (128 x 128 x 8) on the stacked tiles:
 //                hi*hi -> D_main, lo*hi + hi*lo -> D_corr in tensor memory (3xTF32: fp32-accurate, the distances are
 //                1 - cos of nearly parallel frames).  All 3 x 3 problem blocks are computed and only the diagonal ones
-//                used: one 128-wide MMA reads 8 KB of shared memory where three 48-wide ones read 16.5 KB, and shared-memory
-//                bandwidth (operand reads + the converters' traffic), not the tensor pipe, is what this kernel runs out of.
+//                used: one 128-wide MMA reads 8 KB of shared memory where three 48-wide ones read 16.5 KB (measured 241 ->
+//                195 us at P = 4000); the tensor pipe has the headroom.
 //                Two accumulators because the tensor core's fp32 adder truncates: 192 accumulations into one large sum
 //                left a biased 1e-5 relative error on near-parallel videos; the 64 of hi*hi alone stay below 4e-6, and
 //                the correction terms are 2^-11 of that magnitude
