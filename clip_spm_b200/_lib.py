@@ -69,6 +69,14 @@ SIGNATURES = {
                                   c_float, c_float, c_void_p]),
     "spm_otam_distance_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                            c_float, c_void_p, c_void_p, c_void_p]),
+    "spm_tv1_create": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "spm_tv1_destroy": (c_int, [c_void_p]),
+    "spm_tv1_load_weights": (c_int, [c_void_p, c_void_p] + [c_void_p] * 11),
+    "spm_tv1_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "spm_tv1_backward": (c_int, [c_void_p, c_void_p] + [c_void_p] * 13),
+    "spm_linear_backward_workspace": (c_ll, [c_int, c_int, c_int]),
+    "spm_linear_backward": (c_int, [c_void_p, c_int] + [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float]
+                            + [c_void_p] * 4 + [c_ll]),
     "spm_adam_create": (c_int, [c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_void_p)]),
     "spm_adam_destroy": (c_int, [c_void_p]),
     "spm_adam_step": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), ctypes.c_double, ctypes.c_double,

@@ -1,0 +1,474 @@
+// Training step, next piece: forward AND backward of the head's transformer block
+// models/myRes.py:1053-1075 `Transformer_v1` (depth 1, q = k = v = x) --
+//     y   = to_out(softmax(q k^T / sqrt(dh)) v) + b_out + x        q, k, v = to_{q,k,v}(LayerNorm(x))      (:1039-1040, :964-982)
+//     out = W3 gelu(W0 y + b0) + b3 + y                                                                    (:1069, FeedForward :944-955)
+// -- the block behind `context1` / `context2` of CLIP-SPM and `context2` of CLIP-FSAR / CPM2C, i.e. what
+// `scaler.scale(loss).backward()` (run/main_run.py:252) differentiates most of the head's parameters through.
+//
+// Forward = the library's own kernels (LayerNorm, tcgen05 GEMMs with fused bias / GELU / residual epilogues, the short-
+// sequence attention kernel); it leaves LN(x), qkv, the attention output, y and gelu(.) in the handle.  Backward:
+//   * every dX = dY W and dW = dY^T X is the SAME tcgen05 GEMM (out = A B^T, both operands K-contiguous) on transposed
+//     copies -- weights transposed once at load, activations by a tiled transpose kernel (rows padded to 16 bytes with
+//     zeros, which add nothing to the reduction over rows); gradient accumulation across the residual branches rides in the
+//     GEMM's residual epilogue;
+//   * the pre-activation of the MLP is recomputed by one more GEMM (the forward fuses GELU into its epilogue and keeps only
+//     the activated tensor), gelu' applied elementwise;
+//   * attention backward: one CTA per (sequence, head) recomputes P from the saved q, k and forms dV = P^T dO,
+//     dS = P o (dO V^T - rowsum(dO V^T o P)), dQ = dS K / sqrt(dh), dK = dS^T Q / sqrt(dh) in shared memory;
+//   * LayerNorm backward: a warp per row (statistics recomputed), d gamma / d beta by a column-sum kernel; biases likewise.
+// Dropout (Attention_qkv / FeedForward, active in the reference's train mode) is NOT applied: this is the p = 0 block, which
+// is also what the parity oracle differentiates.  fp32 data; products in tf32 (precision 0) or exact fp32 SIMT (precision 1).
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/clipspm_b200.h"
+#include "api_common.cuh"
+#include "gemm.cuh"
+#include "head_kernels.cuh"
+#include "kernels.cuh"
+#include "profile.cuh"
+
+struct spm_tv1 {
+  int D = 0, heads = 0, dh = 0, inner = 0, mlp = 0, fp32 = 0, sms = 148;
+  bool loaded = false;
+  // weights (reference layouts) and their transposes
+  float *ln_g = nullptr, *ln_b = nullptr, *wqkv = nullptr, *wout = nullptr, *bout = nullptr, *w0 = nullptr, *b0 = nullptr,
+        *w3 = nullptr, *b3 = nullptr;
+  float *wqkvT = nullptr, *woutT = nullptr, *w0T = nullptr, *w3T = nullptr;
+  // saved activations of the last forward and backward scratch, sized for cap_rows rows
+  long long cap_rows = 0;
+  const float* x = nullptr;   // the caller's input of the last forward (must stay alive until backward)
+  int B = 0, n = 0;
+  float *HN = nullptr, *QKV = nullptr, *AO = nullptr, *Y = nullptr, *FFH = nullptr;
+  float *PRE = nullptr, *dY = nullptr, *dAO = nullptr, *dQKV = nullptr, *dHN = nullptr, *tA = nullptr, *tB = nullptr;
+  std::vector<void*> allocs;
+};
+
+namespace spm {
+int device_sm_count(int* out);   // api_gemm.cu
+namespace {
+
+#define TV1_KERNEL(call)                                                                                   \
+  do {                                                                                                      \
+    int _r = (call);                                                                                        \
+    if (_r != 0) {                                                                                          \
+      set_error(std::string(#call) + (_r < 0 ? ": unsupported shape" : std::string(": ") + cudaGetErrorString((cudaError_t)_r))); \
+      return 1;                                                                                             \
+    }                                                                                                       \
+  } while (0)
+
+#define TV1_LAUNCH_CHECK()                                                                                  \
+  do {                                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                                    \
+    if (_e != cudaSuccess) { set_error(std::string("tv1 kernel launch: ") + cudaGetErrorString(_e)); return 1; } \
+    count_launch();                                                                                         \
+  } while (0)
+
+// out[c, r] = in[r, c] for r < R, 0 for R <= r < ldo  (in [R, C] row-major, out [C, ldo])
+__global__ void transpose_pad_kernel(const float* __restrict__ in, int R, int C, float* __restrict__ out, int ldo) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(long long)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < ldo) out[(long long)c * ldo + r] = tile[threadIdx.x][i];
+  }
+}
+
+// out[c] = sum_r a[r, c] (* b[r, c] when b != null); fixed summation order (deterministic)
+__global__ void colsum_kernel(const float* __restrict__ a, const float* __restrict__ b, int R, int C, float* __restrict__ out) {
+  __shared__ float part[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < C)
+    for (int r = threadIdx.y; r < R; r += 8) {
+      const float v = a[(long long)r * C + c];
+      s += b != nullptr ? v * b[(long long)r * C + c] : v;
+    }
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+    out[c] = t;
+  }
+}
+
+// g[i] *= gelu'(pre[i]), gelu(x) = x Phi(x) (erf form, nn.GELU default): gelu'(x) = Phi(x) + x phi(x)
+__global__ void gelu_bwd_kernel(float* __restrict__ g, const float* __restrict__ pre, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = pre[i];
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+  g[i] *= cdf + x * pdf;
+}
+
+// g[i] = dy[i] * act'(.) from the layer's OUTPUT y: LeakyReLU (the slope is positive, so y and the pre-activation share
+// their sign), sigmoid (y (1 - y)); `g` holds the recomputed pre-activation on entry for GELU
+__global__ void act_bwd_kernel(float* __restrict__ g, const float* __restrict__ dy, const float* __restrict__ y, int act,
+                               float slope, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float d = 1.f;
+  if (act == ACT_LEAKY) d = y[i] > 0.f ? 1.f : slope;
+  else if (act == ACT_SIGMOID) d = y[i] * (1.f - y[i]);
+  else if (act == ACT_GELU_ERF) {
+    const float x = g[i];
+    d = 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+  }
+  g[i] = dy[i] * d;
+}
+
+// LayerNorm backward, a warp per row: xhat = (x - mean) rstd;  dx = rstd (g gamma - mean(g gamma) - xhat mean(g gamma xhat)) + add
+// also writes xhat o g (for d gamma = column sum) into `gx`
+__global__ void ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ gamma,
+                              const float* __restrict__ add, int R, int C, float* __restrict__ dx, float* __restrict__ gx) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* xr = x + (long long)row * C;
+  const float* gr = g + (long long)row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / (float)C + 1e-5f);
+  float a = 0.f, b = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float gg = gr[c] * gamma[c], xh = (xr[c] - mean) * rstd;
+    a += gg;
+    b += gg * xh;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  a /= (float)C;
+  b /= (float)C;
+  for (int c = lane; c < C; c += 32) {
+    const float xh = (xr[c] - mean) * rstd;
+    dx[(long long)row * C + c] = rstd * (gr[c] * gamma[c] - a - xh * b) + add[(long long)row * C + c];
+    gx[(long long)row * C + c] = gr[c] * xh;
+  }
+}
+
+// Attention backward for one (sequence, head): qkv rows [n, 3*inner] (q | k | v, head h at columns h*dh of each third),
+// dO rows [n, inner] -> dqkv rows in the same layout.  Shared memory: q, k, v, dO [n][dh+1], P, dS [n][n].
+__global__ void __launch_bounds__(256)
+seq_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, float* __restrict__ dqkv, int n,
+                         int heads, int dh) {
+  extern __shared__ float sm_ab[];
+  const int seq = blockIdx.x, head = blockIdx.y, inner = heads * dh, ld = 3 * inner, st = dh + 1;
+  float* sq = sm_ab;
+  float* sk = sq + n * st;
+  float* sv = sk + n * st;
+  float* so = sv + n * st;
+  float* sp = so + n * st;      // [n][n]
+  float* sd = sp + n * n;       // [n][n]
+  const long long row0 = (long long)seq * n;
+  for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
+    const int j = i / dh, d = i % dh;
+    const float* r = qkv + (row0 + j) * ld + head * dh + d;
+    sq[j * st + d] = r[0];
+    sk[j * st + d] = r[inner];
+    sv[j * st + d] = r[2 * inner];
+    so[j * st + d] = dO[(row0 + j) * inner + head * dh + d];
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)dh);
+  // S = q k^T scale and dP = dO v^T, one (i, j) per thread
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    float s = 0.f, dp = 0.f;
+    for (int d = 0; d < dh; ++d) {
+      s += sq[i * st + d] * sk[j * st + d];
+      dp += so[i * st + d] * sv[j * st + d];
+    }
+    sp[e] = s * scale;
+    sd[e] = dp;
+  }
+  __syncthreads();
+  // row softmax and dS = P o (dP - sum_j dP P), one row per warp
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < n; i += 8) {
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, sp[i * n + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float z = 0.f;
+    for (int j = lane; j < n; j += 32) { const float p = expf(sp[i * n + j] - m); sp[i * n + j] = p; z += p; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    const float inv = 1.f / z;
+    float dot = 0.f;
+    for (int j = lane; j < n; j += 32) { const float p = sp[i * n + j] * inv; sp[i * n + j] = p; dot += p * sd[i * n + j]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int j = lane; j < n; j += 32) sd[i * n + j] = sp[i * n + j] * (sd[i * n + j] - dot);
+  }
+  __syncthreads();
+  // dQ[i] = scale sum_j dS[i,j] K[j];  dK[j] = scale sum_i dS[i,j] Q[i];  dV[j] = sum_i P[i,j] dO[i]
+  for (int e = threadIdx.x; e < n * dh; e += blockDim.x) {
+    const int i = e / dh, d = e % dh;
+    float dq = 0.f, dk = 0.f, dv = 0.f;
+    for (int j = 0; j < n; ++j) {
+      dq += sd[i * n + j] * sk[j * st + d];
+      dk += sd[j * n + i] * sq[j * st + d];
+      dv += sp[j * n + i] * so[j * st + d];
+    }
+    float* r = dqkv + (row0 + i) * ld + head * dh + d;
+    r[0] = dq * scale;
+    r[inner] = dk * scale;
+    r[2 * inner] = dv;
+  }
+}
+constexpr int TV1_SEQ_MAX = 64;
+size_t attn_bwd_smem(int n, int dh) { return (size_t)(4 * n * (dh + 1) + 2 * n * n) * sizeof(float); }
+
+int tv1_alloc(spm_tv1* h, float** p, long long n) {
+  SPM_CUDA(cudaMalloc(reinterpret_cast<void**>(p), (size_t)n * sizeof(float)));
+  h->allocs.push_back(*p);
+  return 0;
+}
+
+int tv1_transpose(cudaStream_t st, const float* in, int R, int C, float* out, int ldo) {
+  dim3 grid((C + 31) / 32, (ldo + 31) / 32), block(32, 8);
+  transpose_pad_kernel<<<grid, block, 0, st>>>(in, R, C, out, ldo);
+  TV1_LAUNCH_CHECK();
+  return 0;
+}
+int tv1_colsum(cudaStream_t st, const float* a, const float* b, int R, int C, float* out) {
+  dim3 grid((C + 31) / 32), block(32, 8);
+  colsum_kernel<<<grid, block, 0, st>>>(a, b, R, C, out);
+  TV1_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[M, N] = A[M, K] B[N, K]^T (+ bias) (act) (+ residual); planned and run in one go (the block is not a hot loop)
+int tv1_gemm(spm_tv1* h, cudaStream_t st, const float* A, long long lda, const float* B, long long ldb, int M, int N, int K,
+             const float* bias, int act, const float* residual, float* out) {
+  GemmEpilogue e;
+  e.bias = bias; e.act = act; e.residual = residual; e.ldr = N; e.out = out; e.ldo = N;
+  GemmOp op;
+  const char* err = "";
+  if (gemm_plan(&op, h->fp32 ? GEMM_F32_SIMT : GEMM_TF32, A, lda, B, ldb, M, N, K, e, h->sms, &err) ||
+      gemm_run(&op, st, &err)) {
+    set_error(std::string("tv1 gemm: ") + err);
+    return 1;
+  }
+  return 0;
+}
+
+int tv1_workspace(spm_tv1* h, long long R) {
+  if (R <= h->cap_rows) return 0;
+  SPM_CUDA(cudaDeviceSynchronize());
+  for (float** p : {&h->HN, &h->QKV, &h->AO, &h->Y, &h->FFH, &h->PRE, &h->dY, &h->dAO, &h->dQKV, &h->dHN, &h->tA, &h->tB})
+    if (*p) { cudaFree(*p); h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), (void*)*p), h->allocs.end()); *p = nullptr; }
+  const long long D = h->D, I = h->inner, M = h->mlp, Rp = (R + 3) / 4 * 4, big = std::max<long long>(3 * I, M);
+  SPM_TRY(tv1_alloc(h, &h->HN, R * D));
+  SPM_TRY(tv1_alloc(h, &h->QKV, R * 3 * I));
+  SPM_TRY(tv1_alloc(h, &h->AO, R * I));
+  SPM_TRY(tv1_alloc(h, &h->Y, R * D));
+  SPM_TRY(tv1_alloc(h, &h->FFH, R * M));
+  SPM_TRY(tv1_alloc(h, &h->PRE, R * M));
+  SPM_TRY(tv1_alloc(h, &h->dY, R * D));
+  SPM_TRY(tv1_alloc(h, &h->dAO, R * I));
+  SPM_TRY(tv1_alloc(h, &h->dQKV, R * 3 * I));
+  SPM_TRY(tv1_alloc(h, &h->dHN, R * std::max(D, M)));   // also holds dFFH / dPRE [R, mlp]
+  SPM_TRY(tv1_alloc(h, &h->tA, big * Rp));
+  SPM_TRY(tv1_alloc(h, &h->tB, big * Rp));
+  h->cap_rows = R;
+  return 0;
+}
+
+}  // namespace
+}  // namespace spm
+
+using namespace spm;
+
+extern "C" {
+
+int spm_tv1_create(int D, int heads, int dim_head, int mlp_dim, int precision, spm_tv1** out) {
+  SPM_CHECK(out != nullptr, "spm_tv1_create: null argument");
+  SPM_CHECK(D > 0 && D % 32 == 0 && heads > 0 && dim_head > 0 && dim_head % 32 == 0 && dim_head <= 256 && mlp_dim % 32 == 0,
+            "spm_tv1_create: D, dim_head and mlp_dim must be multiples of 32 (dim_head <= 256)");
+  SPM_CHECK(precision == 0 || precision == 1, "spm_tv1_create: precision 0 (tf32 products) or 1 (fp32)");
+  int ndev = 0;
+  SPM_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "spm_tv1_create: no CUDA device -- this library has no CPU path");
+  const char* err = "";
+  SPM_CHECK(gemm_init(&err) == 0 && gemm2_init(&err) == 0, "spm_tv1_create: gemm_init failed");
+  SPM_CHECK(k_seq_attention_init() == 0, "spm_tv1_create: cudaFuncSetAttribute failed");
+  SPM_CUDA(cudaFuncSetAttribute(seq_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)attn_bwd_smem(48, 256)));
+  spm_tv1* h = new spm_tv1();
+  h->D = D; h->heads = heads; h->dh = dim_head; h->inner = heads * dim_head; h->mlp = mlp_dim; h->fp32 = precision;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, dev);
+  *out = h;
+  return 0;
+}
+
+int spm_tv1_destroy(spm_tv1* h) {
+  if (h == nullptr) return 0;
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return 0;
+}
+
+int spm_tv1_load_weights(spm_tv1* h, void* stream, const float* ln_g, const float* ln_b, const float* wq, const float* wk,
+                         const float* wv, const float* wout, const float* bout, const float* w0, const float* b0,
+                         const float* w3, const float* b3) {
+  SPM_CHECK(h && ln_g && ln_b && wq && wk && wv && wout && bout && w0 && b0 && w3 && b3, "spm_tv1_load_weights: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long D = h->D, I = h->inner, M = h->mlp;
+  if (!h->loaded) {
+    SPM_TRY(tv1_alloc(h, &h->ln_g, D)); SPM_TRY(tv1_alloc(h, &h->ln_b, D));
+    SPM_TRY(tv1_alloc(h, &h->wqkv, 3 * I * D)); SPM_TRY(tv1_alloc(h, &h->wout, D * I)); SPM_TRY(tv1_alloc(h, &h->bout, D));
+    SPM_TRY(tv1_alloc(h, &h->w0, M * D)); SPM_TRY(tv1_alloc(h, &h->b0, M));
+    SPM_TRY(tv1_alloc(h, &h->w3, D * M)); SPM_TRY(tv1_alloc(h, &h->b3, D));
+    SPM_TRY(tv1_alloc(h, &h->wqkvT, D * 3 * I)); SPM_TRY(tv1_alloc(h, &h->woutT, I * D));
+    SPM_TRY(tv1_alloc(h, &h->w0T, D * M)); SPM_TRY(tv1_alloc(h, &h->w3T, M * D));
+    h->loaded = true;
+  }
+  auto cp = [&](float* dst, const float* src, long long n) {
+    return cudaMemcpyAsync(dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+  };
+  SPM_CUDA(cp(h->ln_g, ln_g, D)); SPM_CUDA(cp(h->ln_b, ln_b, D));
+  SPM_CUDA(cp(h->wqkv, wq, I * D)); SPM_CUDA(cp(h->wqkv + I * D, wk, I * D)); SPM_CUDA(cp(h->wqkv + 2 * I * D, wv, I * D));
+  SPM_CUDA(cp(h->wout, wout, D * I)); SPM_CUDA(cp(h->bout, bout, D));
+  SPM_CUDA(cp(h->w0, w0, M * D)); SPM_CUDA(cp(h->b0, b0, M)); SPM_CUDA(cp(h->w3, w3, D * M)); SPM_CUDA(cp(h->b3, b3, D));
+  // transposes for the dgrad GEMMs (B operand = W^T, K-contiguous): [rows, cols] -> [cols, rows]
+  SPM_TRY(tv1_transpose(st, h->wqkv, (int)(3 * I), (int)D, h->wqkvT, (int)(3 * I)));
+  SPM_TRY(tv1_transpose(st, h->wout, (int)D, (int)I, h->woutT, (int)D));
+  SPM_TRY(tv1_transpose(st, h->w0, (int)M, (int)D, h->w0T, (int)M));
+  SPM_TRY(tv1_transpose(st, h->w3, (int)D, (int)M, h->w3T, (int)D));
+  return 0;
+}
+
+int spm_tv1_forward(spm_tv1* h, void* stream, const float* x, int n_seq, int seq_len, float* out) {
+  SPM_CHECK(h && x && out, "spm_tv1_forward: null argument");
+  SPM_CHECK(h->loaded, "spm_tv1_forward: weights not loaded");
+  SPM_CHECK(n_seq > 0 && seq_len > 0 && seq_len <= 48, "spm_tv1_forward: 1..48 tokens per sequence");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = h->D, I = h->inner, M = h->mlp, R = n_seq * seq_len;
+  SPM_TRY(tv1_workspace(h, R));
+  h->x = x; h->B = n_seq; h->n = seq_len;
+  TV1_KERNEL(k_layernorm(st, x, D, R, D, h->ln_g, h->ln_b, nullptr, 0, h->HN, nullptr, D));
+  SPM_TRY(tv1_gemm(h, st, h->HN, D, h->wqkv, D, R, 3 * I, D, nullptr, ACT_NONE, nullptr, h->QKV));
+  TV1_KERNEL(k_seq_attention(st, h->QKV, h->AO, n_seq, seq_len, 1, 0, seq_len, 0, 0, h->heads, h->dh));
+  SPM_TRY(tv1_gemm(h, st, h->AO, I, h->wout, I, R, D, I, h->bout, ACT_NONE, x, h->Y));
+  SPM_TRY(tv1_gemm(h, st, h->Y, D, h->w0, D, R, M, D, h->b0, ACT_GELU_ERF, nullptr, h->FFH));
+  SPM_TRY(tv1_gemm(h, st, h->FFH, M, h->w3, M, R, D, M, h->b3, ACT_NONE, h->Y, out));
+  return 0;
+}
+
+int spm_tv1_backward(spm_tv1* h, void* stream, const float* grad_out, float* grad_x, float* g_ln_g, float* g_ln_b,
+                     float* g_wq, float* g_wk, float* g_wv, float* g_wout, float* g_bout, float* g_w0, float* g_b0,
+                     float* g_w3, float* g_b3) {
+  SPM_CHECK(h && grad_out && grad_x && g_ln_g && g_ln_b && g_wq && g_wk && g_wv && g_wout && g_bout && g_w0 && g_b0 && g_w3 &&
+                g_b3, "spm_tv1_backward: null argument");
+  SPM_CHECK(h->x != nullptr, "spm_tv1_backward: no forward to differentiate");
+  SPM_CHECK(g_wk == g_wq + (long long)h->inner * h->D && g_wv == g_wk + (long long)h->inner * h->D,
+            "spm_tv1_backward: the q / k / v weight gradients must be three consecutive [inner, D] blocks");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = h->D, I = h->inner, M = h->mlp, n = h->n, R = h->B * h->n, Rp = (R + 3) / 4 * 4;
+  float* dF = h->dHN;   // [R, mlp]: dFFH, then dPRE in place
+  // ---- out = W3 gelu(PRE) + b3 + y
+  SPM_TRY(tv1_colsum(st, grad_out, nullptr, R, D, g_b3));
+  SPM_TRY(tv1_transpose(st, grad_out, R, D, h->tA, Rp));
+  SPM_TRY(tv1_transpose(st, h->FFH, R, M, h->tB, Rp));
+  SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, D, M, Rp, nullptr, ACT_NONE, nullptr, g_w3));             // dW3 = dOut^T gelu(PRE)
+  SPM_TRY(tv1_gemm(h, st, grad_out, D, h->w3T, D, R, M, D, nullptr, ACT_NONE, nullptr, dF));              // dFFH = dOut W3
+  SPM_TRY(tv1_gemm(h, st, h->Y, D, h->w0, D, R, M, D, h->b0, ACT_NONE, nullptr, h->PRE));                 // PRE recomputed
+  {
+    const long long nel = (long long)R * M;
+    gelu_bwd_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(dF, h->PRE, nel);
+    TV1_LAUNCH_CHECK();
+  }
+  SPM_TRY(tv1_colsum(st, dF, nullptr, R, M, g_b0));
+  SPM_TRY(tv1_transpose(st, dF, R, M, h->tA, Rp));
+  SPM_TRY(tv1_transpose(st, h->Y, R, D, h->tB, Rp));
+  SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, M, D, Rp, nullptr, ACT_NONE, nullptr, g_w0));              // dW0 = dPRE^T y
+  SPM_TRY(tv1_gemm(h, st, dF, M, h->w0T, M, R, D, M, nullptr, ACT_NONE, grad_out, h->dY));                // dY = dPRE W0 + dOut
+  // ---- y = Wout ao + b_out + x
+  SPM_TRY(tv1_colsum(st, h->dY, nullptr, R, D, g_bout));
+  SPM_TRY(tv1_transpose(st, h->dY, R, D, h->tA, Rp));
+  SPM_TRY(tv1_transpose(st, h->AO, R, I, h->tB, Rp));
+  SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, D, I, Rp, nullptr, ACT_NONE, nullptr, g_wout));            // dWout = dY^T ao
+  SPM_TRY(tv1_gemm(h, st, h->dY, D, h->woutT, D, R, I, D, nullptr, ACT_NONE, nullptr, h->dAO));           // dAO = dY Wout
+  // ---- attention
+  SPM_CHECK(n <= TV1_SEQ_MAX && attn_bwd_smem(n, h->dh) <= attn_bwd_smem(48, 256), "spm_tv1_backward: sequence too long");
+  {
+    dim3 grid(h->B, h->heads);
+    seq_attention_bwd_kernel<<<grid, 256, attn_bwd_smem(n, h->dh), st>>>(h->QKV, h->dAO, h->dQKV, n, h->heads, h->dh);
+    TV1_LAUNCH_CHECK();
+  }
+  // ---- q, k, v = W{q,k,v} LN(x)
+  SPM_TRY(tv1_transpose(st, h->dQKV, R, 3 * I, h->tA, Rp));
+  SPM_TRY(tv1_transpose(st, h->HN, R, D, h->tB, Rp));
+  SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, 3 * I, D, Rp, nullptr, ACT_NONE, nullptr, g_wq));          // [dWq; dWk; dWv]
+  SPM_TRY(tv1_gemm(h, st, h->dQKV, 3 * I, h->wqkvT, 3 * I, R, D, 3 * I, nullptr, ACT_NONE, nullptr, h->dHN));   // dLN = dQKV Wqkv
+  // ---- LayerNorm + the residual branch (dY)
+  SPM_TRY(tv1_colsum(st, h->dHN, nullptr, R, D, g_ln_b));
+  ln_bwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(h->x, h->dHN, h->ln_g, h->dY, R, D, grad_x, h->HN);   // HN := xhat o dLN
+  TV1_LAUNCH_CHECK();
+  SPM_TRY(tv1_colsum(st, h->HN, nullptr, R, D, g_ln_g));
+  return 0;
+}
+
+long long spm_linear_backward_workspace(int M, int N, int K) {
+  const long long Mp = (M + 3) / 4 * 4;
+  return (long long)M * N + (long long)N * Mp + (long long)K * Mp + (long long)K * N;
+}
+
+int spm_linear_backward(void* stream, int precision, const float* x, const float* W, const float* bias, const float* y,
+                        const float* dy, int M, int N, int K, int act, float slope, float* dx, float* dW, float* db,
+                        float* workspace, long long workspace_floats) {
+  SPM_CHECK(x && W && dy && dW && workspace, "spm_linear_backward: null argument");
+  SPM_CHECK(M > 0 && N > 0 && K > 0 && N % 32 == 0 && K % 32 == 0, "spm_linear_backward: N and K must be multiples of 32");
+  SPM_CHECK(precision == 0 || precision == 1, "spm_linear_backward: precision 0 (tf32 products) or 1 (fp32)");
+  SPM_CHECK(act == ACT_NONE || act == ACT_LEAKY || act == ACT_SIGMOID || act == ACT_GELU_ERF,
+            "spm_linear_backward: activation none / GELU(erf) / LeakyReLU / sigmoid");
+  SPM_CHECK(act == ACT_NONE || act == ACT_GELU_ERF || y != nullptr, "spm_linear_backward: the layer's output is needed");
+  SPM_CHECK(workspace_floats >= spm_linear_backward_workspace(M, N, K), "spm_linear_backward: workspace too small");
+  const char* err = "";
+  SPM_CHECK(gemm_init(&err) == 0 && gemm2_init(&err) == 0, "spm_linear_backward: gemm_init failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  spm_tv1 cfg;   // carries the precision and SM count into tv1_gemm
+  cfg.fp32 = precision;
+  SPM_TRY(device_sm_count(&cfg.sms));
+  const int Mp = (M + 3) / 4 * 4;
+  float* g = workspace;
+  float* gT = g + (long long)M * N;
+  float* xT = gT + (long long)N * Mp;
+  float* WT = xT + (long long)K * Mp;
+  const float* gr = dy;
+  if (act != ACT_NONE) {
+    if (act == ACT_GELU_ERF) SPM_TRY(tv1_gemm(&cfg, st, x, K, W, K, M, N, K, bias, ACT_NONE, nullptr, g));   // pre-activation
+    const long long nel = (long long)M * N;
+    act_bwd_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(g, dy, y, act, slope, nel);
+    TV1_LAUNCH_CHECK();
+    gr = g;
+  }
+  if (db != nullptr) SPM_TRY(tv1_colsum(st, gr, nullptr, M, N, db));
+  SPM_TRY(tv1_transpose(st, gr, M, N, gT, Mp));
+  SPM_TRY(tv1_transpose(st, x, M, K, xT, Mp));
+  SPM_TRY(tv1_gemm(&cfg, st, gT, Mp, xT, Mp, N, K, Mp, nullptr, ACT_NONE, nullptr, dW));          // dW = g^T x
+  if (dx != nullptr) {
+    SPM_TRY(tv1_transpose(st, W, N, K, WT, N));
+    SPM_TRY(tv1_gemm(&cfg, st, gr, N, WT, N, M, K, N, nullptr, ACT_NONE, nullptr, dx));           // dx = g W
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -223,6 +223,7 @@ class CNN(nn.Module):
         self.text_features_train = text_features_train
         self._h = None
         self._packed_text = None
+        self._train_ready = False    # None until here: nn.Module.__init__ -> train() must not touch the parameters
         self.eval()
 
     # ------------------------------------------------------------------------------------------------ plumbing
@@ -337,6 +338,62 @@ class CNN(nn.Module):
         except Exception:
             pass
 
+    # ------------------------------------------------------------------------------------------------- training
+    def _head_param_names(self):
+        return [n for n, _ in self.named_parameters() if not n.startswith("backbone.")]
+
+    def train(self, mode=True):
+        """nn.Module.train.  Train mode (CLIP-SPM head only) makes the head parameters CUDA leaves with requires_grad and routes
+        `forward` / `head` through clip_spm_b200.train (differentiable head over the frozen frame encoder, run/main_run.py:
+        245-254); leaving train mode drops the packed weights so that evaluation re-packs the trained ones."""
+        was = self.training
+        super().train(mode)
+        if mode and not was and getattr(self, "_dev", None) is not None and self.HEAD == "clipspm" and torch.cuda.is_available() \
+                and getattr(self, "_train_ready", None) is not None:
+            for n in self._head_param_names():
+                p = self.get_parameter(n)
+                if not p.is_cuda:
+                    p.data = p.data.to(self._dev, torch.float32).contiguous()
+                p.requires_grad_(n != "scale")   # `scale` is a parameter the CLIP-SPM forward never reads
+            self._train_ready = True
+        if not mode and was and getattr(self, "_train_ready", False) and self._h is not None:
+            torch.cuda.synchronize(self._dev)
+            _lib.load().spm_destroy(self._h)     # the handle holds a packed copy of the head weights
+            self._h, self._packed_text = None, None
+        return self
+
+    def trainable_parameters(self):
+        """The parameters train mode differentiates (the head of models/model_clipspm.py:72-99; the CLIP tower is frozen)."""
+        return [p for p in self.parameters() if p.requires_grad]
+
+    def _train_blocks(self):
+        if getattr(self, "_tv1", None) is None:
+            from .train import TransformerV1
+            exact = self.precision == "fp32"
+            self._tv1 = (TransformerV1(self.mid_dim, exact=exact), TransformerV1(self.mid_dim, exact=exact))
+        for b in self._tv1:
+            b.reset()
+        return self._tv1
+
+    def _train_head(self, su, qu, lab, rs, rt):
+        from . import train as _train
+        if self.HEAD != "clipspm":
+            raise RuntimeError("train mode is implemented for the CLIP-SPM head only")
+        if not getattr(self, "_train_ready", False):
+            raise RuntimeError("call model.train() on a CUDA machine before the train-mode forward")
+        if self.text_features_train is None:
+            raise RuntimeError("text_features_train is not set")          # model_clipspm.py:116-118
+        text = self.text_features_train.to(self._dev, torch.float32)
+        w = dict(self.named_parameters())
+        c1, c2 = self._train_blocks()
+        return _train.spm_head_forward(w, text, su, qu, lab, rs, rt, self.params, c1, c2, self.single_direct,
+                                       self.precision == "fp32")
+
+    def loss(self, out, target_labels):
+        """run/main_run.py:390-392 on a train-mode output (differentiable): CE / TASKS_PER_BATCH + 0.001 * dists."""
+        from .train import spm_loss
+        return spm_loss(out, target_labels.to(self._dev), self.tasks_per_batch)
+
     def _way(self, labels):
         if self.way is not None:
             return int(self.way)
@@ -363,7 +420,22 @@ class CNN(nn.Module):
         """`n_episodes` episodes stacked along dim 0 of every tensor (images [E*S*T,3,224,224] etc.).
         Returns logits [E,Q,W], dists [E] and, with target_labels, loss [E], acc [E], pred [E,Q]."""
         if self.training:
-            raise RuntimeError("only the evaluation path is implemented (model.eval())")
+            # run/main_run.py:245-254: the frame encoder runs without a graph (frozen), the head is differentiable
+            if int(n_episodes) != 1:
+                raise RuntimeError("train mode takes one episode per call, like the reference's train_task")
+            T, D = self.seq_len, self.mid_dim
+            with torch.no_grad():
+                su = self.encode_frames(self._f32(context_images).view(-1, 3, 224, 224)).view(-1, T, D)
+                qu = self.encode_frames(self._f32(target_images).view(-1, 3, 224, 224)).view(-1, T, D)
+            out = self._train_head(su, qu, self._f32(context_labels).view(-1), self._f32(real_support_labels).view(-1),
+                                   self._f32(real_target_labels).view(-1))
+            out = {"logits": out["logits"], "dists": out["dists"].view(1)}
+            if target_labels is not None:
+                lg = out["logits"][0]
+                tl = target_labels.to(self._dev).long().view(-1)
+                out.update(loss=self.loss({"logits": out["logits"], "dists": out["dists"][0]}, tl).view(1),
+                           pred=lg.argmax(-1).view(1, -1).int(), acc=(lg.argmax(-1) == tl).float().mean().view(1))
+            return out
         h = self._handle()
         self._text()
         lib = _lib.load()
@@ -518,6 +590,12 @@ class CNN(nn.Module):
 
     def head(self, su, qu, context_labels, real_support_labels, real_target_labels, n_episodes=1):
         """models/model_clipspm.py:125-143 on precomputed features su [E,S,T,D], qu [E,Q,T,D]."""
+        if self.training:
+            if int(n_episodes) != 1:
+                raise RuntimeError("train mode takes one episode per call, like the reference's train_task")
+            T, D = self.seq_len, self.mid_dim
+            return self._train_head(self._f32(su).view(-1, T, D), self._f32(qu).view(-1, T, D), self._f32(context_labels).view(-1),
+                                    self._f32(real_support_labels).view(-1), self._f32(real_target_labels).view(-1))
         h = self._handle()
         self._text()
         E = int(n_episodes)

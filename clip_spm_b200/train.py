@@ -1,0 +1,242 @@
+"""Training step of the CLIP-SPM metric head (run/main_run.py:245-254 `train_task`:
+`model(input)` in train mode, `scaler.scale(loss).backward()`), over FROZEN frame-encoder features.
+
+What runs where: every dense contraction of the head and its gradient -- the two `Transformer_v1` blocks (forward and
+backward as one library call each, csrc/tv1_train.cu), the gate / FeedForward / temporal-convolution linears (spm_gemm
+forward, spm_linear_backward) and the metric tail (spm_otam_distance / _backward) -- is this library's CUDA code behind
+`torch.autograd.Function`s; torch's autograd engine only walks the graph between them and does the small elementwise
+glue (gathers, concatenations, means, the gating products, `_dis`, the cross-entropy).  The frame encoder's backward is
+not built: `CNN` in train mode encodes the frames without a graph and differentiates the head, i.e. it trains the head
+parameters of models/model_clipspm.py:72-99 with the CLIP tower frozen (the reference's optimiser also steps the tower).
+Dropout: `Transformer_v1` / `FeedForward` carry nn.Dropout(0.2 / 0.05) in the reference (myRes.py:964-996,1053-1064);
+here p = 0 by default (what the parity oracle pins against the reference); `dropout=True` draws the masks with torch's
+generator on the device and applies them as un-fused elementwise steps."""
+import ctypes
+
+import torch
+
+from . import _lib
+from .ops import ACT, _need_cuda, _ptr, _stream, otam_distance
+
+__all__ = ["linear", "TransformerV1", "spm_head_forward", "spm_loss"]
+
+
+class _Linear(torch.autograd.Function):
+    """y = act(x W^T + b): forward spm_gemm (tf32 tensor cores, or exact fp32), backward spm_linear_backward."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act, slope, exact):
+        lib = _lib.load()
+        M, K = x.shape
+        N = W.shape[0]
+        y = torch.empty(M, N, device=x.device)
+        _lib.check(lib.spm_gemm(_stream(), 2 if exact else 1, _ptr(x), K, _ptr(W), K, M, N, K, _ptr(b), act, float(slope),
+                                None, 0, 0, 0, 0, 0, 0, _ptr(y), N, 0))
+        ctx.save_for_backward(x, W, b, y)
+        ctx.cfg = (act, float(slope), bool(exact))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, W, b, y = ctx.saved_tensors
+        act, slope, exact = ctx.cfg
+        M, K = x.shape
+        N = W.shape[0]
+        dy = dy.contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dW = torch.empty_like(W)
+        db = torch.empty_like(b) if b is not None else None
+        n_ws = lib.spm_linear_backward_workspace(M, N, K)
+        ws = torch.empty(n_ws, device=x.device)
+        _lib.check(lib.spm_linear_backward(_stream(), 1 if exact else 0, _ptr(x), _ptr(W), _ptr(b), _ptr(y), _ptr(dy), M, N, K,
+                                           act, slope, _ptr(dx), _ptr(dW), _ptr(db), _ptr(ws), n_ws))
+        return dx, dW, db, None, None, None
+
+
+def linear(x, W, b=None, act="none", slope=0.0, exact=False):
+    """Differentiable y = act(x W^T + b) over the last dim of x (nn.Linear [+ activation]); fp32 CUDA tensors."""
+    _need_cuda(x, W, b)
+    x2 = x.reshape(-1, x.shape[-1]).contiguous().float()
+    y = _Linear.apply(x2, W.contiguous(), None if b is None else b.contiguous(), ACT[act], slope, exact)
+    return y.view(*x.shape[:-1], W.shape[0])
+
+
+class _TV1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pool, *w):
+        lib = _lib.load()
+        h = pool._take()
+        st = _stream()
+        _lib.check(lib.spm_tv1_load_weights(h, st, *[_ptr(t) for t in w]))
+        B, n, D = x.shape
+        out = torch.empty_like(x)
+        _lib.check(lib.spm_tv1_forward(h, st, _ptr(x), B, n, _ptr(out)))
+        ctx.save_for_backward(x, *w)   # x must outlive the backward (the handle keeps its address)
+        ctx.pool, ctx.h = pool, h
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        lib = _lib.load()
+        x, *w = ctx.saved_tensors
+        ln_g, ln_b, wq, wk, wv, wout, bout, w0, b0, w3, b3 = w
+        go = go.contiguous()
+        gx = torch.empty_like(x)
+        gqkv = torch.empty(3 * wq.shape[0], wq.shape[1], device=x.device)
+        inner = wq.shape[0]
+        g = [torch.empty_like(t) for t in (ln_g, ln_b)] + [gqkv[:inner], gqkv[inner:2 * inner], gqkv[2 * inner:]] + \
+            [torch.empty_like(t) for t in (wout, bout, w0, b0, w3, b3)]
+        _lib.check(lib.spm_tv1_backward(ctx.h, _stream(), _ptr(go), _ptr(gx), *[_ptr(t) for t in g]))
+        ctx.pool._give(ctx.h)
+        return (gx, None) + tuple(g)
+
+
+class TransformerV1:
+    """models/myRes.py:1053-1075 `Transformer_v1(dim, heads=8, dim_head_k=256, mlp_dim=2048, depth=1)` called as
+    block(x, x, x), differentiable: forward and backward are one library call each (spm_tv1_forward / _backward).
+    A library handle holds the activations of ONE forward, so the object keeps a pool: each call inside a graph takes a
+    handle, its backward returns it (`reset()` reclaims the handles of graphs that were dropped without a backward)."""
+
+    NAMES = ("0.norm.weight", "0.norm.bias", "0.fn.to_q.weight", "0.fn.to_k.weight", "0.fn.to_v.weight",
+             "0.fn.to_out.0.weight", "0.fn.to_out.0.bias", "1.net.0.weight", "1.net.0.bias", "1.net.3.weight", "1.net.3.bias")
+
+    def __init__(self, dim, heads=8, dim_head=256, mlp_dim=2048, exact=False):
+        self.cfg = (int(dim), int(heads), int(dim_head), int(mlp_dim), 1 if exact else 0)
+        self._free, self._all = [], []
+
+    def _take(self):
+        if self._free:
+            return self._free.pop()
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().spm_tv1_create(*self.cfg, ctypes.byref(h)))
+        self._all.append(h)
+        return h
+
+    def _give(self, h):
+        self._free.append(h)
+
+    def reset(self):
+        self._free = list(self._all)
+
+    def close(self):
+        lib = _lib.load()
+        for h in self._all:
+            lib.spm_tv1_destroy(h)
+        self._free, self._all = [], []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, x, weights, prefix="layers.0."):
+        """x [n_seq, seq_len, D] (seq_len <= 48); weights: mapping with the reference's parameter names under `prefix`."""
+        _need_cuda(x)
+        w = [weights[prefix + n].contiguous() for n in self.NAMES]
+        return _TV1.apply(x.contiguous().float(), self, *w)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the CLIP-SPM head in train mode (models/model_clipspm.py:111-143 with self.training = True)
+# ------------------------------------------------------------------------------------------------------------------
+def _motion_feats(x, w, exact):
+    """models/model_clipspm.py:169-191 get_motion_feats on x [N,T,D] -> [N,D]; the two Conv1d(k=3, padding=1) as im2col
+    linears (weight [Cout, Cin, 3] -> [Cout, 3*Cin] with column tap*Cin + c)."""
+    def conv(t, name):
+        tp = torch.nn.functional.pad(t, (0, 0, 1, 1))
+        col = torch.cat([tp[:, :-2], tp[:, 1:-1], tp[:, 2:]], dim=-1)
+        W = w[name + ".weight"]
+        return linear(col, W.permute(0, 2, 1).reshape(W.shape[0], -1), w[name + ".bias"], exact=exact)
+    c = conv(conv(x, "motion_conv1"), "motion_conv2")
+    f = c[:, 1:] - x[:, :-1]
+    b = c[:, :-1] - x[:, 1:]
+    return (0.5 * (f + b)).mean(1)
+
+
+def _gate(x, w, p, slope, exact):
+    """models/model_clipspm.py:88-99: Linear -> LeakyReLU -> Linear -> Sigmoid (activations fused into the GEMM epilogues)."""
+    h = linear(x, w[p + "0.weight"], w[p + "0.bias"], "leaky_relu", slope, exact)
+    return linear(h, w[p + "2.weight"], w[p + "2.bias"], "sigmoid", 0.0, exact)
+
+
+def _feed_forward(x, w, p, exact):
+    """models/myRes.py:984-996 FeedForward with p = 0."""
+    h = linear(x, w[p + "net.0.weight"], w[p + "net.0.bias"], "gelu", 0.0, exact)
+    return linear(h, w[p + "net.3.weight"], w[p + "net.3.bias"], "none", 0.0, exact)
+
+
+def _dis(x, y):
+    """models/model_clipspm.py:341-346."""
+    d = x - y
+    return (d * d).sum(dim=[-2, -1] if d.dim() == 3 else [-1]).mean()
+
+
+def _class_mean_matrix(labels):
+    """[W, S] averaging matrix of the sorted unique labels (models/myRes.py:730-739 extract_class_indices + mean)."""
+    uniq = torch.unique(labels)
+    m = (labels.view(1, -1) == uniq.view(-1, 1)).float()
+    return m / m.sum(1, keepdim=True), uniq
+
+
+def _class_means(cm, x):
+    """[W,S] x [S,T,D] -> [W,T,D] as a broadcast product + sum (elementwise glue, no library GEMM)."""
+    return (cm.view(cm.shape[0], cm.shape[1], 1, 1) * x.unsqueeze(0)).sum(1)
+
+
+def spm_head_forward(w, text_features, su, qu, support_labels, real_support, real_target, params, context1, context2,
+                     single_direct=False, exact=False):
+    """models/model_clipspm.py:116-143 after get_feats on su [S,T,D], qu [Q,T,D], differentiable with respect to the head
+    parameters `w` (reference names) and the features.  The four live `se_te` calls (:296-314) share one `context2` pass;
+    the two whose outputs only reach the discarded consistency distances (:258-265) are skipped, as in the evaluation path."""
+    S, T, D = su.shape
+    Q = qu.shape[0]
+    slope, alpha = float(params["negative_slope"]), float(params["alpha"])
+    ctx_s = text_features[real_support.long()].unsqueeze(1)    # :117 (train table) / :120
+    ctx_q = text_features[real_target.long()].unsqueeze(1)
+    x = torch.cat([su, qu], dim=0)                                                     # [V,T,D]
+    mo = _motion_feats(x, w, exact)                                                    # :194  [V,D]
+    su_mo, qu_mo = mo[:S], mo[S:]
+    token = torch.cat([ctx_q, ctx_s], dim=0).mean(dim=0)                               # :213-214 [1,D]
+    target_token = _feed_forward(token.expand(Q, -1, -1) * qu.mean(dim=[1, 2], keepdim=True), w, "token_tr.mlp.", exact)
+    # se_te x 4 (:196-197 on the motion tokens, :226,229 on the prompt tokens): [qu|su] frames with tokens [qu_mo|su_mo], then
+    # [qu|su] with [target_token|ctx_s]
+    tok = torch.cat([qu_mo.unsqueeze(1), su_mo.unsqueeze(1), target_token, ctx_s], dim=0)     # [2V,1,D]
+    gv = _gate(x, w, "gate_vision.", slope, exact)                                     # once per frame set
+    xg = x * gv
+    xg = torch.cat([xg[S:], xg[:S], xg[S:], xg[:S]], dim=0)                            # [2V,T,D]
+    q = tok * _gate(tok, w, "gate_text.", slope, exact) * alpha + xg
+    z = context2(torch.cat([tok, q], dim=1), w, "context2.layers.0.")                  # [2V,T+1,D]
+    zt, zf = z[:, 0, :], z[:, 1:, :]
+    qu_m, su_m, qu_fake, su_real = zf[:Q], zf[Q:Q + S], zf[Q + S:2 * Q + S], zf[2 * Q + S:]
+    qu_mo2, su_mo2 = zt[:Q], zt[Q:Q + S]
+    new_m = _motion_feats(torch.cat([su_m, qu_m], dim=0), w, exact)                    # :199
+    mo_dist = _dis(new_m[S:], qu_mo2) + _dis(new_m[:S], su_mo2)                        # :201-205
+    cm, uniq = _class_mean_matrix(support_labels)
+    W = cm.shape[0]
+    su_pro = _class_means(cm, su_real)                                                 # :231-239
+    class_dists_l = otam_distance(su_pro.unsqueeze(0), qu_fake.unsqueeze(0), single_direct)[0]        # :269 [Q,W]
+    dists = w["mo_alpha1"] * mo_dist                                                   # :129
+    # taskM (:275-294)
+    K = (cm > 0).sum(1).view(-1, 1, 1).float()
+    token_s = (su_pro * K + qu_fake.sum(0, keepdim=True)) / (K + Q)                    # :283 mean over [class members | queries]
+    token_q = token_s.mean(dim=0, keepdim=True)
+    su_t = torch.cat([token_s, su_real], dim=0).permute(1, 0, 2)                       # [T,W+S,D]
+    qu_t = torch.cat([token_q, qu_fake], dim=0).permute(1, 0, 2)                       # [T,1+Q,D]
+    _su = context1(su_t, w, "context1.layers.0.").permute(1, 0, 2)
+    _qu = context1(qu_t, w, "context1.layers.0.").permute(1, 0, 2)
+    su_2, qu_2, su_t2, qu_t2 = _su[W:], _qu[1:], _su[:W], _qu[0:1]
+    su_pro2 = _class_means(cm, su_2)                                                   # :133-137
+    task_dist = otam_distance(su_pro2.unsqueeze(0), qu_2.unsqueeze(0), single_direct)[0] + \
+        otam_distance(su_t2.unsqueeze(0), qu_t2.unsqueeze(0), single_direct)[0]        # :138
+    logits = -(0.5 * class_dists_l + task_dist).unsqueeze(0)                           # :141
+    return {"logits": logits, "dists": dists}
+
+
+def spm_loss(out, target_labels, tasks_per_batch=16.0):
+    """utils/utils.py:174-186 `loss` on the single logit sample + run/main_run.py:390-392: CE summed over the queries /
+    TASKS_PER_BATCH + 0.001 * dists."""
+    lg = out["logits"][0]
+    ce = -(torch.log_softmax(lg, dim=-1).gather(1, target_labels.long().view(-1, 1))).sum()
+    return ce / tasks_per_batch + 0.001 * out["dists"]

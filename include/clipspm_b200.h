@@ -23,6 +23,7 @@
  *   spm_softdtw_forward/backward  models/OTAM.py:34-203 (TA2N's numba.cuda soft-DTW kernels, _SoftDTWCUDA)
  *   spm_jpeg_info / spm_jpeg_decode   video_reader.py:227-230 read_single_image (PIL JPEG decode of every frame)
  *   spm_adam_* / spm_scaler_update    run/main_run.py:84-88,76,207-209 (torch.optim.Adam + GradScaler of the training loop)
+ *   spm_tv1_* / spm_linear_backward   autograd through models/myRes.py:1053-1075 Transformer_v1 and the head's nn.Linear layers
  *   spm_gemm                      ATen linear / conv-as-GEMM calls (cuBLASLt) under all of the above
  */
 #ifndef CLIPSPM_B200_H
@@ -34,12 +35,13 @@
 extern "C" {
 #endif
 
-#define SPM_ABI_VERSION 7 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
+#define SPM_ABI_VERSION 8 /* 2: spm_config gained `head`, `cls_value`; sibling heads, soft-DTW, spm_eval_host_set_next
                            * 3: spm_head_stage (per-stage taps for the parity tests)
                            * 4: spm_jpeg_info / spm_jpeg_decode, spm_eval_u8
                            * 5: SPM_HEAD_CPM2C: spm_config gained its parameters; spm_cpm2c_outputs
                            * 6: spm_config gained fsar_depth, fsar_merge_before (CLIP-FSAR's optional branches)
-                           * 7: spm_adam_*, spm_scaler_update */
+                           * 7: spm_adam_*, spm_scaler_update
+                           * 8: spm_tv1_* (head transformer block forward + backward), spm_linear_backward */
 
 typedef struct spm_handle spm_handle;
 
@@ -201,6 +203,34 @@ int spm_softdtw_backward(void* stream, int n_pairs, int N, int M, const float* D
 int spm_otam_distance_backward(void* stream, int n_pairs, int W, int Q, int T, int D, const float* support,
                                const float* target, int single_direct, float alpha, const float* grad_out,
                                float* grad_support, float* grad_target);
+
+/* Training step, head blocks (run/main_run.py:245-254 `scaler.scale(loss).backward()` through the metric head):
+ * forward AND backward of models/myRes.py:1053-1075 `Transformer_v1` (depth 1, q = k = v = x; LayerNorm -> to_q / to_k / to_v ->
+ * softmax attention -> to_out + x -> FeedForward + residual) -- `context1` / `context2` of CLIP-SPM, `context2` of CLIP-FSAR and
+ * CPM2C -- with dropout p = 0.  x, out, grads: fp32 [n_seq * seq_len, D] (seq_len <= 48).  A handle keeps the activations
+ * of its LAST forward (and the caller's x pointer, which must stay alive) for the one backward that follows; weight
+ * gradients are OVERWRITTEN, g_wq / g_wk / g_wv must be three consecutive [heads*dim_head, D] blocks.
+ * precision: 0 = tf32 tensor-core products, 1 = exact fp32. */
+typedef struct spm_tv1 spm_tv1;
+int spm_tv1_create(int D, int heads, int dim_head, int mlp_dim, int precision, spm_tv1** out);
+int spm_tv1_destroy(spm_tv1* h);
+int spm_tv1_load_weights(spm_tv1* h, void* stream, const float* ln_g, const float* ln_b, const float* wq, const float* wk,
+                         const float* wv, const float* wout, const float* bout, const float* w0, const float* b0,
+                         const float* w3, const float* b3);   /* device pointers, reference layouts ([out, in]) */
+int spm_tv1_forward(spm_tv1* h, void* stream, const float* x, int n_seq, int seq_len, float* out);
+int spm_tv1_backward(spm_tv1* h, void* stream, const float* grad_out, float* grad_x, float* g_ln_g, float* g_ln_b,
+                     float* g_wq, float* g_wk, float* g_wv, float* g_wout, float* g_bout, float* g_w0, float* g_b0,
+                     float* g_w3, float* g_b3);
+
+/* Backward of y = act(x W^T + bias) (nn.Linear [+ LeakyReLU | Sigmoid | GELU]: the gates models/model_clipspm.py:88-99, the
+ * FeedForward of token_trans :371-378, the temporal convolutions :169-172 as im2col GEMMs; forward = spm_gemm):
+ * x [M,K], W [N,K], y / dy [M,N] fp32 contiguous -> dx [M,K] (null: skipped), dW [N,K], db [N] (null: skipped), all
+ * overwritten.  y = the layer's OUTPUT (needed for LeakyReLU / sigmoid; GELU recomputes its pre-activation, bias may be
+ * null).  act codes as spm_gemm.  workspace: spm_linear_backward_workspace(M, N, K) floats, 16-byte aligned. */
+long long spm_linear_backward_workspace(int M, int N, int K);
+int spm_linear_backward(void* stream, int precision, const float* x, const float* W, const float* bias, const float* y,
+                        const float* dy, int M, int N, int K, int act, float slope, float* dx, float* dW, float* db,
+                        float* workspace, long long workspace_floats);
 
 /* Optimiser half of the training step (run/main_run.py:84-88 torch.optim.Adam(betas=(0.5, 0.999), weight_decay); :76,207-209
  * GradScaler.step / .update): multi-tensor kernels over all parameters, no host synchronisation.

@@ -858,6 +858,34 @@ def class_text_features(w, tokens_by_template):
     return torch.stack([encode_text(w, t) for t in tokens_by_template]).mean(dim=0)
 
 
+def head_loss_and_grads(w, text_features, su, qu, support_labels, real_support, real_target, target_labels, params,
+                         single_direct=False, tasks_per_batch=16, dtype=torch.float32):
+    """run/main_run.py:245-254 train_task on a head-only episode with dropout p = 0: loss = CE / TASKS_PER_BATCH + 0.001 * dists
+    (:390-392) of head_forward (train mode only swaps the prompt table, model_clipspm.py:116-118, so `text_features` is the
+    TRAIN table here), differentiated by torch autograd on the CPU with respect to every head parameter and the features.
+    Returns (loss, {name: grad}) with the feature gradients under "su" / "qu"; parameters the loss does not reach are absent."""
+    leaves = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in w.items()
+              if not k.startswith("backbone.") and v.dtype.is_floating_point}
+    su_, qu_ = su.detach().to(dtype).clone().requires_grad_(True), qu.detach().to(dtype).clone().requires_grad_(True)
+    st = head_forward(leaves, text_features.to(dtype), su_, qu_, support_labels, real_support, real_target, params,
+                      single_direct)
+    lg = st["logits"][0]
+    ce = -(lg.log_softmax(-1).gather(1, target_labels.long().view(-1, 1)).squeeze(1))
+    loss = ce.sum() / tasks_per_batch + 0.001 * st["dists"]
+    loss.backward()
+    grads = {k: v.grad.detach() for k, v in leaves.items() if v.grad is not None}
+    grads["su"], grads["qu"] = su_.grad.detach(), qu_.grad.detach()
+    return loss.detach(), grads
+
+
+def grad_sample_index(numel, n=4096, seed=0):
+    """fixed sample positions of a large gradient tensor stored in the goldens (the full head gradients are ~70 MB)"""
+    if numel <= n:
+        return torch.arange(numel)
+    g = torch.Generator().manual_seed(seed * 7919 + numel)
+    return torch.randperm(numel, generator=g)[:n].sort().values
+
+
 def make_otam_grad_inputs(W, Q, T, D, seed):
     """seeded inputs of the metric-tail gradient golden (pin_against_reference.py otam_grad): support [W,T,D],
     target [Q,T,D] with a shared component (cosine similarities well above zero) and an upstream gradient [Q,W]"""

@@ -229,6 +229,66 @@ def run_otam_grad_case(m):
                         shape=np.array([W, Q, T, D, seed], np.int32))
 
 
+# name: backbone (-> D), way, shot, queries per class, T, n text classes, SINGLE_DIRECT, seed
+HEAD_GRAD_CASES = {
+    "head_grad_5w2s_t8": ("ViT-B/16", 5, 2, 1, 8, 24, False, 4001),
+    "head_grad_3w1s_t4_d1024_single": ("RN50", 3, 1, 2, 4, 10, True, 4002),
+}
+
+
+def run_head_grad_case(m, name):
+    """Training step through the head (run/main_run.py:245-254): the REFERENCE's own CNN in train mode (prompt rows from
+    text_features_train, model_clipspm.py:116-118; every nn.Dropout set to p = 0 on the instance, no source is modified),
+    frame features in place of get_feats, loss of :390-392 through the reference's utils.loss, `.backward()`.  The oracle's
+    autograd (head_loss_and_grads) must reproduce the loss and every parameter / feature gradient; the reference gradients
+    become the golden (full tensors up to 4096 entries, else a fixed sample of 4096 + the L2 norm)."""
+    backbone, way, shot, qpc, T, ncls, single, seed = HEAD_GRAD_CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    net = build_reference(m, backbone, T, single)
+    w = O.make_weights(backbone, seed=0, protocol="P1", head_only=False)
+    missing, unexpected = net.load_state_dict(w, strict=False)
+    assert not missing and not unexpected
+    net.train()
+    n_drop = 0
+    for mod in net.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+            n_drop += 1
+    assert n_drop >= 8   # context1 / context2 (3 each) + token_tr (2)
+    text_train = O.make_text_features(ncls, D, seed=1)
+    net.text_features_train = text_train
+    net.text_features_test = None          # the train branch must not touch it
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, "P1", images=False)
+    su, qu = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+    su_r, qu_r = su.clone().requires_grad_(True), qu.clone().requires_grad_(True)
+    net.get_feats = lambda *a, **k: (su_r, qu_r, None)
+    ep["context_images"] = torch.zeros(1)
+    ep["target_images"] = torch.zeros(1)
+    for mod in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    import utils.utils as U
+    out = net(ep)
+    loss_ref = U.loss(out["logits"], ep["target_labels"].long(), "cpu") / 16 + 0.001 * out["dists"]
+    loss_ref.backward()
+    ref = {k: p.grad.detach() for k, p in net.named_parameters() if not k.startswith("backbone.") and p.grad is not None}
+    ref["su"], ref["qu"] = su_r.grad.detach(), qu_r.grad.detach()
+    loss, grads = O.head_loss_and_grads(w, text_train, su, qu, ep["context_labels"], ep["real_support_labels"],
+                                        ep["real_target_labels"], ep["target_labels"], O.DEFAULT_PARAMS, single)
+    assert set(ref) == set(grads), (sorted(set(ref) ^ set(grads)))
+    worst = rel(loss.reshape(()), loss_ref.detach().reshape(()))
+    gold = {"loss": loss_ref.detach().numpy().reshape(()), "logits": out["logits"].detach().numpy()}
+    for k, g in ref.items():
+        r = rel(grads[k].reshape(g.shape), g)
+        worst = max(worst, r)
+        assert r < 2e-4, "oracle autograd disagrees with the reference on d loss / d %s: rel err %.3e" % (k, r)
+        flat = g.reshape(-1)
+        gold["g:" + k] = flat[O.grad_sample_index(flat.numel())].numpy()
+        gold["n:" + k] = np.float64(flat.double().norm())
+    print("%-24s oracle autograd == reference autograd through CNN.forward (train mode, p = 0): %d gradients, worst rel err "
+          "%.2e, loss %.5f" % (name, len(ref), worst, float(loss_ref)))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
+
+
 FSAR_CASES = {
     # name: (backbone, way, shot, qpc, T, n_test_cls, n_train_cls, head_only, single_direct, seed)
     "fsar_head_5w5s_t8": ("ViT-B/16", 5, 5, 1, 8, 24, 30, True, False, 2002),
@@ -561,7 +621,7 @@ def run_softdtw_case(name):
 
 if __name__ == "__main__":
     m = import_reference()
-    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + ["fsar_dead_branches"] + list(STEN_CASES) + list(CPM2C_CASES) + list(SOFTDTW_CASES))
+    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + ["fsar_dead_branches"] + list(STEN_CASES) + list(CPM2C_CASES) + list(SOFTDTW_CASES) + list(HEAD_GRAD_CASES))
     for n in names:
         if n == "text":
             run_text_case(m)
@@ -577,5 +637,7 @@ if __name__ == "__main__":
             run_cpm2c_case(m, n)
         elif n in SOFTDTW_CASES:
             run_softdtw_case(n)
+        elif n in HEAD_GRAD_CASES:
+            run_head_grad_case(m, n)
         else:
             run_case(m, n)

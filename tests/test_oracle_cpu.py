@@ -138,7 +138,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     loaded = _lib.load()
-    assert loaded.spm_abi_version() == 7
+    assert loaded.spm_abi_version() == 8
     assert isinstance(loaded.spm_last_error(), bytes)
 
 

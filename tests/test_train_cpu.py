@@ -1,0 +1,96 @@
+"""Training step of the head, CPU side: the oracle's autograd against the goldens written from the REFERENCE's own
+`CNN.forward(...)` + `.backward()` in train mode (oracle/pin_against_reference.py head_grad_*), and the host composition
+of clip_spm_b200/train.py (which dense node is fed what) with its CUDA nodes swapped for torch stand-ins."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import clipspm_oracle as O
+from tests.helpers import golden
+
+# must match oracle/pin_against_reference.py::HEAD_GRAD_CASES
+HEAD_GRAD_CASES = {
+    "head_grad_5w2s_t8": ("ViT-B/16", 5, 2, 1, 8, 24, False, 4001),
+    "head_grad_3w1s_t4_d1024_single": ("RN50", 3, 1, 2, 4, 10, True, 4002),
+}
+
+
+def head_grad_inputs(name):
+    backbone, way, shot, qpc, T, ncls, single, seed = HEAD_GRAD_CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    w = O.make_weights(backbone, seed=0, protocol="P1", head_only=True)
+    text_train = O.make_text_features(ncls, D, seed=1)
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, "P1", images=False)
+    su, qu = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+    return dict(backbone=backbone, D=D, T=T, way=way, single=single, w=w, text=text_train, ep=ep, su=su, qu=qu)
+
+
+def check_against_golden(grads, loss, gold, tol, l2=False):
+    """every gradient the reference produced: its stored sample (or full tensor) and its L2 norm.  l2: the sample is judged by
+    its relative L2 error (tf32 products: a pre-activation within rounding of zero takes the other LeakyReLU slope, which
+    moves single entries by far more than the rest) with a loose cap on single entries"""
+    names = sorted(k[2:] for k in gold if k.startswith("g:"))
+    assert sorted(grads) == names
+    assert abs(float(loss) - float(gold["loss"])) < tol * max(1.0, abs(float(gold["loss"])))
+    for k in names:
+        flat = grads[k].detach().cpu().double().reshape(-1)
+        ref = gold["g:" + k].double()
+        mine = flat[O.grad_sample_index(flat.numel())]
+        scale = float(ref.abs().max().clamp_min(1e-30))
+        if l2:
+            assert float((mine - ref).norm()) < tol * float(ref.norm()) + 1e-30, (k, float((mine - ref).norm()), float(ref.norm()))
+            assert float((mine - ref).abs().max()) < 10 * tol * scale, (k, float((mine - ref).abs().max()), scale)
+        else:
+            assert float((mine - ref).abs().max()) < tol * scale, (k, float((mine - ref).abs().max()), scale)
+        assert abs(float(flat.norm()) - float(gold["n:" + k])) < tol * float(gold["n:" + k]) + 1e-30, k
+
+
+@pytest.mark.parametrize("name", list(HEAD_GRAD_CASES))
+def test_oracle_autograd_matches_reference_golden(name):
+    ci = head_grad_inputs(name)
+    ep = ci["ep"]
+    loss, grads = O.head_loss_and_grads(ci["w"], ci["text"], ci["su"], ci["qu"], ep["context_labels"],
+                                        ep["real_support_labels"], ep["real_target_labels"], ep["target_labels"],
+                                        O.DEFAULT_PARAMS, ci["single"])
+    check_against_golden(grads, loss, golden(name), 2e-4)
+
+
+class _Block:
+    """stand-in for train.TransformerV1: the oracle's restatement of the block"""
+
+    def __call__(self, x, w, prefix):
+        assert prefix.endswith("layers.0.")
+        return O.transformer_v1(x, w, prefix[:-len("layers.0.")])
+
+
+def _linear(x, W, b=None, act="none", slope=0.0, exact=False):
+    y = F.linear(x, W, b)
+    return {"none": lambda t: t, "gelu": F.gelu, "sigmoid": torch.sigmoid,
+            "leaky_relu": lambda t: F.leaky_relu(t, slope)}[act](y)
+
+
+def _otam(support, target, single_direct=False):
+    return torch.stack([O.otam_distance(support[p], target[p], single_direct) for p in range(support.shape[0])])
+
+
+@pytest.mark.parametrize("name", list(HEAD_GRAD_CASES))
+def test_train_head_composition_matches_oracle(name, monkeypatch):
+    """train.spm_head_forward batches the four se_te calls, the motion passes and the class means differently from the
+    reference; with torch stand-ins for its CUDA nodes it must still be the oracle's head, value and gradients"""
+    from clip_spm_b200 import train
+    monkeypatch.setattr(train, "linear", _linear)
+    monkeypatch.setattr(train, "otam_distance", _otam)
+    ci = head_grad_inputs(name)
+    ep = ci["ep"]
+    w = {k: v.clone().requires_grad_(True) for k, v in ci["w"].items() if v.dtype.is_floating_point}
+    su, qu = ci["su"].clone().requires_grad_(True), ci["qu"].clone().requires_grad_(True)
+    out = train.spm_head_forward(w, ci["text"], su, qu, ep["context_labels"], ep["real_support_labels"],
+                                 ep["real_target_labels"], O.DEFAULT_PARAMS, _Block(), _Block(), ci["single"])
+    loss = train.spm_loss(out, ep["target_labels"], 16.0)
+    loss.backward()
+    grads = {k: v.grad for k, v in w.items() if v.grad is not None}
+    grads["su"], grads["qu"] = su.grad, qu.grad
+    gold = golden(name)
+    assert torch.allclose(out["logits"].detach(), gold["logits"], atol=2e-4, rtol=1e-4)
+    check_against_golden(grads, loss.detach(), gold, 5e-4)

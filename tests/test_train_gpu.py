@@ -1,0 +1,156 @@
+"""Training step of the head on the GPU: the library's Transformer_v1 block and linear backward
+against torch autograd through the oracle restatement, the whole head's gradients against the goldens written from the
+REFERENCE's own train-mode forward + backward, and a few optimiser steps through optim.Adam / optim.GradScaler."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import clipspm_oracle as O
+from tests.helpers import golden, make_cfg
+from tests.test_train_cpu import HEAD_GRAD_CASES, check_against_golden, head_grad_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _block_weights(D, seed):
+    g = torch.Generator().manual_seed(seed)
+    sh = {"0.norm.weight": (D,), "0.norm.bias": (D,), "0.fn.to_q.weight": (2048, D), "0.fn.to_k.weight": (2048, D),
+          "0.fn.to_v.weight": (2048, D), "0.fn.to_out.0.weight": (D, 2048), "0.fn.to_out.0.bias": (D,),
+          "1.net.0.weight": (2048, D), "1.net.0.bias": (2048,), "1.net.3.weight": (D, 2048), "1.net.3.bias": (D,)}
+    w = {}
+    for k, s in sh.items():
+        if len(s) == 1:
+            w["layers.0." + k] = torch.randn(s, generator=g) * 0.1 + (1.0 if k.endswith("norm.weight") else 0.0)
+        else:
+            w["layers.0." + k] = torch.randn(s, generator=g) * (1.7 * s[1] ** -0.5)
+    return w
+
+
+def _rel(a, b, l2=False):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    if l2:
+        return float((a - b).norm() / b.norm().clamp_min(1e-30))
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("B,n,D,exact,tol", [(20, 9, 512, True, 2e-4), (20, 9, 512, False, 8e-3), (8, 30, 512, True, 2e-4),
+                                              (4, 5, 1024, False, 8e-3), (3, 48, 512, True, 2e-4), (1, 1, 512, True, 2e-4)])
+def test_transformer_v1_forward_backward_matches_oracle_autograd(B, n, D, exact, tol):
+    from clip_spm_b200.train import TransformerV1
+    w = _block_weights(D, B * 100 + n)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, n, D, generator=g)
+    go = torch.randn(B, n, D, generator=g)
+    wr = {k: v.double().requires_grad_(True) for k, v in w.items()}
+    xr = x.double().requires_grad_(True)
+    ref = O.transformer_v1(xr, wr, "")
+    (ref * go.double()).sum().backward()
+    wc = {k: v.cuda().requires_grad_(True) for k, v in w.items()}
+    xc = x.cuda().requires_grad_(True)
+    blk = TransformerV1(D, exact=exact)
+    out = blk(xc, wc)
+    (out * go.cuda()).sum().backward()
+    assert _rel(out, ref) < tol
+    assert _rel(xc.grad, xr.grad) < tol, "d x"
+    for k in w:
+        assert _rel(wc[k].grad, wr[k].grad) < tol, k
+    # a second graph on the same object reuses the returned handle
+    out2 = blk(xc.detach(), wc)
+    assert torch.equal(out2, out) and len(blk._all) == 1
+    blk.close()
+
+
+@pytest.mark.parametrize("act", ["none", "gelu", "leaky_relu", "sigmoid"])
+@pytest.mark.parametrize("M,N,K,exact,tol", [(225, 768, 512, True, 1e-4), (25, 256, 1024, False, 5e-3), (1, 2048, 512, True, 1e-4),
+                                             (330, 512, 1536, False, 5e-3)])
+def test_linear_backward_matches_torch_autograd(act, M, N, K, exact, tol):
+    from clip_spm_b200.train import linear
+    g = torch.Generator().manual_seed(M + N)
+    x, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * K ** -0.5, torch.randn(N, generator=g) * 0.1
+    go = torch.randn(M, N, generator=g)
+    fn = {"none": lambda t: t, "gelu": F.gelu, "sigmoid": torch.sigmoid, "leaky_relu": lambda t: F.leaky_relu(t, 0.0025)}[act]
+    xr, Wr, br = (t.double().requires_grad_(True) for t in (x, W, b))
+    ref = fn(F.linear(xr, Wr, br))
+    (ref * go.double()).sum().backward()
+    xc, Wc, bc = (t.cuda().requires_grad_(True) for t in (x, W, b))
+    out = linear(xc, Wc, bc, act, 0.0025, exact)
+    (out * go.cuda()).sum().backward()
+    # tf32 + LeakyReLU: a pre-activation within rounding of zero takes the other slope -> judged in L2
+    l2 = act == "leaky_relu" and not exact
+    assert _rel(out, ref) < tol
+    for name, mine, want in (("dx", xc.grad, xr.grad), ("dW", Wc.grad, Wr.grad), ("db", bc.grad, br.grad)):
+        assert _rel(mine, want, l2) < (3e-2 if l2 else tol), name
+
+
+def _cuda_head_grads(ci, exact):
+    from clip_spm_b200 import train
+    ep = ci["ep"]
+    w = {k: v.cuda().requires_grad_(True) for k, v in ci["w"].items() if v.dtype.is_floating_point}
+    su, qu = ci["su"].cuda().requires_grad_(True), ci["qu"].cuda().requires_grad_(True)
+    c1, c2 = train.TransformerV1(ci["D"], exact=exact), train.TransformerV1(ci["D"], exact=exact)
+    out = train.spm_head_forward(w, ci["text"].cuda(), su, qu, ep["context_labels"].cuda(), ep["real_support_labels"].cuda(),
+                                 ep["real_target_labels"].cuda(), O.DEFAULT_PARAMS, c1, c2, ci["single"], exact)
+    loss = train.spm_loss(out, ep["target_labels"].cuda(), 16.0)
+    loss.backward()
+    grads = {k: v.grad for k, v in w.items() if v.grad is not None}
+    grads["su"], grads["qu"] = su.grad, qu.grad
+    return out, loss.detach(), grads
+
+
+@pytest.mark.parametrize("name", list(HEAD_GRAD_CASES))
+def test_head_gradients_match_reference_golden_fp32(name):
+    """exact-fp32 products: every head-parameter and feature gradient the reference's backward produced"""
+    ci = head_grad_inputs(name)
+    gold = golden(name)
+    out, loss, grads = _cuda_head_grads(ci, exact=True)
+    assert torch.allclose(out["logits"].cpu(), gold["logits"], atol=5e-4, rtol=1e-4)
+    check_against_golden(grads, loss.cpu(), gold, 1e-3)
+
+
+@pytest.mark.parametrize("name", list(HEAD_GRAD_CASES))
+def test_head_gradients_match_reference_golden_tf32(name):
+    """tf32 tensor-core products (the training default): same goldens at the tf32 tolerance"""
+    ci = head_grad_inputs(name)
+    gold = golden(name)
+    out, loss, grads = _cuda_head_grads(ci, exact=False)
+    assert torch.allclose(out["logits"].cpu(), gold["logits"], atol=3e-2, rtol=1e-2)
+    check_against_golden(grads, loss.cpu(), gold, 5e-2, l2=True)
+
+
+def test_model_train_mode_steps_the_head():
+    """CNN in train mode: frames -> frozen tower -> differentiable head; run/main_run.py:245-254,207-209 with the library's
+    Adam and GradScaler.  The loss of a fixed episode must go down and only head parameters may move."""
+    from clip_spm_b200 import CNN, optim
+    ci = head_grad_inputs("head_grad_5w2s_t8")
+    ep = ci["ep"]
+    net = CNN(make_cfg(ci["backbone"], ci["T"], ci["single"], ci["way"]), text_features_test=ci["text"],
+              text_features_train=ci["text"], precision="bf16")
+    net.load_state_dict(ci["w"], strict=False)
+    net.train()
+    params = net.trainable_parameters()
+    names = [n for n, _ in net.named_parameters() if _.requires_grad]
+    assert names and not any(n.startswith("backbone.") for n in names)
+    before = {n: p.detach().clone() for n, p in net.named_parameters()}
+    opt = optim.Adam(params, lr=1e-4, betas=(0.5, 0.999), weight_decay=0.0)
+    scaler = optim.GradScaler("cuda", init_scale=1024.0)
+    losses = []
+    for _ in range(6):
+        out = net.head(ci["su"].cuda().unsqueeze(0), ci["qu"].cuda().unsqueeze(0), ep["context_labels"],
+                       ep["real_support_labels"], ep["real_target_labels"])
+        loss = net.loss(out, ep["target_labels"])
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        opt.zero_grad()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
+    moved = [n for n, p in net.named_parameters() if not torch.equal(p.detach().cpu(), before[n].cpu())]
+    assert moved and not any(n.startswith("backbone.") for n in moved)
+    # back to evaluation: the packed weights are rebuilt from the trained parameters
+    net.eval()
+    ev = net.head(ci["su"].cuda().unsqueeze(0), ci["qu"].cuda().unsqueeze(0), ep["context_labels"],
+                  ep["real_support_labels"], ep["real_target_labels"])
+    net.train()
+    tr = net.head(ci["su"].cuda().unsqueeze(0), ci["qu"].cuda().unsqueeze(0), ep["context_labels"],
+                  ep["real_support_labels"], ep["real_target_labels"])
+    assert torch.allclose(ev["logits"], tr["logits"].detach(), atol=2e-2, rtol=1e-2)
