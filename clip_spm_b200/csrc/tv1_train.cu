@@ -41,6 +41,11 @@ struct spm_tv1 {
   const float* x = nullptr;   // the caller's input of the last forward (must stay alive until backward)
   int B = 0, n = 0;
   float *HN = nullptr, *QKV = nullptr, *AO = nullptr, *Y = nullptr, *FFH = nullptr;
+  float p_atte = 0.f, p_ffn = 0.f;          // dropout of the NEXT forward (spm_tv1_set_dropout); fwd_* = of the last one
+  unsigned long long seed = 0;
+  float fwd_p_atte = 0.f, fwd_p_ffn = 0.f;
+  unsigned long long fwd_seed = 0;
+  float* G3 = nullptr;
   float *PRE = nullptr, *dY = nullptr, *dAO = nullptr, *dQKV = nullptr, *dHN = nullptr, *tA = nullptr, *tB = nullptr;
   std::vector<void*> allocs;
 };
@@ -124,6 +129,42 @@ __global__ void act_bwd_kernel(float* __restrict__ g, const float* __restrict__ 
     d = 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
   }
   g[i] = dy[i] * d;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11; the generator behind torch's CUDA dropout): counter (c.x..c.w), key (k.x, k.y)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// nn.Dropout(p) with a replayable mask: element i of `site` is kept iff (word i % 4 of philox(counter = (i / 4, site),
+// key = seed) >> 8) * 2^-24 >= p, kept values are scaled by 1 / (1 - p);  y = dropout(x) (+ add).  The same call with the
+// upstream gradient as x is the backward.  One thread per four consecutive elements (one Philox block).
+__global__ void dropout_kernel(const float* x, const float* __restrict__ add, float* y, long long n,
+                               float p, unsigned long long seed, unsigned site) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q * 4 >= n) return;
+  const uint4 r = philox4x32_10(make_uint4((unsigned)q, (unsigned)(q >> 32), site, 0u),
+                                make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  const unsigned w[4] = {r.x, r.y, r.z, r.w};
+  const float scale = 1.f / (1.f - p);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long i = q * 4 + j;
+    if (i < n) {
+      const float u = (float)(w[j] >> 8) * 5.9604644775390625e-08f;
+      float v = u >= p ? x[i] * scale : 0.f;
+      if (add != nullptr) v += add[i];
+      y[i] = v;
+    }
+  }
 }
 
 // LayerNorm backward, a warp per row: xhat = (x - mean) rstd;  dx = rstd (g gamma - mean(g gamma) - xhat mean(g gamma xhat)) + add
@@ -246,6 +287,13 @@ int tv1_transpose(cudaStream_t st, const float* in, int R, int C, float* out, in
   TV1_LAUNCH_CHECK();
   return 0;
 }
+int tv1_dropout(cudaStream_t st, const float* x, const float* add, float* y, long long n, float p, unsigned long long seed,
+                unsigned site) {
+  const long long quads = (n + 3) / 4;
+  dropout_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(x, add, y, n, p, seed, site);
+  TV1_LAUNCH_CHECK();
+  return 0;
+}
 int tv1_colsum(cudaStream_t st, const float* a, const float* b, int R, int C, float* out) {
   dim3 grid((C + 31) / 32), block(32, 8);
   colsum_kernel<<<grid, block, 0, st>>>(a, b, R, C, out);
@@ -271,7 +319,7 @@ int tv1_gemm(spm_tv1* h, cudaStream_t st, const float* A, long long lda, const f
 int tv1_workspace(spm_tv1* h, long long R) {
   if (R <= h->cap_rows) return 0;
   SPM_CUDA(cudaDeviceSynchronize());
-  for (float** p : {&h->HN, &h->QKV, &h->AO, &h->Y, &h->FFH, &h->PRE, &h->dY, &h->dAO, &h->dQKV, &h->dHN, &h->tA, &h->tB})
+  for (float** p : {&h->HN, &h->QKV, &h->AO, &h->Y, &h->FFH, &h->PRE, &h->dY, &h->dAO, &h->dQKV, &h->dHN, &h->tA, &h->tB, &h->G3})
     if (*p) { cudaFree(*p); h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), (void*)*p), h->allocs.end()); *p = nullptr; }
   const long long D = h->D, I = h->inner, M = h->mlp, Rp = (R + 3) / 4 * 4, big = std::max<long long>(3 * I, M);
   SPM_TRY(tv1_alloc(h, &h->HN, R * D));
@@ -284,6 +332,7 @@ int tv1_workspace(spm_tv1* h, long long R) {
   SPM_TRY(tv1_alloc(h, &h->dAO, R * I));
   SPM_TRY(tv1_alloc(h, &h->dQKV, R * 3 * I));
   SPM_TRY(tv1_alloc(h, &h->dHN, R * std::max(D, M)));   // also holds dFFH / dPRE [R, mlp]
+  SPM_TRY(tv1_alloc(h, &h->G3, R * D));
   SPM_TRY(tv1_alloc(h, &h->tA, big * Rp));
   SPM_TRY(tv1_alloc(h, &h->tB, big * Rp));
   h->cap_rows = R;
@@ -355,6 +404,19 @@ int spm_tv1_load_weights(spm_tv1* h, void* stream, const float* ln_g, const floa
   return 0;
 }
 
+int spm_tv1_set_dropout(spm_tv1* h, float p_atte, float p_ffn, unsigned long long seed) {
+  SPM_CHECK(h != nullptr, "spm_tv1_set_dropout: null handle");
+  SPM_CHECK(p_atte >= 0.f && p_atte < 1.f && p_ffn >= 0.f && p_ffn < 1.f, "spm_tv1_set_dropout: probabilities in [0, 1)");
+  h->p_atte = p_atte; h->p_ffn = p_ffn; h->seed = seed;
+  return 0;
+}
+
+int spm_dropout(void* stream, const float* x, long long n, float p, unsigned long long seed, unsigned site, float* y) {
+  SPM_CHECK(x && y && n > 0, "spm_dropout: null argument");
+  SPM_CHECK(p >= 0.f && p < 1.f, "spm_dropout: p in [0, 1)");
+  return tv1_dropout((cudaStream_t)stream, x, nullptr, y, n, p, seed, site);
+}
+
 int spm_tv1_forward(spm_tv1* h, void* stream, const float* x, int n_seq, int seq_len, float* out) {
   SPM_CHECK(h && x && out, "spm_tv1_forward: null argument");
   SPM_CHECK(h->loaded, "spm_tv1_forward: weights not loaded");
@@ -366,9 +428,24 @@ int spm_tv1_forward(spm_tv1* h, void* stream, const float* x, int n_seq, int seq
   TV1_KERNEL(k_layernorm(st, x, D, R, D, h->ln_g, h->ln_b, nullptr, 0, h->HN, nullptr, D));
   SPM_TRY(tv1_gemm(h, st, h->HN, D, h->wqkv, D, R, 3 * I, D, nullptr, ACT_NONE, nullptr, h->QKV));
   TV1_KERNEL(k_seq_attention(st, h->QKV, h->AO, n_seq, seq_len, 1, 0, seq_len, 0, 0, h->heads, h->dh));
-  SPM_TRY(tv1_gemm(h, st, h->AO, I, h->wout, I, R, D, I, h->bout, ACT_NONE, x, h->Y));
+  // nn.Dropout sites of the block (myRes.py:961-962 to_out, :990,992 FeedForward): 0 = after to_out, 1 = after GELU, 2 = after
+  // net.3; each is applied BEFORE the residual add, so with p > 0 the residual leaves the GEMM epilogue
+  h->fwd_p_atte = h->p_atte; h->fwd_p_ffn = h->p_ffn; h->fwd_seed = h->seed;
+  const long long nD = (long long)R * D, nM = (long long)R * M;
+  if (h->p_atte > 0.f) {
+    SPM_TRY(tv1_gemm(h, st, h->AO, I, h->wout, I, R, D, I, h->bout, ACT_NONE, nullptr, h->Y));
+    SPM_TRY(tv1_dropout(st, h->Y, x, h->Y, nD, h->p_atte, h->seed, 0));
+  } else {
+    SPM_TRY(tv1_gemm(h, st, h->AO, I, h->wout, I, R, D, I, h->bout, ACT_NONE, x, h->Y));
+  }
   SPM_TRY(tv1_gemm(h, st, h->Y, D, h->w0, D, R, M, D, h->b0, ACT_GELU_ERF, nullptr, h->FFH));
-  SPM_TRY(tv1_gemm(h, st, h->FFH, M, h->w3, M, R, D, M, h->b3, ACT_NONE, h->Y, out));
+  if (h->p_ffn > 0.f) {
+    SPM_TRY(tv1_dropout(st, h->FFH, nullptr, h->FFH, nM, h->p_ffn, h->seed, 1));
+    SPM_TRY(tv1_gemm(h, st, h->FFH, M, h->w3, M, R, D, M, h->b3, ACT_NONE, nullptr, out));
+    SPM_TRY(tv1_dropout(st, out, h->Y, out, nD, h->p_ffn, h->seed, 2));
+  } else {
+    SPM_TRY(tv1_gemm(h, st, h->FFH, M, h->w3, M, R, D, M, h->b3, ACT_NONE, h->Y, out));
+  }
   return 0;
 }
 
@@ -384,11 +461,16 @@ int spm_tv1_backward(spm_tv1* h, void* stream, const float* grad_out, float* gra
   const int D = h->D, I = h->inner, M = h->mlp, n = h->n, R = h->B * h->n, Rp = (R + 3) / 4 * 4;
   float* dF = h->dHN;   // [R, mlp]: dFFH, then dPRE in place
   // ---- out = W3 gelu(PRE) + b3 + y
-  SPM_TRY(tv1_colsum(st, grad_out, nullptr, R, D, g_b3));
-  SPM_TRY(tv1_transpose(st, grad_out, R, D, h->tA, Rp));
+  const long long nD = (long long)R * D, nM = (long long)R * M;
+  const float pa = h->fwd_p_atte, pf = h->fwd_p_ffn;
+  const float* g3 = grad_out;          // gradient behind the dropout of site 2 (the residual branch keeps grad_out itself)
+  if (pf > 0.f) { SPM_TRY(tv1_dropout(st, grad_out, nullptr, h->G3, nD, pf, h->fwd_seed, 2)); g3 = h->G3; }
+  SPM_TRY(tv1_colsum(st, g3, nullptr, R, D, g_b3));
+  SPM_TRY(tv1_transpose(st, g3, R, D, h->tA, Rp));
   SPM_TRY(tv1_transpose(st, h->FFH, R, M, h->tB, Rp));
-  SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, D, M, Rp, nullptr, ACT_NONE, nullptr, g_w3));             // dW3 = dOut^T gelu(PRE)
-  SPM_TRY(tv1_gemm(h, st, grad_out, D, h->w3T, D, R, M, D, nullptr, ACT_NONE, nullptr, dF));              // dFFH = dOut W3
+  SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, D, M, Rp, nullptr, ACT_NONE, nullptr, g_w3));             // dW3 = dOut^T drop(gelu(PRE))
+  SPM_TRY(tv1_gemm(h, st, g3, D, h->w3T, D, R, M, D, nullptr, ACT_NONE, nullptr, dF));                    // dFFH = dOut W3
+  if (pf > 0.f) SPM_TRY(tv1_dropout(st, dF, nullptr, dF, nM, pf, h->fwd_seed, 1));
   SPM_TRY(tv1_gemm(h, st, h->Y, D, h->w0, D, R, M, D, h->b0, ACT_NONE, nullptr, h->PRE));                 // PRE recomputed
   {
     const long long nel = (long long)R * M;
@@ -401,11 +483,13 @@ int spm_tv1_backward(spm_tv1* h, void* stream, const float* grad_out, float* gra
   SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, M, D, Rp, nullptr, ACT_NONE, nullptr, g_w0));              // dW0 = dPRE^T y
   SPM_TRY(tv1_gemm(h, st, dF, M, h->w0T, M, R, D, M, nullptr, ACT_NONE, grad_out, h->dY));                // dY = dPRE W0 + dOut
   // ---- y = Wout ao + b_out + x
-  SPM_TRY(tv1_colsum(st, h->dY, nullptr, R, D, g_bout));
-  SPM_TRY(tv1_transpose(st, h->dY, R, D, h->tA, Rp));
+  const float* gy = h->dY;             // gradient behind the dropout of site 0 (the residual branch keeps dY itself)
+  if (pa > 0.f) { SPM_TRY(tv1_dropout(st, h->dY, nullptr, h->G3, nD, pa, h->fwd_seed, 0)); gy = h->G3; }
+  SPM_TRY(tv1_colsum(st, gy, nullptr, R, D, g_bout));
+  SPM_TRY(tv1_transpose(st, gy, R, D, h->tA, Rp));
   SPM_TRY(tv1_transpose(st, h->AO, R, I, h->tB, Rp));
   SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, D, I, Rp, nullptr, ACT_NONE, nullptr, g_wout));            // dWout = dY^T ao
-  SPM_TRY(tv1_gemm(h, st, h->dY, D, h->woutT, D, R, I, D, nullptr, ACT_NONE, nullptr, h->dAO));           // dAO = dY Wout
+  SPM_TRY(tv1_gemm(h, st, gy, D, h->woutT, D, R, I, D, nullptr, ACT_NONE, nullptr, h->dAO));              // dAO = dY Wout
   // ---- attention
   SPM_CHECK(n <= TV1_SEQ_MAX && attn_bwd_smem(n, h->dh) <= attn_bwd_smem(48, 256), "spm_tv1_backward: sequence too long");
   {

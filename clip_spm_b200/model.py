@@ -386,8 +386,11 @@ class CNN(nn.Module):
         text = self.text_features_train.to(self._dev, torch.float32)
         w = dict(self.named_parameters())
         c1, c2 = self._train_blocks()
+        # train-mode dropout (myRes.py:961-996): one fresh 62-bit seed per forward from torch's CPU generator, so that
+        # torch.manual_seed reproduces a run; `model.train_dropout = False` gives the p = 0 head the parity goldens pin
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if getattr(self, "train_dropout", True) else None
         return _train.spm_head_forward(w, text, su, qu, lab, rs, rt, self.params, c1, c2, self.single_direct,
-                                       self.precision == "fp32")
+                                       self.precision == "fp32", seed)
 
     def loss(self, out, target_labels):
         """run/main_run.py:390-392 on a train-mode output (differentiable): CE / TASKS_PER_BATCH + 0.001 * dists."""

@@ -9,8 +9,9 @@ glue (gathers, concatenations, means, the gating products, `_dis`, the cross-ent
 not built: `CNN` in train mode encodes the frames without a graph and differentiates the head, i.e. it trains the head
 parameters of models/model_clipspm.py:72-99 with the CLIP tower frozen (the reference's optimiser also steps the tower).
 Dropout: `Transformer_v1` / `FeedForward` carry nn.Dropout(0.2 / 0.05) in the reference (myRes.py:964-996,1053-1064);
-here p = 0 by default (what the parity oracle pins against the reference); `dropout=True` draws the masks with torch's
-generator on the device and applies them as un-fused elementwise steps."""
+with `dropout_seed=None` p = 0 (what the parity oracle pins against the reference's backward); with a seed the library
+applies replayable Philox masks (spm_tv1_set_dropout / spm_dropout) at the reference's dropout sites -- the oracle
+regenerates the same masks on the CPU (oracle.dropout_mask), torch's own generator stream cannot be reproduced."""
 import ctypes
 
 import torch
@@ -18,7 +19,7 @@ import torch
 from . import _lib
 from .ops import ACT, _need_cuda, _ptr, _stream, otam_distance
 
-__all__ = ["linear", "TransformerV1", "spm_head_forward", "spm_loss"]
+__all__ = ["linear", "dropout", "TransformerV1", "spm_head_forward", "spm_loss"]
 
 
 class _Linear(torch.autograd.Function):
@@ -62,12 +63,39 @@ def linear(x, W, b=None, act="none", slope=0.0, exact=False):
     return y.view(*x.shape[:-1], W.shape[0])
 
 
+class _Dropout(torch.autograd.Function):
+    """nn.Dropout(p) with the library's replayable mask; the backward is the same kernel on the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, site):
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().spm_dropout(_stream(), _ptr(x), x.numel(), p, seed, site, _ptr(y)))
+        ctx.cfg = (p, seed, site)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        _lib.check(_lib.load().spm_dropout(_stream(), _ptr(dy), dy.numel(), *ctx.cfg, _ptr(dx)))
+        return dx, None, None, None
+
+
+def dropout(x, p, seed, site=0):
+    """y = x * keep / (1 - p) with keep a pure function of (seed, site, element index) (include/clipspm_b200.h)."""
+    _need_cuda(x)
+    if p <= 0.0:
+        return x
+    return _Dropout.apply(x.contiguous().float(), float(p), int(seed) & (2 ** 64 - 1), int(site))
+
+
 class _TV1(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, pool, *w):
+    def forward(ctx, x, pool, drop, *w):
         lib = _lib.load()
         h = pool._take()
         st = _stream()
+        _lib.check(lib.spm_tv1_set_dropout(h, *drop))
         _lib.check(lib.spm_tv1_load_weights(h, st, *[_ptr(t) for t in w]))
         B, n, D = x.shape
         out = torch.empty_like(x)
@@ -89,7 +117,7 @@ class _TV1(torch.autograd.Function):
             [torch.empty_like(t) for t in (wout, bout, w0, b0, w3, b3)]
         _lib.check(lib.spm_tv1_backward(ctx.h, _stream(), _ptr(go), _ptr(gx), *[_ptr(t) for t in g]))
         ctx.pool._give(ctx.h)
-        return (gx, None) + tuple(g)
+        return (gx, None, None) + tuple(g)
 
 
 class TransformerV1:
@@ -101,8 +129,9 @@ class TransformerV1:
     NAMES = ("0.norm.weight", "0.norm.bias", "0.fn.to_q.weight", "0.fn.to_k.weight", "0.fn.to_v.weight",
              "0.fn.to_out.0.weight", "0.fn.to_out.0.bias", "1.net.0.weight", "1.net.0.bias", "1.net.3.weight", "1.net.3.bias")
 
-    def __init__(self, dim, heads=8, dim_head=256, mlp_dim=2048, exact=False):
+    def __init__(self, dim, heads=8, dim_head=256, mlp_dim=2048, exact=False, dropout_atte=0.2, dropout_ffn=0.05):
         self.cfg = (int(dim), int(heads), int(dim_head), int(mlp_dim), 1 if exact else 0)
+        self.p = (float(dropout_atte), float(dropout_ffn))   # model_clipspm.py:80-81: dropout_atte=0.2, dropout_ffn default 0.05
         self._free, self._all = [], []
 
     def _take(self):
@@ -131,11 +160,13 @@ class TransformerV1:
         except Exception:
             pass
 
-    def __call__(self, x, weights, prefix="layers.0."):
-        """x [n_seq, seq_len, D] (seq_len <= 48); weights: mapping with the reference's parameter names under `prefix`."""
+    def __call__(self, x, weights, prefix="layers.0.", dropout_seed=None):
+        """x [n_seq, seq_len, D] (seq_len <= 48); weights: mapping with the reference's parameter names under `prefix`.
+        dropout_seed: None = no dropout (eval, or the p = 0 parity mode), else the 64-bit seed of this call's masks."""
         _need_cuda(x)
         w = [weights[prefix + n].contiguous() for n in self.NAMES]
-        return _TV1.apply(x.contiguous().float(), self, *w)
+        drop = (0.0, 0.0, 0) if dropout_seed is None else (self.p[0], self.p[1], int(dropout_seed) & (2 ** 64 - 1))
+        return _TV1.apply(x.contiguous().float(), self, drop, *w)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -161,10 +192,13 @@ def _gate(x, w, p, slope, exact):
     return linear(h, w[p + "2.weight"], w[p + "2.bias"], "sigmoid", 0.0, exact)
 
 
-def _feed_forward(x, w, p, exact):
-    """models/myRes.py:984-996 FeedForward with p = 0."""
+def _feed_forward(x, w, p, exact, drop_p=0.0, seed=None):
+    """models/myRes.py:984-996 FeedForward (Linear -> GELU -> Dropout -> Linear -> Dropout; seed None: p = 0)."""
     h = linear(x, w[p + "net.0.weight"], w[p + "net.0.bias"], "gelu", 0.0, exact)
-    return linear(h, w[p + "net.3.weight"], w[p + "net.3.bias"], "none", 0.0, exact)
+    if seed is not None:
+        h = dropout(h, drop_p, seed, 1)
+    y = linear(h, w[p + "net.3.weight"], w[p + "net.3.bias"], "none", 0.0, exact)
+    return dropout(y, drop_p, seed, 2) if seed is not None else y
 
 
 def _dis(x, y):
@@ -186,10 +220,13 @@ def _class_means(cm, x):
 
 
 def spm_head_forward(w, text_features, su, qu, support_labels, real_support, real_target, params, context1, context2,
-                     single_direct=False, exact=False):
+                     single_direct=False, exact=False, dropout_seed=None):
     """models/model_clipspm.py:116-143 after get_feats on su [S,T,D], qu [Q,T,D], differentiable with respect to the head
     parameters `w` (reference names) and the features.  The four live `se_te` calls (:296-314) share one `context2` pass;
-    the two whose outputs only reach the discarded consistency distances (:258-265) are skipped, as in the evaluation path."""
+    the two whose outputs only reach the discarded consistency distances (:258-265) are skipped, as in the evaluation path.
+    dropout_seed: None = p = 0; an int = the reference's train-mode dropout (token_tr 0.05, the blocks 0.2 / 0.05) with one
+    independent mask stream per call site (seed + k)."""
+    sd = (lambda k: None) if dropout_seed is None else (lambda k: int(dropout_seed) + k)
     S, T, D = su.shape
     Q = qu.shape[0]
     slope, alpha = float(params["negative_slope"]), float(params["alpha"])
@@ -199,7 +236,7 @@ def spm_head_forward(w, text_features, su, qu, support_labels, real_support, rea
     mo = _motion_feats(x, w, exact)                                                    # :194  [V,D]
     su_mo, qu_mo = mo[:S], mo[S:]
     token = torch.cat([ctx_q, ctx_s], dim=0).mean(dim=0)                               # :213-214 [1,D]
-    target_token = _feed_forward(token.expand(Q, -1, -1) * qu.mean(dim=[1, 2], keepdim=True), w, "token_tr.mlp.", exact)
+    target_token = _feed_forward(token.expand(Q, -1, -1) * qu.mean(dim=[1, 2], keepdim=True), w, "token_tr.mlp.", exact, 0.05, sd(0))
     # se_te x 4 (:196-197 on the motion tokens, :226,229 on the prompt tokens): [qu|su] frames with tokens [qu_mo|su_mo], then
     # [qu|su] with [target_token|ctx_s]
     tok = torch.cat([qu_mo.unsqueeze(1), su_mo.unsqueeze(1), target_token, ctx_s], dim=0)     # [2V,1,D]
@@ -207,7 +244,7 @@ def spm_head_forward(w, text_features, su, qu, support_labels, real_support, rea
     xg = x * gv
     xg = torch.cat([xg[S:], xg[:S], xg[S:], xg[:S]], dim=0)                            # [2V,T,D]
     q = tok * _gate(tok, w, "gate_text.", slope, exact) * alpha + xg
-    z = context2(torch.cat([tok, q], dim=1), w, "context2.layers.0.")                  # [2V,T+1,D]
+    z = context2(torch.cat([tok, q], dim=1), w, "context2.layers.0.", sd(1))           # [2V,T+1,D]
     zt, zf = z[:, 0, :], z[:, 1:, :]
     qu_m, su_m, qu_fake, su_real = zf[:Q], zf[Q:Q + S], zf[Q + S:2 * Q + S], zf[2 * Q + S:]
     qu_mo2, su_mo2 = zt[:Q], zt[Q:Q + S]
@@ -224,8 +261,8 @@ def spm_head_forward(w, text_features, su, qu, support_labels, real_support, rea
     token_q = token_s.mean(dim=0, keepdim=True)
     su_t = torch.cat([token_s, su_real], dim=0).permute(1, 0, 2)                       # [T,W+S,D]
     qu_t = torch.cat([token_q, qu_fake], dim=0).permute(1, 0, 2)                       # [T,1+Q,D]
-    _su = context1(su_t, w, "context1.layers.0.").permute(1, 0, 2)
-    _qu = context1(qu_t, w, "context1.layers.0.").permute(1, 0, 2)
+    _su = context1(su_t, w, "context1.layers.0.", sd(2)).permute(1, 0, 2)
+    _qu = context1(qu_t, w, "context1.layers.0.", sd(3)).permute(1, 0, 2)
     su_2, qu_2, su_t2, qu_t2 = _su[W:], _qu[1:], _su[:W], _qu[0:1]
     su_pro2 = _class_means(cm, su_2)                                                   # :133-137
     task_dist = otam_distance(su_pro2.unsqueeze(0), qu_2.unsqueeze(0), single_direct)[0] + \

@@ -218,6 +218,13 @@ int spm_tv1_load_weights(spm_tv1* h, void* stream, const float* ln_g, const floa
                          const float* wv, const float* wout, const float* bout, const float* w0, const float* b0,
                          const float* w3, const float* b3);   /* device pointers, reference layouts ([out, in]) */
 int spm_tv1_forward(spm_tv1* h, void* stream, const float* x, int n_seq, int seq_len, float* out);
+/* nn.Dropout of the block in the reference's train mode (models/myRes.py:961-962 after to_out: p_atte; :990,992 after GELU
+ * and after net.3: p_ffn; model_clipspm.py:80-81 builds the blocks with 0.2 / 0.05) for the forwards that follow.  The masks
+ * are a pure function of (seed, site, element index): Philox4x32-10 with counter (index / 4, site), key = seed, word
+ * index % 4; keep iff (word >> 8) * 2^-24 >= p; kept values times 1 / (1 - p) -- replayable by the oracle, never stored.
+ * spm_dropout applies the same mask to a plain tensor (y may alias x); calling it on the upstream gradient is its backward. */
+int spm_tv1_set_dropout(spm_tv1* h, float p_atte, float p_ffn, unsigned long long seed);
+int spm_dropout(void* stream, const float* x, long long n, float p, unsigned long long seed, unsigned site, float* y);
 int spm_tv1_backward(spm_tv1* h, void* stream, const float* grad_out, float* grad_x, float* g_ln_g, float* g_ln_b,
                      float* g_wq, float* g_wk, float* g_wv, float* g_wout, float* g_bout, float* g_w0, float* g_b0,
                      float* g_w3, float* g_b3);

@@ -132,13 +132,46 @@ def rn50_forward(w, images, prefix="backbone.", chunk=16):
 # =====================================================================================================
 # metric head
 # =====================================================================================================
-def feed_forward(x, w, p):
-    """models/myRes.py:984-996 FeedForward: Linear -> exact (erf) GELU -> Linear (dropouts are identity in eval)."""
+def feed_forward(x, w, p, masks=None):
+    """models/myRes.py:984-996 FeedForward: Linear -> exact (erf) GELU -> Dropout -> Linear -> Dropout (identity in eval;
+    in train mode `masks` = the two keep-masks already scaled by 1 / (1 - p), see dropout_mask)."""
     h = F.gelu(x @ w[p + "net.0.weight"].t() + w[p + "net.0.bias"])
-    return h @ w[p + "net.3.weight"].t() + w[p + "net.3.bias"]
+    if masks is not None:
+        h = h * masks[0]
+    y = h @ w[p + "net.3.weight"].t() + w[p + "net.3.bias"]
+    return y * masks[1] if masks is not None else y
 
 
-def transformer_v1(x, w, p, heads=8, dim_head=256, depth=1):
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon et al., SC'11) on numpy uint64 arrays holding 32-bit words: ctr = 4 arrays, key = 2 ints.
+    Known answers (Random123 kat_vectors) are checked in tests/test_train_cpu.py."""
+    import numpy as np
+    m32 = np.uint64(0xFFFFFFFF)
+    c = [np.asarray(v, dtype=np.uint64) for v in ctr]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    for _ in range(10):
+        p0, p1 = np.uint64(0xD2511F53) * c[0], np.uint64(0xCD9E8D57) * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & m32, p1 & m32, ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & m32, p0 & m32]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & m32, (k1 + np.uint64(0xBB67AE85)) & m32
+    return c
+
+
+def dropout_mask(shape, p, seed, site):
+    """The keep-mask (times 1 / (1 - p)) the library's train-mode dropout applies (include/clipspm_b200.h,
+    spm_tv1_set_dropout): element i keeps iff (word i % 4 of philox(counter = (i // 4, site), key = seed) >> 8) * 2^-24 >= p.
+    Replays the device masks on the CPU so that the oracle can follow a train-mode forward with p > 0."""
+    import numpy as np
+    n = int(np.prod(shape))
+    q = np.arange((n + 3) // 4, dtype=np.uint64)
+    words = philox4x32_10([q & np.uint64(0xFFFFFFFF), q >> np.uint64(32), np.full_like(q, site), np.zeros_like(q)],
+                          [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF])
+    r = np.stack(words, axis=1).reshape(-1)[:n]
+    u = (r >> np.uint64(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    keep = u >= np.float32(p)
+    return torch.from_numpy((keep.astype(np.float32) * (np.float32(1.0) / (np.float32(1.0) - np.float32(p)))).reshape(shape))
+
+
+def transformer_v1(x, w, p, heads=8, dim_head=256, depth=1, masks=None):
     """models/myRes.py:1066-1075 Transformer_v1.forward with q=k=v=x:
     PreNormattention_qkv (:1039-1040, the SAME LayerNorm on q,k,v, residual is the un-normalised q),
     Attention_qkv.forward (:964-982), then x = ff(x) + x; layers 1.. (depth > 1, :1070-1073) repeat it on the output."""
@@ -151,8 +184,11 @@ def transformer_v1(x, w, p, heads=8, dim_head=256, depth=1):
         v = (h @ w[l + "0.fn.to_v.weight"].t()).view(B, n, heads, dim_head).transpose(1, 2)
         att = torch.softmax((q @ k.transpose(-1, -2)) * dim_head ** -0.5, dim=-1)
         o = (att @ v).transpose(1, 2).reshape(B, n, heads * dim_head)
-        y = o @ w[l + "0.fn.to_out.0.weight"].t() + w[l + "0.fn.to_out.0.bias"] + x
-        x = feed_forward(y, w, l + "1.") + y
+        a = o @ w[l + "0.fn.to_out.0.weight"].t() + w[l + "0.fn.to_out.0.bias"]
+        if masks is not None:    # train mode: (to_out dropout :961-962, FeedForward's two :990,992) of layer 0
+            a = a * masks[0]
+        y = a + x
+        x = feed_forward(y, w, l + "1.", None if masks is None else masks[1:]) + y
     return x
 
 

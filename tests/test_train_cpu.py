@@ -59,7 +59,8 @@ def test_oracle_autograd_matches_reference_golden(name):
 class _Block:
     """stand-in for train.TransformerV1: the oracle's restatement of the block"""
 
-    def __call__(self, x, w, prefix):
+    def __call__(self, x, w, prefix, dropout_seed=None):
+        assert dropout_seed is None
         assert prefix.endswith("layers.0.")
         return O.transformer_v1(x, w, prefix[:-len("layers.0.")])
 
@@ -94,3 +95,16 @@ def test_train_head_composition_matches_oracle(name, monkeypatch):
     gold = golden(name)
     assert torch.allclose(out["logits"].detach(), gold["logits"], atol=2e-4, rtol=1e-4)
     check_against_golden(grads, loss.detach(), gold, 5e-4)
+
+
+def test_philox_known_answers_and_mask_statistics():
+    """oracle.philox4x32_10 against the Random123 known-answer vectors of Philox4x32-10; the keep rate of dropout_mask"""
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        assert [int(v) for v in O.philox4x32_10(ctr, key)] == want
+    m = O.dropout_mask((1000, 101), 0.2, 99, 0)
+    assert set(np.unique(m.numpy()).round(4)) == {0.0, 1.25} and abs(float((m > 0).float().mean()) - 0.8) < 5e-3
+    assert not torch.equal(m, O.dropout_mask((1000, 101), 0.2, 99, 1)) and not torch.equal(m, O.dropout_mask((1000, 101), 0.2, 98, 0))

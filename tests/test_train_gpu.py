@@ -82,6 +82,45 @@ def test_linear_backward_matches_torch_autograd(act, M, N, K, exact, tol):
         assert _rel(mine, want, l2) < (3e-2 if l2 else tol), name
 
 
+@pytest.mark.parametrize("B,n,D,exact,tol", [(20, 9, 512, True, 2e-4), (8, 30, 512, False, 8e-3), (5, 7, 1024, True, 2e-4)])
+def test_transformer_v1_dropout_replayed_by_the_oracle(B, n, D, exact, tol):
+    """train-mode dropout (p = 0.2 after to_out, 0.05 in the FeedForward): the oracle regenerates the library's Philox masks
+    on the CPU and must reproduce the forward and every gradient"""
+    from clip_spm_b200.train import TransformerV1
+    seed = 0x1234567890ABCDEF + B
+    w = _block_weights(D, B * 100 + n)
+    g = torch.Generator().manual_seed(11)
+    x, go = torch.randn(B, n, D, generator=g), torch.randn(B, n, D, generator=g)
+    masks = [O.dropout_mask((B, n, D), 0.2, seed, 0).double(), O.dropout_mask((B, n, 2048), 0.05, seed, 1).double(),
+             O.dropout_mask((B, n, D), 0.05, seed, 2).double()]
+    wr = {k: v.double().requires_grad_(True) for k, v in w.items()}
+    xr = x.double().requires_grad_(True)
+    ref = O.transformer_v1(xr, wr, "", masks=masks)
+    (ref * go.double()).sum().backward()
+    wc = {k: v.cuda().requires_grad_(True) for k, v in w.items()}
+    xc = x.cuda().requires_grad_(True)
+    blk = TransformerV1(D, exact=exact)
+    out = blk(xc, wc, dropout_seed=seed)
+    (out * go.cuda()).sum().backward()
+    assert _rel(out, ref) < tol
+    assert _rel(xc.grad, xr.grad) < tol, "d x"
+    for k in w:
+        assert _rel(wc[k].grad, wr[k].grad) < tol, k
+    plain = blk(xc.detach(), wc)
+    assert not torch.equal(plain, out.detach())          # p = 0 on the same handle: the masks are really off again
+    blk.close()
+
+
+def test_dropout_mask_matches_oracle_bit_for_bit():
+    from clip_spm_b200.train import dropout
+    x = torch.ones(1237, 33).cuda().requires_grad_(True)
+    y = dropout(x, 0.3, 2 ** 63 + 17, 5)
+    y.sum().backward()
+    want = O.dropout_mask((1237, 33), 0.3, 2 ** 63 + 17, 5)
+    assert torch.equal((y > 0).cpu(), want > 0) and torch.allclose(y.detach().cpu(), want, rtol=1e-6)
+    assert torch.equal(x.grad, y.detach())
+
+
 def _cuda_head_grads(ci, exact):
     from clip_spm_b200 import train
     ep = ci["ep"]
@@ -127,7 +166,20 @@ def test_model_train_mode_steps_the_head():
               text_features_train=ci["text"], precision="bf16")
     net.load_state_dict(ci["w"], strict=False)
     net.train()
-    params = net.trainable_parameters()
+    # train-mode dropout is on by default and reproducible through torch.manual_seed
+    hd = lambda: net.head(ci["su"].cuda().unsqueeze(0), ci["qu"].cuda().unsqueeze(0), ep["context_labels"],  # noqa: E731
+                          ep["real_support_labels"], ep["real_target_labels"])["logits"].detach()
+    hd_out = lambda: net.head(ci["su"].cuda().unsqueeze(0), ci["qu"].cuda().unsqueeze(0), ep["context_labels"],  # noqa: E731
+                              ep["real_support_labels"], ep["real_target_labels"])
+    torch.manual_seed(5)
+    a = hd()
+    b = hd()
+    torch.manual_seed(5)
+    c = hd()
+    assert torch.equal(a, c) and not torch.equal(a, b)
+    net.train_dropout = False
+    assert torch.equal(hd(), hd())
+    params = net.trainable_parameters()   # the loss-goes-down loop below runs without the dropout noise
     names = [n for n, _ in net.named_parameters() if _.requires_grad]
     assert names and not any(n.startswith("backbone.") for n in names)
     before = {n: p.detach().clone() for n, p in net.named_parameters()}
@@ -144,6 +196,12 @@ def test_model_train_mode_steps_the_head():
         opt.zero_grad()
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
+    net.train_dropout = True               # one more step the way the reference trains (dropout active)
+    scaler.scale(net.loss(hd_out(), ep["target_labels"])).backward()
+    scaler.step(opt)
+    scaler.update()
+    opt.zero_grad()
+    net.train_dropout = False
     moved = [n for n, p in net.named_parameters() if not torch.equal(p.detach().cpu(), before[n].cpu())]
     assert moved and not any(n.startswith("backbone.") for n in moved)
     # back to evaluation: the packed weights are rebuilt from the trained parameters
