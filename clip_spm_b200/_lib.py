@@ -76,6 +76,12 @@ SIGNATURES = {
     "spm_tv1_set_dropout": (c_int, [c_void_p, c_float, c_float, ctypes.c_ulonglong]),
     "spm_dropout": (c_int, [c_void_p, c_void_p, c_ll, c_float, ctypes.c_ulonglong, ctypes.c_uint, c_void_p]),
     "spm_tv1_backward": (c_int, [c_void_p, c_void_p] + [c_void_p] * 13),
+    "spm_vitblock_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    "spm_vitblock_load_weights": (c_int, [c_void_p, c_void_p] + [c_void_p] * 12),
+    "spm_vitblock_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "spm_vitblock_backward": (c_int, [c_void_p, c_void_p] + [c_void_p] * 14),
+    "spm_layernorm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "spm_layernorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 4),
     "spm_linear_backward_workspace": (c_ll, [c_int, c_int, c_int]),
     "spm_linear_backward": (c_int, [c_void_p, c_int] + [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float]
                             + [c_void_p] * 4 + [c_ll]),

@@ -16,8 +16,13 @@
 //   * attention backward: one CTA per (sequence, head) recomputes P from the saved q, k and forms dV = P^T dO,
 //     dS = P o (dO V^T - rowsum(dO V^T o P)), dQ = dS K / sqrt(dh), dK = dS^T Q / sqrt(dh) in shared memory;
 //   * LayerNorm backward: a warp per row (statistics recomputed), d gamma / d beta by a column-sum kernel; biases likewise.
-// Dropout (Attention_qkv / FeedForward, active in the reference's train mode) is NOT applied: this is the p = 0 block, which
-// is also what the parity oracle differentiates.  fp32 data; products in tf32 (precision 0) or exact fp32 SIMT (precision 1).
+// Dropout (Attention_qkv / FeedForward, active in the reference's train mode): replayable Philox masks, p = 0 by default.
+// fp32 data; products in tf32 (precision 0) or exact fp32 SIMT (precision 1).
+//
+// The same code with three switches is the frame encoder's residual block models/clip_fsar.py:622-643
+// `ResidualAttentionBlock` (spm_vitblock_*): a second LayerNorm in front of the MLP, biases on the fused q/k/v projection,
+// QuickGELU, and 197-token x 12-head x 64-dim attention (forward: the fp32 kernel of sgemm_f32.cu; backward: the two-phase
+// kernel below) -- i.e. the backward of the CLIP ViT-B/16 tower the reference's optimiser also steps.
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -32,11 +37,14 @@
 struct spm_tv1 {
   int D = 0, heads = 0, dh = 0, inner = 0, mlp = 0, fp32 = 0, sms = 148;
   bool loaded = false;
+  // ViT variant (clip_fsar.py:622-643): ln_2 before the MLP, q/k/v bias, QuickGELU, 197-token attention kernels
+  bool vit = false;
+  float *ln2_g = nullptr, *ln2_b = nullptr, *bqkv = nullptr, *H2 = nullptr;
   // weights (reference layouts) and their transposes
   float *ln_g = nullptr, *ln_b = nullptr, *wqkv = nullptr, *wout = nullptr, *bout = nullptr, *w0 = nullptr, *b0 = nullptr,
         *w3 = nullptr, *b3 = nullptr;
   float *wqkvT = nullptr, *woutT = nullptr, *w0T = nullptr, *w3T = nullptr;
-  // saved activations of the last forward and backward scratch, sized for cap_rows rows
+  // saved activations of the last forward, sized for cap_rows rows (the backward scratch is process-wide, Tv1Scratch)
   long long cap_rows = 0;
   const float* x = nullptr;   // the caller's input of the last forward (must stay alive until backward)
   int B = 0, n = 0;
@@ -45,8 +53,7 @@ struct spm_tv1 {
   unsigned long long seed = 0;
   float fwd_p_atte = 0.f, fwd_p_ffn = 0.f;
   unsigned long long fwd_seed = 0;
-  float* G3 = nullptr;
-  float *PRE = nullptr, *dY = nullptr, *dAO = nullptr, *dQKV = nullptr, *dHN = nullptr, *tA = nullptr, *tB = nullptr;
+
   std::vector<void*> allocs;
 };
 
@@ -197,7 +204,7 @@ __global__ void ln_bwd_kernel(const float* __restrict__ x, const float* __restri
   b /= (float)C;
   for (int c = lane; c < C; c += 32) {
     const float xh = (xr[c] - mean) * rstd;
-    dx[(long long)row * C + c] = rstd * (gr[c] * gamma[c] - a - xh * b) + add[(long long)row * C + c];
+    dx[(long long)row * C + c] = rstd * (gr[c] * gamma[c] - a - xh * b) + (add != nullptr ? add[(long long)row * C + c] : 0.f);
     gx[(long long)row * C + c] = gr[c] * xh;
   }
 }
@@ -272,6 +279,140 @@ seq_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict_
     r[2 * inner] = dv;
   }
 }
+// g[i] *= quickgelu'(pre[i]), quickgelu(x) = x sigmoid(1.702 x) (clip_fsar.py:618-620)
+__global__ void quickgelu_bwd_kernel(float* __restrict__ g, const float* __restrict__ pre, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = pre[i];
+  const float sg = 1.f / (1.f + expf(-1.702f * x));
+  g[i] *= sg * (1.f + 1.702f * x * (1.f - sg));
+}
+
+// Attention backward of the frame encoder: 197 tokens x 64 dims per (frame, head), 12 heads (clip_fsar.py:626,636-638).
+// One CTA per (frame, head) keeps q, k, v, dO [197][65] in shared memory (205 KB) and works in two phases, each the
+// forward kernel's shape (a warp per row, a lane per 7 columns of the score row, outputs as 2 dims per lane):
+//   phase 1, per QUERY row i:  p_i = softmax(q_i K^T / 8), dp_ij = dO_i . v_j, delta_i = sum_j p_ij dp_ij,
+//                              dq_i = 1/8 sum_j p_ij (dp_ij - delta_i) k_j;   keeps m_i, 1 / l_i, delta_i
+//   phase 2, per KEY row j:    p_ij and dp_ij rebuilt from the kept row statistics,
+//                              dk_j = 1/8 sum_i p_ij (dp_ij - delta_i) q_i,  dv_j = sum_i p_ij dO_i
+// -- no atomics, no [197 x 197] table; the price is computing the two score products twice.
+constexpr int VL = 197, VHD = 64, VHEADS = 12, VC = 768, VST = VHD + 1;
+constexpr int VIT_ATT_BWD_SMEM = (4 * VL * VST + 3 * VL) * 4;
+
+__global__ void __launch_bounds__(256)
+vit_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, float* __restrict__ dqkv) {
+  extern __shared__ float sm_vb[];
+  float* sQ = sm_vb;
+  float* sK = sQ + VL * VST;
+  float* sV = sK + VL * VST;
+  float* sO = sV + VL * VST;
+  float* sM = sO + VL * VST;      // row max
+  float* sL = sM + VL;            // 1 / row sum
+  float* sD = sL + VL;            // delta
+  const int frame = blockIdx.x / VHEADS, head = blockIdx.x % VHEADS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)frame * VL;
+  const float* base = qkv + row0 * (3 * VC) + head * VHD;
+  for (int i = threadIdx.x; i < VL * VHD; i += blockDim.x) {
+    const int r = i / VHD, d = i % VHD;
+    sQ[r * VST + d] = base[(long long)r * (3 * VC) + d];
+    sK[r * VST + d] = base[(long long)r * (3 * VC) + VC + d];
+    sV[r * VST + d] = base[(long long)r * (3 * VC) + 2 * VC + d];
+    sO[r * VST + d] = dO[(row0 + r) * VC + head * VHD + d];
+  }
+  __syncthreads();
+  float* out = dqkv + row0 * (3 * VC) + head * VHD;
+  // ---- phase 1: query rows
+  for (int i = warp; i < VL; i += 8) {
+    float s[7], dp[7];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      const int j = lane + 32 * t;
+      s[t] = -INFINITY;
+      dp[t] = 0.f;
+      if (j < VL) {
+        float a = 0.f, b = 0.f;
+        for (int d = 0; d < VHD; ++d) {
+          a = fmaf(sQ[i * VST + d], sK[j * VST + d], a);
+          b = fmaf(sO[i * VST + d], sV[j * VST + d], b);
+        }
+        s[t] = a * 0.125f;
+        dp[t] = b;
+      }
+      mx = fmaxf(mx, s[t]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float l = 0.f;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      s[t] = (lane + 32 * t < VL) ? expf(s[t] - mx) : 0.f;
+      l += s[t];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float inv = 1.f / l;
+    float delta = 0.f;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) { s[t] *= inv; delta = fmaf(s[t], dp[t], delta); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+    if (lane == 0) { sM[i] = mx; sL[i] = inv; sD[i] = delta; }
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      const float ds = s[t] * (dp[t] - delta);
+      for (int src = 0; src < 32; ++src) {
+        const int j = src + 32 * t;
+        if (j >= VL) break;
+        const float w = __shfl_sync(0xffffffffu, ds, src);
+        a0 = fmaf(w, sK[j * VST + lane], a0);
+        a1 = fmaf(w, sK[j * VST + lane + 32], a1);
+      }
+    }
+    out[(long long)i * (3 * VC) + lane] = a0 * 0.125f;
+    out[(long long)i * (3 * VC) + lane + 32] = a1 * 0.125f;
+  }
+  __syncthreads();
+  // ---- phase 2: key rows
+  for (int j = warp; j < VL; j += 8) {
+    float pr[7], ds[7];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      const int i = lane + 32 * t;
+      pr[t] = 0.f;
+      ds[t] = 0.f;
+      if (i < VL) {
+        float a = 0.f, b = 0.f;
+        for (int d = 0; d < VHD; ++d) {
+          a = fmaf(sQ[i * VST + d], sK[j * VST + d], a);
+          b = fmaf(sO[i * VST + d], sV[j * VST + d], b);
+        }
+        pr[t] = expf(a * 0.125f - sM[i]) * sL[i];
+        ds[t] = pr[t] * (b - sD[i]);
+      }
+    }
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      for (int src = 0; src < 32; ++src) {
+        const int i = src + 32 * t;
+        if (i >= VL) break;
+        const float wd = __shfl_sync(0xffffffffu, ds[t], src), wp = __shfl_sync(0xffffffffu, pr[t], src);
+        k0 = fmaf(wd, sQ[i * VST + lane], k0);
+        k1 = fmaf(wd, sQ[i * VST + lane + 32], k1);
+        v0 = fmaf(wp, sO[i * VST + lane], v0);
+        v1 = fmaf(wp, sO[i * VST + lane + 32], v1);
+      }
+    }
+    out[(long long)j * (3 * VC) + VC + lane] = k0 * 0.125f;
+    out[(long long)j * (3 * VC) + VC + lane + 32] = k1 * 0.125f;
+    out[(long long)j * (3 * VC) + 2 * VC + lane] = v0;
+    out[(long long)j * (3 * VC) + 2 * VC + lane + 32] = v1;
+  }
+}
+
 constexpr int TV1_SEQ_MAX = 64;
 size_t attn_bwd_smem(int n, int dh) { return (size_t)(4 * n * (dh + 1) + 2 * n * n) * sizeof(float); }
 
@@ -316,26 +457,207 @@ int tv1_gemm(spm_tv1* h, cudaStream_t st, const float* A, long long lda, const f
   return 0;
 }
 
+// Backward scratch (recomputed pre-activation, gradient tensors, transposed copies) is shared by every handle of the
+// process: a training step runs its blocks one after the other on one stream, and 12 encoder blocks x 3 GB of private
+// scratch would be waste.  The per-handle buffers are only what a forward must keep for its backward.
+struct Tv1Scratch {
+  long long cap_rows = 0, cap_wide = 0, cap_d = 0, cap_i3 = 0;
+  float *PRE = nullptr, *dY = nullptr, *dAO = nullptr, *dQKV = nullptr, *dHN = nullptr, *tA = nullptr, *tB = nullptr, *G3 = nullptr;
+} g_scr;
+
+int tv1_scratch(const spm_tv1* h, long long R) {
+  const long long D = h->D, I3 = 3LL * h->inner, wide = std::max<long long>(std::max<long long>(I3, h->mlp), D);
+  if (R <= g_scr.cap_rows && wide <= g_scr.cap_wide && D <= g_scr.cap_d && I3 <= g_scr.cap_i3) return 0;
+  SPM_CUDA(cudaDeviceSynchronize());
+  for (float** p : {&g_scr.PRE, &g_scr.dY, &g_scr.dAO, &g_scr.dQKV, &g_scr.dHN, &g_scr.tA, &g_scr.tB, &g_scr.G3})
+    if (*p) { cudaFree(*p); *p = nullptr; }
+  const long long r = std::max(R, g_scr.cap_rows), w = std::max(wide, g_scr.cap_wide), d = std::max(D, g_scr.cap_d),
+                  i3 = std::max(I3, g_scr.cap_i3), rp = (r + 3) / 4 * 4;
+  g_scr.cap_rows = g_scr.cap_wide = g_scr.cap_d = g_scr.cap_i3 = 0;
+  auto al = [](float** p, long long n) { return cudaMalloc(reinterpret_cast<void**>(p), (size_t)n * sizeof(float)); };
+  SPM_CUDA(al(&g_scr.PRE, r * w));
+  SPM_CUDA(al(&g_scr.dY, r * d));
+  SPM_CUDA(al(&g_scr.dAO, r * i3 / 3));
+  SPM_CUDA(al(&g_scr.dQKV, r * i3));
+  SPM_CUDA(al(&g_scr.dHN, r * w));      // also dFFH / dPRE [R, mlp]
+  SPM_CUDA(al(&g_scr.tA, w * rp));
+  SPM_CUDA(al(&g_scr.tB, w * rp));
+  SPM_CUDA(al(&g_scr.G3, r * d));
+  g_scr.cap_rows = r; g_scr.cap_wide = w; g_scr.cap_d = d; g_scr.cap_i3 = i3;
+  return 0;
+}
+
 int tv1_workspace(spm_tv1* h, long long R) {
   if (R <= h->cap_rows) return 0;
   SPM_CUDA(cudaDeviceSynchronize());
-  for (float** p : {&h->HN, &h->QKV, &h->AO, &h->Y, &h->FFH, &h->PRE, &h->dY, &h->dAO, &h->dQKV, &h->dHN, &h->tA, &h->tB, &h->G3})
+  for (float** p : {&h->HN, &h->QKV, &h->AO, &h->Y, &h->FFH, &h->H2})
     if (*p) { cudaFree(*p); h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), (void*)*p), h->allocs.end()); *p = nullptr; }
-  const long long D = h->D, I = h->inner, M = h->mlp, Rp = (R + 3) / 4 * 4, big = std::max<long long>(3 * I, M);
+  const long long D = h->D, I = h->inner, M = h->mlp;
   SPM_TRY(tv1_alloc(h, &h->HN, R * D));
   SPM_TRY(tv1_alloc(h, &h->QKV, R * 3 * I));
   SPM_TRY(tv1_alloc(h, &h->AO, R * I));
   SPM_TRY(tv1_alloc(h, &h->Y, R * D));
   SPM_TRY(tv1_alloc(h, &h->FFH, R * M));
-  SPM_TRY(tv1_alloc(h, &h->PRE, R * M));
-  SPM_TRY(tv1_alloc(h, &h->dY, R * D));
-  SPM_TRY(tv1_alloc(h, &h->dAO, R * I));
-  SPM_TRY(tv1_alloc(h, &h->dQKV, R * 3 * I));
-  SPM_TRY(tv1_alloc(h, &h->dHN, R * std::max(D, M)));   // also holds dFFH / dPRE [R, mlp]
-  SPM_TRY(tv1_alloc(h, &h->G3, R * D));
-  SPM_TRY(tv1_alloc(h, &h->tA, big * Rp));
-  SPM_TRY(tv1_alloc(h, &h->tB, big * Rp));
+  if (h->vit) SPM_TRY(tv1_alloc(h, &h->H2, R * D));
   h->cap_rows = R;
+  return 0;
+}
+
+int block_create(int D, int heads, int dim_head, int mlp_dim, int precision, bool vit, spm_tv1** out) {
+  SPM_CHECK(out != nullptr, "block create: null argument");
+  SPM_CHECK(D > 0 && D % 32 == 0 && heads > 0 && dim_head > 0 && dim_head % 32 == 0 && dim_head <= 256 && mlp_dim % 32 == 0,
+            "block create: D, dim_head and mlp_dim must be multiples of 32 (dim_head <= 256)");
+  SPM_CHECK(precision == 0 || precision == 1, "block create: precision 0 (tf32 products) or 1 (fp32)");
+  int ndev = 0;
+  SPM_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "block create: no CUDA device -- this library has no CPU path");
+  const char* err = "";
+  SPM_CHECK(gemm_init(&err) == 0 && gemm2_init(&err) == 0, "block create: gemm_init failed");
+  SPM_CHECK(k_seq_attention_init() == 0 && k_vit_attention_f32_init() == 0, "block create: cudaFuncSetAttribute failed");
+  SPM_CUDA(cudaFuncSetAttribute(seq_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)attn_bwd_smem(48, 256)));
+  SPM_CUDA(cudaFuncSetAttribute(vit_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VIT_ATT_BWD_SMEM));
+  spm_tv1* h = new spm_tv1();
+  h->D = D; h->heads = heads; h->dh = dim_head; h->inner = heads * dim_head; h->mlp = mlp_dim; h->fp32 = precision; h->vit = vit;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, dev);
+  *out = h;
+  return 0;
+}
+
+// weights: wqkv = [q; k; v] rows ([3*inner, D]); ViT: + bqkv, ln2
+int block_load(spm_tv1* h, cudaStream_t st, const float* ln_g, const float* ln_b, const float* wq, const float* wk,
+               const float* wv, const float* bqkv, const float* wout, const float* bout, const float* ln2_g, const float* ln2_b,
+               const float* w0, const float* b0, const float* w3, const float* b3) {
+  const long long D = h->D, I = h->inner, M = h->mlp;
+  if (!h->loaded) {
+    SPM_TRY(tv1_alloc(h, &h->ln_g, D)); SPM_TRY(tv1_alloc(h, &h->ln_b, D));
+    SPM_TRY(tv1_alloc(h, &h->wqkv, 3 * I * D)); SPM_TRY(tv1_alloc(h, &h->wout, D * I)); SPM_TRY(tv1_alloc(h, &h->bout, D));
+    SPM_TRY(tv1_alloc(h, &h->w0, M * D)); SPM_TRY(tv1_alloc(h, &h->b0, M));
+    SPM_TRY(tv1_alloc(h, &h->w3, D * M)); SPM_TRY(tv1_alloc(h, &h->b3, D));
+    SPM_TRY(tv1_alloc(h, &h->wqkvT, D * 3 * I)); SPM_TRY(tv1_alloc(h, &h->woutT, I * D));
+    SPM_TRY(tv1_alloc(h, &h->w0T, D * M)); SPM_TRY(tv1_alloc(h, &h->w3T, M * D));
+    if (h->vit) { SPM_TRY(tv1_alloc(h, &h->ln2_g, D)); SPM_TRY(tv1_alloc(h, &h->ln2_b, D)); SPM_TRY(tv1_alloc(h, &h->bqkv, 3 * I)); }
+    h->loaded = true;
+  }
+  auto cp = [&](float* dst, const float* src, long long n) {
+    return cudaMemcpyAsync(dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+  };
+  SPM_CUDA(cp(h->ln_g, ln_g, D)); SPM_CUDA(cp(h->ln_b, ln_b, D));
+  SPM_CUDA(cp(h->wqkv, wq, I * D)); SPM_CUDA(cp(h->wqkv + I * D, wk, I * D)); SPM_CUDA(cp(h->wqkv + 2 * I * D, wv, I * D));
+  SPM_CUDA(cp(h->wout, wout, D * I)); SPM_CUDA(cp(h->bout, bout, D));
+  SPM_CUDA(cp(h->w0, w0, M * D)); SPM_CUDA(cp(h->b0, b0, M)); SPM_CUDA(cp(h->w3, w3, D * M)); SPM_CUDA(cp(h->b3, b3, D));
+  if (h->vit) { SPM_CUDA(cp(h->ln2_g, ln2_g, D)); SPM_CUDA(cp(h->ln2_b, ln2_b, D)); SPM_CUDA(cp(h->bqkv, bqkv, 3 * I)); }
+  // transposes for the dgrad GEMMs (B operand = W^T, K-contiguous): [rows, cols] -> [cols, rows]
+  SPM_TRY(tv1_transpose(st, h->wqkv, (int)(3 * I), (int)D, h->wqkvT, (int)(3 * I)));
+  SPM_TRY(tv1_transpose(st, h->wout, (int)D, (int)I, h->woutT, (int)D));
+  SPM_TRY(tv1_transpose(st, h->w0, (int)M, (int)D, h->w0T, (int)M));
+  SPM_TRY(tv1_transpose(st, h->w3, (int)D, (int)M, h->w3T, (int)D));
+  return 0;
+}
+
+int block_forward(spm_tv1* h, cudaStream_t st, const float* x, int n_seq, int seq_len, float* out) {
+  const int D = h->D, I = h->inner, M = h->mlp, R = n_seq * seq_len;
+  SPM_TRY(tv1_workspace(h, R));
+  h->x = x; h->B = n_seq; h->n = seq_len;
+  TV1_KERNEL(k_layernorm(st, x, D, R, D, h->ln_g, h->ln_b, nullptr, 0, h->HN, nullptr, D));
+  SPM_TRY(tv1_gemm(h, st, h->HN, D, h->wqkv, D, R, 3 * I, D, h->vit ? h->bqkv : nullptr, ACT_NONE, nullptr, h->QKV));
+  if (h->vit) TV1_KERNEL(k_vit_attention_f32(st, h->QKV, h->AO, n_seq));
+  else TV1_KERNEL(k_seq_attention(st, h->QKV, h->AO, n_seq, seq_len, 1, 0, seq_len, 0, 0, h->heads, h->dh));
+  // nn.Dropout sites of the block (myRes.py:961-962 to_out, :990,992 FeedForward): 0 = after to_out, 1 = after GELU, 2 = after
+  // net.3; each is applied BEFORE the residual add, so with p > 0 the residual leaves the GEMM epilogue
+  h->fwd_p_atte = h->p_atte; h->fwd_p_ffn = h->p_ffn; h->fwd_seed = h->seed;
+  const long long nD = (long long)R * D, nM = (long long)R * M;
+  if (h->p_atte > 0.f) {
+    SPM_TRY(tv1_gemm(h, st, h->AO, I, h->wout, I, R, D, I, h->bout, ACT_NONE, nullptr, h->Y));
+    SPM_TRY(tv1_dropout(st, h->Y, x, h->Y, nD, h->p_atte, h->seed, 0));
+  } else {
+    SPM_TRY(tv1_gemm(h, st, h->AO, I, h->wout, I, R, D, I, h->bout, ACT_NONE, x, h->Y));
+  }
+  const float* h2 = h->Y;          // input of the MLP: y itself, or ln_2(y) in the encoder block
+  if (h->vit) {
+    TV1_KERNEL(k_layernorm(st, h->Y, D, R, D, h->ln2_g, h->ln2_b, nullptr, 0, h->H2, nullptr, D));
+    h2 = h->H2;
+  }
+  const int act = h->vit ? ACT_QUICKGELU : ACT_GELU_ERF;
+  SPM_TRY(tv1_gemm(h, st, h2, D, h->w0, D, R, M, D, h->b0, act, nullptr, h->FFH));
+  if (h->p_ffn > 0.f) {
+    SPM_TRY(tv1_dropout(st, h->FFH, nullptr, h->FFH, nM, h->p_ffn, h->seed, 1));
+    SPM_TRY(tv1_gemm(h, st, h->FFH, M, h->w3, M, R, D, M, h->b3, ACT_NONE, nullptr, out));
+    SPM_TRY(tv1_dropout(st, out, h->Y, out, nD, h->p_ffn, h->seed, 2));
+  } else {
+    SPM_TRY(tv1_gemm(h, st, h->FFH, M, h->w3, M, R, D, M, h->b3, ACT_NONE, h->Y, out));
+  }
+  return 0;
+}
+
+// g_qkv: [3*inner, D]; g_bqkv / g_ln2_*: ViT only
+int block_backward(spm_tv1* h, cudaStream_t st, const float* grad_out, float* grad_x, float* g_ln_g, float* g_ln_b,
+                   float* g_qkv, float* g_bqkv, float* g_wout, float* g_bout, float* g_ln2_g, float* g_ln2_b, float* g_w0,
+                   float* g_b0, float* g_w3, float* g_b3) {
+  const int D = h->D, I = h->inner, M = h->mlp, n = h->n, R = h->B * h->n, Rp = (R + 3) / 4 * 4;
+  SPM_TRY(tv1_scratch(h, R));
+  Tv1Scratch& s = g_scr;
+  float* dF = s.dHN;   // [R, mlp]: dFFH, then dPRE in place
+  const long long nD = (long long)R * D, nM = (long long)R * M;
+  const float pa = h->fwd_p_atte, pf = h->fwd_p_ffn;
+  const float* h2 = h->vit ? h->H2 : h->Y;
+  // ---- out = drop2(W3 drop1(act(PRE)) + b3) + y
+  const float* g3 = grad_out;          // gradient behind the dropout of site 2 (the residual branch keeps grad_out itself)
+  if (pf > 0.f) { SPM_TRY(tv1_dropout(st, grad_out, nullptr, s.G3, nD, pf, h->fwd_seed, 2)); g3 = s.G3; }
+  SPM_TRY(tv1_colsum(st, g3, nullptr, R, D, g_b3));
+  SPM_TRY(tv1_transpose(st, g3, R, D, s.tA, Rp));
+  SPM_TRY(tv1_transpose(st, h->FFH, R, M, s.tB, Rp));
+  SPM_TRY(tv1_gemm(h, st, s.tA, Rp, s.tB, Rp, D, M, Rp, nullptr, ACT_NONE, nullptr, g_w3));               // dW3 = dOut^T drop(act(PRE))
+  SPM_TRY(tv1_gemm(h, st, g3, D, h->w3T, D, R, M, D, nullptr, ACT_NONE, nullptr, dF));                    // dFFH = dOut W3
+  if (pf > 0.f) SPM_TRY(tv1_dropout(st, dF, nullptr, dF, nM, pf, h->fwd_seed, 1));
+  SPM_TRY(tv1_gemm(h, st, h2, D, h->w0, D, R, M, D, h->b0, ACT_NONE, nullptr, s.PRE));                    // PRE recomputed
+  if (h->vit) quickgelu_bwd_kernel<<<(unsigned)((nM + 255) / 256), 256, 0, st>>>(dF, s.PRE, nM);
+  else gelu_bwd_kernel<<<(unsigned)((nM + 255) / 256), 256, 0, st>>>(dF, s.PRE, nM);
+  TV1_LAUNCH_CHECK();
+  SPM_TRY(tv1_colsum(st, dF, nullptr, R, M, g_b0));
+  SPM_TRY(tv1_transpose(st, dF, R, M, s.tA, Rp));
+  SPM_TRY(tv1_transpose(st, h2, R, D, s.tB, Rp));
+  SPM_TRY(tv1_gemm(h, st, s.tA, Rp, s.tB, Rp, M, D, Rp, nullptr, ACT_NONE, nullptr, g_w0));               // dW0 = dPRE^T h2
+  if (h->vit) {
+    // h2 = ln_2(y): dY = LN-backward(dPRE W0) + dOut
+    SPM_TRY(tv1_gemm(h, st, dF, M, h->w0T, M, R, D, M, nullptr, ACT_NONE, nullptr, s.PRE));               // dH2 (PRE is free again)
+    SPM_TRY(tv1_colsum(st, s.PRE, nullptr, R, D, g_ln2_b));
+    ln_bwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(h->Y, s.PRE, h->ln2_g, grad_out, R, D, s.dY, s.tA);        // tA := yhat o dH2
+    TV1_LAUNCH_CHECK();
+    SPM_TRY(tv1_colsum(st, s.tA, nullptr, R, D, g_ln2_g));
+  } else {
+    SPM_TRY(tv1_gemm(h, st, dF, M, h->w0T, M, R, D, M, nullptr, ACT_NONE, grad_out, s.dY));               // dY = dPRE W0 + dOut
+  }
+  // ---- y = drop0(Wout ao + b_out) + x
+  const float* gy = s.dY;              // gradient behind the dropout of site 0 (the residual branch keeps dY itself)
+  if (pa > 0.f) { SPM_TRY(tv1_dropout(st, s.dY, nullptr, s.G3, nD, pa, h->fwd_seed, 0)); gy = s.G3; }
+  SPM_TRY(tv1_colsum(st, gy, nullptr, R, D, g_bout));
+  SPM_TRY(tv1_transpose(st, gy, R, D, s.tA, Rp));
+  SPM_TRY(tv1_transpose(st, h->AO, R, I, s.tB, Rp));
+  SPM_TRY(tv1_gemm(h, st, s.tA, Rp, s.tB, Rp, D, I, Rp, nullptr, ACT_NONE, nullptr, g_wout));             // dWout = dY^T ao
+  SPM_TRY(tv1_gemm(h, st, gy, D, h->woutT, D, R, I, D, nullptr, ACT_NONE, nullptr, s.dAO));               // dAO = dY Wout
+  // ---- attention
+  if (h->vit) {
+    vit_attention_bwd_kernel<<<h->B * VHEADS, 256, VIT_ATT_BWD_SMEM, st>>>(h->QKV, s.dAO, s.dQKV);
+    TV1_LAUNCH_CHECK();
+  } else {
+    SPM_CHECK(n <= TV1_SEQ_MAX && attn_bwd_smem(n, h->dh) <= attn_bwd_smem(48, 256), "block backward: sequence too long");
+    dim3 grid(h->B, h->heads);
+    seq_attention_bwd_kernel<<<grid, 256, attn_bwd_smem(n, h->dh), st>>>(h->QKV, s.dAO, s.dQKV, n, h->heads, h->dh);
+    TV1_LAUNCH_CHECK();
+  }
+  // ---- q, k, v = W{q,k,v} LN(x) (+ b)
+  if (h->vit) SPM_TRY(tv1_colsum(st, s.dQKV, nullptr, R, 3 * I, g_bqkv));
+  SPM_TRY(tv1_transpose(st, s.dQKV, R, 3 * I, s.tA, Rp));
+  SPM_TRY(tv1_transpose(st, h->HN, R, D, s.tB, Rp));
+  SPM_TRY(tv1_gemm(h, st, s.tA, Rp, s.tB, Rp, 3 * I, D, Rp, nullptr, ACT_NONE, nullptr, g_qkv));          // [dWq; dWk; dWv]
+  SPM_TRY(tv1_gemm(h, st, s.dQKV, 3 * I, h->wqkvT, 3 * I, R, D, 3 * I, nullptr, ACT_NONE, nullptr, s.dHN));   // dLN = dQKV Wqkv
+  // ---- LayerNorm + the residual branch (dY)
+  SPM_TRY(tv1_colsum(st, s.dHN, nullptr, R, D, g_ln_b));
+  ln_bwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(h->x, s.dHN, h->ln_g, s.dY, R, D, grad_x, s.tA);             // tA := xhat o dLN
+  TV1_LAUNCH_CHECK();
+  SPM_TRY(tv1_colsum(st, s.tA, nullptr, R, D, g_ln_g));
   return 0;
 }
 
@@ -347,24 +669,7 @@ using namespace spm;
 extern "C" {
 
 int spm_tv1_create(int D, int heads, int dim_head, int mlp_dim, int precision, spm_tv1** out) {
-  SPM_CHECK(out != nullptr, "spm_tv1_create: null argument");
-  SPM_CHECK(D > 0 && D % 32 == 0 && heads > 0 && dim_head > 0 && dim_head % 32 == 0 && dim_head <= 256 && mlp_dim % 32 == 0,
-            "spm_tv1_create: D, dim_head and mlp_dim must be multiples of 32 (dim_head <= 256)");
-  SPM_CHECK(precision == 0 || precision == 1, "spm_tv1_create: precision 0 (tf32 products) or 1 (fp32)");
-  int ndev = 0;
-  SPM_CHECK(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "spm_tv1_create: no CUDA device -- this library has no CPU path");
-  const char* err = "";
-  SPM_CHECK(gemm_init(&err) == 0 && gemm2_init(&err) == 0, "spm_tv1_create: gemm_init failed");
-  SPM_CHECK(k_seq_attention_init() == 0, "spm_tv1_create: cudaFuncSetAttribute failed");
-  SPM_CUDA(cudaFuncSetAttribute(seq_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)attn_bwd_smem(48, 256)));
-  spm_tv1* h = new spm_tv1();
-  h->D = D; h->heads = heads; h->dh = dim_head; h->inner = heads * dim_head; h->mlp = mlp_dim; h->fp32 = precision;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, dev);
-  *out = h;
-  return 0;
+  return block_create(D, heads, dim_head, mlp_dim, precision, false, out);
 }
 
 int spm_tv1_destroy(spm_tv1* h) {
@@ -378,30 +683,8 @@ int spm_tv1_load_weights(spm_tv1* h, void* stream, const float* ln_g, const floa
                          const float* wv, const float* wout, const float* bout, const float* w0, const float* b0,
                          const float* w3, const float* b3) {
   SPM_CHECK(h && ln_g && ln_b && wq && wk && wv && wout && bout && w0 && b0 && w3 && b3, "spm_tv1_load_weights: null argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long D = h->D, I = h->inner, M = h->mlp;
-  if (!h->loaded) {
-    SPM_TRY(tv1_alloc(h, &h->ln_g, D)); SPM_TRY(tv1_alloc(h, &h->ln_b, D));
-    SPM_TRY(tv1_alloc(h, &h->wqkv, 3 * I * D)); SPM_TRY(tv1_alloc(h, &h->wout, D * I)); SPM_TRY(tv1_alloc(h, &h->bout, D));
-    SPM_TRY(tv1_alloc(h, &h->w0, M * D)); SPM_TRY(tv1_alloc(h, &h->b0, M));
-    SPM_TRY(tv1_alloc(h, &h->w3, D * M)); SPM_TRY(tv1_alloc(h, &h->b3, D));
-    SPM_TRY(tv1_alloc(h, &h->wqkvT, D * 3 * I)); SPM_TRY(tv1_alloc(h, &h->woutT, I * D));
-    SPM_TRY(tv1_alloc(h, &h->w0T, D * M)); SPM_TRY(tv1_alloc(h, &h->w3T, M * D));
-    h->loaded = true;
-  }
-  auto cp = [&](float* dst, const float* src, long long n) {
-    return cudaMemcpyAsync(dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
-  };
-  SPM_CUDA(cp(h->ln_g, ln_g, D)); SPM_CUDA(cp(h->ln_b, ln_b, D));
-  SPM_CUDA(cp(h->wqkv, wq, I * D)); SPM_CUDA(cp(h->wqkv + I * D, wk, I * D)); SPM_CUDA(cp(h->wqkv + 2 * I * D, wv, I * D));
-  SPM_CUDA(cp(h->wout, wout, D * I)); SPM_CUDA(cp(h->bout, bout, D));
-  SPM_CUDA(cp(h->w0, w0, M * D)); SPM_CUDA(cp(h->b0, b0, M)); SPM_CUDA(cp(h->w3, w3, D * M)); SPM_CUDA(cp(h->b3, b3, D));
-  // transposes for the dgrad GEMMs (B operand = W^T, K-contiguous): [rows, cols] -> [cols, rows]
-  SPM_TRY(tv1_transpose(st, h->wqkv, (int)(3 * I), (int)D, h->wqkvT, (int)(3 * I)));
-  SPM_TRY(tv1_transpose(st, h->wout, (int)D, (int)I, h->woutT, (int)D));
-  SPM_TRY(tv1_transpose(st, h->w0, (int)M, (int)D, h->w0T, (int)M));
-  SPM_TRY(tv1_transpose(st, h->w3, (int)D, (int)M, h->w3T, (int)D));
-  return 0;
+  SPM_CHECK(!h->vit, "spm_tv1_load_weights: this handle is an encoder block (spm_vitblock_load_weights)");
+  return block_load(h, (cudaStream_t)stream, ln_g, ln_b, wq, wk, wv, nullptr, wout, bout, nullptr, nullptr, w0, b0, w3, b3);
 }
 
 int spm_tv1_set_dropout(spm_tv1* h, float p_atte, float p_ffn, unsigned long long seed) {
@@ -419,34 +702,9 @@ int spm_dropout(void* stream, const float* x, long long n, float p, unsigned lon
 
 int spm_tv1_forward(spm_tv1* h, void* stream, const float* x, int n_seq, int seq_len, float* out) {
   SPM_CHECK(h && x && out, "spm_tv1_forward: null argument");
-  SPM_CHECK(h->loaded, "spm_tv1_forward: weights not loaded");
+  SPM_CHECK(h->loaded && !h->vit, "spm_tv1_forward: weights not loaded");
   SPM_CHECK(n_seq > 0 && seq_len > 0 && seq_len <= 48, "spm_tv1_forward: 1..48 tokens per sequence");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int D = h->D, I = h->inner, M = h->mlp, R = n_seq * seq_len;
-  SPM_TRY(tv1_workspace(h, R));
-  h->x = x; h->B = n_seq; h->n = seq_len;
-  TV1_KERNEL(k_layernorm(st, x, D, R, D, h->ln_g, h->ln_b, nullptr, 0, h->HN, nullptr, D));
-  SPM_TRY(tv1_gemm(h, st, h->HN, D, h->wqkv, D, R, 3 * I, D, nullptr, ACT_NONE, nullptr, h->QKV));
-  TV1_KERNEL(k_seq_attention(st, h->QKV, h->AO, n_seq, seq_len, 1, 0, seq_len, 0, 0, h->heads, h->dh));
-  // nn.Dropout sites of the block (myRes.py:961-962 to_out, :990,992 FeedForward): 0 = after to_out, 1 = after GELU, 2 = after
-  // net.3; each is applied BEFORE the residual add, so with p > 0 the residual leaves the GEMM epilogue
-  h->fwd_p_atte = h->p_atte; h->fwd_p_ffn = h->p_ffn; h->fwd_seed = h->seed;
-  const long long nD = (long long)R * D, nM = (long long)R * M;
-  if (h->p_atte > 0.f) {
-    SPM_TRY(tv1_gemm(h, st, h->AO, I, h->wout, I, R, D, I, h->bout, ACT_NONE, nullptr, h->Y));
-    SPM_TRY(tv1_dropout(st, h->Y, x, h->Y, nD, h->p_atte, h->seed, 0));
-  } else {
-    SPM_TRY(tv1_gemm(h, st, h->AO, I, h->wout, I, R, D, I, h->bout, ACT_NONE, x, h->Y));
-  }
-  SPM_TRY(tv1_gemm(h, st, h->Y, D, h->w0, D, R, M, D, h->b0, ACT_GELU_ERF, nullptr, h->FFH));
-  if (h->p_ffn > 0.f) {
-    SPM_TRY(tv1_dropout(st, h->FFH, nullptr, h->FFH, nM, h->p_ffn, h->seed, 1));
-    SPM_TRY(tv1_gemm(h, st, h->FFH, M, h->w3, M, R, D, M, h->b3, ACT_NONE, nullptr, out));
-    SPM_TRY(tv1_dropout(st, out, h->Y, out, nD, h->p_ffn, h->seed, 2));
-  } else {
-    SPM_TRY(tv1_gemm(h, st, h->FFH, M, h->w3, M, R, D, M, h->b3, ACT_NONE, h->Y, out));
-  }
-  return 0;
+  return block_forward(h, (cudaStream_t)stream, x, n_seq, seq_len, out);
 }
 
 int spm_tv1_backward(spm_tv1* h, void* stream, const float* grad_out, float* grad_x, float* g_ln_g, float* g_ln_b,
@@ -454,59 +712,59 @@ int spm_tv1_backward(spm_tv1* h, void* stream, const float* grad_out, float* gra
                      float* g_w3, float* g_b3) {
   SPM_CHECK(h && grad_out && grad_x && g_ln_g && g_ln_b && g_wq && g_wk && g_wv && g_wout && g_bout && g_w0 && g_b0 && g_w3 &&
                 g_b3, "spm_tv1_backward: null argument");
-  SPM_CHECK(h->x != nullptr, "spm_tv1_backward: no forward to differentiate");
+  SPM_CHECK(h->x != nullptr && !h->vit, "spm_tv1_backward: no forward to differentiate");
   SPM_CHECK(g_wk == g_wq + (long long)h->inner * h->D && g_wv == g_wk + (long long)h->inner * h->D,
             "spm_tv1_backward: the q / k / v weight gradients must be three consecutive [inner, D] blocks");
+  return block_backward(h, (cudaStream_t)stream, grad_out, grad_x, g_ln_g, g_ln_b, g_wq, nullptr, g_wout, g_bout, nullptr, nullptr,
+                        g_w0, g_b0, g_w3, g_b3);
+}
+
+/* ---- frame-encoder residual block (models/clip_fsar.py:622-643), 197 tokens per frame ---- */
+int spm_vitblock_create(int precision, spm_tv1** out) { return block_create(VC, VHEADS, VHD, 4 * VC, precision, true, out); }
+
+int spm_vitblock_load_weights(spm_tv1* h, void* stream, const float* ln1_g, const float* ln1_b, const float* in_proj_w,
+                              const float* in_proj_b, const float* out_w, const float* out_b, const float* ln2_g,
+                              const float* ln2_b, const float* fc_w, const float* fc_b, const float* proj_w, const float* proj_b) {
+  SPM_CHECK(h && ln1_g && ln1_b && in_proj_w && in_proj_b && out_w && out_b && ln2_g && ln2_b && fc_w && fc_b && proj_w && proj_b,
+            "spm_vitblock_load_weights: null argument");
+  SPM_CHECK(h->vit, "spm_vitblock_load_weights: not an encoder-block handle");
+  const long long ID = (long long)h->inner * h->D;
+  return block_load(h, (cudaStream_t)stream, ln1_g, ln1_b, in_proj_w, in_proj_w + ID, in_proj_w + 2 * ID, in_proj_b, out_w, out_b,
+                    ln2_g, ln2_b, fc_w, fc_b, proj_w, proj_b);
+}
+
+int spm_vitblock_forward(spm_tv1* h, void* stream, const float* x, int n_frames, float* out) {
+  SPM_CHECK(h && x && out, "spm_vitblock_forward: null argument");
+  SPM_CHECK(h->loaded && h->vit, "spm_vitblock_forward: weights not loaded");
+  SPM_CHECK(n_frames > 0, "spm_vitblock_forward: no frames");
+  return block_forward(h, (cudaStream_t)stream, x, n_frames, VL, out);
+}
+
+int spm_vitblock_backward(spm_tv1* h, void* stream, const float* grad_out, float* grad_x, float* g_ln1_g, float* g_ln1_b,
+                          float* g_in_proj_w, float* g_in_proj_b, float* g_out_w, float* g_out_b, float* g_ln2_g, float* g_ln2_b,
+                          float* g_fc_w, float* g_fc_b, float* g_proj_w, float* g_proj_b) {
+  SPM_CHECK(h && grad_out && grad_x && g_ln1_g && g_ln1_b && g_in_proj_w && g_in_proj_b && g_out_w && g_out_b && g_ln2_g &&
+                g_ln2_b && g_fc_w && g_fc_b && g_proj_w && g_proj_b, "spm_vitblock_backward: null argument");
+  SPM_CHECK(h->x != nullptr && h->vit, "spm_vitblock_backward: no forward to differentiate");
+  return block_backward(h, (cudaStream_t)stream, grad_out, grad_x, g_ln1_g, g_ln1_b, g_in_proj_w, g_in_proj_b, g_out_w, g_out_b,
+                        g_ln2_g, g_ln2_b, g_fc_w, g_fc_b, g_proj_w, g_proj_b);
+}
+
+/* ---- nn.LayerNorm (eps 1e-5) forward / backward over rows of C ---- */
+int spm_layernorm_forward(void* stream, const float* x, int rows, int C, const float* gamma, const float* beta, float* y) {
+  SPM_CHECK(x && gamma && beta && y && rows > 0 && C > 0, "spm_layernorm_forward: null argument");
+  TV1_KERNEL(k_layernorm((cudaStream_t)stream, x, C, rows, C, gamma, beta, nullptr, 0, y, nullptr, C));
+  return 0;
+}
+
+int spm_layernorm_backward(void* stream, const float* x, const float* dy, const float* gamma, int rows, int C, float* dx,
+                           float* dgamma, float* dbeta, float* workspace) {
+  SPM_CHECK(x && dy && gamma && dx && dgamma && dbeta && workspace && rows > 0 && C > 0, "spm_layernorm_backward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  const int D = h->D, I = h->inner, M = h->mlp, n = h->n, R = h->B * h->n, Rp = (R + 3) / 4 * 4;
-  float* dF = h->dHN;   // [R, mlp]: dFFH, then dPRE in place
-  // ---- out = W3 gelu(PRE) + b3 + y
-  const long long nD = (long long)R * D, nM = (long long)R * M;
-  const float pa = h->fwd_p_atte, pf = h->fwd_p_ffn;
-  const float* g3 = grad_out;          // gradient behind the dropout of site 2 (the residual branch keeps grad_out itself)
-  if (pf > 0.f) { SPM_TRY(tv1_dropout(st, grad_out, nullptr, h->G3, nD, pf, h->fwd_seed, 2)); g3 = h->G3; }
-  SPM_TRY(tv1_colsum(st, g3, nullptr, R, D, g_b3));
-  SPM_TRY(tv1_transpose(st, g3, R, D, h->tA, Rp));
-  SPM_TRY(tv1_transpose(st, h->FFH, R, M, h->tB, Rp));
-  SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, D, M, Rp, nullptr, ACT_NONE, nullptr, g_w3));             // dW3 = dOut^T drop(gelu(PRE))
-  SPM_TRY(tv1_gemm(h, st, g3, D, h->w3T, D, R, M, D, nullptr, ACT_NONE, nullptr, dF));                    // dFFH = dOut W3
-  if (pf > 0.f) SPM_TRY(tv1_dropout(st, dF, nullptr, dF, nM, pf, h->fwd_seed, 1));
-  SPM_TRY(tv1_gemm(h, st, h->Y, D, h->w0, D, R, M, D, h->b0, ACT_NONE, nullptr, h->PRE));                 // PRE recomputed
-  {
-    const long long nel = (long long)R * M;
-    gelu_bwd_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(dF, h->PRE, nel);
-    TV1_LAUNCH_CHECK();
-  }
-  SPM_TRY(tv1_colsum(st, dF, nullptr, R, M, g_b0));
-  SPM_TRY(tv1_transpose(st, dF, R, M, h->tA, Rp));
-  SPM_TRY(tv1_transpose(st, h->Y, R, D, h->tB, Rp));
-  SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, M, D, Rp, nullptr, ACT_NONE, nullptr, g_w0));              // dW0 = dPRE^T y
-  SPM_TRY(tv1_gemm(h, st, dF, M, h->w0T, M, R, D, M, nullptr, ACT_NONE, grad_out, h->dY));                // dY = dPRE W0 + dOut
-  // ---- y = Wout ao + b_out + x
-  const float* gy = h->dY;             // gradient behind the dropout of site 0 (the residual branch keeps dY itself)
-  if (pa > 0.f) { SPM_TRY(tv1_dropout(st, h->dY, nullptr, h->G3, nD, pa, h->fwd_seed, 0)); gy = h->G3; }
-  SPM_TRY(tv1_colsum(st, gy, nullptr, R, D, g_bout));
-  SPM_TRY(tv1_transpose(st, gy, R, D, h->tA, Rp));
-  SPM_TRY(tv1_transpose(st, h->AO, R, I, h->tB, Rp));
-  SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, D, I, Rp, nullptr, ACT_NONE, nullptr, g_wout));            // dWout = dY^T ao
-  SPM_TRY(tv1_gemm(h, st, gy, D, h->woutT, D, R, I, D, nullptr, ACT_NONE, nullptr, h->dAO));              // dAO = dY Wout
-  // ---- attention
-  SPM_CHECK(n <= TV1_SEQ_MAX && attn_bwd_smem(n, h->dh) <= attn_bwd_smem(48, 256), "spm_tv1_backward: sequence too long");
-  {
-    dim3 grid(h->B, h->heads);
-    seq_attention_bwd_kernel<<<grid, 256, attn_bwd_smem(n, h->dh), st>>>(h->QKV, h->dAO, h->dQKV, n, h->heads, h->dh);
-    TV1_LAUNCH_CHECK();
-  }
-  // ---- q, k, v = W{q,k,v} LN(x)
-  SPM_TRY(tv1_transpose(st, h->dQKV, R, 3 * I, h->tA, Rp));
-  SPM_TRY(tv1_transpose(st, h->HN, R, D, h->tB, Rp));
-  SPM_TRY(tv1_gemm(h, st, h->tA, Rp, h->tB, Rp, 3 * I, D, Rp, nullptr, ACT_NONE, nullptr, g_wq));          // [dWq; dWk; dWv]
-  SPM_TRY(tv1_gemm(h, st, h->dQKV, 3 * I, h->wqkvT, 3 * I, R, D, 3 * I, nullptr, ACT_NONE, nullptr, h->dHN));   // dLN = dQKV Wqkv
-  // ---- LayerNorm + the residual branch (dY)
-  SPM_TRY(tv1_colsum(st, h->dHN, nullptr, R, D, g_ln_b));
-  ln_bwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(h->x, h->dHN, h->ln_g, h->dY, R, D, grad_x, h->HN);   // HN := xhat o dLN
+  SPM_TRY(tv1_colsum(st, dy, nullptr, rows, C, dbeta));
+  ln_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, dy, gamma, nullptr, rows, C, dx, workspace);   // workspace [rows, C] := xhat o dy
   TV1_LAUNCH_CHECK();
-  SPM_TRY(tv1_colsum(st, h->HN, nullptr, R, D, g_ln_g));
+  SPM_TRY(tv1_colsum(st, workspace, nullptr, rows, C, dgamma));
   return 0;
 }
 

@@ -350,8 +350,12 @@ class CNN(nn.Module):
         super().train(mode)
         if mode and not was and getattr(self, "_dev", None) is not None and self.HEAD == "clipspm" and torch.cuda.is_available() \
                 and getattr(self, "_train_ready", None) is not None:
-            for n in self._head_param_names():
-                p = self.get_parameter(n)
+            tower = bool(getattr(self, "train_backbone", False))
+            if tower and self.backbone_name != "ViT-B/16":
+                raise RuntimeError("train_backbone: only the ViT-B/16 tower has a backward (RN50: head-only training)")
+            for n, p in self.named_parameters():
+                if n.startswith("backbone.") and not tower:
+                    continue
                 if not p.is_cuda:
                     p.data = p.data.to(self._dev, torch.float32).contiguous()
                 p.requires_grad_(n != "scale")   # `scale` is a parameter the CLIP-SPM forward never reads
@@ -366,14 +370,24 @@ class CNN(nn.Module):
         """The parameters train mode differentiates (the head of models/model_clipspm.py:72-99; the CLIP tower is frozen)."""
         return [p for p in self.parameters() if p.requires_grad]
 
+    def _train_tower(self, images):
+        """models/clip_fsar.py:672-689 with a graph (train_backbone): the differentiable tf32 / fp32 tower of clip_spm_b200.train"""
+        from . import train as _train
+        if getattr(self, "_vitblk", None) is None:
+            self._vitblk = _train.VitBlock(exact=self.precision == "fp32")
+        return _train.vit_forward(dict(self.named_parameters()), images, self._vitblk, "backbone.", self.precision == "fp32")
+
     def _train_blocks(self):
         if getattr(self, "_tv1", None) is None:
             from .train import TransformerV1
             exact = self.precision == "fp32"
             self._tv1 = (TransformerV1(self.mid_dim, exact=exact), TransformerV1(self.mid_dim, exact=exact))
-        for b in self._tv1:
-            b.reset()
         return self._tv1
+
+    def _reset_train_pools(self):
+        """a new train-mode forward starts: block handles still held by a graph that never ran its backward are reclaimed"""
+        for b in (getattr(self, "_tv1", None) or ()) + ((self._vitblk,) if getattr(self, "_vitblk", None) is not None else ()):
+            b.reset()
 
     def _train_head(self, su, qu, lab, rs, rt):
         from . import train as _train
@@ -427,9 +441,16 @@ class CNN(nn.Module):
             if int(n_episodes) != 1:
                 raise RuntimeError("train mode takes one episode per call, like the reference's train_task")
             T, D = self.seq_len, self.mid_dim
-            with torch.no_grad():
-                su = self.encode_frames(self._f32(context_images).view(-1, 3, 224, 224)).view(-1, T, D)
-                qu = self.encode_frames(self._f32(target_images).view(-1, 3, 224, 224)).view(-1, T, D)
+            self._reset_train_pools()
+            if getattr(self, "train_backbone", False):
+                ns = self._f32(context_images).view(-1, 3, 224, 224).shape[0]
+                feats = self._train_tower(torch.cat([self._f32(context_images).view(-1, 3, 224, 224),
+                                                     self._f32(target_images).view(-1, 3, 224, 224)], dim=0))
+                su, qu = feats[:ns].view(-1, T, D), feats[ns:].view(-1, T, D)
+            else:
+                with torch.no_grad():
+                    su = self.encode_frames(self._f32(context_images).view(-1, 3, 224, 224)).view(-1, T, D)
+                    qu = self.encode_frames(self._f32(target_images).view(-1, 3, 224, 224)).view(-1, T, D)
             out = self._train_head(su, qu, self._f32(context_labels).view(-1), self._f32(real_support_labels).view(-1),
                                    self._f32(real_target_labels).view(-1))
             out = {"logits": out["logits"], "dists": out["dists"].view(1)}
@@ -597,6 +618,7 @@ class CNN(nn.Module):
             if int(n_episodes) != 1:
                 raise RuntimeError("train mode takes one episode per call, like the reference's train_task")
             T, D = self.seq_len, self.mid_dim
+            self._reset_train_pools()
             return self._train_head(self._f32(su).view(-1, T, D), self._f32(qu).view(-1, T, D), self._f32(context_labels).view(-1),
                                     self._f32(real_support_labels).view(-1), self._f32(real_target_labels).view(-1))
         h = self._handle()

@@ -19,7 +19,7 @@ import torch
 from . import _lib
 from .ops import ACT, _need_cuda, _ptr, _stream, otam_distance
 
-__all__ = ["linear", "dropout", "TransformerV1", "spm_head_forward", "spm_loss"]
+__all__ = ["linear", "dropout", "layer_norm", "TransformerV1", "VitBlock", "vit_forward", "spm_head_forward", "spm_loss"]
 
 
 class _Linear(torch.autograd.Function):
@@ -143,7 +143,8 @@ class TransformerV1:
         return h
 
     def _give(self, h):
-        self._free.append(h)
+        if not any(f is h for f in self._free):
+            self._free.append(h)
 
     def reset(self):
         self._free = list(self._all)
@@ -167,6 +168,98 @@ class TransformerV1:
         w = [weights[prefix + n].contiguous() for n in self.NAMES]
         drop = (0.0, 0.0, 0) if dropout_seed is None else (self.p[0], self.p[1], int(dropout_seed) & (2 ** 64 - 1))
         return _TV1.apply(x.contiguous().float(), self, drop, *w)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g, b):
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().spm_layernorm_forward(_stream(), _ptr(x), x.shape[0], x.shape[1], _ptr(g), _ptr(b), _ptr(y)))
+        ctx.save_for_backward(x, g)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx, dg, db, ws = torch.empty_like(x), torch.empty_like(g), torch.empty_like(g), torch.empty_like(x)
+        _lib.check(_lib.load().spm_layernorm_backward(_stream(), _ptr(x), _ptr(dy), _ptr(g), x.shape[0], x.shape[1], _ptr(dx),
+                                                      _ptr(dg), _ptr(db), _ptr(ws)))
+        return dx, dg, db
+
+
+def layer_norm(x, weight, bias):
+    """Differentiable nn.LayerNorm (eps 1e-5) over the last dim."""
+    _need_cuda(x, weight, bias)
+    y = _LayerNorm.apply(x.reshape(-1, x.shape[-1]).contiguous().float(), weight.contiguous(), bias.contiguous())
+    return y.view(x.shape)
+
+
+class _VitBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pool, *w):
+        lib = _lib.load()
+        h = pool._take()
+        st = _stream()
+        _lib.check(lib.spm_vitblock_load_weights(h, st, *[_ptr(t) for t in w]))
+        out = torch.empty_like(x)
+        _lib.check(lib.spm_vitblock_forward(h, st, _ptr(x), x.shape[0], _ptr(out)))
+        ctx.save_for_backward(x, *w)
+        ctx.pool, ctx.h = pool, h
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        x, *w = ctx.saved_tensors
+        go = go.contiguous()
+        gx = torch.empty_like(x)
+        g = [torch.empty_like(t) for t in w]
+        _lib.check(_lib.load().spm_vitblock_backward(ctx.h, _stream(), _ptr(go), _ptr(gx), *[_ptr(t) for t in g]))
+        ctx.pool._give(ctx.h)
+        return (gx, None) + tuple(g)
+
+
+class VitBlock(TransformerV1):
+    """models/clip_fsar.py:622-643 `ResidualAttentionBlock` of the ViT-B/16 tower on x [F,197,768], differentiable
+    (spm_vitblock_forward / _backward); same handle pool as TransformerV1 -- the 12 blocks of a tower take 12 handles."""
+
+    NAMES = ("ln_1.weight", "ln_1.bias", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight",
+             "attn.out_proj.bias", "ln_2.weight", "ln_2.bias", "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight",
+             "mlp.c_proj.bias")
+
+    def __init__(self, exact=False):
+        self.exact = 1 if exact else 0
+        self._free, self._all = [], []
+
+    def _take(self):
+        if self._free:
+            return self._free.pop()
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().spm_vitblock_create(self.exact, ctypes.byref(h)))
+        self._all.append(h)
+        return h
+
+    def __call__(self, x, weights, prefix):
+        _need_cuda(x)
+        if x.dim() != 3 or x.shape[1] != 197 or x.shape[2] != 768:
+            raise RuntimeError("VitBlock takes [frames, 197, 768]")
+        w = [weights[prefix + n].contiguous() for n in self.NAMES]
+        return _VitBlockFn.apply(x.contiguous().float(), self, *w)
+
+
+def vit_forward(w, images, blocks, prefix="backbone.", exact=False):
+    """models/clip_fsar.py:672-689 VisionTransformer.forward, differentiable with respect to every tower parameter:
+    images [F,3,224,224] -> [F,512].  conv1 (16x16 / stride 16, no bias) is a linear over the patch matrix."""
+    Fn = images.shape[0]
+    patches = images.float().view(Fn, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(Fn * 196, 768)   # column c*256+ky*16+kx
+    x = linear(patches, w[prefix + "conv1.weight"].reshape(768, 768), None, exact=exact).view(Fn, 196, 768)      # :673-675
+    cls = w[prefix + "class_embedding"].expand(Fn, 1, -1)
+    x = torch.cat([cls, x], dim=1) + w[prefix + "positional_embedding"]                                       # :676-677
+    x = layer_norm(x, w[prefix + "ln_pre.weight"], w[prefix + "ln_pre.bias"])                                 # :678
+    for i in range(12):                                                                                       # :680-682
+        x = blocks(x, w, prefix + "transformer.resblocks.%d." % i)
+    x = layer_norm(x[:, 0, :], w[prefix + "ln_post.weight"], w[prefix + "ln_post.bias"])                      # :684
+    return linear(x, w[prefix + "proj"].t().contiguous(), None, exact=exact)                                  # :686-687
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -41,7 +41,8 @@ extern "C" {
                            * 5: SPM_HEAD_CPM2C: spm_config gained its parameters; spm_cpm2c_outputs
                            * 6: spm_config gained fsar_depth, fsar_merge_before (CLIP-FSAR's optional branches)
                            * 7: spm_adam_*, spm_scaler_update
-                           * 8: spm_tv1_* (head transformer block forward + backward), spm_linear_backward */
+                           * 8: spm_tv1_* (head transformer block forward + backward), spm_linear_backward, spm_dropout,
+                           *    spm_vitblock_* (encoder block forward + backward), spm_layernorm_forward / _backward */
 
 typedef struct spm_handle spm_handle;
 
@@ -228,6 +229,28 @@ int spm_dropout(void* stream, const float* x, long long n, float p, unsigned lon
 int spm_tv1_backward(spm_tv1* h, void* stream, const float* grad_out, float* grad_x, float* g_ln_g, float* g_ln_b,
                      float* g_wq, float* g_wk, float* g_wv, float* g_wout, float* g_bout, float* g_w0, float* g_b0,
                      float* g_w3, float* g_b3);
+
+/* The same block with the frame encoder's switches: models/clip_fsar.py:622-643 `ResidualAttentionBlock` of the CLIP ViT-B/16
+ * tower (x + out_proj(attn(ln_1 x)); + c_proj(QuickGELU(c_fc(ln_2 .)))), 197 tokens per frame, 12 heads x 64 -- forward and
+ * backward for the training step (the reference's optimiser steps the tower too, run/main_run.py:84-88).  Parameters in the
+ * reference's layouts: attn.in_proj_weight [2304,768] / in_proj_bias, attn.out_proj, ln_1, ln_2, mlp.c_fc, mlp.c_proj.
+ * x, out, grads: fp32 [n_frames * 197, 768]; same handle rules as spm_tv1 (one backward per forward, gradients overwritten;
+ * spm_tv1_set_dropout / spm_tv1_destroy apply; the backward scratch is shared process-wide, so training calls belong on
+ * one stream). */
+int spm_vitblock_create(int precision, spm_tv1** out);
+int spm_vitblock_load_weights(spm_tv1* h, void* stream, const float* ln1_g, const float* ln1_b, const float* in_proj_w,
+                              const float* in_proj_b, const float* out_w, const float* out_b, const float* ln2_g,
+                              const float* ln2_b, const float* fc_w, const float* fc_b, const float* proj_w, const float* proj_b);
+int spm_vitblock_forward(spm_tv1* h, void* stream, const float* x, int n_frames, float* out);
+int spm_vitblock_backward(spm_tv1* h, void* stream, const float* grad_out, float* grad_x, float* g_ln1_g, float* g_ln1_b,
+                          float* g_in_proj_w, float* g_in_proj_b, float* g_out_w, float* g_out_b, float* g_ln2_g, float* g_ln2_b,
+                          float* g_fc_w, float* g_fc_b, float* g_proj_w, float* g_proj_b);
+
+/* nn.LayerNorm (eps 1e-5) over rows of C, forward and backward (ln_pre / ln_post of the tower, clip_fsar.py:664,668):
+ * dx, dgamma, dbeta overwritten; workspace: rows * C floats. */
+int spm_layernorm_forward(void* stream, const float* x, int rows, int C, const float* gamma, const float* beta, float* y);
+int spm_layernorm_backward(void* stream, const float* x, const float* dy, const float* gamma, int rows, int C, float* dx,
+                           float* dgamma, float* dbeta, float* workspace);
 
 /* Backward of y = act(x W^T + bias) (nn.Linear [+ LeakyReLU | Sigmoid | GELU]: the gates models/model_clipspm.py:88-99, the
  * FeedForward of token_trans :371-378, the temporal convolutions :169-172 as im2col GEMMs; forward = spm_gemm):

@@ -914,6 +914,19 @@ def head_loss_and_grads(w, text_features, su, qu, support_labels, real_support, 
     return loss.detach(), grads
 
 
+def train_loss_and_grads(w, text_features, inputs, cfg, tasks_per_batch=16):
+    """run/main_run.py:245-254 train_task from the frames on (dropout p = 0): loss of :390-392 on forward() -- frame encoder
+    AND head -- differentiated by torch autograd on the CPU with respect to every floating-point parameter in `w`.
+    `text_features` is the TRAIN prompt table (model_clipspm.py:116-118).  Returns (loss, {name: grad})."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in w.items() if v.dtype.is_floating_point}
+    st = forward(leaves, text_features, inputs, cfg)
+    lg = st["logits"][0]
+    ce = -(lg.log_softmax(-1).gather(1, inputs["target_labels"].long().view(-1, 1)).squeeze(1))
+    loss = ce.sum() / tasks_per_batch + 0.001 * st["dists"]
+    loss.backward()
+    return loss.detach(), {k: v.grad.detach() for k, v in leaves.items() if v.grad is not None}
+
+
 def grad_sample_index(numel, n=4096, seed=0):
     """fixed sample positions of a large gradient tensor stored in the goldens (the full head gradients are ~70 MB)"""
     if numel <= n:

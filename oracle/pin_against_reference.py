@@ -289,6 +289,55 @@ def run_head_grad_case(m, name):
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
 
 
+# name: backbone, way, shot, queries per class, T, n text classes, seed  (frames -> loss -> every gradient, tower included)
+TRAIN_CASES = {
+    "train_vit_2w1s_t2": ("ViT-B/16", 2, 1, 1, 2, 24, 4101),
+}
+
+
+def run_train_case(m, name):
+    """The whole training step's backward: the REFERENCE's CNN in train mode (dropout p = 0 on the instances) from the frames,
+    loss through utils.loss, `.backward()` -> gradients of every parameter of the CLIP visual tower and of the head.  The
+    oracle's autograd (train_loss_and_grads) must reproduce them; the reference gradients become the golden (samples)."""
+    backbone, way, shot, qpc, T, ncls, seed = TRAIN_CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    net = build_reference(m, backbone, T, False)
+    w = O.make_weights(backbone, seed=0, protocol="P1", head_only=False)
+    missing, unexpected = net.load_state_dict(w, strict=False)
+    assert not missing and not unexpected
+    net.train()
+    for mod in net.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    text_train = O.make_text_features(ncls, D, seed=1)
+    net.text_features_train, net.text_features_test = text_train, None
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, "P1", images=True)
+    for mod in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    import utils.utils as U
+    out = net(ep)
+    loss_ref = U.loss(out["logits"], ep["target_labels"].long(), "cpu") / 16 + 0.001 * out["dists"]
+    loss_ref.backward()
+    ref = {k: p.grad.detach() for k, p in net.named_parameters() if p.grad is not None}
+    cfg = dict(backbone=backbone, seq_len=T, mid_dim=D, params=O.DEFAULT_PARAMS, single_direct=False)
+    loss, grads = O.train_loss_and_grads(w, text_train, ep, cfg)
+    assert set(ref) == set(grads), sorted(set(ref) ^ set(grads))
+    assert any(k.startswith("backbone.") for k in ref)
+    worst = rel(loss.reshape(()), loss_ref.detach().reshape(()))
+    gold = {"loss": loss_ref.detach().numpy().reshape(()), "logits": out["logits"].detach().numpy()}
+    for k, g in ref.items():
+        r = rel(grads[k].reshape(g.shape), g)
+        worst = max(worst, r)
+        assert r < 5e-4, "oracle autograd disagrees with the reference on d loss / d %s: rel err %.3e" % (k, r)
+        flat = g.reshape(-1)
+        gold["g:" + k] = flat[O.grad_sample_index(flat.numel(), 1024)].numpy()
+        gold["n:" + k] = np.float64(flat.double().norm())
+    print("%-24s oracle autograd == reference autograd, frames -> loss (train mode, p = 0): %d gradients (%d of the tower), "
+          "worst rel err %.2e, loss %.5f" % (name, len(ref), sum(k.startswith("backbone.") for k in ref), worst,
+                                             float(loss_ref.detach())))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
+
+
 FSAR_CASES = {
     # name: (backbone, way, shot, qpc, T, n_test_cls, n_train_cls, head_only, single_direct, seed)
     "fsar_head_5w5s_t8": ("ViT-B/16", 5, 5, 1, 8, 24, 30, True, False, 2002),
@@ -621,7 +670,7 @@ def run_softdtw_case(name):
 
 if __name__ == "__main__":
     m = import_reference()
-    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + ["fsar_dead_branches"] + list(STEN_CASES) + list(CPM2C_CASES) + list(SOFTDTW_CASES) + list(HEAD_GRAD_CASES))
+    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + ["fsar_dead_branches"] + list(STEN_CASES) + list(CPM2C_CASES) + list(SOFTDTW_CASES) + list(HEAD_GRAD_CASES) + list(TRAIN_CASES))
     for n in names:
         if n == "text":
             run_text_case(m)
@@ -639,5 +688,7 @@ if __name__ == "__main__":
             run_softdtw_case(n)
         elif n in HEAD_GRAD_CASES:
             run_head_grad_case(m, n)
+        elif n in TRAIN_CASES:
+            run_train_case(m, n)
         else:
             run_case(m, n)

@@ -212,3 +212,91 @@ def test_model_train_mode_steps_the_head():
     tr = net.head(ci["su"].cuda().unsqueeze(0), ci["qu"].cuda().unsqueeze(0), ep["context_labels"],
                   ep["real_support_labels"], ep["real_target_labels"])
     assert torch.allclose(ev["logits"], tr["logits"].detach(), atol=2e-2, rtol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ frame encoder backward
+def _vit_block_weights(seed):
+    g = torch.Generator().manual_seed(seed)
+    C = 768
+    sh = {"ln_1.weight": (C,), "ln_1.bias": (C,), "attn.in_proj_weight": (3 * C, C), "attn.in_proj_bias": (3 * C,),
+          "attn.out_proj.weight": (C, C), "attn.out_proj.bias": (C,), "ln_2.weight": (C,), "ln_2.bias": (C,),
+          "mlp.c_fc.weight": (4 * C, C), "mlp.c_fc.bias": (4 * C,), "mlp.c_proj.weight": (C, 4 * C), "mlp.c_proj.bias": (C,)}
+    w = {}
+    for k, s in sh.items():
+        if len(s) == 1:
+            w["b." + k] = torch.randn(s, generator=g) * 0.1 + (1.0 if k in ("ln_1.weight", "ln_2.weight") else 0.0)
+        else:
+            w["b." + k] = torch.randn(s, generator=g) * (1.5 * s[1] ** -0.5)
+    return w
+
+
+@pytest.mark.parametrize("frames,exact,tol", [(2, True, 2e-4), (3, False, 8e-3), (1, True, 2e-4)])
+def test_vit_block_forward_backward_matches_oracle_autograd(frames, exact, tol):
+    """models/clip_fsar.py:622-643 ResidualAttentionBlock: value, d x and all 12 parameter gradients"""
+    from clip_spm_b200.train import VitBlock
+    w = _vit_block_weights(frames)
+    g = torch.Generator().manual_seed(3)
+    x, go = torch.randn(frames, 197, 768, generator=g), torch.randn(frames, 197, 768, generator=g)
+    wr = {k: v.double().requires_grad_(True) for k, v in w.items()}
+    xr = x.double().requires_grad_(True)
+    ref = O.vit_block(xr, wr, "b.", 12)
+    (ref * go.double()).sum().backward()
+    wc = {k: v.cuda().requires_grad_(True) for k, v in w.items()}
+    xc = x.cuda().requires_grad_(True)
+    blk = VitBlock(exact=exact)
+    out = blk(xc, wc, "b.")
+    (out * go.cuda()).sum().backward()
+    assert _rel(out, ref) < tol
+    assert _rel(xc.grad, xr.grad) < tol, "d x"
+    for k in w:
+        assert _rel(wc[k].grad, wr[k].grad) < tol, k
+    blk.close()
+
+
+def test_layer_norm_backward_matches_torch():
+    from clip_spm_b200.train import layer_norm
+    g = torch.Generator().manual_seed(1)
+    x, w, b, go = torch.randn(5, 197, 768, generator=g) * 3 + 1, torch.randn(768, generator=g), torch.randn(768, generator=g), \
+        torch.randn(5, 197, 768, generator=g)
+    xr, wr_, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    (F.layer_norm(xr, (768,), wr_, br) * go.double()).sum().backward()
+    xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    (layer_norm(xc, wc, bc) * go.cuda()).sum().backward()
+    for mine, want in ((xc.grad, xr.grad), (wc.grad, wr_.grad), (bc.grad, br.grad)):
+        assert _rel(mine, want) < 1e-4
+
+
+TRAIN_VIT = ("ViT-B/16", 2, 1, 1, 2, 24, 4101)     # must match oracle/pin_against_reference.py::TRAIN_CASES["train_vit_2w1s_t2"]
+
+
+@pytest.mark.parametrize("precision,tol,l2", [("fp32", 2e-3, False), ("bf16", 5e-2, True)])
+def test_whole_training_backward_matches_reference_golden(precision, tol, l2):
+    """frames -> ViT-B/16 tower -> head -> loss -> .backward(): all 191 gradients the REFERENCE's backward produced (152 of the
+    tower), through CNN in train mode with train_backbone (precision fp32: exact products; bf16: the tf32 training path)"""
+    from clip_spm_b200 import CNN
+    backbone, way, shot, qpc, T, ncls, seed = TRAIN_VIT
+    w = O.make_weights(backbone, seed=0, protocol="P1", head_only=False)
+    text = O.make_text_features(ncls, 512, seed=1)
+    ep = O.make_episode(seed, way, shot, qpc, T, ncls, "P1", images=True)
+    net = CNN(make_cfg(backbone, T, False, way), text_features_test=text, text_features_train=text, precision=precision)
+    missing, unexpected = net.load_state_dict(w, strict=False)
+    assert not missing and not unexpected
+    net.train_backbone, net.train_dropout = True, False
+    net.train()
+    out = net(ep)
+    loss = net.loss(out, ep["target_labels"])
+    loss.backward()
+    grads = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    gold = golden("train_vit_2w1s_t2")
+    assert torch.allclose(out["logits"].detach().cpu(), gold["logits"], atol=tol, rtol=tol)
+    names = sorted(k[2:] for k in gold if k.startswith("g:"))
+    assert sorted(grads) == names and sum(k.startswith("backbone.") for k in names) == 152
+    for k in names:
+        flat = grads[k].detach().cpu().double().reshape(-1)
+        ref = gold["g:" + k].double()
+        mine = flat[O.grad_sample_index(flat.numel(), 1024)]
+        if l2:
+            assert float((mine - ref).norm()) < tol * float(ref.norm()) + 1e-30, (k, float((mine - ref).norm()), float(ref.norm()))
+        else:
+            assert float((mine - ref).abs().max()) < tol * float(ref.abs().max()) + 1e-30, (k, float((mine - ref).abs().max()))
+        assert abs(float(flat.norm()) - float(gold["n:" + k])) < tol * float(gold["n:" + k]) + 1e-30, k
