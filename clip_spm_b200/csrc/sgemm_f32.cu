@@ -67,14 +67,16 @@ sgemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __rest
 }
 
 constexpr int AL = 197, AHD = 64, AHEADS = 12, AC = 768;
-constexpr int ATT32_SMEM = (AL * (AHD + 1) + AL * AHD + 8 * AHD) * 4;
+constexpr int ATT32_SMEM = (AL * (AHD + 1) + AL * AHD + 8 * 4 * AHD) * 4;
 
+// A warp handles FOUR query rows per pass: the lane's 7 key columns x 4 rows form a register tile, so a step of the dot
+// products costs 4 broadcast + 7 strided shared-memory reads per 28 FMAs (one row at a time paid 2 reads per FMA).
 __global__ void __launch_bounds__(256)
 vit_attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
   extern __shared__ float sm_a32[];
   float* sK = sm_a32;                  // [197][65]
   float* sV = sK + AL * (AHD + 1);     // [197][64]
-  float* sQ = sV + AL * AHD;           // [8 warps][64]
+  float* sQ = sV + AL * AHD;           // [8 warps][4 rows][64]
   const int frame = blockIdx.x / AHEADS, head = blockIdx.x % AHEADS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* base = qkv + (long long)frame * AL * (3 * AC) + head * AHD;
@@ -84,49 +86,78 @@ vit_attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out)
     sV[r * AHD + d] = base[(long long)r * (3 * AC) + 2 * AC + d];
   }
   __syncthreads();
-  float* q = sQ + warp * AHD;
-  for (int r = warp; r < AL; r += 8) {
-    q[lane] = base[(long long)r * (3 * AC) + lane];
-    q[lane + 32] = base[(long long)r * (3 * AC) + lane + 32];
+  float* q = sQ + warp * 4 * AHD;
+  int col[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) col[j] = min(lane + 32 * j, AL - 1) * (AHD + 1);
+  for (int g = warp; g < (AL + 3) / 4; g += 8) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = min(4 * g + r, AL - 1);
+      q[r * AHD + lane] = base[(long long)row * (3 * AC) + lane];
+      q[r * AHD + lane + 32] = base[(long long)row * (3 * AC) + lane + 32];
+    }
     __syncwarp();
-    float s[7];
-    float mx = -INFINITY;
+    float s[4][7];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      const int key = lane + 32 * j;
-      s[j] = -INFINITY;
-      if (key < AL) {
-        float a = 0.f;
-        for (int d = 0; d < AHD; ++d) a = fmaf(q[d], sK[key * (AHD + 1) + d], a);
-        s[j] = a * 0.125f;
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 7; ++j) s[r][j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < AHD; ++d) {
+      float a[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = q[r * AHD + d];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const float k = sK[col[j] + d];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s[r][j] = fmaf(a[r], k, s[r][j]);
       }
-      mx = fmaxf(mx, s[j]);
     }
+    float inv[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float l = 0.f;
+    for (int r = 0; r < 4; ++r) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        s[r][j] = (lane + 32 * j < AL) ? s[r][j] * 0.125f : -INFINITY;
+        mx = fmaxf(mx, s[r][j]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        s[r][j] = (lane + 32 * j < AL) ? expf(s[r][j] - mx) : 0.f;
+        l += s[r][j];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+      inv[r] = 1.f / l;
+    }
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
-      s[j] = (lane + 32 * j < AL) ? expf(s[j] - mx) : 0.f;
-      l += s[j];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      for (int src = 0; src < 32; ++src) {
+      const int nsrc = j < 6 ? 32 : AL - 192;
+      for (int src = 0; src < nsrc; ++src) {
         const int key = src + 32 * j;
-        if (key >= AL) break;
-        const float p = __shfl_sync(0xffffffffu, s[j], src);
-        a0 = fmaf(p, sV[key * AHD + lane], a0);
-        a1 = fmaf(p, sV[key * AHD + lane + 32], a1);
+        const float v0 = sV[key * AHD + lane], v1 = sV[key * AHD + lane + 32];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float p = __shfl_sync(0xffffffffu, s[r][j], src);
+          a0[r] = fmaf(p, v0, a0[r]);
+          a1[r] = fmaf(p, v1, a1[r]);
+        }
       }
     }
-    const float inv = 1.f / l;
-    float* o = out + ((long long)frame * AL + r) * AC + head * AHD;
-    o[lane] = a0 * inv;
-    o[lane + 32] = a1 * inv;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (4 * g + r < AL) {
+        float* o = out + ((long long)frame * AL + 4 * g + r) * AC + head * AHD;
+        o[lane] = a0[r] * inv[r];
+        o[lane + 32] = a1[r] * inv[r];
+      }
     __syncwarp();
   }
 }

@@ -92,6 +92,32 @@ __global__ void transpose_pad_kernel(const float* __restrict__ in, int R, int C,
   }
 }
 
+// two-stage column sum for tall matrices: partial sums of CS_CHUNKS row ranges, then their sum in a fixed order (deterministic,
+// no atomics); the one-stage kernel below walks all R rows with C / 32 blocks, far too few for the encoder's 15 760+ rows
+constexpr int CS_CHUNKS = 64;
+__global__ void colsum_part_kernel(const float* __restrict__ a, int R, int C, int rows_per_chunk, float* __restrict__ part) {
+  __shared__ float red[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
+  float s = 0.f;
+  if (c < C)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += a[(long long)r * C + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    part[(long long)blockIdx.y * C + c] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int n_chunks, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int k = 0; k < n_chunks; ++k) t += part[(long long)k * C + c];
+  out[c] = t;
+}
+
 // out[c] = sum_r a[r, c] (* b[r, c] when b != null); fixed summation order (deterministic)
 __global__ void colsum_kernel(const float* __restrict__ a, const float* __restrict__ b, int R, int C, float* __restrict__ out) {
   __shared__ float part[8][32];
@@ -299,6 +325,53 @@ __global__ void quickgelu_bwd_kernel(float* __restrict__ g, const float* __restr
 constexpr int VL = 197, VHD = 64, VHEADS = 12, VC = 768, VST = VHD + 1;
 constexpr int VIT_ATT_BWD_SMEM = (4 * VL * VST + 3 * VL) * 4;
 
+// s[r][t] = bc1[row_r] . st1[col_t], dp[r][t] = bc2[row_r] . st2[col_t] for 4 rows (warp-uniform: broadcast reads) and the
+// lane's 7 columns col_t = lane + 32 t: a 4 x 7 register tile per lane, 8 broadcast + 14 strided shared-memory reads per
+// 56 FMAs (the one-row version paid 2 reads per FMA and was bound by shared-memory bandwidth)
+__device__ __forceinline__ void vit_scores4(const float* __restrict__ bc1, const float* __restrict__ bc2,
+                                            const float* __restrict__ st1, const float* __restrict__ st2, const int (&rows)[4],
+                                            int lane, float (&sc)[4][7], float (&dp)[4][7]) {
+  int col[7];
+#pragma unroll
+  for (int t = 0; t < 7; ++t) col[t] = min(lane + 32 * t, VL - 1) * VST;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int t = 0; t < 7; ++t) { sc[r][t] = 0.f; dp[r][t] = 0.f; }
+#pragma unroll 4
+  for (int d = 0; d < VHD; ++d) {
+    float a[4], b[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { a[r] = bc1[rows[r] * VST + d]; b[r] = bc2[rows[r] * VST + d]; }
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      const float x = st1[col[t] + d], y = st2[col[t] + d];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { sc[r][t] = fmaf(a[r], x, sc[r][t]); dp[r][t] = fmaf(b[r], y, dp[r][t]); }
+    }
+  }
+}
+
+// out[r][0..1] = sum_j w[r][j] mat[j][lane, lane + 32] with w spread over the lanes (column j = lane + 32 t lives in lane j % 32)
+__device__ __forceinline__ void vit_accum4(const float (&w)[4][7], const float* __restrict__ mat, int lane, float (&out)[4][2]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { out[r][0] = 0.f; out[r][1] = 0.f; }
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    const int nsrc = t < 6 ? 32 : VL - 192;
+    for (int src = 0; src < nsrc; ++src) {
+      const int j = src + 32 * t;
+      const float m0 = mat[j * VST + lane], m1 = mat[j * VST + lane + 32];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float wr = __shfl_sync(0xffffffffu, w[r][t], src);
+        out[r][0] = fmaf(wr, m0, out[r][0]);
+        out[r][1] = fmaf(wr, m1, out[r][1]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 vit_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dO, float* __restrict__ dqkv) {
   extern __shared__ float sm_vb[];
@@ -322,94 +395,85 @@ vit_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict_
   }
   __syncthreads();
   float* out = dqkv + row0 * (3 * VC) + head * VHD;
-  // ---- phase 1: query rows
-  for (int i = warp; i < VL; i += 8) {
-    float s[7], dp[7];
-    float mx = -INFINITY;
+  constexpr int GROUPS = (VL + 3) / 4;
+  float sc[4][7], dp[4][7], acc[4][2];
+  // ---- phase 1: query rows, four per warp pass
+  for (int g = warp; g < GROUPS; g += 8) {
+    int rows[4];
 #pragma unroll
-    for (int t = 0; t < 7; ++t) {
-      const int j = lane + 32 * t;
-      s[t] = -INFINITY;
-      dp[t] = 0.f;
-      if (j < VL) {
-        float a = 0.f, b = 0.f;
-        for (int d = 0; d < VHD; ++d) {
-          a = fmaf(sQ[i * VST + d], sK[j * VST + d], a);
-          b = fmaf(sO[i * VST + d], sV[j * VST + d], b);
-        }
-        s[t] = a * 0.125f;
-        dp[t] = b;
+    for (int r = 0; r < 4; ++r) rows[r] = min(4 * g + r, VL - 1);
+    vit_scores4(sQ, sO, sK, sV, rows, lane, sc, dp);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        sc[r][t] = (lane + 32 * t < VL) ? sc[r][t] * 0.125f : -INFINITY;
+        mx = fmaxf(mx, sc[r][t]);
       }
-      mx = fmaxf(mx, s[t]);
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float l = 0.f;
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float l = 0.f;
 #pragma unroll
-    for (int t = 0; t < 7; ++t) {
-      s[t] = (lane + 32 * t < VL) ? expf(s[t] - mx) : 0.f;
-      l += s[t];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-    const float inv = 1.f / l;
-    float delta = 0.f;
-#pragma unroll
-    for (int t = 0; t < 7; ++t) { s[t] *= inv; delta = fmaf(s[t], dp[t], delta); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
-    if (lane == 0) { sM[i] = mx; sL[i] = inv; sD[i] = delta; }
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 7; ++t) {
-      const float ds = s[t] * (dp[t] - delta);
-      for (int src = 0; src < 32; ++src) {
-        const int j = src + 32 * t;
-        if (j >= VL) break;
-        const float w = __shfl_sync(0xffffffffu, ds, src);
-        a0 = fmaf(w, sK[j * VST + lane], a0);
-        a1 = fmaf(w, sK[j * VST + lane + 32], a1);
+      for (int t = 0; t < 7; ++t) {
+        sc[r][t] = (lane + 32 * t < VL) ? expf(sc[r][t] - mx) : 0.f;
+        l += sc[r][t];
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+      const float inv = 1.f / l;
+      float delta = 0.f;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) { sc[r][t] *= inv; delta = fmaf(sc[r][t], dp[r][t], delta); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+      if (lane == 0 && 4 * g + r < VL) { sM[rows[r]] = mx; sL[rows[r]] = inv; sD[rows[r]] = delta; }
+#pragma unroll
+      for (int t = 0; t < 7; ++t) sc[r][t] *= dp[r][t] - delta;       // dS (up to the 1/8)
     }
-    out[(long long)i * (3 * VC) + lane] = a0 * 0.125f;
-    out[(long long)i * (3 * VC) + lane + 32] = a1 * 0.125f;
+    vit_accum4(sc, sK, lane, acc);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (4 * g + r < VL) {
+        out[(long long)rows[r] * (3 * VC) + lane] = acc[r][0] * 0.125f;
+        out[(long long)rows[r] * (3 * VC) + lane + 32] = acc[r][1] * 0.125f;
+      }
   }
   __syncthreads();
-  // ---- phase 2: key rows
-  for (int j = warp; j < VL; j += 8) {
-    float pr[7], ds[7];
+  // ---- phase 2: key rows, four per warp pass; the lane's columns are now QUERY rows
+  for (int g = warp; g < GROUPS; g += 8) {
+    int rows[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rows[r] = min(4 * g + r, VL - 1);
+    vit_scores4(sK, sV, sQ, sO, rows, lane, sc, dp);
+    float m[7], li[7], de[7];
 #pragma unroll
     for (int t = 0; t < 7; ++t) {
-      const int i = lane + 32 * t;
-      pr[t] = 0.f;
-      ds[t] = 0.f;
-      if (i < VL) {
-        float a = 0.f, b = 0.f;
-        for (int d = 0; d < VHD; ++d) {
-          a = fmaf(sQ[i * VST + d], sK[j * VST + d], a);
-          b = fmaf(sO[i * VST + d], sV[j * VST + d], b);
-        }
-        pr[t] = expf(a * 0.125f - sM[i]) * sL[i];
-        ds[t] = pr[t] * (b - sD[i]);
-      }
+      const int i = min(lane + 32 * t, VL - 1);
+      m[t] = sM[i]; li[t] = sL[i]; de[t] = sD[i];
     }
-    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
 #pragma unroll
-    for (int t = 0; t < 7; ++t) {
-      for (int src = 0; src < 32; ++src) {
-        const int i = src + 32 * t;
-        if (i >= VL) break;
-        const float wd = __shfl_sync(0xffffffffu, ds[t], src), wp = __shfl_sync(0xffffffffu, pr[t], src);
-        k0 = fmaf(wd, sQ[i * VST + lane], k0);
-        k1 = fmaf(wd, sQ[i * VST + lane + 32], k1);
-        v0 = fmaf(wp, sO[i * VST + lane], v0);
-        v1 = fmaf(wp, sO[i * VST + lane + 32], v1);
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        const float pr = (lane + 32 * t < VL) ? expf(sc[r][t] * 0.125f - m[t]) * li[t] : 0.f;
+        sc[r][t] = pr;                              // P
+        dp[r][t] = pr * (dp[r][t] - de[t]);         // dS (up to the 1/8)
       }
-    }
-    out[(long long)j * (3 * VC) + VC + lane] = k0 * 0.125f;
-    out[(long long)j * (3 * VC) + VC + lane + 32] = k1 * 0.125f;
-    out[(long long)j * (3 * VC) + 2 * VC + lane] = v0;
-    out[(long long)j * (3 * VC) + 2 * VC + lane + 32] = v1;
+    vit_accum4(dp, sQ, lane, acc);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (4 * g + r < VL) {
+        out[(long long)rows[r] * (3 * VC) + VC + lane] = acc[r][0] * 0.125f;
+        out[(long long)rows[r] * (3 * VC) + VC + lane + 32] = acc[r][1] * 0.125f;
+      }
+    vit_accum4(sc, sO, lane, acc);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (4 * g + r < VL) {
+        out[(long long)rows[r] * (3 * VC) + 2 * VC + lane] = acc[r][0];
+        out[(long long)rows[r] * (3 * VC) + 2 * VC + lane + 32] = acc[r][1];
+      }
   }
 }
 
@@ -435,7 +499,17 @@ int tv1_dropout(cudaStream_t st, const float* x, const float* add, float* y, lon
   TV1_LAUNCH_CHECK();
   return 0;
 }
-int tv1_colsum(cudaStream_t st, const float* a, const float* b, int R, int C, float* out) {
+// part: CS_CHUNKS * C floats of scratch for the two-stage form (null, or a short matrix: one stage)
+int tv1_colsum(cudaStream_t st, const float* a, const float* b, int R, int C, float* out, float* part = nullptr) {
+  if (part != nullptr && b == nullptr && R >= 512) {
+    const int rpc = ((R + CS_CHUNKS - 1) / CS_CHUNKS + 7) / 8 * 8, nch = (R + rpc - 1) / rpc;
+    dim3 g1((C + 31) / 32, nch), blk(32, 8);
+    colsum_part_kernel<<<g1, blk, 0, st>>>(a, R, C, rpc, part);
+    TV1_LAUNCH_CHECK();
+    colsum_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nch, C, out);
+    TV1_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid((C + 31) / 32), block(32, 8);
   colsum_kernel<<<grid, block, 0, st>>>(a, b, R, C, out);
   TV1_LAUNCH_CHECK();
@@ -462,14 +536,15 @@ int tv1_gemm(spm_tv1* h, cudaStream_t st, const float* A, long long lda, const f
 // scratch would be waste.  The per-handle buffers are only what a forward must keep for its backward.
 struct Tv1Scratch {
   long long cap_rows = 0, cap_wide = 0, cap_d = 0, cap_i3 = 0;
-  float *PRE = nullptr, *dY = nullptr, *dAO = nullptr, *dQKV = nullptr, *dHN = nullptr, *tA = nullptr, *tB = nullptr, *G3 = nullptr;
+  float *PRE = nullptr, *dY = nullptr, *dAO = nullptr, *dQKV = nullptr, *dHN = nullptr, *tA = nullptr, *tB = nullptr, *G3 = nullptr,
+        *part = nullptr;   // CS_CHUNKS x widest row of column-sum partials
 } g_scr;
 
 int tv1_scratch(const spm_tv1* h, long long R) {
   const long long D = h->D, I3 = 3LL * h->inner, wide = std::max<long long>(std::max<long long>(I3, h->mlp), D);
   if (R <= g_scr.cap_rows && wide <= g_scr.cap_wide && D <= g_scr.cap_d && I3 <= g_scr.cap_i3) return 0;
   SPM_CUDA(cudaDeviceSynchronize());
-  for (float** p : {&g_scr.PRE, &g_scr.dY, &g_scr.dAO, &g_scr.dQKV, &g_scr.dHN, &g_scr.tA, &g_scr.tB, &g_scr.G3})
+  for (float** p : {&g_scr.PRE, &g_scr.dY, &g_scr.dAO, &g_scr.dQKV, &g_scr.dHN, &g_scr.tA, &g_scr.tB, &g_scr.G3, &g_scr.part})
     if (*p) { cudaFree(*p); *p = nullptr; }
   const long long r = std::max(R, g_scr.cap_rows), w = std::max(wide, g_scr.cap_wide), d = std::max(D, g_scr.cap_d),
                   i3 = std::max(I3, g_scr.cap_i3), rp = (r + 3) / 4 * 4;
@@ -483,6 +558,7 @@ int tv1_scratch(const spm_tv1* h, long long R) {
   SPM_CUDA(al(&g_scr.tA, w * rp));
   SPM_CUDA(al(&g_scr.tB, w * rp));
   SPM_CUDA(al(&g_scr.G3, r * d));
+  SPM_CUDA(al(&g_scr.part, (long long)CS_CHUNKS * w));
   g_scr.cap_rows = r; g_scr.cap_wide = w; g_scr.cap_d = d; g_scr.cap_i3 = i3;
   return 0;
 }
@@ -605,7 +681,7 @@ int block_backward(spm_tv1* h, cudaStream_t st, const float* grad_out, float* gr
   // ---- out = drop2(W3 drop1(act(PRE)) + b3) + y
   const float* g3 = grad_out;          // gradient behind the dropout of site 2 (the residual branch keeps grad_out itself)
   if (pf > 0.f) { SPM_TRY(tv1_dropout(st, grad_out, nullptr, s.G3, nD, pf, h->fwd_seed, 2)); g3 = s.G3; }
-  SPM_TRY(tv1_colsum(st, g3, nullptr, R, D, g_b3));
+  SPM_TRY(tv1_colsum(st, g3, nullptr, R, D, g_b3, s.part));
   SPM_TRY(tv1_transpose(st, g3, R, D, s.tA, Rp));
   SPM_TRY(tv1_transpose(st, h->FFH, R, M, s.tB, Rp));
   SPM_TRY(tv1_gemm(h, st, s.tA, Rp, s.tB, Rp, D, M, Rp, nullptr, ACT_NONE, nullptr, g_w3));               // dW3 = dOut^T drop(act(PRE))
@@ -615,24 +691,24 @@ int block_backward(spm_tv1* h, cudaStream_t st, const float* grad_out, float* gr
   if (h->vit) quickgelu_bwd_kernel<<<(unsigned)((nM + 255) / 256), 256, 0, st>>>(dF, s.PRE, nM);
   else gelu_bwd_kernel<<<(unsigned)((nM + 255) / 256), 256, 0, st>>>(dF, s.PRE, nM);
   TV1_LAUNCH_CHECK();
-  SPM_TRY(tv1_colsum(st, dF, nullptr, R, M, g_b0));
+  SPM_TRY(tv1_colsum(st, dF, nullptr, R, M, g_b0, s.part));
   SPM_TRY(tv1_transpose(st, dF, R, M, s.tA, Rp));
   SPM_TRY(tv1_transpose(st, h2, R, D, s.tB, Rp));
   SPM_TRY(tv1_gemm(h, st, s.tA, Rp, s.tB, Rp, M, D, Rp, nullptr, ACT_NONE, nullptr, g_w0));               // dW0 = dPRE^T h2
   if (h->vit) {
     // h2 = ln_2(y): dY = LN-backward(dPRE W0) + dOut
     SPM_TRY(tv1_gemm(h, st, dF, M, h->w0T, M, R, D, M, nullptr, ACT_NONE, nullptr, s.PRE));               // dH2 (PRE is free again)
-    SPM_TRY(tv1_colsum(st, s.PRE, nullptr, R, D, g_ln2_b));
+    SPM_TRY(tv1_colsum(st, s.PRE, nullptr, R, D, g_ln2_b, s.part));
     ln_bwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(h->Y, s.PRE, h->ln2_g, grad_out, R, D, s.dY, s.tA);        // tA := yhat o dH2
     TV1_LAUNCH_CHECK();
-    SPM_TRY(tv1_colsum(st, s.tA, nullptr, R, D, g_ln2_g));
+    SPM_TRY(tv1_colsum(st, s.tA, nullptr, R, D, g_ln2_g, s.part));
   } else {
     SPM_TRY(tv1_gemm(h, st, dF, M, h->w0T, M, R, D, M, nullptr, ACT_NONE, grad_out, s.dY));               // dY = dPRE W0 + dOut
   }
   // ---- y = drop0(Wout ao + b_out) + x
   const float* gy = s.dY;              // gradient behind the dropout of site 0 (the residual branch keeps dY itself)
   if (pa > 0.f) { SPM_TRY(tv1_dropout(st, s.dY, nullptr, s.G3, nD, pa, h->fwd_seed, 0)); gy = s.G3; }
-  SPM_TRY(tv1_colsum(st, gy, nullptr, R, D, g_bout));
+  SPM_TRY(tv1_colsum(st, gy, nullptr, R, D, g_bout, s.part));
   SPM_TRY(tv1_transpose(st, gy, R, D, s.tA, Rp));
   SPM_TRY(tv1_transpose(st, h->AO, R, I, s.tB, Rp));
   SPM_TRY(tv1_gemm(h, st, s.tA, Rp, s.tB, Rp, D, I, Rp, nullptr, ACT_NONE, nullptr, g_wout));             // dWout = dY^T ao
@@ -648,16 +724,16 @@ int block_backward(spm_tv1* h, cudaStream_t st, const float* grad_out, float* gr
     TV1_LAUNCH_CHECK();
   }
   // ---- q, k, v = W{q,k,v} LN(x) (+ b)
-  if (h->vit) SPM_TRY(tv1_colsum(st, s.dQKV, nullptr, R, 3 * I, g_bqkv));
+  if (h->vit) SPM_TRY(tv1_colsum(st, s.dQKV, nullptr, R, 3 * I, g_bqkv, s.part));
   SPM_TRY(tv1_transpose(st, s.dQKV, R, 3 * I, s.tA, Rp));
   SPM_TRY(tv1_transpose(st, h->HN, R, D, s.tB, Rp));
   SPM_TRY(tv1_gemm(h, st, s.tA, Rp, s.tB, Rp, 3 * I, D, Rp, nullptr, ACT_NONE, nullptr, g_qkv));          // [dWq; dWk; dWv]
   SPM_TRY(tv1_gemm(h, st, s.dQKV, 3 * I, h->wqkvT, 3 * I, R, D, 3 * I, nullptr, ACT_NONE, nullptr, s.dHN));   // dLN = dQKV Wqkv
   // ---- LayerNorm + the residual branch (dY)
-  SPM_TRY(tv1_colsum(st, s.dHN, nullptr, R, D, g_ln_b));
+  SPM_TRY(tv1_colsum(st, s.dHN, nullptr, R, D, g_ln_b, s.part));
   ln_bwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(h->x, s.dHN, h->ln_g, s.dY, R, D, grad_x, s.tA);             // tA := xhat o dLN
   TV1_LAUNCH_CHECK();
-  SPM_TRY(tv1_colsum(st, s.tA, nullptr, R, D, g_ln_g));
+  SPM_TRY(tv1_colsum(st, s.tA, nullptr, R, D, g_ln_g, s.part));
   return 0;
 }
 
@@ -761,16 +837,16 @@ int spm_layernorm_backward(void* stream, const float* x, const float* dy, const 
                            float* dgamma, float* dbeta, float* workspace) {
   SPM_CHECK(x && dy && gamma && dx && dgamma && dbeta && workspace && rows > 0 && C > 0, "spm_layernorm_backward: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  SPM_TRY(tv1_colsum(st, dy, nullptr, rows, C, dbeta));
-  ln_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, dy, gamma, nullptr, rows, C, dx, workspace);   // workspace [rows, C] := xhat o dy
+  SPM_TRY(tv1_colsum(st, dy, nullptr, rows, C, dbeta, workspace + (long long)rows * C));
+  ln_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, dy, gamma, nullptr, rows, C, dx, workspace);   // workspace [rows, C] := xhat o dy, then 64 x C partials
   TV1_LAUNCH_CHECK();
-  SPM_TRY(tv1_colsum(st, workspace, nullptr, rows, C, dgamma));
+  SPM_TRY(tv1_colsum(st, workspace, nullptr, rows, C, dgamma, workspace + (long long)rows * C));
   return 0;
 }
 
 long long spm_linear_backward_workspace(int M, int N, int K) {
   const long long Mp = (M + 3) / 4 * 4;
-  return (long long)M * N + (long long)N * Mp + (long long)K * Mp + (long long)K * N;
+  return (long long)M * N + (long long)N * Mp + (long long)K * Mp + (long long)K * N + (long long)CS_CHUNKS * N;
 }
 
 int spm_linear_backward(void* stream, int precision, const float* x, const float* W, const float* bias, const float* y,
@@ -794,6 +870,7 @@ int spm_linear_backward(void* stream, int precision, const float* x, const float
   float* gT = g + (long long)M * N;
   float* xT = gT + (long long)N * Mp;
   float* WT = xT + (long long)K * Mp;
+  float* part = WT + (long long)K * N;
   const float* gr = dy;
   if (act != ACT_NONE) {
     if (act == ACT_GELU_ERF) SPM_TRY(tv1_gemm(&cfg, st, x, K, W, K, M, N, K, bias, ACT_NONE, nullptr, g));   // pre-activation
@@ -802,7 +879,7 @@ int spm_linear_backward(void* stream, int precision, const float* x, const float
     TV1_LAUNCH_CHECK();
     gr = g;
   }
-  if (db != nullptr) SPM_TRY(tv1_colsum(st, gr, nullptr, M, N, db));
+  if (db != nullptr) SPM_TRY(tv1_colsum(st, gr, nullptr, M, N, db, part));
   SPM_TRY(tv1_transpose(st, gr, M, N, gT, Mp));
   SPM_TRY(tv1_transpose(st, x, M, K, xT, Mp));
   SPM_TRY(tv1_gemm(&cfg, st, gT, Mp, xT, Mp, N, K, Mp, nullptr, ACT_NONE, nullptr, dW));          // dW = g^T x

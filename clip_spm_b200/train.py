@@ -182,7 +182,8 @@ class _LayerNorm(torch.autograd.Function):
     def backward(ctx, dy):
         x, g = ctx.saved_tensors
         dy = dy.contiguous()
-        dx, dg, db, ws = torch.empty_like(x), torch.empty_like(g), torch.empty_like(g), torch.empty_like(x)
+        dx, dg, db = torch.empty_like(x), torch.empty_like(g), torch.empty_like(g)
+        ws = torch.empty((x.shape[0] + 64) * x.shape[1], device=x.device)
         _lib.check(_lib.load().spm_layernorm_backward(_stream(), _ptr(x), _ptr(dy), _ptr(g), x.shape[0], x.shape[1], _ptr(dx),
                                                       _ptr(dg), _ptr(db), _ptr(ws)))
         return dx, dg, db

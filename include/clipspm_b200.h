@@ -234,9 +234,9 @@ int spm_tv1_backward(spm_tv1* h, void* stream, const float* grad_out, float* gra
  * tower (x + out_proj(attn(ln_1 x)); + c_proj(QuickGELU(c_fc(ln_2 .)))), 197 tokens per frame, 12 heads x 64 -- forward and
  * backward for the training step (the reference's optimiser steps the tower too, run/main_run.py:84-88).  Parameters in the
  * reference's layouts: attn.in_proj_weight [2304,768] / in_proj_bias, attn.out_proj, ln_1, ln_2, mlp.c_fc, mlp.c_proj.
- * x, out, grads: fp32 [n_frames * 197, 768]; same handle rules as spm_tv1 (one backward per forward, gradients overwritten;
+ * x, out, grads: fp32 [n_frames * 197, 768]; same handle rules as the spm_tv1_* block: one backward per forward, gradients overwritten,
  * spm_tv1_set_dropout / spm_tv1_destroy apply; the backward scratch is shared process-wide, so training calls belong on
- * one stream). */
+  * one stream. */
 int spm_vitblock_create(int precision, spm_tv1** out);
 int spm_vitblock_load_weights(spm_tv1* h, void* stream, const float* ln1_g, const float* ln1_b, const float* in_proj_w,
                               const float* in_proj_b, const float* out_w, const float* out_b, const float* ln2_g,
@@ -247,7 +247,7 @@ int spm_vitblock_backward(spm_tv1* h, void* stream, const float* grad_out, float
                           float* g_fc_w, float* g_fc_b, float* g_proj_w, float* g_proj_b);
 
 /* nn.LayerNorm (eps 1e-5) over rows of C, forward and backward (ln_pre / ln_post of the tower, clip_fsar.py:664,668):
- * dx, dgamma, dbeta overwritten; workspace: rows * C floats. */
+ * dx, dgamma, dbeta overwritten; workspace: (rows + 64) * C floats. */
 int spm_layernorm_forward(void* stream, const float* x, int rows, int C, const float* gamma, const float* beta, float* y);
 int spm_layernorm_backward(void* stream, const float* x, const float* dy, const float* gamma, int rows, int C, float* dx,
                            float* dgamma, float* dbeta, float* workspace);

@@ -57,6 +57,9 @@ def mine(dropout=True, backward=True):
     opt.zero_grad()
 
 
+ONLY_WHOLE = os.environ.get("SPM_TIMING_ONLY_WHOLE") == "1"      # ncu launch list of one whole step: skip everything else
+if ONLY_WHOLE:
+    steps = 1
 with torch.no_grad():
     ms_f, l_f = timed(lambda: mine(True, False), steps)
 ms_s, l_s = timed(mine, steps)
@@ -82,6 +85,67 @@ def eager():
     opt_e.zero_grad()
 
 
-ms_e, _ = timed(eager, max(3, steps // 5))
+ms_e, _ = timed(eager, max(3, steps // 5)) if not ONLY_WHOLE else (float("nan"), 0)
 print("PyTorch eager (oracle head on CUDA, autograd, TF32 matmuls, fused Adam, GradScaler; dropout p = 0): %.2f ms/step = "
       "%.1f steps/s  ->  %.1fx" % (ms_e, 1e3 / ms_e, ms_e / ms_s))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# whole training step from the frames: ViT-B/16 tower + head forward, backward, Adam over all parameters (config-1 shape)
+# ------------------------------------------------------------------------------------------------------------------
+def whole_step(way, shot, qpc, T, n_steps):
+    from clip_spm_b200 import CNN
+    from tests.helpers import make_cfg
+    wf = O.make_weights("ViT-B/16", seed=0, protocol="P1", head_only=False)
+    epi = O.make_episode(6001, way, shot, qpc, T, ncls, "P1", images=True)
+    epi = {k: v.to(dev) for k, v in epi.items()}
+    frames = (way * shot + way * qpc) * T
+    net = CNN(make_cfg("ViT-B/16", T, False, way), text_features_test=text.cpu(), text_features_train=text.cpu(), precision="bf16")
+    net.load_state_dict(wf, strict=False)
+    net.train_backbone = True
+    net.train()
+    opt_w = optim.Adam(net.trainable_parameters(), lr=1e-6, betas=(0.5, 0.999))
+    sc = optim.GradScaler(dev)
+
+    def step():
+        out = net(epi)
+        sc.scale(net.loss(out, epi["target_labels"])).backward()
+        sc.step(opt_w)
+        sc.update()
+        opt_w.zero_grad()
+    ms, launches = timed(step, n_steps)
+    torch.cuda.reset_peak_memory_stats()
+    step()
+    torch.cuda.synchronize()
+    print("clip_spm_b200 WHOLE train step (%d frames: tower + head forward, backward, Adam over %d parameters; tf32 products, "
+          "dropout on): %.1f ms/step = %.2f episodes/s (%d library launches/step, torch allocator peak %.1f GB)"
+          % (frames, sum(p.numel() for p in net.trainable_parameters()), ms, 1e3 / ms, launches,
+             torch.cuda.max_memory_allocated() / 2 ** 30))
+    del net, opt_w
+    torch.cuda.empty_cache()
+    if ONLY_WHOLE:
+        return
+    # PyTorch eager: the oracle tower + head on CUDA under autograd, fp32 with TF32 matmuls and under autocast(bf16)
+    wfe = {k: v.to(dev).clone().requires_grad_(v.dtype.is_floating_point and k != "scale") for k, v in wf.items()}
+    oe = torch.optim.Adam([p for p in wfe.values() if p.requires_grad], lr=1e-6, betas=(0.5, 0.999), fused=True)
+    se = torch.amp.GradScaler(dev)
+    cfg = dict(backbone="ViT-B/16", seq_len=T, mid_dim=512, params=O.DEFAULT_PARAMS, single_direct=False)
+    for ac in (False, True):
+        def estep():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                su_ = O.vit_forward(wfe, epi["context_images"], chunk=512).reshape(-1, T, 512)
+                qu_ = O.vit_forward(wfe, epi["target_images"], chunk=512).reshape(-1, T, 512)
+            st = O.head_forward(wfe, text, su_.float(), qu_.float(), epi["context_labels"], epi["real_support_labels"],
+                                epi["real_target_labels"], O.DEFAULT_PARAMS, False)
+            loss = torch.nn.functional.cross_entropy(st["logits"][0], epi["target_labels"].long(), reduction="sum") / 16 \
+                + 0.001 * st["dists"]
+            se.scale(loss).backward()
+            se.step(oe)
+            se.update()
+            oe.zero_grad()
+        ms_e, _ = timed(estep, max(2, n_steps // 3))
+        print("PyTorch eager whole step (%s): %.1f ms/step = %.2f episodes/s -> library is %.2fx"
+              % ("autocast bf16 tower" if ac else "fp32 / TF32 matmuls", ms_e, 1e3 / ms_e, ms_e / ms))
+
+
+whole_step(5, 1, 1, 8, 1 if ONLY_WHOLE else 6)
