@@ -284,6 +284,54 @@ def single_episode_leg(CNN, make_cfg, sweep, dev, way, shot, qpc, n_episodes, la
     return rec
 
 
+def train_step_leg(CNN, make_cfg, sweep, optim, _lib, dev, way, shot, qpc, tower, n_steps, label):
+    """The reference's training iteration (run/main_run.py:245-254 train_task + :207-209 optimiser): model(input) in train mode
+    (dropout active, prompt rows of text_features_train), loss, scaler.scale(loss).backward(), scaler.step, scaler.update,
+    zero_grad -- through clip_spm_b200's train mode, the library's Adam(betas=(0.5, 0.999)) and GradScaler.  tower=False: the
+    frame encoder runs frozen on the bf16 evaluation kernels and only the head is differentiated; tower=True (ViT-B/16): the
+    differentiable tf32 tower as well, Adam over every parameter.  Inputs resident on the device, CUDA-event timing."""
+    net = CNN(make_cfg("ViT-B/16", T, False, way), max_episodes=1, device=dev)
+    net.init_random_(seed=0)
+    text = torch.randn(N_TEXT, 512, generator=torch.Generator().manual_seed(0))
+    net.text_features_test, net.text_features_train = text, text
+    net.train_backbone = bool(tower)
+    net.train()
+    ep = sweep.synthetic_episode_batch([30000], way, shot, qpc, T, N_TEXT, dev)
+    inp = {k: (v if k.endswith("images") else v[0]) for k, v in ep.items()}
+    opt = optim.Adam(net.trainable_parameters(), lr=1e-6, betas=(0.5, 0.999))
+    scaler = optim.GradScaler(dev)
+
+    def step():
+        out = net(inp)
+        loss = net.loss(out, inp["target_labels"])
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        opt.zero_grad()
+        return loss
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    l0 = _lib.load().spm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n_steps
+    frames = (way * shot + way * qpc) * T
+    rec = {"workload": label, "value": 1e3 / ms, "unit": "episodes/s (training steps/s)", "ms_per_step": ms, "steps_timed": n_steps,
+           "frames_per_step": frames, "trainable_parameters": int(sum(p.numel() for p in net.trainable_parameters())),
+           "library_launches_per_step": (_lib.load().spm_launch_count() - l0) / n_steps, "last_loss": float(loss.detach()),
+           "arithmetic": ("tf32 tensor-core products, fp32 SIMT attention, fp32 accumulation and state" if tower else
+                          "frozen tower: bf16 tcgen05 evaluation kernels; head: tf32 products"),
+           "call": "CNN.forward(dict) in train mode + loss + optim.GradScaler.scale(loss).backward() + step + update + zero_grad"}
+    del net, opt, ep, inp
+    torch.cuda.empty_cache()
+    return rec
+
+
 def _loss_acc(out, target_labels, tasks_per_batch):
     """run/main_run.py:390-392 + utils/utils.py:174-186,259-264 on the forward's outputs (plain torch, as the caller's
     own _loss_and_acc is; the hot path's fused version is spm_eval)."""
@@ -358,7 +406,7 @@ def main():
 
     import __graft_entry__
     __graft_entry__.build()
-    from clip_spm_b200 import CNN, _lib, sweep
+    from clip_spm_b200 import CNN, _lib, optim, sweep
     from clip_spm_b200.config import make_cfg
     # several ranks on one box: keep each rank (and the pinned buffers it allocates) on its GPU's NUMA node
     bound = sweep.bind_to_gpu_cpus(local) if world > 1 else None
@@ -547,6 +595,10 @@ def main():
                 "BASELINE config 1 shape: ViT-B/16 5-way 1-shot, 80 frames, one episode per CNN.forward(dict) call")),
             ("single_episode_config2", lambda: single_episode_leg(CNN, make_cfg, sweep, dev, 5, 5, 1, 24,
                 "BASELINE config 2 shape: ViT-B/16 5-way 5-shot, 240 frames, one episode per CNN.forward(dict) call")),
+            ("train_step_head_config2", lambda: train_step_leg(CNN, make_cfg, sweep, optim, _lib, dev, 5, 5, 1, False, 10,
+                "training iteration at BASELINE config 2 shape (240 frames): frozen ViT-B/16 tower, differentiable CLIP-SPM head")),
+            ("train_step_full_config1", lambda: train_step_leg(CNN, make_cfg, sweep, optim, _lib, dev, 5, 1, 1, True, 6,
+                "training iteration at BASELINE config 1 shape (80 frames): ViT-B/16 tower AND head differentiated, Adam over all parameters")),
             ("config3", lambda: config_leg(lib, _lib, sweep, CNN, make_cfg, dev, peaks, "ViT-B/16", 5, 1, 1, 16, 24, 8, 6,
                 VIT_GFLOP_PER_FRAME_EXECUTED, "BASELINE config 3: ViT-B/16 SSv2-Full shape 5-way 1-shot, T=16 (160 frames), "
                 "bidirectional OTAM 16x18")),
