@@ -89,6 +89,8 @@ SIGNATURES = {
     "spm_adam_destroy": (c_int, [c_void_p]),
     "spm_adam_step": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), ctypes.c_double, ctypes.c_double,
                               ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p]),
+    "spm_sgd_step": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p), ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                             c_void_p]),
     "spm_adam_state": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
     "spm_scaler_update": (c_int, [c_void_p, c_void_p, c_float, c_float, c_int]),
     "spm_softdtw_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p]),

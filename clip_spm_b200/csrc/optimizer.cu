@@ -90,6 +90,32 @@ __global__ void adam_kernel(float* const* __restrict__ params, float* const* __r
   }
 }
 
+// torch.optim.SGD(lr, momentum, weight_decay) (dampening 0, nesterov False; run/main_run.py:92-96): g += wd p;
+// buf = g on a parameter's first step, momentum buf + g afterwards; p -= lr buf  (momentum 0: p -= lr g).  The momentum buffer is
+// the handle's first state tensor.
+__global__ void sgd_kernel(float* const* __restrict__ params, float* const* __restrict__ grads, float* const* __restrict__ bufs,
+                           const long long* __restrict__ numel, const int* __restrict__ chunk_tensor,
+                           const long long* __restrict__ chunk_off, const float* __restrict__ step,
+                           const float* __restrict__ found_inf, float lr, float momentum, float weight_decay) {
+  if (*found_inf != 0.f) return;
+  const int t = chunk_tensor[blockIdx.x];
+  const float* g = grads[t];
+  if (g == nullptr) return;
+  float* p = params[t];
+  float* b = bufs[t];
+  const bool first = step[t] == 0.f;
+  const long long o0 = chunk_off[blockIdx.x], o1 = min(o0 + OPT_CHUNK, numel[t]);
+  for (long long i = o0 + threadIdx.x; i < o1; i += blockDim.x) {
+    const float pi = p[i];
+    float gi = fmaf(weight_decay, pi, g[i]);
+    if (momentum != 0.f) {
+      gi = first ? gi : fmaf(momentum, b[i], gi);
+      b[i] = gi;
+    }
+    p[i] = fmaf(-lr, gi, pi);
+  }
+}
+
 __global__ void adam_bump_kernel(float* __restrict__ step, float* const* __restrict__ grads, int n,
                                  const float* __restrict__ found_inf) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,6 +234,34 @@ int spm_adam_step(spm_adam* a, void* stream, float* const* grads, double lr, dou
   }
   adam_kernel<<<a->n_chunks, 256, 0, st>>>(a->d_params, a->d_grads, a->d_m, a->d_v, a->d_numel, a->d_chunk_tensor, a->d_chunk_off,
                                           a->d_step, found, lr, beta1, beta2, (float)eps, (float)weight_decay);
+  SPM_CUDA(cudaGetLastError());
+  count_launch();
+  adam_bump_kernel<<<(a->n + 255) / 256, 256, 0, st>>>(a->d_step, a->d_grads, a->n, found);
+  SPM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int spm_sgd_step(spm_adam* a, void* stream, float* const* grads, double lr, double momentum, double weight_decay,
+                 float* scaler_state) {
+  SPM_CHECK(a != nullptr && grads != nullptr, "spm_sgd_step: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool same = true;
+  for (int i = 0; i < a->n; ++i) same = same && a->h_grads[i] == grads[i];
+  if (!same) {
+    std::memcpy(a->h_grads.data(), grads, (size_t)a->n * sizeof(float*));
+    SPM_CUDA(cudaMemcpyAsync(a->d_grads, a->h_grads.data(), (size_t)a->n * sizeof(float*), cudaMemcpyHostToDevice, st));
+    SPM_CUDA(cudaStreamSynchronize(st));
+  }
+  const float* found = a->d_found_inf;
+  if (scaler_state != nullptr) {
+    unscale_check_kernel<<<a->n_chunks, 256, 0, st>>>(a->d_grads, a->d_numel, a->d_chunk_tensor, a->d_chunk_off, scaler_state);
+    SPM_CUDA(cudaGetLastError());
+    count_launch();
+    found = scaler_state + 2;
+  }
+  sgd_kernel<<<a->n_chunks, 256, 0, st>>>(a->d_params, a->d_grads, a->d_m, a->d_numel, a->d_chunk_tensor, a->d_chunk_off, a->d_step,
+                                         found, (float)lr, (float)momentum, (float)weight_decay);
   SPM_CUDA(cudaGetLastError());
   count_launch();
   adam_bump_kernel<<<(a->n + 255) / 256, 256, 0, st>>>(a->d_step, a->d_grads, a->n, found);

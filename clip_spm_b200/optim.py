@@ -75,6 +75,25 @@ class Adam:
         return m.view_as(self.params[i]), v.view_as(self.params[i]), float(t)
 
 
+class SGD(Adam):
+    """torch.optim.SGD(params, lr, momentum, weight_decay) (run/main_run.py:92-96, SOLVER.OPTIM_METHOD == "sgd") on the same
+    multi-tensor machinery; `state(i)[0]` is the momentum buffer."""
+
+    def __init__(self, params, lr=1e-3, momentum=0.0, weight_decay=0.0):
+        super().__init__(params, lr=lr, weight_decay=weight_decay)
+        self.param_groups[0].update(momentum=float(momentum))
+
+    def step(self, _scaler_state=None):
+        g = self.param_groups[0]
+        grads = [None if p.grad is None else p.grad for p in self.params]
+        for t in grads:
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+                raise RuntimeError("gradients must be contiguous fp32")
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.load().spm_sgd_step(self._h, st, _ptr_array(grads), g["lr"], g["momentum"], g["weight_decay"],
+                                            None if _scaler_state is None else ctypes.c_void_p(_scaler_state.data_ptr())))
+
+
 class _DeviceArray:
     """A raw fp32 device buffer of the library, viewed through __cuda_array_interface__ (read-only use: state_dict)."""
 

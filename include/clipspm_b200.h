@@ -277,6 +277,10 @@ int spm_adam_destroy(spm_adam* a);
 int spm_adam_step(spm_adam* a, void* stream, float* const* grads, double lr, double beta1, double beta2, double eps,
                   double weight_decay, float* scaler_state);   /* the hyper-parameters as the Python floats they are */
 int spm_adam_state(spm_adam* a, int i, float** exp_avg, float** exp_avg_sq, float** step);
+/* SOLVER.OPTIM_METHOD == "sgd" (run/main_run.py:92-96 torch.optim.SGD(lr, momentum, weight_decay)) on the same handle: its first
+ * state tensor is the momentum buffer (spm_adam_state's exp_avg); same scaler_state contract as spm_adam_step */
+int spm_sgd_step(spm_adam* a, void* stream, float* const* grads, double lr, double momentum, double weight_decay,
+                 float* scaler_state);
 int spm_scaler_update(void* stream, float* scaler_state, float growth_factor, float backoff_factor, int growth_interval);
 
 /* Frame-encoder self-attention stage (models/clip_fsar.py:626,638): qkv [F*197, 2304] bf16 (q | k | v, head h at

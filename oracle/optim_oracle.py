@@ -30,6 +30,25 @@ class AdamOracle:
             self.p[i] = self.p[i] - step_size * (self.m[i] / denom)
 
 
+class SGDOracle:
+    """torch.optim.SGD(params, lr, momentum, weight_decay), dampening 0, nesterov False (run/main_run.py:92-96)."""
+
+    def __init__(self, params, lr=1e-3, momentum=0.0, weight_decay=0.0):
+        self.p = [np.array(p, dtype=np.float32) for p in params]
+        self.buf = [None] * len(self.p)
+        self.lr, self.mom, self.wd = lr, momentum, weight_decay
+
+    def step(self, grads):
+        for i, g in enumerate(grads):
+            if g is None:
+                continue
+            g = np.asarray(g, dtype=np.float32) + np.float32(self.wd) * self.p[i]
+            if self.mom != 0:
+                self.buf[i] = g.copy() if self.buf[i] is None else np.float32(self.mom) * self.buf[i] + g
+                g = self.buf[i]
+            self.p[i] = self.p[i] - np.float32(self.lr) * g
+
+
 class GradScalerOracle:
     """torch.amp.GradScaler(init_scale=65536, growth_factor=2, backoff_factor=0.5, growth_interval=2000):
     step(opt, grads) unscales, skips the optimiser step when a gradient is inf / nan; update() adapts the scale."""

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.optim_oracle import AdamOracle, GradScalerOracle
+from oracle.optim_oracle import AdamOracle, GradScalerOracle, SGDOracle
 
 
 def _problem(seed=0):
@@ -33,6 +33,24 @@ def test_adam_oracle_matches_torch_adam():
     for p, m, v in zip(tp, orc.m, orc.v):
         assert np.allclose(opt.state[p]["exp_avg"].numpy(), m, rtol=2e-6, atol=1e-6)
         assert np.allclose(opt.state[p]["exp_avg_sq"].numpy(), v, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("momentum", [0.0, 0.9])
+def test_sgd_oracle_matches_torch_sgd(momentum):
+    params, grads = _problem(1)
+    tp = [p.clone().requires_grad_(True) for p in params]
+    opt = torch.optim.SGD(tp, lr=1e-2, momentum=momentum, weight_decay=5e-4)
+    orc = SGDOracle([p.numpy() for p in params], lr=1e-2, momentum=momentum, weight_decay=5e-4)
+    for k, gs in enumerate(grads):
+        for p, g in zip(tp, gs):
+            p.grad = g.clone()
+        if k == 0:
+            tp[2].grad = None            # no gradient on the first step: its momentum buffer starts one step later
+            gs = [g if i != 2 else None for i, g in enumerate(gs)]
+        opt.step()
+        orc.step([None if g is None else g.numpy() for g in gs])
+    for p, q in zip(tp, orc.p):
+        assert np.allclose(p.detach().numpy(), q, rtol=2e-6, atol=2e-6)
 
 
 def test_grad_scaler_oracle_matches_torch_grad_scaler():

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.optim_oracle import AdamOracle, GradScalerOracle
+from oracle.optim_oracle import AdamOracle, GradScalerOracle, SGDOracle
 from tests.test_optim_cpu import _problem
 
 pytestmark = pytest.mark.gpu
@@ -37,6 +37,31 @@ def test_adam_matches_oracle_and_torch():
     assert np.allclose(v.cpu().numpy(), orc.v[4], rtol=1e-5, atol=1e-7)
     opt.zero_grad()
     assert all(p.grad is None for p in mine)
+
+
+@pytest.mark.parametrize("momentum", [0.0, 0.9])
+def test_sgd_matches_oracle_and_torch(momentum):
+    from clip_spm_b200 import optim
+    params, grads = _problem(1)
+    mine = [p.clone().cuda().requires_grad_(True) for p in params]
+    theirs = [p.clone().cuda().requires_grad_(True) for p in params]
+    opt = optim.SGD(mine, lr=1e-2, momentum=momentum, weight_decay=5e-4)
+    ref = torch.optim.SGD(theirs, lr=1e-2, momentum=momentum, weight_decay=5e-4)
+    orc = SGDOracle([p.numpy() for p in params], lr=1e-2, momentum=momentum, weight_decay=5e-4)
+    for k, gs in enumerate(grads):
+        for p, q, g in zip(mine, theirs, gs):
+            p.grad = g.clone().cuda()
+            q.grad = g.clone().cuda()
+        if k == 0:
+            mine[2].grad = None
+            theirs[2].grad = None
+            gs = [g if i != 2 else None for i, g in enumerate(gs)]
+        opt.step()
+        ref.step()
+        orc.step([None if g is None else g.numpy() for g in gs])
+    for p, q, o in zip(mine, theirs, orc.p):
+        assert np.allclose(p.detach().cpu().numpy(), o, rtol=2e-6, atol=2e-6)
+        assert torch.allclose(p.detach(), q.detach(), rtol=2e-6, atol=2e-6)
 
 
 def test_grad_scaler_skips_overflowed_steps_on_the_device():
