@@ -249,7 +249,7 @@ def config_leg(lib, _lib, sweep, CNN, make_cfg, dev, peaks, backbone, way, shot,
     return rec
 
 
-def single_episode_leg(CNN, make_cfg, sweep, dev, way, shot, qpc, n_episodes, label):
+def single_episode_leg(CNN, make_cfg, sweep, dev, way, shot, qpc, n_episodes, label, host_dict=False):
     """The reference caller's own loop (run/main_run.py:266-279 Learner.test): per episode, move the task's tensors to
     the device (prepare_task), ONE model(inputs) call on the dict, loss / accuracy, two .item() host syncs."""
     net = CNN(make_cfg("ViT-B/16", T, False, way), max_episodes=1, device=dev)
@@ -258,7 +258,18 @@ def single_episode_leg(CNN, make_cfg, sweep, dev, way, shot, qpc, n_episodes, la
     S_, Q_ = way * shot, way * qpc
     hosts = [sweep.synthetic_episode_batch([20000 + i], way, shot, qpc, T, N_TEXT, "cpu", pin=True) for i in range(4)]
 
-    def one(h):
+    def one_host(h, nxt=None):
+        # the same caller without prepare_task's `.to(device)` of the images: the model takes the pinned host tensors and
+        # overlaps their copy with the encoder (CNN.forward -> spm_eval_host); loss / accuracy arrive with the outputs
+        out = net({"context_images": h["context_images"], "target_images": h["target_images"],
+                   "context_labels": h["context_labels"][0], "real_support_labels": h["real_support_labels"][0],
+                   "real_target_labels": h["real_target_labels"][0], "target_labels": h["target_labels"][0],
+                   "next_images": None if nxt is None else (nxt["context_images"], nxt["target_images"])})
+        return out["loss"].item(), out["acc"].item()
+
+    def one(h, nxt=None):
+        if host_dict:
+            return one_host(h, nxt)
         inp = {"context_images": h["context_images"].to(dev, non_blocking=True),
                "target_images": h["target_images"].to(dev, non_blocking=True),
                "context_labels": h["context_labels"][0].to(dev), "real_support_labels": h["real_support_labels"][0].to(dev),
@@ -267,17 +278,19 @@ def single_episode_leg(CNN, make_cfg, sweep, dev, way, shot, qpc, n_episodes, la
         loss, acc = _loss_acc(out, inp["target_labels"], net.tasks_per_batch)
         return loss.item(), acc.item()                   # run/main_run.py:278-279
     for i in range(3):
-        one(hosts[i % 4])
+        one(hosts[i % 4], hosts[(i + 1) % 4])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(n_episodes):
-        one(hosts[i % 4])
+        one(hosts[i % 4], hosts[(i + 1) % 4])    # look-ahead of one episode, as a prefetching DataLoader provides
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     frames = (S_ + Q_) * T
     rec = {"workload": label, "value": n_episodes / dt, "unit": "episodes/s", "ms_per_episode": 1e3 * dt / n_episodes,
            "frames_per_s": n_episodes * frames / dt, "episodes_timed": n_episodes,
-           "call": "CNN.forward(dict) per episode from pinned host tensors + loss/accuracy + 2 x .item()",
+           "call": ("CNN.forward(dict of PINNED HOST tensors + the next episode's images as a look-ahead) per episode: the next "
+                    "episode's copy runs behind this one's compute; loss/accuracy returned with the outputs + 2 x .item()") if host_dict else
+                   "CNN.forward(dict) per episode from pinned host tensors + loss/accuracy + 2 x .item()",
            "h2d_bytes_per_episode": frames * 3 * 224 * 224 * 4}
     del net, hosts
     torch.cuda.empty_cache()
@@ -595,6 +608,10 @@ def main():
                 "BASELINE config 1 shape: ViT-B/16 5-way 1-shot, 80 frames, one episode per CNN.forward(dict) call")),
             ("single_episode_config2", lambda: single_episode_leg(CNN, make_cfg, sweep, dev, 5, 5, 1, 24,
                 "BASELINE config 2 shape: ViT-B/16 5-way 5-shot, 240 frames, one episode per CNN.forward(dict) call")),
+            ("single_episode_config2_host_dict", lambda: single_episode_leg(CNN, make_cfg, sweep, dev, 5, 5, 1, 24,
+                "BASELINE config 2 shape, one episode per CNN.forward(dict) call, images handed over as pinned host tensors", True)),
+            ("single_episode_config1_host_dict", lambda: single_episode_leg(CNN, make_cfg, sweep, dev, 5, 1, 1, 40,
+                "BASELINE config 1 shape, one episode per CNN.forward(dict) call, images handed over as pinned host tensors", True)),
             ("train_step_head_config2", lambda: train_step_leg(CNN, make_cfg, sweep, optim, _lib, dev, 5, 5, 1, False, 10,
                 "training iteration at BASELINE config 2 shape (240 frames): frozen ViT-B/16 tower, differentiable CLIP-SPM head")),
             ("train_step_full_config1", lambda: train_step_leg(CNN, make_cfg, sweep, optim, _lib, dev, 5, 1, 1, True, 6,

@@ -418,8 +418,11 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
   const long long my_s = (long long)first_n * fs * frame_bytes, my_q = (long long)first_n * fq * frame_bytes;
   if (hint_su != nullptr && (pf_s > h->pf_cap_s || pf_q > h->pf_cap_q)) {
     SPM_CUDA(cudaStreamSynchronize(h->copy_stream));   // nobody may still be writing the old buffers
+    SPM_CUDA(cudaStreamSynchronize(h->compute_stream));
     SPM_TRY(drealloc_t(h, &h->pf_su, pf_s));
     SPM_TRY(drealloc_t(h, &h->pf_qu, pf_q));
+    SPM_TRY(drealloc_t(h, &h->pf_su_alt, pf_s));
+    SPM_TRY(drealloc_t(h, &h->pf_qu_alt, pf_q));
     h->pf_cap_s = pf_s; h->pf_cap_q = pf_q;
     h->pf_src_su = h->pf_src_qu = nullptr;
   }
@@ -498,11 +501,13 @@ static int eval_host_impl(spm_handle* h, int n_episodes, int S, int Q, int W, co
     SPM_CUDA(cudaMemcpyAsync(p_pred + (long long)e0 * Q, s.pred + (long long)slot * Q, (size_t)E * Q * 4, cudaMemcpyDeviceToHost, ks));
     SPM_CUDA(cudaEventRecord(h->ev_done[c], ks));
   }
-  // Behind this call's own copies (same FIFO copy stream): the first chunk of the next call, while the last chunks of
-  // this one compute.  The buffers may still be read by this call's chunk 0.
+  // Behind this call's own copies (same FIFO copy stream): the first chunk of the next call, while this call computes.
+  // This call's chunk 0 may be reading the current prefetch buffers, so the copy goes into the other set (last read by the
+  // PREVIOUS call, which synchronised its compute stream before returning) and the two sets swap roles.
   h->pf_src_su = h->pf_src_qu = nullptr;
   if (hint_su != nullptr && hint_qu != nullptr && hint_n > 0) {
-    SPM_CUDA(cudaStreamWaitEvent(cs, h->ev_done[0], 0));
+    std::swap(h->pf_su, h->pf_su_alt);
+    std::swap(h->pf_qu, h->pf_qu_alt);
     SPM_CUDA(cudaMemcpyAsync(h->pf_su, hint_su, (size_t)pf_s, cudaMemcpyHostToDevice, cs));
     SPM_CUDA(cudaMemcpyAsync(h->pf_qu, hint_qu, (size_t)pf_q, cudaMemcpyHostToDevice, cs));
     SPM_CUDA(cudaEventRecord(h->pf_event, cs));

@@ -219,6 +219,9 @@ struct spm_handle {
   const void *next_su = nullptr, *next_qu = nullptr;   // hint given by the caller, consumed by the next call
   int next_n = 0;                                      // episodes the hinted call will evaluate
   uint8_t *pf_su = nullptr, *pf_qu = nullptr;
+  // second set: the next call's first chunk is copied into the buffers the CURRENT call does not read, so that the copy
+  // need not wait for this call's compute (a one-chunk call -- one episode per call -- would otherwise overlap nothing)
+  uint8_t *pf_su_alt = nullptr, *pf_qu_alt = nullptr;
   long long pf_cap_s = 0, pf_cap_q = 0;
   const void *pf_src_su = nullptr, *pf_src_qu = nullptr;   // what the buffers hold (null = nothing)
   long long pf_bytes_s = 0, pf_bytes_q = 0;

@@ -421,7 +421,25 @@ class CNN(nn.Module):
 
     # ------------------------------------------------------------------------------------------------- forward
     def forward(self, inputs):
-        """models/model_clipspm.py:111-144: one episode dict -> {"logits": [1,Q,W], "dists": 0-d}."""
+        """models/model_clipspm.py:111-144: one episode dict -> {"logits": [1,Q,W], "dists": 0-d}.
+        HOST image tensors (the DataLoader's pinned batch, before run/main_run.py:prepare_task's `.to(device)`) take the
+        copy-overlapped host call: the episode's frames go host->device in chunks while earlier chunks encode, and the
+        outputs come back as host tensors (plus "loss" / "acc" when the dict carries target_labels).  An optional
+        "next_images" = (context_images, target_images) of the NEXT episode (a look-ahead of one over the DataLoader) lets this
+        call copy them behind its own, so that the next call starts computing at once (spm_eval_host_set_next)."""
+        ci = inputs["context_images"]
+        if not ci.is_cuda and not self.training and self.HEAD == "clipspm":
+            c = lambda t, dt=torch.float32: t.detach().to("cpu", dt).contiguous()   # noqa: E731
+            lab = c(inputs["context_labels"]).view(-1)
+            tl = inputs.get("target_labels")
+            rt = c(inputs["real_target_labels"]).view(-1)
+            r = self.evaluate_host(c(ci), lab, c(inputs["target_images"]), c(inputs["real_support_labels"]).view(-1), rt,
+                                   torch.zeros(rt.numel(), dtype=torch.int64) if tl is None else c(tl, torch.int64).view(-1),
+                                   1, self._way(lab), next_images=inputs.get("next_images"))
+            out = {"logits": r["logits"][0].unsqueeze(0), "dists": r["dists"][0]}
+            if tl is not None:
+                out.update(loss=r["loss"][0], acc=r["acc"][0])
+            return out
         out = self.forward_episodes(inputs["context_images"], inputs["context_labels"], inputs["target_images"],
                                     inputs["real_support_labels"], inputs["real_target_labels"], n_episodes=1)
         return {"logits": out["logits"][0].unsqueeze(0), "dists": out["dists"][0]}

@@ -169,6 +169,22 @@ def test_forward_matches_reference_golden(name):
     assert torch.equal(o3["logits"], out["logits"])
 
 
+def test_forward_on_host_dict_equals_forward_on_device_dict():
+    """the drop-in call with the DataLoader's host tensors (no prepare_task `.to(device)`): same logits / dists, host outputs,
+    loss and accuracy attached"""
+    ci = H.case_inputs("vit_5w1s_t8_p1")
+    net = H.build_cuda_model(ci)
+    ep_h = {k: (v.pin_memory() if torch.is_tensor(v) and v.dtype == torch.float32 and v.dim() == 4 else v)
+            for k, v in ci["episode"].items()}
+    out_h = net(ep_h)
+    out_d = net({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in ci["episode"].items()})
+    assert not out_h["logits"].is_cuda and out_h["logits"].shape == out_d["logits"].shape
+    assert torch.allclose(out_h["logits"], out_d["logits"].cpu(), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(out_h["dists"], out_d["dists"].cpu(), atol=1e-6, rtol=1e-5)
+    loss, acc = net.evaluate({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in ci["episode"].items()})
+    assert abs(float(out_h["loss"]) - float(loss)) < 1e-5 and float(out_h["acc"]) == float(acc)
+
+
 def test_eval_host_matches_device_path():
     ci = H.case_inputs("vit_2w1s_t2_p0")
     net = H.build_cuda_model(ci)
