@@ -348,7 +348,8 @@ class CNN(nn.Module):
         245-254); leaving train mode drops the packed weights so that evaluation re-packs the trained ones."""
         was = self.training
         super().train(mode)
-        if mode and not was and getattr(self, "_dev", None) is not None and self.HEAD == "clipspm" and torch.cuda.is_available() \
+        if mode and not was and getattr(self, "_dev", None) is not None and self.HEAD in ("clipspm", "clipfsar") \
+                and torch.cuda.is_available() \
                 and getattr(self, "_train_ready", None) is not None:
             tower = bool(getattr(self, "train_backbone", False))
             if tower and self.backbone_name != "ViT-B/16":
@@ -358,7 +359,7 @@ class CNN(nn.Module):
                     continue
                 if not p.is_cuda:
                     p.data = p.data.to(self._dev, torch.float32).contiguous()
-                p.requires_grad_(n != "scale")   # `scale` is a parameter the CLIP-SPM forward never reads
+                p.requires_grad_(n != "scale" or self.HEAD == "clipfsar")   # CLIP-SPM's forward never reads `scale`
             self._train_ready = True
         if not mode and was and getattr(self, "_train_ready", False) and self._h is not None:
             torch.cuda.synchronize(self._dev)
@@ -381,7 +382,10 @@ class CNN(nn.Module):
         if getattr(self, "_tv1", None) is None:
             from .train import TransformerV1
             exact = self.precision == "fp32"
-            self._tv1 = (TransformerV1(self.mid_dim, exact=exact), TransformerV1(self.mid_dim, exact=exact))
+            if self.HEAD == "clipfsar":    # model_clipfsar.py:143-146: dim_head_k = mid_dim // 8
+                self._tv1 = (TransformerV1(self.mid_dim, dim_head=self.mid_dim // 8, exact=exact),)
+            else:
+                self._tv1 = (TransformerV1(self.mid_dim, exact=exact), TransformerV1(self.mid_dim, exact=exact))
         return self._tv1
 
     def _reset_train_pools(self):
@@ -391,25 +395,34 @@ class CNN(nn.Module):
 
     def _train_head(self, su, qu, lab, rs, rt):
         from . import train as _train
-        if self.HEAD != "clipspm":
-            raise RuntimeError("train mode is implemented for the CLIP-SPM head only")
+        if self.HEAD not in ("clipspm", "clipfsar"):
+            raise RuntimeError("train mode is implemented for the CLIP-SPM and CLIP-FSAR heads only")
         if not getattr(self, "_train_ready", False):
             raise RuntimeError("call model.train() on a CUDA machine before the train-mode forward")
         if self.text_features_train is None:
             raise RuntimeError("text_features_train is not set")          # model_clipspm.py:116-118
         text = self.text_features_train.to(self._dev, torch.float32)
         w = dict(self.named_parameters())
-        c1, c2 = self._train_blocks()
+        blocks = self._train_blocks()
         # train-mode dropout (myRes.py:961-996): one fresh 62-bit seed per forward from torch's CPU generator, so that
         # torch.manual_seed reproduces a run; `model.train_dropout = False` gives the p = 0 head the parity goldens pin
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if getattr(self, "train_dropout", True) else None
+        if self.HEAD == "clipfsar":
+            return _train.fsar_head_forward(w, text, su, qu, lab, rs, rt, blocks[0], self.transformer_depth, self.single_direct,
+                                            self.merge_before, bool(_cfg_get(self.args, "MODEL.USE_CLASSIFICATION", False)),
+                                            self.precision == "fp32", seed)
+        c1, c2 = blocks
         return _train.spm_head_forward(w, text, su, qu, lab, rs, rt, self.params, c1, c2, self.single_direct,
                                        self.precision == "fp32", seed)
 
-    def loss(self, out, target_labels):
-        """run/main_run.py:390-392 on a train-mode output (differentiable): CE / TASKS_PER_BATCH + 0.001 * dists."""
-        from .train import spm_loss
-        return spm_loss(out, target_labels.to(self._dev), self.tasks_per_batch)
+    def loss(self, out, target_labels, real_support_labels=None, real_target_labels=None):
+        """The runner's loss on a train-mode output (differentiable): CLIP-SPM run/main_run.py:390-392 CE / TASKS_PER_BATCH +
+        0.001 * dists; CLIP-FSAR :355-356 (CE + USE_CLASSIFICATION_VALUE * CE(class_logits, real labels)) / TASKS_PER_BATCH."""
+        from . import train as _train
+        if self.HEAD == "clipfsar":
+            return _train.fsar_loss(out, target_labels.to(self._dev), real_support_labels.to(self._dev).view(-1),
+                                    real_target_labels.to(self._dev).view(-1), self.tasks_per_batch, self.cls_value)
+        return _train.spm_loss(out, target_labels.to(self._dev), self.tasks_per_batch)
 
     def _way(self, labels):
         if self.way is not None:
@@ -471,12 +484,14 @@ class CNN(nn.Module):
                     qu = self.encode_frames(self._f32(target_images).view(-1, 3, 224, 224)).view(-1, T, D)
             out = self._train_head(su, qu, self._f32(context_labels).view(-1), self._f32(real_support_labels).view(-1),
                                    self._f32(real_target_labels).view(-1))
-            out = {"logits": out["logits"], "dists": out["dists"].view(1)}
+            out = dict(out)
             if target_labels is not None:
                 lg = out["logits"][0]
                 tl = target_labels.to(self._dev).long().view(-1)
-                out.update(loss=self.loss({"logits": out["logits"], "dists": out["dists"][0]}, tl).view(1),
+                out.update(loss=self.loss(out, tl, real_support_labels, real_target_labels).view(1),
                            pred=lg.argmax(-1).view(1, -1).int(), acc=(lg.argmax(-1) == tl).float().mean().view(1))
+            if "dists" in out:
+                out["dists"] = out["dists"].view(1)
             return out
         h = self._handle()
         self._text()

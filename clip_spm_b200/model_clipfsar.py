@@ -61,6 +61,8 @@ class CNN_OTAM_CLIPFSAR(CNN):
                          real_target_labels, n_episodes=1, target_labels=None):
         out = super().forward_episodes(context_images, context_labels, target_images, real_support_labels,
                                        real_target_labels, n_episodes, target_labels)
+        if self.training:     # the differentiable branch (clip_spm_b200.train.fsar_head_forward) carries its own class_logits
+            return out
         if self.text_features_train is not None:
             E = int(n_episodes)
             out["class_logits"] = self._class_logits(E, (context_labels.numel() + real_target_labels.numel()) // E)
@@ -70,6 +72,8 @@ class CNN_OTAM_CLIPFSAR(CNN):
         """models/model_clipfsar.py:183-385 (eval): {"logits": [1,Q,W], "class_logits": [1,S+Q,n_train]}"""
         out = self.forward_episodes(inputs["context_images"], inputs["context_labels"], inputs["target_images"],
                                     inputs["real_support_labels"], inputs["real_target_labels"], n_episodes=1)
+        if self.training:     # models/model_clipfsar.py:183-262: logits [1,Q,W] (+ class_logits [1,S+Q,n_train]) on the tape
+            return {k: out[k] for k in ("logits", "class_logits") if k in out}
         res = {"logits": out["logits"][0].unsqueeze(0)}
         if "class_logits" in out:
             res["class_logits"] = out["class_logits"][0].unsqueeze(0)
@@ -78,6 +82,8 @@ class CNN_OTAM_CLIPFSAR(CNN):
     def head(self, su, qu, context_labels, real_support_labels, real_target_labels, n_episodes=1):
         """models/model_clipfsar.py:325-383 on precomputed features su [E,S,T,D], qu [E,Q,T,D]."""
         out = super().head(su, qu, context_labels, real_support_labels, real_target_labels, n_episodes)
+        if self.training:
+            return out
         if self.text_features_train is not None:
             E = int(n_episodes)
             out["class_logits"] = self._class_logits(E, (context_labels.numel() + real_target_labels.numel()) // E)

@@ -19,7 +19,8 @@ import torch
 from . import _lib
 from .ops import ACT, _need_cuda, _ptr, _stream, otam_distance
 
-__all__ = ["linear", "dropout", "layer_norm", "TransformerV1", "VitBlock", "vit_forward", "spm_head_forward", "spm_loss"]
+__all__ = ["linear", "dropout", "layer_norm", "TransformerV1", "VitBlock", "vit_forward", "spm_head_forward", "spm_loss",
+           "fsar_head_forward", "fsar_loss"]
 
 
 class _Linear(torch.autograd.Function):
@@ -371,3 +372,53 @@ def spm_loss(out, target_labels, tasks_per_batch=16.0):
     lg = out["logits"][0]
     ce = -(torch.log_softmax(lg, dim=-1).gather(1, target_labels.long().view(-1, 1))).sum()
     return ce / tasks_per_batch + 0.001 * out["dists"]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sibling head CLIP-FSAR in train mode (models/model_clipfsar.py:183-262)
+# ------------------------------------------------------------------------------------------------------------------
+def _cos_sim(x, y, exact, eps=0.01):
+    """models/myRes.py:756-765 with the product on the library's GEMM (the table's rows padded to a multiple of 32)."""
+    n = y.shape[0]
+    yp = torch.nn.functional.pad(y, (0, 0, 0, (-n) % 32))
+    num = linear(x, yp, None, exact=exact)[:, :n]
+    den = x.norm(dim=-1).unsqueeze(-1) * y.norm(dim=-1).unsqueeze(0) + eps
+    return num / den
+
+
+def fsar_head_forward(w, text_train, su, qu, support_labels, real_support, real_target, context2, depth=1, single_direct=False,
+                      merge_before=False, use_classification=True, exact=False, dropout_seed=None):
+    """models/model_clipfsar.py:183-262 (the training branch: prompt rows from text_features_train :197-198) after get_feats on
+    su [S,T,D], qu [Q,T,D]: `context2` over each query's frames and over each support's frames + its prompt, class-mean
+    prototypes, OTAM; class_text_logits = cos_sim(mean_t feats, text_features_train) * scale when MODEL.USE_CLASSIFICATION."""
+    S, T, D = su.shape
+    sd = (lambda k: None) if dropout_seed is None else (lambda k: int(dropout_seed) + k)
+
+    def ctx2(x, k):
+        for i in range(depth):                                                                # myRes.py:1066-1075
+            x = context2(x, w, "context2.layers.%d." % i, sd(10 * k + i))
+        return x
+    class_logits = None
+    if use_classification:                                                                    # :187-190
+        class_logits = (_cos_sim(torch.cat([su, qu], dim=0).mean(1), text_train, exact) * w["scale"]).unsqueeze(0)
+    ctx = text_train[real_support.long()].unsqueeze(1)                                        # :197
+    qu2 = ctx2(qu, 0)                                                                         # :201
+    cm, _ = _class_mean_matrix(support_labels)
+    if merge_before:                                                                          # :203-207
+        su, ctx = _class_means(cm, su), _class_means(cm, ctx)
+    su2 = ctx2(torch.cat([su, ctx], dim=1), 1)[:, :T]                                         # :208-209
+    su_pro = su2 if merge_before else _class_means(cm, su2)                                   # :210-215
+    cum = otam_distance(su_pro.unsqueeze(0), qu2.unsqueeze(0), single_direct)[0]              # :221-237
+    out = {"logits": -cum.unsqueeze(0)}
+    if class_logits is not None:
+        out["class_logits"] = class_logits
+    return out
+
+
+def fsar_loss(out, target_labels, real_support, real_target, tasks_per_batch, cls_value):
+    """run/main_run.py:355-356: (CE(logits) + USE_CLASSIFICATION_VALUE * CE(class_logits, cat[real_support, real_target])) /
+    TASKS_PER_BATCH with utils/utils.py:174-186 `loss` (summed over the rows)."""
+    ce = -(torch.log_softmax(out["logits"][0], dim=-1).gather(1, target_labels.long().view(-1, 1))).sum()
+    real = torch.cat([real_support, real_target]).long().view(-1, 1)
+    ce_cls = -(torch.log_softmax(out["class_logits"][0], dim=-1).gather(1, real)).sum()
+    return (ce + cls_value * ce_cls) / tasks_per_batch

@@ -927,6 +927,27 @@ def train_loss_and_grads(w, text_features, inputs, cfg, tasks_per_batch=16):
     return loss.detach(), {k: v.grad.detach() for k, v in leaves.items() if v.grad is not None}
 
 
+def fsar_head_loss_and_grads(w, text_train, su, qu, support_labels, real_support, real_target, target_labels,
+                             tasks_per_batch, cls_value, single_direct=False, merge_before=False, depth=1):
+    """CLIP-FSAR's training iteration on a head-only episode (models/model_clipfsar.py:183-262 train branch with
+    MODEL.USE_CLASSIFICATION, dropout p = 0: the evaluation branch's arithmetic with the prompt rows taken from
+    text_features_train, :197-198; loss run/main_run.py:355-356), differentiated by torch autograd.  Returns (loss, grads)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in w.items()
+              if not k.startswith("backbone.") and v.dtype.is_floating_point}
+    su_, qu_ = su.detach().clone().requires_grad_(True), qu.detach().clone().requires_grad_(True)
+    st = fsar_head_forward(leaves, text_train, text_train, su_, qu_, support_labels, real_support, real_target,
+                           single_direct, merge_before, depth)
+    lg, cl = st["logits"][0], st["class_logits"][0]
+    ce = -(lg.log_softmax(-1).gather(1, target_labels.long().view(-1, 1)).squeeze(1)).sum()
+    real = torch.cat([real_support, real_target]).long()
+    ce_cls = -(cl.log_softmax(-1).gather(1, real.view(-1, 1)).squeeze(1)).sum()
+    loss = (ce + cls_value * ce_cls) / tasks_per_batch
+    loss.backward()
+    grads = {k: v.grad.detach() for k, v in leaves.items() if v.grad is not None}
+    grads["su"], grads["qu"] = su_.grad.detach(), qu_.grad.detach()
+    return loss.detach(), grads
+
+
 def grad_sample_index(numel, n=4096, seed=0):
     """fixed sample positions of a large gradient tensor stored in the goldens (the full head gradients are ~70 MB)"""
     if numel <= n:

@@ -289,6 +289,72 @@ def run_head_grad_case(m, name):
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
 
 
+# name: backbone (-> D), way, shot, queries per class, T, n train classes, SINGLE_DIRECT, options, seed
+FSAR_GRAD_CASES = {
+    "fsar_grad_5w2s_t8": ("ViT-B/16", 5, 2, 1, 8, 30, False, {}, 4201),
+    "fsar_grad_3w2s_t4_d1024_depth2": ("RN50", 3, 2, 2, 4, 12, True, dict(depth=2), 4202),
+}
+
+
+def run_fsar_grad_case(m, name):
+    """CLIP-FSAR's training iteration: the REFERENCE's CNN_OTAM_CLIPFSAR in train mode (MODEL.USE_CLASSIFICATION, dropout
+    p = 0 on the instances, prompt rows from text_features_train :197-198), frame features in place of get_feats, loss of
+    run/main_run.py:355-356, `.backward()`; the oracle's autograd must reproduce every gradient (context2.*, scale, features)."""
+    backbone, way, shot, qpc, T, ntrain, single, opt, seed = FSAR_GRAD_CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    f = import_reference_fsar(m)
+    cfg = NS(MODEL=NS(BACKBONE=backbone, USE_CLASSIFICATION=True), TRAIN=NS(CLASS_NAME=["run"]), TEST=NS(CLASS_NAME=["run"]),
+             DATA=NS(SEQ_LEN=T), DEVICE=NS(NUM_GPUS=1))
+    if single:
+        cfg.MODEL.SINGLE_DIRECT = True
+    if opt.get("depth", 1) > 1:
+        cfg.MODEL.TRANSFORMER_DEPTH = opt["depth"]
+        cfg.TRAIN.TRANSFORMER_DEPTH = opt["depth"]
+    torch.manual_seed(0)
+    net = f.CNN_OTAM_CLIPFSAR(cfg)
+    w = O.make_fsar_weights(D, seed=0, depth=opt.get("depth", 1))
+    missing, unexpected = net.load_state_dict(w, strict=False)
+    assert not unexpected and all(k.startswith("backbone.") for k in missing)
+    net.train()
+    for mod in net.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    text_train = O.make_text_features(ntrain, D, seed=1)
+    net.text_features_train, net.text_features_test = text_train, None
+    ep = O.make_episode(seed, way, shot, qpc, T, ntrain, "P1", images=False)
+    su, qu = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+    su_r, qu_r = su.clone().requires_grad_(True), qu.clone().requires_grad_(True)
+    net.get_feats = lambda *a, **k: (su_r, qu_r, None)
+    ep["context_images"], ep["target_images"] = torch.zeros(1), torch.zeros(1)
+    for mod in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    import utils.utils as U
+    out = net(ep)
+    real = torch.cat([ep["real_support_labels"], ep["real_target_labels"]], 0).long()
+    loss_ref = (U.loss(out["logits"], ep["target_labels"].long(), "cpu")
+                + FSAR_CLS_VALUE * U.loss(out["class_logits"], real, "cpu")) / FSAR_TASKS_PER_BATCH
+    loss_ref.backward()
+    ref = {k: p.grad.detach() for k, p in net.named_parameters() if not k.startswith("backbone.") and p.grad is not None}
+    ref["su"], ref["qu"] = su_r.grad.detach(), qu_r.grad.detach()
+    loss, grads = O.fsar_head_loss_and_grads(w, text_train, su, qu, ep["context_labels"], ep["real_support_labels"],
+                                             ep["real_target_labels"], ep["target_labels"], FSAR_TASKS_PER_BATCH,
+                                             FSAR_CLS_VALUE, single, **opt)
+    assert set(ref) == set(grads), sorted(set(ref) ^ set(grads))
+    worst = rel(loss.reshape(()), loss_ref.detach().reshape(()))
+    gold = {"loss": loss_ref.detach().numpy().reshape(()), "logits": out["logits"].detach().numpy(),
+            "class_logits": out["class_logits"].detach().numpy()}
+    for k, g in ref.items():
+        r = rel(grads[k].reshape(g.shape), g)
+        worst = max(worst, r)
+        assert r < 2e-4, "oracle autograd disagrees with the reference on d loss / d %s: rel err %.3e" % (k, r)
+        flat = g.reshape(-1)
+        gold["g:" + k] = flat[O.grad_sample_index(flat.numel())].numpy()
+        gold["n:" + k] = np.float64(flat.double().norm())
+    print("%-24s oracle autograd == reference autograd through CNN_OTAM_CLIPFSAR.forward (train mode, p = 0): %d gradients, "
+          "worst rel err %.2e, loss %.5f" % (name, len(ref), worst, float(loss_ref.detach())))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **gold)
+
+
 # name: backbone, way, shot, queries per class, T, n text classes, seed  (frames -> loss -> every gradient, tower included)
 TRAIN_CASES = {
     "train_vit_2w1s_t2": ("ViT-B/16", 2, 1, 1, 2, 24, 4101),
@@ -670,7 +736,7 @@ def run_softdtw_case(name):
 
 if __name__ == "__main__":
     m = import_reference()
-    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + ["fsar_dead_branches"] + list(STEN_CASES) + list(CPM2C_CASES) + list(SOFTDTW_CASES) + list(HEAD_GRAD_CASES) + list(TRAIN_CASES))
+    names = sys.argv[1:] or (list(CASES) + ["text", "otam_grad"] + list(FSAR_CASES) + ["fsar_dead_branches"] + list(STEN_CASES) + list(CPM2C_CASES) + list(SOFTDTW_CASES) + list(HEAD_GRAD_CASES) + list(TRAIN_CASES) + list(FSAR_GRAD_CASES))
     for n in names:
         if n == "text":
             run_text_case(m)
@@ -690,5 +756,7 @@ if __name__ == "__main__":
             run_head_grad_case(m, n)
         elif n in TRAIN_CASES:
             run_train_case(m, n)
+        elif n in FSAR_GRAD_CASES:
+            run_fsar_grad_case(m, n)
         else:
             run_case(m, n)

@@ -57,12 +57,15 @@ def test_oracle_autograd_matches_reference_golden(name):
 
 
 class _Block:
-    """stand-in for train.TransformerV1: the oracle's restatement of the block"""
+    """stand-in for train.TransformerV1: the oracle's restatement of ONE layer of the block"""
+
+    def __init__(self, dim_head=256):
+        self.dim_head = dim_head
 
     def __call__(self, x, w, prefix, dropout_seed=None):
         assert dropout_seed is None
-        assert prefix.endswith("layers.0.")
-        return O.transformer_v1(x, w, prefix[:-len("layers.0.")])
+        layer = {k.replace(prefix, "L.layers.0."): v for k, v in w.items() if k.startswith(prefix)}
+        return O.transformer_v1(x, layer, "L.", dim_head=self.dim_head)
 
 
 def _linear(x, W, b=None, act="none", slope=0.0, exact=False):
@@ -95,6 +98,49 @@ def test_train_head_composition_matches_oracle(name, monkeypatch):
     gold = golden(name)
     assert torch.allclose(out["logits"].detach(), gold["logits"], atol=2e-4, rtol=1e-4)
     check_against_golden(grads, loss.detach(), gold, 5e-4)
+
+
+# must match oracle/pin_against_reference.py::FSAR_GRAD_CASES (+ FSAR_TASKS_PER_BATCH, FSAR_CLS_VALUE)
+FSAR_GRAD_CASES = {
+    "fsar_grad_5w2s_t8": ("ViT-B/16", 5, 2, 1, 8, 30, False, {}, 4201),
+    "fsar_grad_3w2s_t4_d1024_depth2": ("RN50", 3, 2, 2, 4, 12, True, dict(depth=2), 4202),
+}
+FSAR_TPB, FSAR_CLS = 4, 3.0
+
+
+def fsar_grad_inputs(name):
+    backbone, way, shot, qpc, T, ntrain, single, opt, seed = FSAR_GRAD_CASES[name]
+    D = 512 if backbone == "ViT-B/16" else 1024
+    w = O.make_fsar_weights(D, seed=0, depth=opt.get("depth", 1))
+    text = O.make_text_features(ntrain, D, seed=1)
+    ep = O.make_episode(seed, way, shot, qpc, T, ntrain, "P1", images=False)
+    su, qu = O.make_features(seed, way * shot, way * qpc, T, D, ep["context_labels"], ep["target_labels"].float())
+    return dict(backbone=backbone, D=D, T=T, way=way, single=single, opt=opt, w=w, text=text, ep=ep, su=su, qu=qu)
+
+
+@pytest.mark.parametrize("name", list(FSAR_GRAD_CASES))
+def test_fsar_oracle_autograd_and_train_composition_match_reference_golden(name, monkeypatch):
+    """CLIP-FSAR's training branch: the oracle's autograd, and train.fsar_head_forward with torch stand-ins for its CUDA
+    nodes, against the gradients of the reference's own backward"""
+    from clip_spm_b200 import train
+    ci = fsar_grad_inputs(name)
+    ep, gold = ci["ep"], golden(name)
+    loss, grads = O.fsar_head_loss_and_grads(ci["w"], ci["text"], ci["su"], ci["qu"], ep["context_labels"],
+                                             ep["real_support_labels"], ep["real_target_labels"], ep["target_labels"],
+                                             FSAR_TPB, FSAR_CLS, ci["single"], **ci["opt"])
+    check_against_golden(grads, loss, gold, 2e-4)
+    monkeypatch.setattr(train, "linear", _linear)
+    monkeypatch.setattr(train, "otam_distance", _otam)
+    w = {k: v.clone().requires_grad_(True) for k, v in ci["w"].items()}
+    su, qu = ci["su"].clone().requires_grad_(True), ci["qu"].clone().requires_grad_(True)
+    out = train.fsar_head_forward(w, ci["text"], su, qu, ep["context_labels"], ep["real_support_labels"],
+                                  ep["real_target_labels"], _Block(ci["D"] // 8), ci["opt"].get("depth", 1), ci["single"])
+    loss2 = train.fsar_loss(out, ep["target_labels"], ep["real_support_labels"], ep["real_target_labels"], FSAR_TPB, FSAR_CLS)
+    loss2.backward()
+    g2 = {k: v.grad for k, v in w.items() if v.grad is not None}
+    g2["su"], g2["qu"] = su.grad, qu.grad
+    assert torch.allclose(out["class_logits"].detach(), gold["class_logits"], atol=2e-4, rtol=1e-4)
+    check_against_golden(g2, loss2.detach(), gold, 5e-4)
 
 
 def test_philox_known_answers_and_mask_statistics():

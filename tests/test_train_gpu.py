@@ -7,7 +7,8 @@ import torch.nn.functional as F
 
 from oracle import clipspm_oracle as O
 from tests.helpers import golden, make_cfg
-from tests.test_train_cpu import HEAD_GRAD_CASES, check_against_golden, head_grad_inputs
+from tests.test_train_cpu import (FSAR_CLS, FSAR_GRAD_CASES, FSAR_TPB, HEAD_GRAD_CASES, check_against_golden, fsar_grad_inputs,
+                                  head_grad_inputs)
 
 pytestmark = pytest.mark.gpu
 
@@ -300,3 +301,33 @@ def test_whole_training_backward_matches_reference_golden(precision, tol, l2):
         else:
             assert float((mine - ref).abs().max()) < tol * float(ref.abs().max()) + 1e-30, (k, float((mine - ref).abs().max()))
         assert abs(float(flat.norm()) - float(gold["n:" + k])) < tol * float(gold["n:" + k]) + 1e-30, k
+
+
+# ------------------------------------------------------------------------------------------------ sibling head CLIP-FSAR
+@pytest.mark.parametrize("name", list(FSAR_GRAD_CASES))
+@pytest.mark.parametrize("precision,tol,l2", [("fp32", 1e-3, False), ("bf16", 5e-2, True)])
+def test_fsar_train_mode_gradients_match_reference_golden(name, precision, tol, l2):
+    """CNN_OTAM_CLIPFSAR in train mode (models/model_clipfsar.py:183-262 + run/main_run.py:355-356): logits, class_logits and
+    every gradient of the reference's own backward (context2.*, scale, the features), incl. TRANSFORMER_DEPTH = 2"""
+    from clip_spm_b200 import CNN_OTAM_CLIPFSAR
+    from clip_spm_b200.config import make_cfg as mk
+    ci = fsar_grad_inputs(name)
+    ep, gold = ci["ep"], golden(name)
+    cfg = mk(ci["backbone"], ci["T"], ci["single"], ci["way"], params={}, tasks_per_batch=FSAR_TPB, cls_value=FSAR_CLS)
+    cfg.MODEL.USE_CLASSIFICATION = True
+    if ci["opt"].get("depth", 1) > 1:
+        cfg.MODEL.TRANSFORMER_DEPTH = ci["opt"]["depth"]
+        cfg.TRAIN.TRANSFORMER_DEPTH = ci["opt"]["depth"]
+    net = CNN_OTAM_CLIPFSAR(cfg, text_features_test=ci["text"], text_features_train=ci["text"], precision=precision)
+    net.load_state_dict(ci["w"], strict=False)
+    net.train_dropout = False
+    net.train()
+    su, qu = ci["su"].cuda().requires_grad_(True), ci["qu"].cuda().requires_grad_(True)
+    out = net.head(su.unsqueeze(0), qu.unsqueeze(0), ep["context_labels"], ep["real_support_labels"], ep["real_target_labels"])
+    loss = net.loss(out, ep["target_labels"], ep["real_support_labels"], ep["real_target_labels"])
+    loss.backward()
+    grads = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    grads["su"], grads["qu"] = su.grad, qu.grad
+    assert torch.allclose(out["class_logits"].detach().cpu(), gold["class_logits"], atol=10 * tol, rtol=tol)
+    assert torch.allclose(out["logits"].detach().cpu(), gold["logits"], atol=tol, rtol=tol)
+    check_against_golden(grads, loss.detach().cpu(), gold, tol, l2=l2)
