@@ -20,7 +20,7 @@ from . import _lib
 from .ops import ACT, _need_cuda, _ptr, _stream, otam_distance
 
 __all__ = ["linear", "dropout", "layer_norm", "TransformerV1", "VitBlock", "vit_forward", "spm_head_forward", "spm_loss",
-           "fsar_head_forward", "fsar_loss"]
+           "fsar_head_forward", "fsar_loss", "shard_tasks", "allreduce_gradients"]
 
 
 class _Linear(torch.autograd.Function):
@@ -422,3 +422,44 @@ def fsar_loss(out, target_labels, real_support, real_target, tasks_per_batch, cl
     real = torch.cat([real_support, real_target]).long().view(-1, 1)
     ce_cls = -(torch.log_softmax(out["class_logits"][0], dim=-1).gather(1, real)).sum()
     return (ce + cls_value * ce_cls) / tasks_per_batch
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# several GPUs: the TASKS_PER_BATCH tasks of one optimiser step are split over the ranks
+# ------------------------------------------------------------------------------------------------------------------
+def shard_tasks(tasks_per_batch, rank, world):
+    """Which of the TASKS_PER_BATCH tasks between two optimiser steps (run/main_run.py:203-209: gradients accumulate over
+    them, the loss already carries the 1 / TASKS_PER_BATCH) this rank runs: a contiguous, balanced range."""
+    lo = (tasks_per_batch * rank) // world
+    hi = (tasks_per_batch * (rank + 1)) // world
+    return range(lo, hi)
+
+
+def allreduce_gradients(params, group=None, bucket_numel=1 << 24):
+    """The training step's one exchange: SUM of the accumulated gradients over the ranks (NCCL all-reduce through
+    torch.distributed, before `scaler.step`), in buckets of `bucket_numel` floats, so that every rank then takes the optimiser
+    step one process would have taken on all TASKS_PER_BATCH tasks.  The reference's own multi-GPU form is DataParallel over
+    the backbone (models/model_clipspm.py:103-109: frames of ONE task split over the GPUs); tasks are independent, so here
+    the task batch is split instead and the exchange is one all-reduce per step.  A parameter must have a gradient on
+    every rank or on none.  The scaled gradients are reduced as they are: inf / nan propagate to every rank, so all ranks
+    skip the same steps."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    i = 0
+    while i < len(grads):
+        j, n = i, 0
+        while j < len(grads) and (n == 0 or n + grads[j].numel() <= bucket_numel):
+            n += grads[j].numel()
+            j += 1
+        if j == i + 1:
+            dist.all_reduce(grads[i], op=dist.ReduceOp.SUM, group=group)
+        else:
+            flat = torch.cat([g.reshape(-1) for g in grads[i:j]])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            o = 0
+            for g in grads[i:j]:
+                g.copy_(flat[o:o + g.numel()].view_as(g))
+                o += g.numel()
+        i = j

@@ -54,3 +54,15 @@ def test_two_rank_nccl_sweep_equals_unsharded():
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{") and "check_sharding" in l]
     assert lines and lines[0]["check_sharding"] == "ok" and lines[0]["predictions_equal"]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL)")
+def test_two_rank_nccl_training_equals_single_process():
+    """tasks of an optimiser step split over 2 ranks + one gradient all-reduce == the same steps by one process"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29641", os.path.join(ROOT, "tools", "run_train.py"), "--steps", "2",
+           "--tasks-per-batch", "4", "--seq-len", "2", "--way", "2", "--check"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{") and "check" in l]
+    assert lines and lines[0]["check"] == "ok", lines

@@ -143,6 +143,40 @@ def test_fsar_oracle_autograd_and_train_composition_match_reference_golden(name,
     check_against_golden(g2, loss2.detach(), gold, 5e-4)
 
 
+def _dp_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    from clip_spm_b200 import train
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    params = [torch.zeros(s, requires_grad=True) for s in [(5,), (300, 7), (3, 4, 5), (1,), (70000,)]]
+    task_grads = [[torch.randn(p.shape, generator=g) for p in params] for _ in range(6)]    # the same on every rank
+    for t in train.shard_tasks(6, rank, world):
+        for p, tg in zip(params, task_grads[t]):
+            p.grad = tg.clone() if p.grad is None else p.grad + tg
+    train.allreduce_gradients(params, bucket_numel=4096)
+    want = [sum(task_grads[t][i] for t in range(6)) for i in range(len(params))]
+    out[rank] = max(float((p.grad - w).abs().max()) for p, w in zip(params, want))
+    dist.destroy_process_group()
+
+
+def test_task_sharded_gradients_equal_single_process_accumulation():
+    """world_size 2 over gloo (the GPU path is the same code over NCCL): tasks split over the ranks + one bucketed
+    all-reduce(SUM) == the gradients one process accumulates over all TASKS_PER_BATCH tasks"""
+    import socket
+    import torch.multiprocessing as mp
+    from clip_spm_b200 import train
+    assert [list(train.shard_tasks(16, r, 3)) for r in range(3)] == [list(range(0, 5)), list(range(5, 10)), list(range(10, 16))]
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = mp.Manager().dict()
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert len(out) == 2 and max(out.values()) < 1e-5, dict(out)
+
+
 def test_philox_known_answers_and_mask_statistics():
     """oracle.philox4x32_10 against the Random123 known-answer vectors of Philox4x32-10; the keep rate of dropout_mask"""
     kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
