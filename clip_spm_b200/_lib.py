@@ -105,6 +105,7 @@ SIGNATURES = {
     "spm_text_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "spm_text_class_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "spm_transform_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "spm_transform_frames_train": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "spm_frame_geometry": (c_int, [c_int, c_int] + [ctypes.POINTER(c_int)] * 4),
     "spm_encode_frames_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "spm_eval_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int] + [c_void_p] * 6 + [c_float]

@@ -30,8 +30,9 @@ struct Taps {          // per cropped output coordinate: first input coordinate,
   int ksize = 1;
 };
 
-// Resample.c precompute_coeffs + normalize_coeffs_8bpc (bilinear filter, support 1) for outputs [first, first+CROP)
-void bilinear_taps(int in_size, int out_size, int first, Taps* t) {
+// Resample.c precompute_coeffs + normalize_coeffs_8bpc (bilinear filter, support 1) for outputs [first, first+count)
+void bilinear_taps(int in_size, int out_size, int first, Taps* t, int count = CROP) {
+  const int CROP = count;   // (the evaluation transform needs the crop window only; the training transform the whole extent)
   t->mn.assign(CROP, 0);
   t->cnt.assign(CROP, 1);
   if (in_size == out_size) {  // the pass is skipped by Pillow: identity taps give the same bytes
@@ -99,10 +100,12 @@ int geometry(int H, int W, Geometry* g) {
 struct DevTables {
   int *hmin, *hcnt, *hk, *vmin, *vcnt, *vk;
   int hks, vks, max_rows;
+  int ow, oh;   // full-extent tables (training transform): the resized size the tables cover; 0 for crop-window tables
 };
 
 std::mutex g_mu;
 std::map<std::pair<int, int>, DevTables> g_tables;
+std::map<std::pair<int, int>, DevTables> g_tables_full;
 
 int upload(const std::vector<int>& v, int** dst) {
   SPM_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), v.size() * sizeof(int)));
@@ -145,25 +148,71 @@ int get_tables(int H, int W, DevTables* out) {
   return 0;
 }
 
+// Tables over the WHOLE resized frame: the training transform crops at a per-clip random origin (and may mirror the clip), so
+// the taps of any 224-wide window must be at hand
+int get_tables_full(int H, int W, DevTables* out) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_tables_full.find({H, W});
+  if (it != g_tables_full.end()) { *out = it->second; return 0; }
+  Geometry g;
+  SPM_TRY(geometry(H, W, &g));
+  Taps th, tv;
+  bilinear_taps(W, g.ow, 0, &th, g.ow);
+  bilinear_taps(H, g.oh, 0, &tv, g.oh);
+  DevTables d{};
+  d.hks = th.ksize; d.vks = tv.ksize; d.ow = g.ow; d.oh = g.oh;
+  d.max_rows = 0;
+  for (int y0 = 0; y0 < g.oh; ++y0) {      // a 32-row output tile may start at any row
+    const int y1 = std::min(g.oh, y0 + TILE) - 1;
+    d.max_rows = std::max(d.max_rows, tv.mn[y1] + tv.cnt[y1] - tv.mn[y0]);
+  }
+  if ((size_t)d.max_rows * TILE * 4 > 200 * 1024) {
+    set_error("frame transform: down-scaling factor too large for the shared-memory tile");
+    return 1;
+  }
+  if (g_tables_full.size() >= 256) {
+    SPM_CUDA(cudaDeviceSynchronize());
+    for (auto& kv : g_tables_full) {
+      cudaFree(kv.second.hmin); cudaFree(kv.second.hcnt); cudaFree(kv.second.hk);
+      cudaFree(kv.second.vmin); cudaFree(kv.second.vcnt); cudaFree(kv.second.vk);
+    }
+    g_tables_full.clear();
+  }
+  SPM_TRY(upload(th.mn, &d.hmin)); SPM_TRY(upload(th.cnt, &d.hcnt)); SPM_TRY(upload(th.k, &d.hk));
+  SPM_TRY(upload(tv.mn, &d.vmin)); SPM_TRY(upload(tv.cnt, &d.vcnt)); SPM_TRY(upload(tv.k, &d.vk));
+  g_tables_full[{H, W}] = d;
+  *out = d;
+  return 0;
+}
+
 __device__ __forceinline__ int clip8(int acc) { return min(max(acc >> PBITS, 0), 255); }
 
 // MODE 0: fp32 [F,3,224,224]; MODE 1: bf16 ViT patch rows [F*196, 768]
-template <int MODE>
+// AUG (training transform, video_reader.py:97-103: Resize -> RandomHorizontalFlip -> RandomCrop): the tables cover the whole
+// resized frame and aug[f] = {crop y1, crop x1, flip} picks the window (and mirrors it) per frame
+template <int MODE, bool AUG = false>
 __global__ void __launch_bounds__(256)
 frame_transform_kernel(const uint8_t* __restrict__ frames, int H, int W, DevTables t, float* __restrict__ out_f32,
-                       __nv_bfloat16* __restrict__ out_patch) {
+                       __nv_bfloat16* __restrict__ out_patch, const int* __restrict__ aug = nullptr) {
   extern __shared__ uint32_t hbuf[];  // [rows][TILE] packed R | G<<8 | B<<16 after the horizontal pass
   const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * TILE;
   const long long f = blockIdx.z;
   const uint8_t* src = frames + f * (long long)H * W * 3;
-  const int rlo = __ldg(t.vmin + y0);
+  int oy = 0, ox = 0, flip = 0;     // table index of output (y, x): row oy + y, column ox + x (mirrored: ow - 1 - (ox + x))
+  if (AUG) {
+    oy = min(max(__ldg(aug + 3 * f), 0), t.oh - CROP);
+    ox = min(max(__ldg(aug + 3 * f + 1), 0), t.ow - CROP);
+    flip = __ldg(aug + 3 * f + 2) != 0;
+  }
+  const int rlo = __ldg(t.vmin + oy + y0);
   const int ylast = min(CROP, y0 + TILE) - 1;
-  const int nrows = __ldg(t.vmin + ylast) + __ldg(t.vcnt + ylast) - rlo;
+  const int nrows = __ldg(t.vmin + oy + ylast) + __ldg(t.vcnt + oy + ylast) - rlo;
   // (A) horizontal pass of the needed input rows for the tile's 32 columns (a warp = one row: contiguous bytes)
   {
     const int col = threadIdx.x & 31;
-    const int mn = __ldg(t.hmin + x0 + col), cnt = __ldg(t.hcnt + x0 + col);
-    const int* kp = t.hk + (x0 + col) * t.hks;
+    const int tx = AUG ? (flip ? t.ow - 1 - (ox + x0 + col) : ox + x0 + col) : x0 + col;
+    const int mn = __ldg(t.hmin + tx), cnt = __ldg(t.hcnt + tx);
+    const int* kp = t.hk + tx * t.hks;
     for (int r = threadIdx.x >> 5; r < nrows; r += 8) {
       const uint8_t* p = src + ((long long)(rlo + r) * W + mn) * 3;
       int a0 = 1 << (PBITS - 1), a1 = a0, a2 = a0;
@@ -181,8 +230,8 @@ frame_transform_kernel(const uint8_t* __restrict__ frames, int H, int W, DevTabl
     const int xg = item % GROUPS, c = (item / GROUPS) % 3, ry = item / (GROUPS * 3);
     const int y = y0 + ry;
     if (y >= CROP) break;
-    const int r0 = __ldg(t.vmin + y) - rlo, cnt = __ldg(t.vcnt + y);
-    const int* kp = t.vk + y * t.vks;
+    const int r0 = __ldg(t.vmin + oy + y) - rlo, cnt = __ldg(t.vcnt + oy + y);
+    const int* kp = t.vk + (oy + y) * t.vks;
     int acc[PIX];
 #pragma unroll
     for (int i = 0; i < PIX; ++i) acc[i] = 1 << (PBITS - 1);
@@ -239,9 +288,39 @@ int k_frame_transform(cudaStream_t st, const uint8_t* frames, int n_frames, int 
   }
   return 0;
 }
+// training transform: frames [F,H,W,3] uint8, aug [F,3] int32 {y1, x1, flip} (device) -> out_f32 [F,3,224,224]
+int k_frame_transform_train(cudaStream_t st, const uint8_t* frames, int n_frames, int H, int W, const int* aug, float* out_f32) {
+  if (n_frames <= 0) return 0;
+  if (H < 1 || W < 1 || (long long)H * W > (1LL << 26)) { set_error("frame transform: bad frame size"); return 1; }
+  DevTables t;
+  SPM_TRY(get_tables_full(H, W, &t));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPM_CUDA(cudaFuncSetAttribute(frame_transform_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)t.max_rows * TILE * 4;
+  for (int f0 = 0; f0 < n_frames; f0 += 65535) {
+    const int nf = std::min(65535, n_frames - f0);
+    const dim3 grid(CROP / TILE, CROP / TILE, nf);
+    frame_transform_kernel<0, true><<<grid, 256, smem, st>>>(frames + (long long)f0 * H * W * 3, H, W, t,
+                                                             out_f32 + (long long)f0 * 3 * CROP * CROP, nullptr, aug + 3LL * f0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(std::string("frame transform launch: ") + cudaGetErrorString(e)); return 1; }
+    count_launch();
+  }
+  return 0;
+}
 }  // namespace spm
 
 extern "C" {
+
+int spm_transform_frames_train(void* stream, const uint8_t* frames, int n_frames, int H, int W, const int32_t* aug,
+                               float* images_out) {
+  if (n_frames <= 0) return 0;
+  SPM_CHECK(frames && aug && images_out, "spm_transform_frames_train: null argument");
+  return spm::k_frame_transform_train((cudaStream_t)stream, frames, n_frames, H, W, aug, images_out);
+}
 
 int spm_frame_geometry(int H, int W, int* resized_h, int* resized_w, int* crop_y, int* crop_x) {
   spm::Geometry g;

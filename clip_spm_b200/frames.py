@@ -2,7 +2,7 @@
 and the GPU frame transform that replaces the PIL Resize/CenterCrop/ToTensor chain of the data loader."""
 import numpy as np
 
-from .ops import frame_geometry, transform_frames  # noqa: F401  (re-exported)
+from .ops import frame_geometry, transform_frames, transform_frames_train  # noqa: F401  (re-exported)
 
 
 def eval_frame_indices(n_frames, seq_len):
@@ -37,6 +37,17 @@ def train_frame_indices(n_frames, seq_len, rng):
     return idxs
 
 
+def train_augmentation(rng, frame_h, frame_w, flip=True):
+    """The random draws of the loader's TRAINING transform for one clip, in the reference's order (video_reader.py:97-103 ->
+    videotransforms/video_transforms.py:46 RandomHorizontalFlip, absent for ssv2; :152-153 RandomCrop on the resized clip):
+    -> (crop y1, crop x1, flip), the `aug` row of ops.transform_frames_train."""
+    oh, ow, _, _ = frame_geometry(frame_h, frame_w)
+    fl = bool(rng.random() < 0.5) if flip else False
+    x1 = rng.randint(0, ow - 224)
+    y1 = rng.randint(0, oh - 224)
+    return y1, x1, fl
+
+
 class Split:
     """The listing the sampler draws from (video_reader.py:14-50 `Split`): videos[i] = list of frame paths (or any
     per-frame handles), gt_a_list[i] = its class id."""
@@ -55,13 +66,17 @@ class Split:
         return list(set(self.gt_a_list))
 
 
-def sample_episode_plan(split, way, shot, n_queries, seq_len, train=False, rng=None):
+def sample_episode_plan(split, way, shot, n_queries, seq_len, train=False, rng=None, frame_size=None, flip=True):
     """The episode a `VideoDataset.__getitem__` call builds (video_reader.py:275-329), as a PLAN: which frames of which
     videos form the support / target sets, in the order the reference stacks them, plus the four label lists --
     everything but the pixel work (decode + Resize/CenterCrop/ToTensor), which `CNN.evaluate_host_u8` does on the GPU.
     `rng` is a `random.Random` (default: the global `random` module, the reference's own source); the draws are made in
     the reference's order (classes; per class the videos; per video the frame jitter when training; the two shuffles),
     so the same seed yields the same episode.
+    Training with the loader's real transform: pass frame_size = (H, W) of the decoded frames (or a callable video_index ->
+    (H, W)); the per-clip draws of RandomHorizontalFlip / RandomCrop (flip=False for ssv2, video_reader.py:95-100) are then
+    made where the reference makes them -- right after the clip's frame jitter -- and every entry becomes
+    (video_index, [frame indices], (crop y1, crop x1, flip)).
     Returns dict(support=[(video_index, [frame indices])...], target=[...], support_labels, target_labels,
     real_support_labels, real_target_labels, batch_class_list)."""
     import random as _random
@@ -76,7 +91,11 @@ def sample_episode_plan(split, way, shot, n_queries, seq_len, train=False, rng=N
             v = vids[idx]
             n = len(split.videos[v])
             fr = train_frame_indices(n, seq_len, rng) if train else eval_frame_indices(n, seq_len)
-            (support if k < shot else target).append(((v, fr), bl, bc))
+            entry = (v, fr)
+            if train and frame_size is not None:
+                fh, fw = frame_size(v) if callable(frame_size) else frame_size
+                entry = (v, fr, train_augmentation(rng, fh, fw, flip))
+            (support if k < shot else target).append((entry, bl, bc))
     rng.shuffle(support)
     rng.shuffle(target)
     return dict(support=[s[0] for s in support], target=[t[0] for t in target],

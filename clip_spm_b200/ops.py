@@ -127,6 +127,28 @@ def transform_frames(frames):
     return out
 
 
+def transform_frames_train(frames, aug):
+    """The loader's TRAINING transform (video_reader.py:83-103: Resize(256) -> RandomHorizontalFlip -> RandomCrop(224) ->
+    ToTensor), bit-exact given the draws: frames uint8 [F, H, W, 3], aug = per frame (crop y1, crop x1, flip) -- an
+    [F, 3] int tensor / list, or ONE triple for the whole clip (frames.train_augmentation draws it the reference's way)."""
+    lib = _lib.load()
+    _need_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+    frames = frames.contiguous()
+    F, H, W, _ = frames.shape
+    a = torch.as_tensor(aug, dtype=torch.int32).reshape(-1, 3)
+    if a.shape[0] == 1:
+        a = a.expand(F, 3)
+    oh, ow, _, _ = frame_geometry(H, W)
+    if a.shape[0] != F or int(a[:, 0].min()) < 0 or int(a[:, 1].min()) < 0 or int(a[:, 0].max()) > oh - 224 or \
+            int(a[:, 1].max()) > ow - 224:
+        raise RuntimeError("transform_frames_train: one (y1, x1, flip) per frame with 0 <= y1 <= %d, 0 <= x1 <= %d" % (oh - 224, ow - 224))
+    a = a.contiguous().to(frames.device)
+    out = torch.empty(F, 3, 224, 224, device=frames.device)
+    _lib.check(lib.spm_transform_frames_train(_stream(), _ptr(frames), F, H, W, _ptr(a), _ptr(out)))
+    return out
+
+
 def jpeg_info(data):
     """Header of one JPEG file (bytes): (height, width, luma h sampling, luma v sampling)."""
     lib = _lib.load()

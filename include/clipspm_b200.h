@@ -319,6 +319,13 @@ int spm_text_class_features(spm_text* h, void* stream, const int32_t* tokens, in
  * [video_transforms.py:204-247] -> ToTensor [uint8 HWC -> fp32 CHW / 255], bit-exact.
  * frames: device uint8 [n_frames, H, W, 3] (decoded RGB, all of one size) -> images_out fp32 [n_frames, 3, 224, 224] */
 int spm_transform_frames(void* stream, const uint8_t* frames, int n_frames, int H, int W, float* images_out);
+/* The TRAINING transform of the loader (video_reader.py:83-103: Resize(256) -> RandomHorizontalFlip [not for ssv2] ->
+ * RandomCrop(224) -> ToTensor), bit-exact given the clip's random draws: aug = device int32 [n_frames, 3] {crop y1, crop x1,
+ * flip} per frame in the coordinates of the RESIZED (and, when flip != 0, already mirrored) frame -- the numbers
+ * videotransforms/video_transforms.py:152-153 draws (clip_spm_b200.frames.train_augmentation mirrors the draws and their
+ * order); origins are clamped to the resized frame. */
+int spm_transform_frames_train(void* stream, const uint8_t* frames, int n_frames, int H, int W, const int32_t* aug,
+                               float* images_out);
 /* spm_encode_frames on decoded frames: transform + encoder (on the bf16 ViT path the transform kernel writes the
  * patch-embedding GEMM's bf16 operand directly; the fp32 image is never materialised) */
 int spm_encode_frames_u8(spm_handle* h, void* stream, const uint8_t* frames, int n_frames, int H, int W,

@@ -123,6 +123,33 @@ def preprocess_frames(frames):
     return out
 
 
+def train_augmentation(rng, oh, ow, flip=True):
+    """The draws the TRAINING transform makes per clip, in its order (video_reader.py:97-103): RandomHorizontalFlip
+    (video_transforms.py:46: `random.random() < 0.5`; absent for ssv2) then RandomCrop (:152-153: x1 = randint(0, w - 224),
+    y1 = randint(0, h - 224)) on the resized clip of oh x ow.  rng: a random.Random or the random module.  -> (y1, x1, flip)"""
+    fl = bool(rng.random() < 0.5) if flip else False
+    x1 = rng.randint(0, ow - CROP)
+    y1 = rng.randint(0, oh - CROP)
+    return y1, x1, fl
+
+
+def preprocess_frames_train(frames, y1, x1, flip):
+    """Resize(256) -> [mirror] -> crop at (y1, x1) -> ToTensor: frames uint8 [F, H, W, 3] of ONE clip -> float32 [F,3,224,224]"""
+    frames = np.asarray(frames)
+    F, H, W, _ = frames.shape
+    oh, ow, _, _ = geometry(H, W)
+    out = np.empty((F, 3, CROP, CROP), np.float32)
+    for f in range(F):
+        img = frames[f]
+        if (oh, ow) != (H, W):
+            img = pil_resize_bilinear(img, oh, ow)
+        if flip:
+            img = img[:, ::-1]
+        img = img[y1:y1 + CROP, x1:x1 + CROP]
+        out[f] = img.transpose(2, 0, 1).astype(np.float32) / np.float32(255)
+    return out
+
+
 def eval_frame_indices(n_frames, seq_len):
     """video_reader.py:231-260, evaluation branch: which of a video's n_frames are read"""
     if n_frames == seq_len:

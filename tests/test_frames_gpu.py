@@ -127,3 +127,43 @@ def test_listing_sweep_matches_per_episode_forward():
     assert res["n"] == n_ep
     assert abs(res["accuracy"] - 100.0 * sum(accs) / n_ep) < 1e-4
     assert abs(res["loss"] - sum(losses) / n_ep) < 2e-3 * max(1.0, abs(sum(losses) / n_ep))
+
+
+def test_training_transform_bit_exact_against_oracle():
+    """ops.transform_frames_train (Resize -> mirror -> crop at the clip's random origin -> ToTensor) against the numpy
+    restatement that is pinned on the reference's own train-mode __getitem__ pixels; per-frame origins, every flip state,
+    corner origins, and geometries with real resampling"""
+    import random
+    from clip_spm_b200.ops import frame_geometry, transform_frames_train
+    rng = random.Random(5)
+    for name in ("k100_340x256", "up_320x240", "down_1280x720", "portrait_360x480", "odd_427x241", "square_256"):
+        frames = P.make_frames(name)
+        F, Hh, Ww = frames.shape[:3]
+        oh, ow, _, _ = frame_geometry(Hh, Ww)
+        augs = [(0, 0, False), (oh - 224, ow - 224, True), (0, ow - 224, True), (rng.randint(0, oh - 224), rng.randint(0, ow - 224), False),
+                (rng.randint(0, oh - 224), rng.randint(0, ow - 224), True)]
+        for y1, x1, fl in augs:
+            ref = P.preprocess_frames_train(frames, y1, x1, fl)
+            out = transform_frames_train(torch.from_numpy(frames).cuda(), (y1, x1, int(fl))).cpu().numpy()
+            assert (out != ref).sum() == 0, (name, y1, x1, fl, int((out != ref).sum()))
+    # one row per frame: two frames of a clip with different draws in ONE call
+    frames = P.make_frames("k100_340x256")
+    out = transform_frames_train(torch.from_numpy(frames).cuda(), [[3, 77, 1], [30, 5, 0]]).cpu().numpy()
+    assert np.array_equal(out[0], P.preprocess_frames_train(frames[:1], 3, 77, True)[0])
+    assert np.array_equal(out[1], P.preprocess_frames_train(frames[1:], 30, 5, False)[0])
+    with pytest.raises(RuntimeError):
+        transform_frames_train(torch.from_numpy(frames).cuda(), (40, 0, 0))      # 256 - 224 = 32 is the largest y origin
+
+
+def test_training_episode_from_plan_matches_reference_golden():
+    """a whole train-mode episode: plan (frames + draws) -> GPU training transform == the pixels the reference's loader produced"""
+    import hashlib
+    from clip_spm_b200.ops import transform_frames_train
+    from tests.test_frames_cpu import AUG_CASES, aug_case, standin_frame
+    for name in AUG_CASES:
+        plan, sp, g, fh, fw = aug_case(name)
+        for key, items in (("support_set", plan["support"]), ("target_set", plan["target"])):
+            frames = np.stack([standin_frame(sp.videos[v][f], fh, fw) for v, fr, _ in items for f in fr])
+            aug = [[a[0], a[1], int(a[2])] for _, fr, a in items for _f in fr]
+            px = transform_frames_train(torch.from_numpy(frames).cuda(), aug).cpu().numpy()
+            assert hashlib.sha256(np.ascontiguousarray(px).tobytes()).digest() == g[key + "_sha256"].tobytes(), (name, key)
