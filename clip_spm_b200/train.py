@@ -20,7 +20,7 @@ from . import _lib
 from .ops import ACT, _need_cuda, _ptr, _stream, otam_distance
 
 __all__ = ["linear", "dropout", "layer_norm", "TransformerV1", "VitBlock", "vit_forward", "spm_head_forward", "spm_loss",
-           "fsar_head_forward", "fsar_loss", "shard_tasks", "allreduce_gradients"]
+           "fsar_head_forward", "fsar_loss", "shard_tasks", "allreduce_gradients", "run_listing_training"]
 
 
 class _Linear(torch.autograd.Function):
@@ -463,3 +463,65 @@ def allreduce_gradients(params, group=None, bucket_numel=1 << 24):
                 g.copy_(flat[o:o + g.numel()].view_as(g))
                 o += g.numel()
         i = j
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the training loop from a listing of decoded frames (run/main_run.py:180-243 `Learner.run`, training branch)
+# ------------------------------------------------------------------------------------------------------------------
+def run_listing_training(net, split, load_frame, iterations, way, shot, n_queries, optimizer, scaler, seed=0, flip=True,
+                         lr_milestone=None, rank=0, world_size=1, on_iteration=None):
+    """`Learner.run`'s training branch over `VideoDataset` episodes on this library, from DECODED frames:
+    per iteration (numbered from 1 like the reference's `iteration`) one train-mode episode is sampled
+    (`frames.sample_episode_plan(train=True)`: class / video / frame-jitter draws AND the draws of the loader's training
+    transform, rng seeded `seed + iteration` so that any split over ranks sees the same episodes), its frames come from
+    `load_frame(handle) -> uint8 [H, W, 3]` (one size per run), Resize -> RandomHorizontalFlip -> RandomCrop -> ToTensor run on
+    the GPU (`ops.transform_frames_train`, bit-exact with the loader's PIL chain), then `train_task` (:245-254):
+    `net(inputs)` in train mode, `net.loss`, `scaler.scale(loss).backward()`; the optimiser steps when
+    `(iteration + 1) % TASKS_PER_BATCH == 0` or on the last iteration (:203-209, the reference's own off-by-one), and
+    `lr_scheduler.MultiStepLR(milestones=[lr_milestone], gamma=0.1).step()` follows every iteration (:99,210).
+    world_size > 1: iteration i is computed by rank i % world_size, the gradients are exchanged once per optimiser step
+    (`allreduce_gradients`).  `net` must be in train mode; `on_iteration(iteration, loss, acc)` is the logging / validation hook.
+    Returns [(loss, accuracy)] of the iterations this rank computed (host floats: the reference logs both every iteration)."""
+    import random
+
+    from . import frames as F
+    from . import ops
+    if not net.training:
+        raise RuntimeError("run_listing_training: call net.train() first")
+    T, tpb = net.seq_len, int(net.tasks_per_batch)
+    params = net.trainable_parameters()
+    base_lr = optimizer.param_groups[0]["lr"]
+    dev = net._dev
+    log, size = [], None
+    for iteration in range(1, int(iterations) + 1):
+        if iteration % world_size == rank:
+            rng = random.Random(seed + iteration)
+            if size is None:
+                size = tuple(int(v) for v in torch.as_tensor(load_frame(split.videos[0][0])).shape[:2])
+            plan = F.sample_episode_plan(split, way, shot, n_queries, T, train=True, rng=rng, frame_size=size, flip=flip)
+
+            def clip_images(items):
+                fr = torch.stack([torch.as_tensor(load_frame(split.videos[v][f])) for v, idx, _ in items for f in idx])
+                aug = [[a[0], a[1], int(a[2])] for _, idx, a in items for _f in idx]
+                return ops.transform_frames_train(fr.to(dev, non_blocking=True), aug)
+            tl = torch.tensor([int(x) for x in plan["target_labels"]], dtype=torch.int64, device=dev)
+            inputs = {"context_images": clip_images(plan["support"]), "target_images": clip_images(plan["target"]),
+                      "context_labels": torch.tensor(plan["support_labels"], device=dev),
+                      "real_support_labels": torch.tensor(plan["real_support_labels"], device=dev),
+                      "real_target_labels": torch.tensor(plan["real_target_labels"], device=dev), "target_labels": tl}
+            out = net(inputs)
+            loss = net.loss(out, tl, inputs["real_support_labels"], inputs["real_target_labels"])
+            scaler.scale(loss).backward()
+            acc = (out["logits"][0].argmax(-1) == tl).float().mean()
+            log.append((float(loss.detach()), float(acc)))          # run/main_run.py:199-201 keeps both as host numbers
+            if on_iteration is not None:
+                on_iteration(iteration, log[-1][0], log[-1][1])
+        if (iteration + 1) % tpb == 0 or iteration == int(iterations):
+            if world_size > 1:
+                allreduce_gradients(params)
+            scaler.step(optimizer)
+            scaler.update()
+            optimizer.zero_grad()
+        if lr_milestone is not None:                                 # MultiStepLR, stepped once per iteration
+            optimizer.param_groups[0]["lr"] = base_lr * (0.1 if iteration >= int(lr_milestone) else 1.0)
+    return log

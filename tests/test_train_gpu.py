@@ -331,3 +331,37 @@ def test_fsar_train_mode_gradients_match_reference_golden(name, precision, tol, 
     assert torch.allclose(out["class_logits"].detach().cpu(), gold["class_logits"], atol=10 * tol, rtol=tol)
     assert torch.allclose(out["logits"].detach().cpu(), gold["logits"], atol=tol, rtol=tol)
     check_against_golden(grads, loss.detach().cpu(), gold, tol, l2=l2)
+
+
+def test_training_loop_from_a_listing_of_decoded_frames():
+    """run/main_run.py:180-243: episodes sampled the loader's way (incl. the training transform's draws), frames transformed on
+    the GPU, train_task, optimiser steps on the reference's schedule, MultiStepLR; deterministic under torch.manual_seed"""
+    import numpy as np
+    from clip_spm_b200 import CNN, optim, train
+    from clip_spm_b200 import frames as Fr
+    sp = Fr.Split()
+    for vid in range(3):
+        for cls in range(3):
+            sp.add_vid([(cls, vid, f) for f in range(6 + vid)], cls)
+    load = lambda h: np.random.RandomState(h[0] * 10007 + h[1] * 101 + h[2]).randint(0, 256, size=(256, 288, 3)).astype(np.uint8)  # noqa: E731
+    text = O.make_text_features(24, 512, seed=1)
+
+    def run():
+        torch.manual_seed(3)
+        net = CNN(make_cfg("ViT-B/16", 2, False, 2, ), text_features_test=text, text_features_train=text)
+        net.tasks_per_batch = 2.0
+        net.load_state_dict(O.make_weights("ViT-B/16", seed=0, protocol="P1"), strict=False)
+        net.train_backbone = True
+        net.train()
+        opt = optim.Adam(net.trainable_parameters(), lr=1e-5, betas=(0.5, 0.999))
+        steps = []
+        log = train.run_listing_training(net, sp, load, 5, 2, 1, 1, opt, optim.GradScaler("cuda", init_scale=64.0), seed=7,
+                                         lr_milestone=4, on_iteration=lambda i, l, a: steps.append(i))
+        return log, steps, opt.param_groups[0]["lr"], net.get_parameter("backbone.conv1.weight").detach().clone()
+    log1, steps, lr, w1 = run()
+    log2, _, _, w2 = run()
+    assert steps == [1, 2, 3, 4, 5] and len(log1) == 5 and all(np.isfinite(l) and 0.0 <= a <= 1.0 for l, a in log1)
+    assert log1 == log2 and torch.equal(w1, w2)                   # same seeds -> same episodes, same dropout masks, same weights
+    assert abs(lr - 1e-6) < 1e-12                                 # MultiStepLR(milestones=[4], gamma=0.1) has fired
+    w0 = O.make_weights("ViT-B/16", seed=0, protocol="P1")["backbone.conv1.weight"]
+    assert not torch.equal(w1.cpu(), w0)                          # optimiser steps at iterations 1 (2 % 2), 3 and 5 (last)
