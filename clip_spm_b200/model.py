@@ -374,6 +374,8 @@ class CNN(nn.Module):
     def _train_tower(self, images):
         """models/clip_fsar.py:672-689 with a graph (train_backbone): the differentiable tf32 / fp32 tower of clip_spm_b200.train"""
         from . import train as _train
+        if not self.get_parameter("backbone.conv1.weight").requires_grad:
+            raise RuntimeError("train_backbone was set after model.train(): set it first (train() prepares the tower's parameters)")
         if getattr(self, "_vitblk", None) is None:
             self._vitblk = _train.VitBlock(exact=self.precision == "fp32")
         return _train.vit_forward(dict(self.named_parameters()), images, self._vitblk, "backbone.", self.precision == "fp32")

@@ -1,4 +1,5 @@
-"""__graft_entry__.smoke(): one small episode through the CUDA path on cuda:0, checked against the oracle.
+"""__graft_entry__.smoke(): one small episode through the CUDA path on cuda:0 -- the evaluation forward, then the same episode
+forward + backward in train mode (tower and head) -- checked against the oracle.
 Lives outside the product package: it imports the oracle (the checker), which nothing in clip_spm_b200/ may do."""
 import os
 import sys
@@ -27,3 +28,24 @@ def run():
           "rel err %.3e" % err)
     if not err < 2e-2:
         raise RuntimeError("smoke: CUDA path disagrees with the oracle (rel err %.3e)" % err)
+    # forward + backward: the same 8 frames in train mode (dropout off), every gradient of the tower and the head against the
+    # oracle's autograd on the CPU (relative L2; the training path multiplies in tf32)
+    net.text_features_train = ci["text"]
+    net.train_backbone, net.train_dropout = True, False
+    net.train()
+    tout = net(ep)
+    net.loss(tout, ep["target_labels"]).backward()
+    torch.cuda.synchronize()
+    loss, grads = O.train_loss_and_grads(ci["weights"], ci["text"], ci["episode"], cfg)
+    worst, n = 0.0, 0
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        g = grads[k].reshape(p.grad.shape).double()
+        worst = max(worst, float((p.grad.cpu().double() - g).norm() / g.norm().clamp_min(1e-30)))
+        n += 1
+    print("smoke: train-mode forward + backward, %d gradients, worst relative L2 error %.3e" % (n, worst))
+    # (a gross-error gate: the tf32 path measures 2.8e-2 here; the strict gradient parity -- fp32 mode 2e-3, tf32 5e-2 on the
+    # goldens of the reference's own backward -- lives in tests/test_train_gpu.py)
+    if n != len(grads) or not worst < 0.15:
+        raise RuntimeError("smoke: gradients disagree with the oracle's autograd (%d of %d tensors, worst %.3e)" % (n, len(grads), worst))
