@@ -188,3 +188,21 @@ def test_philox_known_answers_and_mask_statistics():
     m = O.dropout_mask((1000, 101), 0.2, 99, 0)
     assert set(np.unique(m.numpy()).round(4)) == {0.0, 1.25} and abs(float((m > 0).float().mean()) - 0.8) < 5e-3
     assert not torch.equal(m, O.dropout_mask((1000, 101), 0.2, 99, 1)) and not torch.equal(m, O.dropout_mask((1000, 101), 0.2, 98, 0))
+
+
+def test_training_ops_fail_loudly_without_gpu():
+    """the differentiable nodes have no CPU path: CPU tensors (or a box without a GPU) raise instead of falling back"""
+    from clip_spm_b200 import CNN, train
+    from clip_spm_b200.config import make_cfg
+    x, W = torch.randn(4, 64), torch.randn(32, 64)
+    for fn in (lambda: train.linear(x, W), lambda: train.layer_norm(x, torch.ones(64), torch.zeros(64)),
+               lambda: train.dropout(x, 0.5, 1), lambda: train.TransformerV1(64)(torch.randn(1, 2, 64), {}),
+               lambda: train.VitBlock()(torch.randn(1, 197, 768), {}, "b.")):
+        with pytest.raises(RuntimeError):
+            fn()
+    if not torch.cuda.is_available():
+        net = CNN(make_cfg("ViT-B/16", 2), text_features_test=torch.zeros(4, 512), text_features_train=torch.zeros(4, 512))
+        net.train()
+        with pytest.raises(RuntimeError):
+            net.head(torch.zeros(1, 2, 2, 512), torch.zeros(1, 2, 2, 512), torch.tensor([0., 1.]), torch.tensor([0., 1.]),
+                     torch.tensor([0., 1.]))
