@@ -303,6 +303,10 @@ def train_step_leg(CNN, make_cfg, sweep, optim, _lib, dev, way, shot, qpc, tower
     zero_grad -- through clip_spm_b200's train mode, the library's Adam(betas=(0.5, 0.999)) and GradScaler.  tower=False: the
     frame encoder runs frozen on the bf16 evaluation kernels and only the head is differentiated; tower=True (ViT-B/16): the
     differentiable tf32 tower as well, Adam over every parameter.  Inputs resident on the device, CUDA-event timing."""
+    # a Python-driven training step launches ~1500 kernels: keep the process on the CPUs next to its GPU while it runs
+    # (unbound, the same step was measured anywhere between 54 and 176 ms); the affinity is restored afterwards
+    saved_affinity = os.sched_getaffinity(0)
+    bound = sweep.bind_to_gpu_cpus(torch.device(dev).index or 0)
     net = CNN(make_cfg("ViT-B/16", T, False, way), max_episodes=1, device=dev)
     net.init_random_(seed=0)
     text = torch.randn(N_TEXT, 512, generator=torch.Generator().manual_seed(0))
@@ -340,6 +344,8 @@ def train_step_leg(CNN, make_cfg, sweep, optim, _lib, dev, way, shot, qpc, tower
            "arithmetic": ("tf32 tensor-core products, fp32 SIMT attention, fp32 accumulation and state" if tower else
                           "frozen tower: bf16 tcgen05 evaluation kernels; head: tf32 products"),
            "call": "CNN.forward(dict) in train mode + loss + optim.GradScaler.scale(loss).backward() + step + update + zero_grad"}
+    rec["cpu_binding"] = ("%d CPUs local to the GPU (NVML)" % len(bound)) if bound else "none"
+    os.sched_setaffinity(0, saved_affinity)
     del net, opt, ep, inp
     torch.cuda.empty_cache()
     return rec

@@ -24,6 +24,7 @@
 // QuickGELU, and 197-token x 12-head x 64-dim attention (forward: the fp32 kernel of sgemm_f32.cu; backward: the two-phase
 // kernel below) -- i.e. the backward of the CLIP ViT-B/16 tower the reference's optimiser also steps.
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -477,6 +478,201 @@ vit_attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict_
   }
 }
 
+// ---- the same backward on the tensor cores (mma.sync m16n8k8 tf32, fp32 accumulation): the tf32 training path ----
+// One CTA per (frame, head); q, k, v, dO rounded to tf32 in shared memory as [208][68] (rows >= 197 zero; a row stride of 68
+// floats makes the scalar fragment reads conflict-free).  Row statistics come first, so that no pass needs a row reduction:
+//   delta_i = dO_i . O_i            (= sum_j p_ij dp_ij; O is the forward's attention output, kept by the block)
+//   L_i     = log2 sum_j 2^(s_ij)   (s = q k^T scaled to base 2; online over the key tiles, then across the 4 lanes of a row)
+// phase 1, a warp per 16 QUERY rows, key tiles of 8: S and dP tiles by 2 x 8 MMAs, p = 2^(s - L_i), dS = p (dp - delta_i) in the
+//   accumulator registers, which ARE the A fragment of the next product (slot t <-> column 2t, slot t+4 <-> column 2t+1, the
+//   B rows read in the same order): dQ += dS K.
+// phase 2, a warp per 16 KEY rows, query tiles of 8: the transposed tiles K Q^T and V dO^T with the column statistics,
+//   dK += dS^T Q, dV += P^T dO.
+// 25 key tiles x (16 + 8) MMAs per row tile instead of 35 MFLOP of FFMA per (frame, head).
+constexpr int ML = 68, MROWS = 208, MTILES = MROWS / 16, NTILES = (VL + 7) / 8;
+constexpr int VIT_ATT_BWD_MMA_SMEM = (4 * MROWS * ML + 2 * MROWS) * 4;
+constexpr float V_SCALE_LOG2 = 0.125f * 1.4426950408889634f;
+
+__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A fragments of rows r0 .. r0+15 of X over the 64 dims: k-slot t <-> dim 8 ks + 2t, slot t+4 <-> dim 8 ks + 2t + 1
+__device__ __forceinline__ void vit_afrag(const float* __restrict__ X, int r0, int g, int t, uint32_t (&a)[8][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const float2 v0 = *reinterpret_cast<const float2*>(X + (r0 + g) * ML + 8 * ks + 2 * t);
+    const float2 v1 = *reinterpret_cast<const float2*>(X + (r0 + g + 8) * ML + 8 * ks + 2 * t);
+    a[ks][0] = __float_as_uint(v0.x); a[ks][1] = __float_as_uint(v1.x);
+    a[ks][2] = __float_as_uint(v0.y); a[ks][3] = __float_as_uint(v1.y);
+  }
+}
+// c[16 x 8] = X rows (fragments a) . Y[j0 .. j0+7, :]^T
+__device__ __forceinline__ void vit_score_tile(const uint32_t (&a)[8][4], const float* __restrict__ Y, int j0, int g, int t,
+                                               float (&c)[4]) {
+  c[0] = c[1] = c[2] = c[3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const float2 v = *reinterpret_cast<const float2*>(Y + (j0 + g) * ML + 8 * ks + 2 * t);
+    mma_tf32(c, a[ks], __float_as_uint(v.x), __float_as_uint(v.y));
+  }
+}
+// acc[16 x 64] += W[16 x 8] . Z[j0 .. j0+7, :64], W given in the accumulator layout (c0,c1: row g, cols 2t,2t+1; c2,c3: row g+8)
+__device__ __forceinline__ void vit_accum_tile(const float (&w)[4], const float* __restrict__ Z, int j0, int g, int t,
+                                               float (&acc)[8][4]) {
+  const uint32_t a[4] = {__float_as_uint(tf32_round(w[0])), __float_as_uint(tf32_round(w[2])),
+                         __float_as_uint(tf32_round(w[1])), __float_as_uint(tf32_round(w[3]))};
+  const float* z0 = Z + (j0 + 2 * t) * ML + g;
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd) mma_tf32(acc[nd], a, __float_as_uint(z0[8 * nd]), __float_as_uint(z0[ML + 8 * nd]));
+}
+
+__global__ void __launch_bounds__(256, 1)
+vit_attention_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ AO, const float* __restrict__ dO,
+                             float* __restrict__ dqkv) {
+  extern __shared__ __align__(16) float sm_vm[];
+  float* sQ = sm_vm;
+  float* sK = sQ + MROWS * ML;
+  float* sV = sK + MROWS * ML;
+  float* sO = sV + MROWS * ML;
+  float* sL = sO + MROWS * ML;    // log2 of the row's softmax denominator (base-2 scores)
+  float* sD = sL + MROWS;         // delta
+  const int frame = blockIdx.x / VHEADS, head = blockIdx.x % VHEADS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long row0 = (long long)frame * VL;
+  const float* base = qkv + row0 * (3 * VC) + head * VHD;
+  for (int i = threadIdx.x; i < MROWS * (VHD / 4); i += blockDim.x) {
+    const int r = i / (VHD / 4), d = (i % (VHD / 4)) * 4;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q, o = q;
+    if (r < VL) {
+      q = *reinterpret_cast<const float4*>(base + (long long)r * (3 * VC) + d);
+      k = *reinterpret_cast<const float4*>(base + (long long)r * (3 * VC) + VC + d);
+      v = *reinterpret_cast<const float4*>(base + (long long)r * (3 * VC) + 2 * VC + d);
+      o = *reinterpret_cast<const float4*>(dO + (row0 + r) * VC + head * VHD + d);
+    }
+    *reinterpret_cast<float4*>(sQ + r * ML + d) = make_float4(tf32_round(q.x), tf32_round(q.y), tf32_round(q.z), tf32_round(q.w));
+    *reinterpret_cast<float4*>(sK + r * ML + d) = make_float4(tf32_round(k.x), tf32_round(k.y), tf32_round(k.z), tf32_round(k.w));
+    *reinterpret_cast<float4*>(sV + r * ML + d) = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+    *reinterpret_cast<float4*>(sO + r * ML + d) = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+  }
+  // delta_i = dO_i . O_i on the unrounded values, a warp per row
+  for (int i = warp; i < MROWS; i += 8) {
+    float s = 0.f;
+    if (i < VL) {
+      const float* o = AO + (row0 + i) * VC + head * VHD;
+      const float* d = dO + (row0 + i) * VC + head * VHD;
+      s = o[lane] * d[lane] + o[lane + 32] * d[lane + 32];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) sD[i] = s;
+  }
+  __syncthreads();
+  uint32_t xa[8][4], ya[8][4];
+  float c[4], d[4];
+  // ---- phase 0: L_i
+  for (int rt = warp; rt < MTILES; rt += 8) {
+    const int r0 = 16 * rt;
+    vit_afrag(sQ, r0, g, t, xa);
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+    for (int jt = 0; jt < NTILES; ++jt) {
+      const int j0 = 8 * jt, col = j0 + 2 * t;
+      vit_score_tile(xa, sK, j0, g, t, c);
+      const float s00 = col < VL ? c[0] * V_SCALE_LOG2 : -INFINITY, s01 = col + 1 < VL ? c[1] * V_SCALE_LOG2 : -INFINITY;
+      const float s10 = col < VL ? c[2] * V_SCALE_LOG2 : -INFINITY, s11 = col + 1 < VL ? c[3] * V_SCALE_LOG2 : -INFINITY;
+      const float n0 = fmaxf(m0, fmaxf(s00, s01)), n1 = fmaxf(m1, fmaxf(s10, s11));
+      if (n0 > -INFINITY) { l0 = l0 * exp2f(m0 - n0) + exp2f(s00 - n0) + exp2f(s01 - n0); m0 = n0; }
+      if (n1 > -INFINITY) { l1 = l1 * exp2f(m1 - n1) + exp2f(s10 - n1) + exp2f(s11 - n1); m1 = n1; }
+    }
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {      // the 4 lanes of a row hold disjoint columns
+      const float mo0 = __shfl_xor_sync(0xffffffffu, m0, off), lo0 = __shfl_xor_sync(0xffffffffu, l0, off);
+      const float mo1 = __shfl_xor_sync(0xffffffffu, m1, off), lo1 = __shfl_xor_sync(0xffffffffu, l1, off);
+      const float n0 = fmaxf(m0, mo0), n1 = fmaxf(m1, mo1);
+      l0 = (m0 > -INFINITY ? l0 * exp2f(m0 - n0) : 0.f) + (mo0 > -INFINITY ? lo0 * exp2f(mo0 - n0) : 0.f);
+      l1 = (m1 > -INFINITY ? l1 * exp2f(m1 - n1) : 0.f) + (mo1 > -INFINITY ? lo1 * exp2f(mo1 - n1) : 0.f);
+      m0 = n0; m1 = n1;
+    }
+    if (t == 0) { sL[r0 + g] = m0 + log2f(l0); sL[r0 + g + 8] = m1 + log2f(l1); }
+  }
+  __syncthreads();
+  float* out = dqkv + row0 * (3 * VC) + head * VHD;
+  float acc[8][4], acc2[8][4];
+  // ---- phase 1: dQ, a warp per 16 query rows
+  for (int rt = warp; rt < MTILES; rt += 8) {
+    const int r0 = 16 * rt;
+    vit_afrag(sQ, r0, g, t, xa);
+    vit_afrag(sO, r0, g, t, ya);
+    const float L0 = sL[r0 + g], L1 = sL[r0 + g + 8], D0 = sD[r0 + g], D1 = sD[r0 + g + 8];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
+#pragma unroll 1
+    for (int jt = 0; jt < NTILES; ++jt) {
+      const int j0 = 8 * jt, col = j0 + 2 * t;
+      vit_score_tile(xa, sK, j0, g, t, c);     // S
+      vit_score_tile(ya, sV, j0, g, t, d);     // dP
+      const bool v0 = col < VL, v1 = col + 1 < VL;
+      float ds[4];
+      ds[0] = v0 ? exp2f(c[0] * V_SCALE_LOG2 - L0) * (d[0] - D0) : 0.f;
+      ds[1] = v1 ? exp2f(c[1] * V_SCALE_LOG2 - L0) * (d[1] - D0) : 0.f;
+      ds[2] = v0 ? exp2f(c[2] * V_SCALE_LOG2 - L1) * (d[2] - D1) : 0.f;
+      ds[3] = v1 ? exp2f(c[3] * V_SCALE_LOG2 - L1) * (d[3] - D1) : 0.f;
+      vit_accum_tile(ds, sK, j0, g, t, acc);
+    }
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      if (r0 + g < VL)
+        *reinterpret_cast<float2*>(out + (long long)(r0 + g) * (3 * VC) + 8 * nd + 2 * t) = make_float2(acc[nd][0] * 0.125f, acc[nd][1] * 0.125f);
+      if (r0 + g + 8 < VL)
+        *reinterpret_cast<float2*>(out + (long long)(r0 + g + 8) * (3 * VC) + 8 * nd + 2 * t) = make_float2(acc[nd][2] * 0.125f, acc[nd][3] * 0.125f);
+    }
+  }
+  // ---- phase 2: dK, dV, a warp per 16 key rows; the tile columns are QUERY rows
+  for (int rt = warp; rt < MTILES; rt += 8) {
+    const int r0 = 16 * rt;
+    vit_afrag(sK, r0, g, t, xa);
+    vit_afrag(sV, r0, g, t, ya);
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
+      acc2[nd][0] = acc2[nd][1] = acc2[nd][2] = acc2[nd][3] = 0.f;
+    }
+#pragma unroll 1
+    for (int it = 0; it < NTILES; ++it) {
+      const int i0 = 8 * it, col = i0 + 2 * t;
+      vit_score_tile(xa, sQ, i0, g, t, c);     // S^T: c[row = key][col = query]
+      vit_score_tile(ya, sO, i0, g, t, d);     // dP^T
+      const bool v0 = col < VL, v1 = col + 1 < VL;
+      const float L0 = sL[col], L1 = sL[col + 1], D0 = sD[col], D1 = sD[col + 1];
+      float pr[4], ds[4];
+      pr[0] = v0 ? exp2f(c[0] * V_SCALE_LOG2 - L0) : 0.f;
+      pr[1] = v1 ? exp2f(c[1] * V_SCALE_LOG2 - L1) : 0.f;
+      pr[2] = v0 ? exp2f(c[2] * V_SCALE_LOG2 - L0) : 0.f;
+      pr[3] = v1 ? exp2f(c[3] * V_SCALE_LOG2 - L1) : 0.f;
+      ds[0] = pr[0] * (d[0] - D0); ds[1] = pr[1] * (d[1] - D1); ds[2] = pr[2] * (d[2] - D0); ds[3] = pr[3] * (d[3] - D1);
+      vit_accum_tile(ds, sQ, i0, g, t, acc);    // dK += dS^T Q
+      vit_accum_tile(pr, sO, i0, g, t, acc2);   // dV += P^T dO
+    }
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      if (r0 + g < VL) {
+        float* o = out + (long long)(r0 + g) * (3 * VC) + 8 * nd + 2 * t;
+        *reinterpret_cast<float2*>(o + VC) = make_float2(acc[nd][0] * 0.125f, acc[nd][1] * 0.125f);
+        *reinterpret_cast<float2*>(o + 2 * VC) = make_float2(acc2[nd][0], acc2[nd][1]);
+      }
+      if (r0 + g + 8 < VL) {
+        float* o = out + (long long)(r0 + g + 8) * (3 * VC) + 8 * nd + 2 * t;
+        *reinterpret_cast<float2*>(o + VC) = make_float2(acc[nd][2] * 0.125f, acc[nd][3] * 0.125f);
+        *reinterpret_cast<float2*>(o + 2 * VC) = make_float2(acc2[nd][2], acc2[nd][3]);
+      }
+    }
+  }
+}
+
 constexpr int TV1_SEQ_MAX = 64;
 size_t attn_bwd_smem(int n, int dh) { return (size_t)(4 * n * (dh + 1) + 2 * n * n) * sizeof(float); }
 
@@ -592,6 +788,7 @@ int block_create(int D, int heads, int dim_head, int mlp_dim, int precision, boo
   SPM_CUDA(cudaFuncSetAttribute(seq_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)attn_bwd_smem(48, 256)));
   SPM_CUDA(cudaFuncSetAttribute(vit_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VIT_ATT_BWD_SMEM));
+  SPM_CUDA(cudaFuncSetAttribute(vit_attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VIT_ATT_BWD_MMA_SMEM));
   spm_tv1* h = new spm_tv1();
   h->D = D; h->heads = heads; h->dh = dim_head; h->inner = heads * dim_head; h->mlp = mlp_dim; h->fp32 = precision; h->vit = vit;
   int dev = 0;
@@ -715,7 +912,12 @@ int block_backward(spm_tv1* h, cudaStream_t st, const float* grad_out, float* gr
   SPM_TRY(tv1_gemm(h, st, gy, D, h->woutT, D, R, I, D, nullptr, ACT_NONE, nullptr, s.dAO));               // dAO = dY Wout
   // ---- attention
   if (h->vit) {
-    vit_attention_bwd_kernel<<<h->B * VHEADS, 256, VIT_ATT_BWD_SMEM, st>>>(h->QKV, s.dAO, s.dQKV);
+    // tf32 path: tensor cores (mma.sync); exact-fp32 path (and SPM_TRAIN_ATTN=simt, the cross-check): the FFMA kernel
+    static const bool simt = [] { const char* e = getenv("SPM_TRAIN_ATTN"); return e != nullptr && std::string(e) == "simt"; }();
+    if (h->fp32 || simt)
+      vit_attention_bwd_kernel<<<h->B * VHEADS, 256, VIT_ATT_BWD_SMEM, st>>>(h->QKV, s.dAO, s.dQKV);
+    else
+      vit_attention_bwd_mma_kernel<<<h->B * VHEADS, 256, VIT_ATT_BWD_MMA_SMEM, st>>>(h->QKV, h->AO, s.dAO, s.dQKV);
     TV1_LAUNCH_CHECK();
   } else {
     SPM_CHECK(n <= TV1_SEQ_MAX && attn_bwd_smem(n, h->dh) <= attn_bwd_smem(48, 256), "block backward: sequence too long");

@@ -14,6 +14,9 @@ from oracle import clipspm_oracle as O
 from clip_spm_b200 import _lib, optim, train
 
 dev = "cuda"
+if os.environ.get("SPM_BIND_CPUS", "1") != "0":      # a Python-driven step launches ~1500 kernels: keep the process next to its GPU
+    from clip_spm_b200 import sweep as _sweep
+    print("bound to CPUs:", (_sweep.bind_to_gpu_cpus(0) or "unchanged"))
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 way, shot, qpc, T, D, ncls = 5, 5, 1, 8, 512, 24
 w0 = {k: v for k, v in O.make_weights("ViT-B/16", seed=0, protocol="P1", head_only=True).items() if v.dtype.is_floating_point}
@@ -148,4 +151,4 @@ def whole_step(way, shot, qpc, T, n_steps):
               % ("autocast bf16 tower" if ac else "fp32 / TF32 matmuls", ms_e, 1e3 / ms_e, ms_e / ms))
 
 
-whole_step(5, 1, 1, 8, 1 if ONLY_WHOLE else 6)
+whole_step(5, 1, 1, 8, int(os.environ.get("SPM_TIMING_WHOLE_STEPS", "1" if ONLY_WHOLE else "6")))
