@@ -41,6 +41,8 @@ struct spm_tv1 {
   // ViT variant (clip_fsar.py:622-643): ln_2 before the MLP, q/k/v bias, QuickGELU, 197-token attention kernels
   bool vit = false;
   float *ln2_g = nullptr, *ln2_b = nullptr, *bqkv = nullptr, *H2 = nullptr;
+  float* Lsm = nullptr;      // [frames * 12][208] log2 softmax denominators of the tensor-core attention forward
+  bool have_L = false;
   // weights (reference layouts) and their transposes
   float *ln_g = nullptr, *ln_b = nullptr, *wqkv = nullptr, *wout = nullptr, *bout = nullptr, *w0 = nullptr, *b0 = nullptr,
         *w3 = nullptr, *b3 = nullptr;
@@ -530,9 +532,88 @@ __device__ __forceinline__ void vit_accum_tile(const float (&w)[4], const float*
   for (int nd = 0; nd < 8; ++nd) mma_tf32(acc[nd], a, __float_as_uint(z0[8 * nd]), __float_as_uint(z0[ML + 8 * nd]));
 }
 
+// Forward of the same attention on the tensor cores (tf32 training path): L_i first (as in the backward's phase 0), then
+// p = 2^(s - L_i) is final at once and O += P V needs no rescaling; L is kept for the backward.
+constexpr int VIT_ATT_FWD_MMA_SMEM = (3 * MROWS * ML + MROWS) * 4;
+
+__global__ void __launch_bounds__(256, 1)
+vit_attention_fwd_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ Lout) {
+  extern __shared__ __align__(16) float sm_vf[];
+  float* sQ = sm_vf;
+  float* sK = sQ + MROWS * ML;
+  float* sV = sK + MROWS * ML;
+  const int frame = blockIdx.x / VHEADS, head = blockIdx.x % VHEADS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long row0 = (long long)frame * VL;
+  const float* base = qkv + row0 * (3 * VC) + head * VHD;
+  for (int i = threadIdx.x; i < MROWS * (VHD / 4); i += blockDim.x) {
+    const int r = i / (VHD / 4), d = (i % (VHD / 4)) * 4;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q;
+    if (r < VL) {
+      q = *reinterpret_cast<const float4*>(base + (long long)r * (3 * VC) + d);
+      k = *reinterpret_cast<const float4*>(base + (long long)r * (3 * VC) + VC + d);
+      v = *reinterpret_cast<const float4*>(base + (long long)r * (3 * VC) + 2 * VC + d);
+    }
+    *reinterpret_cast<float4*>(sQ + r * ML + d) = make_float4(tf32_round(q.x), tf32_round(q.y), tf32_round(q.z), tf32_round(q.w));
+    *reinterpret_cast<float4*>(sK + r * ML + d) = make_float4(tf32_round(k.x), tf32_round(k.y), tf32_round(k.z), tf32_round(k.w));
+    *reinterpret_cast<float4*>(sV + r * ML + d) = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+  }
+  __syncthreads();
+  uint32_t xa[8][4];
+  float c[4], acc[8][4];
+  float* Lrow = Lout + (long long)blockIdx.x * MROWS;
+  for (int rt = warp; rt < MTILES; rt += 8) {
+    const int r0 = 16 * rt;
+    vit_afrag(sQ, r0, g, t, xa);
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+    for (int jt = 0; jt < NTILES; ++jt) {
+      const int j0 = 8 * jt, col = j0 + 2 * t;
+      vit_score_tile(xa, sK, j0, g, t, c);
+      const float s00 = col < VL ? c[0] * V_SCALE_LOG2 : -INFINITY, s01 = col + 1 < VL ? c[1] * V_SCALE_LOG2 : -INFINITY;
+      const float s10 = col < VL ? c[2] * V_SCALE_LOG2 : -INFINITY, s11 = col + 1 < VL ? c[3] * V_SCALE_LOG2 : -INFINITY;
+      const float n0 = fmaxf(m0, fmaxf(s00, s01)), n1 = fmaxf(m1, fmaxf(s10, s11));
+      if (n0 > -INFINITY) { l0 = l0 * exp2f(m0 - n0) + exp2f(s00 - n0) + exp2f(s01 - n0); m0 = n0; }
+      if (n1 > -INFINITY) { l1 = l1 * exp2f(m1 - n1) + exp2f(s10 - n1) + exp2f(s11 - n1); m1 = n1; }
+    }
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {
+      const float mo0 = __shfl_xor_sync(0xffffffffu, m0, off), lo0 = __shfl_xor_sync(0xffffffffu, l0, off);
+      const float mo1 = __shfl_xor_sync(0xffffffffu, m1, off), lo1 = __shfl_xor_sync(0xffffffffu, l1, off);
+      const float n0 = fmaxf(m0, mo0), n1 = fmaxf(m1, mo1);
+      l0 = (m0 > -INFINITY ? l0 * exp2f(m0 - n0) : 0.f) + (mo0 > -INFINITY ? lo0 * exp2f(mo0 - n0) : 0.f);
+      l1 = (m1 > -INFINITY ? l1 * exp2f(m1 - n1) : 0.f) + (mo1 > -INFINITY ? lo1 * exp2f(mo1 - n1) : 0.f);
+      m0 = n0; m1 = n1;
+    }
+    const float L0 = m0 + log2f(l0), L1 = m1 + log2f(l1);
+    if (t == 0) { Lrow[r0 + g] = L0; Lrow[r0 + g + 8] = L1; }
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
+#pragma unroll 1
+    for (int jt = 0; jt < NTILES; ++jt) {
+      const int j0 = 8 * jt, col = j0 + 2 * t;
+      vit_score_tile(xa, sK, j0, g, t, c);
+      const bool v0 = col < VL, v1 = col + 1 < VL;
+      float pr[4];
+      pr[0] = v0 ? exp2f(c[0] * V_SCALE_LOG2 - L0) : 0.f;
+      pr[1] = v1 ? exp2f(c[1] * V_SCALE_LOG2 - L0) : 0.f;
+      pr[2] = v0 ? exp2f(c[2] * V_SCALE_LOG2 - L1) : 0.f;
+      pr[3] = v1 ? exp2f(c[3] * V_SCALE_LOG2 - L1) : 0.f;
+      vit_accum_tile(pr, sV, j0, g, t, acc);
+    }
+    float* o = out + row0 * VC + head * VHD;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      if (r0 + g < VL) *reinterpret_cast<float2*>(o + (long long)(r0 + g) * VC + 8 * nd + 2 * t) = make_float2(acc[nd][0], acc[nd][1]);
+      if (r0 + g + 8 < VL)
+        *reinterpret_cast<float2*>(o + (long long)(r0 + g + 8) * VC + 8 * nd + 2 * t) = make_float2(acc[nd][2], acc[nd][3]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256, 1)
 vit_attention_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ AO, const float* __restrict__ dO,
-                             float* __restrict__ dqkv) {
+                             float* __restrict__ dqkv, const float* __restrict__ Lin) {
   extern __shared__ __align__(16) float sm_vm[];
   float* sQ = sm_vm;
   float* sK = sQ + MROWS * ML;
@@ -573,7 +654,10 @@ vit_attention_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restr
   __syncthreads();
   uint32_t xa[8][4], ya[8][4];
   float c[4], d[4];
-  // ---- phase 0: L_i
+  // ---- phase 0: L_i (kept by the tensor-core forward; recomputed here when the forward was the fp32 kernel)
+  if (Lin != nullptr) {
+    for (int i = threadIdx.x; i < MROWS; i += blockDim.x) sL[i] = Lin[(long long)blockIdx.x * MROWS + i];
+  } else
   for (int rt = warp; rt < MTILES; rt += 8) {
     const int r0 = 16 * rt;
     vit_afrag(sQ, r0, g, t, xa);
@@ -762,7 +846,7 @@ int tv1_scratch(const spm_tv1* h, long long R) {
 int tv1_workspace(spm_tv1* h, long long R) {
   if (R <= h->cap_rows) return 0;
   SPM_CUDA(cudaDeviceSynchronize());
-  for (float** p : {&h->HN, &h->QKV, &h->AO, &h->Y, &h->FFH, &h->H2})
+  for (float** p : {&h->HN, &h->QKV, &h->AO, &h->Y, &h->FFH, &h->H2, &h->Lsm})
     if (*p) { cudaFree(*p); h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), (void*)*p), h->allocs.end()); *p = nullptr; }
   const long long D = h->D, I = h->inner, M = h->mlp;
   SPM_TRY(tv1_alloc(h, &h->HN, R * D));
@@ -771,6 +855,7 @@ int tv1_workspace(spm_tv1* h, long long R) {
   SPM_TRY(tv1_alloc(h, &h->Y, R * D));
   SPM_TRY(tv1_alloc(h, &h->FFH, R * M));
   if (h->vit) SPM_TRY(tv1_alloc(h, &h->H2, R * D));
+  if (h->vit) SPM_TRY(tv1_alloc(h, &h->Lsm, (R / VL + 1) * (long long)VHEADS * MROWS));
   h->cap_rows = R;
   return 0;
 }
@@ -789,6 +874,7 @@ int block_create(int D, int heads, int dim_head, int mlp_dim, int precision, boo
                                 (int)attn_bwd_smem(48, 256)));
   SPM_CUDA(cudaFuncSetAttribute(vit_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VIT_ATT_BWD_SMEM));
   SPM_CUDA(cudaFuncSetAttribute(vit_attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VIT_ATT_BWD_MMA_SMEM));
+  SPM_CUDA(cudaFuncSetAttribute(vit_attention_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VIT_ATT_FWD_MMA_SMEM));
   spm_tv1* h = new spm_tv1();
   h->D = D; h->heads = heads; h->dh = dim_head; h->inner = heads * dim_head; h->mlp = mlp_dim; h->fp32 = precision; h->vit = vit;
   int dev = 0;
@@ -835,7 +921,13 @@ int block_forward(spm_tv1* h, cudaStream_t st, const float* x, int n_seq, int se
   h->x = x; h->B = n_seq; h->n = seq_len;
   TV1_KERNEL(k_layernorm(st, x, D, R, D, h->ln_g, h->ln_b, nullptr, 0, h->HN, nullptr, D));
   SPM_TRY(tv1_gemm(h, st, h->HN, D, h->wqkv, D, R, 3 * I, D, h->vit ? h->bqkv : nullptr, ACT_NONE, nullptr, h->QKV));
-  if (h->vit) TV1_KERNEL(k_vit_attention_f32(st, h->QKV, h->AO, n_seq));
+  static const bool simt_attn = [] { const char* e = getenv("SPM_TRAIN_ATTN"); return e != nullptr && std::string(e) == "simt"; }();
+  h->have_L = false;
+  if (h->vit && !h->fp32 && !simt_attn) {      // tf32 path: tensor cores; keeps L for the backward
+    vit_attention_fwd_mma_kernel<<<n_seq * VHEADS, 256, VIT_ATT_FWD_MMA_SMEM, st>>>(h->QKV, h->AO, h->Lsm);
+    TV1_LAUNCH_CHECK();
+    h->have_L = true;
+  } else if (h->vit) TV1_KERNEL(k_vit_attention_f32(st, h->QKV, h->AO, n_seq));
   else TV1_KERNEL(k_seq_attention(st, h->QKV, h->AO, n_seq, seq_len, 1, 0, seq_len, 0, 0, h->heads, h->dh));
   // nn.Dropout sites of the block (myRes.py:961-962 to_out, :990,992 FeedForward): 0 = after to_out, 1 = after GELU, 2 = after
   // net.3; each is applied BEFORE the residual add, so with p > 0 the residual leaves the GEMM epilogue
@@ -917,7 +1009,8 @@ int block_backward(spm_tv1* h, cudaStream_t st, const float* grad_out, float* gr
     if (h->fp32 || simt)
       vit_attention_bwd_kernel<<<h->B * VHEADS, 256, VIT_ATT_BWD_SMEM, st>>>(h->QKV, s.dAO, s.dQKV);
     else
-      vit_attention_bwd_mma_kernel<<<h->B * VHEADS, 256, VIT_ATT_BWD_MMA_SMEM, st>>>(h->QKV, h->AO, s.dAO, s.dQKV);
+      vit_attention_bwd_mma_kernel<<<h->B * VHEADS, 256, VIT_ATT_BWD_MMA_SMEM, st>>>(h->QKV, h->AO, s.dAO, s.dQKV,
+                                                                                        h->have_L ? h->Lsm : nullptr);
     TV1_LAUNCH_CHECK();
   } else {
     SPM_CHECK(n <= TV1_SEQ_MAX && attn_bwd_smem(n, h->dh) <= attn_bwd_smem(48, 256), "block backward: sequence too long");
