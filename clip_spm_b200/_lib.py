@@ -74,6 +74,7 @@ SIGNATURES = {
     "spm_tv1_load_weights": (c_int, [c_void_p, c_void_p] + [c_void_p] * 11),
     "spm_tv1_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "spm_tv1_set_dropout": (c_int, [c_void_p, c_float, c_float, ctypes.c_ulonglong]),
+    "spm_dropout_seed_source": (c_int, [c_void_p]),
     "spm_dropout": (c_int, [c_void_p, c_void_p, c_ll, c_float, ctypes.c_ulonglong, ctypes.c_uint, c_void_p]),
     "spm_tv1_backward": (c_int, [c_void_p, c_void_p] + [c_void_p] * 13),
     "spm_vitblock_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),

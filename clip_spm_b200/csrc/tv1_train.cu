@@ -184,9 +184,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // key = seed) >> 8) * 2^-24 >= p, kept values are scaled by 1 / (1 - p);  y = dropout(x) (+ add).  The same call with the
 // upstream gradient as x is the backward.  One thread per four consecutive elements (one Philox block).
 __global__ void dropout_kernel(const float* x, const float* __restrict__ add, float* y, long long n,
-                               float p, unsigned long long seed, unsigned site) {
+                               float p, unsigned long long seed, unsigned site, const unsigned long long* __restrict__ seed_src) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q * 4 >= n) return;
+  if (seed_src != nullptr) seed += *seed_src;     // device-resident seed offset (CUDA-graph replays: spm_dropout_seed_source)
   const uint4 r = philox4x32_10(make_uint4((unsigned)q, (unsigned)(q >> 32), site, 0u),
                                 make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
   const unsigned w[4] = {r.x, r.y, r.z, r.w};
@@ -772,10 +773,12 @@ int tv1_transpose(cudaStream_t st, const float* in, int R, int C, float* out, in
   TV1_LAUNCH_CHECK();
   return 0;
 }
+const unsigned long long* g_seed_src = nullptr;   // spm_dropout_seed_source
+
 int tv1_dropout(cudaStream_t st, const float* x, const float* add, float* y, long long n, float p, unsigned long long seed,
                 unsigned site) {
   const long long quads = (n + 3) / 4;
-  dropout_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(x, add, y, n, p, seed, site);
+  dropout_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(x, add, y, n, p, seed, site, g_seed_src);
   TV1_LAUNCH_CHECK();
   return 0;
 }
@@ -1062,6 +1065,11 @@ int spm_tv1_set_dropout(spm_tv1* h, float p_atte, float p_ffn, unsigned long lon
   SPM_CHECK(h != nullptr, "spm_tv1_set_dropout: null handle");
   SPM_CHECK(p_atte >= 0.f && p_atte < 1.f && p_ffn >= 0.f && p_ffn < 1.f, "spm_tv1_set_dropout: probabilities in [0, 1)");
   h->p_atte = p_atte; h->p_ffn = p_ffn; h->seed = seed;
+  return 0;
+}
+
+int spm_dropout_seed_source(const unsigned long long* device_counter) {
+  g_seed_src = device_counter;
   return 0;
 }
 

@@ -409,13 +409,15 @@ class CNN(nn.Module):
         # train-mode dropout (myRes.py:961-996): one fresh 62-bit seed per forward from torch's CPU generator, so that
         # torch.manual_seed reproduces a run; `model.train_dropout = False` gives the p = 0 head the parity goldens pin
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if getattr(self, "train_dropout", True) else None
+        if getattr(self, "_graph_seed", None) is not None:     # train.GraphedStep: constant base seed + a device counter
+            seed = self._graph_seed
         if self.HEAD == "clipfsar":
             return _train.fsar_head_forward(w, text, su, qu, lab, rs, rt, blocks[0], self.transformer_depth, self.single_direct,
                                             self.merge_before, bool(_cfg_get(self.args, "MODEL.USE_CLASSIFICATION", False)),
-                                            self.precision == "fp32", seed)
+                                            self.precision == "fp32", seed, self.way)
         c1, c2 = blocks
         return _train.spm_head_forward(w, text, su, qu, lab, rs, rt, self.params, c1, c2, self.single_direct,
-                                       self.precision == "fp32", seed)
+                                       self.precision == "fp32", seed, self.way)
 
     def loss(self, out, target_labels, real_support_labels=None, real_target_labels=None):
         """The runner's loss on a train-mode output (differentiable): CLIP-SPM run/main_run.py:390-392 CE / TASKS_PER_BATCH +

@@ -20,7 +20,7 @@ from . import _lib
 from .ops import ACT, _need_cuda, _ptr, _stream, otam_distance
 
 __all__ = ["linear", "dropout", "layer_norm", "TransformerV1", "VitBlock", "vit_forward", "spm_head_forward", "spm_loss",
-           "fsar_head_forward", "fsar_loss", "shard_tasks", "allreduce_gradients", "run_listing_training"]
+           "fsar_head_forward", "fsar_loss", "shard_tasks", "allreduce_gradients", "run_listing_training", "GraphedStep"]
 
 
 class _Linear(torch.autograd.Function):
@@ -302,9 +302,10 @@ def _dis(x, y):
     return (d * d).sum(dim=[-2, -1] if d.dim() == 3 else [-1]).mean()
 
 
-def _class_mean_matrix(labels):
-    """[W, S] averaging matrix of the sorted unique labels (models/myRes.py:730-739 extract_class_indices + mean)."""
-    uniq = torch.unique(labels)
+def _class_mean_matrix(labels, way=None):
+    """[W, S] averaging matrix of the sorted unique labels (models/myRes.py:730-739 extract_class_indices + mean).  way given:
+    the labels are the episode's class indices 0 .. way-1 (video_reader.py:312-318), no torch.unique (a host sync)."""
+    uniq = torch.unique(labels) if way is None else torch.arange(int(way), device=labels.device, dtype=labels.dtype)
     m = (labels.view(1, -1) == uniq.view(-1, 1)).float()
     return m / m.sum(1, keepdim=True), uniq
 
@@ -315,7 +316,7 @@ def _class_means(cm, x):
 
 
 def spm_head_forward(w, text_features, su, qu, support_labels, real_support, real_target, params, context1, context2,
-                     single_direct=False, exact=False, dropout_seed=None):
+                     single_direct=False, exact=False, dropout_seed=None, way=None):
     """models/model_clipspm.py:116-143 after get_feats on su [S,T,D], qu [Q,T,D], differentiable with respect to the head
     parameters `w` (reference names) and the features.  The four live `se_te` calls (:296-314) share one `context2` pass;
     the two whose outputs only reach the discarded consistency distances (:258-265) are skipped, as in the evaluation path.
@@ -345,7 +346,7 @@ def spm_head_forward(w, text_features, su, qu, support_labels, real_support, rea
     qu_mo2, su_mo2 = zt[:Q], zt[Q:Q + S]
     new_m = _motion_feats(torch.cat([su_m, qu_m], dim=0), w, exact)                    # :199
     mo_dist = _dis(new_m[S:], qu_mo2) + _dis(new_m[:S], su_mo2)                        # :201-205
-    cm, uniq = _class_mean_matrix(support_labels)
+    cm, uniq = _class_mean_matrix(support_labels, way)
     W = cm.shape[0]
     su_pro = _class_means(cm, su_real)                                                 # :231-239
     class_dists_l = otam_distance(su_pro.unsqueeze(0), qu_fake.unsqueeze(0), single_direct)[0]        # :269 [Q,W]
@@ -387,7 +388,7 @@ def _cos_sim(x, y, exact, eps=0.01):
 
 
 def fsar_head_forward(w, text_train, su, qu, support_labels, real_support, real_target, context2, depth=1, single_direct=False,
-                      merge_before=False, use_classification=True, exact=False, dropout_seed=None):
+                      merge_before=False, use_classification=True, exact=False, dropout_seed=None, way=None):
     """models/model_clipfsar.py:183-262 (the training branch: prompt rows from text_features_train :197-198) after get_feats on
     su [S,T,D], qu [Q,T,D]: `context2` over each query's frames and over each support's frames + its prompt, class-mean
     prototypes, OTAM; class_text_logits = cos_sim(mean_t feats, text_features_train) * scale when MODEL.USE_CLASSIFICATION."""
@@ -403,7 +404,7 @@ def fsar_head_forward(w, text_train, su, qu, support_labels, real_support, real_
         class_logits = (_cos_sim(torch.cat([su, qu], dim=0).mean(1), text_train, exact) * w["scale"]).unsqueeze(0)
     ctx = text_train[real_support.long()].unsqueeze(1)                                        # :197
     qu2 = ctx2(qu, 0)                                                                         # :201
-    cm, _ = _class_mean_matrix(support_labels)
+    cm, _ = _class_mean_matrix(support_labels, way)
     if merge_before:                                                                          # :203-207
         su, ctx = _class_means(cm, su), _class_means(cm, ctx)
     su2 = ctx2(torch.cat([su, ctx], dim=1), 1)[:, :T]                                         # :208-209
@@ -525,3 +526,71 @@ def run_listing_training(net, split, load_frame, iterations, way, shot, n_querie
         if lr_milestone is not None:                                 # MultiStepLR, stepped once per iteration
             optimizer.param_groups[0]["lr"] = base_lr * (0.1 if iteration >= int(lr_milestone) else 1.0)
     return log
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the training iteration as ONE CUDA graph
+# ------------------------------------------------------------------------------------------------------------------
+class GraphedStep:
+    """forward + loss + backward + optimiser step of one training iteration captured into a CUDA graph and replayed: the step is
+    600-1500 launches driven from Python (autograd Functions over ctypes calls) and runs close to launch-bound -- a replay issues
+    them from the device queue.  What makes the step capturable: the library never synchronises inside it (the GradScaler's
+    skip-on-overflow is decided on the device, gradient tensors are kept so that the optimiser's pointer table does not change,
+    workspaces are grown by the warm-up iterations), `cfg.TRAIN.WAY` replaces the torch.unique host syncs, and the dropout seed is
+    a DEVICE counter incremented inside the graph (spm_dropout_seed_source), so every replay draws fresh masks.
+    inputs: dict of tensors with fixed shapes (copied into static buffers at every call); forward(net, inputs) -> the model's
+    output dict (default `net(inputs)`); the learning rate is baked in at capture (re-create the object after a schedule step).
+    Call it with the next episode's tensors; returns the (device) loss of that iteration."""
+
+    def __init__(self, net, optimizer, scaler, inputs, forward=None, warmup=3):
+        if not net.training:
+            raise RuntimeError("GraphedStep: call net.train() first")
+        if net.way is None:
+            raise RuntimeError("GraphedStep needs cfg.TRAIN.WAY (torch.unique on the labels would synchronise inside the capture)")
+        self.net, self.opt, self.scaler = net, optimizer, scaler
+        self.forward = forward or (lambda n, x: n(x))
+        dev = net._dev
+        self.static = {k: v.detach().to(dev).clone() for k, v in inputs.items() if torch.is_tensor(v)}
+        if net.text_features_train is not None:
+            net.text_features_train = net.text_features_train.to(dev, torch.float32)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        _lib.check(_lib.load().spm_dropout_seed_source(_ptr(self.counter)))
+        self._dropout = getattr(net, "train_dropout", True)
+        net._graph_seed = 0x5eed if self._dropout else None      # a constant base seed; the device counter moves it
+        self.params = net.trainable_parameters()
+        for p in self.params:
+            p.grad = torch.zeros_like(p)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, int(warmup))):
+                self._step()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+
+    def _step(self):
+        self.counter += 1
+        torch._foreach_zero_([p.grad for p in self.params])
+        out = self.forward(self.net, self.static)
+        loss = self.net.loss(out, self.static["target_labels"], self.static.get("real_support_labels"),
+                             self.static.get("real_target_labels"))
+        self.scaler.scale(loss).backward()
+        self.scaler.step(self.opt)
+        self.scaler.update()
+        return loss.detach()
+
+    def __call__(self, inputs):
+        for k, v in inputs.items():
+            if torch.is_tensor(v) and k in self.static:
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    def close(self):
+        """detach the device seed counter (dropout seeds are host arguments again)"""
+        _lib.check(_lib.load().spm_dropout_seed_source(None))
+        self.net._graph_seed = None

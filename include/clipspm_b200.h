@@ -226,6 +226,10 @@ int spm_tv1_forward(spm_tv1* h, void* stream, const float* x, int n_seq, int seq
  * spm_dropout applies the same mask to a plain tensor (y may alias x); calling it on the upstream gradient is its backward. */
 int spm_tv1_set_dropout(spm_tv1* h, float p_atte, float p_ffn, unsigned long long seed);
 int spm_dropout(void* stream, const float* x, long long n, float p, unsigned long long seed, unsigned site, float* y);
+/* CUDA graphs: a captured training step replays with the kernel arguments it was captured with, the seed included.  With a
+ * device counter registered here every dropout kernel of the process adds `*device_counter` to its seed when it RUNS, so a
+ * step that increments the counter on the device (inside the graph) draws fresh masks at every replay; null: off. */
+int spm_dropout_seed_source(const unsigned long long* device_counter);
 int spm_tv1_backward(spm_tv1* h, void* stream, const float* grad_out, float* grad_x, float* g_ln_g, float* g_ln_b,
                      float* g_wq, float* g_wk, float* g_wv, float* g_wout, float* g_bout, float* g_w0, float* g_b0,
                      float* g_w3, float* g_b3);

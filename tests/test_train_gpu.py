@@ -365,3 +365,63 @@ def test_training_loop_from_a_listing_of_decoded_frames():
     assert abs(lr - 1e-6) < 1e-12                                 # MultiStepLR(milestones=[4], gamma=0.1) has fired
     w0 = O.make_weights("ViT-B/16", seed=0, protocol="P1")["backbone.conv1.weight"]
     assert not torch.equal(w1.cpu(), w0)                          # optimiser steps at iterations 1 (2 % 2), 3 and 5 (last)
+
+
+def test_graphed_training_step_equals_eager_steps():
+    """train.GraphedStep: the whole iteration (forward, loss, backward, Adam through the GradScaler) captured into ONE CUDA graph;
+    replays must walk the same trajectory as eager steps (dropout off: bit for bit), draw fresh dropout masks per replay through
+    the device seed counter, and be faster than the Python-driven step"""
+    import time
+    from clip_spm_b200 import CNN, optim, train
+    ci = head_grad_inputs("head_grad_5w2s_t8")
+    ep = ci["ep"]
+
+    def build(dropout):
+        net = CNN(make_cfg(ci["backbone"], ci["T"], ci["single"], ci["way"]), text_features_test=ci["text"],
+                  text_features_train=ci["text"], precision="bf16")
+        net.load_state_dict(ci["w"], strict=False)
+        net.train_dropout = dropout
+        net.train()
+        opt = optim.Adam(net.trainable_parameters(), lr=1e-4, betas=(0.5, 0.999))
+        return net, opt, optim.GradScaler("cuda", init_scale=1024.0)
+    inputs = {"su": ci["su"].cuda().unsqueeze(0), "qu": ci["qu"].cuda().unsqueeze(0), "context_labels": ep["context_labels"].cuda(),
+              "real_support_labels": ep["real_support_labels"].cuda(), "real_target_labels": ep["real_target_labels"].cuda(),
+              "target_labels": ep["target_labels"].cuda()}
+    fwd = lambda n, x: n.head(x["su"], x["qu"], x["context_labels"], x["real_support_labels"], x["real_target_labels"])  # noqa: E731
+    # eager: 5 steps
+    net_e, opt_e, sc_e = build(False)
+    for _ in range(5):
+        loss_e = net_e.loss(fwd(net_e, inputs), inputs["target_labels"])
+        sc_e.scale(loss_e).backward()
+        sc_e.step(opt_e); sc_e.update(); opt_e.zero_grad()
+    # graphed: 3 warm-up steps + 2 replays
+    net_g, opt_g, sc_g = build(False)
+    step = train.GraphedStep(net_g, opt_g, sc_g, inputs, forward=fwd, warmup=3)
+    for _ in range(2):
+        loss_g = step(inputs)
+    torch.cuda.synchronize()
+    assert torch.equal(loss_g, loss_e.detach())
+    for (n, p), (_, q) in zip(net_g.named_parameters(), net_e.named_parameters()):
+        assert torch.equal(p.detach(), q.detach()), n
+    # speed: replays against Python-driven steps of the same model
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(20):
+        step(inputs)
+    torch.cuda.synchronize(); t_graph = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(20):
+        l = net_e.loss(fwd(net_e, inputs), inputs["target_labels"])
+        sc_e.scale(l).backward()
+        sc_e.step(opt_e); sc_e.update(); opt_e.zero_grad()
+    torch.cuda.synchronize(); t_eager = (time.perf_counter() - t0) / 20
+    print("\nhead training iteration: CUDA-graph replay %.2f ms, Python-driven %.2f ms" % (1e3 * t_graph, 1e3 * t_eager))
+    assert t_graph < t_eager
+    step.close()
+    # dropout on: the device counter gives every replay its own masks
+    net_d, opt_d, sc_d = build(True)
+    opt_d.param_groups[0]["lr"] = 0.0                      # frozen weights: only the masks can change the loss
+    step_d = train.GraphedStep(net_d, opt_d, sc_d, inputs, forward=fwd, warmup=2)
+    losses = [float(step_d(inputs)) for _ in range(4)]
+    assert len(set(losses)) == 4, losses
+    assert int(step_d.counter) == 2 + 4
+    step_d.close()
