@@ -355,6 +355,46 @@ def train_step_leg(CNN, make_cfg, sweep, optim, _lib, dev, way, shot, qpc, tower
     return rec
 
 
+def train_step_graph_leg(CNN, make_cfg, sweep, optim, train, dev, way, shot, qpc, tower, n_steps, label):
+    """The same training iteration replayed as ONE CUDA graph (train.GraphedStep: forward, loss, backward, Adam through the
+    GradScaler; dropout seeds from a device counter incremented inside the graph).  tower=True: from the frames, tower + head;
+    tower=False: the head on frame features computed once by the frozen tower (the features are the step's input)."""
+    net = CNN(make_cfg("ViT-B/16", T, False, way), max_episodes=1, device=dev)
+    net.init_random_(seed=0)
+    text = torch.randn(N_TEXT, 512, generator=torch.Generator().manual_seed(0))
+    net.text_features_test, net.text_features_train = text, text
+    net.train_backbone = bool(tower)
+    ep = sweep.synthetic_episode_batch([30001], way, shot, qpc, T, N_TEXT, dev)
+    inp = {k: (v if k.endswith("images") else v[0]) for k, v in ep.items()}
+    fwd = None
+    if not tower:
+        with torch.no_grad():
+            inp["su"] = net.encode_frames(inp.pop("context_images")).view(1, -1, T, 512)
+            inp["qu"] = net.encode_frames(inp.pop("target_images")).view(1, -1, T, 512)
+        fwd = lambda n, x: n.head(x["su"], x["qu"], x["context_labels"], x["real_support_labels"], x["real_target_labels"])  # noqa: E731
+    net.train()
+    opt = optim.Adam(net.trainable_parameters(), lr=1e-6, betas=(0.5, 0.999))
+    step = train.GraphedStep(net, opt, optim.GradScaler(dev), inp, forward=fwd, warmup=3)
+    for _ in range(3):
+        step(inp)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
+    evs[0].record()
+    for i in range(n_steps):
+        loss = step(inp)
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(n_steps)]
+    ms = statistics.median(per_step)
+    rec = {"workload": label, "value": 1e3 / ms, "unit": "episodes/s (training steps/s)", "ms_per_step": ms,
+           "ms_per_step_min_max": [min(per_step), max(per_step)], "steps_timed": n_steps,
+           "trainable_parameters": int(sum(p.numel() for p in net.trainable_parameters())), "last_loss": float(loss),
+           "call": "train.GraphedStep(...)(inputs): one cudaGraphLaunch per training iteration"}
+    step.close()
+    del net, opt, step, ep, inp
+    torch.cuda.empty_cache()
+    return rec
+
+
 def _loss_acc(out, target_labels, tasks_per_batch):
     """run/main_run.py:390-392 + utils/utils.py:174-186,259-264 on the forward's outputs (plain torch, as the caller's
     own _loss_and_acc is; the hot path's fused version is spm_eval)."""
@@ -429,7 +469,7 @@ def main():
 
     import __graft_entry__
     __graft_entry__.build()
-    from clip_spm_b200 import CNN, _lib, optim, sweep
+    from clip_spm_b200 import CNN, _lib, optim, sweep, train
     from clip_spm_b200.config import make_cfg
     # several ranks on one box: keep each rank (and the pinned buffers it allocates) on its GPU's NUMA node
     bound = sweep.bind_to_gpu_cpus(local) if world > 1 else None
@@ -626,6 +666,10 @@ def main():
                 "training iteration at BASELINE config 2 shape (240 frames): frozen ViT-B/16 tower, differentiable CLIP-SPM head")),
             ("train_step_full_config1", lambda: train_step_leg(CNN, make_cfg, sweep, optim, _lib, dev, 5, 1, 1, True, 8,
                 "training iteration at BASELINE config 1 shape (80 frames): ViT-B/16 tower AND head differentiated, Adam over all parameters")),
+            ("train_step_full_config1_graph", lambda: train_step_graph_leg(CNN, make_cfg, sweep, optim, train, dev, 5, 1, 1, True, 8,
+                "training iteration at BASELINE config 1 shape (80 frames), tower + head, replayed as one CUDA graph")),
+            ("train_step_head_config2_graph", lambda: train_step_graph_leg(CNN, make_cfg, sweep, optim, train, dev, 5, 5, 1, False, 12,
+                "training iteration of the CLIP-SPM head on the features of a config 2 episode (25 + 5 videos), one CUDA graph")),
             ("config3", lambda: config_leg(lib, _lib, sweep, CNN, make_cfg, dev, peaks, "ViT-B/16", 5, 1, 1, 16, 24, 8, 6,
                 VIT_GFLOP_PER_FRAME_EXECUTED, "BASELINE config 3: ViT-B/16 SSv2-Full shape 5-way 1-shot, T=16 (160 frames), "
                 "bidirectional OTAM 16x18")),
