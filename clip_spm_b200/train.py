@@ -148,7 +148,9 @@ class TransformerV1:
             self._free.append(h)
 
     def reset(self):
-        self._free = list(self._all)
+        # creation order: the k-th call of a forward always gets the k-th handle, so a handle sees ONE shape and its workspace
+        # stops growing after the first iteration (a regrow synchronises the device -- fatal inside a CUDA-graph capture)
+        self._free = list(reversed(self._all))
 
     def close(self):
         lib = _lib.load()
@@ -470,7 +472,7 @@ def allreduce_gradients(params, group=None, bucket_numel=1 << 24):
 # the training loop from a listing of decoded frames (run/main_run.py:180-243 `Learner.run`, training branch)
 # ------------------------------------------------------------------------------------------------------------------
 def run_listing_training(net, split, load_frame, iterations, way, shot, n_queries, optimizer, scaler, seed=0, flip=True,
-                         lr_milestone=None, rank=0, world_size=1, on_iteration=None):
+                         lr_milestone=None, rank=0, world_size=1, on_iteration=None, graph=False):
     """`Learner.run`'s training branch over `VideoDataset` episodes on this library, from DECODED frames:
     per iteration (numbered from 1 like the reference's `iteration`) one train-mode episode is sampled
     (`frames.sample_episode_plan(train=True)`: class / video / frame-jitter draws AND the draws of the loader's training
@@ -482,6 +484,9 @@ def run_listing_training(net, split, load_frame, iterations, way, shot, n_querie
     `lr_scheduler.MultiStepLR(milestones=[lr_milestone], gamma=0.1).step()` follows every iteration (:99,210).
     world_size > 1: iteration i is computed by rank i % world_size, the gradients are exchanged once per optimiser step
     (`allreduce_gradients`).  `net` must be in train mode; `on_iteration(iteration, loss, acc)` is the logging / validation hook.
+    graph=True (single rank, cfg.TRAIN.WAY set): the first TASKS_PER_BATCH window runs Python-driven (it warms the workspaces),
+    then every iteration is ONE CUDA-graph replay (`GraphedStep`, re-captured when the learning rate changes); the trajectory is
+    the Python-driven one when dropout is off, with dropout the masks come from the graph's device counter.
     Returns [(loss, accuracy)] of the iterations this rank computed (host floats: the reference logs both every iteration)."""
     import random
 
@@ -489,12 +494,24 @@ def run_listing_training(net, split, load_frame, iterations, way, shot, n_querie
     from . import ops
     if not net.training:
         raise RuntimeError("run_listing_training: call net.train() first")
+    if graph and world_size == 1 and torch.cuda.current_stream(net._dev) == torch.cuda.default_stream(net._dev):
+        # the Python-driven iterations that precede the capture must not run on the legacy default stream: autograd binds every
+        # parameter's gradient accumulator to the stream of its first use, and a capture may not depend on the legacy stream
+        side = torch.cuda.Stream(device=net._dev)
+        side.wait_stream(torch.cuda.current_stream(net._dev))
+        with torch.cuda.stream(side):
+            log = run_listing_training(net, split, load_frame, iterations, way, shot, n_queries, optimizer, scaler, seed, flip,
+                                       lr_milestone, rank, world_size, on_iteration, graph)
+        torch.cuda.current_stream(net._dev).wait_stream(side)
+        return log
     T, tpb = net.seq_len, int(net.tasks_per_batch)
     params = net.trainable_parameters()
     base_lr = optimizer.param_groups[0]["lr"]
     dev = net._dev
     log, size = [], None
+    gstep, gstep_lr, graphed = None, None, False
     for iteration in range(1, int(iterations) + 1):
+        graphed = False
         if iteration % world_size == rank:
             rng = random.Random(seed + iteration)
             if size is None:
@@ -510,21 +527,36 @@ def run_listing_training(net, split, load_frame, iterations, way, shot, n_querie
                       "context_labels": torch.tensor(plan["support_labels"], device=dev),
                       "real_support_labels": torch.tensor(plan["real_support_labels"], device=dev),
                       "real_target_labels": torch.tensor(plan["real_target_labels"], device=dev), "target_labels": tl}
-            out = net(inputs)
-            loss = net.loss(out, tl, inputs["real_support_labels"], inputs["real_target_labels"])
-            scaler.scale(loss).backward()
+            do_step = (iteration + 1) % tpb == 0 or iteration == int(iterations)
+            if graph and world_size == 1 and iteration > tpb:
+                lr_now = optimizer.param_groups[0]["lr"]
+                if gstep is None or gstep_lr != lr_now:        # first graphed iteration, or the schedule moved the learning rate
+                    if gstep is not None:
+                        gstep.close()
+                    gstep, gstep_lr = GraphedStep(net, optimizer, scaler, inputs, warmup=0, accumulate_graph=tpb > 1,
+                                                  seed_base=seed + iteration), lr_now
+                loss = gstep(inputs, optimizer_step=do_step)
+                out = gstep.last_out
+                graphed = True
+            else:
+                out = net(inputs)
+                loss = net.loss(out, tl, inputs["real_support_labels"], inputs["real_target_labels"])
+                scaler.scale(loss).backward()
+                graphed = False
             acc = (out["logits"][0].argmax(-1) == tl).float().mean()
             log.append((float(loss.detach()), float(acc)))          # run/main_run.py:199-201 keeps both as host numbers
             if on_iteration is not None:
                 on_iteration(iteration, log[-1][0], log[-1][1])
-        if (iteration + 1) % tpb == 0 or iteration == int(iterations):
+        if ((iteration + 1) % tpb == 0 or iteration == int(iterations)) and not (graphed and iteration % world_size == rank):
             if world_size > 1:
                 allreduce_gradients(params)
             scaler.step(optimizer)
             scaler.update()
-            optimizer.zero_grad()
+            optimizer.zero_grad(set_to_none=not graph)     # graph mode keeps the gradient tensors (stable addresses)
         if lr_milestone is not None:                                 # MultiStepLR, stepped once per iteration
             optimizer.param_groups[0]["lr"] = base_lr * (0.1 if iteration >= int(lr_milestone) else 1.0)
+    if gstep is not None:
+        gstep.close()
     return log
 
 
@@ -542,7 +574,10 @@ class GraphedStep:
     output dict (default `net(inputs)`); the learning rate is baked in at capture (re-create the object after a schedule step).
     Call it with the next episode's tensors; returns the (device) loss of that iteration."""
 
-    def __init__(self, net, optimizer, scaler, inputs, forward=None, warmup=3):
+    def __init__(self, net, optimizer, scaler, inputs, forward=None, warmup=3, accumulate_graph=False, seed_base=0x5eed):
+        """warmup: eager iterations run before the capture (REAL training steps on `inputs`: they grow the workspaces and fill the
+        optimiser's pointer table); 0 when the model has already trained on this shape.  accumulate_graph: also capture the
+        iteration WITHOUT the optimiser step (gradient accumulation over TASKS_PER_BATCH tasks): `step(x, optimizer_step=False)`."""
         if not net.training:
             raise RuntimeError("GraphedStep: call net.train() first")
         if net.way is None:
@@ -556,39 +591,63 @@ class GraphedStep:
         self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
         _lib.check(_lib.load().spm_dropout_seed_source(_ptr(self.counter)))
         self._dropout = getattr(net, "train_dropout", True)
-        net._graph_seed = 0x5eed if self._dropout else None      # a constant base seed; the device counter moves it
+        net._graph_seed = int(seed_base) if self._dropout else None      # a constant base seed; the device counter moves it
         self.params = net.trainable_parameters()
         for p in self.params:
-            p.grad = torch.zeros_like(p)
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(max(1, int(warmup))):
-                self._step()
-        cur.wait_stream(side)
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        if int(warmup) > 0:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(int(warmup)):
+                    self._step(True)
+            cur.wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._step()
+        import gc
+        gc.collect()
+        gc_was = gc.isenabled()
+        gc.disable()     # a collected model would free its block handles (cudaFree) in the middle of the capture
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss, self.out = self._step(True)
+            self.graph_acc = None
+            if accumulate_graph:
+                self.graph_acc = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_acc):
+                    self.loss_acc, self.out_acc = self._step(False)
+        finally:
+            if gc_was:
+                gc.enable()
+        self.last_out = self.out
 
-    def _step(self):
+    def _step(self, optimizer_step):
         self.counter += 1
-        torch._foreach_zero_([p.grad for p in self.params])
         out = self.forward(self.net, self.static)
         loss = self.net.loss(out, self.static["target_labels"], self.static.get("real_support_labels"),
                              self.static.get("real_target_labels"))
-        self.scaler.scale(loss).backward()
-        self.scaler.step(self.opt)
-        self.scaler.update()
-        return loss.detach()
+        self.scaler.scale(loss).backward()        # accumulates into the kept .grad tensors
+        if optimizer_step:                        # run/main_run.py:207-209
+            self.scaler.step(self.opt)
+            self.scaler.update()
+            torch._foreach_zero_([p.grad for p in self.params])
+        return loss.detach(), {k: v.detach() for k, v in out.items() if torch.is_tensor(v)}
 
-    def __call__(self, inputs):
+    def __call__(self, inputs, optimizer_step=True):
         for k, v in inputs.items():
             if torch.is_tensor(v) and k in self.static:
                 self.static[k].copy_(v, non_blocking=True)
-        self.graph.replay()
-        return self.loss
+        if optimizer_step:
+            self.graph.replay()
+            self.last_out = self.out
+            return self.loss
+        if self.graph_acc is None:
+            raise RuntimeError("GraphedStep: created without accumulate_graph")
+        self.graph_acc.replay()
+        self.last_out = self.out_acc
+        return self.loss_acc
 
     def close(self):
         """detach the device seed counter (dropout seeds are host arguments again)"""

@@ -425,3 +425,34 @@ def test_graphed_training_step_equals_eager_steps():
     assert len(set(losses)) == 4, losses
     assert int(step_d.counter) == 2 + 4
     step_d.close()
+
+
+def test_training_loop_with_cuda_graphs_walks_the_same_trajectory():
+    """run_listing_training(graph=True): the first TASKS_PER_BATCH window Python-driven, then one CUDA-graph replay per iteration
+    (accumulate-only and accumulate-and-step graphs, re-captured when MultiStepLR moves the learning rate) -- same losses, same
+    weights as the Python-driven loop (dropout off)"""
+    import numpy as np
+    from clip_spm_b200 import CNN, optim, train
+    from clip_spm_b200 import frames as Fr
+    sp = Fr.Split()
+    for vid in range(3):
+        for cls in range(3):
+            sp.add_vid([(cls, vid, f) for f in range(6 + vid)], cls)
+    load = lambda h: np.random.RandomState(h[0] * 10007 + h[1] * 101 + h[2]).randint(0, 256, size=(256, 288, 3)).astype(np.uint8)  # noqa: E731
+    text = O.make_text_features(24, 512, seed=1)
+
+    def run(graph):
+        net = CNN(make_cfg("ViT-B/16", 2, False, 2), text_features_test=text, text_features_train=text)
+        net.tasks_per_batch = 2.0
+        net.load_state_dict(O.make_weights("ViT-B/16", seed=0, protocol="P1"), strict=False)
+        net.train_backbone, net.train_dropout = True, False
+        net.train()
+        opt = optim.Adam(net.trainable_parameters(), lr=1e-5, betas=(0.5, 0.999))
+        log = train.run_listing_training(net, sp, load, 7, 2, 1, 1, opt, optim.GradScaler("cuda", init_scale=64.0), seed=7,
+                                         lr_milestone=5, graph=graph)
+        return log, {n: p.detach().clone() for n, p in net.named_parameters()}
+    log_e, w_e = run(False)
+    log_g, w_g = run(True)
+    assert len(log_g) == 7 and log_g == log_e, (log_e, log_g)
+    for n in w_e:
+        assert torch.equal(w_e[n], w_g[n]), n
