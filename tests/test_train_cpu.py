@@ -206,3 +206,96 @@ def test_training_ops_fail_loudly_without_gpu():
         with pytest.raises(RuntimeError):
             net.head(torch.zeros(1, 2, 2, 512), torch.zeros(1, 2, 2, 512), torch.tensor([0., 1.]), torch.tensor([0., 1.]),
                      torch.tensor([0., 1.]))
+
+
+def test_training_loop_schedule_on_cpu_stand_ins(monkeypatch):
+    """host logic of train.run_listing_training with stand-ins for the CUDA pieces: which iterations step the optimiser
+    ((iteration + 1) % TASKS_PER_BATCH == 0 or the last one, run/main_run.py:203-209), MultiStepLR per iteration (:99,210), the
+    episodes are the seeded train-mode plans (same for every rank split), frames go through the training transform with the
+    plan's draws, and a 2-rank split computes disjoint iterations that together cover all of them"""
+    import random
+    from clip_spm_b200 import frames as Fr
+    from clip_spm_b200 import ops, train
+    sp = Fr.Split()
+    for vid in range(3):
+        for cls in range(3):
+            sp.add_vid([(cls, vid, f) for f in range(6 + vid)], cls)
+    H_, W_ = 256, 288
+    load = lambda h: standin_frame_small(h, H_, W_)    # noqa: E731
+    seen_aug = []
+
+    def fake_transform(frames, aug):
+        seen_aug.append([tuple(a) for a in aug])
+        return torch.zeros(frames.shape[0], 3, 224, 224)
+    monkeypatch.setattr(ops, "transform_frames_train", fake_transform)
+    monkeypatch.setattr(ops, "frame_geometry", lambda h, w: P_geometry(h, w))
+    monkeypatch.setattr(Fr, "frame_geometry", lambda h, w: P_geometry(h, w))
+
+    class FakeNet:
+        training, seq_len, tasks_per_batch, _dev = True, 2, 3.0, "cpu"
+
+        def __init__(self):
+            self.p = torch.nn.Parameter(torch.zeros(2))
+            self.calls = 0
+
+        def trainable_parameters(self):
+            return [self.p]
+
+        def __call__(self, inputs):
+            self.calls += 1
+            q = inputs["target_labels"].numel()
+            return {"logits": (self.p.view(1, 1, 2) + torch.zeros(1, q, 2))}
+
+        def loss(self, out, tl, rs, rt):
+            return out["logits"].sum() * 0.0 + self.p.sum()
+
+    class FakeOpt:
+        def __init__(self):
+            self.param_groups, self.steps, self.lrs = [{"lr": 1.0}], [], []
+
+        def zero_grad(self, set_to_none=True):
+            pass
+
+    class FakeScaler:
+        def __init__(self, opt, it):
+            self.opt, self.it = opt, it
+
+        def scale(self, loss):
+            return loss
+
+        def step(self, opt):
+            opt.steps.append(self.it[0])
+            opt.lrs.append(opt.param_groups[0]["lr"])
+
+        def update(self):
+            pass
+
+    def run(rank, world):
+        net, opt, it = FakeNet(), FakeOpt(), [0]
+        log = train.run_listing_training(net, sp, load, 8, 2, 1, 1, opt, FakeScaler(opt, it), seed=5, lr_milestone=6, rank=rank,
+                                         world_size=world, on_iteration=lambda i, l, a: it.__setitem__(0, i))
+        return net, opt, log
+    monkeypatch.setattr(train, "allreduce_gradients", lambda params, group=None: None)
+    net, opt, log = run(0, 1)
+    assert net.calls == 8 and len(log) == 8
+    # optimiser steps: iterations where (i + 1) % 3 == 0 -> 2, 5, 8 (8 is also the last one)
+    assert opt.steps == [2, 5, 8]
+    assert opt.lrs == [1.0, 1.0, 0.1]                      # MultiStepLR(milestones=[6]) fires after iteration 6
+    # the draws handed to the transform are the plan's, one row per frame, support clips then target clips
+    plan = Fr.sample_episode_plan(sp, 2, 1, 1, 2, train=True, rng=random.Random(5 + 1), frame_size=(H_, W_), flip=True)
+    want = [tuple([a[0], a[1], int(a[2])]) for _, fr, a in plan["support"] for _f in fr]
+    assert seen_aug[0] == want
+    # two ranks: disjoint iterations (i % 2 == rank), every optimiser step on both
+    n0, o0, l0 = run(0, 2)
+    n1, o1, l1 = run(1, 2)
+    assert n0.calls + n1.calls == 8 and len(l0) == 4 and len(l1) == 4
+
+
+def standin_frame_small(triple, H, W):
+    cls, vid, f = triple
+    return np.full((H, W, 3), (cls * 31 + vid * 7 + f) % 256, np.uint8)
+
+
+def P_geometry(h, w):
+    from oracle import preprocess_oracle as P
+    return P.geometry(h, w)
