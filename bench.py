@@ -666,15 +666,16 @@ def main():
                 "training iteration at BASELINE config 2 shape (240 frames): frozen ViT-B/16 tower, differentiable CLIP-SPM head")),
             ("train_step_full_config1", lambda: train_step_leg(CNN, make_cfg, sweep, optim, _lib, dev, 5, 1, 1, True, 8,
                 "training iteration at BASELINE config 1 shape (80 frames): ViT-B/16 tower AND head differentiated, Adam over all parameters")),
-            ("train_step_full_config1_graph", lambda: train_step_graph_leg(CNN, make_cfg, sweep, optim, train, dev, 5, 1, 1, True, 8,
-                "training iteration at BASELINE config 1 shape (80 frames), tower + head, replayed as one CUDA graph")),
-            ("train_step_head_config2_graph", lambda: train_step_graph_leg(CNN, make_cfg, sweep, optim, train, dev, 5, 5, 1, False, 12,
-                "training iteration of the CLIP-SPM head on the features of a config 2 episode (25 + 5 videos), one CUDA graph")),
             ("config3", lambda: config_leg(lib, _lib, sweep, CNN, make_cfg, dev, peaks, "ViT-B/16", 5, 1, 1, 16, 24, 8, 6,
                 VIT_GFLOP_PER_FRAME_EXECUTED, "BASELINE config 3: ViT-B/16 SSv2-Full shape 5-way 1-shot, T=16 (160 frames), "
                 "bidirectional OTAM 16x18")),
             ("config4", lambda: config_leg(lib, _lib, sweep, CNN, make_cfg, dev, peaks, "RN50", 5, 3, 1, 8, 10, 8, 6,
-                RN50_GFLOP_PER_FRAME, "BASELINE config 4: RN50 HMDB51 shape 5-way 3-shot (160 frames), D=1024"))):
+                RN50_GFLOP_PER_FRAME, "BASELINE config 4: RN50 HMDB51 shape 5-way 3-shot (160 frames), D=1024")),
+            # the CUDA-graph legs come last: a capture that fails must not be able to disturb the legs above
+            ("train_step_full_config1_graph", lambda: train_step_graph_leg(CNN, make_cfg, sweep, optim, train, dev, 5, 1, 1, True, 8,
+                "training iteration at BASELINE config 1 shape (80 frames), tower + head, replayed as one CUDA graph")),
+            ("train_step_head_config2_graph", lambda: train_step_graph_leg(CNN, make_cfg, sweep, optim, train, dev, 5, 5, 1, False, 12,
+                "training iteration of the CLIP-SPM head on the features of a config 2 episode (25 + 5 videos), one CUDA graph"))):
             try:
                 legs[key] = fn()
             except Exception as ex:
