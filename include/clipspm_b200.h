@@ -22,8 +22,11 @@
  *   spm_set_text_features_train / spm_class_logits   models/model_clipfsar.py:127,329-331 (sibling head CLIP-FSAR)
  *   spm_softdtw_forward/backward  models/OTAM.py:34-203 (TA2N's numba.cuda soft-DTW kernels, _SoftDTWCUDA)
  *   spm_jpeg_info / spm_jpeg_decode   video_reader.py:227-230 read_single_image (PIL JPEG decode of every frame)
- *   spm_adam_* / spm_scaler_update    run/main_run.py:84-88,76,207-209 (torch.optim.Adam + GradScaler of the training loop)
+ *   spm_adam_* / spm_sgd_step / spm_scaler_update    run/main_run.py:84-96,76,207-209 (torch.optim.Adam / SGD + GradScaler)
  *   spm_tv1_* / spm_linear_backward   autograd through models/myRes.py:1053-1075 Transformer_v1 and the head's nn.Linear layers
+ *   spm_vitblock_* / spm_layernorm_*  autograd through models/clip_fsar.py:622-643,664,668 (the ViT-B/16 tower's blocks, ln_pre / ln_post)
+ *   spm_dropout / spm_tv1_set_dropout / spm_dropout_seed_source   nn.Dropout of models/myRes.py:961-996 in train mode
+ *   spm_transform_frames / spm_transform_frames_train   video_reader.py:83-111 (the loader's test / training transform)
  *   spm_gemm                      ATen linear / conv-as-GEMM calls (cuBLASLt) under all of the above
  */
 #ifndef CLIPSPM_B200_H
