@@ -557,6 +557,8 @@ class CNN(nn.Module):
         logits, dists = torch.empty(E, Q, W), torch.empty(E)
         loss, acc, pred = torch.empty(E), torch.empty(E), torch.empty(E, Q, dtype=torch.int32)
         with torch.cuda.device(self._dev):
+            # the host call runs on the handle's own streams: earlier device-tensor calls of this handle (caller's stream) must be done
+            torch.cuda.current_stream(self._dev).synchronize()
             _lib.check(lib.spm_eval_host(h, E, S, Q, W, _p(context_images), _p(target_images), _p(context_labels),
                                          _p(real_support_labels), _p(real_target_labels), _p(target_labels),
                                          self.tasks_per_batch, _p(logits), _p(dists), _p(loss), _p(acc), _p(pred)))
@@ -584,6 +586,7 @@ class CNN(nn.Module):
         logits, dists = torch.empty(E, Q, W), torch.empty(E)
         loss, acc, pred = torch.empty(E), torch.empty(E), torch.empty(E, Q, dtype=torch.int32)
         with torch.cuda.device(self._dev):
+            torch.cuda.current_stream(self._dev).synchronize()      # see evaluate_host
             _lib.check(lib.spm_eval_host_u8(h, E, S, Q, W, H, Wd, _p(context_frames), _p(target_frames),
                                             _p(context_labels), _p(real_support_labels), _p(real_target_labels),
                                             _p(target_labels), self.tasks_per_batch, _p(logits), _p(dists), _p(loss),

@@ -5,7 +5,9 @@
  * status (0 = ok) and records a message readable with spm_last_error().  All tensor arguments are
  * DEVICE pointers unless the name says `host`; the caller owns every buffer; the library owns only
  * the opaque handle (packed weights + workspace).  `stream` is a cudaStream_t passed as void*.
- * A handle is not thread-safe: one handle per (process, device).
+ * A handle is not thread-safe: one handle per (process, device).  The *_host entry points run on the handle's own streams and
+ * share its workspaces with the stream-taking ones: synchronise the caller's stream before switching from a device-pointer
+ * call to a host call on the same handle (the Python mirror does).
  *
  * Reference interfaces replaced (paths relative to the reference repo root):
  *   spm_create / spm_destroy      models/model_clipspm.py:15-101   CNN.__init__ (module construction)
